@@ -1,0 +1,596 @@
+// C-ABI of the B200-native Defense-GAN projection loop (see include/defensegan_b200.h).
+// Host side: generator plan (pixel-graph tables), weight re-layout, workspace carving and the
+// on-device L-step driver.  Everything is enqueued on the caller's stream; nothing here
+// synchronises the host.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+namespace dgan {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+// ---------------------------------------------------------------------------------------
+// geometry tables
+// ---------------------------------------------------------------------------------------
+PairTable deconv_fwd_pairs(int h_in, int w_in, int h_used, int w_used) {
+  PairTable t;
+  t.off.push_back(0);
+  for (int i = 0; i < h_used; ++i)
+    for (int j = 0; j < w_used; ++j) {
+      for (int ka = 0; ka < 5; ++ka) {
+        const int oo = i + 1 - ka;
+        if (oo < 0 || (oo & 1) || (oo >> 1) >= h_in) continue;
+        for (int kb = 0; kb < 5; ++kb) {
+          const int pp = j + 1 - kb;
+          if (pp < 0 || (pp & 1) || (pp >> 1) >= w_in) continue;
+          t.pairs.push_back(make_int2((oo >> 1) * w_in + (pp >> 1), ka * 5 + kb));
+        }
+      }
+      t.off.push_back((int)t.pairs.size());
+    }
+  return t;
+}
+
+PairTable deconv_bwd_pairs(int h_in, int w_in, int h_used, int w_used) {
+  PairTable t;
+  t.off.push_back(0);
+  for (int o = 0; o < h_in; ++o)
+    for (int p = 0; p < w_in; ++p) {
+      for (int ka = 0; ka < 5; ++ka) {
+        const int i = 2 * o + ka - 1;
+        if (i < 0 || i >= h_used) continue;
+        for (int kb = 0; kb < 5; ++kb) {
+          const int j = 2 * p + kb - 1;
+          if (j < 0 || j >= w_used) continue;
+          t.pairs.push_back(make_int2(i * w_used + j, ka * 5 + kb));
+        }
+      }
+      t.off.push_back((int)t.pairs.size());
+    }
+  return t;
+}
+
+PairTable linear_fwd_pairs(int n_pix) {
+  PairTable t;
+  t.off.push_back(0);
+  for (int q = 0; q < n_pix; ++q) {
+    t.pairs.push_back(make_int2(0, q));
+    t.off.push_back((int)t.pairs.size());
+  }
+  return t;
+}
+
+PairTable linear_bwd_pairs(int n_pix) {
+  PairTable t;
+  t.off.push_back(0);
+  for (int q = 0; q < n_pix; ++q) t.pairs.push_back(make_int2(q, q));
+  t.off.push_back((int)t.pairs.size());
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct DevTable {
+  int* off = nullptr;
+  int2* pairs = nullptr;
+  int n_out = 0;
+  int n_pairs = 0;
+};
+
+struct GemmLayer {
+  // forward: [P_in][N][C_in] -> [P_out][N][C_out]
+  int P_in, C_in, P_out, C_out;
+  int h_in, w_in, h_used, w_used;  // spatial geometry (Linear: 1x1 -> 4x4)
+  bool relu;                       // ReLU after bias (false: CelebA Generator.5)
+  DevTable fwd, bwd;
+  PairTable fwd_host, bwd_host;
+  // fp32 weight tiles.  forward tile t: rows = C_in (K), cols = C_out; backward: rows = C_out, cols = C_in
+  const float* wf = nullptr; int wf_tile_stride = 0, wf_ld = 0;
+  const float* wb = nullptr; int wb_tile_stride = 0, wb_ld = 0;
+  const float* bias = nullptr;
+  int bias_pstride = 0;            // Linear: bias is per flat feature f = pixel*C_out + c
+  // fp16 K-major tiles for the tensor-core path (kernels_tc.cuh): [tile][N rows][K cols]
+  TcWeights tc_f, tc_b;
+};
+
+struct FinalLayer {
+  int h_in, w_in, C_in, C_out, act;
+  const float* w = nullptr;  // [25][C_out][C_in] == the TF filter layout
+  const float* bias = nullptr;
+  int n_bands = 0;
+  size_t fwd_smem = 0, bwd_smem = 0;
+};
+
+}  // namespace dgan
+
+using namespace dgan;
+
+struct dgan_ctx {
+  dgan_desc desc;
+  int H = 0, W = 0, C = 0, hwc = 0;
+  std::vector<GemmLayer> layers;
+  FinalLayer fin;
+  std::vector<void*> allocs;
+  int64_t macs_per_row = 0;
+  int64_t last_launches = 0;
+  int64_t launches = 0;
+  TcState tc;
+};
+
+namespace dgan {
+
+static int dev_alloc(dgan_ctx* c, void** p, size_t bytes) {
+  DGAN_CUDA_CHECK(cudaMalloc(p, bytes));
+  c->allocs.push_back(*p);
+  return 0;
+}
+
+static int upload_table(dgan_ctx* c, const PairTable& t, DevTable* d, cudaStream_t s) {
+  d->n_out = (int)t.off.size() - 1;
+  d->n_pairs = (int)t.pairs.size();
+  int rc;
+  if ((rc = dev_alloc(c, (void**)&d->off, t.off.size() * sizeof(int)))) return rc;
+  if ((rc = dev_alloc(c, (void**)&d->pairs, t.pairs.size() * sizeof(int2)))) return rc;
+  // pageable-source async copies are staged by the runtime before returning
+  DGAN_CUDA_CHECK(cudaMemcpyAsync(d->off, t.off.data(), t.off.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  DGAN_CUDA_CHECK(cudaMemcpyAsync(d->pairs, t.pairs.data(), t.pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+// out[t][c][r] = in[t][r][c]   (per-tile transpose; rows x cols -> cols x rows)
+__global__ void transpose_tiles_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                       size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t per = (size_t)rows * cols;
+  const size_t t = i / per, rem = i % per;
+  const int r = (int)(rem / cols), cc = (int)(rem % cols);
+  out[t * per + (size_t)cc * rows + r] = in[i];
+}
+
+__global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, float s, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * s;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------
+struct Workspace {
+  int n_rows = 0, n_pad = 0;
+  float *z = nullptr, *v = nullptr, *g = nullptr;
+  std::vector<float*> act, dact;     // fp32 path: per hidden layer output [P][n_pad][C]
+  std::vector<__half*> act_h, dact_h;  // fp16 path
+  __half* z_h = nullptr;
+  float *y = nullptr, *dpre = nullptr, *loss_part = nullptr, *loss = nullptr;
+  size_t bytes = 0;
+};
+
+static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
+  Workspace w;
+  w.n_rows = n_rows;
+  w.n_pad = (int)align_up((size_t)std::max(n_rows, 1), kRowTile);
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) -> void* {
+    void* p = b ? (void*)(b + off) : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  const size_t np = (size_t)w.n_pad;
+  const int latent = c->desc.latent_dim;
+  w.z = (float*)take(np * latent * 4);
+  w.v = (float*)take(np * latent * 4);
+  w.g = (float*)take(np * latent * 4);
+  const bool tc = c->desc.precision == DGAN_PREC_FP16;
+  if (tc) w.z_h = (__half*)take(np * latent * 2);
+  for (const GemmLayer& l : c->layers) {
+    const size_t elems = (size_t)l.P_out * np * l.C_out;
+    if (tc) {
+      w.act_h.push_back((__half*)take(elems * 2));
+      w.dact_h.push_back((__half*)take(elems * 2));
+    } else {
+      w.act.push_back((float*)take(elems * 4));
+      w.dact.push_back((float*)take(elems * 4));
+    }
+  }
+  w.y = (float*)take(np * c->hwc * 4);
+  w.dpre = (float*)take(np * c->hwc * 4);
+  w.loss_part = (float*)take(np * c->fin.n_bands * 4);
+  w.loss = (float*)take(np * 4);
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------
+#define DGAN_LAUNCH_CHECK(c)                                                     \
+  do {                                                                           \
+    (c)->launches++;                                                             \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) {                                                     \
+      set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));        \
+      return DGAN_ERR_CUDA;                                                      \
+    }                                                                            \
+  } while (0)
+
+static int launch_bsgemm_f32(dgan_ctx* c, int epi, const float* in, int C_in, int n_pad, const float* wt,
+                             int tile_stride, int ldw, const DevTable& tab, float* out, int C_out,
+                             const float* bias, int bias_pstride, const float* mask_src, cudaStream_t s) {
+  dim3 grid(n_pad / kRowTile, tab.n_out, C_out / 64), block(256);
+  switch (epi) {
+    case EPI_BIAS_RELU:
+      bsgemm_f32_kernel<EPI_BIAS_RELU><<<grid, block, 0, s>>>(in, C_in, n_pad, wt, tile_stride, ldw, tab.off,
+                                                              tab.pairs, out, C_out, bias, bias_pstride, mask_src);
+      break;
+    case EPI_BIAS:
+      bsgemm_f32_kernel<EPI_BIAS><<<grid, block, 0, s>>>(in, C_in, n_pad, wt, tile_stride, ldw, tab.off, tab.pairs,
+                                                         out, C_out, bias, bias_pstride, mask_src);
+      break;
+    case EPI_MASK:
+      bsgemm_f32_kernel<EPI_MASK><<<grid, block, 0, s>>>(in, C_in, n_pad, wt, tile_stride, ldw, tab.off, tab.pairs,
+                                                         out, C_out, bias, bias_pstride, mask_src);
+      break;
+    default:
+      bsgemm_f32_kernel<EPI_NONE><<<grid, block, 0, s>>>(in, C_in, n_pad, wt, tile_stride, ldw, tab.off, tab.pairs,
+                                                         out, C_out, bias, bias_pstride, mask_src);
+      break;
+  }
+  DGAN_LAUNCH_CHECK(c);
+  return 0;
+}
+
+template <typename TIN>
+static int launch_final_fwd(dgan_ctx* c, const TIN* hin, const Workspace& w, const float* x, int R, int B,
+                            bool want_grad, cudaStream_t s) {
+  const FinalLayer& f = c->fin;
+  dim3 grid(f.n_bands, w.n_rows), block(128);
+  const size_t smem = f.fwd_smem;
+  float* dpre = want_grad ? w.dpre : nullptr;
+  float* lp = x ? w.loss_part : nullptr;
+#define FF(CO, ACT)                                                                                         \
+  final_fwd_loss_kernel<TIN, CO, ACT><<<grid, block, smem, s>>>(hin, w.n_pad, f.h_in, f.w_in, f.C_in, f.w, \
+                                                                f.bias, x, R, B, w.y, dpre ? dpre : w.dpre, lp)
+  if (f.C_out == 1 && f.act == ACT_SIGMOID) FF(1, ACT_SIGMOID);
+  else if (f.C_out == 3 && f.act == ACT_TANH) FF(3, ACT_TANH);
+  else { set_error("unsupported final layer"); return DGAN_ERR_UNSUPPORTED; }
+#undef FF
+  DGAN_LAUNCH_CHECK(c);
+  return 0;
+}
+
+template <typename TOUT>
+static int launch_final_bwd(dgan_ctx* c, const Workspace& w, const TOUT* mask_src, float gscale, TOUT* din,
+                            cudaStream_t s) {
+  const FinalLayer& f = c->fin;
+  const size_t work = (size_t)f.h_in * f.w_in * w.n_pad * (f.C_in / 4);
+  dim3 grid((unsigned)((work + 255) / 256)), block(256);
+  if (f.C_out == 1)
+    final_bwd_kernel<TOUT, 1><<<grid, block, f.bwd_smem, s>>>(w.dpre, w.n_pad, f.h_in, f.w_in, f.C_in, f.w, mask_src,
+                                                              gscale, din);
+  else
+    final_bwd_kernel<TOUT, 3><<<grid, block, f.bwd_smem, s>>>(w.dpre, w.n_pad, f.h_in, f.w_in, f.C_in, f.w, mask_src,
+                                                              gscale, din);
+  DGAN_LAUNCH_CHECK(c);
+  return 0;
+}
+
+// ---- one generator forward (+ loss and dL/dpre when x != null) ---------------------------
+static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, int B, bool want_grad,
+                       cudaStream_t s) {
+  int rc;
+  const int nl = (int)c->layers.size();
+  if (c->desc.precision == DGAN_PREC_FP16) {
+    const __half* in = w.z_h;
+    for (int l = 0; l < nl; ++l) {
+      const GemmLayer& L = c->layers[l];
+      if ((rc = tc_launch(c->tc, &c->launches, L.tc_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS,
+                          L.bias, nullptr, 1.f, s)))
+        return rc;
+      in = w.act_h[l];
+    }
+    return launch_final_fwd<__half>(c, in, w, x, R, B, want_grad, s);
+  }
+  const float* in = w.z;
+  for (int l = 0; l < nl; ++l) {
+    const GemmLayer& L = c->layers[l];
+    if ((rc = launch_bsgemm_f32(c, L.relu ? EPI_BIAS_RELU : EPI_BIAS, in, L.C_in, w.n_pad, L.wf, L.wf_tile_stride,
+                                L.wf_ld, L.fwd, w.act[l], L.C_out, L.bias, L.bias_pstride, nullptr, s)))
+      return rc;
+    in = w.act[l];
+  }
+  return launch_final_fwd<float>(c, in, w, x, R, B, want_grad, s);
+}
+
+// ---- backward-to-z: w.g = J^T dpre (unscaled by 2/HWC; fp16 path additionally x gscale) -----
+static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s) {
+  int rc;
+  const int nl = (int)c->layers.size();
+  if (c->desc.precision == DGAN_PREC_FP16) {
+    const GemmLayer& last = c->layers[nl - 1];
+    if ((rc = launch_final_bwd<__half>(c, w, last.relu ? w.act_h[nl - 1] : nullptr, c->tc.grad_scale,
+                                       w.dact_h[nl - 1], s)))
+      return rc;
+    for (int l = nl - 1; l >= 1; --l) {
+      const GemmLayer& L = c->layers[l];
+      const bool mask = c->layers[l - 1].relu;
+      if ((rc = tc_launch(c->tc, &c->launches, L.tc_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad,
+                          mask ? EPI_MASK : EPI_NONE, nullptr, mask ? w.act_h[l - 1] : nullptr, 1.f, s)))
+        return rc;
+    }
+    const GemmLayer& L0 = c->layers[0];
+    return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
+  }
+  const GemmLayer& last = c->layers[nl - 1];
+  if ((rc = launch_final_bwd<float>(c, w, last.relu ? w.act[nl - 1] : nullptr, 1.f, w.dact[nl - 1], s))) return rc;
+  for (int l = nl - 1; l >= 1; --l) {
+    const GemmLayer& L = c->layers[l];
+    const bool mask = c->layers[l - 1].relu;
+    if ((rc = launch_bsgemm_f32(c, mask ? EPI_MASK : EPI_NONE, w.dact[l], L.C_out, w.n_pad, L.wb, L.wb_tile_stride,
+                                L.wb_ld, L.bwd, w.dact[l - 1], L.C_in, nullptr, 0, mask ? w.act[l - 1] : nullptr, s)))
+      return rc;
+  }
+  const GemmLayer& L0 = c->layers[0];
+  return launch_bsgemm_f32(c, EPI_NONE, w.dact[0], L0.C_out, w.n_pad, L0.wb, L0.wb_tile_stride, L0.wb_ld, L0.bwd, w.g,
+                           L0.C_in, nullptr, 0, nullptr, s);
+}
+
+static int run_init_z(dgan_ctx* c, const Workspace& w, const float* z0, uint64_t seed, cudaStream_t s) {
+  const int latent = c->desc.latent_dim;
+  const size_t total4 = (size_t)w.n_pad * latent / 4;
+  init_z_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(w.z, w.v, w.z_h, z0, w.n_rows, w.n_pad, latent, seed,
+                                                                 sqrtf(1.0f / (float)latent));
+  DGAN_LAUNCH_CHECK(c);
+  return 0;
+}
+
+static int check_ws(const dgan_ctx* c, int n_rows, void* ws, size_t ws_bytes, Workspace* out) {
+  if (ws == nullptr) { set_error("workspace is NULL"); return DGAN_ERR_WORKSPACE; }
+  if (((uintptr_t)ws & 1023) != 0) { set_error("workspace must be 1024-byte aligned"); return DGAN_ERR_WORKSPACE; }
+  *out = carve(c, n_rows, ws);
+  if (out->bytes > ws_bytes) {
+    set_error("workspace too small: need " + std::to_string(out->bytes) + " bytes, got " + std::to_string(ws_bytes));
+    return DGAN_ERR_WORKSPACE;
+  }
+  return 0;
+}
+
+static float grad_multiplier(const dgan_ctx* c) {
+  float m = 2.0f / (float)c->hwc;  // d/dy mean_{HWC}(y-x)^2
+  if (c->desc.precision == DGAN_PREC_FP16) m /= c->tc.grad_scale;
+  return m;
+}
+
+}  // namespace dgan
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int dgan_abi_version(void) { return DGAN_ABI_VERSION; }
+const char* dgan_last_error(void) { return g_last_error.c_str(); }
+
+int dgan_num_weights(const dgan_desc* d) {
+  if (d == nullptr) return DGAN_ERR_INVALID_ARG;
+  const int n_deconv = d->arch == DGAN_ARCH_CELEBA ? 4 : 3;
+  return 2 + 2 * n_deconv + (d->use_bn ? 6 : 0);
+}
+
+int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weights, int n_weights, void* stream) {
+  if (out == nullptr || d == nullptr || weights == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
+  *out = nullptr;
+  if (d->abi_version != DGAN_ABI_VERSION) { set_error("ABI version mismatch"); return DGAN_ERR_INVALID_ARG; }
+  if (d->arch != DGAN_ARCH_MNIST && d->arch != DGAN_ARCH_CELEBA) { set_error("unknown arch"); return DGAN_ERR_INVALID_ARG; }
+  if (d->precision != DGAN_PREC_FP32 && d->precision != DGAN_PREC_FP16) { set_error("unknown precision"); return DGAN_ERR_INVALID_ARG; }
+  if (d->use_bn) {
+    set_error("use_bn=True (batch-statistics BatchNorm, tflib/ops/batchnorm.py:80-93) is not built yet");
+    return DGAN_ERR_UNSUPPORTED;
+  }
+  if (d->net_dim <= 0 || d->net_dim % 64 != 0) { set_error("net_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
+  if (d->latent_dim <= 0 || d->latent_dim % 64 != 0) { set_error("latent_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
+  if (n_weights != dgan_num_weights(d)) { set_error("wrong number of weight tensors"); return DGAN_ERR_INVALID_ARG; }
+  for (int i = 0; i < n_weights; ++i)
+    if (weights[i] == nullptr) { set_error("NULL weight pointer"); return DGAN_ERR_INVALID_ARG; }
+  int dev_major = 0, dev = 0;
+  DGAN_CUDA_CHECK(cudaGetDevice(&dev));
+  DGAN_CUDA_CHECK(cudaDeviceGetAttribute(&dev_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (dev_major != 10) { set_error("defensegan_b200 requires an sm_100 (B200) device"); return DGAN_ERR_UNSUPPORTED; }
+
+  cudaStream_t s = (cudaStream_t)stream;
+  std::unique_ptr<dgan_ctx> c(new (std::nothrow) dgan_ctx());
+  if (!c) { set_error("out of host memory"); return DGAN_ERR_INVALID_ARG; }
+  c->desc = *d;
+  const bool celeba = d->arch == DGAN_ARCH_CELEBA;
+  const int nd = d->net_dim, latent = d->latent_dim;
+  c->H = celeba ? 64 : 28; c->W = c->H; c->C = celeba ? 3 : 1;
+  c->hwc = c->H * c->W * c->C;
+  int rc = 0;
+  auto fail = [&](int code) { dgan_destroy(c.release()); return code; };
+
+  // ---- Linear (Generator.Input): [1][N][latent] -> [16][N][4*nd]
+  {
+    GemmLayer L{};
+    L.P_in = 1; L.C_in = latent; L.P_out = 16; L.C_out = 4 * nd; L.h_in = 1; L.w_in = 1; L.h_used = 4; L.w_used = 4;
+    L.relu = true;
+    L.fwd_host = linear_fwd_pairs(16); L.bwd_host = linear_bwd_pairs(16);
+    const float* W = weights[0];             // (latent, 16*4nd), column f = pixel*4nd + c
+    L.wf = W; L.wf_tile_stride = L.C_out; L.wf_ld = 16 * L.C_out;
+    float* Wt = nullptr;                     // [16*4nd][latent]: backward tile q rows = c, cols = latent
+    if ((rc = dev_alloc(c.get(), (void**)&Wt, (size_t)latent * 16 * L.C_out * 4))) return fail(rc);
+    const size_t total = (size_t)latent * 16 * L.C_out;
+    transpose_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, Wt, latent, 16 * L.C_out, total);
+    L.wb = Wt; L.wb_tile_stride = L.C_out * latent; L.wb_ld = latent;
+    L.bias = weights[1]; L.bias_pstride = L.C_out;   // bias index f = pixel*C_out + c
+    c->layers.push_back(L);
+  }
+  // ---- hidden deconvs
+  struct DSpec { int c_in, c_out, h_in, h_used; bool relu; };
+  std::vector<DSpec> specs;
+  if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, true}, {2 * nd, nd, 8, 16, true}, {nd, nd, 16, 32, false}};
+  else specs = {{4 * nd, 2 * nd, 4, 7, true}, {2 * nd, nd, 7, 14, true}};
+  int wi = 2;
+  for (const DSpec& sp : specs) {
+    GemmLayer L{};
+    L.P_in = sp.h_in * sp.h_in; L.C_in = sp.c_in; L.P_out = sp.h_used * sp.h_used; L.C_out = sp.c_out;
+    L.h_in = L.w_in = sp.h_in; L.h_used = L.w_used = sp.h_used; L.relu = sp.relu;
+    L.fwd_host = deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used);
+    L.bwd_host = deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used);
+    const float* F = weights[wi];            // (5,5,C_out,C_in)
+    float* Ff = nullptr;                     // [25][C_in][C_out]
+    const size_t total = (size_t)kTaps * sp.c_out * sp.c_in;
+    if ((rc = dev_alloc(c.get(), (void**)&Ff, total * 4))) return fail(rc);
+    transpose_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(F, Ff, sp.c_out, sp.c_in, total);
+    L.wf = Ff; L.wf_tile_stride = sp.c_in * sp.c_out; L.wf_ld = sp.c_out;
+    L.wb = F;  L.wb_tile_stride = sp.c_in * sp.c_out; L.wb_ld = sp.c_in;
+    L.bias = weights[wi + 1];
+    c->layers.push_back(L);
+    wi += 2;
+  }
+  // ---- final layer
+  {
+    FinalLayer& f = c->fin;
+    f.h_in = f.w_in = celeba ? 32 : 14; f.C_in = nd; f.C_out = c->C; f.act = celeba ? ACT_TANH : ACT_SIGMOID;
+    f.w = weights[wi]; f.bias = weights[wi + 1];
+    f.n_bands = (2 * f.h_in + kBandRows - 1) / kBandRows;
+    f.fwd_smem = ((size_t)kTaps * f.C_out * f.C_in + (size_t)(kBandRows / 2 + 2) * f.w_in * (f.C_in + 4)) * 4;
+    f.bwd_smem = (size_t)kTaps * f.C_out * f.C_in * 4;
+  }
+  // exact in-bounds MACs per latent row
+  c->macs_per_row = 0;
+  for (const GemmLayer& L : c->layers) c->macs_per_row += (int64_t)L.fwd_host.pairs.size() * L.C_in * L.C_out;
+  {
+    PairTable ft = deconv_fwd_pairs(c->fin.h_in, c->fin.w_in, 2 * c->fin.h_in, 2 * c->fin.w_in);
+    c->macs_per_row += (int64_t)ft.pairs.size() * c->fin.C_in * c->fin.C_out;
+  }
+  for (GemmLayer& L : c->layers) {
+    if ((rc = upload_table(c.get(), L.fwd_host, &L.fwd, s))) return fail(rc);
+    if ((rc = upload_table(c.get(), L.bwd_host, &L.bwd, s))) return fail(rc);
+  }
+  // opt in to > 48 KB dynamic shared memory where needed
+#define OPTIN(K, BYTES) DGAN_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)))
+  OPTIN((final_fwd_loss_kernel<float, 1, ACT_SIGMOID>), 100 * 1024);
+  OPTIN((final_fwd_loss_kernel<float, 3, ACT_TANH>), 100 * 1024);
+  OPTIN((final_fwd_loss_kernel<__half, 1, ACT_SIGMOID>), 100 * 1024);
+  OPTIN((final_fwd_loss_kernel<__half, 3, ACT_TANH>), 100 * 1024);
+#undef OPTIN
+  if (d->precision == DGAN_PREC_FP16) {
+    std::vector<TcLayerSpec> tspecs;
+    for (GemmLayer& L : c->layers) {
+      TcLayerSpec t{};
+      t.P_in = L.P_in; t.C_in = L.C_in; t.P_out = L.P_out; t.C_out = L.C_out;
+      t.h_in = L.h_in; t.w_in = L.w_in; t.h_used = L.h_used; t.w_used = L.w_used;
+      t.fwd = &L.fwd_host; t.bwd = &L.bwd_host;
+      t.w_fwd_kmajor_src = (&L == &c->layers[0]) ? nullptr : L.wb;  // F[t][co][ci]: rows co (N), cols ci (K)
+      t.w_bwd_kmajor_src = (&L == &c->layers[0]) ? nullptr : L.wf;  // Ff[t][ci][co]: rows ci (N), cols co (K)
+      t.linear_W = (&L == &c->layers[0]) ? weights[0] : nullptr;
+      t.linear_Wt = (&L == &c->layers[0]) ? L.wb : nullptr;
+      t.out_f = &L.tc_f; t.out_b = &L.tc_b;
+      tspecs.push_back(t);
+    }
+    if ((rc = tc_build(c->tc, tspecs, latent, &c->allocs, s))) return fail(rc);
+  }
+  DGAN_CUDA_CHECK(cudaGetLastError());
+  *out = c.release();
+  return DGAN_OK;
+}
+
+int dgan_destroy(dgan_handle h) {
+  if (h == nullptr) return DGAN_OK;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return DGAN_OK;
+}
+
+size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
+  if (h == nullptr || batch <= 0 || rec_rr <= 0) return 0;
+  return carve(h, batch * rec_rr, nullptr).bytes;
+}
+
+int64_t dgan_last_launch_count(dgan_handle h) { return h ? h->last_launches : 0; }
+int64_t dgan_macs_per_row(dgan_handle h) { return h ? h->macs_per_row : 0; }
+
+int dgan_forward(dgan_handle h, const float* z_dev, int n_rows, float* y_dev, void* ws, size_t ws_bytes, void* stream) {
+  if (h == nullptr || z_dev == nullptr || y_dev == nullptr || n_rows <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w;
+  int rc;
+  if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
+  if ((rc = run_init_z(h, w, z_dev, 0, s))) return rc;
+  if ((rc = run_forward(h, w, nullptr, 1, 1, false, s))) return rc;
+  DGAN_CUDA_CHECK(cudaMemcpyAsync(y_dev, w.y, (size_t)n_rows * h->hwc * 4, cudaMemcpyDeviceToDevice, s));
+  return DGAN_OK;
+}
+
+int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, const float* z_dev, float* y_dev,
+                   float* loss_dev, float* grad_dev, void* ws, size_t ws_bytes, void* stream) {
+  if (h == nullptr || x_dev == nullptr || z_dev == nullptr || batch <= 0 || rec_rr <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_rows = batch * rec_rr;
+  Workspace w;
+  int rc;
+  if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
+  if ((rc = run_init_z(h, w, z_dev, 0, s))) return rc;
+  if ((rc = run_forward(h, w, x_dev, rec_rr, batch, true, s))) return rc;
+  if ((rc = run_backward(h, w, s))) return rc;
+  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, h->fin.n_bands, 1.0f / (float)h->hwc, n_rows, w.loss);
+  DGAN_LAUNCH_CHECK(h);
+  if (y_dev) DGAN_CUDA_CHECK(cudaMemcpyAsync(y_dev, w.y, (size_t)n_rows * h->hwc * 4, cudaMemcpyDeviceToDevice, s));
+  if (loss_dev) DGAN_CUDA_CHECK(cudaMemcpyAsync(loss_dev, w.loss, (size_t)n_rows * 4, cudaMemcpyDeviceToDevice, s));
+  if (grad_dev) {
+    const size_t n = (size_t)n_rows * h->desc.latent_dim;
+    scale_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.g, grad_dev, grad_multiplier(h), n);
+    DGAN_LAUNCH_CHECK(h);
+  }
+  return DGAN_OK;
+}
+
+int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uint64_t seed, int batch, int rec_rr,
+                     int rec_iters, float rec_lr, float momentum, int decay_lr, float* rec_dev, float* loss_dev,
+                     int32_t* idx_dev, void* ws, size_t ws_bytes, void* stream) {
+  if (h == nullptr || x_dev == nullptr || rec_dev == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
+  if (batch <= 0 || rec_rr <= 0 || rec_iters <= 0) { set_error("batch, rec_rr and rec_iters must be positive"); return DGAN_ERR_INVALID_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_rows = batch * rec_rr;
+  Workspace w;
+  int rc;
+  if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
+  const int64_t launches0 = h->launches;
+  if ((rc = run_init_z(h, w, z0_dev, seed, s))) return rc;
+  const size_t zcount = (size_t)w.n_pad * h->desc.latent_dim;
+  const int decay_iter = (int)std::ceil(rec_iters * 0.8);
+  for (int t = 0; t < rec_iters; ++t) {
+    const bool last = (t == rec_iters - 1);
+    // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
+    // the L-th update is never observed, so its backward pass is not run.
+    if ((rc = run_forward(h, w, x_dev, rec_rr, batch, !last, s))) return rc;
+    if (last) break;
+    if ((rc = run_backward(h, w, s))) return rc;
+    float lr = rec_lr;
+    if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
+    momentum_kernel<<<(unsigned)((zcount + 255) / 256), 256, 0, s>>>(w.z, w.v, w.g, grad_multiplier(h), lr, momentum,
+                                                                     zcount, w.z_h);
+    DGAN_LAUNCH_CHECK(h);
+  }
+  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, h->fin.n_bands, 1.0f / (float)h->hwc, n_rows, w.loss);
+  DGAN_LAUNCH_CHECK(h);
+  select_kernel<<<batch, 256, 0, s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev, loss_dev, idx_dev);
+  DGAN_LAUNCH_CHECK(h);
+  h->last_launches = h->launches - launches0;
+  return DGAN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+/*
+ * defensegan_b200.h - C ABI of the B200-native Defense-GAN projection loop.
+ *
+ * The reference (kabkabm/defensegan) has no FFI/plugin interface: the boundary is the Python
+ * method DefenseGANBase.reconstruct (models/gan.py:333-449) plus the eval driver
+ * utils/gan_defense.py:32-179.  This header is the C-ABI that sits directly underneath that
+ * Python surface; each entry point cites the reference lines it replaces.
+ * Plain pointers and sizes only - no torch types.  All device pointers are owned by the
+ * caller; the handle owns only its re-laid-out weight copies.  Nothing is freed across the
+ * boundary.  No function synchronises the host: work is enqueued on `stream`.
+ *
+ * Every function returns 0 on success, a negative dgan_status otherwise; the message is
+ * available (thread-local) from dgan_last_error().  No C++ exception crosses the boundary.
+ */
+#ifndef DEFENSEGAN_B200_H_
+#define DEFENSEGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGAN_ABI_VERSION 1
+
+typedef struct dgan_ctx* dgan_handle;
+
+enum dgan_status {
+  DGAN_OK = 0,
+  DGAN_ERR_INVALID_ARG = -1,
+  DGAN_ERR_CUDA = -2,
+  DGAN_ERR_UNSUPPORTED = -3,
+  DGAN_ERR_WORKSPACE = -4
+};
+
+/* generator architectures (models/dataset_models.py:36-71 mnist_generator - also used by
+ * F-MNIST, models/gan.py:688-698 - and :127-165 celeba_generator) */
+enum dgan_arch { DGAN_ARCH_MNIST = 0, DGAN_ARCH_CELEBA = 1 };
+
+/* arithmetic of the contractions.  State (z, momentum, loss, accumulators) is always fp32. */
+enum dgan_precision {
+  DGAN_PREC_FP32 = 0, /* fp32 operands, CUDA-core FMA: the reference's arithmetic type */
+  DGAN_PREC_FP16 = 1  /* fp16 operands, fp32 accumulate, tcgen05 tensor cores */
+};
+
+typedef struct dgan_desc {
+  int32_t abi_version; /* DGAN_ABI_VERSION */
+  int32_t arch;        /* dgan_arch */
+  int32_t latent_dim;  /* LATENT_DIM (experiments/cfgs/gans/default.yml:4) */
+  int32_t net_dim;     /* NET_DIM    (default.yml:7) */
+  int32_t use_bn;      /* USE_BN     (default.yml:3); batch-statistics BN, tflib/ops/batchnorm.py:80-93 */
+  int32_t precision;   /* dgan_precision */
+} dgan_desc;
+
+/* Number of weight tensors dgan_create expects for a descriptor, in the reference's variable
+ * creation order (tflib/__init__.py:7-33 names):
+ *   Generator.Input.W [latent,4096*] , Generator.Input.b,
+ *   [BN1.offset, BN1.scale,]
+ *   Generator.2.Filters [5,5,Cout,Cin], Generator.2.Biases, [BN2.offset, BN2.scale,]
+ *   Generator.3.Filters, Generator.3.Biases, [BN3.offset, BN3.scale,]
+ *   Generator.5.Filters, Generator.5.Biases, (celeba: Generator.6.Filters, Generator.6.Biases)
+ * All fp32, device memory, TF layouts (Linear W is (in,out), tflib/ops/linear.py:129-133;
+ * Deconv filters are (kh,kw,Cout,Cin), tflib/ops/deconv2d.py:67,104-110). */
+int dgan_num_weights(const dgan_desc* desc);
+
+/* Replaces DefenseGANBase.load_generator + the tflib.param registry (models/gan.py:80-87,
+ * tflib/__init__.py:7-33): uploads nothing (weights are already on the device) but builds the
+ * handle's re-laid-out copies (per-tap tiles, transposes, fp16 copies) on `stream`. */
+int dgan_create(dgan_handle* out, const dgan_desc* desc, const float* const* weights_dev,
+                int n_weights, void* stream);
+int dgan_destroy(dgan_handle h);
+
+/* Bytes of caller-owned scratch needed by dgan_reconstruct / dgan_forward / dgan_loss_grad
+ * for `batch` images x `rec_rr` restarts. */
+size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr);
+
+/* Replaces one sess.run of the op built by DefenseGANBase.reconstruct (models/gan.py:333-449)
+ * preceded by tf.local_variables_initializer() (utils/gan_defense.py:119):
+ *   x_dev     [batch, H, W, C] fp32 NHWC, already input-transformed
+ *   z0_dev    [batch*rec_rr, latent] fp32 (the reference's z_init_val, gan.py:395-397) or NULL:
+ *             z0 ~ N(0, 1/latent) from a Philox stream keyed by `seed` (gan.py:370-377)
+ *   rec_iters L, rec_lr (constant: the reference's decay is dead code), momentum 0.7
+ *   rec_dev   [batch, H, W, C] fp32: G(z_{L-1}) of the arg-min restart (gan.py:438-449)
+ *   loss_dev  [batch] fp32 min per-image MSE, nullable;  idx_dev [batch] int32 chosen restart, nullable
+ *   decay_lr  0 = reference behaviour; 1 = intended x0.1 at ceil(0.8 L) (off by default)
+ * The whole L-step loop is enqueued on `stream` with no host synchronisation. */
+int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uint64_t seed,
+                     int batch, int rec_rr, int rec_iters, float rec_lr, float momentum,
+                     int decay_lr, float* rec_dev, float* loss_dev, int32_t* idx_dev,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* generator_fn(z) (models/gan.py:657-665,726-735): y_dev [n_rows, H*W*C] fp32. */
+int dgan_forward(dgan_handle h, const float* z_dev, int n_rows, float* y_dev, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* One evaluation of the loop body (models/gan.py:409-417) without the update, for known-answer
+ * tests: y [batch*rec_rr, HWC], loss [batch*rec_rr], grad = d(sum loss)/dz [batch*rec_rr, latent]. */
+int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, const float* z_dev,
+                   float* y_dev, float* loss_dev, float* grad_dev, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Kernel launches enqueued by the most recent dgan_reconstruct on this handle. */
+int64_t dgan_last_launch_count(dgan_handle h);
+
+/* Algorithmic multiply-accumulates of one generator forward per latent row (exact in-bounds
+ * taps); backward-to-z has the same count. */
+int64_t dgan_macs_per_row(dgan_handle h);
+
+const char* dgan_last_error(void);
+int dgan_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFENSEGAN_B200_H_ */

@@ -1,0 +1,187 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every call goes through the C-ABI
+(ctypes -> libdefensegan_b200.so) and is checked against the CPU oracle / golden vectors.
+
+Tolerances (stated per precision):
+  fp32 (CUDA-core FMA, the reference's arithmetic type): elementwise |rec - rec_oracle64| <= 1e-4,
+       identical arg-min indices, |loss_min - oracle| <= 1e-6 at the C1 horizon.
+  fp16 (tcgen05 operands, fp32 accumulate): per-image |MSE_min - oracle| <= 1e-4 (BASELINE.json's
+       bar), elementwise |rec - rec_oracle| <= 2e-2 at the C1 horizon.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import defensegan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32", "fp16"]
+TOL = {
+    "fp32": dict(fwd=2e-5, grad_rel=2e-4, rec=1e-4, loss=1e-6),
+    "fp16": dict(fwd=5e-3, grad_rel=2e-2, rec=2e-2, loss=1e-4),
+}
+
+
+def _native_gen(arch, weights, precision):
+    from defensegan_b200 import _native
+    dev = torch.device("cuda", 0)
+    tensors = [torch.as_tensor(v).to(dev) for v in weights.values()]
+    return _native.NativeGenerator(arch, tensors, precision=precision, device=dev)
+
+
+@pytest.fixture(scope="module")
+def gens():
+    cache = {}
+
+    def get(arch, precision, random_bias=False):
+        key = (arch, precision, random_bias)
+        if key not in cache:
+            w = O.init_generator_weights(arch, random_bias=random_bias)
+            cache[key] = (w, _native_gen(arch, w, precision))
+        return cache[key]
+
+    yield get
+    for _, g in cache.values():
+        g.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("arch", ["mnist", "celeba"])
+def test_forward_matches_oracle(gens, arch, precision):
+    w, gen = gens(arch, precision, True)
+    z = O.sample_z0(5, 128, seed=3)
+    want = O.generator_forward(arch, O.weights_to_torch(w, torch.float64), torch.tensor(z, dtype=torch.float64)).numpy()
+    got = gen.forward(torch.tensor(z).cuda()).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= TOL[precision]["fwd"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("arch", ["mnist", "celeba"])
+def test_loss_and_grad_match_oracle(gens, arch, precision):
+    w, gen = gens(arch, precision, True)
+    B, R = 3, 2
+    imgs = O.synthetic_images(arch, w, B, kind="S2", seed=5)
+    z = O.sample_z0(B * R, 128, seed=6)
+    y64, loss64, grad64 = O.loss_and_grad(arch, w, imgs, z, R, dtype=torch.float64)
+    y, loss, grad = gen.loss_grad(torch.tensor(imgs).cuda(), torch.tensor(z).cuda(), R)
+    t = TOL[precision]
+    assert np.abs(y.cpu().numpy() - y64).max() <= t["fwd"]
+    assert np.abs(loss.cpu().numpy() - loss64).max() <= max(t["loss"], 1e-3 * t["fwd"] / 2e-5 * 1e-3)
+    gerr = np.abs(grad.cpu().numpy() - grad64).max() / np.abs(grad64).max()
+    assert gerr <= t["grad_rel"], gerr
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("case", ["mnist_c1", "mnist_ragged_bias", "celeba_small"])
+def test_reconstruct_matches_golden(gens, golden_dir, case, precision):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    arch = str(g["arch"])
+    w, gen = gens(arch, precision, bool(int(g["random_bias"])))
+    rec, loss, idx = gen.reconstruct(torch.tensor(g["images"]).cuda(), int(g["R"]), int(g["L"]), float(g["lr"]),
+                                     z_init_val=torch.tensor(g["z0"]).cuda(), return_aux=True)
+    rec, loss, idx = rec.cpu().numpy(), loss.cpu().numpy(), idx.cpu().numpy()
+    t = TOL[precision]
+    assert rec.shape == g["images"].shape
+    np.testing.assert_array_equal(idx, g["idx64"])
+    assert np.abs(loss - g["loss_min64"]).max() <= t["loss"]
+    assert np.abs(rec - g["rec64"]).max() <= t["rec"]
+    # and against the fp32 oracle run (the reference-precision stand-in)
+    assert np.abs(rec - g["rec32"]).max() <= t["rec"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_size_independent_properties_at_full_size(gens, precision):
+    """BASELINE configs[1] size (B=256, R=10) at a shortened horizon plus properties that need no
+    oracle: run-to-run bit-exactness, loss_min == MSE(rec, x), tie -> lowest index, batch-split
+    invariance (== what sharding across GPUs relies on)."""
+    arch = "mnist"
+    w, gen = gens(arch, precision)
+    B, R, L = 256, 10, 12
+    x = torch.tensor(O.synthetic_images(arch, w, B)).cuda()
+    z0 = torch.tensor(O.sample_z0(B * R, 128)).cuda()
+    rec, loss, idx = gen.reconstruct(x, R, L, 10.0, z_init_val=z0, return_aux=True)
+    rec2, loss2, idx2 = gen.reconstruct(x, R, L, 10.0, z_init_val=z0, return_aux=True)
+    assert torch.equal(rec, rec2) and torch.equal(loss, loss2) and torch.equal(idx, idx2)
+    mse = ((rec - x) ** 2).mean(dim=(1, 2, 3))
+    assert float((mse - loss).abs().max()) <= 1e-6
+    assert int(idx.min()) >= 0 and int(idx.max()) < R and len(torch.unique(idx)) > 1
+    # the projection must actually descend: loss after L steps < loss of the best initial restart
+    _, loss_l1, _ = gen.reconstruct(x, R, 1, 10.0, z_init_val=z0, return_aux=True)
+    assert float(loss.mean()) < float(loss_l1.mean())
+    # batch-split invariance (rows are independent without BatchNorm)
+    h = 96
+    rec_a = gen.reconstruct(x[:h], R, L, 10.0, z_init_val=z0[:h * R])
+    rec_b = gen.reconstruct(x[h:], R, L, 10.0, z_init_val=z0[h * R:])
+    assert torch.equal(torch.cat([rec_a, rec_b]), rec)
+    # identical restarts tie -> index 0 (tf.argmin)
+    z_tie = z0.view(B, R, -1)[:, :1].expand(B, R, 128).reshape(B * R, 128).contiguous()
+    _, _, idx_tie = gen.reconstruct(x, R, 3, 10.0, z_init_val=z_tie, return_aux=True)
+    assert int(idx_tie.abs().max()) == 0
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_long_horizon_statistical_parity(gens, precision):
+    """L=200, R=10 (the metric's operating point) on a batch the oracle finishes in ~20 s:
+    per-image |MSE_min - oracle_fp32| <= 1e-4 (BASELINE.json), restart agreement reported."""
+    arch = "mnist"
+    w, gen = gens(arch, precision)
+    B, R, L = 8, 10, 200
+    imgs = O.synthetic_images(arch, w, B)
+    z0 = O.sample_z0(B * R, 128)
+    ref = O.reconstruct(arch, w, imgs, R, L, z_init_val=z0)
+    rec, loss, idx = gen.reconstruct(torch.tensor(imgs).cuda(), R, L, 10.0, z_init_val=torch.tensor(z0).cuda(),
+                                     return_aux=True)
+    dmse = np.abs(loss.cpu().numpy() - ref["loss_min"])
+    agree = float((idx.cpu().numpy() == ref["idx"]).mean())
+    print("precision=%s max|dMSE|=%.3g restart agreement=%.2f" % (precision, dmse.max(), agree))
+    assert dmse.max() <= 1e-4
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_python_surface_and_random_restarts(precision):
+    from defensegan_b200.models.gan import MnistDefenseGAN
+    from defensegan_b200.utils.gan_defense import model_eval_gan, SharedReconstruction
+    gan = MnistDefenseGAN(test_mode=True, verbose=False, precision=precision)
+    assert gan.load_generator() is False          # no checkpoint: keeps reference-style random init
+    gan.rec_rr, gan.rec_iters = 4, 5
+    x = torch.tensor(O.synthetic_images("mnist", gan.weights, 6)).cuda()
+    a = gan.reconstruct(x)
+    b = gan.reconstruct(x)
+    assert a.shape == x.shape and a.is_cuda and not a.requires_grad
+    assert not torch.equal(a, b)                  # fresh z0 per call (utils/gan_defense.py:119)
+    z0 = torch.tensor(O.sample_z0(6 * 4, 128)).cuda()
+    assert torch.equal(gan.reconstruct(x, z_init_val=z0), gan.reconstruct(x, z_init_val=z0))
+    with pytest.raises(ValueError):
+        gan.reconstruct(x[:, :14])
+    labels = np.eye(10, dtype="f4")[np.arange(6) % 10]
+    rec = SharedReconstruction(gan)
+    clf = torch.nn.Linear(784, 10).cuda()
+    acc, roc = model_eval_gan(None, None, None, predictions=lambda xb: clf(rec(xb).reshape(len(xb), -1)),
+                              test_images=x.cpu().numpy(), test_labels=labels, args={"batch_size": 4},
+                              diff_op=lambda xb: ((xb - rec(xb)) ** 2).mean(dim=(1, 2, 3)))
+    assert 0.0 <= acc <= 1.0 and roc[2].shape == (6,) and np.all(roc[2] > 0)
+    gan.close()
+
+
+def test_error_paths_through_c_abi(gens):
+    from defensegan_b200 import _native
+    w, gen = gens("mnist", "fp32")
+    lib = gen.lib
+    x = torch.zeros(2, 28, 28, 1, device="cuda")
+    rec = torch.empty_like(x)
+    small = torch.empty(4096, dtype=torch.uint8, device="cuda")
+    base = (small.data_ptr() + 1023) // 1024 * 1024
+    rc = lib.dgan_reconstruct(gen._handle, x.data_ptr(), None, 0, 2, 2, 3, 10.0, 0.7, 0, rec.data_ptr(), None, None,
+                              ctypes.c_void_p(base), 1024, None)
+    assert rc == -4 and b"workspace" in lib.dgan_last_error()
+    rc = lib.dgan_reconstruct(gen._handle, x.data_ptr(), None, 0, 0, 2, 3, 10.0, 0.7, 0, rec.data_ptr(), None, None,
+                              ctypes.c_void_p(base), 1024, None)
+    assert rc == -1
+    d = _native.dgan_desc(1, 0, 128, 64, 1, 0)     # use_bn: not built yet -> explicit UNSUPPORTED, no fallback
+    h = ctypes.c_void_p(0)
+    arr = (ctypes.c_void_p * 14)(*([x.data_ptr()] * 14))
+    assert lib.dgan_create(ctypes.byref(h), ctypes.byref(d), arr, 14, None) == -3
