@@ -31,7 +31,8 @@ NVCC_FLAGS = [
 ABI_SYMBOLS = [
     "dgan_abi_version", "dgan_last_error", "dgan_num_weights", "dgan_create", "dgan_destroy",
     "dgan_workspace_bytes", "dgan_reconstruct", "dgan_forward", "dgan_loss_grad",
-    "dgan_last_launch_count", "dgan_macs_per_row",
+    "dgan_last_launch_count", "dgan_macs_per_row", "dgan_profile_enable", "dgan_profile_num_kinds",
+    "dgan_profile_kind_name", "dgan_profile_read",
 ]
 
 
@@ -95,6 +96,15 @@ def load_library() -> ctypes.CDLL:
     lib.dgan_last_launch_count.argtypes = [vp]
     lib.dgan_macs_per_row.restype = ctypes.c_int64
     lib.dgan_macs_per_row.argtypes = [vp]
+    lib.dgan_profile_enable.restype = i32
+    lib.dgan_profile_enable.argtypes = [vp, i32]
+    lib.dgan_profile_num_kinds.restype = i32
+    lib.dgan_profile_num_kinds.argtypes = [vp]
+    lib.dgan_profile_kind_name.restype = ctypes.c_char_p
+    lib.dgan_profile_kind_name.argtypes = [vp, i32]
+    lib.dgan_profile_read.restype = i32
+    lib.dgan_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 
@@ -181,6 +191,19 @@ class NativeGenerator:
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.dgan_last_launch_count(self._handle))
+
+    def profile_enable(self, on: bool) -> None:
+        _check(self.lib, self.lib.dgan_profile_enable(self._handle, int(bool(on))), "dgan_profile_enable")
+
+    def profile_read(self):
+        """[{name, ms, launches, flops_per_launch}] for the launches recorded since profile_enable(True)."""
+        nk = int(self.lib.dgan_profile_num_kinds(self._handle))
+        ms = (ctypes.c_double * nk)()
+        cnt = (ctypes.c_int64 * nk)()
+        fl = (ctypes.c_double * nk)()
+        _check(self.lib, self.lib.dgan_profile_read(self._handle, nk, ms, cnt, fl), "dgan_profile_read")
+        return [dict(name=self.lib.dgan_profile_kind_name(self._handle, k).decode(), ms=float(ms[k]),
+                     launches=int(cnt[k]), flops_per_launch=float(fl[k])) for k in range(nk)]
 
     # -- entry points ----------------------------------------------------------------------
     def reconstruct(self, images: torch.Tensor, rec_rr: int, rec_iters: int, rec_lr: float = 10.0,

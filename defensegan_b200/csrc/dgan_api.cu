@@ -125,9 +125,32 @@ struct dgan_ctx {
   int64_t last_launches = 0;
   int64_t launches = 0;
   TcState tc;
+  // optional per-launch CUDA-event timing (dgan_profile_*): serialises nothing by itself but
+  // adds two event records per launch, so it is never enabled in a timed benchmark pass
+  bool profile = false;
+  int n_rows_cur = 0;
+  struct ProfRec { int kind; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<std::string> kind_names;
+  std::vector<double> kind_macs_per_row;
 };
 
 namespace dgan {
+
+struct ProfScope {
+  dgan_ctx* c; cudaStream_t s; bool on; dgan_ctx::ProfRec r;
+  ProfScope(dgan_ctx* c_, int kind, cudaStream_t s_) : c(c_), s(s_), on(c_->profile) {
+    if (!on) return;
+    r.kind = kind;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, s);
+    c->prof.push_back(r);
+  }
+};
 
 static int dev_alloc(dgan_ctx* c, void** p, size_t bytes) {
   DGAN_CUDA_CHECK(cudaMalloc(p, bytes));
@@ -297,21 +320,25 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     const __half* in = w.z_h;
     for (int l = 0; l < nl; ++l) {
       const GemmLayer& L = c->layers[l];
+      ProfScope ps(c, 2 * l, s);
       if ((rc = tc_launch(c->tc, &c->launches, L.tc_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS,
                           L.bias, nullptr, 1.f, s)))
         return rc;
       in = w.act_h[l];
     }
+    ProfScope ps(c, 2 * nl, s);
     return launch_final_fwd<__half>(c, in, w, x, R, B, want_grad, s);
   }
   const float* in = w.z;
   for (int l = 0; l < nl; ++l) {
     const GemmLayer& L = c->layers[l];
+    ProfScope ps(c, 2 * l, s);
     if ((rc = launch_bsgemm_f32(c, L.relu ? EPI_BIAS_RELU : EPI_BIAS, in, L.C_in, w.n_pad, L.wf, L.wf_tile_stride,
                                 L.wf_ld, L.fwd, w.act[l], L.C_out, L.bias, L.bias_pstride, nullptr, s)))
       return rc;
     in = w.act[l];
   }
+  ProfScope ps(c, 2 * nl, s);
   return launch_final_fwd<float>(c, in, w, x, R, B, want_grad, s);
 }
 
@@ -321,29 +348,39 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s) {
   const int nl = (int)c->layers.size();
   if (c->desc.precision == DGAN_PREC_FP16) {
     const GemmLayer& last = c->layers[nl - 1];
-    if ((rc = launch_final_bwd<__half>(c, w, last.relu ? w.act_h[nl - 1] : nullptr, c->tc.grad_scale,
-                                       w.dact_h[nl - 1], s)))
-      return rc;
+    {
+      ProfScope ps(c, 2 * nl + 1, s);
+      if ((rc = launch_final_bwd<__half>(c, w, last.relu ? w.act_h[nl - 1] : nullptr, c->tc.grad_scale,
+                                         w.dact_h[nl - 1], s)))
+        return rc;
+    }
     for (int l = nl - 1; l >= 1; --l) {
       const GemmLayer& L = c->layers[l];
       const bool mask = c->layers[l - 1].relu;
+      ProfScope ps(c, 2 * l + 1, s);
       if ((rc = tc_launch(c->tc, &c->launches, L.tc_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad,
                           mask ? EPI_MASK : EPI_NONE, nullptr, mask ? w.act_h[l - 1] : nullptr, 1.f, s)))
         return rc;
     }
     const GemmLayer& L0 = c->layers[0];
+    ProfScope ps(c, 1, s);
     return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
   }
   const GemmLayer& last = c->layers[nl - 1];
-  if ((rc = launch_final_bwd<float>(c, w, last.relu ? w.act[nl - 1] : nullptr, 1.f, w.dact[nl - 1], s))) return rc;
+  {
+    ProfScope ps(c, 2 * nl + 1, s);
+    if ((rc = launch_final_bwd<float>(c, w, last.relu ? w.act[nl - 1] : nullptr, 1.f, w.dact[nl - 1], s))) return rc;
+  }
   for (int l = nl - 1; l >= 1; --l) {
     const GemmLayer& L = c->layers[l];
     const bool mask = c->layers[l - 1].relu;
+    ProfScope ps(c, 2 * l + 1, s);
     if ((rc = launch_bsgemm_f32(c, mask ? EPI_MASK : EPI_NONE, w.dact[l], L.C_out, w.n_pad, L.wb, L.wb_tile_stride,
                                 L.wb_ld, L.bwd, w.dact[l - 1], L.C_in, nullptr, 0, mask ? w.act[l - 1] : nullptr, s)))
       return rc;
   }
   const GemmLayer& L0 = c->layers[0];
+  ProfScope ps(c, 1, s);
   return launch_bsgemm_f32(c, EPI_NONE, w.dact[0], L0.C_out, w.n_pad, L0.wb, L0.wb_tile_stride, L0.wb_ld, L0.bwd, w.g,
                            L0.C_in, nullptr, 0, nullptr, s);
 }
@@ -498,10 +535,27 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
       t.w_bwd_kmajor_src = (&L == &c->layers[0]) ? nullptr : L.wf;  // Ff[t][ci][co]: rows ci (N), cols co (K)
       t.linear_W = (&L == &c->layers[0]) ? weights[0] : nullptr;
       t.linear_Wt = (&L == &c->layers[0]) ? L.wb : nullptr;
-      t.out_f = &L.tc_f; t.out_b = &L.tc_b;
+      t.out_f = &L.tc_f; t.out_b = &L.tc_b; t.bias_pstride = L.bias_pstride;
       tspecs.push_back(t);
     }
     if ((rc = tc_build(c->tc, tspecs, latent, &c->allocs, s))) return fail(rc);
+  }
+  {
+    static const char* lname_m[] = {"Linear", "Generator.2", "Generator.3"};
+    static const char* lname_c[] = {"Linear", "Generator.2", "Generator.3", "Generator.5"};
+    for (size_t l = 0; l < c->layers.size(); ++l) {
+      const std::string nm = celeba ? lname_c[l] : lname_m[l];
+      const double macs = (double)c->layers[l].fwd_host.pairs.size() * c->layers[l].C_in * c->layers[l].C_out;
+      c->kind_names.push_back(nm + ".fwd"); c->kind_macs_per_row.push_back(macs);
+      c->kind_names.push_back(nm + ".bwd"); c->kind_macs_per_row.push_back(macs);
+    }
+    double fmacs = 0;
+    for (const GemmLayer& L : c->layers) fmacs += (double)L.fwd_host.pairs.size() * L.C_in * L.C_out;
+    fmacs = (double)c->macs_per_row - fmacs;
+    const std::string fn = celeba ? "Generator.6" : "Generator.5";
+    c->kind_names.push_back(fn + "+loss.fwd"); c->kind_macs_per_row.push_back(fmacs);
+    c->kind_names.push_back(fn + ".bwd"); c->kind_macs_per_row.push_back(fmacs);
+    c->kind_names.push_back("momentum"); c->kind_macs_per_row.push_back(0.0);
   }
   DGAN_CUDA_CHECK(cudaGetLastError());
   *out = c.release();
@@ -510,6 +564,7 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
 
 int dgan_destroy(dgan_handle h) {
   if (h == nullptr) return DGAN_OK;
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return DGAN_OK;
@@ -569,6 +624,7 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
   int rc;
   if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
   const int64_t launches0 = h->launches;
+  h->n_rows_cur = n_rows;
   if ((rc = run_init_z(h, w, z0_dev, seed, s))) return rc;
   const size_t zcount = (size_t)w.n_pad * h->desc.latent_dim;
   const int decay_iter = (int)std::ceil(rec_iters * 0.8);
@@ -581,15 +637,51 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
     if ((rc = run_backward(h, w, s))) return rc;
     float lr = rec_lr;
     if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
-    momentum_kernel<<<(unsigned)((zcount + 255) / 256), 256, 0, s>>>(w.z, w.v, w.g, grad_multiplier(h), lr, momentum,
-                                                                     zcount, w.z_h);
-    DGAN_LAUNCH_CHECK(h);
+    {
+      ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
+      momentum_kernel<<<(unsigned)((zcount + 255) / 256), 256, 0, s>>>(w.z, w.v, w.g, grad_multiplier(h), lr, momentum,
+                                                                       zcount, w.z_h);
+      DGAN_LAUNCH_CHECK(h);
+    }
   }
   loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, h->fin.n_bands, 1.0f / (float)h->hwc, n_rows, w.loss);
   DGAN_LAUNCH_CHECK(h);
   select_kernel<<<batch, 256, 0, s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev, loss_dev, idx_dev);
   DGAN_LAUNCH_CHECK(h);
   h->last_launches = h->launches - launches0;
+  return DGAN_OK;
+}
+
+int dgan_profile_enable(dgan_handle h, int enable) {
+  if (h == nullptr) return DGAN_ERR_INVALID_ARG;
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
+  h->profile = enable != 0;
+  return DGAN_OK;
+}
+
+int dgan_profile_num_kinds(dgan_handle h) { return h ? (int)h->kind_names.size() : 0; }
+
+const char* dgan_profile_kind_name(dgan_handle h, int kind) {
+  if (h == nullptr || kind < 0 || kind >= (int)h->kind_names.size()) return "";
+  return h->kind_names[kind].c_str();
+}
+
+int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* launches_out, double* flops_per_launch_out) {
+  if (h == nullptr || ms_out == nullptr || launches_out == nullptr || flops_per_launch_out == nullptr) return DGAN_ERR_INVALID_ARG;
+  const int nk = std::min(max_kinds, (int)h->kind_names.size());
+  for (int k = 0; k < nk; ++k) {
+    ms_out[k] = 0.0; launches_out[k] = 0;
+    flops_per_launch_out[k] = 2.0 * h->kind_macs_per_row[k] * (double)h->n_rows_cur;
+  }
+  for (auto& r : h->prof) {
+    DGAN_CUDA_CHECK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    DGAN_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.kind >= 0 && r.kind < nk) { ms_out[r.kind] += ms; launches_out[r.kind]++; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  h->prof.clear();
   return DGAN_OK;
 }
 

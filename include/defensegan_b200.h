@@ -107,6 +107,17 @@ int64_t dgan_last_launch_count(dgan_handle h);
  * taps); backward-to-z has the same count. */
 int64_t dgan_macs_per_row(dgan_handle h);
 
+/* Per-kernel device timing for roofline reports (no reference counterpart).  While enabled every
+ * kernel launch of dgan_reconstruct is bracketed by CUDA events on the launching stream; never
+ * enable it in a timed throughput pass.  dgan_profile_read synchronises on the recorded events
+ * and returns, per kernel kind (layer x direction), the summed milliseconds, the launch count and
+ * the algorithmic FLOPs of one launch (2 x exact in-bounds MACs x latent rows of the last call). */
+int dgan_profile_enable(dgan_handle h, int enable);
+int dgan_profile_num_kinds(dgan_handle h);
+const char* dgan_profile_kind_name(dgan_handle h, int kind);
+int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* launches_out,
+                      double* flops_per_launch_out);
+
 const char* dgan_last_error(void);
 int dgan_abi_version(void);
 

@@ -20,8 +20,10 @@ pytestmark = pytest.mark.gpu
 
 PRECISIONS = ["fp32", "fp16"]
 TOL = {
-    "fp32": dict(fwd=2e-5, grad_rel=2e-4, rec=1e-4, loss=1e-6),
-    "fp16": dict(fwd=5e-3, grad_rel=2e-2, rec=2e-2, loss=1e-4),
+    "fp32": dict(fwd=2e-5, grad_rel=2e-4, grad_cos=0.999999, rec=1e-4, loss=1e-6),
+    # fp16 gradient: rounding flips the ReLU mask of units whose pre-activation is ~0, which moves the
+    # gradient by finite (not rounding-sized) amounts: a few % of max |g| while the direction stays put
+    "fp16": dict(fwd=5e-3, grad_rel=6e-2, grad_cos=0.998, rec=2e-2, loss=1e-4),
 }
 
 
@@ -71,8 +73,11 @@ def test_loss_and_grad_match_oracle(gens, arch, precision):
     t = TOL[precision]
     assert np.abs(y.cpu().numpy() - y64).max() <= t["fwd"]
     assert np.abs(loss.cpu().numpy() - loss64).max() <= max(t["loss"], 1e-3 * t["fwd"] / 2e-5 * 1e-3)
-    gerr = np.abs(grad.cpu().numpy() - grad64).max() / np.abs(grad64).max()
+    g = grad.cpu().numpy()
+    gerr = np.abs(g - grad64).max() / np.abs(grad64).max()
+    cos = float((g * grad64).sum() / np.sqrt((g * g).sum() * (grad64 * grad64).sum()))
     assert gerr <= t["grad_rel"], gerr
+    assert cos >= t["grad_cos"], cos
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
