@@ -109,6 +109,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """Threads the CPU port actually uses: the per-step tensors are small (tens of rows), so the
+    torch CPU kernels stop scaling (and then slow down) well before a 100+-core box is full."""
+    return int(os.environ.get("DGAN_CPU_THREADS", min(os.cpu_count() or 1, 16)))
+
+
 def cpu_port_images_per_sec(dataset, R, L, sample_images, threads, repeats=1):
     """The oracle port of the reference's TF1 CPU path (oracle/defensegan_oracle.py), fp32, all
     host threads, on a bounded sample of the same workload: `sample_images` images at the full
@@ -135,7 +141,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     dataset, B, R, L = resolve_workload(args)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sample = max(1, args.ref_sample)
     for _ in range(args.warmup):
         cpu_port_images_per_sec(dataset, R, L, sample, threads)
@@ -188,7 +194,7 @@ def main():
     ap.add_argument("--rec_rr", type=int, default=0)
     ap.add_argument("--rec_iters", type=int, default=0)
     ap.add_argument("--ref_sample", type=int, default=4, help="images per step of the CPU reference arm")
-    ap.add_argument("--cpu_sample", type=int, default=16, help="images of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--cpu_sample", type=int, default=4, help="images of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no_profile", action="store_true")
     args = ap.parse_args()
 
@@ -324,7 +330,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only, bounded sample) ----------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and args.cpu_sample > 0:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         v, secs = cpu_port_images_per_sec(dataset, R, L, args.cpu_sample, threads)
         cpu_baseline = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
                         "sample": "%d images at full R=%d, L=%d in %.1f s (oracle restatement of the TF1 CPU path)"

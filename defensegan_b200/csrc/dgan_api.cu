@@ -125,6 +125,7 @@ struct dgan_ctx {
   int64_t last_launches = 0;
   int64_t launches = 0;
   TcState tc;
+  TcFinal tc_fin;
   // optional per-launch CUDA-event timing (dgan_profile_*): serialises nothing by itself but
   // adds two event records per launch, so it is never enabled in a timed benchmark pass
   bool profile = false;
@@ -181,9 +182,13 @@ __global__ void transpose_tiles_kernel(const float* __restrict__ in, float* __re
   out[t * per + (size_t)cc * rows + r] = in[i];
 }
 
-__global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, float s, size_t n) {
+__global__ void scale_copy_kernel(const float* __restrict__ in, int n_parts, size_t part_stride,
+                                  float* __restrict__ out, float s, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] * s;
+  if (i >= n) return;
+  float g = in[i];
+  for (int p = 1; p < n_parts; ++p) g += in[i + (size_t)p * part_stride];
+  out[i] = g * s;
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -197,6 +202,8 @@ struct Workspace {
   std::vector<float*> act, dact;     // fp32 path: per hidden layer output [P][n_pad][C]
   std::vector<__half*> act_h, dact_h;  // fp16 path
   __half* z_h = nullptr;
+  __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
+  int n_loss_parts = 0, n_g_parts = 1;
   float *y = nullptr, *dpre = nullptr, *loss_part = nullptr, *loss = nullptr;
   size_t bytes = 0;
 };
@@ -216,9 +223,12 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   const int latent = c->desc.latent_dim;
   w.z = (float*)take(np * latent * 4);
   w.v = (float*)take(np * latent * 4);
-  w.g = (float*)take(np * latent * 4);
   const bool tc = c->desc.precision == DGAN_PREC_FP16;
+  w.n_g_parts = tc ? TC_LINEAR_SPLIT : 1;
+  w.g = (float*)take(np * latent * 4 * w.n_g_parts);
   if (tc) w.z_h = (__half*)take(np * latent * 2);
+  if (tc) w.dblk = (__half*)take((size_t)c->tc_fin.n_blocks * np * 64 * 2);
+  w.n_loss_parts = tc ? c->tc_fin.n_blocks : c->fin.n_bands;
   for (const GemmLayer& l : c->layers) {
     const size_t elems = (size_t)l.P_out * np * l.C_out;
     if (tc) {
@@ -231,7 +241,7 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   }
   w.y = (float*)take(np * c->hwc * 4);
   w.dpre = (float*)take(np * c->hwc * 4);
-  w.loss_part = (float*)take(np * c->fin.n_bands * 4);
+  w.loss_part = (float*)take(np * w.n_loss_parts * 4);
   w.loss = (float*)take(np * 4);
   w.bytes = off;
   return w;
@@ -327,7 +337,10 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
       in = w.act_h[l];
     }
     ProfScope ps(c, 2 * nl, s);
-    return launch_final_fwd<__half>(c, in, w, x, R, B, want_grad, s);
+    TcFinalArgs fa{};
+    fa.x = x; fa.y = w.y; fa.loss_part = w.loss_part; fa.R = R; fa.B = B; fa.n_rows = w.n_rows;
+    fa.nbx = c->tc_fin.nbx; fa.w_out = c->tc_fin.w_out; fa.gscale = c->tc.grad_scale;
+    return tc_launch_final_fwd(c->tc, &c->launches, c->tc_fin, in, w.dblk, w.n_pad, c->fin.bias, fa, s);
   }
   const float* in = w.z;
   for (int l = 0; l < nl; ++l) {
@@ -350,8 +363,8 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s) {
     const GemmLayer& last = c->layers[nl - 1];
     {
       ProfScope ps(c, 2 * nl + 1, s);
-      if ((rc = launch_final_bwd<__half>(c, w, last.relu ? w.act_h[nl - 1] : nullptr, c->tc.grad_scale,
-                                         w.dact_h[nl - 1], s)))
+      if ((rc = tc_launch(c->tc, &c->launches, c->tc_fin.b, w.dblk, w.dact_h[nl - 1], w.n_pad,
+                          last.relu ? EPI_MASK : EPI_NONE, nullptr, last.relu ? w.act_h[nl - 1] : nullptr, 1.f, s)))
         return rc;
     }
     for (int l = nl - 1; l >= 1; --l) {
@@ -539,6 +552,9 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
       tspecs.push_back(t);
     }
     if ((rc = tc_build(c->tc, tspecs, latent, &c->allocs, s))) return fail(rc);
+    if ((rc = tc_build_final(c->tc, &c->tc_fin, c->fin.w, c->fin.h_in, c->fin.w_in, c->fin.C_in, c->fin.C_out,
+                             c->fin.act, &c->allocs, s)))
+      return fail(rc);
   }
   {
     static const char* lname_m[] = {"Linear", "Generator.2", "Generator.3"};
@@ -601,13 +617,14 @@ int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, con
   if ((rc = run_init_z(h, w, z_dev, 0, s))) return rc;
   if ((rc = run_forward(h, w, x_dev, rec_rr, batch, true, s))) return rc;
   if ((rc = run_backward(h, w, s))) return rc;
-  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, h->fin.n_bands, 1.0f / (float)h->hwc, n_rows, w.loss);
+  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, 1.0f / (float)h->hwc, n_rows, w.loss);
   DGAN_LAUNCH_CHECK(h);
   if (y_dev) DGAN_CUDA_CHECK(cudaMemcpyAsync(y_dev, w.y, (size_t)n_rows * h->hwc * 4, cudaMemcpyDeviceToDevice, s));
   if (loss_dev) DGAN_CUDA_CHECK(cudaMemcpyAsync(loss_dev, w.loss, (size_t)n_rows * 4, cudaMemcpyDeviceToDevice, s));
   if (grad_dev) {
     const size_t n = (size_t)n_rows * h->desc.latent_dim;
-    scale_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.g, grad_dev, grad_multiplier(h), n);
+    scale_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.g, w.n_g_parts, (size_t)w.n_pad * h->desc.latent_dim,
+                                                                  grad_dev, grad_multiplier(h), n);
     DGAN_LAUNCH_CHECK(h);
   }
   return DGAN_OK;
@@ -639,12 +656,12 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
     if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
     {
       ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
-      momentum_kernel<<<(unsigned)((zcount + 255) / 256), 256, 0, s>>>(w.z, w.v, w.g, grad_multiplier(h), lr, momentum,
-                                                                       zcount, w.z_h);
+      momentum_kernel<<<(unsigned)((zcount + 255) / 256), 256, 0, s>>>(w.z, w.v, w.g, w.n_g_parts, grad_multiplier(h), lr,
+                                                                       momentum, zcount, w.z_h);
       DGAN_LAUNCH_CHECK(h);
     }
   }
-  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, h->fin.n_bands, 1.0f / (float)h->hwc, n_rows, w.loss);
+  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, 1.0f / (float)h->hwc, n_rows, w.loss);
   DGAN_LAUNCH_CHECK(h);
   select_kernel<<<batch, 256, 0, s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev, loss_dev, idx_dev);
   DGAN_LAUNCH_CHECK(h);

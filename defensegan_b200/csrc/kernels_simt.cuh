@@ -275,11 +275,13 @@ final_bwd_kernel(const float* __restrict__ dpre /*[n_pad][P_out*C_OUT]*/, int n_
 // gmul carries the 2/(HWC) of the mean (gan.py:411-413) and undoes any fp16 gradient scaling.
 // Optionally refreshes the fp16 copy of z that feeds the tensor-core Linear.
 // ------------------------------------------------------------------------------------------
-__global__ void momentum_kernel(float* __restrict__ z, float* __restrict__ v, const float* __restrict__ g,
+__global__ void momentum_kernel(float* __restrict__ z, float* __restrict__ v, const float* __restrict__ g, int n_parts,
                                 float gmul, float lr, float mu, size_t count, __half* __restrict__ z_h) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const float vv = fmaf(mu, v[i], gmul * g[i]);
+  float gs = g[i];
+  for (int p = 1; p < n_parts; ++p) gs += g[i + (size_t)p * count];   // split-K partials, fixed order
+  const float vv = fmaf(mu, v[i], gmul * gs);
   const float zz = z[i] - lr * vv;
   v[i] = vv;
   z[i] = zz;

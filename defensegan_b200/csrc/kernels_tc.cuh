@@ -28,6 +28,7 @@ constexpr int TC_STAGE_BYTES = 48 * 1024;    // A + up to 32 KB of weight tiles
 constexpr int TC_MAXB = 4;
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_THREADS = 192;
+constexpr int TC_LINEAR_SPLIT = 4;           // partial sums of the Linear backward (dz)
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct __align__(16) TcStep {
@@ -130,6 +131,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
@@ -150,6 +159,81 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Extra epilogue kinds of the tensor-core path: the generator's last layer (C_out <= 3) is run as
+// a pixel-graph GEMM whose "output pixels" are 4x4 blocks of image pixels (N = 16*C_out columns =
+// the block's pre-activations), so that the output non-linearity, the squared error, its
+// derivative and the per-row loss partial are all lane-local in the epilogue
+// (models/dataset_models.py:68-69,161-163; models/gan.py:411-414).
+enum TcEpilogue : int { EPI_FINAL_SIGMOID1 = 8, EPI_FINAL_TANH3 = 9 };
+
+struct TcFinalArgs {
+  const float* x;        // [B][H*W*C] target images (NULL: forward only)
+  float* y;              // [n_pad][H*W*C] G(z)
+  float* loss_part;      // [n_pad][n_blocks] sum over the block of (y-x)^2
+  int R, B, n_rows;      // restarts per image, images, valid latent rows
+  int nbx, w_out;        // blocks per image row, image width
+  float gscale;          // fp16 gradient scaling applied to dL/dpre
+};
+
+template <int C_OUT, int ACT>
+__device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalArgs& fa, const float* __restrict__ bias,
+                                                  int blk, int n, int n_pad, __half* __restrict__ dblk) {
+  constexpr int NV = 16 * C_OUT;
+  float v[NV];
+#pragma unroll
+  for (int c = 0; c < NV; c += 16) {
+    uint32_t r[16];
+    ptx::tmem_ld16(taddr + c, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[c + j] = __uint_as_float(r[j]);
+  }
+  const int by = blk / fa.nbx, bx = blk % fa.nbx;
+  const int hwc = fa.w_out * fa.w_out * C_OUT;
+  const int img = min(n / fa.R, fa.B - 1);
+  float bsv[C_OUT];
+#pragma unroll
+  for (int co = 0; co < C_OUT; ++co) bsv[co] = __ldg(bias + co);
+  float lsum = 0.f;
+  uint32_t packed[32];   // 64 fp16 of this row of the block tensor (zero padded)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) packed[j] = 0u;
+#pragma unroll
+  for (int li = 0; li < 4; ++li) {
+    const size_t off = (size_t)((4 * by + li) * fa.w_out + 4 * bx) * C_OUT;
+    float xv[4 * C_OUT], yv[4 * C_OUT], dv[4 * C_OUT];
+    if (fa.x != nullptr) {
+#pragma unroll
+      for (int e4 = 0; e4 < C_OUT; ++e4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(fa.x + (size_t)img * hwc + off) + e4);
+        xv[e4 * 4 + 0] = t.x; xv[e4 * 4 + 1] = t.y; xv[e4 * 4 + 2] = t.z; xv[e4 * 4 + 3] = t.w;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4 * C_OUT; ++e) {
+      const float pre = v[li * 4 * C_OUT + e] + bsv[e % C_OUT];
+      float yy, dact;
+      if (ACT == ACT_SIGMOID) { yy = 1.f / (1.f + expf(-pre)); dact = yy * (1.f - yy); }
+      else { yy = tanhf(pre); dact = 1.f - yy * yy; }
+      yv[e] = yy;
+      float d = 0.f;
+      if (fa.x != nullptr) { d = yy - xv[e]; lsum = fmaf(d, d, lsum); }
+      dv[e] = d * dact * fa.gscale;
+    }
+    float4* yp = reinterpret_cast<float4*>(fa.y + (size_t)n * hwc + off);
+#pragma unroll
+    for (int e4 = 0; e4 < C_OUT; ++e4) yp[e4] = make_float4(yv[e4 * 4], yv[e4 * 4 + 1], yv[e4 * 4 + 2], yv[e4 * 4 + 3]);
+#pragma unroll
+    for (int e2 = 0; e2 < 2 * C_OUT; ++e2) packed[li * 2 * C_OUT + e2] = pack_half2(dv[2 * e2], dv[2 * e2 + 1]);
+  }
+  if (fa.x != nullptr) {
+    uint4* dp = reinterpret_cast<uint4*>(dblk + ((size_t)blk * n_pad + n) * 64);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) dp[j4] = make_uint4(packed[j4 * 4], packed[j4 * 4 + 1], packed[j4 * 4 + 2], packed[j4 * 4 + 3]);
+    fa.loss_part[(size_t)n * (fa.nbx * fa.nbx) + blk] = lsum;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -158,8 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_bsgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const TcItem* __restrict__ items, const TcStep* __restrict__ steps, int n_windows, int n_mtiles,
                  TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
-                 const __half* __restrict__ mask_src, float out_scale) {
+                 const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
   constexpr int B_BYTES = N_TILE * 128;
+  constexpr int ACC_STRIDE = N_TILE < 64 ? 64 : N_TILE;   // TMEM columns between accumulators
   static_assert(TC_A_BYTES + TC_MAXB * 64 * 128 <= TC_STAGE_BYTES, "stage too small");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -255,7 +340,7 @@ tc_bsgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               const int acc = (tb0 >> (8 * b + 5)) & 0x7;
               const uint32_t first = (w1 >> b) & 1u;
               const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES + b * B_BYTES);
-              const uint32_t d = tmem_base + acc * N_TILE;
+              const uint32_t d = tmem_base + acc * ACC_STRIDE;
 #pragma unroll
               for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 64-wide swizzle atom: +32 bytes each
                 ptx::umma_f16(d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (k > 0 || !first) ? 1u : 0u);
@@ -279,49 +364,59 @@ tc_bsgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int n_acc = (int)ip->n_acc;
       ptx::mbar_wait(bar_acc_full, item_count & 1);
       ptx::tc_fence_after();
+      if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
+        for (int a = 0; a < n_acc; ++a) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * ACC_STRIDE);
+          if (EPI == EPI_FINAL_SIGMOID1)
+            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out));
+          else
+            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out));
+        }
+      } else {
       for (int a = 0; a < n_acc; ++a) {
-        const int q = ip->q[a];
-        const size_t orow = ((size_t)q * n_pad + (size_t)m * kRowTile + row) * N_TILE;
+          const int q = ip->q[a];
+          const size_t orow = ((size_t)q * n_pad + (size_t)m * kRowTile + row) * N_TILE;
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * N_TILE + c0), r);
-          ptx::tmem_ld_wait();
-          float v[32];
+          for (int c0 = 0; c0 + 32 <= N_TILE; c0 += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * ACC_STRIDE + c0), r);
+            ptx::tmem_ld_wait();
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
-          if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
-            const float* bp = bias + (size_t)q * bias_pstride + c0;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
+            if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
+              const float* bp = bias + (size_t)q * bias_pstride + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] += __ldg(bp + j);
-              if (EPI == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
-            }
-          }
-          if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
-            const uint4* mp = reinterpret_cast<const uint4*>(mask_src + orow + c0);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const uint4 mv = __ldg(mp + j4);
-              const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
-                if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
-                if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
+              for (int j = 0; j < 32; ++j) {
+                v[j] += __ldg(bp + j);
+                if (EPI == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
               }
             }
-          }
-          if (sizeof(TOUT) == 2) {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
+            if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
+              const uint4* mp = reinterpret_cast<const uint4*>(mask_src + orow + c0);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-              op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
-                                  pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
-          } else {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 mv = __ldg(mp + j4);
+                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
+                  if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
+                  if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
+                }
+              }
+            }
+            if (sizeof(TOUT) == 2) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
+                                    pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
+            } else {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            }
           }
         }
       }
@@ -385,8 +480,9 @@ static int tc_make_map(const TcState& st, CUtensorMap* map, const void* base, ui
 // h_grid x w_grid raster (1 x P for the Linear directions); windows are 2x2 (4 accumulators),
 // 1x2 (2) or single pixels depending on how many N-wide accumulators fit in 256 TMEM columns.
 static void tc_build_schedule(const PairTable& tab, int h_grid, int w_grid, int N, int K, std::vector<TcItem>* items,
-                              std::vector<TcStep>* steps) {
-  const int max_acc = std::max(1, std::min(4, TC_TMEM_COLS / N));
+                              std::vector<TcStep>* steps, int force_max_acc = 0) {
+  int max_acc = std::max(1, std::min(4, TC_TMEM_COLS / std::max(N, 64)));
+  if (force_max_acc > 0) max_acc = std::min(max_acc, force_max_acc);
   const int wh = (max_acc >= 4) ? 2 : 1, ww = (max_acc >= 2) ? 2 : 1;
   const int kch = K / 64;
   for (int y0 = 0; y0 < h_grid; y0 += wh)
@@ -450,20 +546,115 @@ static int tc_upload(std::vector<void*>* allocs, const void* host, size_t bytes,
 }
 
 static int tc_build_direction(TcState& st, TcWeights* w, const PairTable& tab, int h_grid, int w_grid, int N, int K,
-                              int n_tiles, int P_in, int P_out, std::vector<void*>* allocs, cudaStream_t s) {
-  if (N != 64 && N != 128 && N != 256) { set_error("tensor-core path needs 64/128/256 output channels per pixel"); return DGAN_ERR_UNSUPPORTED; }
+                              int n_tiles, int P_in, int P_out, std::vector<void*>* allocs, cudaStream_t s,
+                              int force_max_acc) {
+  if (N != 16 && N != 48 && N != 64 && N != 128 && N != 256) { set_error("tensor-core path needs 64/128/256 output channels per pixel"); return DGAN_ERR_UNSUPPORTED; }
   if (K % 64 != 0) { set_error("tensor-core path needs input channels in multiples of 64"); return DGAN_ERR_UNSUPPORTED; }
   if (n_tiles > 32 || P_in > 65535 || P_out > 65535) { set_error("tensor-core schedule limits exceeded"); return DGAN_ERR_UNSUPPORTED; }
   w->N = N; w->K = K; w->P_in = P_in; w->P_out = P_out; w->n_tiles = n_tiles;
   std::vector<TcItem> items;
   std::vector<TcStep> steps;
-  tc_build_schedule(tab, h_grid, w_grid, N, K, &items, &steps);
+  tc_build_schedule(tab, h_grid, w_grid, N, K, &items, &steps, force_max_acc);
   w->n_windows = (int)items.size();
   w->n_steps_total = (int)steps.size();
   int rc;
   if ((rc = tc_upload(allocs, items.data(), items.size() * sizeof(TcItem), (void**)&w->items, s))) return rc;
   if ((rc = tc_upload(allocs, steps.data(), steps.size() * sizeof(TcStep), (void**)&w->steps, s))) return rc;
   return tc_make_map(st, &w->tm_b, w->w, (uint64_t)K, (uint64_t)N, (uint64_t)n_tiles, (uint32_t)N);
+}
+
+
+// ---- the generator's last layer as block GEMMs ---------------------------------------------
+// Image pixels are grouped into 4x4 blocks; block (by,bx) receives from the 4x4 input pixels
+// o = 2by-1+ry, p = 2bx-1+rx (ry,rx in 0..3): out row 4by+li = 2o+ka-1  =>  ka = li - 2ry + 3.
+// Weight tile (ry,rx), forward:  rows (li*4+lj)*C_out+co, cols ci   = F[ka][kb][co][ci] or 0
+//                      backward: rows ci, cols (li*4+lj)*C_out+co (zero padded to 64)
+__global__ void tc_final_tiles_kernel(const float* __restrict__ F /*[25][C_out][C_in]*/, int C_out, int C_in,
+                                      __half* __restrict__ wf /*[16][16*C_out][C_in]*/,
+                                      __half* __restrict__ wb /*[16][C_in][64]*/) {
+  const int tile = blockIdx.x, ry = tile >> 2, rx = tile & 3;
+  const int nrow = 16 * C_out;
+  for (int e = threadIdx.x; e < nrow * C_in; e += blockDim.x) {
+    const int r = e / C_in, ci = e % C_in;
+    const int co = r % C_out, l = r / C_out, li = l >> 2, lj = l & 3;
+    const int ka = li - 2 * ry + 3, kb = lj - 2 * rx + 3;
+    float v = 0.f;
+    if (ka >= 0 && ka < 5 && kb >= 0 && kb < 5) v = F[((size_t)(ka * 5 + kb) * C_out + co) * C_in + ci];
+    wf[((size_t)tile * nrow + r) * C_in + ci] = __float2half_rn(v);
+  }
+  for (int e = threadIdx.x; e < C_in * 64; e += blockDim.x) {
+    const int ci = e / 64, k = e % 64;
+    float v = 0.f;
+    if (k < nrow) {
+      const int co = k % C_out, l = k / C_out, li = l >> 2, lj = l & 3;
+      const int ka = li - 2 * ry + 3, kb = lj - 2 * rx + 3;
+      if (ka >= 0 && ka < 5 && kb >= 0 && kb < 5) v = F[((size_t)(ka * 5 + kb) * C_out + co) * C_in + ci];
+    }
+    wb[((size_t)tile * C_in + ci) * 64 + k] = __float2half_rn(v);
+  }
+}
+
+static PairTable final_block_fwd_pairs(int h_in, int w_in) {
+  PairTable t;
+  t.off.push_back(0);
+  const int nby = h_in / 2, nbx = w_in / 2;   // (2*h_in)/4 blocks per side
+  for (int by = 0; by < nby; ++by)
+    for (int bx = 0; bx < nbx; ++bx) {
+      for (int ry = 0; ry < 4; ++ry)
+        for (int rx = 0; rx < 4; ++rx) {
+          const int o = 2 * by - 1 + ry, p = 2 * bx - 1 + rx;
+          if (o < 0 || o >= h_in || p < 0 || p >= w_in) continue;
+          t.pairs.push_back(make_int2(o * w_in + p, ry * 4 + rx));
+        }
+      t.off.push_back((int)t.pairs.size());
+    }
+  return t;
+}
+
+static PairTable final_block_bwd_pairs(int h_in, int w_in) {
+  PairTable t;
+  t.off.push_back(0);
+  const int nby = h_in / 2, nbx = w_in / 2;
+  for (int o = 0; o < h_in; ++o)
+    for (int p = 0; p < w_in; ++p) {
+      for (int by = 0; by < nby; ++by) {
+        const int ry = o - 2 * by + 1;
+        if (ry < 0 || ry > 3) continue;
+        for (int bx = 0; bx < nbx; ++bx) {
+          const int rx = p - 2 * bx + 1;
+          if (rx < 0 || rx > 3) continue;
+          t.pairs.push_back(make_int2(by * nbx + bx, ry * 4 + rx));
+        }
+      }
+      t.off.push_back((int)t.pairs.size());
+    }
+  return t;
+}
+
+struct TcFinal {
+  TcWeights f, b;
+  int n_blocks = 0, nbx = 0, w_out = 0, C_out = 0, act = 0;
+};
+
+static int tc_build_direction(TcState& st, TcWeights* w, const PairTable& tab, int h_grid, int w_grid, int N, int K,
+                              int n_tiles, int P_in, int P_out, std::vector<void*>* allocs, cudaStream_t s,
+                              int force_max_acc = 0);
+
+static int tc_build_final(TcState& st, TcFinal* tf, const float* F, int h_in, int w_in, int C_in, int C_out, int act,
+                          std::vector<void*>* allocs, cudaStream_t s) {
+  if (C_in != 64) { set_error("tensor-core final layer needs net_dim == 64"); return DGAN_ERR_UNSUPPORTED; }
+  if ((h_in % 2) || (w_in % 2) || h_in != w_in) { set_error("final layer geometry unsupported"); return DGAN_ERR_UNSUPPORTED; }
+  tf->C_out = C_out; tf->act = act; tf->nbx = w_in / 2; tf->n_blocks = (h_in / 2) * (w_in / 2); tf->w_out = 2 * w_in;
+  const int nrow = 16 * C_out;
+  DGAN_CUDA_CHECK(cudaMalloc((void**)&tf->f.w, (size_t)16 * nrow * C_in * 2)); allocs->push_back(tf->f.w);
+  DGAN_CUDA_CHECK(cudaMalloc((void**)&tf->b.w, (size_t)16 * C_in * 64 * 2)); allocs->push_back(tf->b.w);
+  tc_final_tiles_kernel<<<16, 256, 0, s>>>(F, C_out, C_in, tf->f.w, tf->b.w);
+  DGAN_CUDA_CHECK(cudaGetLastError());
+  int rc;
+  const PairTable ft = final_block_fwd_pairs(h_in, w_in), bt = final_block_bwd_pairs(h_in, w_in);
+  if ((rc = tc_build_direction(st, &tf->f, ft, h_in / 2, w_in / 2, nrow, C_in, 16, h_in * w_in, tf->n_blocks, allocs, s))) return rc;
+  if ((rc = tc_build_direction(st, &tf->b, bt, h_in, w_in, C_in, 64, 16, tf->n_blocks, h_in * w_in, allocs, s))) return rc;
+  return 0;
 }
 
 static int tc_build(TcState& st, std::vector<TcLayerSpec>& specs, int latent, std::vector<void*>* allocs, cudaStream_t s) {
@@ -501,8 +692,21 @@ static int tc_build(TcState& st, std::vector<TcLayerSpec>& specs, int latent, st
                                  sp.P_out, allocs, s)))
       return rc;
     // backward: outputs on the h_in x w_in raster; N = C_in, K = C_out
-    if ((rc = tc_build_direction(st, sp.out_b, *sp.bwd, sp.h_in, sp.w_in, sp.C_in, sp.C_out, n_tiles, sp.P_out,
-                                 sp.P_in, allocs, s)))
+    if (linear) {
+      // dz = sum over the 16 pixels: split the sum into TC_LINEAR_SPLIT partial outputs (more CTAs;
+      // the z update adds the partials in a fixed order)
+      PairTable split;
+      split.off.push_back(0);
+      const int per = sp.P_out / TC_LINEAR_SPLIT;
+      for (int part = 0; part < TC_LINEAR_SPLIT; ++part) {
+        for (int q = part * per; q < (part + 1) * per; ++q) split.pairs.push_back(make_int2(q, q));
+        split.off.push_back((int)split.pairs.size());
+      }
+      if ((rc = tc_build_direction(st, sp.out_b, split, 1, TC_LINEAR_SPLIT, sp.C_in, sp.C_out, n_tiles, sp.P_out,
+                                   TC_LINEAR_SPLIT, allocs, s, /*force_max_acc=*/1)))
+        return rc;
+    } else if ((rc = tc_build_direction(st, sp.out_b, *sp.bwd, sp.h_in, sp.w_in, sp.C_in, sp.C_out, n_tiles, sp.P_out,
+                                        sp.P_in, allocs, s)))
       return rc;
   }
 #define TC_OPTIN(NT, EP, T) \
@@ -512,13 +716,17 @@ static int tc_build(TcState& st, std::vector<TcLayerSpec>& specs, int latent, st
   TC_OPTIN(64, EPI_MASK, __half); TC_OPTIN(128, EPI_MASK, __half); TC_OPTIN(256, EPI_MASK, __half);
   TC_OPTIN(64, EPI_NONE, __half); TC_OPTIN(128, EPI_NONE, __half); TC_OPTIN(256, EPI_NONE, __half);
   TC_OPTIN(64, EPI_NONE, float); TC_OPTIN(128, EPI_NONE, float); TC_OPTIN(256, EPI_NONE, float);
+  TC_OPTIN(16, EPI_FINAL_SIGMOID1, __half); TC_OPTIN(48, EPI_FINAL_TANH3, __half);
 #undef TC_OPTIN
   return 0;
 }
 
 template <typename TOUT>
 static int tc_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const __half* in, TOUT* out, int n_pad,
-                          int epi, const float* bias, const __half* mask_src, float out_scale, cudaStream_t s) {
+                          int epi, const float* bias, const __half* mask_src, float out_scale, cudaStream_t s,
+                          const TcFinalArgs* final_args = nullptr) {
+  TcFinalArgs fa{};
+  if (final_args) fa = *final_args;
   CUtensorMap tm_a;
   int rc;
   if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
@@ -528,7 +736,11 @@ static int tc_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, co
 #define TC_GO(NT, EP)                                                                                              \
   tc_bsgemm_kernel<NT, EP, TOUT><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_a, w.tm_b, w.items, w.steps, w.n_windows, \
                                                                          n_mtiles, out, n_pad, bias, w.bias_pstride, \
-                                                                         mask_src, out_scale)
+                                                                         mask_src, out_scale, fa)
+#define TC_GO_FINAL(NT, EP)                                                                                             \
+  tc_bsgemm_kernel<NT, EP, __half><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_a, w.tm_b, w.items, w.steps, w.n_windows, \
+                                                                           n_mtiles, reinterpret_cast<__half*>(out),  \
+                                                                           n_pad, bias, 0, mask_src, out_scale, fa)
 #define TC_BY_N(EP)                                         \
   do {                                                      \
     if (w.N == 64) TC_GO(64, EP);                           \
@@ -536,12 +748,15 @@ static int tc_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, co
     else TC_GO(256, EP);                                    \
   } while (0)
   if (sizeof(TOUT) == 4) { TC_BY_N(EPI_NONE); }
+  else if (epi == EPI_FINAL_SIGMOID1) { if (sizeof(TOUT) == 2) TC_GO_FINAL(16, EPI_FINAL_SIGMOID1); }
+  else if (epi == EPI_FINAL_TANH3) { if (sizeof(TOUT) == 2) TC_GO_FINAL(48, EPI_FINAL_TANH3); }
   else if (epi == EPI_BIAS_RELU) { TC_BY_N(EPI_BIAS_RELU); }
   else if (epi == EPI_BIAS) { TC_BY_N(EPI_BIAS); }
   else if (epi == EPI_MASK) { TC_BY_N(EPI_MASK); }
   else { TC_BY_N(EPI_NONE); }
 #undef TC_BY_N
 #undef TC_GO
+#undef TC_GO_FINAL
   (*launches)++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("tc_bsgemm launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
@@ -551,6 +766,11 @@ static int tc_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, co
 static int tc_launch(TcState& st, int64_t* launches, const TcWeights& w, const __half* in, __half* out, int n_pad, int epi,
                      const float* bias, const __half* mask_src, float out_scale, cudaStream_t s) {
   return tc_launch_impl<__half>(st, launches, w, in, out, n_pad, epi, bias, mask_src, out_scale, s);
+}
+static int tc_launch_final_fwd(TcState& st, int64_t* launches, const TcFinal& tf, const __half* in, __half* dblk, int n_pad,
+                               const float* bias, const TcFinalArgs& fa, cudaStream_t s) {
+  return tc_launch_impl<__half>(st, launches, tf.f, in, dblk, n_pad, tf.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3,
+                                bias, nullptr, 1.f, s, &fa);
 }
 static int tc_launch_f32out(TcState& st, int64_t* launches, const TcWeights& w, const __half* in, float* out, int n_pad,
                             cudaStream_t s) {
