@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc2.cuh"
 
 namespace dgan {
 
@@ -101,6 +102,7 @@ struct GemmLayer {
   int bias_pstride = 0;            // Linear: bias is per flat feature f = pixel*C_out + c
   // fp16 K-major tiles for the tensor-core path (kernels_tc.cuh): [tile][N rows][K cols]
   TcWeights tc_f, tc_b;
+  TcWeights2 tc2_f, tc2_b;
 };
 
 struct FinalLayer {
@@ -126,6 +128,7 @@ struct dgan_ctx {
   int64_t launches = 0;
   TcState tc;
   TcFinal tc_fin;
+  TcWeights2 tc2_fin_f, tc2_fin_b;
   // optional per-launch CUDA-event timing (dgan_profile_*): serialises nothing by itself but
   // adds two event records per launch, so it is never enabled in a timed benchmark pass
   bool profile = false;
@@ -211,7 +214,7 @@ struct Workspace {
 static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   Workspace w;
   w.n_rows = n_rows;
-  w.n_pad = (int)align_up((size_t)std::max(n_rows, 1), kRowTile);
+  w.n_pad = (int)align_up((size_t)std::max(n_rows, 1), c->desc.precision == DGAN_PREC_FP16 ? 2 * kRowTile : kRowTile);
   size_t off = 0;
   char* b = (char*)base;
   auto take = [&](size_t bytes) -> void* {
@@ -321,6 +324,9 @@ static int launch_final_bwd(dgan_ctx* c, const Workspace& w, const TOUT* mask_sr
   return 0;
 }
 
+static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
+                      int epi, const float* bias, const __half* mask_src, cudaStream_t s);
+
 // ---- one generator forward (+ loss and dL/dpre when x != null) ---------------------------
 static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, int B, bool want_grad,
                        cudaStream_t s) {
@@ -331,8 +337,7 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     for (int l = 0; l < nl; ++l) {
       const GemmLayer& L = c->layers[l];
       ProfScope ps(c, 2 * l, s);
-      if ((rc = tc_launch(c->tc, &c->launches, L.tc_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS,
-                          L.bias, nullptr, 1.f, s)))
+      if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, nullptr, s)))
         return rc;
       in = w.act_h[l];
     }
@@ -340,6 +345,9 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     TcFinalArgs fa{};
     fa.x = x; fa.y = w.y; fa.loss_part = w.loss_part; fa.R = R; fa.B = B; fa.n_rows = w.n_rows;
     fa.nbx = c->tc_fin.nbx; fa.w_out = c->tc_fin.w_out; fa.gscale = c->tc.grad_scale;
+    if (c->tc.mode == 2)
+      return tc2_launch_impl<__half>(c->tc, &c->launches, c->tc_fin.f, c->tc2_fin_f, in, w.dblk, w.n_pad,
+                                     c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, c->fin.bias, nullptr, 1.f, s, &fa);
     return tc_launch_final_fwd(c->tc, &c->launches, c->tc_fin, in, w.dblk, w.n_pad, c->fin.bias, fa, s);
   }
   const float* in = w.z;
@@ -363,20 +371,22 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s) {
     const GemmLayer& last = c->layers[nl - 1];
     {
       ProfScope ps(c, 2 * nl + 1, s);
-      if ((rc = tc_launch(c->tc, &c->launches, c->tc_fin.b, w.dblk, w.dact_h[nl - 1], w.n_pad,
-                          last.relu ? EPI_MASK : EPI_NONE, nullptr, last.relu ? w.act_h[nl - 1] : nullptr, 1.f, s)))
+      if ((rc = tcx_launch(c, c->tc_fin.b, c->tc2_fin_b, w.dblk, w.dact_h[nl - 1], w.n_pad, last.relu ? EPI_MASK : EPI_NONE,
+                           nullptr, last.relu ? w.act_h[nl - 1] : nullptr, s)))
         return rc;
     }
     for (int l = nl - 1; l >= 1; --l) {
       const GemmLayer& L = c->layers[l];
       const bool mask = c->layers[l - 1].relu;
       ProfScope ps(c, 2 * l + 1, s);
-      if ((rc = tc_launch(c->tc, &c->launches, L.tc_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad,
-                          mask ? EPI_MASK : EPI_NONE, nullptr, mask ? w.act_h[l - 1] : nullptr, 1.f, s)))
+      if ((rc = tcx_launch(c, L.tc_b, L.tc2_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad, mask ? EPI_MASK : EPI_NONE, nullptr,
+                           mask ? w.act_h[l - 1] : nullptr, s)))
         return rc;
     }
     const GemmLayer& L0 = c->layers[0];
     ProfScope ps(c, 1, s);
+    if (c->tc.mode == 2)
+      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s);
     return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
   }
   const GemmLayer& last = c->layers[nl - 1];
@@ -416,6 +426,13 @@ static int check_ws(const dgan_ctx* c, int n_rows, void* ws, size_t ws_bytes, Wo
     return DGAN_ERR_WORKSPACE;
   }
   return 0;
+}
+
+// tensor-core launch, dispatching on the kernel generation
+static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
+                      int epi, const float* bias, const __half* mask_src, cudaStream_t s) {
+  if (c->tc.mode == 2) return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, mask_src, 1.f, s);
+  return tc_launch(c->tc, &c->launches, w1, in, out, n_pad, epi, bias, mask_src, 1.f, s);
 }
 
 static float grad_multiplier(const dgan_ctx* c) {
@@ -555,6 +572,29 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     if ((rc = tc_build_final(c->tc, &c->tc_fin, c->fin.w, c->fin.h_in, c->fin.w_in, c->fin.C_in, c->fin.C_out,
                              c->fin.act, &c->allocs, s)))
       return fail(rc);
+    const char* mode_env = getenv("DGAN_TC_MODE");
+    c->tc.mode = (mode_env && mode_env[0] == '1') ? 1 : 2;
+    if (getenv("DGAN_TC_DEBUG")) {   // developer aid: per-CTA role timing of the first launches (tools/tc_timing.py)
+      c->tc.dbg_max_launches = 64;
+      if ((rc = dev_alloc(c.get(), (void**)&c->tc.dbg, (size_t)64 * 160 * 8 * sizeof(unsigned long long)))) return fail(rc);
+      DGAN_CUDA_CHECK(cudaMemsetAsync(c->tc.dbg, 0, (size_t)64 * 160 * 8 * sizeof(unsigned long long), s));
+    }
+    if (c->tc.mode == 2) {
+      if ((rc = tc2_optin_all())) return fail(rc);
+      for (size_t l = 0; l < c->layers.size(); ++l) {
+        GemmLayer& L = c->layers[l];
+        if ((rc = tc2_build_direction(c->tc, L.tc_f, &L.tc2_f, L.fwd_host, L.h_used, L.w_used, 0, &c->allocs, s))) return fail(rc);
+        if (l == 0) {
+          const PairTable split = linear_split_pairs(L.P_out);
+          if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, split, 1, TC_LINEAR_SPLIT, 1, &c->allocs, s))) return fail(rc);
+        } else if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, L.bwd_host, L.h_in, L.w_in, 0, &c->allocs, s))) {
+          return fail(rc);
+        }
+      }
+      const PairTable ft = final_block_fwd_pairs(c->fin.h_in, c->fin.w_in), bt = final_block_bwd_pairs(c->fin.h_in, c->fin.w_in);
+      if ((rc = tc2_build_direction(c->tc, c->tc_fin.f, &c->tc2_fin_f, ft, c->fin.h_in / 2, c->fin.w_in / 2, 0, &c->allocs, s))) return fail(rc);
+      if ((rc = tc2_build_direction(c->tc, c->tc_fin.b, &c->tc2_fin_b, bt, c->fin.h_in, c->fin.w_in, 0, &c->allocs, s))) return fail(rc);
+    }
   }
   {
     static const char* lname_m[] = {"Linear", "Generator.2", "Generator.3"};
@@ -700,6 +740,15 @@ int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* lau
   }
   h->prof.clear();
   return DGAN_OK;
+}
+
+/* developer aid (not in the public header): copy the DGAN_TC_DEBUG role-timing counters to the host */
+int dgan_debug_tc_timing(dgan_handle h, unsigned long long* out, int max_launches) {
+  if (h == nullptr || out == nullptr || h->tc.dbg == nullptr) return 0;
+  const int n = std::min(max_launches, h->tc.dbg_launch);
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, h->tc.dbg, (size_t)n * 160 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
 }
 
 }  // extern "C"

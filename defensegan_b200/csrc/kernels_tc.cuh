@@ -53,8 +53,11 @@ struct TcWeights {
 };
 
 struct TcState {
+  int mode = 2;                 // 1 = one CTA per MMA (kernels_tc.cuh), 2 = CTA pairs (kernels_tc2.cuh)
   float grad_scale = 64.f;      // fp16 gradient scaling (undone in the z update)
   void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
+  unsigned long long* dbg = nullptr;   // DGAN_TC_DEBUG=1: [launch][cta][8] role-timing counters
+  int dbg_launch = 0, dbg_max_launches = 0;
   int num_sms = 148;
 };
 
@@ -173,6 +176,7 @@ struct TcFinalArgs {
   int R, B, n_rows;      // restarts per image, images, valid latent rows
   int nbx, w_out;        // blocks per image row, image width
   float gscale;          // fp16 gradient scaling applied to dL/dpre
+  unsigned long long* dbg;  // optional per-CTA role timing (8 counters per CTA), NULL in production
 };
 
 template <int C_OUT, int ACT>
@@ -231,6 +235,112 @@ __device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalA
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) dp[j4] = make_uint4(packed[j4 * 4], packed[j4 * 4 + 1], packed[j4 * 4 + 2], packed[j4 * 4 + 3]);
     fa.loss_part[(size_t)n * (fa.nbx * fa.nbx) + blk] = lsum;
+  }
+}
+
+// One 32-column chunk of an accumulator (already in registers) -> epilogue -> out[q][n][c0..c0+32)
+// ReLU-mask words (32 fp16 = 4 x uint4) of one chunk: loaded one unit ahead of their use
+template <int N_TILE>
+__device__ __forceinline__ void tc_load_mask(uint4 (&mv)[4], const __half* __restrict__ mask_src, int q, int c0, size_t n,
+                                             int n_pad) {
+  const uint4* mp = reinterpret_cast<const uint4*>(mask_src + ((size_t)q * n_pad + n) * N_TILE + c0);
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) mv[j4] = __ldg(mp + j4);
+}
+
+template <int N_TILE, int EPI, typename TOUT>
+__device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], const uint4 (&mv)[4], int q, int c0, size_t n,
+                                               int n_pad, TOUT* __restrict__ out, const float* __restrict__ bias,
+                                               int bias_pstride, float out_scale) {
+  const size_t orow = ((size_t)q * n_pad + n) * N_TILE;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
+  if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
+    const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + c0);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 b = __ldg(bp + j4);
+      v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+    }
+    if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+  }
+  if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const uint32_t mw[4] = {mv[j4].x, mv[j4].y, mv[j4].z, mv[j4].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
+        if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
+        if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
+      }
+    }
+  }
+  if (sizeof(TOUT) == 2) {
+    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4)
+      op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
+                          pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
+  } else {
+    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+  }
+}
+
+// One accumulator (128 lanes x N_TILE fp32 columns at `taddr`) -> bias/ReLU | ReLU-mask | none ->
+// fp16 (or fp32) row of out[q][n][0..N_TILE).  Each thread owns one latent row (TMEM lane).
+template <int N_TILE, int EPI, typename TOUT>
+__device__ __forceinline__ void tc_generic_epilogue(uint32_t taddr, int q, size_t n, int n_pad, TOUT* __restrict__ out,
+                                                    const float* __restrict__ bias, int bias_pstride,
+                                                    const __half* __restrict__ mask_src, float out_scale) {
+  const size_t orow = ((size_t)q * n_pad + n) * N_TILE;
+#pragma unroll 1
+  for (int c0 = 0; c0 + 32 <= N_TILE; c0 += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld32(taddr + (uint32_t)c0, r);
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
+    if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
+      const float* bp = bias + (size_t)q * bias_pstride + c0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] += __ldg(bp + j);
+        if (EPI == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
+      }
+    }
+    if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
+      const uint4* mp = reinterpret_cast<const uint4*>(mask_src + orow + c0);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const uint4 mv = __ldg(mp + j4);
+        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
+          if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
+          if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
+        }
+      }
+    }
+    if (sizeof(TOUT) == 2) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4)
+        op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
+                            pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+    }
   }
 }
 
@@ -373,52 +483,9 @@ tc_bsgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out));
         }
       } else {
-      for (int a = 0; a < n_acc; ++a) {
-          const int q = ip->q[a];
-          const size_t orow = ((size_t)q * n_pad + (size_t)m * kRowTile + row) * N_TILE;
-#pragma unroll 1
-          for (int c0 = 0; c0 + 32 <= N_TILE; c0 += 32) {
-            uint32_t r[32];
-            ptx::tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * ACC_STRIDE + c0), r);
-            ptx::tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
-            if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
-              const float* bp = bias + (size_t)q * bias_pstride + c0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                v[j] += __ldg(bp + j);
-                if (EPI == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
-              }
-            }
-            if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
-              const uint4* mp = reinterpret_cast<const uint4*>(mask_src + orow + c0);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 mv = __ldg(mp + j4);
-                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
-                  if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
-                  if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
-                }
-              }
-            }
-            if (sizeof(TOUT) == 2) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
-                                    pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
-            } else {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-            }
-          }
-        }
+        for (int a = 0; a < n_acc; ++a)
+          tc_generic_epilogue<N_TILE, EPI, TOUT>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * ACC_STRIDE), ip->q[a],
+                                                 (size_t)m * kRowTile + row, n_pad, out, bias, bias_pstride, mask_src, out_scale);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_acc_empty);
@@ -594,6 +661,18 @@ __global__ void tc_final_tiles_kernel(const float* __restrict__ F /*[25][C_out][
   }
 }
 
+// dz = sum over the Linear's 16 output pixels, as TC_LINEAR_SPLIT partial sums
+static PairTable linear_split_pairs(int n_pix) {
+  PairTable split;
+  split.off.push_back(0);
+  const int per = n_pix / TC_LINEAR_SPLIT;
+  for (int part = 0; part < TC_LINEAR_SPLIT; ++part) {
+    for (int q = part * per; q < (part + 1) * per; ++q) split.pairs.push_back(make_int2(q, q));
+    split.off.push_back((int)split.pairs.size());
+  }
+  return split;
+}
+
 static PairTable final_block_fwd_pairs(int h_in, int w_in) {
   PairTable t;
   t.off.push_back(0);
@@ -695,13 +774,7 @@ static int tc_build(TcState& st, std::vector<TcLayerSpec>& specs, int latent, st
     if (linear) {
       // dz = sum over the 16 pixels: split the sum into TC_LINEAR_SPLIT partial outputs (more CTAs;
       // the z update adds the partials in a fixed order)
-      PairTable split;
-      split.off.push_back(0);
-      const int per = sp.P_out / TC_LINEAR_SPLIT;
-      for (int part = 0; part < TC_LINEAR_SPLIT; ++part) {
-        for (int q = part * per; q < (part + 1) * per; ++q) split.pairs.push_back(make_int2(q, q));
-        split.off.push_back((int)split.pairs.size());
-      }
+      const PairTable split = linear_split_pairs(sp.P_out);
       if ((rc = tc_build_direction(st, sp.out_b, split, 1, TC_LINEAR_SPLIT, sp.C_in, sp.C_out, n_tiles, sp.P_out,
                                    TC_LINEAR_SPLIT, allocs, s, /*force_max_acc=*/1)))
         return rc;

@@ -1,0 +1,451 @@
+// Tensor-core path, version 2: CTA-pair (cta_group::2) pixel-graph GEMM.
+//
+// ncu on version 1 (profiles/r1a_*) showed the tcgen05 kernels bound by L2->SM delivery
+// (~7-8 TB/s with the tensor pipe ~29 % busy): every CTA streamed its own copy of every weight
+// tile.  Here two CTAs on the two SMs of a TPC form one MMA of M = 256 latent rows:
+//   * each CTA stages its own 128-row activation tile A and only HALF of each weight tile
+//     (N/2 rows) - the tensor cores read the other half from the peer's shared memory, so
+//     weight traffic per SM is halved;
+//   * one CTA per SM owns all 512 TMEM columns, so a window holds up to 8 accumulators
+//     (2x4 output pixels at N = 64): every staged A tile feeds more MMAs;
+//   * stages are sized per instantiation (A + MAXB half-tiles), 4-8 stages deep.
+// Roles per CTA as in version 1 (TMA producer / MMA issuer / 4 epilogue warps); only the even
+// (leader) CTA issues tcgen05.mma.cta_group::2, commits are multicast to both CTAs, TMA
+// completions of both CTAs land on the leader's "full" barrier (peer-bit mask), and the
+// epilogue warps of both CTAs release the accumulators on the leader's "acc_empty" barrier.
+#pragma once
+#include "kernels_tc.cuh"
+
+namespace dgan {
+
+constexpr int TC2_SMEM_BUDGET = 200 * 1024;
+constexpr int TC2_BUF_COLS = 256;            // TMEM columns per accumulator buffer (2 buffers: MMA i+1 overlaps epilogue i)
+constexpr int TC2_EPI_WARPS = 8;             // two epilogue warps per TMEM lane quarter
+constexpr int TC2_THREADS = 64 + 32 * TC2_EPI_WARPS;
+
+struct __align__(16) TcStep2 {
+  uint32_t w0;       // in pixel [0,16) | k-chunk [16,24) | n_b [24,32)
+  uint32_t w1;       // bit b: first MMA into that accumulator
+  uint32_t pad[2];
+  uint16_t tb[8];    // weight tile id [0,8) | accumulator index [8,16)
+};
+struct __align__(16) TcItem2 {
+  uint16_t q[16];
+  uint32_t n_acc, step_beg, n_steps, pad;
+};
+
+template <int N_TILE>
+struct Tc2Cfg {
+  static constexpr int HALF_B = (N_TILE / 2) * 128;                      // bytes of this CTA's half weight tile
+  static constexpr int ACC_STRIDE = N_TILE < 64 ? 64 : N_TILE;
+  static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (4 / 2 / 1)
+  static constexpr int STAGE_BYTES = ((TC_A_BYTES + MAXB * HALF_B + 1023) / 1024) * 1024;
+  static constexpr int STAGES_RAW = TC2_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+namespace ptx {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load executed by either CTA of the pair into its OWN shared memory; the transaction bytes
+// are credited to the barrier of the even CTA (peer bit cleared).
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar), "r"(cta) : "memory");
+}
+}  // namespace ptx
+
+template <int N_TILE, int EPI, typename TOUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const TcItem2* __restrict__ items, const TcStep2* __restrict__ steps, int n_windows, int n_mpairs,
+                  TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
+                  const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
+  using Cfg = Tc2Cfg<N_TILE>;
+  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
+  const uint32_t tmem_slot = bar_base + 160;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int total_items = n_windows * n_mpairs;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_b);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);    // leader's producer arrive.expect_tx (bytes of both CTAs)
+      ptx::mbar_init(bar_empty + 8 * s, 1);   // one multicast commit per CTA
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar_acc_full + 8 * b, 1);
+      ptx::mbar_init(bar_acc_empty + 8 * b, 2 * TC2_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                     // barriers of BOTH CTAs initialised before any remote signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    // The whole warp walks the step list convergently; every table value is loaded from a
+    // warp-uniform address so the TMA operands live in uniform registers (no per-instruction
+    // R2UR/ELECT loop), and one elected lane issues.
+    uint32_t it = 0;
+    long long t_wait = 0;
+    for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs) {
+      const int win = item_idx / n_mpairs, mp = item_idx % n_mpairs;
+      const TcItem2* ip = items + win;
+      const uint32_t n_steps = ip->n_steps;
+      const uint4* sp = reinterpret_cast<const uint4*>(steps + ip->step_beg);
+      const int row0 = (2 * mp + (int)rank) * kRowTile;
+      uint4 nx0 = __ldg(sp), nx1 = __ldg(sp + 1);
+      for (uint32_t si = 0; si < n_steps; ++si, ++it) {
+        const uint4 c0 = nx0, c1 = nx1;
+        if (si + 1 < n_steps) { nx0 = __ldg(sp + 2 * (si + 1)); nx1 = __ldg(sp + 2 * (si + 1) + 1); }
+        const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1;
+        const int p = c0.x & 0xFFFF, kc = (c0.x >> 16) & 0xFF, nb = (c0.x >> 24) & 0xFF;
+        const uint32_t tbw[4] = {c1.x, c1.y, c1.z, c1.w};
+        const long long tw0 = fa.dbg ? clock64() : 0;
+        ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (fa.dbg) t_wait += clock64() - tw0;
+        const uint32_t full = bar_full + 8 * stage;
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_expect_tx(full, 2u * (uint32_t)(TC_A_BYTES + nb * HALF_B));
+          ptx::tma_load_3d_2sm(sa, &tm_a, full, kc * 64, row0, p);
+          for (int b = 0; b < nb; ++b) {
+            const int tile = (tbw[b >> 1] >> (16 * (b & 1))) & 0xFF;
+            ptx::tma_load_3d_2sm(sa + TC_A_BYTES + b * HALF_B, &tm_b, full, kc * 64, (int)rank * (N_TILE / 2), tile);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (fa.dbg && lane == 0) fa.dbg[blockIdx.x * 8 + 0] = (unsigned long long)t_wait;
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_f16(256, N_TILE);
+      uint32_t it = 0, item_count = 0;
+      long long t_wait_full = 0, t_wait_acc = 0, t_issue = 0;
+      for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs, ++item_count) {
+        const int win = item_idx / n_mpairs;
+        const TcItem2* ip = items + win;
+        const uint32_t n_steps = ip->n_steps;
+        const uint4* sp = reinterpret_cast<const uint4*>(steps + ip->step_beg);
+        const uint32_t buf = item_count & 1;
+        const long long ta0 = fa.dbg ? clock64() : 0;
+        ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);   // both CTAs drained this buffer
+        if (fa.dbg) t_wait_acc += clock64() - ta0;
+        ptx::tc_fence_after();
+        uint4 nx0 = __ldg(sp), nx1 = __ldg(sp + 1);
+        for (uint32_t si = 0; si < n_steps; ++si, ++it) {
+          const uint4 c0 = nx0, c1 = nx1;
+          if (si + 1 < n_steps) { nx0 = __ldg(sp + 2 * (si + 1)); nx1 = __ldg(sp + 2 * (si + 1) + 1); }
+          const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1;
+          const int nb = (c0.x >> 24) & 0xFF;
+          const uint32_t firsts = c0.y;
+          const uint32_t tbw[4] = {c1.x, c1.y, c1.z, c1.w};
+          const long long tf0 = fa.dbg ? clock64() : 0;
+          ptx::mbar_wait(bar_full + 8 * stage, phase);
+          const long long tf1 = fa.dbg ? clock64() : 0;
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          if (ptx::elect_one()) {
+            const uint64_t a_desc = make_smem_desc_sw128(sa);
+            for (int b = 0; b < nb; ++b) {
+              const int acc = (tbw[b >> 1] >> (16 * (b & 1) + 8)) & 0xFF;
+              const uint32_t first = (firsts >> b) & 1u;
+              const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES + b * HALF_B);
+              const uint32_t d = tmem_base + buf * TC2_BUF_COLS + acc * ACC_STRIDE;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_f16_2sm(d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (k > 0 || !first) ? 1u : 0u);
+            }
+            ptx::umma_commit_2sm(bar_empty + 8 * stage);          // frees this stage in both CTAs
+          }
+          __syncwarp();
+          if (fa.dbg) { t_wait_full += tf1 - tf0; t_issue += clock64() - tf1; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit_2sm(bar_acc_full + 8 * buf); // accumulators complete in both CTAs
+        __syncwarp();
+      }
+      if (fa.dbg && lane == 0) {
+        fa.dbg[blockIdx.x * 8 + 1] = (unsigned long long)t_wait_full;
+        fa.dbg[blockIdx.x * 8 + 2] = (unsigned long long)t_wait_acc;
+        fa.dbg[blockIdx.x * 8 + 3] = (unsigned long long)t_issue;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    // Two warps per TMEM lane quarter split the (accumulator, 32-column chunk) units of an item;
+    // the TMEM load of a warp's next unit is in flight while it converts and stores the current one.
+    const int lq = warp & 3;                          // TMEM lanes this warp may access
+    const int half = (warp - 2) >> 2;                 // 0 | 1: which of the two warps of this quarter
+    const int row = lq * 32 + lane;
+    uint32_t item_count = 0;
+    long long t_ewait = 0, t_ework = 0;
+    const long long t_start = fa.dbg ? clock64() : 0;
+    for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs, ++item_count) {
+      const int win = item_idx / n_mpairs, mp = item_idx % n_mpairs;
+      const TcItem2* ip = items + win;
+      const int n_acc = (int)ip->n_acc;
+      const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
+      const uint32_t buf = item_count & 1;
+      const uint32_t tbuf = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * TC2_BUF_COLS;
+      const long long te0 = fa.dbg ? clock64() : 0;
+      ptx::mbar_wait(bar_acc_full + 8 * buf, (item_count >> 1) & 1);
+      const long long te1 = fa.dbg ? clock64() : 0;
+      ptx::tc_fence_after();
+      if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
+        for (int a = half; a < n_acc; a += 2) {
+          const uint32_t taddr = tbuf + (uint32_t)(a * ACC_STRIDE);
+          if (EPI == EPI_FINAL_SIGMOID1)
+            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out));
+          else
+            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out));
+        }
+      } else {
+        constexpr int CH = N_TILE >= 32 ? N_TILE / 32 : 1;     // 32-column chunks per accumulator
+        const int n_units = n_acc * CH;
+        uint32_t rA[32], rB[32];
+        uint4 mA[4], mB[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mA[j] = make_uint4(0, 0, 0, 0); mB[j] = make_uint4(0, 0, 0, 0); }
+        int u = half;
+        if (u < n_units) {
+          ptx::tmem_ld32(tbuf + (uint32_t)((u / CH) * ACC_STRIDE + (u % CH) * 32), rA);
+          if (EPI == EPI_MASK) tc_load_mask<N_TILE>(mA, mask_src, ip->q[u / CH], (u % CH) * 32, n, n_pad);
+        }
+        for (; u < n_units; u += 4) {
+          ptx::tmem_ld_wait();
+          if (u + 2 < n_units) {
+            ptx::tmem_ld32(tbuf + (uint32_t)(((u + 2) / CH) * ACC_STRIDE + ((u + 2) % CH) * 32), rB);
+            if (EPI == EPI_MASK) tc_load_mask<N_TILE>(mB, mask_src, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad);
+          }
+          tc_store_chunk<N_TILE, EPI, TOUT>(rA, mA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale);
+          if (u + 2 < n_units) {
+            ptx::tmem_ld_wait();
+            if (u + 4 < n_units) {
+              ptx::tmem_ld32(tbuf + (uint32_t)(((u + 4) / CH) * ACC_STRIDE + ((u + 4) % CH) * 32), rA);
+              if (EPI == EPI_MASK) tc_load_mask<N_TILE>(mA, mask_src, ip->q[(u + 4) / CH], ((u + 4) % CH) * 32, n, n_pad);
+            }
+            tc_store_chunk<N_TILE, EPI, TOUT>(rB, mB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote(bar_acc_empty + 8 * buf, 0);
+      if (fa.dbg) { t_ewait += te1 - te0; t_ework += clock64() - te1; }
+    }
+    if (fa.dbg && warp == 2 && lane == 0) {
+      fa.dbg[blockIdx.x * 8 + 4] = (unsigned long long)t_ewait;
+      fa.dbg[blockIdx.x * 8 + 5] = (unsigned long long)t_ework;
+      fa.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_start);
+      fa.dbg[blockIdx.x * 8 + 7] = (unsigned long long)item_count;
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();     // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct TcWeights2 {
+  CUtensorMap tm_b;            // box {64, N/2, 1}
+  TcItem2* items = nullptr;
+  TcStep2* steps = nullptr;
+  int n_windows = 0;
+};
+
+static int tc2_maxb(int N) { return TC2_BUF_COLS / std::max(N, 64); }
+
+// windows of up to `max_acc` output pixels: 8 -> 2 rows x 4 cols, 4 -> 2x2, 2 -> 1x2, 1 -> 1x1
+static void tc2_build_schedule(const PairTable& tab, int h_grid, int w_grid, int N, int K, int max_acc,
+                               std::vector<TcItem2>* items, std::vector<TcStep2>* steps) {
+  const int wh = max_acc >= 4 ? 2 : 1;
+  const int ww = max_acc >= 8 ? 4 : (max_acc >= 2 ? 2 : 1);
+  const int kch = K / 64;
+  const size_t maxb = (size_t)tc2_maxb(N);
+  for (int y0 = 0; y0 < h_grid; y0 += wh)
+    for (int x0 = 0; x0 < w_grid; x0 += ww) {
+      TcItem2 item{};
+      std::vector<int> qs;
+      for (int dy = 0; dy < wh && y0 + dy < h_grid; ++dy)
+        for (int dx = 0; dx < ww && x0 + dx < w_grid; ++dx) qs.push_back((y0 + dy) * w_grid + x0 + dx);
+      item.n_acc = (uint32_t)qs.size();
+      for (size_t a = 0; a < qs.size(); ++a) item.q[a] = (uint16_t)qs[a];
+      item.step_beg = (uint32_t)steps->size();
+      std::vector<std::pair<int, std::vector<std::pair<int, int>>>> by_p;
+      for (size_t a = 0; a < qs.size(); ++a)
+        for (int e = tab.off[qs[a]]; e < tab.off[qs[a] + 1]; ++e) {
+          const int p = tab.pairs[e].x, t = tab.pairs[e].y;
+          size_t g = 0;
+          for (; g < by_p.size(); ++g)
+            if (by_p[g].first == p) break;
+          if (g == by_p.size()) by_p.push_back({p, {}});
+          by_p[g].second.push_back({t, (int)a});
+        }
+      std::sort(by_p.begin(), by_p.end(), [](const auto& l, const auto& r) { return l.first < r.first; });
+      uint32_t seen = 0;
+      for (auto& g : by_p)
+        for (size_t b0 = 0; b0 < g.second.size(); b0 += maxb) {
+          const size_t nb = std::min(maxb, g.second.size() - b0);
+          for (int kc = 0; kc < kch; ++kc) {
+            TcStep2 s{};
+            s.w0 = (uint32_t)g.first | ((uint32_t)kc << 16) | ((uint32_t)nb << 24);
+            uint32_t firsts = 0;
+            for (size_t b = 0; b < nb; ++b) {
+              const auto& ta = g.second[b0 + b];
+              s.tb[b] = (uint16_t)((ta.first & 0xFF) | (ta.second << 8));
+              if (!(seen & (1u << ta.second))) firsts |= 1u << b;
+            }
+            s.w1 = (kc == 0) ? firsts : 0;
+            steps->push_back(s);
+          }
+          for (size_t b = 0; b < nb; ++b) seen |= 1u << g.second[b0 + b].second;
+        }
+      item.n_steps = (uint32_t)steps->size() - item.step_beg;
+      items->push_back(item);
+    }
+}
+
+static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2, const PairTable& tab, int h_grid,
+                               int w_grid, int force_max_acc, std::vector<void*>* allocs, cudaStream_t s) {
+  const int N = w1.N, K = w1.K;
+  int max_acc = TC2_BUF_COLS / std::max(N, 64);
+  if (force_max_acc > 0) max_acc = std::min(max_acc, force_max_acc);
+  std::vector<TcItem2> items;
+  std::vector<TcStep2> steps;
+  tc2_build_schedule(tab, h_grid, w_grid, N, K, max_acc, &items, &steps);
+  w2->n_windows = (int)items.size();
+  int rc;
+  if ((rc = tc_upload(allocs, items.data(), items.size() * sizeof(TcItem2), (void**)&w2->items, s))) return rc;
+  if ((rc = tc_upload(allocs, steps.data(), steps.size() * sizeof(TcStep2), (void**)&w2->steps, s))) return rc;
+  return tc_make_map(st, &w2->tm_b, w1.w, (uint64_t)K, (uint64_t)N, (uint64_t)w1.n_tiles, (uint32_t)(N / 2));
+}
+
+template <int NT, int EP, typename TOUT>
+static cudaError_t tc2_optin() {
+  return cudaFuncSetAttribute(tc_bsgemm2_kernel<NT, EP, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Tc2Cfg<NT>::SMEM_BYTES);
+}
+
+static int tc2_optin_all() {
+#define TC2_OPTIN(NT, EP, T) DGAN_CUDA_CHECK((tc2_optin<NT, EP, T>()))
+  TC2_OPTIN(64, EPI_BIAS_RELU, __half); TC2_OPTIN(128, EPI_BIAS_RELU, __half); TC2_OPTIN(256, EPI_BIAS_RELU, __half);
+  TC2_OPTIN(64, EPI_BIAS, __half); TC2_OPTIN(128, EPI_BIAS, __half); TC2_OPTIN(256, EPI_BIAS, __half);
+  TC2_OPTIN(64, EPI_MASK, __half); TC2_OPTIN(128, EPI_MASK, __half); TC2_OPTIN(256, EPI_MASK, __half);
+  TC2_OPTIN(64, EPI_NONE, __half); TC2_OPTIN(128, EPI_NONE, __half); TC2_OPTIN(256, EPI_NONE, __half);
+  TC2_OPTIN(64, EPI_NONE, float); TC2_OPTIN(128, EPI_NONE, float); TC2_OPTIN(256, EPI_NONE, float);
+  TC2_OPTIN(16, EPI_FINAL_SIGMOID1, __half); TC2_OPTIN(48, EPI_FINAL_TANH3, __half);
+#undef TC2_OPTIN
+  return 0;
+}
+
+template <typename TOUT>
+static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const TcWeights2& w2, const __half* in,
+                           TOUT* out, int n_pad, int epi, const float* bias, const __half* mask_src, float out_scale,
+                           cudaStream_t s, const TcFinalArgs* final_args = nullptr) {
+  TcFinalArgs fa{};
+  if (final_args) fa = *final_args;
+  fa.dbg = nullptr;
+  if (st.dbg != nullptr && st.dbg_launch < st.dbg_max_launches) fa.dbg = st.dbg + (size_t)(st.dbg_launch++) * 160 * 8;
+  CUtensorMap tm_a;
+  int rc;
+  if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
+  if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
+  const int n_mpairs = n_pad / (2 * kRowTile);
+  const int total = w2.n_windows * n_mpairs;
+  const int grid = 2 * std::min(total, st.num_sms / 2);
+#define TC2_GO(NT, EP)                                                                                                 \
+  tc_bsgemm2_kernel<NT, EP, TOUT><<<grid, TC2_THREADS, Tc2Cfg<NT>::SMEM_BYTES, s>>>(                                    \
+      tm_a, w2.tm_b, w2.items, w2.steps, w2.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+#define TC2_GO_H(NT, EP)                                                                                               \
+  tc_bsgemm2_kernel<NT, EP, __half><<<grid, TC2_THREADS, Tc2Cfg<NT>::SMEM_BYTES, s>>>(                                  \
+      tm_a, w2.tm_b, w2.items, w2.steps, w2.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0,       \
+      mask_src, out_scale, fa)
+#define TC2_BY_N(EP)                    \
+  do {                                  \
+    if (w.N == 64) TC2_GO(64, EP);      \
+    else if (w.N == 128) TC2_GO(128, EP); \
+    else TC2_GO(256, EP);               \
+  } while (0)
+  if (sizeof(TOUT) == 4) { TC2_BY_N(EPI_NONE); }
+  else if (epi == EPI_FINAL_SIGMOID1) { TC2_GO_H(16, EPI_FINAL_SIGMOID1); }
+  else if (epi == EPI_FINAL_TANH3) { TC2_GO_H(48, EPI_FINAL_TANH3); }
+  else if (epi == EPI_BIAS_RELU) { TC2_BY_N(EPI_BIAS_RELU); }
+  else if (epi == EPI_BIAS) { TC2_BY_N(EPI_BIAS); }
+  else if (epi == EPI_MASK) { TC2_BY_N(EPI_MASK); }
+  else { TC2_BY_N(EPI_NONE); }
+#undef TC2_BY_N
+#undef TC2_GO
+#undef TC2_GO_H
+  (*launches)++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("tc_bsgemm2 launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
+  return 0;
+}
+
+}  // namespace dgan

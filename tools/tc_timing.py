@@ -1,0 +1,40 @@
+"""Developer aid: per-role wait/work cycles of the CTA-pair tensor-core kernels (DGAN_TC_DEBUG=1).
+Prints, for each of the first launches of one projection, the mean over CTAs of: producer wait on
+'empty', MMA wait on 'full', MMA wait on 'acc_empty', MMA issue, epilogue wait, epilogue work, total."""
+import ctypes
+import os
+import sys
+
+os.environ["DGAN_TC_DEBUG"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from defensegan_b200.models.gan import dataset_gan_dict
+
+dataset = sys.argv[1] if len(sys.argv) > 1 else "mnist"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+R, L = 10, 2
+gan = dataset_gan_dict[dataset](test_mode=True, verbose=False, precision="fp16", batch_size=50)
+gan.rec_rr, gan.rec_iters = R, L
+g = torch.Generator().manual_seed(0)
+x = torch.rand(B, *gan.image_dim, generator=g).cuda()
+z0 = (torch.randn(B * R, 128, generator=g) * 128 ** -0.5).cuda()
+gan.reconstruct(x, z_init_val=z0)
+torch.cuda.synchronize()
+nat = gan._native
+buf = (ctypes.c_ulonglong * (64 * 160 * 8))()
+nat.lib.dgan_debug_tc_timing.restype = ctypes.c_int
+nat.lib.dgan_debug_tc_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+n = nat.lib.dgan_debug_tc_timing(nat._handle, buf, 64)
+a = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 8)[:n].astype(np.float64)
+names = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "mma_issue", "epi_wait", "epi_work", "total", "items"]
+print("launch | " + " | ".join(names) + "   (mean cycles over active CTAs; MMA columns: leader CTAs only)")
+for i in range(n):
+    act = a[i][:, 6] > 0
+    lead = act & (a[i][:, 3] > 0)
+    row = []
+    for k in range(8):
+        m = lead if k in (1, 2, 3) else act
+        row.append(a[i][m, k].mean() if m.any() else 0.0)
+    print("%2d | " % i + " | ".join("%9.0f" % v for v in row) + " | maxtotal %9.0f" % a[i][:, 6].max())
