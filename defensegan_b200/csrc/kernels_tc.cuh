@@ -57,7 +57,7 @@ struct TcState {
   float grad_scale = 64.f;      // fp16 gradient scaling (undone in the z update)
   void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
   unsigned long long* dbg = nullptr;   // DGAN_TC_DEBUG=1: [launch][cta][8] role-timing counters
-  int dbg_launch = 0, dbg_max_launches = 0;
+  int dbg_launch = 0, dbg_max_launches = 0, dbg_flags = 0;
   int num_sms = 148;
 };
 
@@ -177,6 +177,7 @@ struct TcFinalArgs {
   int nbx, w_out;        // blocks per image row, image width
   float gscale;          // fp16 gradient scaling applied to dL/dpre
   unsigned long long* dbg;  // optional per-CTA role timing (8 counters per CTA), NULL in production
+  int dbg_flags;            // timing experiments only: 1 = skip epilogue stores, 2 = skip mask loads, 4 = skip bias
 };
 
 template <int C_OUT, int ACT>
@@ -251,7 +252,7 @@ __device__ __forceinline__ void tc_load_mask(uint4 (&mv)[4], const __half* __res
 template <int N_TILE, int EPI, typename TOUT>
 __device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], const uint4 (&mv)[4], int q, int c0, size_t n,
                                                int n_pad, TOUT* __restrict__ out, const float* __restrict__ bias,
-                                               int bias_pstride, float out_scale) {
+                                               int bias_pstride, float out_scale, int dbg_flags = 0) {
   const size_t orow = ((size_t)q * n_pad + n) * N_TILE;
   float v[32];
 #pragma unroll
@@ -280,6 +281,7 @@ __device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], const ui
       }
     }
   }
+  if ((dbg_flags & 1) && v[0] != 12345.678f) return;   // timing experiment: no stores
   if (sizeof(TOUT) == 2) {
     uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
 #pragma unroll

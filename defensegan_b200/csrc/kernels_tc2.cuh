@@ -18,7 +18,8 @@
 
 namespace dgan {
 
-constexpr int TC2_SMEM_BUDGET = 200 * 1024;
+constexpr int TC2_SMEM_MAX = 232448;         // 227 KB opt-in limit per CTA
+constexpr int TC2_TILE_BYTES = 128 * 128;    // one 128-row x 64-channel fp16 tile (TMA box, 128B swizzle)
 constexpr int TC2_BUF_COLS = 256;            // TMEM columns per accumulator buffer (2 buffers: MMA i+1 overlaps epilogue i)
 constexpr int TC2_EPI_WARPS = 8;             // two epilogue warps per TMEM lane quarter
 constexpr int TC2_THREADS = 64 + 32 * TC2_EPI_WARPS;
@@ -34,15 +35,23 @@ struct __align__(16) TcItem2 {
   uint32_t n_acc, step_beg, n_steps, pad;
 };
 
-template <int N_TILE>
+// Does this instantiation stage its output (and ReLU-mask) tiles through shared memory + TMA?
+__host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out_bytes) {
+  return out_bytes == 2 && n_tile >= 64 && epi != EPI_FINAL_SIGMOID1 && epi != EPI_FINAL_TANH3;
+}
+
+template <int N_TILE, int EPI = EPI_NONE, int OUT_BYTES = 2>
 struct Tc2Cfg {
   static constexpr int HALF_B = (N_TILE / 2) * 128;                      // bytes of this CTA's half weight tile
   static constexpr int ACC_STRIDE = N_TILE < 64 ? 64 : N_TILE;
   static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (4 / 2 / 1)
   static constexpr int STAGE_BYTES = ((TC_A_BYTES + MAXB * HALF_B + 1023) / 1024) * 1024;
-  static constexpr int STAGES_RAW = TC2_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
+  // epilogue staging: one output tile per epilogue half (+ one mask tile per half for EPI_MASK)
+  static constexpr int EPI_BYTES = TMA_EPI ? (EPI == EPI_MASK ? 4 : 2) * TC2_TILE_BYTES : 0;
+  static constexpr int STAGES_RAW = (TC2_SMEM_MAX - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
 namespace ptx {
@@ -81,6 +90,30 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, u
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_local(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 // true in exactly one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -98,15 +131,19 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 template <int N_TILE, int EPI, typename TOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_mask,
                   const TcItem2* __restrict__ items, const TcStep2* __restrict__ steps, int n_windows, int n_mpairs,
                   TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
                   const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
-  using Cfg = Tc2Cfg<N_TILE>;
+  using Cfg = Tc2Cfg<N_TILE, EPI, (int)sizeof(TOUT)>;
+  constexpr bool TMA_EPI = Cfg::TMA_EPI;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160
+  const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;       // [out tile half0][out tile half1][mask half0][mask half1]
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+  const uint32_t bar_mask = bar_base + 176;                          // mask_full[2]
+  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160, mask_full[2] @ +176
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
   const uint32_t tmem_slot = bar_base + 160;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -127,7 +164,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_acc_full + 8 * b, 1);
       ptx::mbar_init(bar_acc_empty + 8 * b, 2 * TC2_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
+      ptx::mbar_init(bar_mask + 8 * b, 1);
     }
+    if (TMA_EPI) { ptx::prefetch_tmap(&tm_out); if (EPI == EPI_MASK) ptx::prefetch_tmap(&tm_mask); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -238,6 +277,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int half = (warp - 2) >> 2;                 // 0 | 1: which of the two warps of this quarter
     const int row = lq * 32 + lane;
     uint32_t item_count = 0;
+    uint32_t mask_phase = 0;
     long long t_ewait = 0, t_ework = 0;
     const long long t_start = fa.dbg ? clock64() : 0;
     for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs, ++item_count) {
@@ -247,6 +287,14 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
       const uint32_t buf = item_count & 1;
       const uint32_t tbuf = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * TC2_BUF_COLS;
+      if (TMA_EPI && EPI == EPI_MASK) {   // first mask tile of this half: needs nothing from the MMAs, fetch it now
+        constexpr int G0 = N_TILE / 64;
+        if ((warp == 2 + 4 * half) && lane == 0 && half < n_acc * G0) {
+          ptx::mbar_expect_tx(bar_mask + 8 * half, TC2_TILE_BYTES);
+          ptx::tma_load_3d_local(epi_base + (2 + half) * TC2_TILE_BYTES, &tm_mask, bar_mask + 8 * half, (half % G0) * 64,
+                                 (2 * mp + (int)rank) * kRowTile, ip->q[half / G0]);
+        }
+      }
       const long long te0 = fa.dbg ? clock64() : 0;
       ptx::mbar_wait(bar_acc_full + 8 * buf, (item_count >> 1) & 1);
       const long long te1 = fa.dbg ? clock64() : 0;
@@ -259,6 +307,75 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           else
             tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out));
         }
+      } else if (TMA_EPI) {
+        // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 ->
+        //      128B-swizzled smem tile -> one TMA store per 128x64 tile; mask tiles arrive by TMA load.
+        constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
+        const int n_units = n_acc * G;
+        const uint32_t s_out = epi_base + half * TC2_TILE_BYTES;
+        const uint32_t s_mask = epi_base + (2 + half) * TC2_TILE_BYTES;
+        const uint32_t bar_m = bar_mask + 8 * half;
+        const bool t0 = (warp == 2 + 4 * half) && lane == 0;  // issues this half's bulk copies
+        const int row0 = (2 * mp + (int)rank) * kRowTile;
+        const uint32_t swz = (uint32_t)(row & 7);
+        for (int u = half; u < n_units; u += 2) {
+          const int a = u / G, g = u % G, q = ip->q[a];
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64), r0);
+          ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64 + 32), r1);
+          ptx::tmem_ld_wait();
+          uint32_t pk[32];
+          {
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]) * out_scale; v[32 + j] = __uint_as_float(r1[j]) * out_scale; }
+            if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
+              const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + g * 64);
+#pragma unroll
+              for (int j4 = 0; j4 < 16; ++j4) {
+                const float4 b = __ldg(bp + j4);
+                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+              }
+              if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+            }
+            if (EPI == EPI_MASK) {
+              ptx::mbar_wait(bar_m, mask_phase);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 mv = ptx::ld_shared_v4(s_mask + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4));
+                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
+                  if (!(__low2float(h) > 0.f)) v[c * 8 + e * 2] = 0.f;
+                  if (!(__high2float(h) > 0.f)) v[c * 8 + e * 2 + 1] = 0.f;
+                }
+              }
+              mask_phase ^= 1;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pk[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+          }
+          if (t0) ptx::bulk_wait_read0();                  // the previous store has finished reading s_out
+          ptx::named_bar_sync(1 + half, 128);              // s_out free; everybody is done with s_mask
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::st_shared_v4(s_out + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1 + half, 128);              // tile complete
+          if (t0) {
+            ptx::tma_store_3d(&tm_out, s_out, g * 64, row0, q);
+            ptx::bulk_commit();
+            if (EPI == EPI_MASK && u + 2 < n_units) {      // mask tile of this half's next unit
+              const int a2 = (u + 2) / G, g2 = (u + 2) % G;
+              ptx::mbar_expect_tx(bar_m, TC2_TILE_BYTES);
+              ptx::tma_load_3d_local(s_mask, &tm_mask, bar_m, g2 * 64, row0, ip->q[a2]);
+            }
+          }
+        }
       } else {
         constexpr int CH = N_TILE >= 32 ? N_TILE / 32 : 1;     // 32-column chunks per accumulator
         const int n_units = n_acc * CH;
@@ -269,22 +386,22 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         int u = half;
         if (u < n_units) {
           ptx::tmem_ld32(tbuf + (uint32_t)((u / CH) * ACC_STRIDE + (u % CH) * 32), rA);
-          if (EPI == EPI_MASK) tc_load_mask<N_TILE>(mA, mask_src, ip->q[u / CH], (u % CH) * 32, n, n_pad);
+          if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mA, mask_src, ip->q[u / CH], (u % CH) * 32, n, n_pad);
         }
         for (; u < n_units; u += 4) {
           ptx::tmem_ld_wait();
           if (u + 2 < n_units) {
             ptx::tmem_ld32(tbuf + (uint32_t)(((u + 2) / CH) * ACC_STRIDE + ((u + 2) % CH) * 32), rB);
-            if (EPI == EPI_MASK) tc_load_mask<N_TILE>(mB, mask_src, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad);
+            if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mB, mask_src, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad);
           }
-          tc_store_chunk<N_TILE, EPI, TOUT>(rA, mA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale);
+          tc_store_chunk<N_TILE, EPI, TOUT>(rA, mA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
           if (u + 2 < n_units) {
             ptx::tmem_ld_wait();
             if (u + 4 < n_units) {
               ptx::tmem_ld32(tbuf + (uint32_t)(((u + 4) / CH) * ACC_STRIDE + ((u + 4) % CH) * 32), rA);
-              if (EPI == EPI_MASK) tc_load_mask<N_TILE>(mA, mask_src, ip->q[(u + 4) / CH], ((u + 4) % CH) * 32, n, n_pad);
+              if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mA, mask_src, ip->q[(u + 4) / CH], ((u + 4) % CH) * 32, n, n_pad);
             }
-            tc_store_chunk<N_TILE, EPI, TOUT>(rB, mB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale);
+            tc_store_chunk<N_TILE, EPI, TOUT>(rB, mB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
           }
         }
       }
@@ -293,6 +410,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (lane == 0) ptx::mbar_arrive_remote(bar_acc_empty + 8 * buf, 0);
       if (fa.dbg) { t_ewait += te1 - te0; t_ework += clock64() - te1; }
     }
+    if (TMA_EPI && lane == 0 && (warp == 2 || warp == 6)) ptx::bulk_wait_all0();   // stores landed before exit
     if (fa.dbg && warp == 2 && lane == 0) {
       fa.dbg[blockIdx.x * 8 + 4] = (unsigned long long)t_ewait;
       fa.dbg[blockIdx.x * 8 + 5] = (unsigned long long)t_ework;
@@ -389,7 +507,7 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
 template <int NT, int EP, typename TOUT>
 static cudaError_t tc2_optin() {
   return cudaFuncSetAttribute(tc_bsgemm2_kernel<NT, EP, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              Tc2Cfg<NT>::SMEM_BYTES);
+                              Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES);
 }
 
 static int tc2_optin_all() {
@@ -411,20 +529,26 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   TcFinalArgs fa{};
   if (final_args) fa = *final_args;
   fa.dbg = nullptr;
+  fa.dbg_flags = st.dbg_flags;
   if (st.dbg != nullptr && st.dbg_launch < st.dbg_max_launches) fa.dbg = st.dbg + (size_t)(st.dbg_launch++) * 160 * 8;
   CUtensorMap tm_a;
   int rc;
   if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
+  CUtensorMap tm_out = tm_a, tm_mask = tm_a;     // placeholders when unused
+  if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT))) {
+    if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
+    if (epi == EPI_MASK && (rc = tc_make_map(st, &tm_mask, mask_src, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
+  }
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
   const int n_mpairs = n_pad / (2 * kRowTile);
   const int total = w2.n_windows * n_mpairs;
   const int grid = 2 * std::min(total, st.num_sms / 2);
 #define TC2_GO(NT, EP)                                                                                                 \
-  tc_bsgemm2_kernel<NT, EP, TOUT><<<grid, TC2_THREADS, Tc2Cfg<NT>::SMEM_BYTES, s>>>(                                    \
-      tm_a, w2.tm_b, w2.items, w2.steps, w2.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+  tc_bsgemm2_kernel<NT, EP, TOUT><<<grid, TC2_THREADS, Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s>>>(             \
+      tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
-  tc_bsgemm2_kernel<NT, EP, __half><<<grid, TC2_THREADS, Tc2Cfg<NT>::SMEM_BYTES, s>>>(                                  \
-      tm_a, w2.tm_b, w2.items, w2.steps, w2.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0,       \
+  tc_bsgemm2_kernel<NT, EP, __half><<<grid, TC2_THREADS, Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s>>>(                           \
+      tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0,       \
       mask_src, out_scale, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
