@@ -103,6 +103,7 @@ struct GemmLayer {
   // fp16 K-major tiles for the tensor-core path (kernels_tc.cuh): [tile][N rows][K cols]
   TcWeights tc_f, tc_b;
   TcWeights2 tc2_f, tc2_b;
+  TcWeights2 tc2_b_fused;          // Linear only: un-split dz with the momentum update in the epilogue
 };
 
 struct FinalLayer {
@@ -364,7 +365,11 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
 }
 
 // ---- backward-to-z: w.g = J^T dpre (unscaled by 2/HWC; fp16 path additionally x gscale) -----
-static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s) {
+struct MomentumArgs { bool fused = false; float lr = 0.f, mu = 0.f; };
+
+static float grad_multiplier(const dgan_ctx* c);
+
+static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, MomentumArgs mom = MomentumArgs()) {
   int rc;
   const int nl = (int)c->layers.size();
   if (c->desc.precision == DGAN_PREC_FP16) {
@@ -385,6 +390,12 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s) {
     }
     const GemmLayer& L0 = c->layers[0];
     ProfScope ps(c, 1, s);
+    if (c->tc.mode == 2 && mom.fused) {
+      TcFinalArgs fa{};
+      fa.mz = w.z; fa.mv = w.v; fa.mz_h = w.z_h; fa.m_gmul = grad_multiplier(c); fa.m_lr = mom.lr; fa.m_mu = mom.mu;
+      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b_fused, w.dact_h[0], w.g, w.n_pad, EPI_MOMENTUM, nullptr,
+                                    nullptr, 1.f, s, &fa);
+    }
     if (c->tc.mode == 2)
       return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s);
     return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
@@ -588,6 +599,7 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
         if (l == 0) {
           const PairTable split = linear_split_pairs(L.P_out);
           if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, split, 1, TC_LINEAR_SPLIT, 1, &c->allocs, s))) return fail(rc);
+          if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b_fused, L.bwd_host, 1, 1, 1, &c->allocs, s))) return fail(rc);
         } else if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, L.bwd_host, L.h_in, L.w_in, 0, &c->allocs, s))) {
           return fail(rc);
         }
@@ -692,10 +704,14 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
     // the L-th update is never observed, so its backward pass is not run.
     if ((rc = run_forward(h, w, x_dev, rec_rr, batch, !last, s))) return rc;
     if (last) break;
-    if ((rc = run_backward(h, w, s))) return rc;
     float lr = rec_lr;
     if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
-    {
+    // fused Linear-backward + momentum epilogue exists (EPI_MOMENTUM) but measured slower than split-K + momentum_kernel
+    const bool fused = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 && getenv("DGAN_FUSED_MOMENTUM") != nullptr;
+    MomentumArgs mom;
+    mom.fused = fused; mom.lr = lr; mom.mu = momentum;
+    if ((rc = run_backward(h, w, s, mom))) return rc;
+    if (!fused) {
       ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
       momentum_kernel<<<(unsigned)((zcount + 255) / 256), 256, 0, s>>>(w.z, w.v, w.g, w.n_g_parts, grad_multiplier(h), lr,
                                                                        momentum, zcount, w.z_h);

@@ -167,7 +167,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // the block's pre-activations), so that the output non-linearity, the squared error, its
 // derivative and the per-row loss partial are all lane-local in the epilogue
 // (models/dataset_models.py:68-69,161-163; models/gan.py:411-414).
-enum TcEpilogue : int { EPI_FINAL_SIGMOID1 = 8, EPI_FINAL_TANH3 = 9 };
+enum TcEpilogue : int { EPI_FINAL_SIGMOID1 = 8, EPI_FINAL_TANH3 = 9, EPI_MOMENTUM = 10 };
 
 struct TcFinalArgs {
   const float* x;        // [B][H*W*C] target images (NULL: forward only)
@@ -176,6 +176,9 @@ struct TcFinalArgs {
   int R, B, n_rows;      // restarts per image, images, valid latent rows
   int nbx, w_out;        // blocks per image row, image width
   float gscale;          // fp16 gradient scaling applied to dL/dpre
+  // EPI_MOMENTUM (Linear backward fused with tf.train.MomentumOptimizer, models/gan.py:389-391):
+  float* mz; float* mv; __half* mz_h;   // z, velocity [n_pad][latent] fp32, fp16 copy of z
+  float m_gmul, m_lr, m_mu;             // g = gmul * acc;  v <- mu v + g;  z <- z - lr v
   unsigned long long* dbg;  // optional per-CTA role timing (8 counters per CTA), NULL in production
   int dbg_flags;            // timing experiments only: 1 = skip epilogue stores, 2 = skip mask loads, 4 = skip bias
 };
@@ -236,6 +239,27 @@ __device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalA
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) dp[j4] = make_uint4(packed[j4 * 4], packed[j4 * 4 + 1], packed[j4 * 4 + 2], packed[j4 * 4 + 3]);
     fa.loss_part[(size_t)n * (fa.nbx * fa.nbx) + blk] = lsum;
+  }
+}
+
+// dz chunk (32 latent dims of one row, in registers) -> momentum update of z and v in place
+__device__ __forceinline__ void tc_momentum_chunk(const uint32_t (&r)[32], int c0, size_t n, int latent, const TcFinalArgs& fa) {
+  float4* __restrict__ vp = reinterpret_cast<float4*>(fa.mv + n * latent + c0);
+  float4* __restrict__ zp = reinterpret_cast<float4*>(fa.mz + n * latent + c0);
+  uint2* __restrict__ hp = reinterpret_cast<uint2*>(fa.mz_h + n * latent + c0);
+  float4 vv[8], zz[8];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) { vv[j4] = vp[j4]; zz[j4] = zp[j4]; }   // all loads in flight before any store
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float4 v = vv[j4], z = zz[j4];
+    v.x = fmaf(fa.m_mu, v.x, fa.m_gmul * __uint_as_float(r[j4 * 4 + 0]));
+    v.y = fmaf(fa.m_mu, v.y, fa.m_gmul * __uint_as_float(r[j4 * 4 + 1]));
+    v.z = fmaf(fa.m_mu, v.z, fa.m_gmul * __uint_as_float(r[j4 * 4 + 2]));
+    v.w = fmaf(fa.m_mu, v.w, fa.m_gmul * __uint_as_float(r[j4 * 4 + 3]));
+    z.x -= fa.m_lr * v.x; z.y -= fa.m_lr * v.y; z.z -= fa.m_lr * v.z; z.w -= fa.m_lr * v.w;
+    vp[j4] = v; zp[j4] = z;
+    hp[j4] = make_uint2(pack_half2(z.x, z.y), pack_half2(z.z, z.w));
   }
 }
 

@@ -394,14 +394,16 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             ptx::tmem_ld32(tbuf + (uint32_t)(((u + 2) / CH) * ACC_STRIDE + ((u + 2) % CH) * 32), rB);
             if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mB, mask_src, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad);
           }
-          tc_store_chunk<N_TILE, EPI, TOUT>(rA, mA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
+          if (EPI == EPI_MOMENTUM) tc_momentum_chunk(rA, (u % CH) * 32, n, N_TILE, fa);
+          else tc_store_chunk<N_TILE, EPI, TOUT>(rA, mA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
           if (u + 2 < n_units) {
             ptx::tmem_ld_wait();
             if (u + 4 < n_units) {
               ptx::tmem_ld32(tbuf + (uint32_t)(((u + 4) / CH) * ACC_STRIDE + ((u + 4) % CH) * 32), rA);
               if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mA, mask_src, ip->q[(u + 4) / CH], ((u + 4) % CH) * 32, n, n_pad);
             }
-            tc_store_chunk<N_TILE, EPI, TOUT>(rB, mB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
+            if (EPI == EPI_MOMENTUM) tc_momentum_chunk(rB, ((u + 2) % CH) * 32, n, N_TILE, fa);
+            else tc_store_chunk<N_TILE, EPI, TOUT>(rB, mB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
           }
         }
       }
@@ -497,6 +499,9 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
   std::vector<TcItem2> items;
   std::vector<TcStep2> steps;
   tc2_build_schedule(tab, h_grid, w_grid, N, K, max_acc, &items, &steps);
+  // largest windows first: with the static round-robin item -> CTA-pair mapping every pair then
+  // gets a big-to-small mix (border windows have fewer in-bounds taps), which evens out the tail
+  std::stable_sort(items.begin(), items.end(), [](const TcItem2& l, const TcItem2& r) { return l.n_steps > r.n_steps; });
   w2->n_windows = (int)items.size();
   int rc;
   if ((rc = tc_upload(allocs, items.data(), items.size() * sizeof(TcItem2), (void**)&w2->items, s))) return rc;
@@ -517,6 +522,7 @@ static int tc2_optin_all() {
   TC2_OPTIN(64, EPI_MASK, __half); TC2_OPTIN(128, EPI_MASK, __half); TC2_OPTIN(256, EPI_MASK, __half);
   TC2_OPTIN(64, EPI_NONE, __half); TC2_OPTIN(128, EPI_NONE, __half); TC2_OPTIN(256, EPI_NONE, __half);
   TC2_OPTIN(64, EPI_NONE, float); TC2_OPTIN(128, EPI_NONE, float); TC2_OPTIN(256, EPI_NONE, float);
+  TC2_OPTIN(64, EPI_MOMENTUM, float); TC2_OPTIN(128, EPI_MOMENTUM, float); TC2_OPTIN(256, EPI_MOMENTUM, float);
   TC2_OPTIN(16, EPI_FINAL_SIGMOID1, __half); TC2_OPTIN(48, EPI_FINAL_TANH3, __half);
 #undef TC2_OPTIN
   return 0;
@@ -556,7 +562,8 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
     else if (w.N == 128) TC2_GO(128, EP); \
     else TC2_GO(256, EP);               \
   } while (0)
-  if (sizeof(TOUT) == 4) { TC2_BY_N(EPI_NONE); }
+  if (sizeof(TOUT) == 4 && epi == EPI_MOMENTUM) { TC2_BY_N(EPI_MOMENTUM); }
+  else if (sizeof(TOUT) == 4) { TC2_BY_N(EPI_NONE); }
   else if (epi == EPI_FINAL_SIGMOID1) { TC2_GO_H(16, EPI_FINAL_SIGMOID1); }
   else if (epi == EPI_FINAL_TANH3) { TC2_GO_H(48, EPI_FINAL_TANH3); }
   else if (epi == EPI_BIAS_RELU) { TC2_BY_N(EPI_BIAS_RELU); }
