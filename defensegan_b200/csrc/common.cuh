@@ -25,6 +25,24 @@ void set_error(const std::string& msg);
     }                                                                                      \
   } while (0)
 
+// Programmatic dependent launch: kernels of the L-step loop are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization; each calls pdl_launch_dependents() at its start
+// (the next kernel's CTAs may be scheduled on SMs as they free up and run their prologue) and
+// pdl_wait() before touching memory written by its predecessors (waits for their full completion).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 constexpr int kRowTile = 128;   // latent rows per tile: the MMA M dimension / SIMT block tile
 constexpr int kTaps = 25;       // 5x5 filter
 

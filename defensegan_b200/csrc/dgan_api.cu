@@ -206,6 +206,7 @@ struct Workspace {
   std::vector<float*> act, dact;     // fp32 path: per hidden layer output [P][n_pad][C]
   std::vector<__half*> act_h, dact_h;  // fp16 path
   __half* z_h = nullptr;
+  std::vector<unsigned long long*> maskbits;   // fp16 path: 1-bit ReLU masks per hidden layer output
   __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
   int n_loss_parts = 0, n_g_parts = 1;
   float *y = nullptr, *dpre = nullptr, *loss_part = nullptr, *loss = nullptr;
@@ -238,6 +239,7 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
     if (tc) {
       w.act_h.push_back((__half*)take(elems * 2));
       w.dact_h.push_back((__half*)take(elems * 2));
+      w.maskbits.push_back((unsigned long long*)take(elems / 8));
     } else {
       w.act.push_back((float*)take(elems * 4));
       w.dact.push_back((float*)take(elems * 4));
@@ -326,7 +328,8 @@ static int launch_final_bwd(dgan_ctx* c, const Workspace& w, const TOUT* mask_sr
 }
 
 static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
-                      int epi, const float* bias, const __half* mask_src, cudaStream_t s);
+                      int epi, const float* bias, const __half* mask_src, cudaStream_t s,
+                      unsigned long long* mb_out = nullptr, const unsigned long long* mb_in = nullptr);
 
 // ---- one generator forward (+ loss and dL/dpre when x != null) ---------------------------
 static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, int B, bool want_grad,
@@ -338,7 +341,8 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     for (int l = 0; l < nl; ++l) {
       const GemmLayer& L = c->layers[l];
       ProfScope ps(c, 2 * l, s);
-      if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, nullptr, s)))
+      if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, nullptr, s,
+                           (L.relu && want_grad) ? w.maskbits[l] : nullptr, nullptr)))
         return rc;
       in = w.act_h[l];
     }
@@ -377,7 +381,7 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
     {
       ProfScope ps(c, 2 * nl + 1, s);
       if ((rc = tcx_launch(c, c->tc_fin.b, c->tc2_fin_b, w.dblk, w.dact_h[nl - 1], w.n_pad, last.relu ? EPI_MASK : EPI_NONE,
-                           nullptr, last.relu ? w.act_h[nl - 1] : nullptr, s)))
+                           nullptr, last.relu ? w.act_h[nl - 1] : nullptr, s, nullptr, last.relu ? w.maskbits[nl - 1] : nullptr)))
         return rc;
     }
     for (int l = nl - 1; l >= 1; --l) {
@@ -385,7 +389,7 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
       const bool mask = c->layers[l - 1].relu;
       ProfScope ps(c, 2 * l + 1, s);
       if ((rc = tcx_launch(c, L.tc_b, L.tc2_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad, mask ? EPI_MASK : EPI_NONE, nullptr,
-                           mask ? w.act_h[l - 1] : nullptr, s)))
+                           mask ? w.act_h[l - 1] : nullptr, s, nullptr, mask ? w.maskbits[l - 1] : nullptr)))
         return rc;
     }
     const GemmLayer& L0 = c->layers[0];
@@ -441,8 +445,13 @@ static int check_ws(const dgan_ctx* c, int n_rows, void* ws, size_t ws_bytes, Wo
 
 // tensor-core launch, dispatching on the kernel generation
 static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
-                      int epi, const float* bias, const __half* mask_src, cudaStream_t s) {
-  if (c->tc.mode == 2) return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, mask_src, 1.f, s);
+                      int epi, const float* bias, const __half* mask_src, cudaStream_t s, unsigned long long* mb_out,
+                      const unsigned long long* mb_in) {
+  if (c->tc.mode == 2) {
+    TcFinalArgs fa{};
+    fa.mb_out = mb_out; fa.mb_in = mb_in;
+    return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, mask_src, 1.f, s, &fa);
+  }
   return tc_launch(c->tc, &c->launches, w1, in, out, n_pad, epi, bias, mask_src, 1.f, s);
 }
 
@@ -713,8 +722,8 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
     if ((rc = run_backward(h, w, s, mom))) return rc;
     if (!fused) {
       ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
-      momentum_kernel<<<(unsigned)((zcount + 255) / 256), 256, 0, s>>>(w.z, w.v, w.g, w.n_g_parts, grad_multiplier(h), lr,
-                                                                       momentum, zcount, w.z_h);
+      DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
+                                 (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
       DGAN_LAUNCH_CHECK(h);
     }
   }

@@ -277,6 +277,8 @@ final_bwd_kernel(const float* __restrict__ dpre /*[n_pad][P_out*C_OUT]*/, int n_
 // ------------------------------------------------------------------------------------------
 __global__ void momentum_kernel(float* __restrict__ z, float* __restrict__ v, const float* __restrict__ g, int n_parts,
                                 float gmul, float lr, float mu, size_t count, __half* __restrict__ z_h) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float gs = g[i];

@@ -176,6 +176,11 @@ struct TcFinalArgs {
   int R, B, n_rows;      // restarts per image, images, valid latent rows
   int nbx, w_out;        // blocks per image row, image width
   float gscale;          // fp16 gradient scaling applied to dL/dpre
+  // 1-bit ReLU masks of the CTA-pair path: bit j of word [(q*n_pad + n)*(N/64) + g] <=> out[q][n][g*64+j] > 0.
+  // Written by the forward EPI_BIAS_RELU epilogue, read by the backward EPI_MASK epilogue
+  // (tf.nn.relu's gradient passes where the forward output was > 0).
+  unsigned long long* mb_out;
+  const unsigned long long* mb_in;
   // EPI_MOMENTUM (Linear backward fused with tf.train.MomentumOptimizer, models/gan.py:389-391):
   float* mz; float* mv; __half* mz_h;   // z, velocity [n_pad][latent] fp32, fp16 copy of z
   float m_gmul, m_lr, m_mu;             // g = gmul * acc;  v <- mu v + g;  z <- z - lr v

@@ -47,8 +47,8 @@ struct Tc2Cfg {
   static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (4 / 2 / 1)
   static constexpr int STAGE_BYTES = ((TC_A_BYTES + MAXB * HALF_B + 1023) / 1024) * 1024;
   static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
-  // epilogue staging: one output tile per epilogue half (+ one mask tile per half for EPI_MASK)
-  static constexpr int EPI_BYTES = TMA_EPI ? (EPI == EPI_MASK ? 4 : 2) * TC2_TILE_BYTES : 0;
+  // epilogue staging: one output tile per epilogue half
+  static constexpr int EPI_BYTES = TMA_EPI ? 2 * TC2_TILE_BYTES : 0;
   static constexpr int STAGES_RAW = (TC2_SMEM_MAX - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
@@ -166,7 +166,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       ptx::mbar_init(bar_acc_empty + 8 * b, 2 * TC2_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
       ptx::mbar_init(bar_mask + 8 * b, 1);
     }
-    if (TMA_EPI) { ptx::prefetch_tmap(&tm_out); if (EPI == EPI_MASK) ptx::prefetch_tmap(&tm_mask); }
+    if (TMA_EPI) ptx::prefetch_tmap(&tm_out);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -177,6 +177,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   ptx::cluster_sync_all();                     // barriers of BOTH CTAs initialised before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above overlapped the previous kernel's tail (PDL); from here on we read what it wrote
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -277,7 +280,6 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int half = (warp - 2) >> 2;                 // 0 | 1: which of the two warps of this quarter
     const int row = lq * 32 + lane;
     uint32_t item_count = 0;
-    uint32_t mask_phase = 0;
     long long t_ewait = 0, t_ework = 0;
     const long long t_start = fa.dbg ? clock64() : 0;
     for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs, ++item_count) {
@@ -287,14 +289,6 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
       const uint32_t buf = item_count & 1;
       const uint32_t tbuf = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * TC2_BUF_COLS;
-      if (TMA_EPI && EPI == EPI_MASK) {   // first mask tile of this half: needs nothing from the MMAs, fetch it now
-        constexpr int G0 = N_TILE / 64;
-        if ((warp == 2 + 4 * half) && lane == 0 && half < n_acc * G0) {
-          ptx::mbar_expect_tx(bar_mask + 8 * half, TC2_TILE_BYTES);
-          ptx::tma_load_3d_local(epi_base + (2 + half) * TC2_TILE_BYTES, &tm_mask, bar_mask + 8 * half, (half % G0) * 64,
-                                 (2 * mp + (int)rank) * kRowTile, ip->q[half / G0]);
-        }
-      }
       const long long te0 = fa.dbg ? clock64() : 0;
       ptx::mbar_wait(bar_acc_full + 8 * buf, (item_count >> 1) & 1);
       const long long te1 = fa.dbg ? clock64() : 0;
@@ -313,13 +307,13 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
         const int n_units = n_acc * G;
         const uint32_t s_out = epi_base + half * TC2_TILE_BYTES;
-        const uint32_t s_mask = epi_base + (2 + half) * TC2_TILE_BYTES;
-        const uint32_t bar_m = bar_mask + 8 * half;
         const bool t0 = (warp == 2 + 4 * half) && lane == 0;  // issues this half's bulk copies
         const int row0 = (2 * mp + (int)rank) * kRowTile;
         const uint32_t swz = (uint32_t)(row & 7);
         for (int u = half; u < n_units; u += 2) {
           const int a = u / G, g = u % G, q = ip->q[a];
+          unsigned long long mbits = ~0ull;
+          if (EPI == EPI_MASK) mbits = __ldg(fa.mb_in + ((size_t)q * n_pad + n) * G + g);   // in flight during the TMEM load
           uint32_t r0[32], r1[32];
           ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64), r0);
           ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64 + 32), r1);
@@ -341,26 +335,22 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
               }
             }
+            if (EPI == EPI_BIAS_RELU && fa.mb_out != nullptr) {
+              unsigned long long bits = 0ull;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) bits |= (unsigned long long)(v[j] > 0.f) << j;
+              fa.mb_out[((size_t)q * n_pad + n) * G + g] = bits;
+            }
             if (EPI == EPI_MASK) {
-              ptx::mbar_wait(bar_m, mask_phase);
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint4 mv = ptx::ld_shared_v4(s_mask + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4));
-                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
-                  if (!(__low2float(h) > 0.f)) v[c * 8 + e * 2] = 0.f;
-                  if (!(__high2float(h) > 0.f)) v[c * 8 + e * 2 + 1] = 0.f;
-                }
-              }
-              mask_phase ^= 1;
+              for (int j = 0; j < 64; ++j)
+                if (!((mbits >> j) & 1ull)) v[j] = 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) pk[j] = pack_half2(v[2 * j], v[2 * j + 1]);
           }
           if (t0) ptx::bulk_wait_read0();                  // the previous store has finished reading s_out
-          ptx::named_bar_sync(1 + half, 128);              // s_out free; everybody is done with s_mask
+          ptx::named_bar_sync(1 + half, 128);              // s_out free
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             ptx::st_shared_v4(s_out + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
@@ -369,11 +359,6 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (t0) {
             ptx::tma_store_3d(&tm_out, s_out, g * 64, row0, q);
             ptx::bulk_commit();
-            if (EPI == EPI_MASK && u + 2 < n_units) {      // mask tile of this half's next unit
-              const int a2 = (u + 2) / G, g2 = (u + 2) % G;
-              ptx::mbar_expect_tx(bar_m, TC2_TILE_BYTES);
-              ptx::tma_load_3d_local(s_mask, &tm_mask, bar_m, g2 * 64, row0, ip->q[a2]);
-            }
           }
         }
       } else {
@@ -543,19 +528,19 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   CUtensorMap tm_out = tm_a, tm_mask = tm_a;     // placeholders when unused
   if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT))) {
     if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
-    if (epi == EPI_MASK && (rc = tc_make_map(st, &tm_mask, mask_src, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
   }
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
   const int n_mpairs = n_pad / (2 * kRowTile);
   const int total = w2.n_windows * n_mpairs;
   const int grid = 2 * std::min(total, st.num_sms / 2);
+  cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
-  tc_bsgemm2_kernel<NT, EP, TOUT><<<grid, TC2_THREADS, Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s>>>(             \
-      tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+  le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
+                  tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
-  tc_bsgemm2_kernel<NT, EP, __half><<<grid, TC2_THREADS, Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s>>>(                           \
-      tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0,       \
-      mask_src, out_scale, fa)
+  le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
+                  tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
+                  mask_src, out_scale, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
     if (w.N == 64) TC2_GO(64, EP);      \
@@ -574,7 +559,7 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
 #undef TC2_GO
 #undef TC2_GO_H
   (*launches)++;
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = (le != cudaSuccess) ? le : cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("tc_bsgemm2 launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
   return 0;
 }
