@@ -322,8 +322,14 @@ def main():
         peak = peaks["bf16_tflops"]        # kernel timed alone -> burst figure (fp16 and bf16 share kind::f16 rate)
         if args.precision == "fp32":
             peak = None
+        traffic = None   # DRAM read+write bytes per launch of that kernel from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", "r1b_dram_traffic.json")
+        if os.path.exists(tp) and args.precision == "fp16" and dataset == "mnist" and B * R == 2560:
+            with open(tp) as f:
+                traffic = json.load(f)["kernels"].get(dom["kernel"], {}).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak,
-                    "unit": "TFLOP/s", "frac": (dom["tflops"] / peak) if peak else None, "traffic": None,
+                    "unit": "TFLOP/s", "frac": (dom["tflops"] / peak) if peak else None, "traffic": traffic,
+                    "traffic_unit": "bytes/launch (dram__bytes_read+write, profiles/r1b_dram_traffic.json)",
                     "peak_source": "%s cuBLAS bf16 burst (MEASURED_PEAKS.json)" % peaks["_source"],
                     "operand_format": args.precision}
 
