@@ -73,8 +73,11 @@ struct PairTable {
 // TF conv2d_transpose(k=5, stride 2, SAME): out[i] += in[o] * w[k], i = 2o + k - 1
 // (tflib/ops/deconv2d.py:100-110).  h_used/w_used = the output rows/cols that are
 // kept (MNIST crops 8x8 -> 7x7 after Generator.2, models/dataset_models.py:59).
-PairTable deconv_fwd_pairs(int h_in, int w_in, int h_used, int w_used);
-PairTable deconv_bwd_pairs(int h_in, int w_in, int h_used, int w_used);
+// `in_raster` (>= w_in): the input buffer is an in_raster x in_raster pixel raster of which only the
+// top-left h_in x w_in pixels are consumed (MNIST + BatchNorm: Generator.2 keeps its full 8x8 output
+// because the batch statistics cover the pixels that are cropped afterwards).
+PairTable deconv_fwd_pairs(int h_in, int w_in, int h_used, int w_used, int in_raster = 0);
+PairTable deconv_bwd_pairs(int h_in, int w_in, int h_used, int w_used, int in_raster = 0);
 // Linear [latent] -> [16 pixels x C]: column f = (h*4 + w)*C + c
 PairTable linear_fwd_pairs(int n_pix);
 PairTable linear_bwd_pairs(int n_pix);

@@ -22,7 +22,8 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 // ---------------------------------------------------------------------------------------
 // geometry tables
 // ---------------------------------------------------------------------------------------
-PairTable deconv_fwd_pairs(int h_in, int w_in, int h_used, int w_used) {
+PairTable deconv_fwd_pairs(int h_in, int w_in, int h_used, int w_used, int in_raster) {
+  if (in_raster <= 0) in_raster = w_in;
   PairTable t;
   t.off.push_back(0);
   for (int i = 0; i < h_used; ++i)
@@ -33,7 +34,7 @@ PairTable deconv_fwd_pairs(int h_in, int w_in, int h_used, int w_used) {
         for (int kb = 0; kb < 5; ++kb) {
           const int pp = j + 1 - kb;
           if (pp < 0 || (pp & 1) || (pp >> 1) >= w_in) continue;
-          t.pairs.push_back(make_int2((oo >> 1) * w_in + (pp >> 1), ka * 5 + kb));
+          t.pairs.push_back(make_int2((oo >> 1) * in_raster + (pp >> 1), ka * 5 + kb));
         }
       }
       t.off.push_back((int)t.pairs.size());
@@ -41,12 +42,14 @@ PairTable deconv_fwd_pairs(int h_in, int w_in, int h_used, int w_used) {
   return t;
 }
 
-PairTable deconv_bwd_pairs(int h_in, int w_in, int h_used, int w_used) {
+PairTable deconv_bwd_pairs(int h_in, int w_in, int h_used, int w_used, int in_raster) {
+  if (in_raster <= 0) in_raster = w_in;
   PairTable t;
   t.off.push_back(0);
-  for (int o = 0; o < h_in; ++o)
-    for (int p = 0; p < w_in; ++p) {
-      for (int ka = 0; ka < 5; ++ka) {
+  for (int o = 0; o < in_raster; ++o)
+    for (int p = 0; p < in_raster; ++p) {
+      // raster pixels outside the consumed h_in x w_in window receive no gradient (empty list -> zeros)
+      for (int ka = 0; ka < 5 && o < h_in && p < w_in; ++ka) {
         const int i = 2 * o + ka - 1;
         if (i < 0 || i >= h_used) continue;
         for (int kb = 0; kb < 5; ++kb) {
@@ -100,6 +103,9 @@ struct GemmLayer {
   const float* wb = nullptr; int wb_tile_stride = 0, wb_ld = 0;
   const float* bias = nullptr;
   int bias_pstride = 0;            // Linear: bias is per flat feature f = pixel*C_out + c
+  const float* bn_offset = nullptr;   // use_bn: Generator.BN{1,2,3}.offset / .scale (else null)
+  const float* bn_scale = nullptr;
+  int bn_per_pixel = 0;               // BN1 normalises each flat feature (axes [0]); BN2/3 each channel (axes [0,1,2])
   // fp16 K-major tiles for the tensor-core path (kernels_tc.cuh): [tile][N rows][K cols]
   TcWeights tc_f, tc_b;
   TcWeights2 tc2_f, tc2_b;
@@ -204,6 +210,8 @@ struct Workspace {
   int n_rows = 0, n_pad = 0;
   float *z = nullptr, *v = nullptr, *g = nullptr;
   std::vector<float*> act, dact;     // fp32 path: per hidden layer output [P][n_pad][C]
+  std::vector<float*> pre;           // use_bn: pre-normalisation outputs (null otherwise)
+  std::vector<float*> bn_part;       // use_bn: [4][kBnSplits][G] partial sums (mean, var, S1, S2)
   std::vector<__half*> act_h, dact_h;  // fp16 path
   __half* z_h = nullptr;
   std::vector<unsigned long long*> maskbits;   // fp16 path: 1-bit ReLU masks per hidden layer output
@@ -243,6 +251,14 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
     } else {
       w.act.push_back((float*)take(elems * 4));
       w.dact.push_back((float*)take(elems * 4));
+      if (l.bn_scale != nullptr) {
+        const size_t G = l.bn_per_pixel ? (size_t)l.P_out * l.C_out : (size_t)l.C_out;
+        w.pre.push_back((float*)take(elems * 4));
+        w.bn_part.push_back((float*)take((size_t)4 * kBnSplits * G * 4));
+      } else {
+        w.pre.push_back(nullptr);
+        w.bn_part.push_back(nullptr);
+      }
     }
   }
   w.y = (float*)take(np * c->hwc * 4);
@@ -359,9 +375,29 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
   for (int l = 0; l < nl; ++l) {
     const GemmLayer& L = c->layers[l];
     ProfScope ps(c, 2 * l, s);
-    if ((rc = launch_bsgemm_f32(c, L.relu ? EPI_BIAS_RELU : EPI_BIAS, in, L.C_in, w.n_pad, L.wf, L.wf_tile_stride,
-                                L.wf_ld, L.fwd, w.act[l], L.C_out, L.bias, L.bias_pstride, nullptr, s)))
+    if (L.bn_scale != nullptr) {
+      // pre = GEMM + bias;  act = relu(BN_batchstat(pre))
+      if ((rc = launch_bsgemm_f32(c, EPI_BIAS, in, L.C_in, w.n_pad, L.wf, L.wf_tile_stride, L.wf_ld, L.fwd, w.pre[l], L.C_out,
+                                  L.bias, L.bias_pstride, nullptr, s)))
+        return rc;
+      const int G = L.bn_per_pixel ? L.P_out * L.C_out : L.C_out;
+      float* part = w.bn_part[l];
+      float *mean_p = part, *var_p = part + (size_t)kBnSplits * G;
+      dim3 rgrid(G / 32, kBnSplits);
+      bn_reduce_kernel<0><<<rgrid, 256, 0, s>>>(w.pre[l], nullptr, nullptr, nullptr, nullptr, L.P_out, w.n_rows, w.n_pad, L.C_out,
+                                                L.bn_per_pixel, mean_p, nullptr);
+      DGAN_LAUNCH_CHECK(c);
+      bn_reduce_kernel<1><<<rgrid, 256, 0, s>>>(w.pre[l], nullptr, nullptr, mean_p, nullptr, L.P_out, w.n_rows, w.n_pad, L.C_out,
+                                                L.bn_per_pixel, var_p, nullptr);
+      DGAN_LAUNCH_CHECK(c);
+      const size_t total = (size_t)L.P_out * w.n_pad * L.C_out;
+      bn_apply_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.pre[l], mean_p, var_p, L.bn_scale, L.bn_offset, L.P_out,
+                                                                           w.n_rows, w.n_pad, L.C_out, L.bn_per_pixel, w.act[l]);
+      DGAN_LAUNCH_CHECK(c);
+    } else if ((rc = launch_bsgemm_f32(c, L.relu ? EPI_BIAS_RELU : EPI_BIAS, in, L.C_in, w.n_pad, L.wf, L.wf_tile_stride,
+                                       L.wf_ld, L.fwd, w.act[l], L.C_out, L.bias, L.bias_pstride, nullptr, s))) {
       return rc;
+    }
     in = w.act[l];
   }
   ProfScope ps(c, 2 * nl, s);
@@ -404,18 +440,40 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
       return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s);
     return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
   }
+  // d(act) -> d(pre) through ReLU + batch-statistics BN of layer l (in place in w.dact[l])
+  auto bn_backward = [&](int l) -> int {
+    const GemmLayer& L = c->layers[l];
+    const int G = L.bn_per_pixel ? L.P_out * L.C_out : L.C_out;
+    float* part = w.bn_part[l];
+    float *mean_p = part, *var_p = part + (size_t)kBnSplits * G, *s1_p = part + (size_t)2 * kBnSplits * G,
+          *s2_p = part + (size_t)3 * kBnSplits * G;
+    dim3 rgrid(G / 32, kBnSplits);
+    bn_reduce_kernel<2><<<rgrid, 256, 0, s>>>(w.pre[l], w.act[l], w.dact[l], mean_p, var_p, L.P_out, w.n_rows, w.n_pad, L.C_out,
+                                              L.bn_per_pixel, s1_p, s2_p);
+    DGAN_LAUNCH_CHECK(c);
+    const size_t total = (size_t)L.P_out * w.n_pad * L.C_out;
+    bn_apply_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.pre[l], w.act[l], mean_p, var_p, s1_p, s2_p, L.bn_scale,
+                                                                         L.P_out, w.n_rows, w.n_pad, L.C_out, L.bn_per_pixel,
+                                                                         w.dact[l]);
+    DGAN_LAUNCH_CHECK(c);
+    return 0;
+  };
   const GemmLayer& last = c->layers[nl - 1];
   {
     ProfScope ps(c, 2 * nl + 1, s);
-    if ((rc = launch_final_bwd<float>(c, w, last.relu ? w.act[nl - 1] : nullptr, 1.f, w.dact[nl - 1], s))) return rc;
+    const bool bn = last.bn_scale != nullptr;
+    if ((rc = launch_final_bwd<float>(c, w, (last.relu && !bn) ? w.act[nl - 1] : nullptr, 1.f, w.dact[nl - 1], s))) return rc;
+    if (bn && (rc = bn_backward(nl - 1))) return rc;
   }
   for (int l = nl - 1; l >= 1; --l) {
     const GemmLayer& L = c->layers[l];
-    const bool mask = c->layers[l - 1].relu;
+    const bool bn = c->layers[l - 1].bn_scale != nullptr;
+    const bool mask = c->layers[l - 1].relu && !bn;
     ProfScope ps(c, 2 * l + 1, s);
     if ((rc = launch_bsgemm_f32(c, mask ? EPI_MASK : EPI_NONE, w.dact[l], L.C_out, w.n_pad, L.wb, L.wb_tile_stride,
                                 L.wb_ld, L.bwd, w.dact[l - 1], L.C_in, nullptr, 0, mask ? w.act[l - 1] : nullptr, s)))
       return rc;
+    if (bn && (rc = bn_backward(l - 1))) return rc;
   }
   const GemmLayer& L0 = c->layers[0];
   ProfScope ps(c, 1, s);
@@ -483,8 +541,8 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
   if (d->abi_version != DGAN_ABI_VERSION) { set_error("ABI version mismatch"); return DGAN_ERR_INVALID_ARG; }
   if (d->arch != DGAN_ARCH_MNIST && d->arch != DGAN_ARCH_CELEBA) { set_error("unknown arch"); return DGAN_ERR_INVALID_ARG; }
   if (d->precision != DGAN_PREC_FP32 && d->precision != DGAN_PREC_FP16) { set_error("unknown precision"); return DGAN_ERR_INVALID_ARG; }
-  if (d->use_bn) {
-    set_error("use_bn=True (batch-statistics BatchNorm, tflib/ops/batchnorm.py:80-93) is not built yet");
+  if (d->use_bn && d->precision != DGAN_PREC_FP32) {
+    set_error("use_bn=True (batch-statistics BatchNorm, tflib/ops/batchnorm.py:80-93) is built for precision fp32 only");
     return DGAN_ERR_UNSUPPORTED;
   }
   if (d->net_dim <= 0 || d->net_dim % 64 != 0) { set_error("net_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
@@ -522,20 +580,24 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     transpose_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, Wt, latent, 16 * L.C_out, total);
     L.wb = Wt; L.wb_tile_stride = L.C_out * latent; L.wb_ld = latent;
     L.bias = weights[1]; L.bias_pstride = L.C_out;   // bias index f = pixel*C_out + c
+    if (d->use_bn) { L.bn_offset = weights[2]; L.bn_scale = weights[3]; L.bn_per_pixel = 1; }   // Generator.BN1, axes [0]
     c->layers.push_back(L);
   }
   // ---- hidden deconvs
-  struct DSpec { int c_in, c_out, h_in, h_used; bool relu; };
+  struct DSpec { int c_in, c_out, h_in, h_used; bool relu; int in_raster; };
   std::vector<DSpec> specs;
-  if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, true}, {2 * nd, nd, 8, 16, true}, {nd, nd, 16, 32, false}};
-  else specs = {{4 * nd, 2 * nd, 4, 7, true}, {2 * nd, nd, 7, 14, true}};
-  int wi = 2;
+  if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, true, 4}, {2 * nd, nd, 8, 16, true, 8}, {nd, nd, 16, 32, false, 16}};
+  else if (d->use_bn)   // BN2's batch statistics cover all 8x8 outputs of Generator.2; the 7x7 crop comes after BN+ReLU
+    specs = {{4 * nd, 2 * nd, 4, 8, true, 4}, {2 * nd, nd, 7, 14, true, 8}};
+  else specs = {{4 * nd, 2 * nd, 4, 7, true, 4}, {2 * nd, nd, 7, 14, true, 7}};
+  int wi = d->use_bn ? 4 : 2;
+  int di = 0;
   for (const DSpec& sp : specs) {
     GemmLayer L{};
-    L.P_in = sp.h_in * sp.h_in; L.C_in = sp.c_in; L.P_out = sp.h_used * sp.h_used; L.C_out = sp.c_out;
-    L.h_in = L.w_in = sp.h_in; L.h_used = L.w_used = sp.h_used; L.relu = sp.relu;
-    L.fwd_host = deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used);
-    L.bwd_host = deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used);
+    L.P_in = sp.in_raster * sp.in_raster; L.C_in = sp.c_in; L.P_out = sp.h_used * sp.h_used; L.C_out = sp.c_out;
+    L.h_in = L.w_in = sp.in_raster; L.h_used = L.w_used = sp.h_used; L.relu = sp.relu;
+    L.fwd_host = deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster);
+    L.bwd_host = deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster);
     const float* F = weights[wi];            // (5,5,C_out,C_in)
     float* Ff = nullptr;                     // [25][C_in][C_out]
     const size_t total = (size_t)kTaps * sp.c_out * sp.c_in;
@@ -544,8 +606,13 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     L.wf = Ff; L.wf_tile_stride = sp.c_in * sp.c_out; L.wf_ld = sp.c_out;
     L.wb = F;  L.wb_tile_stride = sp.c_in * sp.c_out; L.wb_ld = sp.c_in;
     L.bias = weights[wi + 1];
-    c->layers.push_back(L);
     wi += 2;
+    if (d->use_bn && di < 2) {               // Generator.BN2 / BN3 follow Generator.2 / Generator.3 (axes [0,1,2])
+      L.bn_offset = weights[wi]; L.bn_scale = weights[wi + 1]; L.bn_per_pixel = 0;
+      wi += 2;
+    }
+    ++di;
+    c->layers.push_back(L);
   }
   // ---- final layer
   {

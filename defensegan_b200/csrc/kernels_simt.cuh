@@ -374,3 +374,114 @@ __global__ void select_kernel(const float* __restrict__ loss, const float* __res
 }
 
 }  // namespace dgan
+
+// ==========================================================================================
+// Batch-statistics BatchNorm of the generator (opt-in, use_bn=True): tflib/ops/batchnorm.py:80-93
+// - the generator always takes the non-fused branch, so BATCH statistics are used even at test
+// time: mean/var = tf.nn.moments (biased variance) over axes [0] (Linear output: one
+// group per flat feature (pixel, channel)) or [0,1,2] (deconv outputs: one group per channel),
+// y = (x - mean) * rsqrt(var + 1e-5) * scale + offset, then ReLU.  All latent rows of a call are
+// coupled; tile-padding rows (n >= n_rows) are excluded.  Reductions are two-level with a fixed
+// order (deterministic).  Activations are [P][n_pad][C]; group index = per_pixel ? p*C + c : c.
+// ==========================================================================================
+namespace dgan {
+
+constexpr int kBnSplits = 16;
+
+// MODE 0: sum x            MODE 1: sum (x - mean)^2
+// MODE 2: S1 = sum dy, S2 = sum dy * xhat with dy = dact * (act > 0), xhat = (pre - mean) * inv
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ act, const float* __restrict__ dact,
+                 const float* __restrict__ mean_part /*[splits][G]*/, const float* __restrict__ var_part, int P, int n_rows,
+                 int n_pad, int C, int per_pixel, float* __restrict__ out0 /*[splits][G]*/, float* __restrict__ out1) {
+  __shared__ float red0[8][33], red1[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int G = per_pixel ? P * C : C;
+  const int g = blockIdx.x * 32 + tx;            // C % 32 == 0, so a block never straddles pixels
+  const int split = blockIdx.y;
+  const long long M = per_pixel ? n_rows : (long long)P * n_rows;
+  float mean = 0.f, inv = 0.f;
+  if (MODE >= 1) {
+    float s = 0.f;
+    for (int k = 0; k < kBnSplits; ++k) s += mean_part[(size_t)k * G + g];
+    mean = s / (float)M;
+  }
+  if (MODE == 2) {
+    float s = 0.f;
+    for (int k = 0; k < kBnSplits; ++k) s += var_part[(size_t)k * G + g];
+    inv = rsqrtf(s / (float)M + 1e-5f);
+  }
+  const int c = per_pixel ? g % C : g;
+  const int p_fixed = per_pixel ? g / C : 0;
+  float a0 = 0.f, a1 = 0.f;
+  for (long long s = (long long)split * 8 + ty; s < M; s += (long long)kBnSplits * 8) {
+    const int p = per_pixel ? p_fixed : (int)(s / n_rows);
+    const int n = per_pixel ? (int)s : (int)(s % n_rows);
+    const size_t idx = ((size_t)p * n_pad + n) * C + c;
+    if (MODE == 0) a0 += x[idx];
+    if (MODE == 1) { const float d = x[idx] - mean; a0 = fmaf(d, d, a0); }
+    if (MODE == 2) {
+      const float dy = act[idx] > 0.f ? dact[idx] : 0.f;
+      a0 += dy;
+      a1 = fmaf(dy, (x[idx] - mean) * inv, a1);
+    }
+  }
+  red0[ty][tx] = a0; red1[ty][tx] = a1;
+  __syncthreads();
+  if (ty == 0) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < 8; ++k) { s0 += red0[k][tx]; s1 += red1[k][tx]; }
+    out0[(size_t)split * G + g] = s0;
+    if (MODE == 2) out1[(size_t)split * G + g] = s1;
+  }
+}
+
+// forward: act = relu((pre - mean) * inv * scale + offset), evaluated the way TF's batch_normalization does:
+// x * (inv*scale) + (offset - mean*inv*scale)
+__global__ void bn_apply_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ mean_part,
+                                    const float* __restrict__ var_part, const float* __restrict__ scale,
+                                    const float* __restrict__ offset, int P, int n_rows, int n_pad, int C, int per_pixel,
+                                    float* __restrict__ act) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P * n_pad * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int n = (int)((i / C) % n_pad);
+  const int p = (int)(i / ((size_t)C * n_pad));
+  if (n >= n_rows) { act[i] = 0.f; return; }
+  const int G = per_pixel ? P * C : C, g = per_pixel ? p * C + c : c;
+  const float M = per_pixel ? (float)n_rows : (float)P * (float)n_rows;
+  float sm = 0.f, sv = 0.f;
+  for (int k = 0; k < kBnSplits; ++k) { sm += mean_part[(size_t)k * G + g]; sv += var_part[(size_t)k * G + g]; }
+  const float mean = sm / M, inv = rsqrtf(sv / M + 1e-5f) * scale[g];
+  act[i] = fmaxf(fmaf(pre[i], inv, offset[g] - mean * inv), 0.f);
+}
+
+// backward through ReLU + BN:  dpre = scale*inv * (dy - S1/M - xhat * S2/M),  dy = dact * (act > 0)
+__global__ void bn_apply_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ act,
+                                    const float* __restrict__ mean_part, const float* __restrict__ var_part,
+                                    const float* __restrict__ s1_part, const float* __restrict__ s2_part,
+                                    const float* __restrict__ scale, int P, int n_rows, int n_pad, int C, int per_pixel,
+                                    float* __restrict__ dact /*in: d(act), out: d(pre)*/) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P * n_pad * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int n = (int)((i / C) % n_pad);
+  const int p = (int)(i / ((size_t)C * n_pad));
+  if (n >= n_rows) { dact[i] = 0.f; return; }
+  const int G = per_pixel ? P * C : C, g = per_pixel ? p * C + c : c;
+  const float M = per_pixel ? (float)n_rows : (float)P * (float)n_rows;
+  float sm = 0.f, sv = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < kBnSplits; ++k) {
+    sm += mean_part[(size_t)k * G + g]; sv += var_part[(size_t)k * G + g];
+    s1 += s1_part[(size_t)k * G + g]; s2 += s2_part[(size_t)k * G + g];
+  }
+  const float mean = sm / M, inv = rsqrtf(sv / M + 1e-5f);
+  const float xhat = (pre[i] - mean) * inv;
+  const float dy = act[i] > 0.f ? dact[i] : 0.f;
+  dact[i] = scale[g] * inv * (dy - s1 / M - xhat * (s2 / M));
+}
+
+}  // namespace dgan

@@ -28,16 +28,17 @@ def weights_digest(w):
     return h.hexdigest()
 
 
-def make_case(name, arch, B, R, L, kind="S1", lr=10.0, random_bias=False, seed_img=O.IMAGE_SEED, seed_z=O.Z0_SEED):
-    w = O.init_generator_weights(arch, random_bias=random_bias)
-    imgs = O.synthetic_images(arch, w, B, kind=kind, seed=seed_img)
+def make_case(name, arch, B, R, L, kind="S1", lr=10.0, random_bias=False, seed_img=O.IMAGE_SEED, seed_z=O.Z0_SEED,
+              use_bn=False):
+    w = O.init_generator_weights(arch, random_bias=random_bias, use_bn=use_bn)
+    imgs = O.synthetic_images(arch, w, B, kind=kind, seed=seed_img)   # S1 images come from the plain (no-BN) forward
     z0 = O.sample_z0(B * R, 128, seed=seed_z)
-    r32 = O.reconstruct(arch, w, imgs, R, L, rec_lr=lr, z_init_val=z0, dtype=torch.float32)
-    r64 = O.reconstruct(arch, w, imgs, R, L, rec_lr=lr, z_init_val=z0, dtype=torch.float64)
-    y, loss, grad = O.loss_and_grad(arch, w, imgs, z0, R, dtype=torch.float64)
+    r32 = O.reconstruct(arch, w, imgs, R, L, rec_lr=lr, z_init_val=z0, dtype=torch.float32, use_bn=use_bn)
+    r64 = O.reconstruct(arch, w, imgs, R, L, rec_lr=lr, z_init_val=z0, dtype=torch.float64, use_bn=use_bn)
+    y, loss, grad = O.loss_and_grad(arch, w, imgs, z0, R, dtype=torch.float64, use_bn=use_bn)
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
-        arch=arch, B=B, R=R, L=L, lr=lr, random_bias=int(random_bias), weights_sha256=weights_digest(w),
+        arch=arch, B=B, R=R, L=L, lr=lr, random_bias=int(random_bias), use_bn=int(use_bn), weights_sha256=weights_digest(w),
         images=imgs, z0=z0,
         rec32=r32["rec"], loss_min32=r32["loss_min"], idx32=r32["idx"], loss_all32=r32["loss_all"],
         rec64=r64["rec"].astype("float32"), loss_min64=r64["loss_min"], idx64=r64["idx"], loss_all64=r64["loss_all"],
@@ -51,3 +52,6 @@ if __name__ == "__main__":
     make_case("mnist_c1", "mnist", 16, 2, 10)                       # BASELINE configs[0]
     make_case("mnist_ragged_bias", "mnist", 5, 3, 6, kind="S2", random_bias=True)
     make_case("celeba_small", "celeba", 3, 2, 4, random_bias=True)
+    # opt-in batch-statistics BatchNorm (use_bn=True): all rows of a call are coupled
+    make_case("mnist_bn", "mnist", 8, 2, 3, random_bias=True, use_bn=True, lr=0.5)
+    make_case("celeba_bn", "celeba", 2, 2, 3, random_bias=True, use_bn=True, lr=0.5)

@@ -186,7 +186,34 @@ def test_error_paths_through_c_abi(gens):
     rc = lib.dgan_reconstruct(gen._handle, x.data_ptr(), None, 0, 0, 2, 3, 10.0, 0.7, 0, rec.data_ptr(), None, None,
                               ctypes.c_void_p(base), 1024, None)
     assert rc == -1
-    d = _native.dgan_desc(1, 0, 128, 64, 1, 0)     # use_bn: not built yet -> explicit UNSUPPORTED, no fallback
+    d = _native.dgan_desc(1, 0, 128, 64, 1, 1)     # use_bn with fp16 operands: explicit UNSUPPORTED, no fallback
     h = ctypes.c_void_p(0)
     arr = (ctypes.c_void_p * 14)(*([x.data_ptr()] * 14))
     assert lib.dgan_create(ctypes.byref(h), ctypes.byref(d), arr, 14, None) == -3
+
+
+@pytest.mark.parametrize("case", ["mnist_bn", "celeba_bn"])
+def test_batchnorm_batch_statistics_path(golden_dir, case):
+    """use_bn=True (opt-in; tflib/ops/batchnorm.py:80-93 else-branch): batch statistics couple all rows
+    (SURVEY F2).  fp32 path vs the fp64 oracle: forward/loss/grad of one loop body and the short loop."""
+    from defensegan_b200 import _native
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    arch, B, R, L = str(g["arch"]), int(g["B"]), int(g["R"]), int(g["L"])
+    w = O.init_generator_weights(arch, random_bias=True, use_bn=True)
+    dev = torch.device("cuda", 0)
+    gen = _native.NativeGenerator(arch, [torch.as_tensor(v).to(dev) for v in w.values()], use_bn=True, precision="fp32",
+                                  device=dev)
+    x, z0 = torch.tensor(g["images"]).cuda(), torch.tensor(g["z0"]).cuda()
+    y, loss, grad = gen.loss_grad(x, z0, R)
+    assert np.abs(y.cpu().numpy() - g["y0_64"]).max() <= 5e-5
+    assert np.abs(loss.cpu().numpy() - g["loss0_64"]).max() <= 1e-5
+    gerr = np.abs(grad.cpu().numpy() - g["grad0_64"]).max() / np.abs(g["grad0_64"]).max()
+    assert gerr <= 1e-3, gerr
+    rec, lmin, idx = gen.reconstruct(x, R, L, float(g["lr"]), z_init_val=z0, return_aux=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["idx64"])
+    assert np.abs(rec.cpu().numpy() - g["rec64"]).max() <= 1e-3
+    assert np.abs(lmin.cpu().numpy() - g["loss_min64"]).max() <= 1e-4
+    # rows are coupled: dropping one image changes the others' reconstructions (unlike the no-BN path)
+    rec_sub = gen.reconstruct(x[:-1], R, L, float(g["lr"]), z_init_val=z0[:-R])
+    assert not torch.equal(rec_sub, rec[:-1])
+    gen.close()
