@@ -667,6 +667,7 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
       if ((rc = dev_alloc(c.get(), (void**)&c->tc.dbg, (size_t)64 * 160 * 8 * sizeof(unsigned long long)))) return fail(rc);
       DGAN_CUDA_CHECK(cudaMemsetAsync(c->tc.dbg, 0, (size_t)64 * 160 * 8 * sizeof(unsigned long long), s));
     }
+    c->tc.allocs = &c->allocs;
     if (c->tc.mode == 2) {
       if ((rc = tc2_optin_all())) return fail(rc);
       for (size_t l = 0; l < c->layers.size(); ++l) {

@@ -58,6 +58,7 @@ struct TcState {
   void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
   unsigned long long* dbg = nullptr;   // DGAN_TC_DEBUG=1: [launch][cta][8] role-timing counters
   int dbg_launch = 0, dbg_max_launches = 0, dbg_flags = 0;
+  std::vector<void*>* allocs = nullptr;   // the handle's allocation list (lazily built schedules are freed with it)
   int num_sms = 148;
 };
 

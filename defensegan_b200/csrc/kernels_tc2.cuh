@@ -417,20 +417,25 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct TcWeights2 {
-  CUtensorMap tm_b;            // box {64, N/2, 1}
+struct Tc2Schedule {           // one window tiling of a layer-direction, uploaded
   TcItem2* items = nullptr;
   TcStep2* steps = nullptr;
   int n_windows = 0;
+  int wh = 0, ww = 0;
+};
+struct TcWeights2 {
+  CUtensorMap tm_b;            // box {64, N/2, 1}
+  PairTable tab;               // host copy: schedules are built lazily per batch size
+  int h_grid = 0, w_grid = 0, max_acc = 1;
+  mutable std::vector<std::pair<int, Tc2Schedule>> by_mpairs;   // chosen schedule per n_mpairs (lazy cache)
+  mutable std::vector<Tc2Schedule> built;                       // distinct (wh, ww) tilings built so far
 };
 
 static int tc2_maxb(int N) { return TC2_BUF_COLS / std::max(N, 64); }
 
-// windows of up to `max_acc` output pixels: 8 -> 2 rows x 4 cols, 4 -> 2x2, 2 -> 1x2, 1 -> 1x1
-static void tc2_build_schedule(const PairTable& tab, int h_grid, int w_grid, int N, int K, int max_acc,
+// windows of wh x ww output pixels (wh*ww accumulators)
+static void tc2_build_schedule(const PairTable& tab, int h_grid, int w_grid, int N, int K, int wh, int ww,
                                std::vector<TcItem2>* items, std::vector<TcStep2>* steps) {
-  const int wh = max_acc >= 4 ? 2 : 1;
-  const int ww = max_acc >= 8 ? 4 : (max_acc >= 2 ? 2 : 1);
   const int kch = K / 64;
   const size_t maxb = (size_t)tc2_maxb(N);
   for (int y0 = 0; y0 < h_grid; y0 += wh)
@@ -478,20 +483,69 @@ static void tc2_build_schedule(const PairTable& tab, int h_grid, int w_grid, int
 
 static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2, const PairTable& tab, int h_grid,
                                int w_grid, int force_max_acc, std::vector<void*>* allocs, cudaStream_t s) {
+  (void)allocs; (void)s;
   const int N = w1.N, K = w1.K;
   int max_acc = TC2_BUF_COLS / std::max(N, 64);
   if (force_max_acc > 0) max_acc = std::min(max_acc, force_max_acc);
-  std::vector<TcItem2> items;
-  std::vector<TcStep2> steps;
-  tc2_build_schedule(tab, h_grid, w_grid, N, K, max_acc, &items, &steps);
-  // largest windows first: with the static round-robin item -> CTA-pair mapping every pair then
-  // gets a big-to-small mix (border windows have fewer in-bounds taps), which evens out the tail
-  std::stable_sort(items.begin(), items.end(), [](const TcItem2& l, const TcItem2& r) { return l.n_steps > r.n_steps; });
-  w2->n_windows = (int)items.size();
-  int rc;
-  if ((rc = tc_upload(allocs, items.data(), items.size() * sizeof(TcItem2), (void**)&w2->items, s))) return rc;
-  if ((rc = tc_upload(allocs, steps.data(), steps.size() * sizeof(TcStep2), (void**)&w2->steps, s))) return rc;
+  w2->tab = tab; w2->h_grid = h_grid; w2->w_grid = w_grid; w2->max_acc = max_acc;
   return tc_make_map(st, &w2->tm_b, w1.w, (uint64_t)K, (uint64_t)N, (uint64_t)w1.n_tiles, (uint32_t)(N / 2));
+}
+
+// Pick (and build on first use) the window tiling for `n_mpairs` row pairs on `n_pairs` CTA pairs:
+// candidates are all wh x ww shapes that fit the accumulator buffer; each is scored by simulating
+// the static round-robin assignment with a per-item cost = bytes staged (A + half-B tiles) + a fixed
+// per-accumulator epilogue charge, and the smallest makespan wins (fits the item count to the machine:
+// e.g. 160 equal items on 74 pairs run 3 waves, 280 smaller ones 3.8).
+static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int n_pairs,
+                            std::vector<void*>* allocs, cudaStream_t s, const Tc2Schedule** out) {
+  for (auto& kv : w2.by_mpairs)
+    if (kv.first == n_mpairs) { *out = &kv.second; return 0; }
+  const int N = w1.N, K = w1.K;
+  const double half_b = (double)(N / 2) * 128.0, a_bytes = (double)TC_A_BYTES;
+  double best_cost = 1e300;
+  int best_wh = 1, best_ww = 1;
+  std::vector<TcItem2> best_items;
+  std::vector<TcStep2> best_steps;
+  for (int wh = 1; wh <= 2; ++wh)
+    for (int ww = 1; ww <= 4; ++ww) {
+      if (wh * ww > w2.max_acc || wh > w2.h_grid || ww > std::max(w2.w_grid, 1)) continue;
+      std::vector<TcItem2> items;
+      std::vector<TcStep2> steps;
+      tc2_build_schedule(w2.tab, w2.h_grid, w2.w_grid, N, K, wh, ww, &items, &steps);
+      std::stable_sort(items.begin(), items.end(), [](const TcItem2& l, const TcItem2& r) { return l.n_steps > r.n_steps; });
+      std::vector<double> icost(items.size());
+      for (size_t i = 0; i < items.size(); ++i) {
+        double c = 0.0;
+        for (uint32_t k = 0; k < items[i].n_steps; ++k) {
+          const int nb = (steps[items[i].step_beg + k].w0 >> 24) & 0xFF;
+          c += a_bytes + nb * half_b;
+        }
+        icost[i] = c + 24.0 * 1024.0 * items[i].n_acc * std::max(1, N / 64) + 48.0 * 1024.0;   // epilogue + per-item fixed
+      }
+      std::vector<double> load((size_t)n_pairs, 0.0);
+      const long long total = (long long)items.size() * n_mpairs;
+      for (long long idx = 0; idx < total; ++idx) load[(size_t)(idx % n_pairs)] += icost[(size_t)(idx / n_mpairs)];
+      const double makespan = *std::max_element(load.begin(), load.end());
+      if (makespan < best_cost) { best_cost = makespan; best_wh = wh; best_ww = ww; best_items.swap(items); best_steps.swap(steps); }
+    }
+  const Tc2Schedule* found = nullptr;
+  for (auto& b : w2.built)
+    if (b.wh == best_wh && b.ww == best_ww) found = &b;
+  if (found == nullptr) {
+    Tc2Schedule sc;
+    sc.wh = best_wh; sc.ww = best_ww; sc.n_windows = (int)best_items.size();
+    int rc;
+    if ((rc = tc_upload(allocs, best_items.data(), best_items.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
+    if ((rc = tc_upload(allocs, best_steps.data(), best_steps.size() * sizeof(TcStep2), (void**)&sc.steps, s))) return rc;
+    w2.built.push_back(sc);
+    found = &w2.built.back();
+  }
+  w2.by_mpairs.push_back({n_mpairs, *found});
+  *out = &w2.by_mpairs.back().second;
+  if (getenv("DGAN_TC_VERBOSE"))
+    fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d, %d windows\n", N, K, w2.h_grid, w2.w_grid,
+            n_mpairs, best_wh, best_ww, (*out)->n_windows);
+  return 0;
 }
 
 template <int NT, int EP, typename TOUT>
@@ -514,7 +568,7 @@ static int tc2_optin_all() {
 }
 
 template <typename TOUT>
-static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const TcWeights2& w2, const __half* in,
+static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const TcWeights2& w2m, const __half* in,
                            TOUT* out, int n_pad, int epi, const float* bias, const __half* mask_src, float out_scale,
                            cudaStream_t s, const TcFinalArgs* final_args = nullptr) {
   TcFinalArgs fa{};
@@ -531,15 +585,18 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   }
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
   const int n_mpairs = n_pad / (2 * kRowTile);
-  const int total = w2.n_windows * n_mpairs;
+  const Tc2Schedule* schp = nullptr;
+  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, st.num_sms / 2, st.allocs, s, &schp))) return rc;
+  const Tc2Schedule& w2s = *schp;
+  const int total = w2s.n_windows * n_mpairs;
   const int grid = 2 * std::min(total, st.num_sms / 2);
   cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
-                  tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.steps, w2s.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
-                  tm_a, w2.tm_b, tm_out, tm_mask, w2.items, w2.steps, w2.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
+                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.steps, w2s.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
                   mask_src, out_scale, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
