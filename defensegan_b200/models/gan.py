@@ -18,7 +18,9 @@ any batch size works (superset of the reference's static-shape graph, SURVEY F10
 from __future__ import annotations
 
 import os
-from typing import Dict, Optional
+import pickle
+import time
+from typing import Callable, Dict, Iterable, Optional
 
 import numpy as np
 import torch
@@ -216,6 +218,142 @@ class DefenseGANBase(object):
                                  momentum=float(self.rec_momentum), decay_lr=bool(self.rec_decay_lr), out=out,
                                  return_aux=return_aux)
         return res
+
+    # -- bulk offline reconstruction + its on-disk cache (reference models/gan.py:451-587, 604-646) --------------
+    def set_dataset_generators(self, train: Optional[Callable] = None, dev: Optional[Callable] = None,
+                               test: Optional[Callable] = None) -> None:
+        """The reference binds `train_gen_test` / `dev_gen_test` / `test_gen_test` to its dataset readers
+        (models/gan.py:666-673; out of scope here).  Each is a zero-argument callable returning an iterable of
+        `(images, targets)` batches of RAW images (what `real_data_test_pl` is fed with); `input_transform` is applied."""
+        if train is not None:
+            self.train_gen_test = train
+        if dev is not None:
+            self.dev_gen_test = dev
+        if test is not None:
+            self.test_gen_test = test
+
+    def rec_cache_dir(self, split: str, max_num: int = -1) -> str:
+        """`<checkpoint_dir>/recs_rr{R}_lr{lr:.5f}_iters{L}[_num{n}]/<split>[_debug]` - the directory name the
+        callers parse back with `recs_rr(.*)_lr(.*)_iters(.*)` (blackbox.py:646-651)."""
+        if max_num > 0:
+            name = 'recs_rr{:d}_lr{:.5f}_iters{:d}_num{:d}'.format(int(self.rec_rr), float(self.rec_lr),
+                                                                   int(self.rec_iters), int(max_num))
+        else:
+            name = 'recs_rr{:d}_lr{:.5f}_iters{:d}'.format(int(self.rec_rr), float(self.rec_lr), int(self.rec_iters))
+        out = os.path.join(self.checkpoint_dir, name, split)
+        if self.debug:
+            out += '_debug'
+        return out
+
+    def _transformed_batch(self, images) -> torch.Tensor:
+        x = self.input_transform(np.asarray(images))
+        x = x.reshape([-1] + list(self.image_dim))
+        return x
+
+    def reconstruct_dataset(self, ckpt_path=None, max_num=-1, max_num_load=-1):
+        """Reconstructs the train/dev/test splits batch by batch, with the reference's per-image pickle
+        cache `pickles/rec_{idx:07d}_l{label}.pkl` and whole-split `feats.pkl`.  Returns
+        `{split: [all_recs, all_targets, orig_imgs]}` (numpy, images `[-1] + image_dim`)."""
+        if not self.initialized:
+            self.load_generator(ckpt_path=ckpt_path)
+        rets = {}
+        for split in ['train', 'dev', 'test']:
+            gen_func = getattr(self, '{}_gen_test'.format(split), None)
+            if gen_func is None:
+                raise RuntimeError("no '{}_gen_test' generator bound: call set_dataset_generators(...) first "
+                                   "(dataset readers are outside this package)".format(split))
+            output_dir = self.rec_cache_dir(split, max_num)
+            os.makedirs(output_dir, exist_ok=True)
+            feats_path = os.path.join(output_dir, 'feats.pkl')
+            could_load = False
+            all_recs = []
+            try:
+                if os.path.exists(feats_path) and not self.test_again:
+                    with open(feats_path, 'rb') as f:
+                        all_recs = pickle.load(f)
+                        could_load = True
+                        if self.verbose:
+                            print('[#] Successfully loaded features.')
+            except Exception as e:  # same tolerance as the reference (gan.py:486-496)
+                all_recs = []
+                print('[#] Exception loading features {}'.format(str(e)))
+            all_targets, orig_imgs = [], []
+            ctr = 0
+            sti = time.time()
+            pickle_out_dir = os.path.join(output_dir, 'pickles')
+            os.makedirs(pickle_out_dir, exist_ok=True)
+            template = os.path.join(pickle_out_dir, 'rec_{:07d}_l{}.pkl')
+            for images, targets in gen_func():
+                batch_size = len(images)
+                im_paths = [template.format(ctr * batch_size + i, targets[i]) for i in range(batch_size)]
+                mn = max(max_num, max_num_load)
+                if (mn > -1 and ctr * batch_size > mn) or (self.debug and ctr > 2):
+                    break
+                batch_could_load = not self.test_again
+                batch_rec_list = []
+                if batch_could_load:
+                    for imp in im_paths:            # per-image cache
+                        try:
+                            with open(imp, 'rb') as f:
+                                batch_rec_list.append(pickle.load(f))
+                        except Exception:
+                            batch_could_load = False
+                            break
+                x = self._transformed_batch(images)
+                recs = None
+                if batch_could_load and not could_load:
+                    recs = np.stack(batch_rec_list)
+                    all_recs.append(recs)
+                if not (could_load or batch_could_load):
+                    recs = self.reconstruct(x).detach().cpu().numpy()      # fresh z0 / momentum per batch (gan.py:541)
+                    if self.verbose:
+                        print('[#] t:{:.2f} batch: {:d} '.format(time.time() - sti, ctr))
+                    all_recs.append(recs)
+                    for i in range(len(recs)):
+                        with open(im_paths[i], 'wb') as f:
+                            pickle.dump(recs[i], f, protocol=pickle.HIGHEST_PROTOCOL)
+                elif self.verbose:
+                    print('[*] could load batch: {:d}'.format(ctr))
+                all_targets.append(np.asarray(targets))
+                orig_imgs.append(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x))
+                ctr += 1
+            if not could_load:
+                all_recs = np.concatenate(all_recs).reshape([-1] + list(self.image_dim)) if all_recs else \
+                    np.zeros([0] + list(self.image_dim), dtype=np.float32)
+            orig_imgs = np.concatenate(orig_imgs).reshape([-1] + list(self.image_dim)) if orig_imgs else \
+                np.zeros([0] + list(self.image_dim), dtype=np.float32)
+            all_targets = np.concatenate(all_targets) if all_targets else np.zeros([0], dtype=np.int64)
+            rets[split] = [all_recs, all_targets, orig_imgs]
+        return rets
+
+    def save_recs(self, rets: Dict, max_num: int = -1) -> None:
+        """Write `feats.pkl` for each split so that the next reconstruct_dataset (and the callers' cache
+        loaders, blackbox.py:249-259,294-329) short-cut.  The reference leaves this to train.py --save_recs."""
+        for split, (all_recs, all_targets, orig_imgs) in rets.items():
+            with open(os.path.join(self.rec_cache_dir(split, max_num), 'feats.pkl'), 'wb') as f:
+                pickle.dump(all_recs, f, pickle.HIGHEST_PROTOCOL)
+
+    def save_ds(self):
+        """Dump the input-transformed dataset: `data/cache/<dataset>_pkl/<split>/feats.pkl` holding two
+        consecutive pickles (images, targets) - the layout blackbox.get_cached_gan_data reads (:332-367)."""
+        for split in ['train', 'dev', 'test']:
+            output_dir = os.path.join('data', 'cache', '{}_pkl'.format(self.dataset_name), split)
+            if self.debug:
+                output_dir += '_debug'
+            os.makedirs(output_dir, exist_ok=True)
+            path = os.path.join(output_dir, 'feats.pkl')
+            if os.path.exists(path) and not self.test_again:
+                print('[#] Dataset is already saved.')
+                return
+            gen_func = getattr(self, '{}_gen_test'.format(split))
+            imgs, tgts = [], []
+            for images, targets in gen_func():
+                x = self._transformed_batch(images)
+                imgs.append(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x))
+                tgts.append(np.asarray(targets))
+            with open(path, 'wb') as f:
+                pickle.dump(np.concatenate(imgs).reshape([-1] + list(self.image_dim)), f, pickle.HIGHEST_PROTOCOL)
+                pickle.dump(np.concatenate(tgts), f, pickle.HIGHEST_PROTOCOL)
 
     def close(self):
         self._drop_native()

@@ -188,3 +188,59 @@ def test_sharded_gather_gloo_world2(n_images):
         p.join(120)
         assert p.exitcode == 0
     assert ret[0] and ret[1]
+
+
+def test_reconstruct_dataset_cache_format(tmp_path, monkeypatch):
+    """f1 (reference models/gan.py:451-587): directory naming, per-image pickles, feats.pkl short-cut and the
+    regex the callers use to parse hyper-parameters back out of the path (blackbox.py:646-651)."""
+    import pickle
+    import re
+    from defensegan_b200.models.gan import MnistDefenseGAN
+    gan = MnistDefenseGAN(test_mode=True, verbose=False, output_dir=str(tmp_path))
+    gan.initialized = True
+    gan.rec_rr, gan.rec_lr, gan.rec_iters = 2, 0.5, 3
+    calls = []
+
+    def fake_reconstruct(x, **kw):                 # the projector needs a GPU; the cache logic does not
+        calls.append(int(x.shape[0]))
+        return x * 0.5
+
+    monkeypatch.setattr(gan, "reconstruct", fake_reconstruct)
+    rs = np.random.RandomState(0)
+    data = {sp: (rs.randint(0, 256, size=(n, 28, 28, 1)).astype("uint8"), np.arange(n) % 10)
+            for sp, n in (("train", 5), ("dev", 3), ("test", 4))}
+
+    def gen(sp, bs=2):
+        def g():
+            x, y = data[sp]
+            for i in range(0, len(x), bs):
+                yield x[i:i + bs], y[i:i + bs]
+        return g
+
+    gan.set_dataset_generators(train=gen("train"), dev=gen("dev"), test=gen("test"))
+    rets = gan.reconstruct_dataset()
+    assert calls == [2, 2, 1, 2, 1, 2, 2]
+    d = gan.rec_cache_dir("test")
+    assert d == os.path.join(str(tmp_path), "gans", "mnist", "recs_rr2_lr0.50000_iters3", "test")
+    assert re.compile("recs_rr(.*)_lr(.*)_iters(.*)").findall(os.path.dirname(d))[0] == ("2", "0.50000", "3")
+    recs, targets, orig = rets["test"]
+    assert recs.shape == (4, 28, 28, 1) and orig.shape == (4, 28, 28, 1) and list(targets) == [0, 1, 2, 3]
+    np.testing.assert_allclose(orig, data["test"][0] / 255.0, rtol=1e-6)
+    np.testing.assert_allclose(recs, orig * 0.5, rtol=1e-6)
+    with open(os.path.join(d, "pickles", "rec_0000003_l3.pkl"), "rb") as f:
+        np.testing.assert_allclose(pickle.load(f), recs[3])
+    # second call: every batch comes from the per-image cache, no projection runs
+    calls.clear()
+    rets2 = gan.reconstruct_dataset()
+    assert calls == []
+    np.testing.assert_array_equal(rets2["train"][0], rets["train"][0])
+    # feats.pkl short-cut
+    gan.save_recs(rets)
+    assert os.path.isfile(os.path.join(d, "feats.pkl"))
+    rets3 = gan.reconstruct_dataset()
+    np.testing.assert_array_equal(rets3["dev"][0], rets["dev"][0])
+    # test_again forces recomputation; max_num changes the directory name
+    gan.test_again = True
+    gan.reconstruct_dataset()
+    assert calls == [2, 2, 1, 2, 1, 2, 2]
+    assert gan.rec_cache_dir("dev", max_num=100).endswith(os.path.join("recs_rr2_lr0.50000_iters3_num100", "dev"))
