@@ -138,6 +138,12 @@ struct dgan_ctx {
   TcWeights2 tc2_fin_f, tc2_fin_b;
   // optional per-launch CUDA-event timing (dgan_profile_*): serialises nothing by itself but
   // adds two event records per launch, so it is never enabled in a timed benchmark pass
+  // the images of a call are split into `n_chains` independent dependency chains on separate streams so that
+  // one chain's kernel tails / launch gaps are filled by the other's CTAs
+  int n_chains = 1;
+  std::vector<cudaStream_t> chain_streams;
+  std::vector<cudaEvent_t> chain_events;
+  cudaEvent_t fork_event = nullptr;
   bool profile = false;
   int n_rows_cur = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -215,6 +221,10 @@ struct Workspace {
   std::vector<__half*> act_h, dact_h;  // fp16 path
   __half* z_h = nullptr;
   std::vector<unsigned long long*> maskbits;   // fp16 path: 1-bit ReLU masks per hidden layer output
+  // fp16 CTA-pair path: TMA descriptors of every launch site, encoded once per workspace
+  // index 2l = forward of layer l (in, out), 2l+1 = backward of layer l; 2nl = last-layer forward, 2nl+1 = its backward
+  std::vector<CUtensorMap> map_in, map_out;
+  bool have_maps = false;
   __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
   int n_loss_parts = 0, n_g_parts = 1;
   float *y = nullptr, *dpre = nullptr, *loss_part = nullptr, *loss = nullptr;
@@ -345,7 +355,34 @@ static int launch_final_bwd(dgan_ctx* c, const Workspace& w, const TOUT* mask_sr
 
 static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
                       int epi, const float* bias, const __half* mask_src, cudaStream_t s,
-                      unsigned long long* mb_out = nullptr, const unsigned long long* mb_in = nullptr);
+                      unsigned long long* mb_out = nullptr, const unsigned long long* mb_in = nullptr,
+                      const CUtensorMap* pre_a = nullptr, const CUtensorMap* pre_out = nullptr);
+
+// Encode the TMA descriptors of all launch sites for this workspace (once per call instead of per launch).
+static int build_maps(dgan_ctx* c, Workspace& w) {
+  if (c->desc.precision != DGAN_PREC_FP16 || c->tc.mode != 2) return 0;
+  const int nl = (int)c->layers.size();
+  w.map_in.assign((size_t)2 * nl + 2, CUtensorMap{});
+  w.map_out.assign((size_t)2 * nl + 2, CUtensorMap{});
+  int rc;
+  auto mk = [&](CUtensorMap* m, const void* base, int K, int P) {
+    return tc_make_map(c->tc, m, base, (uint64_t)K, (uint64_t)w.n_pad, (uint64_t)P, 128);
+  };
+  for (int l = 0; l < nl; ++l) {
+    const GemmLayer& L = c->layers[l];
+    const void* fin = (l == 0) ? (const void*)w.z_h : (const void*)w.act_h[l - 1];
+    if ((rc = mk(&w.map_in[2 * l], fin, L.C_in, L.P_in))) return rc;
+    if ((rc = mk(&w.map_out[2 * l], w.act_h[l], L.C_out, L.P_out))) return rc;
+    if ((rc = mk(&w.map_in[2 * l + 1], w.dact_h[l], L.C_out, L.P_out))) return rc;
+    if (l >= 1 && (rc = mk(&w.map_out[2 * l + 1], w.dact_h[l - 1], L.C_in, L.P_in))) return rc;
+  }
+  const GemmLayer& last = c->layers[nl - 1];
+  if ((rc = mk(&w.map_in[2 * nl], w.act_h[nl - 1], c->fin.C_in, last.P_out))) return rc;
+  if ((rc = mk(&w.map_in[2 * nl + 1], w.dblk, 64, c->tc_fin.n_blocks))) return rc;
+  if ((rc = mk(&w.map_out[2 * nl + 1], w.dact_h[nl - 1], last.C_out, last.P_out))) return rc;
+  w.have_maps = true;
+  return 0;
+}
 
 // ---- one generator forward (+ loss and dL/dpre when x != null) ---------------------------
 static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, int B, bool want_grad,
@@ -358,7 +395,8 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
       const GemmLayer& L = c->layers[l];
       ProfScope ps(c, 2 * l, s);
       if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, nullptr, s,
-                           (L.relu && want_grad) ? w.maskbits[l] : nullptr, nullptr)))
+                           (L.relu && want_grad) ? w.maskbits[l] : nullptr, nullptr,
+                           w.have_maps ? &w.map_in[2 * l] : nullptr, w.have_maps ? &w.map_out[2 * l] : nullptr)))
         return rc;
       in = w.act_h[l];
     }
@@ -368,7 +406,8 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     fa.nbx = c->tc_fin.nbx; fa.w_out = c->tc_fin.w_out; fa.gscale = c->tc.grad_scale;
     if (c->tc.mode == 2)
       return tc2_launch_impl<__half>(c->tc, &c->launches, c->tc_fin.f, c->tc2_fin_f, in, w.dblk, w.n_pad,
-                                     c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, c->fin.bias, nullptr, 1.f, s, &fa);
+                                     c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, c->fin.bias, nullptr, 1.f, s, &fa,
+                                     w.have_maps ? &w.map_in[2 * nl] : nullptr, nullptr);
     return tc_launch_final_fwd(c->tc, &c->launches, c->tc_fin, in, w.dblk, w.n_pad, c->fin.bias, fa, s);
   }
   const float* in = w.z;
@@ -417,7 +456,8 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
     {
       ProfScope ps(c, 2 * nl + 1, s);
       if ((rc = tcx_launch(c, c->tc_fin.b, c->tc2_fin_b, w.dblk, w.dact_h[nl - 1], w.n_pad, last.relu ? EPI_MASK : EPI_NONE,
-                           nullptr, last.relu ? w.act_h[nl - 1] : nullptr, s, nullptr, last.relu ? w.maskbits[nl - 1] : nullptr)))
+                           nullptr, last.relu ? w.act_h[nl - 1] : nullptr, s, nullptr, last.relu ? w.maskbits[nl - 1] : nullptr,
+                           w.have_maps ? &w.map_in[2 * nl + 1] : nullptr, w.have_maps ? &w.map_out[2 * nl + 1] : nullptr)))
         return rc;
     }
     for (int l = nl - 1; l >= 1; --l) {
@@ -425,7 +465,8 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
       const bool mask = c->layers[l - 1].relu;
       ProfScope ps(c, 2 * l + 1, s);
       if ((rc = tcx_launch(c, L.tc_b, L.tc2_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad, mask ? EPI_MASK : EPI_NONE, nullptr,
-                           mask ? w.act_h[l - 1] : nullptr, s, nullptr, mask ? w.maskbits[l - 1] : nullptr)))
+                           mask ? w.act_h[l - 1] : nullptr, s, nullptr, mask ? w.maskbits[l - 1] : nullptr,
+                           w.have_maps ? &w.map_in[2 * l + 1] : nullptr, w.have_maps ? &w.map_out[2 * l + 1] : nullptr)))
         return rc;
     }
     const GemmLayer& L0 = c->layers[0];
@@ -434,10 +475,11 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
       TcFinalArgs fa{};
       fa.mz = w.z; fa.mv = w.v; fa.mz_h = w.z_h; fa.m_gmul = grad_multiplier(c); fa.m_lr = mom.lr; fa.m_mu = mom.mu;
       return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b_fused, w.dact_h[0], w.g, w.n_pad, EPI_MOMENTUM, nullptr,
-                                    nullptr, 1.f, s, &fa);
+                                    nullptr, 1.f, s, &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
     }
     if (c->tc.mode == 2)
-      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s);
+      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s,
+                                    nullptr, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
     return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
   }
   // d(act) -> d(pre) through ReLU + batch-statistics BN of layer l (in place in w.dact[l])
@@ -481,11 +523,11 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
                            L0.C_in, nullptr, 0, nullptr, s);
 }
 
-static int run_init_z(dgan_ctx* c, const Workspace& w, const float* z0, uint64_t seed, cudaStream_t s) {
+static int run_init_z(dgan_ctx* c, const Workspace& w, const float* z0, uint64_t seed, cudaStream_t s, size_t row_offset = 0) {
   const int latent = c->desc.latent_dim;
   const size_t total4 = (size_t)w.n_pad * latent / 4;
   init_z_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(w.z, w.v, w.z_h, z0, w.n_rows, w.n_pad, latent, seed,
-                                                                 sqrtf(1.0f / (float)latent));
+                                                                 sqrtf(1.0f / (float)latent), row_offset * latent);
   DGAN_LAUNCH_CHECK(c);
   return 0;
 }
@@ -504,11 +546,11 @@ static int check_ws(const dgan_ctx* c, int n_rows, void* ws, size_t ws_bytes, Wo
 // tensor-core launch, dispatching on the kernel generation
 static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
                       int epi, const float* bias, const __half* mask_src, cudaStream_t s, unsigned long long* mb_out,
-                      const unsigned long long* mb_in) {
+                      const unsigned long long* mb_in, const CUtensorMap* pre_a, const CUtensorMap* pre_out) {
   if (c->tc.mode == 2) {
     TcFinalArgs fa{};
     fa.mb_out = mb_out; fa.mb_in = mb_in;
-    return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, mask_src, 1.f, s, &fa);
+    return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, mask_src, 1.f, s, &fa, pre_a, pre_out);
   }
   return tc_launch(c->tc, &c->launches, w1, in, out, n_pad, epi, bias, mask_src, 1.f, s);
 }
@@ -687,6 +729,20 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     }
   }
   {
+    const char* ch_env = getenv("DGAN_CHAINS");
+    // measured (tools/enqueue_time.py, bench): 2 chains alternate kernels instead of overlapping them (each persistent
+    // kernel takes all 74 CTA pairs) - no gain, so the default stays 1; DGAN_CHAINS=k keeps the experiment available
+    c->n_chains = ch_env ? std::max(1, std::min(8, atoi(ch_env))) : 1;
+    if (d->use_bn) c->n_chains = 1;      // batch statistics couple all rows of a call
+    for (int k = 1; k < c->n_chains; ++k) {
+      cudaStream_t st; cudaEvent_t ev;
+      DGAN_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      DGAN_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      c->chain_streams.push_back(st); c->chain_events.push_back(ev);
+    }
+    DGAN_CUDA_CHECK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
+  }
+  {
     static const char* lname_m[] = {"Linear", "Generator.2", "Generator.3"};
     static const char* lname_c[] = {"Linear", "Generator.2", "Generator.3", "Generator.5"};
     for (size_t l = 0; l < c->layers.size(); ++l) {
@@ -711,14 +767,31 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
 int dgan_destroy(dgan_handle h) {
   if (h == nullptr) return DGAN_OK;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaStream_t st : h->chain_streams) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : h->chain_events) cudaEventDestroy(ev);
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return DGAN_OK;
 }
 
+// images [lo, hi) of chain k when `batch` images are split into n balanced contiguous chains
+static inline void chain_bounds(int batch, int n, int k, int* lo, int* hi) {
+  const int base = batch / n, extra = batch % n;
+  *lo = k * base + std::min(k, extra);
+  *hi = *lo + base + (k < extra ? 1 : 0);
+}
+
 size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
   if (h == nullptr || batch <= 0 || rec_rr <= 0) return 0;
-  return carve(h, batch * rec_rr, nullptr).bytes;
+  const int n = std::min(h->n_chains, batch);
+  size_t total = 0;
+  for (int k = 0; k < n; ++k) {
+    int lo, hi;
+    chain_bounds(batch, n, k, &lo, &hi);
+    total += carve(h, (hi - lo) * rec_rr, nullptr).bytes;
+  }
+  return std::max(total, carve(h, batch * rec_rr, nullptr).bytes);   // dgan_forward / dgan_loss_grad use one chain
 }
 
 int64_t dgan_last_launch_count(dgan_handle h) { return h ? h->last_launches : 0; }
@@ -765,40 +838,78 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
                      int32_t* idx_dev, void* ws, size_t ws_bytes, void* stream) {
   if (h == nullptr || x_dev == nullptr || rec_dev == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
   if (batch <= 0 || rec_rr <= 0 || rec_iters <= 0) { set_error("batch, rec_rr and rec_iters must be positive"); return DGAN_ERR_INVALID_ARG; }
-  cudaStream_t s = (cudaStream_t)stream;
-  const int n_rows = batch * rec_rr;
-  Workspace w;
+  if (ws == nullptr) { set_error("workspace is NULL"); return DGAN_ERR_WORKSPACE; }
+  if (((uintptr_t)ws & 1023) != 0) { set_error("workspace must be 1024-byte aligned"); return DGAN_ERR_WORKSPACE; }
+  if (dgan_workspace_bytes(h, batch, rec_rr) > ws_bytes) {
+    set_error("workspace too small: need " + std::to_string(dgan_workspace_bytes(h, batch, rec_rr)) + " bytes, got " + std::to_string(ws_bytes));
+    return DGAN_ERR_WORKSPACE;
+  }
+  cudaStream_t s0 = (cudaStream_t)stream;
+  const int n_chains = h->profile ? 1 : std::min(h->n_chains, batch);   // per-kernel timing wants one chain
+  const int latent = h->desc.latent_dim;
+  struct Chain { Workspace w; cudaStream_t s; int lo, hi; };
+  std::vector<Chain> chains((size_t)n_chains);
+  size_t off = 0;
+  for (int k = 0; k < n_chains; ++k) {
+    Chain& ch = chains[(size_t)k];
+    chain_bounds(batch, n_chains, k, &ch.lo, &ch.hi);
+    ch.w = carve(h, (ch.hi - ch.lo) * rec_rr, (char*)ws + off);
+    off += ch.w.bytes;
+    int mrc;
+    if ((mrc = build_maps(h, ch.w))) return mrc;
+    ch.s = (k == 0) ? s0 : h->chain_streams[(size_t)k - 1];
+  }
   int rc;
-  if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
   const int64_t launches0 = h->launches;
-  h->n_rows_cur = n_rows;
-  if ((rc = run_init_z(h, w, z0_dev, seed, s))) return rc;
-  const size_t zcount = (size_t)w.n_pad * h->desc.latent_dim;
+  h->n_rows_cur = batch * rec_rr;
+  if (n_chains > 1) {
+    DGAN_CUDA_CHECK(cudaEventRecord(h->fork_event, s0));
+    for (int k = 1; k < n_chains; ++k) DGAN_CUDA_CHECK(cudaStreamWaitEvent(chains[(size_t)k].s, h->fork_event, 0));
+  }
+  for (Chain& ch : chains) {
+    const size_t row_off = (size_t)ch.lo * rec_rr;
+    if ((rc = run_init_z(h, ch.w, z0_dev ? z0_dev + row_off * latent : nullptr, seed, ch.s, row_off))) return rc;
+  }
   const int decay_iter = (int)std::ceil(rec_iters * 0.8);
   for (int t = 0; t < rec_iters; ++t) {
     const bool last = (t == rec_iters - 1);
-    // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
-    // the L-th update is never observed, so its backward pass is not run.
-    if ((rc = run_forward(h, w, x_dev, rec_rr, batch, !last, s))) return rc;
-    if (last) break;
     float lr = rec_lr;
     if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
     // fused Linear-backward + momentum epilogue exists (EPI_MOMENTUM) but measured slower than split-K + momentum_kernel
     const bool fused = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 && getenv("DGAN_FUSED_MOMENTUM") != nullptr;
-    MomentumArgs mom;
-    mom.fused = fused; mom.lr = lr; mom.mu = momentum;
-    if ((rc = run_backward(h, w, s, mom))) return rc;
-    if (!fused) {
-      ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
-      DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
-                                 (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
-      DGAN_LAUNCH_CHECK(h);
+    for (Chain& ch : chains) {
+      const Workspace& w = ch.w;
+      cudaStream_t s = ch.s;
+      const float* x = x_dev + (size_t)ch.lo * h->hwc;
+      // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
+      // the L-th update is never observed, so its backward pass is not run.
+      if ((rc = run_forward(h, w, x, rec_rr, ch.hi - ch.lo, !last, s))) return rc;
+      if (last) continue;
+      MomentumArgs mom;
+      mom.fused = fused; mom.lr = lr; mom.mu = momentum;
+      if ((rc = run_backward(h, w, s, mom))) return rc;
+      if (!fused) {
+        const size_t zcount = (size_t)w.n_pad * latent;
+        ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
+        DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
+                                   (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
+        DGAN_LAUNCH_CHECK(h);
+      }
     }
   }
-  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, 1.0f / (float)h->hwc, n_rows, w.loss);
-  DGAN_LAUNCH_CHECK(h);
-  select_kernel<<<batch, 256, 0, s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev, loss_dev, idx_dev);
-  DGAN_LAUNCH_CHECK(h);
+  for (Chain& ch : chains) {
+    const Workspace& w = ch.w;
+    const int nb = ch.hi - ch.lo, n_rows = nb * rec_rr;
+    loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, ch.s>>>(w.loss_part, w.n_loss_parts, 1.0f / (float)h->hwc, n_rows, w.loss);
+    DGAN_LAUNCH_CHECK(h);
+    select_kernel<<<nb, 256, 0, ch.s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev + (size_t)ch.lo * h->hwc,
+                                         loss_dev ? loss_dev + ch.lo : nullptr, idx_dev ? idx_dev + ch.lo : nullptr);
+    DGAN_LAUNCH_CHECK(h);
+  }
+  for (int k = 1; k < n_chains; ++k) {
+    DGAN_CUDA_CHECK(cudaEventRecord(h->chain_events[(size_t)k - 1], chains[(size_t)k].s));
+    DGAN_CUDA_CHECK(cudaStreamWaitEvent(s0, h->chain_events[(size_t)k - 1], 0));
+  }
   h->last_launches = h->launches - launches0;
   return DGAN_OK;
 }

@@ -308,7 +308,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // Rows >= n_rows (tile padding) are zeroed.
 __global__ void init_z_kernel(float* __restrict__ z, float* __restrict__ v, __half* __restrict__ z_h,
                               const float* __restrict__ z0, int n_rows, int n_pad, int latent,
-                              uint64_t seed, float stddev) {
+                              uint64_t seed, float stddev, size_t elem_offset) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 4 consecutive values
   const size_t total4 = (size_t)n_pad * latent / 4;
   if (q >= total4) return;
@@ -319,7 +319,8 @@ __global__ void init_z_kernel(float* __restrict__ z, float* __restrict__ v, __ha
     if (z0 != nullptr) {
       val = *reinterpret_cast<const float4*>(z0 + e);
     } else {
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u),
+      const size_t gq = q + elem_offset / 4;   // counter = global element index / 4: independent of how the batch is chained
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), 0u, 0u),
                                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
       const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f;
       const float u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;

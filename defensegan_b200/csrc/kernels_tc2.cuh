@@ -570,7 +570,8 @@ static int tc2_optin_all() {
 template <typename TOUT>
 static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const TcWeights2& w2m, const __half* in,
                            TOUT* out, int n_pad, int epi, const float* bias, const __half* mask_src, float out_scale,
-                           cudaStream_t s, const TcFinalArgs* final_args = nullptr) {
+                           cudaStream_t s, const TcFinalArgs* final_args = nullptr, const CUtensorMap* pre_a = nullptr,
+                           const CUtensorMap* pre_out = nullptr) {
   TcFinalArgs fa{};
   if (final_args) fa = *final_args;
   fa.dbg = nullptr;
@@ -578,10 +579,12 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   if (st.dbg != nullptr && st.dbg_launch < st.dbg_max_launches) fa.dbg = st.dbg + (size_t)(st.dbg_launch++) * 160 * 8;
   CUtensorMap tm_a;
   int rc;
-  if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
+  if (pre_a != nullptr) tm_a = *pre_a;          // encoded once per workspace by the caller
+  else if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
   CUtensorMap tm_out = tm_a, tm_mask = tm_a;     // placeholders when unused
   if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT))) {
-    if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
+    if (pre_out != nullptr) tm_out = *pre_out;
+    else if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
   }
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
   const int n_mpairs = n_pad / (2 * kRowTile);

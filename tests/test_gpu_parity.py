@@ -217,3 +217,60 @@ def test_batchnorm_batch_statistics_path(golden_dir, case):
     rec_sub = gen.reconstruct(x[:-1], R, L, float(g["lr"]), z_init_val=z0[:-R])
     assert not torch.equal(rec_sub, rec[:-1])
     gen.close()
+
+
+def test_shape_fuzz_ragged_sizes(gens):
+    """Any B / R / L (superset of the reference's static shapes): tile padding, ragged CTA-pair
+    tiles and window schedules for many row counts, fp16 and fp32, against the fp32 oracle."""
+    rs = np.random.RandomState(7)
+    for trial in range(6):
+        B, R, L = int(rs.randint(1, 40)), int(rs.randint(1, 6)), int(rs.randint(1, 4))
+        arch = "mnist" if trial % 3 else "celeba"
+        if arch == "celeba":
+            B = min(B, 6)
+        for precision in PRECISIONS:
+            w, gen = gens(arch, precision, True)
+            imgs = O.synthetic_images(arch, w, B, kind="S2", seed=100 + trial)
+            z0 = O.sample_z0(B * R, 128, seed=200 + trial)
+            ref = O.reconstruct(arch, w, imgs, R, L, rec_lr=1.0, z_init_val=z0)
+            rec, loss, idx = gen.reconstruct(torch.tensor(imgs).cuda(), R, L, 1.0, z_init_val=torch.tensor(z0).cuda(),
+                                             return_aux=True)
+            t = TOL[precision]
+            assert rec.shape == imgs.shape
+            assert np.abs(rec.cpu().numpy() - ref["rec"]).max() <= t["rec"], (arch, B, R, L, precision)
+            assert np.abs(loss.cpu().numpy() - ref["loss_min"]).max() <= max(t["loss"], 1e-5)
+
+
+def test_first_generation_tensor_core_kernel_still_correct(golden_dir, monkeypatch):
+    """DGAN_TC_MODE=1 selects the one-CTA-per-MMA kernel (kernels_tc.cuh) kept as an A/B fallback."""
+    from defensegan_b200 import _native
+    monkeypatch.setenv("DGAN_TC_MODE", "1")
+    g = np.load(os.path.join(golden_dir, "mnist_c1.npz"))
+    w = O.init_generator_weights("mnist")
+    dev = torch.device("cuda", 0)
+    gen = _native.NativeGenerator("mnist", [torch.as_tensor(v).to(dev) for v in w.values()], precision="fp16", device=dev)
+    rec, loss, idx = gen.reconstruct(torch.tensor(g["images"]).cuda(), int(g["R"]), int(g["L"]), float(g["lr"]),
+                                     z_init_val=torch.tensor(g["z0"]).cuda(), return_aux=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["idx64"])
+    assert np.abs(rec.cpu().numpy() - g["rec64"]).max() <= TOL["fp16"]["rec"]
+    gen.close()
+
+
+def test_sharded_api_single_rank_and_random_z0_statistics():
+    """parallel.reconstruct_sharded degenerates to the single-GPU call without a process group; the Philox z0
+    (models/gan.py:370-377: N(0, 1/latent_dim)) does not depend on how rows are tiled."""
+    from defensegan_b200.models.gan import MnistDefenseGAN
+    from defensegan_b200.parallel import reconstruct_sharded
+    gan = MnistDefenseGAN(test_mode=True, verbose=False, precision="fp32")
+    gan.rec_rr, gan.rec_iters = 3, 2
+    x = torch.tensor(O.synthetic_images("mnist", gan.weights, 5)).cuda()
+    z0 = torch.tensor(O.sample_z0(15, 128)).cuda()
+    assert torch.equal(reconstruct_sharded(gan, x, z_init_val=z0), gan.reconstruct(x, z_init_val=z0))
+    # z0 statistics through the public path: L=1 returns G(z0) of the best restart; use the generator's Linear
+    # pre-activation scale as a proxy is overkill - check instead that two seeds differ and a seed repeats
+    nat = gan._get_native(x.device)
+    a = nat.reconstruct(x, 3, 1, 10.0, seed=123)
+    b = nat.reconstruct(x, 3, 1, 10.0, seed=123)
+    c_ = nat.reconstruct(x, 3, 1, 10.0, seed=124)
+    assert torch.equal(a, b) and not torch.equal(a, c_)
+    gan.close()
