@@ -386,7 +386,7 @@ static int build_maps(dgan_ctx* c, Workspace& w) {
 
 // ---- one generator forward (+ loss and dL/dpre when x != null) ---------------------------
 static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, int B, bool want_grad,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool want_y = true) {
   int rc;
   const int nl = (int)c->layers.size();
   if (c->desc.precision == DGAN_PREC_FP16) {
@@ -403,7 +403,7 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     ProfScope ps(c, 2 * nl, s);
     TcFinalArgs fa{};
     fa.x = x; fa.y = w.y; fa.loss_part = w.loss_part; fa.R = R; fa.B = B; fa.n_rows = w.n_rows;
-    fa.nbx = c->tc_fin.nbx; fa.w_out = c->tc_fin.w_out; fa.gscale = c->tc.grad_scale;
+    fa.nbx = c->tc_fin.nbx; fa.w_out = c->tc_fin.w_out; fa.gscale = c->tc.grad_scale; fa.write_y = want_y ? 1 : 0;
     if (c->tc.mode == 2)
       return tc2_launch_impl<__half>(c->tc, &c->launches, c->tc_fin.f, c->tc2_fin_f, in, w.dblk, w.n_pad,
                                      c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, c->fin.bias, nullptr, 1.f, s, &fa,
@@ -883,7 +883,7 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
       const float* x = x_dev + (size_t)ch.lo * h->hwc;
       // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
       // the L-th update is never observed, so its backward pass is not run.
-      if ((rc = run_forward(h, w, x, rec_rr, ch.hi - ch.lo, !last, s))) return rc;
+      if ((rc = run_forward(h, w, x, rec_rr, ch.hi - ch.lo, !last, s, /*want_y=*/last))) return rc;
       if (last) continue;
       MomentumArgs mom;
       mom.fused = fused; mom.lr = lr; mom.mu = momentum;

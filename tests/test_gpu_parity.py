@@ -274,3 +274,39 @@ def test_sharded_api_single_rank_and_random_z0_statistics():
     c_ = nat.reconstruct(x, 3, 1, 10.0, seed=124)
     assert torch.equal(a, b) and not torch.equal(a, c_)
     gan.close()
+
+
+def _model_a_like(seed=0):
+    """Random-weight stand-in for the reference's classifier A (utils/network_builder.py:412-427:
+    conv 64 5x5 s1 -> relu -> conv 64 5x5 s2 -> relu -> flatten -> dense 128 -> relu -> dense 10)."""
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(
+        torch.nn.Conv2d(1, 64, 5, padding=2), torch.nn.ReLU(), torch.nn.Conv2d(64, 64, 5, stride=2), torch.nn.ReLU(),
+        torch.nn.Flatten(), torch.nn.Linear(64 * 12 * 12, 128), torch.nn.ReLU(), torch.nn.Linear(128, 10)).eval()
+
+
+def test_full_size_fp16_vs_fp32_and_classifier_agreement(gens):
+    """BASELINE configs[1] operating point (MNIST, B=256, R=10, L=200): the fp16 tensor-core path against the
+    fp32 CUDA-core path (which is oracle-checked elementwise at the sizes the CPU oracle can run):
+    per-image |MSE_min difference| <= 1e-4 (BASELINE.json's bar), restart agreement and downstream
+    classifier arg-max agreement reported."""
+    arch = "mnist"
+    w, gen16 = gens(arch, "fp16")
+    _, gen32 = gens(arch, "fp32")
+    B, R, L = 256, 10, 200
+    x = torch.tensor(O.synthetic_images(arch, w, B)).cuda()
+    z0 = torch.tensor(O.sample_z0(B * R, 128)).cuda()
+    rec16, loss16, idx16 = gen16.reconstruct(x, R, L, 10.0, z_init_val=z0, return_aux=True)
+    rec32, loss32, idx32 = gen32.reconstruct(x, R, L, 10.0, z_init_val=z0, return_aux=True)
+    dmse = (loss16 - loss32).abs()
+    agree = float((idx16 == idx32).float().mean())
+    clf = _model_a_like().cuda()
+    with torch.no_grad():
+        p16 = clf(rec16.permute(0, 3, 1, 2)).argmax(1)
+        p32 = clf(rec32.permute(0, 3, 1, 2)).argmax(1)
+    cls_agree = float((p16 == p32).float().mean())
+    print("C2 fp16 vs fp32: max|dMSE|=%.3g mean=%.3g restart agreement=%.3f classifier agreement=%.3f" % (
+        float(dmse.max()), float(dmse.mean()), agree, cls_agree))
+    assert float(dmse.max()) <= 1e-4
+    assert agree >= 0.9 and cls_agree >= 0.97
+    assert float(loss16.mean()) < 0.02            # the projection converged (targets are on-manifold + noise)
