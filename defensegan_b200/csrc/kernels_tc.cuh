@@ -259,6 +259,134 @@ __device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalA
   }
 }
 
+// dz chunk (32 latent dims of one row, in registers) -> momentum update of z and v in place
+__device__ __forceinline__ void tc_momentum_chunk(const uint32_t (&r)[32], int c0, size_t n, int latent, const TcFinalArgs& fa) {
+  float4* __restrict__ vp = reinterpret_cast<float4*>(fa.mv + n * latent + c0);
+  float4* __restrict__ zp = reinterpret_cast<float4*>(fa.mz + n * latent + c0);
+  uint2* __restrict__ hp = reinterpret_cast<uint2*>(fa.mz_h + n * latent + c0);
+  float4 vv[8], zz[8];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) { vv[j4] = vp[j4]; zz[j4] = zp[j4]; }   // all loads in flight before any store
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float4 v = vv[j4], z = zz[j4];
+    v.x = fmaf(fa.m_mu, v.x, fa.m_gmul * __uint_as_float(r[j4 * 4 + 0]));
+    v.y = fmaf(fa.m_mu, v.y, fa.m_gmul * __uint_as_float(r[j4 * 4 + 1]));
+    v.z = fmaf(fa.m_mu, v.z, fa.m_gmul * __uint_as_float(r[j4 * 4 + 2]));
+    v.w = fmaf(fa.m_mu, v.w, fa.m_gmul * __uint_as_float(r[j4 * 4 + 3]));
+    z.x -= fa.m_lr * v.x; z.y -= fa.m_lr * v.y; z.z -= fa.m_lr * v.z; z.w -= fa.m_lr * v.w;
+    vp[j4] = v; zp[j4] = z;
+    hp[j4] = make_uint2(pack_half2(z.x, z.y), pack_half2(z.z, z.w));
+  }
+}
+
+// One 32-column chunk of an accumulator (already in registers) -> epilogue -> out[q][n][c0..c0+32)
+// ReLU-mask words (32 fp16 = 4 x uint4) of one chunk: loaded one unit ahead of their use
+template <int N_TILE>
+__device__ __forceinline__ void tc_load_mask(uint4 (&mv)[4], const __half* __restrict__ mask_src, int q, int c0, size_t n,
+                                             int n_pad) {
+  const uint4* mp = reinterpret_cast<const uint4*>(mask_src + ((size_t)q * n_pad + n) * N_TILE + c0);
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) mv[j4] = __ldg(mp + j4);
+}
+
+template <int N_TILE, int EPI, typename TOUT>
+__device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], const uint4 (&mv)[4], int q, int c0, size_t n,
+                                               int n_pad, TOUT* __restrict__ out, const float* __restrict__ bias,
+                                               int bias_pstride, float out_scale, int dbg_flags = 0) {
+  const size_t orow = ((size_t)q * n_pad + n) * N_TILE;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
+  if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
+    const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + c0);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 b = __ldg(bp + j4);
+      v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+    }
+    if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+  }
+  if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const uint32_t mw[4] = {mv[j4].x, mv[j4].y, mv[j4].z, mv[j4].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
+        if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
+        if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
+      }
+    }
+  }
+  if ((dbg_flags & 1) && v[0] != 12345.678f) return;   // timing experiment: no stores
+  if (sizeof(TOUT) == 2) {
+    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4)
+      op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
+                          pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
+  } else {
+    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+  }
+}
+
+// One accumulator (128 lanes x N_TILE fp32 columns at `taddr`) -> bias/ReLU | ReLU-mask | none ->
+// fp16 (or fp32) row of out[q][n][0..N_TILE).  Each thread owns one latent row (TMEM lane).
+template <int N_TILE, int EPI, typename TOUT>
+__device__ __forceinline__ void tc_generic_epilogue(uint32_t taddr, int q, size_t n, int n_pad, TOUT* __restrict__ out,
+                                                    const float* __restrict__ bias, int bias_pstride,
+                                                    const __half* __restrict__ mask_src, float out_scale) {
+  const size_t orow = ((size_t)q * n_pad + n) * N_TILE;
+#pragma unroll 1
+  for (int c0 = 0; c0 + 32 <= N_TILE; c0 += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld32(taddr + (uint32_t)c0, r);
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
+    if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
+      const float* bp = bias + (size_t)q * bias_pstride + c0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] += __ldg(bp + j);
+        if (EPI == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
+      }
+    }
+    if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
+      const uint4* mp = reinterpret_cast<const uint4*>(mask_src + orow + c0);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const uint4 mv = __ldg(mp + j4);
+        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
+          if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
+          if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
+        }
+      }
+    }
+    if (sizeof(TOUT) == 2) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4)
+        op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
+                            pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
