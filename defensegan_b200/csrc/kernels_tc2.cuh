@@ -282,6 +282,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     uint32_t item_count = 0;
     long long t_ewait = 0, t_ework = 0;
     const long long t_start = fa.dbg ? clock64() : 0;
+    unsigned long long gt_start = 0;
+    if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
     for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs, ++item_count) {
       const int win = item_idx / n_mpairs, mp = item_idx % n_mpairs;
       const TcItem2* ip = items + win;
@@ -401,8 +403,10 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (fa.dbg && warp == 2 && lane == 0) {
       fa.dbg[blockIdx.x * 8 + 4] = (unsigned long long)t_ewait;
       fa.dbg[blockIdx.x * 8 + 5] = (unsigned long long)t_ework;
-      fa.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_start);
-      fa.dbg[blockIdx.x * 8 + 7] = (unsigned long long)item_count;
+      unsigned long long gt_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+      fa.dbg[blockIdx.x * 8 + 6] = gt_start;      // ns, after the PDL wait
+      fa.dbg[blockIdx.x * 8 + 7] = gt_end;        // ns, after this CTA's last epilogue
     }
   }
 

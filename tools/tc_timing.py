@@ -14,7 +14,7 @@ from defensegan_b200.models.gan import dataset_gan_dict
 
 dataset = sys.argv[1] if len(sys.argv) > 1 else "mnist"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
-R, L = 10, 2
+R, L = 10, 3
 gan = dataset_gan_dict[dataset](test_mode=True, verbose=False, precision="fp16", batch_size=50)
 gan.rec_rr, gan.rec_iters = R, L
 g = torch.Generator().manual_seed(0)
@@ -28,13 +28,28 @@ nat.lib.dgan_debug_tc_timing.restype = ctypes.c_int
 nat.lib.dgan_debug_tc_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 n = nat.lib.dgan_debug_tc_timing(nat._handle, buf, 64)
 a = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 8)[:n].astype(np.float64)
-names = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "mma_issue", "epi_wait", "epi_work", "total", "items"]
-print("launch | " + " | ".join(names) + "   (mean cycles over active CTAs; MMA columns: leader CTAs only)")
+names = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "mma_issue", "active CTAs", "epi_work", "CTA util %"]
+print("launch | " + " | ".join(names) + " | first start us | last start us | first end us | last end us | gap to next us"
+      "   (cycles: mean over active CTAs; MMA columns: leader CTAs only; times: %globaltimer, PDL on)")
+raw = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 8)[:n]
+t0 = None
+rows = []
 for i in range(n):
-    act = a[i][:, 6] > 0
+    act = raw[i][:, 7] > 0
+    if not act.any():
+        continue
     lead = act & (a[i][:, 3] > 0)
-    row = []
-    for k in range(8):
+    vals = []
+    for k in range(6):
         m = lead if k in (1, 2, 3) else act
-        row.append(a[i][m, k].mean() if m.any() else 0.0)
-    print("%2d | " % i + " | ".join("%9.0f" % v for v in row) + " | maxtotal %9.0f" % a[i][:, 6].max())
+        vals.append(a[i][m, k].mean() if m.any() else 0.0)
+    vals[4] = float(act.sum())      # reuse the epi_wait column for the number of active CTAs
+    st, en = raw[i][act, 6].astype(np.int64), raw[i][act, 7].astype(np.int64)
+    if t0 is None:
+        t0 = st.min()
+    util = float((en - st).mean()) / max(1.0, float(en.max() - st.min()))
+    vals.append(100.0 * util)
+    rows.append((i, vals, (st.min() - t0) / 1e3, (st.max() - t0) / 1e3, (en.min() - t0) / 1e3, (en.max() - t0) / 1e3))
+for j, (i, vals, s0, s1, e0, e1) in enumerate(rows):
+    gap = rows[j + 1][2] - e1 if j + 1 < len(rows) else float("nan")
+    print("%2d | " % i + " | ".join("%9.0f" % v for v in vals) + " | %8.1f | %8.1f | %8.1f | %8.1f | %6.1f" % (s0, s1, e0, e1, gap))
