@@ -134,7 +134,7 @@ def cpu_port_images_per_sec(dataset, R, L, sample_images, threads, repeats=1):
     return sample_images / t, t
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, out):
     """--impl reference: the reference's own CPU implementation of the path cannot run here
     (Python 2 + TensorFlow 1.7, neither present nor installable offline) => the oracle port is
     timed on the host cores, rank 0 only."""
@@ -163,7 +163,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
 
 
 def resolve_workload(args):
@@ -182,7 +182,33 @@ def workload_name(dataset, B, R, L):
         dataset, "64x64x3" if dataset == "celeba" else "28x28x1", B, R, L)
 
 
+class _OnlyJsonOnStdout:
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to fd 1) must not
+    leak into it: while active, fd 1 points at stderr; emit() writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self._real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        return False
+
+
 def main():
+    with _OnlyJsonOnStdout() as out:
+        _main(out)
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -202,7 +228,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, out)
         return
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
@@ -363,7 +389,7 @@ def main():
                             "frac_of_sustained_bf16_peak": step_tflops / (world * peaks["bf16_tflops_sustained"])},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
         }
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
     gan.close()
