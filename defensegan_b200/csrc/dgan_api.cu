@@ -704,6 +704,7 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     const char* mode_env = getenv("DGAN_TC_MODE");
     c->tc.mode = (mode_env && mode_env[0] == '1') ? 1 : 2;
     if (getenv("DGAN_TC_DBGFLAGS")) c->tc.dbg_flags = atoi(getenv("DGAN_TC_DBGFLAGS"));
+    if (getenv("DGAN_MAX_PAIRS")) c->tc.max_pairs = atoi(getenv("DGAN_MAX_PAIRS"));
     if (getenv("DGAN_TC_DEBUG")) {   // developer aid: per-CTA role timing of the first launches (tools/tc_timing.py)
       c->tc.dbg_max_launches = 64;
       if ((rc = dev_alloc(c.get(), (void**)&c->tc.dbg, (size_t)64 * 160 * 8 * sizeof(unsigned long long)))) return fail(rc);

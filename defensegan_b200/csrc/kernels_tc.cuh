@@ -60,6 +60,7 @@ struct TcState {
   int dbg_launch = 0, dbg_max_launches = 0, dbg_flags = 0;
   std::vector<void*>* allocs = nullptr;   // the handle's allocation list (lazily built schedules are freed with it)
   int num_sms = 148;
+  int max_pairs = 0;            // cap on CTA pairs per launch (0 = all SMs); used with multi-chain execution
 };
 
 struct TcLayerSpec {

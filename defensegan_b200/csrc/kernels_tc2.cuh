@@ -593,10 +593,11 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
   const int n_mpairs = n_pad / (2 * kRowTile);
   const Tc2Schedule* schp = nullptr;
-  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, st.num_sms / 2, st.allocs, s, &schp))) return rc;
+  const int pairs_avail = st.max_pairs > 0 ? std::min(st.max_pairs, st.num_sms / 2) : st.num_sms / 2;
+  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, pairs_avail, st.allocs, s, &schp))) return rc;
   const Tc2Schedule& w2s = *schp;
   const int total = w2s.n_windows * n_mpairs;
-  const int grid = 2 * std::min(total, st.num_sms / 2);
+  const int grid = 2 * std::min(total, pairs_avail);
   cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
