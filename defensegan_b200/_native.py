@@ -15,7 +15,7 @@ import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libdefensegan_b200.so"
-LIB_PATH = os.path.join(_PKG_DIR, LIB_NAME)
+LIB_PATH = os.environ.get("DGAN_LIB", os.path.join(_PKG_DIR, LIB_NAME))   # DGAN_LIB: A/B-test another build
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
 
