@@ -128,6 +128,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 }
 }  // namespace ptx
 
+// k-th item of CTA pair `pair`: rounds alternate direction (snake order) so that, with the windows sorted
+// largest-first, the pair that got the biggest item of one round gets the smallest of the next.  -1 = done.
+__device__ __forceinline__ int tc2_item_at(int k, int pair, int n_pairs, int total) {
+#ifdef DGAN_NO_SNAKE
+  const int idx = k * n_pairs + pair;
+#else
+  const int idx = k * n_pairs + ((k & 1) ? (n_pairs - 1 - pair) : pair);
+#endif
+  return idx < total ? idx : -1;
+}
+
 template <int N_TILE, int EPI, typename TOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -188,7 +199,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // R2UR/ELECT loop), and one elected lane issues.
     uint32_t it = 0;
     long long t_wait = 0;
-    for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs) {
+    for (int kk = 0, item_idx; (item_idx = tc2_item_at(kk, pair, n_pairs, total_items)) >= 0; ++kk) {
       const int win = item_idx / n_mpairs, mp = item_idx % n_mpairs;
       const TcItem2* ip = items + win;
       const uint32_t n_steps = ip->n_steps;
@@ -224,7 +235,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       constexpr uint32_t idesc = make_idesc_f16(256, N_TILE);
       uint32_t it = 0, item_count = 0;
       long long t_wait_full = 0, t_wait_acc = 0, t_issue = 0;
-      for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs, ++item_count) {
+      for (int kk = 0, item_idx; (item_idx = tc2_item_at(kk, pair, n_pairs, total_items)) >= 0; ++kk, ++item_count) {
         const int win = item_idx / n_mpairs;
         const TcItem2* ip = items + win;
         const uint32_t n_steps = ip->n_steps;
@@ -284,7 +295,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const long long t_start = fa.dbg ? clock64() : 0;
     unsigned long long gt_start = 0;
     if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
-    for (int item_idx = pair; item_idx < total_items; item_idx += n_pairs, ++item_count) {
+    for (int kk = 0, item_idx; (item_idx = tc2_item_at(kk, pair, n_pairs, total_items)) >= 0; ++kk, ++item_count) {
       const int win = item_idx / n_mpairs, mp = item_idx % n_mpairs;
       const TcItem2* ip = items + win;
       const int n_acc = (int)ip->n_acc;
@@ -524,11 +535,21 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
           const int nb = (steps[items[i].step_beg + k].w0 >> 24) & 0xFF;
           c += a_bytes + nb * half_b;
         }
-        icost[i] = c + 24.0 * 1024.0 * items[i].n_acc * std::max(1, N / 64) + 48.0 * 1024.0;   // epilogue + per-item fixed
+#ifndef DGAN_COST_EPI_KB
+#define DGAN_COST_EPI_KB 24.0
+#endif
+#ifndef DGAN_COST_FIXED_KB
+#define DGAN_COST_FIXED_KB 48.0
+#endif
+        icost[i] = c + DGAN_COST_EPI_KB * 1024.0 * items[i].n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;   // epilogue + per-item fixed
       }
       std::vector<double> load((size_t)n_pairs, 0.0);
       const long long total = (long long)items.size() * n_mpairs;
-      for (long long idx = 0; idx < total; ++idx) load[(size_t)(idx % n_pairs)] += icost[(size_t)(idx / n_mpairs)];
+      for (long long idx = 0; idx < total; ++idx) {
+        const long long round = idx / n_pairs, j = idx % n_pairs;
+        const size_t pr = (size_t)((round & 1) ? (n_pairs - 1 - j) : j);       // snake order, as in tc2_item_at
+        load[pr] += icost[(size_t)(idx / n_mpairs)];
+      }
       const double makespan = *std::max_element(load.begin(), load.end());
       if (makespan < best_cost) { best_cost = makespan; best_wh = wh; best_ww = ww; best_items.swap(items); best_steps.swap(steps); }
     }
