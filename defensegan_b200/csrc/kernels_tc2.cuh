@@ -40,6 +40,17 @@ __host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out
   return out_bytes == 2 && n_tile >= 64 && epi != EPI_FINAL_SIGMOID1 && epi != EPI_FINAL_TANH3;
 }
 
+// One step of a CTA pair's work stream (16 bytes).  The host concatenates, per CTA pair, the steps of all the items
+// assigned to it (LPT order), so producer and MMA warps read one contiguous array: 32 records per coalesced
+// warp load, staged in shared memory, the next batch always in flight - no table-load stalls on the issue path.
+struct __align__(16) TcRec {
+  uint32_t w0;       // input pixel [0,16) | k-chunk [16,24) | n_b [24,32)
+  uint32_t w1;       // first-MMA mask [0,8) | flags [8,16): 1 = first step of an item, 2 = last step | row pair mp [16,32)
+  uint8_t tb[8];     // per weight tile: tile id [0,5) | accumulator [5,8)
+};
+constexpr int TC2_REC_BATCH = 32;
+constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // producer + MMA warp rings
+
 template <int N_TILE, int EPI = EPI_NONE, int OUT_BYTES = 2>
 struct Tc2Cfg {
   static constexpr int HALF_B = (N_TILE / 2) * 128;                      // bytes of this CTA's half weight tile
@@ -49,9 +60,9 @@ struct Tc2Cfg {
   static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
   // epilogue staging: one output tile per epilogue half
   static constexpr int EPI_BYTES = TMA_EPI ? 2 * TC2_TILE_BYTES : 0;
-  static constexpr int STAGES_RAW = (TC2_SMEM_MAX - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (TC2_SMEM_MAX - 1024 - 256 - TC2_STAGING_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256;
 };
 
 namespace ptx {
@@ -128,22 +139,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 }
 }  // namespace ptx
 
-// k-th item of CTA pair `pair`: rounds alternate direction (snake order) so that, with the windows sorted
-// largest-first, the pair that got the biggest item of one round gets the smallest of the next.  -1 = done.
-__device__ __forceinline__ int tc2_item_at(int k, int pair, int n_pairs, int total) {
-#ifdef DGAN_NO_SNAKE
-  const int idx = k * n_pairs + pair;
-#else
-  const int idx = k * n_pairs + ((k & 1) ? (n_pairs - 1 - pair) : pair);
-#endif
-  return idx < total ? idx : -1;
+// k-th item (window << 16 | row pair) of CTA pair `pair` from the host-computed table [slot][pair] (-1 = no more work).
+// The host assigns items largest-first to the least-loaded pair (LPT) with the cost model of tc2_get_schedule.
+__device__ __forceinline__ int tc2_item_at(const int* __restrict__ order, int k, int pair, int n_pairs, int n_slots) {
+  return k < n_slots ? __ldg(order + (size_t)k * n_pairs + pair) : -1;
 }
 
 template <int N_TILE, int EPI, typename TOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_mask,
-                  const TcItem2* __restrict__ items, const TcStep2* __restrict__ steps, int n_windows, int n_mpairs,
+                  const TcItem2* __restrict__ items, const TcRec* __restrict__ stream, const uint32_t* __restrict__ stream_off,
+                  const int* __restrict__ eitems, int n_slots,
                   TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
                   const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
   using Cfg = Tc2Cfg<N_TILE, EPI, (int)sizeof(TOUT)>;
@@ -152,7 +159,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;       // [out tile half0][out tile half1][mask half0][mask half1]
-  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+  const uint32_t stg_base = epi_base + Cfg::EPI_BYTES;              // [producer ring][MMA ring] of TcRec
+  const uint32_t bar_base = stg_base + TC2_STAGING_BYTES;
   const uint32_t bar_mask = bar_base + 176;                          // mask_full[2]
   // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160, mask_full[2] @ +176
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
@@ -163,7 +171,6 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int total_items = n_windows * n_mpairs;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -199,19 +206,20 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // R2UR/ELECT loop), and one elected lane issues.
     uint32_t it = 0;
     long long t_wait = 0;
-    for (int kk = 0, item_idx; (item_idx = tc2_item_at(kk, pair, n_pairs, total_items)) >= 0; ++kk) {
-      const int win = item_idx / n_mpairs, mp = item_idx % n_mpairs;
-      const TcItem2* ip = items + win;
-      const uint32_t n_steps = ip->n_steps;
-      const uint4* sp = reinterpret_cast<const uint4*>(steps + ip->step_beg);
-      const int row0 = (2 * mp + (int)rank) * kRowTile;
-      uint4 nx0 = __ldg(sp), nx1 = __ldg(sp + 1);
-      for (uint32_t si = 0; si < n_steps; ++si, ++it) {
-        const uint4 c0 = nx0, c1 = nx1;
-        if (si + 1 < n_steps) { nx0 = __ldg(sp + 2 * (si + 1)); nx1 = __ldg(sp + 2 * (si + 1) + 1); }
+    const uint32_t rbeg = __ldg(stream_off + pair), rend = __ldg(stream_off + pair + 1);
+    const uint32_t ring = stg_base;
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    if (rbeg + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg + lane));
+    for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
+      ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
+      __syncwarp();
+      if (base + TC2_REC_BATCH + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH + lane));
+      const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
+      for (uint32_t i = 0; i < cnt; ++i, ++it) {
+        const uint4 rec = ptx::ld_shared_v4(ring + i * 16u);
         const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1;
-        const int p = c0.x & 0xFFFF, kc = (c0.x >> 16) & 0xFF, nb = (c0.x >> 24) & 0xFF;
-        const uint32_t tbw[4] = {c1.x, c1.y, c1.z, c1.w};
+        const int p = rec.x & 0xFFFF, kc = (rec.x >> 16) & 0xFF, nb = (rec.x >> 24) & 0xFF;
+        const int row0 = (2 * (int)(rec.y >> 16) + (int)rank) * kRowTile;
         const long long tw0 = fa.dbg ? clock64() : 0;
         ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (fa.dbg) t_wait += clock64() - tw0;
@@ -221,12 +229,13 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (leader) ptx::mbar_expect_tx(full, 2u * (uint32_t)(TC_A_BYTES + nb * HALF_B));
           ptx::tma_load_3d_2sm(sa, &tm_a, full, kc * 64, row0, p);
           for (int b = 0; b < nb; ++b) {
-            const int tile = (tbw[b >> 1] >> (16 * (b & 1))) & 0xFF;
+            const int tile = (((b < 4) ? rec.z : rec.w) >> (8 * (b & 3))) & 0x1F;
             ptx::tma_load_3d_2sm(sa + TC_A_BYTES + b * HALF_B, &tm_b, full, kc * 64, (int)rank * (N_TILE / 2), tile);
           }
         }
         __syncwarp();
       }
+      __syncwarp();
     }
     if (fa.dbg && lane == 0) fa.dbg[blockIdx.x * 8 + 0] = (unsigned long long)t_wait;
   } else if (warp == 1) {
@@ -235,24 +244,28 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       constexpr uint32_t idesc = make_idesc_f16(256, N_TILE);
       uint32_t it = 0, item_count = 0;
       long long t_wait_full = 0, t_wait_acc = 0, t_issue = 0;
-      for (int kk = 0, item_idx; (item_idx = tc2_item_at(kk, pair, n_pairs, total_items)) >= 0; ++kk, ++item_count) {
-        const int win = item_idx / n_mpairs;
-        const TcItem2* ip = items + win;
-        const uint32_t n_steps = ip->n_steps;
-        const uint4* sp = reinterpret_cast<const uint4*>(steps + ip->step_beg);
-        const uint32_t buf = item_count & 1;
-        const long long ta0 = fa.dbg ? clock64() : 0;
-        ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);   // both CTAs drained this buffer
-        if (fa.dbg) t_wait_acc += clock64() - ta0;
-        ptx::tc_fence_after();
-        uint4 nx0 = __ldg(sp), nx1 = __ldg(sp + 1);
-        for (uint32_t si = 0; si < n_steps; ++si, ++it) {
-          const uint4 c0 = nx0, c1 = nx1;
-          if (si + 1 < n_steps) { nx0 = __ldg(sp + 2 * (si + 1)); nx1 = __ldg(sp + 2 * (si + 1) + 1); }
+      const long long t_mma_start = fa.dbg ? clock64() : 0;
+      const uint32_t rbeg = __ldg(stream_off + pair), rend = __ldg(stream_off + pair + 1);
+      const uint32_t ring = stg_base + TC2_REC_BATCH * (uint32_t)sizeof(TcRec);
+      uint4 mine = make_uint4(0, 0, 0, 0);
+      if (rbeg + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg + lane));
+      uint32_t buf = 0;
+      for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
+        ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
+        __syncwarp();
+        if (base + TC2_REC_BATCH + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH + lane));
+        const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
+        for (uint32_t i = 0; i < cnt; ++i, ++it) {
+          const uint4 rec = ptx::ld_shared_v4(ring + i * 16u);
           const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1;
-          const int nb = (c0.x >> 24) & 0xFF;
-          const uint32_t firsts = c0.y;
-          const uint32_t tbw[4] = {c1.x, c1.y, c1.z, c1.w};
+          const int nb = (rec.x >> 24) & 0xFF;
+          const uint32_t firsts = rec.y & 0xFFu, flags = (rec.y >> 8) & 0xFFu;
+          if (flags & 1u) {                                   // first step of an item: its accumulator buffer must be drained
+            buf = item_count & 1;
+            const long long ta0 = fa.dbg ? clock64() : 0;
+            ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
+            if (fa.dbg) t_wait_acc += clock64() - ta0;
+          }
           const long long tf0 = fa.dbg ? clock64() : 0;
           ptx::mbar_wait(bar_full + 8 * stage, phase);
           const long long tf1 = fa.dbg ? clock64() : 0;
@@ -261,7 +274,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (ptx::elect_one()) {
             const uint64_t a_desc = make_smem_desc_sw128(sa);
             for (int b = 0; b < nb; ++b) {
-              const int acc = (tbw[b >> 1] >> (16 * (b & 1) + 8)) & 0xFF;
+              const int acc = ((((b < 4) ? rec.z : rec.w) >> (8 * (b & 3))) >> 5) & 0x7;
               const uint32_t first = (firsts >> b) & 1u;
               const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES + b * HALF_B);
               const uint32_t d = tmem_base + buf * TC2_BUF_COLS + acc * ACC_STRIDE;
@@ -270,17 +283,19 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 ptx::umma_f16_2sm(d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (k > 0 || !first) ? 1u : 0u);
             }
             ptx::umma_commit_2sm(bar_empty + 8 * stage);          // frees this stage in both CTAs
+            if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
           }
           __syncwarp();
+          if (flags & 2u) ++item_count;
           if (fa.dbg) { t_wait_full += tf1 - tf0; t_issue += clock64() - tf1; }
         }
-        if (ptx::elect_one()) ptx::umma_commit_2sm(bar_acc_full + 8 * buf); // accumulators complete in both CTAs
         __syncwarp();
       }
       if (fa.dbg && lane == 0) {
         fa.dbg[blockIdx.x * 8 + 1] = (unsigned long long)t_wait_full;
         fa.dbg[blockIdx.x * 8 + 2] = (unsigned long long)t_wait_acc;
         fa.dbg[blockIdx.x * 8 + 3] = (unsigned long long)t_issue;
+        fa.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_mma_start);   // MMA warp: whole item loop
       }
     }
   } else {
@@ -295,8 +310,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const long long t_start = fa.dbg ? clock64() : 0;
     unsigned long long gt_start = 0;
     if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
-    for (int kk = 0, item_idx; (item_idx = tc2_item_at(kk, pair, n_pairs, total_items)) >= 0; ++kk, ++item_count) {
-      const int win = item_idx / n_mpairs, mp = item_idx % n_mpairs;
+    for (int kk = 0, item_e = tc2_item_at(eitems, 0, pair, n_pairs, n_slots), item_next; item_e >= 0; ++kk, ++item_count, item_e = item_next) {
+      item_next = tc2_item_at(eitems, kk + 1, pair, n_pairs, n_slots);      // (window << 16 | row pair), one item ahead
+      const int win = item_e >> 16, mp = item_e & 0xFFFF;
       const TcItem2* ip = items + win;
       const int n_acc = (int)ip->n_acc;
       const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
@@ -412,7 +428,6 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     if (TMA_EPI && lane == 0 && (warp == 2 || warp == 6)) ptx::bulk_wait_all0();   // stores landed before exit
     if (fa.dbg && warp == 2 && lane == 0) {
-      fa.dbg[blockIdx.x * 8 + 4] = (unsigned long long)t_ewait;
       fa.dbg[blockIdx.x * 8 + 5] = (unsigned long long)t_ework;
       unsigned long long gt_end;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
@@ -432,9 +447,12 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct Tc2Schedule {           // one window tiling of a layer-direction, uploaded
+struct Tc2Schedule {           // one window tiling of a layer-direction + its item -> CTA-pair assignment, uploaded
   TcItem2* items = nullptr;
-  TcStep2* steps = nullptr;
+  TcRec* stream = nullptr;         // per CTA pair: the concatenated step records of its items
+  uint32_t* stream_off = nullptr;  // [n_pairs + 1] record offsets into `stream`
+  int* eitems = nullptr;           // [n_slots][n_pairs] (window << 16 | row pair) for the epilogue warps, or -1
+  int n_slots = 0, n_pairs = 0;
   int n_windows = 0;
   int wh = 0, ww = 0;
 };
@@ -521,6 +539,7 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   int best_wh = 1, best_ww = 1;
   std::vector<TcItem2> best_items;
   std::vector<TcStep2> best_steps;
+  std::vector<std::vector<int>> best_lists;
   for (int wh = 1; wh <= 2; ++wh)
     for (int ww = 1; ww <= 4; ++ww) {
       if (wh * ww > w2.max_acc || wh > w2.h_grid || ww > std::max(w2.w_grid, 1)) continue;
@@ -543,29 +562,55 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
 #endif
         icost[i] = c + DGAN_COST_EPI_KB * 1024.0 * items[i].n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;   // epilogue + per-item fixed
       }
-      std::vector<double> load((size_t)n_pairs, 0.0);
+      // LPT: items (window, mp) largest-first, each to the currently least-loaded CTA pair
       const long long total = (long long)items.size() * n_mpairs;
-      for (long long idx = 0; idx < total; ++idx) {
-        const long long round = idx / n_pairs, j = idx % n_pairs;
-        const size_t pr = (size_t)((round & 1) ? (n_pairs - 1 - j) : j);       // snake order, as in tc2_item_at
-        load[pr] += icost[(size_t)(idx / n_mpairs)];
+      std::vector<double> load((size_t)n_pairs, 0.0);
+      std::vector<std::vector<int>> lists((size_t)n_pairs);
+      for (long long idx = 0; idx < total; ++idx) {        // items[] is sorted by cost, mp is the fast index: cost-descending
+        size_t best = 0;
+        for (size_t pr = 1; pr < (size_t)n_pairs; ++pr)
+          if (load[pr] < load[best]) best = pr;
+        load[best] += icost[(size_t)(idx / n_mpairs)];
+        lists[best].push_back((int)idx);
       }
       const double makespan = *std::max_element(load.begin(), load.end());
-      if (makespan < best_cost) { best_cost = makespan; best_wh = wh; best_ww = ww; best_items.swap(items); best_steps.swap(steps); }
+      if (makespan < best_cost) {
+        best_cost = makespan; best_wh = wh; best_ww = ww; best_items.swap(items); best_steps.swap(steps); best_lists.swap(lists);
+      }
     }
-  const Tc2Schedule* found = nullptr;
-  for (auto& b : w2.built)
-    if (b.wh == best_wh && b.ww == best_ww) found = &b;
-  if (found == nullptr) {
-    Tc2Schedule sc;
-    sc.wh = best_wh; sc.ww = best_ww; sc.n_windows = (int)best_items.size();
-    int rc;
-    if ((rc = tc_upload(allocs, best_items.data(), best_items.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
-    if ((rc = tc_upload(allocs, best_steps.data(), best_steps.size() * sizeof(TcStep2), (void**)&sc.steps, s))) return rc;
-    w2.built.push_back(sc);
-    found = &w2.built.back();
+  Tc2Schedule sc;
+  sc.wh = best_wh; sc.ww = best_ww; sc.n_windows = (int)best_items.size(); sc.n_pairs = n_pairs;
+  size_t n_slots = 0;
+  for (auto& l : best_lists) n_slots = std::max(n_slots, l.size());
+  sc.n_slots = (int)n_slots;
+  std::vector<int> eitems(n_slots * (size_t)n_pairs, -1);
+  std::vector<uint32_t> stream_off((size_t)n_pairs + 1, 0);
+  std::vector<TcRec> stream;
+  for (size_t pr = 0; pr < best_lists.size(); ++pr) {
+    stream_off[pr] = (uint32_t)stream.size();
+    for (size_t k = 0; k < best_lists[pr].size(); ++k) {
+      const int win = best_lists[pr][k] / n_mpairs, mp = best_lists[pr][k] % n_mpairs;
+      if (win > 0x7FFF || mp > 0xFFFF) { set_error("tensor-core schedule limits exceeded"); return DGAN_ERR_UNSUPPORTED; }
+      eitems[k * (size_t)n_pairs + pr] = (win << 16) | mp;
+      const TcItem2& itm = best_items[(size_t)win];
+      for (uint32_t j = 0; j < itm.n_steps; ++j) {
+        const TcStep2& st2 = best_steps[itm.step_beg + j];
+        TcRec r{};
+        r.w0 = st2.w0;
+        const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.n_steps ? 2u : 0u);
+        r.w1 = (st2.w1 & 0xFFu) | (flags << 8) | ((uint32_t)mp << 16);
+        for (int b = 0; b < 8; ++b) r.tb[b] = (uint8_t)((st2.tb[b] & 0x1F) | (((st2.tb[b] >> 8) & 0x7) << 5));
+        stream.push_back(r);
+      }
+    }
   }
-  w2.by_mpairs.push_back({n_mpairs, *found});
+  stream_off[(size_t)n_pairs] = (uint32_t)stream.size();
+  int rc;
+  if ((rc = tc_upload(allocs, best_items.data(), best_items.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
+  if ((rc = tc_upload(allocs, stream.data(), stream.size() * sizeof(TcRec), (void**)&sc.stream, s))) return rc;
+  if ((rc = tc_upload(allocs, stream_off.data(), stream_off.size() * sizeof(uint32_t), (void**)&sc.stream_off, s))) return rc;
+  if ((rc = tc_upload(allocs, eitems.data(), eitems.size() * sizeof(int), (void**)&sc.eitems, s))) return rc;
+  w2.by_mpairs.push_back({n_mpairs, sc});
   *out = &w2.by_mpairs.back().second;
   if (getenv("DGAN_TC_VERBOSE"))
     fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d, %d windows\n", N, K, w2.h_grid, w2.w_grid,
@@ -618,14 +663,15 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, pairs_avail, st.allocs, s, &schp))) return rc;
   const Tc2Schedule& w2s = *schp;
   const int total = w2s.n_windows * n_mpairs;
-  const int grid = 2 * std::min(total, pairs_avail);
+  const int grid = 2 * w2s.n_pairs;       // pairs without work find -1 in slot 0 and fall through
+  (void)total;
   cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
-                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.steps, w2s.n_windows, n_mpairs, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
-                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.steps, w2s.n_windows, n_mpairs, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
+                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
                   mask_src, out_scale, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \

@@ -28,7 +28,7 @@ nat.lib.dgan_debug_tc_timing.restype = ctypes.c_int
 nat.lib.dgan_debug_tc_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 n = nat.lib.dgan_debug_tc_timing(nat._handle, buf, 64)
 a = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 8)[:n].astype(np.float64)
-names = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "mma_issue", "active CTAs", "epi_work", "CTA util %"]
+names = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "mma_issue", "mma_loop_total", "epi_work", "CTA util %"]
 print("launch | " + " | ".join(names) + " | first start us | last start us | first end us | last end us | gap to next us"
       "   (cycles: mean over active CTAs; MMA columns: leader CTAs only; times: %globaltimer, PDL on)")
 raw = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 8)[:n]
@@ -41,9 +41,9 @@ for i in range(n):
     lead = act & (a[i][:, 3] > 0)
     vals = []
     for k in range(6):
-        m = lead if k in (1, 2, 3) else act
+        m = lead if k in (1, 2, 3, 4) else act
         vals.append(a[i][m, k].mean() if m.any() else 0.0)
-    vals[4] = float(act.sum())      # reuse the epi_wait column for the number of active CTAs
+    vals[4] = a[i][lead, 4].mean() if lead.any() else 0.0
     st, en = raw[i][act, 6].astype(np.int64), raw[i][act, 7].astype(np.int64)
     if t0 is None:
         t0 = st.min()
