@@ -707,8 +707,8 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     if (getenv("DGAN_MAX_PAIRS")) c->tc.max_pairs = atoi(getenv("DGAN_MAX_PAIRS"));
     if (getenv("DGAN_TC_DEBUG")) {   // developer aid: per-CTA role timing of the first launches (tools/tc_timing.py)
       c->tc.dbg_max_launches = 64;
-      if ((rc = dev_alloc(c.get(), (void**)&c->tc.dbg, (size_t)64 * 160 * 8 * sizeof(unsigned long long)))) return fail(rc);
-      DGAN_CUDA_CHECK(cudaMemsetAsync(c->tc.dbg, 0, (size_t)64 * 160 * 8 * sizeof(unsigned long long), s));
+      if ((rc = dev_alloc(c.get(), (void**)&c->tc.dbg, (size_t)64 * 160 * 16 * sizeof(unsigned long long)))) return fail(rc);
+      DGAN_CUDA_CHECK(cudaMemsetAsync(c->tc.dbg, 0, (size_t)64 * 160 * 16 * sizeof(unsigned long long), s));
     }
     c->tc.allocs = &c->allocs;
     if (c->tc.mode == 2) {
@@ -953,7 +953,7 @@ int dgan_debug_tc_timing(dgan_handle h, unsigned long long* out, int max_launche
   if (h == nullptr || out == nullptr || h->tc.dbg == nullptr) return 0;
   const int n = std::min(max_launches, h->tc.dbg_launch);
   cudaDeviceSynchronize();
-  cudaMemcpy(out, h->tc.dbg, (size_t)n * 160 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out, h->tc.dbg, (size_t)n * 160 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   return n;
 }
 

@@ -56,7 +56,7 @@ struct TcState {
   int mode = 2;                 // 1 = one CTA per MMA (kernels_tc.cuh), 2 = CTA pairs (kernels_tc2.cuh)
   float grad_scale = 64.f;      // fp16 gradient scaling (undone in the z update)
   void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
-  unsigned long long* dbg = nullptr;   // DGAN_TC_DEBUG=1: [launch][cta][8] role-timing counters
+  unsigned long long* dbg = nullptr;   // DGAN_TC_DEBUG=1: [launch][cta][16] role-timing counters
   int dbg_launch = 0, dbg_max_launches = 0, dbg_flags = 0;
   std::vector<void*>* allocs = nullptr;   // the handle's allocation list (lazily built schedules are freed with it)
   int num_sms = 148;
@@ -187,7 +187,7 @@ struct TcFinalArgs {
   // EPI_MOMENTUM (Linear backward fused with tf.train.MomentumOptimizer, models/gan.py:389-391):
   float* mz; float* mv; __half* mz_h;   // z, velocity [n_pad][latent] fp32, fp16 copy of z
   float m_gmul, m_lr, m_mu;             // g = gmul * acc;  v <- mu v + g;  z <- z - lr v
-  unsigned long long* dbg;  // optional per-CTA role timing (8 counters per CTA), NULL in production
+  unsigned long long* dbg;  // optional per-CTA role timing (16 counters per CTA), NULL in production
   int dbg_flags;            // timing experiments only: 1 = skip epilogue stores, 2 = skip mask loads, 4 = skip bias
 };
 

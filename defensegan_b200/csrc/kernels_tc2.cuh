@@ -195,6 +195,17 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   ptx::cluster_sync_all();                     // barriers of BOTH CTAs initialised before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // The schedule tables are constants: fetch each role's first entries before the PDL wait so their latency
+  // overlaps the previous kernel's tail as well.
+  uint32_t rbeg = 0, rend = 0;
+  uint4 mine = make_uint4(0, 0, 0, 0);
+  int item_first = -1;
+  if (warp <= 1) {
+    rbeg = __ldg(stream_off + pair); rend = __ldg(stream_off + pair + 1);
+    if (rbeg + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg + lane));
+  } else {
+    item_first = tc2_item_at(eitems, 0, pair, n_pairs, n_slots);
+  }
   // everything above overlapped the previous kernel's tail (PDL); from here on we read what it wrote
   pdl_launch_dependents();
   pdl_wait();
@@ -206,10 +217,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // R2UR/ELECT loop), and one elected lane issues.
     uint32_t it = 0;
     long long t_wait = 0;
-    const uint32_t rbeg = __ldg(stream_off + pair), rend = __ldg(stream_off + pair + 1);
     const uint32_t ring = stg_base;
-    uint4 mine = make_uint4(0, 0, 0, 0);
-    if (rbeg + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg + lane));
     for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
       ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
       __syncwarp();
@@ -237,7 +245,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       }
       __syncwarp();
     }
-    if (fa.dbg && lane == 0) fa.dbg[blockIdx.x * 8 + 0] = (unsigned long long)t_wait;
+    if (fa.dbg && lane == 0) fa.dbg[blockIdx.x * 16 + 0] = (unsigned long long)t_wait;
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
@@ -245,10 +253,11 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       uint32_t it = 0, item_count = 0;
       long long t_wait_full = 0, t_wait_acc = 0, t_issue = 0;
       const long long t_mma_start = fa.dbg ? clock64() : 0;
-      const uint32_t rbeg = __ldg(stream_off + pair), rend = __ldg(stream_off + pair + 1);
+      unsigned long long gt_mma0 = 0, gt_first = 0;
+      if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_mma0));
       const uint32_t ring = stg_base + TC2_REC_BATCH * (uint32_t)sizeof(TcRec);
-      uint4 mine = make_uint4(0, 0, 0, 0);
-      if (rbeg + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg + lane));
+      const uint64_t desc0 = make_smem_desc_sw128(smem_base);
+      const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
       uint32_t buf = 0;
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
@@ -269,18 +278,21 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const long long tf0 = fa.dbg ? clock64() : 0;
           ptx::mbar_wait(bar_full + 8 * stage, phase);
           const long long tf1 = fa.dbg ? clock64() : 0;
+          if (fa.dbg && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_first));
           ptx::tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
           if (ptx::elect_one()) {
-            const uint64_t a_desc = make_smem_desc_sw128(sa);
+            // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
+            const uint32_t a_lo = desc_lo0 + stage * (uint32_t)(STAGE_BYTES >> 4);
+            const uint32_t d0 = tmem_base + buf * TC2_BUF_COLS;
             for (int b = 0; b < nb; ++b) {
-              const int acc = ((((b < 4) ? rec.z : rec.w) >> (8 * (b & 3))) >> 5) & 0x7;
+              const uint32_t acc = ((((b < 4) ? rec.z : rec.w) >> (8 * (b & 3))) >> 5) & 0x7u;
               const uint32_t first = (firsts >> b) & 1u;
-              const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES + b * HALF_B);
-              const uint32_t d = tmem_base + buf * TC2_BUF_COLS + acc * ACC_STRIDE;
+              const uint32_t b_lo = a_lo + (uint32_t)((TC_A_BYTES + b * HALF_B) >> 4);
+              const uint32_t d = d0 + acc * ACC_STRIDE;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                ptx::umma_f16_2sm(d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (k > 0 || !first) ? 1u : 0u);
+                ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idesc,
+                                  (k > 0 || !first) ? 1u : 0u);
             }
             ptx::umma_commit_2sm(bar_empty + 8 * stage);          // frees this stage in both CTAs
             if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
@@ -292,10 +304,13 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         __syncwarp();
       }
       if (fa.dbg && lane == 0) {
-        fa.dbg[blockIdx.x * 8 + 1] = (unsigned long long)t_wait_full;
-        fa.dbg[blockIdx.x * 8 + 2] = (unsigned long long)t_wait_acc;
-        fa.dbg[blockIdx.x * 8 + 3] = (unsigned long long)t_issue;
-        fa.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_mma_start);   // MMA warp: whole item loop
+        fa.dbg[blockIdx.x * 16 + 1] = (unsigned long long)t_wait_full;
+        fa.dbg[blockIdx.x * 16 + 2] = (unsigned long long)t_wait_acc;
+        fa.dbg[blockIdx.x * 16 + 3] = (unsigned long long)t_issue;
+        fa.dbg[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_mma_start);   // MMA warp: whole item loop
+        unsigned long long gt_mma1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_mma1));
+        fa.dbg[blockIdx.x * 16 + 8] = gt_mma0; fa.dbg[blockIdx.x * 16 + 9] = gt_mma1; fa.dbg[blockIdx.x * 16 + 10] = gt_first;
       }
     }
   } else {
@@ -310,7 +325,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const long long t_start = fa.dbg ? clock64() : 0;
     unsigned long long gt_start = 0;
     if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
-    for (int kk = 0, item_e = tc2_item_at(eitems, 0, pair, n_pairs, n_slots), item_next; item_e >= 0; ++kk, ++item_count, item_e = item_next) {
+    for (int kk = 0, item_e = item_first, item_next; item_e >= 0; ++kk, ++item_count, item_e = item_next) {
       item_next = tc2_item_at(eitems, kk + 1, pair, n_pairs, n_slots);      // (window << 16 | row pair), one item ahead
       const int win = item_e >> 16, mp = item_e & 0xFFFF;
       const TcItem2* ip = items + win;
@@ -339,13 +354,17 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const bool t0 = (warp == 2 + 4 * half) && lane == 0;  // issues this half's bulk copies
         const int row0 = (2 * mp + (int)rank) * kRowTile;
         const uint32_t swz = (uint32_t)(row & 7);
-        for (int u = half; u < n_units; u += 2) {
-          const int a = u / G, g = u % G, q = ip->q[a];
-          unsigned long long mbits = ~0ull;
-          if (EPI == EPI_MASK) mbits = __ldg(fa.mb_in + ((size_t)q * n_pad + n) * G + g);   // in flight during the TMEM load
-          uint32_t r0[32], r1[32];
+        uint32_t r0[32], r1[32];
+        unsigned long long mbits = ~0ull, mbits_next = ~0ull;
+        if (half < n_units) {
+          const int a = half / G, g = half % G;
+          if (EPI == EPI_MASK) mbits_next = __ldg(fa.mb_in + ((size_t)ip->q[a] * n_pad + n) * G + g);
           ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64), r0);
           ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64 + 32), r1);
+        }
+        for (int u = half; u < n_units; u += 2) {
+          const int a = u / G, g = u % G, q = ip->q[a];
+          mbits = mbits_next;
           ptx::tmem_ld_wait();
           uint32_t pk[32];
           {
@@ -377,6 +396,12 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) pk[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+          }
+          if (u + 2 < n_units) {                           // next unit's accumulator columns: in flight during the store phase
+            const int a2 = (u + 2) / G, g2 = (u + 2) % G;
+            if (EPI == EPI_MASK) mbits_next = __ldg(fa.mb_in + ((size_t)ip->q[a2] * n_pad + n) * G + g2);
+            ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64), r0);
+            ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64 + 32), r1);
           }
           if (t0) ptx::bulk_wait_read0();                  // the previous store has finished reading s_out
           ptx::named_bar_sync(1 + half, 128);              // s_out free
@@ -428,11 +453,11 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     if (TMA_EPI && lane == 0 && (warp == 2 || warp == 6)) ptx::bulk_wait_all0();   // stores landed before exit
     if (fa.dbg && warp == 2 && lane == 0) {
-      fa.dbg[blockIdx.x * 8 + 5] = (unsigned long long)t_ework;
+      fa.dbg[blockIdx.x * 16 + 5] = (unsigned long long)t_ework;
       unsigned long long gt_end;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
-      fa.dbg[blockIdx.x * 8 + 6] = gt_start;      // ns, after the PDL wait
-      fa.dbg[blockIdx.x * 8 + 7] = gt_end;        // ns, after this CTA's last epilogue
+      fa.dbg[blockIdx.x * 16 + 6] = gt_start;      // ns, after the PDL wait
+      fa.dbg[blockIdx.x * 16 + 7] = gt_end;        // ns, after this CTA's last epilogue
     }
   }
 
@@ -646,7 +671,7 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   if (final_args) fa = *final_args;
   fa.dbg = nullptr;
   fa.dbg_flags = st.dbg_flags;
-  if (st.dbg != nullptr && st.dbg_launch < st.dbg_max_launches) fa.dbg = st.dbg + (size_t)(st.dbg_launch++) * 160 * 8;
+  if (st.dbg != nullptr && st.dbg_launch < st.dbg_max_launches) fa.dbg = st.dbg + (size_t)(st.dbg_launch++) * 160 * 16;
   CUtensorMap tm_a;
   int rc;
   if (pre_a != nullptr) tm_a = *pre_a;          // encoded once per workspace by the caller

@@ -23,17 +23,18 @@ z0 = (torch.randn(B * R, 128, generator=g) * 128 ** -0.5).cuda()
 gan.reconstruct(x, z_init_val=z0)
 torch.cuda.synchronize()
 nat = gan._native
-buf = (ctypes.c_ulonglong * (64 * 160 * 8))()
+buf = (ctypes.c_ulonglong * (64 * 160 * 16))()
 nat.lib.dgan_debug_tc_timing.restype = ctypes.c_int
 nat.lib.dgan_debug_tc_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 n = nat.lib.dgan_debug_tc_timing(nat._handle, buf, 64)
-a = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 8)[:n].astype(np.float64)
+a = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 16)[:n].astype(np.float64)
 names = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "mma_issue", "mma_loop_total", "epi_work", "CTA util %"]
 print("launch | " + " | ".join(names) + " | first start us | last start us | first end us | last end us | gap to next us"
       "   (cycles: mean over active CTAs; MMA columns: leader CTAs only; times: %globaltimer, PDL on)")
-raw = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 8)[:n]
+raw = np.frombuffer(buf, dtype=np.uint64).reshape(64, 160, 16)[:n]
 t0 = None
 rows = []
+extras = {}
 for i in range(n):
     act = raw[i][:, 7] > 0
     if not act.any():
@@ -49,7 +50,15 @@ for i in range(n):
         t0 = st.min()
     util = float((en - st).mean()) / max(1.0, float(en.max() - st.min()))
     vals.append(100.0 * util)
+    lm = lead & (raw[i][:, 8] > 0)
+    if lm.any():   # leader CTAs: us from the PDL wait to MMA-loop start / first operands landed / loop end / CTA end
+        g0 = raw[i][lm, 6].astype(np.int64)
+        extra = "  [mma start +%.1f, first full +%.1f, loop end +%.1f, cta end +%.1f us]" % tuple(
+            float((raw[i][lm, k].astype(np.int64) - g0).mean()) / 1e3 for k in (8, 10, 9, 7))
+    else:
+        extra = ""
+    extras[i] = extra
     rows.append((i, vals, (st.min() - t0) / 1e3, (st.max() - t0) / 1e3, (en.min() - t0) / 1e3, (en.max() - t0) / 1e3))
 for j, (i, vals, s0, s1, e0, e1) in enumerate(rows):
     gap = rows[j + 1][2] - e1 if j + 1 < len(rows) else float("nan")
-    print("%2d | " % i + " | ".join("%9.0f" % v for v in vals) + " | %8.1f | %8.1f | %8.1f | %8.1f | %6.1f" % (s0, s1, e0, e1, gap))
+    print("%2d | " % i + " | ".join("%9.0f" % v for v in vals) + " | %8.1f | %8.1f | %8.1f | %8.1f | %6.1f" % (s0, s1, e0, e1, gap) + extras.get(i, ""))
