@@ -44,10 +44,16 @@ __host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out
 // assigned to it (LPT order), so producer and MMA warps read one contiguous array: 32 records per coalesced
 // warp load, staged in shared memory, the next batch always in flight - no table-load stalls on the issue path.
 struct __align__(16) TcRec {
-  uint32_t w0;       // input pixel [0,16) | k-chunk [16,24) | n_b [24,32)
-  uint32_t w1;       // first-MMA mask [0,8) | flags [8,16): 1 = first step of an item, 2 = last step | row pair mp [16,32)
-  uint8_t tb[8];     // per weight tile: tile id [0,5) | accumulator [5,8)
+  uint32_t w0;       // producer: input pixel [0,16) | k-chunk [16,24) | weight slots [24,32);   MMA: groups [24,32)
+  uint32_t w1;       // first-MMA mask, bit per group [0,8) | flags [8,16): 1 = first step of an item, 2 = last | row pair mp [16,32)
+  uint8_t tb[8];     // producer, per weight slot: tile id [0,5) | half (row offset N/2) [5,6)
+                     // MMA, per group: first slot [0,3) | slots - 1 [3,5) | accumulator [5,8)
 };
+// Merged-N groups: when one input pixel feeds g accumulators that sit side by side in TMEM (acc, acc+1, ...), its g
+// weight tiles are staged back to back and ONE MMA of N = g * N_TILE updates all of them (the A tile is read from
+// shared memory once instead of g times).  With cta_group::2 the merged B operand [W_0 | W_1 | ...] is split in
+// halves across the pair: CTA r stages half-tiles x = r*g + j (j < g) of the sequence W_0.lo, W_0.hi, W_1.lo, ...
+// - hence per-rank producer streams.  g = 1 reduces to "each CTA stages its half of the tile".
 constexpr int TC2_REC_BATCH = 32;
 constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // producer + MMA warp rings
 
@@ -149,7 +155,8 @@ template <int N_TILE, int EPI, typename TOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_mask,
-                  const TcItem2* __restrict__ items, const TcRec* __restrict__ stream, const uint32_t* __restrict__ stream_off,
+                  const TcItem2* __restrict__ items, const TcRec* __restrict__ stream_p0, const TcRec* __restrict__ stream_p1,
+                  const TcRec* __restrict__ stream_m, const uint32_t* __restrict__ stream_off,
                   const int* __restrict__ eitems, int n_slots,
                   TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
                   const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
@@ -200,6 +207,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   uint32_t rbeg = 0, rend = 0;
   uint4 mine = make_uint4(0, 0, 0, 0);
   int item_first = -1;
+  const TcRec* __restrict__ stream = warp == 1 ? stream_m : (rank ? stream_p1 : stream_p0);
   if (warp <= 1) {
     rbeg = __ldg(stream_off + pair); rend = __ldg(stream_off + pair + 1);
     if (rbeg + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg + lane));
@@ -237,8 +245,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (leader) ptx::mbar_expect_tx(full, 2u * (uint32_t)(TC_A_BYTES + nb * HALF_B));
           ptx::tma_load_3d_2sm(sa, &tm_a, full, kc * 64, row0, p);
           for (int b = 0; b < nb; ++b) {
-            const int tile = (((b < 4) ? rec.z : rec.w) >> (8 * (b & 3))) & 0x1F;
-            ptx::tma_load_3d_2sm(sa + TC_A_BYTES + b * HALF_B, &tm_b, full, kc * 64, (int)rank * (N_TILE / 2), tile);
+            const uint32_t e = ((b < 4) ? rec.z : rec.w) >> (8 * (b & 3));
+            ptx::tma_load_3d_2sm(sa + TC_A_BYTES + b * HALF_B, &tm_b, full, kc * 64, (int)((e >> 5) & 1u) * (N_TILE / 2), (int)(e & 0x1Fu));
           }
         }
         __syncwarp();
@@ -284,14 +292,15 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
             const uint32_t a_lo = desc_lo0 + stage * (uint32_t)(STAGE_BYTES >> 4);
             const uint32_t d0 = tmem_base + buf * TC2_BUF_COLS;
-            for (int b = 0; b < nb; ++b) {
-              const uint32_t acc = ((((b < 4) ? rec.z : rec.w) >> (8 * (b & 3))) >> 5) & 0x7u;
-              const uint32_t first = (firsts >> b) & 1u;
-              const uint32_t b_lo = a_lo + (uint32_t)((TC_A_BYTES + b * HALF_B) >> 4);
-              const uint32_t d = d0 + acc * ACC_STRIDE;
+            for (int gi = 0; gi < nb; ++gi) {                 // nb = merged-N groups of this step
+              const uint32_t e = ((gi < 4) ? rec.z : rec.w) >> (8 * (gi & 3));
+              const uint32_t first = (firsts >> gi) & 1u;
+              const uint32_t b_lo = a_lo + (uint32_t)(TC_A_BYTES >> 4) + (e & 7u) * (uint32_t)(HALF_B >> 4);
+              const uint32_t d = d0 + ((e >> 5) & 7u) * ACC_STRIDE;
+              const uint32_t idg = idesc + ((e >> 3) & 3u) * ((uint32_t)(N_TILE >> 3) << 17);   // N = slots * N_TILE
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idesc,
+                ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idg,
                                   (k > 0 || !first) ? 1u : 0u);
             }
             ptx::umma_commit_2sm(bar_empty + 8 * stage);          // frees this stage in both CTAs
@@ -474,7 +483,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 struct Tc2Schedule {           // one window tiling of a layer-direction + its item -> CTA-pair assignment, uploaded
   TcItem2* items = nullptr;
-  TcRec* stream = nullptr;         // per CTA pair: the concatenated step records of its items
+  TcRec* stream_p[2] = {nullptr, nullptr};   // producer records per cluster rank; per CTA pair: its items' steps, concatenated
+  TcRec* stream_m = nullptr;       // MMA records, same indexing
   uint32_t* stream_off = nullptr;  // [n_pairs + 1] record offsets into `stream`
   int* eitems = nullptr;           // [n_slots][n_pairs] (window << 16 | row pair) for the epilogue warps, or -1
   int n_slots = 0, n_pairs = 0;
@@ -516,6 +526,8 @@ static void tc2_build_schedule(const PairTable& tab, int h_grid, int w_grid, int
           by_p[g].second.push_back({t, (int)a});
         }
       std::sort(by_p.begin(), by_p.end(), [](const auto& l, const auto& r) { return l.first < r.first; });
+      for (auto& g : by_p)
+        std::stable_sort(g.second.begin(), g.second.end(), [](const auto& l, const auto& r) { return l.second < r.second; });
       uint32_t seen = 0;
       for (auto& g : by_p)
         for (size_t b0 = 0; b0 < g.second.size(); b0 += maxb) {
@@ -610,9 +622,12 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   sc.n_slots = (int)n_slots;
   std::vector<int> eitems(n_slots * (size_t)n_pairs, -1);
   std::vector<uint32_t> stream_off((size_t)n_pairs + 1, 0);
-  std::vector<TcRec> stream;
+  std::vector<TcRec> stream_p[2], stream_m;
+  const bool merge = (N >= 64) && !(getenv("DGAN_MERGE_N") && atoi(getenv("DGAN_MERGE_N")) == 0);
+  const int max_g = merge ? std::min(4, 256 / N) : 1;
+  long long n_mma = 0, n_single = 0;
   for (size_t pr = 0; pr < best_lists.size(); ++pr) {
-    stream_off[pr] = (uint32_t)stream.size();
+    stream_off[pr] = (uint32_t)stream_m.size();
     for (size_t k = 0; k < best_lists[pr].size(); ++k) {
       const int win = best_lists[pr][k] / n_mpairs, mp = best_lists[pr][k] % n_mpairs;
       if (win > 0x7FFF || mp > 0xFFFF) { set_error("tensor-core schedule limits exceeded"); return DGAN_ERR_UNSUPPORTED; }
@@ -620,26 +635,51 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
       const TcItem2& itm = best_items[(size_t)win];
       for (uint32_t j = 0; j < itm.n_steps; ++j) {
         const TcStep2& st2 = best_steps[itm.step_beg + j];
-        TcRec r{};
-        r.w0 = st2.w0;
+        const int nb = (int)((st2.w0 >> 24) & 0xFF);
         const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.n_steps ? 2u : 0u);
-        r.w1 = (st2.w1 & 0xFFu) | (flags << 8) | ((uint32_t)mp << 16);
-        for (int b = 0; b < 8; ++b) r.tb[b] = (uint8_t)((st2.tb[b] & 0x1F) | (((st2.tb[b] >> 8) & 0x7) << 5));
-        stream.push_back(r);
+        TcRec rp[2] = {}, rm{};
+        // slots are sorted by accumulator: runs of consecutive accumulators with equal first-MMA flags form one group
+        int n_groups = 0;
+        uint32_t gfirsts = 0;
+        for (int b = 0; b < nb;) {
+          const int acc0 = (st2.tb[b] >> 8) & 0x7;
+          const uint32_t f0 = (st2.w1 >> b) & 1u;
+          int g = 1;
+          while (g < max_g && b + g < nb && (int)((st2.tb[b + g] >> 8) & 0x7) == acc0 + g && ((st2.w1 >> (b + g)) & 1u) == f0) ++g;
+          for (int r = 0; r < 2; ++r)
+            for (int jj = 0; jj < g; ++jj) {
+              const int x = r * g + jj;                     // half-tile index in W_0.lo, W_0.hi, W_1.lo, ...
+              rp[r].tb[b + jj] = (uint8_t)((st2.tb[b + x / 2] & 0x1F) | ((x & 1) << 5));
+            }
+          rm.tb[n_groups] = (uint8_t)(b | ((g - 1) << 3) | (acc0 << 5));
+          gfirsts |= f0 << n_groups;
+          ++n_groups; b += g;
+          n_mma += 1; n_single += g;
+        }
+        for (int r = 0; r < 2; ++r) {
+          rp[r].w0 = st2.w0;
+          rp[r].w1 = (flags << 8) | ((uint32_t)mp << 16);
+          stream_p[r].push_back(rp[r]);
+        }
+        rm.w0 = (st2.w0 & 0x00FFFFFFu) | ((uint32_t)n_groups << 24);
+        rm.w1 = gfirsts | (flags << 8) | ((uint32_t)mp << 16);
+        stream_m.push_back(rm);
       }
     }
   }
-  stream_off[(size_t)n_pairs] = (uint32_t)stream.size();
+  stream_off[(size_t)n_pairs] = (uint32_t)stream_m.size();
   int rc;
   if ((rc = tc_upload(allocs, best_items.data(), best_items.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
-  if ((rc = tc_upload(allocs, stream.data(), stream.size() * sizeof(TcRec), (void**)&sc.stream, s))) return rc;
+  for (int r = 0; r < 2; ++r)
+    if ((rc = tc_upload(allocs, stream_p[r].data(), stream_p[r].size() * sizeof(TcRec), (void**)&sc.stream_p[r], s))) return rc;
+  if ((rc = tc_upload(allocs, stream_m.data(), stream_m.size() * sizeof(TcRec), (void**)&sc.stream_m, s))) return rc;
   if ((rc = tc_upload(allocs, stream_off.data(), stream_off.size() * sizeof(uint32_t), (void**)&sc.stream_off, s))) return rc;
   if ((rc = tc_upload(allocs, eitems.data(), eitems.size() * sizeof(int), (void**)&sc.eitems, s))) return rc;
   w2.by_mpairs.push_back({n_mpairs, sc});
   *out = &w2.by_mpairs.back().second;
   if (getenv("DGAN_TC_VERBOSE"))
-    fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d, %d windows\n", N, K, w2.h_grid, w2.w_grid,
-            n_mpairs, best_wh, best_ww, (*out)->n_windows);
+    fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d, %d windows, %lld tile-MMAs in %lld merged\n", N, K,
+            w2.h_grid, w2.w_grid, n_mpairs, best_wh, best_ww, (*out)->n_windows, n_single, n_mma);
   return 0;
 }
 
@@ -693,10 +733,10 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
-                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
-                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
+                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
                   mask_src, out_scale, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
