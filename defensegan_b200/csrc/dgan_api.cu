@@ -227,6 +227,7 @@ struct Workspace {
   bool have_maps = false;
   __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
   int n_loss_parts = 0, n_g_parts = 1;
+  size_t loss_stride_n = 1, loss_stride_b = 1;   // loss_part index = n * stride_n + part * stride_b
   float *y = nullptr, *dpre = nullptr, *loss_part = nullptr, *loss = nullptr;
   size_t bytes = 0;
 };
@@ -252,6 +253,8 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   if (tc) w.z_h = (__half*)take(np * latent * 2);
   if (tc) w.dblk = (__half*)take((size_t)c->tc_fin.n_blocks * np * 64 * 2);
   w.n_loss_parts = tc ? c->tc_fin.n_blocks : c->fin.n_bands;
+  w.loss_stride_n = tc ? 1 : (size_t)w.n_loss_parts;          // fp16 path: [block][n_pad] (coalesced epilogue stores)
+  w.loss_stride_b = tc ? (size_t)np : 1;
   for (const GemmLayer& l : c->layers) {
     const size_t elems = (size_t)l.P_out * np * l.C_out;
     if (tc) {
@@ -526,6 +529,8 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
 static int run_init_z(dgan_ctx* c, const Workspace& w, const float* z0, uint64_t seed, cudaStream_t s, size_t row_offset = 0) {
   const int latent = c->desc.latent_dim;
   const size_t total4 = (size_t)w.n_pad * latent / 4;
+  // the last layer's block tensor is K-padded to 64 columns; the epilogue only ever writes the 16*C_out valid ones
+  if (w.dblk != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.dblk, 0, (size_t)c->tc_fin.n_blocks * w.n_pad * 64 * sizeof(__half), s));
   init_z_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(w.z, w.v, w.z_h, z0, w.n_rows, w.n_pad, latent, seed,
                                                                  sqrtf(1.0f / (float)latent), row_offset * latent);
   DGAN_LAUNCH_CHECK(c);
@@ -821,7 +826,7 @@ int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, con
   if ((rc = run_init_z(h, w, z_dev, 0, s))) return rc;
   if ((rc = run_forward(h, w, x_dev, rec_rr, batch, true, s))) return rc;
   if ((rc = run_backward(h, w, s))) return rc;
-  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, 1.0f / (float)h->hwc, n_rows, w.loss);
+  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, w.loss_stride_n, w.loss_stride_b, 1.0f / (float)h->hwc, n_rows, w.loss);
   DGAN_LAUNCH_CHECK(h);
   if (y_dev) DGAN_CUDA_CHECK(cudaMemcpyAsync(y_dev, w.y, (size_t)n_rows * h->hwc * 4, cudaMemcpyDeviceToDevice, s));
   if (loss_dev) DGAN_CUDA_CHECK(cudaMemcpyAsync(loss_dev, w.loss, (size_t)n_rows * 4, cudaMemcpyDeviceToDevice, s));
@@ -901,7 +906,7 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
   for (Chain& ch : chains) {
     const Workspace& w = ch.w;
     const int nb = ch.hi - ch.lo, n_rows = nb * rec_rr;
-    loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, ch.s>>>(w.loss_part, w.n_loss_parts, 1.0f / (float)h->hwc, n_rows, w.loss);
+    loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, ch.s>>>(w.loss_part, w.n_loss_parts, w.loss_stride_n, w.loss_stride_b, 1.0f / (float)h->hwc, n_rows, w.loss);
     DGAN_LAUNCH_CHECK(h);
     select_kernel<<<nb, 256, 0, ch.s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev + (size_t)ch.lo * h->hwc,
                                          loss_dev ? loss_dev + ch.lo : nullptr, idx_dev ? idx_dev + ch.lo : nullptr);

@@ -339,12 +339,12 @@ __global__ void init_z_kernel(float* __restrict__ z, float* __restrict__ v, __ha
 }
 
 // loss[n] = (sum of band partials, fixed order) / (H*W*C)            (models/gan.py:411-413)
-__global__ void loss_finish_kernel(const float* __restrict__ loss_part, int n_bands, float inv_hwc,
-                                   int n_rows, float* __restrict__ loss) {
+__global__ void loss_finish_kernel(const float* __restrict__ loss_part, int n_bands, size_t stride_n, size_t stride_b,
+                                   float inv_hwc, int n_rows, float* __restrict__ loss) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_rows) return;
   float s = 0.f;
-  for (int b = 0; b < n_bands; ++b) s += loss_part[(size_t)n * n_bands + b];
+  for (int b = 0; b < n_bands; ++b) s += loss_part[(size_t)n * stride_n + (size_t)b * stride_b];
   loss[n] = s * inv_hwc;
 }
 

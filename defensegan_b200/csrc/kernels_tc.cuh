@@ -174,7 +174,7 @@ enum TcEpilogue : int { EPI_FINAL_SIGMOID1 = 8, EPI_FINAL_TANH3 = 9, EPI_MOMENTU
 struct TcFinalArgs {
   const float* x;        // [B][H*W*C] target images (NULL: forward only)
   float* y;              // [n_pad][H*W*C] G(z)
-  float* loss_part;      // [n_pad][n_blocks] sum over the block of (y-x)^2
+  float* loss_part;      // [n_blocks][n_pad] sum over the block of (y-x)^2 (written when write_y)
   int R, B, n_rows;      // restarts per image, images, valid latent rows
   int nbx, w_out;        // blocks per image row, image width
   int write_y;           // store G(z) (only the last iteration / forward-only calls consume it)
@@ -191,23 +191,28 @@ struct TcFinalArgs {
   int dbg_flags;            // timing experiments only: 1 = skip epilogue stores, 2 = skip mask loads, 4 = skip bias
 };
 
-template <int C_OUT, int ACT>
-__device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalArgs& fa, const float* __restrict__ bias,
-                                                  int blk, int n, int n_pad, __half* __restrict__ dblk) {
-  constexpr int NV = 16 * C_OUT;
+// Target pixels (4x4 block of image n / R) of one row: loaded one accumulator ahead of their use.
+template <int C_OUT>
+__device__ __forceinline__ void tc_final_targets(float4 (&xq)[4 * C_OUT], const TcFinalArgs& fa, int blk, int n) {
+  if (fa.x == nullptr || (fa.dbg_flags & 32)) return;   // flag 32: timing experiment without the target loads
   const int by = blk / fa.nbx, bx = blk % fa.nbx;
   const int hwc = fa.w_out * fa.w_out * C_OUT;
   const int img = min(n / fa.R, fa.B - 1);
-  // target pixels of this row's block: issued before the TMEM load so that both latencies overlap
-  float4 xq[4 * C_OUT];
-  if (fa.x != nullptr) {
 #pragma unroll
-    for (int li = 0; li < 4; ++li) {
-      const size_t off = (size_t)((4 * by + li) * fa.w_out + 4 * bx) * C_OUT;
+  for (int li = 0; li < 4; ++li) {
+    const size_t off = (size_t)((4 * by + li) * fa.w_out + 4 * bx) * C_OUT;
 #pragma unroll
-      for (int e4 = 0; e4 < C_OUT; ++e4) xq[li * C_OUT + e4] = __ldg(reinterpret_cast<const float4*>(fa.x + (size_t)img * hwc + off) + e4);
-    }
+    for (int e4 = 0; e4 < C_OUT; ++e4) xq[li * C_OUT + e4] = __ldg(reinterpret_cast<const float4*>(fa.x + (size_t)img * hwc + off) + e4);
   }
+}
+
+template <int C_OUT, int ACT>
+__device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalArgs& fa, const float* __restrict__ bias,
+                                                  int blk, int n, int n_pad, __half* __restrict__ dblk,
+                                                  const float4 (&xq)[4 * C_OUT]) {
+  constexpr int NV = 16 * C_OUT;
+  const int by = blk / fa.nbx, bx = blk % fa.nbx;
+  const int hwc = fa.w_out * fa.w_out * C_OUT;
   float v[NV];
 #pragma unroll
   for (int c = 0; c < NV; c += 16) {
@@ -221,9 +226,7 @@ __device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalA
 #pragma unroll
   for (int co = 0; co < C_OUT; ++co) bsv[co] = __ldg(bias + co);
   float lsum = 0.f;
-  uint32_t packed[32];   // 64 fp16 of this row of the block tensor (zero padded)
-#pragma unroll
-  for (int j = 0; j < 32; ++j) packed[j] = 0u;
+  uint32_t packed[NV / 2];   // the 16*C_OUT valid fp16 of this row of the block tensor
 #pragma unroll
   for (int li = 0; li < 4; ++li) {
     const size_t off = (size_t)((4 * by + li) * fa.w_out + 4 * bx) * C_OUT;
@@ -252,11 +255,12 @@ __device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalA
 #pragma unroll
     for (int e2 = 0; e2 < 2 * C_OUT; ++e2) packed[li * 2 * C_OUT + e2] = pack_half2(dv[2 * e2], dv[2 * e2 + 1]);
   }
-  if (fa.x != nullptr) {
+  if (fa.x != nullptr && !((fa.dbg_flags & 1) && lsum != 12345.678f)) {   // flag 1: timing experiment without the stores
     uint4* dp = reinterpret_cast<uint4*>(dblk + ((size_t)blk * n_pad + n) * 64);
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) dp[j4] = make_uint4(packed[j4 * 4], packed[j4 * 4 + 1], packed[j4 * 4 + 2], packed[j4 * 4 + 3]);
-    fa.loss_part[(size_t)n * (fa.nbx * fa.nbx) + blk] = lsum;
+    for (int j4 = 0; j4 < NV / 8; ++j4)   // the K-padding columns [NV, 64) stay zero (cleared once per call)
+      dp[j4] = make_uint4(packed[j4 * 4], packed[j4 * 4 + 1], packed[j4 * 4 + 2], packed[j4 * 4 + 3]);
+    if (fa.write_y) fa.loss_part[(size_t)blk * n_pad + n] = lsum;   // the loss is consumed after the last forward only
   }
 }
 
@@ -521,10 +525,15 @@ tc_bsgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
         for (int a = 0; a < n_acc; ++a) {
           const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * ACC_STRIDE);
-          if (EPI == EPI_FINAL_SIGMOID1)
-            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out));
-          else
-            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out));
+          if (EPI == EPI_FINAL_SIGMOID1) {
+            float4 xq[4];
+            tc_final_targets<1>(xq, fa, ip->q[a], m * kRowTile + row);
+            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out), xq);
+          } else {
+            float4 xq[12];
+            tc_final_targets<3>(xq, fa, ip->q[a], m * kRowTile + row);
+            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out), xq);
+          }
         }
       } else {
         for (int a = 0; a < n_acc; ++a)

@@ -35,6 +35,10 @@ struct __align__(16) TcItem2 {
   uint32_t n_acc, step_beg, n_steps, pad;
 };
 
+// TMEM columns between the accumulators of one window.  N <= 32 (MNIST last layer: 16 outputs per block) packs
+// 8 accumulators into a 256-column buffer, so a window can span a whole row of blocks.
+__host__ __device__ constexpr int tc2_acc_stride(int n_tile) { return n_tile <= 32 ? 32 : (n_tile < 64 ? 64 : n_tile); }
+
 // Does this instantiation stage its output (and ReLU-mask) tiles through shared memory + TMA?
 __host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out_bytes) {
   return out_bytes == 2 && n_tile >= 64 && epi != EPI_FINAL_SIGMOID1 && epi != EPI_FINAL_TANH3;
@@ -60,8 +64,8 @@ constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // p
 template <int N_TILE, int EPI = EPI_NONE, int OUT_BYTES = 2>
 struct Tc2Cfg {
   static constexpr int HALF_B = (N_TILE / 2) * 128;                      // bytes of this CTA's half weight tile
-  static constexpr int ACC_STRIDE = N_TILE < 64 ? 64 : N_TILE;
-  static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (4 / 2 / 1)
+  static constexpr int ACC_STRIDE = tc2_acc_stride(N_TILE);
+  static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (8 / 4 / 2 / 1)
   static constexpr int STAGE_BYTES = ((TC_A_BYTES + MAXB * HALF_B + 1023) / 1024) * 1024;
   static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
   // epilogue staging: one output tile per epilogue half
@@ -260,6 +264,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       constexpr uint32_t idesc = make_idesc_f16(256, N_TILE);
       uint32_t it = 0, item_count = 0;
       long long t_wait_full = 0, t_wait_acc = 0, t_issue = 0;
+      const bool fine = fa.dbg != nullptr && !(fa.dbg_flags & 8);   // per-step clocks (perturbs the loop)
+      const bool no_mma = (fa.dbg_flags & 16) != 0;                 // timing experiment: commits only
       const long long t_mma_start = fa.dbg ? clock64() : 0;
       unsigned long long gt_mma0 = 0, gt_first = 0;
       if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_mma0));
@@ -279,20 +285,20 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const uint32_t firsts = rec.y & 0xFFu, flags = (rec.y >> 8) & 0xFFu;
           if (flags & 1u) {                                   // first step of an item: its accumulator buffer must be drained
             buf = item_count & 1;
-            const long long ta0 = fa.dbg ? clock64() : 0;
+            const long long ta0 = fine ? clock64() : 0;
             ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
-            if (fa.dbg) t_wait_acc += clock64() - ta0;
+            if (fine) t_wait_acc += clock64() - ta0;
           }
-          const long long tf0 = fa.dbg ? clock64() : 0;
+          const long long tf0 = fine ? clock64() : 0;
           ptx::mbar_wait(bar_full + 8 * stage, phase);
-          const long long tf1 = fa.dbg ? clock64() : 0;
+          const long long tf1 = fine ? clock64() : 0;
           if (fa.dbg && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_first));
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
             const uint32_t a_lo = desc_lo0 + stage * (uint32_t)(STAGE_BYTES >> 4);
             const uint32_t d0 = tmem_base + buf * TC2_BUF_COLS;
-            for (int gi = 0; gi < nb; ++gi) {                 // nb = merged-N groups of this step
+            for (int gi = 0; gi < (no_mma ? 0 : nb); ++gi) {  // nb = merged-N groups of this step
               const uint32_t e = ((gi < 4) ? rec.z : rec.w) >> (8 * (gi & 3));
               const uint32_t first = (firsts >> gi) & 1u;
               const uint32_t b_lo = a_lo + (uint32_t)(TC_A_BYTES >> 4) + (e & 7u) * (uint32_t)(HALF_B >> 4);
@@ -308,7 +314,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
           __syncwarp();
           if (flags & 2u) ++item_count;
-          if (fa.dbg) { t_wait_full += tf1 - tf0; t_issue += clock64() - tf1; }
+          if (fine) { t_wait_full += tf1 - tf0; t_issue += clock64() - tf1; }
         }
         __syncwarp();
       }
@@ -342,17 +348,28 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
       const uint32_t buf = item_count & 1;
       const uint32_t tbuf = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * TC2_BUF_COLS;
+      constexpr bool FINAL = (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3);
+      float4 xq_next[FINAL ? (EPI == EPI_FINAL_SIGMOID1 ? 4 : 12) : 1];
+      if (FINAL && half < n_acc)     // first block's target pixels: in flight while the MMAs finish
+        tc_final_targets<(EPI == EPI_FINAL_SIGMOID1 ? 1 : 3)>(reinterpret_cast<float4(&)[EPI == EPI_FINAL_SIGMOID1 ? 4 : 12]>(xq_next), fa, ip->q[half], (int)n);
       const long long te0 = fa.dbg ? clock64() : 0;
       ptx::mbar_wait(bar_acc_full + 8 * buf, (item_count >> 1) & 1);
       const long long te1 = fa.dbg ? clock64() : 0;
       ptx::tc_fence_after();
       if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
+        constexpr int CO = (EPI == EPI_FINAL_SIGMOID1) ? 1 : 3;
+        float4 xq[4 * CO];
         for (int a = half; a < n_acc; a += 2) {
+#pragma unroll
+          for (int j = 0; j < 4 * CO; ++j) xq[j] = xq_next[j];
+          if (a + 2 < n_acc) tc_final_targets<CO>(reinterpret_cast<float4(&)[4 * CO]>(xq_next), fa, ip->q[a + 2], (int)n);   // next block's targets in flight
           const uint32_t taddr = tbuf + (uint32_t)(a * ACC_STRIDE);
           if (EPI == EPI_FINAL_SIGMOID1)
-            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out));
+            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out),
+                                              reinterpret_cast<const float4(&)[4]>(xq));
           else
-            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out));
+            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out),
+                                           reinterpret_cast<const float4(&)[12]>(xq));
         }
       } else if (TMA_EPI) {
         // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 ->
@@ -499,7 +516,7 @@ struct TcWeights2 {
   mutable std::vector<Tc2Schedule> built;                       // distinct (wh, ww) tilings built so far
 };
 
-static int tc2_maxb(int N) { return TC2_BUF_COLS / std::max(N, 64); }
+static int tc2_maxb(int N) { return TC2_BUF_COLS / tc2_acc_stride(N); }
 
 // windows of wh x ww output pixels (wh*ww accumulators)
 static void tc2_build_schedule(const PairTable& tab, int h_grid, int w_grid, int N, int K, int wh, int ww,
@@ -555,7 +572,7 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
                                int w_grid, int force_max_acc, std::vector<void*>* allocs, cudaStream_t s) {
   (void)allocs; (void)s;
   const int N = w1.N, K = w1.K;
-  int max_acc = TC2_BUF_COLS / std::max(N, 64);
+  int max_acc = tc2_maxb(N);
   if (force_max_acc > 0) max_acc = std::min(max_acc, force_max_acc);
   w2->tab = tab; w2->h_grid = h_grid; w2->w_grid = w_grid; w2->max_acc = max_acc;
   return tc_make_map(st, &w2->tm_b, w1.w, (uint64_t)K, (uint64_t)N, (uint64_t)w1.n_tiles, (uint32_t)(N / 2));
@@ -578,7 +595,7 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   std::vector<TcStep2> best_steps;
   std::vector<std::vector<int>> best_lists;
   for (int wh = 1; wh <= 2; ++wh)
-    for (int ww = 1; ww <= 4; ++ww) {
+    for (int ww = 1; ww <= 8; ++ww) {
       if (wh * ww > w2.max_acc || wh > w2.h_grid || ww > std::max(w2.w_grid, 1)) continue;
       std::vector<TcItem2> items;
       std::vector<TcStep2> steps;

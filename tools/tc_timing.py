@@ -39,7 +39,7 @@ for i in range(n):
     act = raw[i][:, 7] > 0
     if not act.any():
         continue
-    lead = act & (a[i][:, 3] > 0)
+    lead = act & (a[i][:, 4] > 0)
     vals = []
     for k in range(6):
         m = lead if k in (1, 2, 3, 4) else act
