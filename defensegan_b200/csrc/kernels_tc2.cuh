@@ -44,35 +44,51 @@ __host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out
   return out_bytes == 2 && n_tile >= 64 && epi != EPI_FINAL_SIGMOID1 && epi != EPI_FINAL_TANH3;
 }
 
-// One step of a CTA pair's work stream (16 bytes).  The host concatenates, per CTA pair, the steps of all the items
-// assigned to it (LPT order), so producer and MMA warps read one contiguous array: 32 records per coalesced
+// One step of a CTA pair's work stream (32 bytes).  The host concatenates, per CTA pair, the steps of all the items
+// assigned to it (LPT order), so producer and MMA warps read one contiguous array: 16 records per coalesced
 // warp load, staged in shared memory, the next batch always in flight - no table-load stalls on the issue path.
-struct __align__(16) TcRec {
-  uint32_t w0;       // producer: input pixel [0,16) | k-chunk [16,24) | weight slots [24,32);   MMA: groups [24,32)
-  uint32_t w1;       // first-MMA mask, bit per group [0,8) | flags [8,16): 1 = first step of an item, 2 = last | row pair mp [16,32)
-  uint8_t tb[8];     // producer, per weight slot: tile id [0,5) | half (row offset N/2) [5,6)
-                     // MMA, per group: first slot [0,3) | slots - 1 [3,5) | accumulator [5,8)
-};
-// Merged-N groups: when one input pixel feeds g accumulators that sit side by side in TMEM (acc, acc+1, ...), its g
-// weight tiles are staged back to back and ONE MMA of N = g * N_TILE updates all of them (the A tile is read from
-// shared memory once instead of g times).  With cta_group::2 the merged B operand [W_0 | W_1 | ...] is split in
-// halves across the pair: CTA r stages half-tiles x = r*g + j (j < g) of the sequence W_0.lo, W_0.hi, W_1.lo, ...
-// - hence per-rank producer streams.  g = 1 reduces to "each CTA stages its half of the tile".
-constexpr int TC2_REC_BATCH = 32;
+//
+// A step stages up to 4 input-pixel (A) tiles and up to 8 weight half-tiles (B slots) for one k-chunk into a
+// variable-size region of a circular shared-memory ring (offset chosen by the host, which simulates the ring),
+// then issues up to 12 MMAs that combine them.  Several A tiles per step let one weight tile serve several input
+// pixels (stride-2 transposed conv: outputs of equal parity use the same tap with neighbouring inputs), which
+// is what the L2->SM byte count - the limiter of these kernels - cares about.
+//
+// producer record (per cluster rank):
+//   w[0]: ring offset / 1 KB [0,8) | k-chunk [8,12) | A tiles [12,15) | B slots [15,19) | dep [19,23)
+//         dep = D: the region overlaps that of step k-D (or D = 8, barrier-slot reuse): wait until step k-D is consumed
+//   w[1]: row pair mp [0,16)
+//   w[2..3]: 4 x u16 input pixel of A tile i
+//   w[4..5]: 8 x u8 per B slot: weight tile [0,5) | half (row offset N/2) [5,6)
+// MMA record:
+//   w[0]: ring offset / 1 KB [0,8) | A tiles [8,11) | ops [11,16) | flags [16,18): 1 = first step of an item, 2 = last
+//   w[2..7]: 12 x u16 per MMA: A tile [0,2) | first B slot [2,5) | slots - 1 [5,7) | accumulator [7,10) | first MMA into it [10,11)
+struct __align__(16) TcRec { uint32_t w[8]; };
+constexpr int TC2_MAX_A = 4, TC2_MAX_BSLOTS = 8, TC2_MAX_OPS = 12, TC2_NSLOT = 8;
+// Merged-N groups: when one input pixel feeds g accumulators that sit side by side in TMEM (acc, acc+1, ...) through
+// weight tiles nobody else in the step uses, the g tiles are staged back to back and ONE MMA of N = g * N_TILE
+// updates all of them.  With cta_group::2 the merged B operand [W_0 | W_1 | ...] is split in halves across the pair:
+// CTA r stages half-tiles x = r*g + j (j < g) of the sequence W_0.lo, W_0.hi, W_1.lo, ... - hence per-rank producer
+// streams.  g = 1 reduces to "each CTA stages its half of the tile".
+constexpr int TC2_REC_BATCH = 16;
 constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // producer + MMA warp rings
+
+__host__ __device__ constexpr int tc2_ring_bytes(int n_tile, int epi, int out_bytes) {
+  const int epi_b = tc2_tma_epilogue(n_tile, epi, out_bytes) ? 2 * TC2_TILE_BYTES : 0;
+  const int raw = ((TC2_SMEM_MAX - 1024 - 256 - TC2_STAGING_BYTES - epi_b) / 1024) * 1024;
+  return raw > 255 * 1024 ? 255 * 1024 : raw;
+}
 
 template <int N_TILE, int EPI = EPI_NONE, int OUT_BYTES = 2>
 struct Tc2Cfg {
   static constexpr int HALF_B = (N_TILE / 2) * 128;                      // bytes of this CTA's half weight tile
   static constexpr int ACC_STRIDE = tc2_acc_stride(N_TILE);
   static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (8 / 4 / 2 / 1)
-  static constexpr int STAGE_BYTES = ((TC_A_BYTES + MAXB * HALF_B + 1023) / 1024) * 1024;
   static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
   // epilogue staging: one output tile per epilogue half
   static constexpr int EPI_BYTES = TMA_EPI ? 2 * TC2_TILE_BYTES : 0;
-  static constexpr int STAGES_RAW = (TC2_SMEM_MAX - 1024 - 256 - TC2_STAGING_BYTES - EPI_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256;
+  static constexpr int RING_BYTES = tc2_ring_bytes(N_TILE, EPI, OUT_BYTES);          // operand ring (offsets are 8-bit KB)
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256;
 };
 
 namespace ptx {
@@ -130,6 +146,11 @@ __device__ __forceinline__ void tma_load_3d_local(uint32_t dst, const CUtensorMa
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -166,10 +187,10 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
   using Cfg = Tc2Cfg<N_TILE, EPI, (int)sizeof(TOUT)>;
   constexpr bool TMA_EPI = Cfg::TMA_EPI;
-  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
+  constexpr int HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;       // [out tile half0][out tile half1][mask half0][mask half1]
+  const uint32_t epi_base = smem_base + Cfg::RING_BYTES;       // [out tile half0][out tile half1][mask half0][mask half1]
   const uint32_t stg_base = epi_base + Cfg::EPI_BYTES;              // [producer ring][MMA ring] of TcRec
   const uint32_t bar_base = stg_base + TC2_STAGING_BYTES;
   const uint32_t bar_mask = bar_base + 176;                          // mask_full[2]
@@ -186,7 +207,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < TC2_NSLOT; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);    // leader's producer arrive.expect_tx (bytes of both CTAs)
       ptx::mbar_init(bar_empty + 8 * s, 1);   // one multicast commit per CTA
     }
@@ -214,7 +235,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const TcRec* __restrict__ stream = warp == 1 ? stream_m : (rank ? stream_p1 : stream_p0);
   if (warp <= 1) {
     rbeg = __ldg(stream_off + pair); rend = __ldg(stream_off + pair + 1);
-    if (rbeg + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg + lane));
+    if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);   // lane = 16-byte half
   } else {
     item_first = tc2_item_at(eitems, 0, pair, n_pairs, n_slots);
   }
@@ -233,24 +254,34 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
       ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
       __syncwarp();
-      if (base + TC2_REC_BATCH + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH + lane));
+      if (2 * (base + TC2_REC_BATCH) + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH) + lane);
       const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
       for (uint32_t i = 0; i < cnt; ++i, ++it) {
-        const uint4 rec = ptx::ld_shared_v4(ring + i * 16u);
-        const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1;
-        const int p = rec.x & 0xFFFF, kc = (rec.x >> 16) & 0xFF, nb = (rec.x >> 24) & 0xFF;
-        const int row0 = (2 * (int)(rec.y >> 16) + (int)rank) * kRowTile;
+        const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
+        const uint2 r1 = ptx::ld_shared_v2(ring + i * 32u + 16u);
+        const uint32_t slot = it & (TC2_NSLOT - 1);
+        const int kc = (r0.x >> 8) & 0xF, nA = (r0.x >> 12) & 0x7, nB = (r0.x >> 15) & 0xF;
+        const uint32_t dep = (r0.x >> 19) & 0xF;
+        const int row0 = (2 * (int)(r0.y & 0xFFFFu) + (int)rank) * kRowTile;
         const long long tw0 = fa.dbg ? clock64() : 0;
-        ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (it >= dep) ptx::mbar_wait(bar_empty + 8 * ((it - dep) & (TC2_NSLOT - 1)), ((it - dep) >> 3) & 1);   // step it-dep consumed
         if (fa.dbg) t_wait += clock64() - tw0;
-        const uint32_t full = bar_full + 8 * stage;
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint32_t full = bar_full + 8 * slot;
+        const uint32_t sa = smem_base + ((r0.x & 0xFFu) << 10);
         if (ptx::elect_one()) {
-          if (leader) ptx::mbar_expect_tx(full, 2u * (uint32_t)(TC_A_BYTES + nb * HALF_B));
-          ptx::tma_load_3d_2sm(sa, &tm_a, full, kc * 64, row0, p);
-          for (int b = 0; b < nb; ++b) {
-            const uint32_t e = ((b < 4) ? rec.z : rec.w) >> (8 * (b & 3));
-            ptx::tma_load_3d_2sm(sa + TC_A_BYTES + b * HALF_B, &tm_b, full, kc * 64, (int)((e >> 5) & 1u) * (N_TILE / 2), (int)(e & 0x1Fu));
+          if (leader) ptx::mbar_expect_tx(full, 2u * (uint32_t)(nA * TC_A_BYTES + nB * HALF_B));
+#pragma unroll
+          for (int a = 0; a < TC2_MAX_A; ++a) {
+            if (a >= nA) break;
+            const int p = (int)((((a < 2) ? r0.z : r0.w) >> (16 * (a & 1))) & 0xFFFFu);
+            ptx::tma_load_3d_2sm(sa + a * TC_A_BYTES, &tm_a, full, kc * 64, row0, p);
+          }
+          const uint32_t sb = sa + nA * TC_A_BYTES;
+#pragma unroll
+          for (int b = 0; b < TC2_MAX_BSLOTS; ++b) {
+            if (b >= nB) break;
+            const uint32_t e = ((b < 4) ? r1.x : r1.y) >> (8 * (b & 3));
+            ptx::tma_load_3d_2sm(sb + b * HALF_B, &tm_b, full, kc * 64, (int)((e >> 5) & 1u) * (N_TILE / 2), (int)(e & 0x1Fu));
           }
         }
         __syncwarp();
@@ -276,13 +307,14 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
         __syncwarp();
-        if (base + TC2_REC_BATCH + lane < rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH + lane));
+        if (2 * (base + TC2_REC_BATCH) + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH) + lane);
         const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
         for (uint32_t i = 0; i < cnt; ++i, ++it) {
-          const uint4 rec = ptx::ld_shared_v4(ring + i * 16u);
-          const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1;
-          const int nb = (rec.x >> 24) & 0xFF;
-          const uint32_t firsts = rec.y & 0xFFu, flags = (rec.y >> 8) & 0xFFu;
+          const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
+          const uint4 r1 = ptx::ld_shared_v4(ring + i * 32u + 16u);
+          const uint32_t slot = it & (TC2_NSLOT - 1), phase = (it >> 3) & 1;
+          const int nA = (r0.x >> 8) & 0x7, n_ops = (r0.x >> 11) & 0x1F;
+          const uint32_t flags = (r0.x >> 16) & 0x3u;
           if (flags & 1u) {                                   // first step of an item: its accumulator buffer must be drained
             buf = item_count & 1;
             const long long ta0 = fine ? clock64() : 0;
@@ -290,26 +322,31 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             if (fine) t_wait_acc += clock64() - ta0;
           }
           const long long tf0 = fine ? clock64() : 0;
-          ptx::mbar_wait(bar_full + 8 * stage, phase);
+          ptx::mbar_wait(bar_full + 8 * slot, phase);
           const long long tf1 = fine ? clock64() : 0;
           if (fa.dbg && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_first));
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
-            const uint32_t a_lo = desc_lo0 + stage * (uint32_t)(STAGE_BYTES >> 4);
+            const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
+            const uint32_t b_lo0 = a_lo0 + (uint32_t)nA * (uint32_t)(TC_A_BYTES >> 4);
             const uint32_t d0 = tmem_base + buf * TC2_BUF_COLS;
-            for (int gi = 0; gi < (no_mma ? 0 : nb); ++gi) {  // nb = merged-N groups of this step
-              const uint32_t e = ((gi < 4) ? rec.z : rec.w) >> (8 * (gi & 3));
-              const uint32_t first = (firsts >> gi) & 1u;
-              const uint32_t b_lo = a_lo + (uint32_t)(TC_A_BYTES >> 4) + (e & 7u) * (uint32_t)(HALF_B >> 4);
-              const uint32_t d = d0 + ((e >> 5) & 7u) * ACC_STRIDE;
-              const uint32_t idg = idesc + ((e >> 3) & 3u) * ((uint32_t)(N_TILE >> 3) << 17);   // N = slots * N_TILE
+            const uint32_t opw[6] = {r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int oi = 0; oi < TC2_MAX_OPS; ++oi) {
+              if (oi >= (no_mma ? 0 : n_ops)) break;
+              const uint32_t e = opw[oi >> 1] >> (16 * (oi & 1));
+              const uint32_t first = (e >> 10) & 1u;
+              const uint32_t a_lo = a_lo0 + (e & 3u) * (uint32_t)(TC_A_BYTES >> 4);
+              const uint32_t b_lo = b_lo0 + ((e >> 2) & 7u) * (uint32_t)(HALF_B >> 4);
+              const uint32_t d = d0 + ((e >> 7) & 7u) * ACC_STRIDE;
+              const uint32_t idg = idesc + ((e >> 5) & 3u) * ((uint32_t)(N_TILE >> 3) << 17);   // N = slots * N_TILE
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idg,
                                   (k > 0 || !first) ? 1u : 0u);
             }
-            ptx::umma_commit_2sm(bar_empty + 8 * stage);          // frees this stage in both CTAs
+            ptx::umma_commit_2sm(bar_empty + 8 * slot);           // frees this step's ring region in both CTAs
             if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
           }
           __syncwarp();
@@ -502,70 +539,164 @@ struct Tc2Schedule {           // one window tiling of a layer-direction + its i
   TcItem2* items = nullptr;
   TcRec* stream_p[2] = {nullptr, nullptr};   // producer records per cluster rank; per CTA pair: its items' steps, concatenated
   TcRec* stream_m = nullptr;       // MMA records, same indexing
-  uint32_t* stream_off = nullptr;  // [n_pairs + 1] record offsets into `stream`
+  uint32_t* stream_off = nullptr;  // [n_pairs + 1] record offsets into the streams
   int* eitems = nullptr;           // [n_slots][n_pairs] (window << 16 | row pair) for the epilogue warps, or -1
   int n_slots = 0, n_pairs = 0;
   int n_windows = 0;
-  int wh = 0, ww = 0;
+  int wh = 0, ww = 0, sy = 1, sx = 1;
 };
 struct TcWeights2 {
   CUtensorMap tm_b;            // box {64, N/2, 1}
   PairTable tab;               // host copy: schedules are built lazily per batch size
   int h_grid = 0, w_grid = 0, max_acc = 1;
   mutable std::vector<std::pair<int, Tc2Schedule>> by_mpairs;   // chosen schedule per n_mpairs (lazy cache)
-  mutable std::vector<Tc2Schedule> built;                       // distinct (wh, ww) tilings built so far
 };
 
 static int tc2_maxb(int N) { return TC2_BUF_COLS / tc2_acc_stride(N); }
 
-// windows of wh x ww output pixels (wh*ww accumulators)
-static void tc2_build_schedule(const PairTable& tab, int h_grid, int w_grid, int N, int K, int wh, int ww,
-                               std::vector<TcItem2>* items, std::vector<TcStep2>* steps) {
-  const int kch = K / 64;
-  const size_t maxb = (size_t)tc2_maxb(N);
-  for (int y0 = 0; y0 < h_grid; y0 += wh)
-    for (int x0 = 0; x0 < w_grid; x0 += ww) {
-      TcItem2 item{};
-      std::vector<int> qs;
-      for (int dy = 0; dy < wh && y0 + dy < h_grid; ++dy)
-        for (int dx = 0; dx < ww && x0 + dx < w_grid; ++dx) qs.push_back((y0 + dy) * w_grid + x0 + dx);
-      item.n_acc = (uint32_t)qs.size();
-      for (size_t a = 0; a < qs.size(); ++a) item.q[a] = (uint16_t)qs[a];
-      item.step_beg = (uint32_t)steps->size();
-      std::vector<std::pair<int, std::vector<std::pair<int, int>>>> by_p;
-      for (size_t a = 0; a < qs.size(); ++a)
-        for (int e = tab.off[qs[a]]; e < tab.off[qs[a] + 1]; ++e) {
-          const int p = tab.pairs[e].x, t = tab.pairs[e].y;
-          size_t g = 0;
-          for (; g < by_p.size(); ++g)
-            if (by_p[g].first == p) break;
-          if (g == by_p.size()) by_p.push_back({p, {}});
-          by_p[g].second.push_back({t, (int)a});
-        }
-      std::sort(by_p.begin(), by_p.end(), [](const auto& l, const auto& r) { return l.first < r.first; });
-      for (auto& g : by_p)
-        std::stable_sort(g.second.begin(), g.second.end(), [](const auto& l, const auto& r) { return l.second < r.second; });
-      uint32_t seen = 0;
-      for (auto& g : by_p)
-        for (size_t b0 = 0; b0 < g.second.size(); b0 += maxb) {
-          const size_t nb = std::min(maxb, g.second.size() - b0);
-          for (int kc = 0; kc < kch; ++kc) {
-            TcStep2 s{};
-            s.w0 = (uint32_t)g.first | ((uint32_t)kc << 16) | ((uint32_t)nb << 24);
-            uint32_t firsts = 0;
-            for (size_t b = 0; b < nb; ++b) {
-              const auto& ta = g.second[b0 + b];
-              s.tb[b] = (uint16_t)((ta.first & 0xFF) | (ta.second << 8));
-              if (!(seen & (1u << ta.second))) firsts |= 1u << b;
-            }
-            s.w1 = (kc == 0) ? firsts : 0;
-            steps->push_back(s);
-          }
-          for (size_t b = 0; b < nb; ++b) seen |= 1u << g.second[b0 + b].second;
-        }
-      item.n_steps = (uint32_t)steps->size() - item.step_beg;
-      items->push_back(item);
+// host-side description of one step (same for every row pair; ring offset and dep are filled per CTA-pair stream)
+struct Tc2HostStep {
+  int kc = 0, nA = 0, nB = 0, n_ops = 0;
+  int a_pix[TC2_MAX_A] = {0, 0, 0, 0};
+  uint8_t b_ent[2][TC2_MAX_BSLOTS] = {{0}, {0}};
+  uint16_t ops[TC2_MAX_OPS] = {0};
+  int n_tile_mmas = 0;         // un-merged count (statistics)
+  int bytes = 0;               // operand bytes staged per CTA
+};
+struct Tc2HostItem {
+  TcItem2 hdr{};
+  std::vector<Tc2HostStep> steps;
+  double stage_bytes = 0.0;
+};
+
+// Steps of one window (accumulator a <-> output pixel qs[a]).  Input pixels are taken in ascending order and packed
+// greedily into steps of <= max_a A tiles (max_a = 1: one input pixel per step); a weight tile needed by several
+// pixels of a step is staged once.  Within a pixel, runs of consecutive accumulators whose tiles nobody else in
+// the step uses (and whose first-MMA flags agree) become one merged-N MMA.
+static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int N, int K, int max_g, int max_a,
+                           int step_max_bytes, Tc2HostItem* out) {
+  const int kch = K / 64, half_b = (N / 2) * 128;
+  out->hdr = TcItem2{};
+  out->hdr.n_acc = (uint32_t)qs.size();
+  for (size_t a = 0; a < qs.size(); ++a) out->hdr.q[a] = (uint16_t)qs[a];
+  out->steps.clear();
+  std::vector<std::pair<int, std::vector<std::pair<int, int>>>> by_p;   // pixel -> (tile, acc), sorted by acc
+  for (size_t a = 0; a < qs.size(); ++a)
+    for (int e = tab.off[qs[a]]; e < tab.off[qs[a] + 1]; ++e) {
+      const int p = tab.pairs[e].x, t = tab.pairs[e].y;
+      size_t g = 0;
+      for (; g < by_p.size(); ++g)
+        if (by_p[g].first == p) break;
+      if (g == by_p.size()) by_p.push_back({p, {}});
+      by_p[g].second.push_back({t, (int)a});
     }
+  std::sort(by_p.begin(), by_p.end(), [](const auto& l, const auto& r) { return l.first < r.first; });
+  for (auto& g : by_p)
+    std::stable_sort(g.second.begin(), g.second.end(), [](const auto& l, const auto& r) { return l.second < r.second; });
+  // a pixel with more entries than one step can hold is split (Linear layers: 16 tiles per input "pixel")
+  std::vector<std::pair<int, std::vector<std::pair<int, int>>>> px;
+  const int ent_cap = std::min({TC2_MAX_BSLOTS, TC2_MAX_OPS, std::max(1, (step_max_bytes - TC_A_BYTES) / half_b)});
+  for (auto& g : by_p)
+    for (size_t b0 = 0; b0 < g.second.size(); b0 += (size_t)ent_cap)
+      px.push_back({g.first, std::vector<std::pair<int, int>>(g.second.begin() + b0,
+                                                               g.second.begin() + std::min(g.second.size(), b0 + (size_t)ent_cap))});
+  uint32_t seen = 0;
+  size_t i0 = 0;
+  while (i0 < px.size()) {
+    // ---- greedy group [i0, i1)
+    size_t i1 = i0;
+    std::vector<int> tiles;
+    int n_ent = 0;
+    while (i1 < px.size() && (int)(i1 - i0) < max_a) {
+      int fresh = 0;
+      for (auto& ta : px[i1].second)
+        if (std::find(tiles.begin(), tiles.end(), ta.first) == tiles.end()) ++fresh;
+      const int nA = (int)(i1 - i0) + 1, nB = (int)tiles.size() + fresh;
+      const bool dup_pixel = (i1 > i0 && px[i1].first == px[i1 - 1].first);   // split halves of one pixel stay apart
+      if (i1 > i0 && (dup_pixel || nB > TC2_MAX_BSLOTS || n_ent + (int)px[i1].second.size() > TC2_MAX_OPS ||
+                      nA * TC_A_BYTES + nB * half_b > step_max_bytes))
+        break;
+      for (auto& ta : px[i1].second)
+        if (std::find(tiles.begin(), tiles.end(), ta.first) == tiles.end()) tiles.push_back(ta.first);
+      n_ent += (int)px[i1].second.size();
+      ++i1;
+    }
+    // ---- ops + B slots of the group
+    std::vector<int> use(32, 0);
+    for (size_t i = i0; i < i1; ++i)
+      for (auto& ta : px[i].second) ++use[ta.first];
+    Tc2HostStep st;
+    st.nA = (int)(i1 - i0);
+    int slot_of[32];
+    for (int t = 0; t < 32; ++t) slot_of[t] = -1;
+    for (size_t i = i0; i < i1; ++i) {
+      st.a_pix[i - i0] = px[i].first;
+      const auto& ent = px[i].second;
+      for (size_t e = 0; e < ent.size();) {
+        const int acc0 = ent[e].second;
+        const bool f0 = !(seen & (1u << acc0));
+        size_t g = 1;
+        if (use[ent[e].first] == 1)
+          while ((int)g < max_g && e + g < ent.size() && ent[e + g].second == acc0 + (int)g && use[ent[e + g].first] == 1 &&
+                 (!(seen & (1u << ent[e + g].second))) == f0)
+            ++g;
+        int slot;
+        if (use[ent[e].first] == 1) {
+          slot = st.nB;
+          for (int r = 0; r < 2; ++r)
+            for (size_t jj = 0; jj < g; ++jj) {
+              const size_t x = (size_t)r * g + jj;              // half-tile index in W_0.lo, W_0.hi, W_1.lo, ...
+              st.b_ent[r][slot + jj] = (uint8_t)((ent[e + x / 2].first & 0x1F) | ((x & 1) << 5));
+            }
+          st.nB += (int)g;
+        } else if (slot_of[ent[e].first] >= 0) {
+          slot = slot_of[ent[e].first];
+        } else {
+          slot = slot_of[ent[e].first] = st.nB;
+          for (int r = 0; r < 2; ++r) st.b_ent[r][slot] = (uint8_t)((ent[e].first & 0x1F) | (r << 5));
+          st.nB += 1;
+        }
+        st.ops[st.n_ops++] = (uint16_t)((i - i0) | (slot << 2) | ((g - 1) << 5) | (acc0 << 7) | ((f0 ? 1 : 0) << 10));
+        st.n_tile_mmas += (int)g;
+        for (size_t jj = 0; jj < g; ++jj) seen |= 1u << ent[e + jj].second;
+        e += g;
+      }
+    }
+    st.bytes = st.nA * TC_A_BYTES + st.nB * half_b;
+    out->steps.push_back(st);
+    i0 = i1;
+  }
+  // k-chunk outermost: every accumulator then sums its (k-chunk, input pixel) contributions in one canonical order
+  // - ascending k-chunk, ascending pixel - whatever the window shape and step grouping, so results do not depend
+  // on the batch size (the schedule does) and a sharded batch reproduces the unsharded one bit for bit.
+  const size_t n_groups = out->steps.size();
+  for (int kc = 1; kc < kch; ++kc)
+    for (size_t gi = 0; gi < n_groups; ++gi) {
+      Tc2HostStep sk = out->steps[gi];
+      sk.kc = kc;
+      for (int o = 0; o < sk.n_ops; ++o) sk.ops[o] &= (uint16_t)~(1u << 10);
+      out->steps.push_back(sk);
+    }
+  out->stage_bytes = 0.0;
+  for (auto& stp : out->steps) out->stage_bytes += stp.bytes;
+}
+
+// Windows of wh x ww accumulators with strides (sy, sx) over the output grid.  Stride 2 gathers outputs of equal
+// parity of a stride-2 transposed conv: they use the same taps with neighbouring inputs, so weight tiles are shared.
+static void tc2_enumerate_windows(int h_grid, int w_grid, int wh, int ww, int sy, int sx, std::vector<std::vector<int>>* wins) {
+  wins->clear();
+  for (int by = 0; by < h_grid; by += wh * sy)
+    for (int bx = 0; bx < w_grid; bx += ww * sx)
+      for (int ry = 0; ry < sy; ++ry)
+        for (int rx = 0; rx < sx; ++rx) {
+          std::vector<int> qs;
+          for (int i = 0; i < wh; ++i)
+            for (int j = 0; j < ww; ++j) {
+              const int y = by + ry + i * sy, x = bx + rx + j * sx;
+              if (y < h_grid && x < w_grid) qs.push_back(y * w_grid + x);
+            }
+          if (!qs.empty()) wins->push_back(qs);
+        }
 }
 
 static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2, const PairTable& tab, int h_grid,
@@ -578,115 +709,122 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
   return tc_make_map(st, &w2->tm_b, w1.w, (uint64_t)K, (uint64_t)N, (uint64_t)w1.n_tiles, (uint32_t)(N / 2));
 }
 
-// Pick (and build on first use) the window tiling for `n_mpairs` row pairs on `n_pairs` CTA pairs:
-// candidates are all wh x ww shapes that fit the accumulator buffer; each is scored by simulating
-// the static round-robin assignment with a per-item cost = bytes staged (A + half-B tiles) + a fixed
-// per-accumulator epilogue charge, and the smallest makespan wins (fits the item count to the machine:
-// e.g. 160 equal items on 74 pairs run 3 waves, 280 smaller ones 3.8).
-static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int n_pairs,
-                            std::vector<void*>* allocs, cudaStream_t s, const Tc2Schedule** out) {
-  for (auto& kv : w2.by_mpairs)
-    if (kv.first == n_mpairs) { *out = &kv.second; return 0; }
-  const int N = w1.N, K = w1.K;
-  const double half_b = (double)(N / 2) * 128.0, a_bytes = (double)TC_A_BYTES;
-  double best_cost = 1e300;
-  int best_wh = 1, best_ww = 1;
-  std::vector<TcItem2> best_items;
-  std::vector<TcStep2> best_steps;
-  std::vector<std::vector<int>> best_lists;
-  for (int wh = 1; wh <= 2; ++wh)
-    for (int ww = 1; ww <= 8; ++ww) {
-      if (wh * ww > w2.max_acc || wh > w2.h_grid || ww > std::max(w2.w_grid, 1)) continue;
-      std::vector<TcItem2> items;
-      std::vector<TcStep2> steps;
-      tc2_build_schedule(w2.tab, w2.h_grid, w2.w_grid, N, K, wh, ww, &items, &steps);
-      std::stable_sort(items.begin(), items.end(), [](const TcItem2& l, const TcItem2& r) { return l.n_steps > r.n_steps; });
-      std::vector<double> icost(items.size());
-      for (size_t i = 0; i < items.size(); ++i) {
-        double c = 0.0;
-        for (uint32_t k = 0; k < items[i].n_steps; ++k) {
-          const int nb = (steps[items[i].step_beg + k].w0 >> 24) & 0xFF;
-          c += a_bytes + nb * half_b;
-        }
 #ifndef DGAN_COST_EPI_KB
 #define DGAN_COST_EPI_KB 24.0
 #endif
 #ifndef DGAN_COST_FIXED_KB
 #define DGAN_COST_FIXED_KB 48.0
 #endif
-        icost[i] = c + DGAN_COST_EPI_KB * 1024.0 * items[i].n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;   // epilogue + per-item fixed
-      }
-      // LPT: items (window, mp) largest-first, each to the currently least-loaded CTA pair
-      const long long total = (long long)items.size() * n_mpairs;
-      std::vector<double> load((size_t)n_pairs, 0.0);
-      std::vector<std::vector<int>> lists((size_t)n_pairs);
-      for (long long idx = 0; idx < total; ++idx) {        // items[] is sorted by cost, mp is the fast index: cost-descending
-        size_t best = 0;
-        for (size_t pr = 1; pr < (size_t)n_pairs; ++pr)
-          if (load[pr] < load[best]) best = pr;
-        load[best] += icost[(size_t)(idx / n_mpairs)];
-        lists[best].push_back((int)idx);
-      }
-      const double makespan = *std::max_element(load.begin(), load.end());
-      if (makespan < best_cost) {
-        best_cost = makespan; best_wh = wh; best_ww = ww; best_items.swap(items); best_steps.swap(steps); best_lists.swap(lists);
-      }
-    }
+
+// Pick (and build on first use) the window tiling for `n_mpairs` row pairs on `n_pairs` CTA pairs: every candidate
+// shape (wh x ww accumulators, strides 1 or 2) is scored by an LPT assignment of its items (window, row pair) to the
+// CTA pairs with cost = operand bytes staged + a per-accumulator epilogue charge + a fixed per-item charge;
+// the smallest makespan wins.  Then each pair's items are concatenated into its step streams, the circular operand
+// ring is simulated to give every step its offset and its dependency distance, and everything is uploaded.
+static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int n_pairs, int ring_bytes,
+                            std::vector<void*>* allocs, cudaStream_t s, const Tc2Schedule** out) {
+  for (auto& kv : w2.by_mpairs)
+    if (kv.first == n_mpairs) { *out = &kv.second; return 0; }
+  const int N = w1.N, K = w1.K;
+  const bool merge = (N >= 64) && !(getenv("DGAN_MERGE_N") && atoi(getenv("DGAN_MERGE_N")) == 0);
+  const int max_g = merge ? std::min(4, 256 / N) : 1;
+  const int max_a = getenv("DGAN_MULTI_A") ? std::max(1, std::min(TC2_MAX_A, atoi(getenv("DGAN_MULTI_A")))) : TC2_MAX_A;
+  // Step size: a step is consumed only once all of it has landed, so big steps cost pipeline depth (4 x 48 KB fit the
+  // ring); measured on C2: 32 KB (= one A tile per step) 5359, 40 KB 5466, 48-56 KB 5660, 64 KB 5553, 96 KB 5385 images/s.
+  int step_max = std::min((ring_bytes / 2) & ~1023, 48 * 1024);
+  if (getenv("DGAN_STEP_MAX_KB")) step_max = std::min((ring_bytes / 2) & ~1023, std::max(32, atoi(getenv("DGAN_STEP_MAX_KB"))) * 1024);
+  double best_cost = 1e300;
+  int best_shape[4] = {1, 1, 1, 1};
+  std::vector<Tc2HostItem> best_items;
+  std::vector<std::vector<int>> best_lists;
+  std::vector<std::vector<int>> wins;
+  for (int wh = 1; wh <= 2; ++wh)
+    for (int ww = 1; ww <= 8; ++ww)
+      for (int sy = 1; sy <= (wh > 1 ? 2 : 1); ++sy)
+        for (int sx = 1; sx <= (ww > 1 ? 2 : 1); ++sx) {
+          if (wh * ww > w2.max_acc || wh > w2.h_grid || ww > std::max(w2.w_grid, 1)) continue;
+          if ((sy > 1 || sx > 1) && max_a == 1) continue;
+          tc2_enumerate_windows(w2.h_grid, std::max(w2.w_grid, 1), wh, ww, sy, sx, &wins);
+          std::vector<Tc2HostItem> items(wins.size());
+          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(w2.tab, wins[i], N, K, max_g, max_a, step_max, &items[i]);
+          std::stable_sort(items.begin(), items.end(), [](const Tc2HostItem& l, const Tc2HostItem& r) { return l.stage_bytes > r.stage_bytes; });
+          std::vector<double> icost(items.size());
+          for (size_t i = 0; i < items.size(); ++i)
+            icost[i] = items[i].stage_bytes + DGAN_COST_EPI_KB * 1024.0 * items[i].hdr.n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;
+          // LPT: items (window, mp) largest-first, each to the currently least-loaded CTA pair
+          const long long total = (long long)items.size() * n_mpairs;
+          std::vector<double> load((size_t)n_pairs, 0.0);
+          std::vector<std::vector<int>> lists((size_t)n_pairs);
+          for (long long idx = 0; idx < total; ++idx) {        // items[] is sorted by cost, mp is the fast index: cost-descending
+            size_t best = 0;
+            for (size_t pr = 1; pr < (size_t)n_pairs; ++pr)
+              if (load[pr] < load[best]) best = pr;
+            load[best] += icost[(size_t)(idx / n_mpairs)];
+            lists[best].push_back((int)idx);
+          }
+          const double makespan = *std::max_element(load.begin(), load.end());
+          if (makespan < best_cost) {
+            best_cost = makespan;
+            best_shape[0] = wh; best_shape[1] = ww; best_shape[2] = sy; best_shape[3] = sx;
+            best_items.swap(items); best_lists.swap(lists);
+          }
+        }
   Tc2Schedule sc;
-  sc.wh = best_wh; sc.ww = best_ww; sc.n_windows = (int)best_items.size(); sc.n_pairs = n_pairs;
+  sc.wh = best_shape[0]; sc.ww = best_shape[1]; sc.sy = best_shape[2]; sc.sx = best_shape[3];
+  sc.n_windows = (int)best_items.size(); sc.n_pairs = n_pairs;
   size_t n_slots = 0;
   for (auto& l : best_lists) n_slots = std::max(n_slots, l.size());
   sc.n_slots = (int)n_slots;
   std::vector<int> eitems(n_slots * (size_t)n_pairs, -1);
   std::vector<uint32_t> stream_off((size_t)n_pairs + 1, 0);
   std::vector<TcRec> stream_p[2], stream_m;
-  const bool merge = (N >= 64) && !(getenv("DGAN_MERGE_N") && atoi(getenv("DGAN_MERGE_N")) == 0);
-  const int max_g = merge ? std::min(4, 256 / N) : 1;
-  long long n_mma = 0, n_single = 0;
+  long long n_mma = 0, n_single = 0, n_steps = 0, n_bytes = 0;
   for (size_t pr = 0; pr < best_lists.size(); ++pr) {
     stream_off[pr] = (uint32_t)stream_m.size();
+    // circular operand ring of this CTA pair: sequential allocation, wrap when the step does not fit
+    std::vector<std::pair<int, int>> region;     // [begin, end) in KB of every step of this stream
+    int cursor = 0;
     for (size_t k = 0; k < best_lists[pr].size(); ++k) {
       const int win = best_lists[pr][k] / n_mpairs, mp = best_lists[pr][k] % n_mpairs;
       if (win > 0x7FFF || mp > 0xFFFF) { set_error("tensor-core schedule limits exceeded"); return DGAN_ERR_UNSUPPORTED; }
       eitems[k * (size_t)n_pairs + pr] = (win << 16) | mp;
-      const TcItem2& itm = best_items[(size_t)win];
-      for (uint32_t j = 0; j < itm.n_steps; ++j) {
-        const TcStep2& st2 = best_steps[itm.step_beg + j];
-        const int nb = (int)((st2.w0 >> 24) & 0xFF);
-        const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.n_steps ? 2u : 0u);
-        TcRec rp[2] = {}, rm{};
-        // slots are sorted by accumulator: runs of consecutive accumulators with equal first-MMA flags form one group
-        int n_groups = 0;
-        uint32_t gfirsts = 0;
-        for (int b = 0; b < nb;) {
-          const int acc0 = (st2.tb[b] >> 8) & 0x7;
-          const uint32_t f0 = (st2.w1 >> b) & 1u;
-          int g = 1;
-          while (g < max_g && b + g < nb && (int)((st2.tb[b + g] >> 8) & 0x7) == acc0 + g && ((st2.w1 >> (b + g)) & 1u) == f0) ++g;
-          for (int r = 0; r < 2; ++r)
-            for (int jj = 0; jj < g; ++jj) {
-              const int x = r * g + jj;                     // half-tile index in W_0.lo, W_0.hi, W_1.lo, ...
-              rp[r].tb[b + jj] = (uint8_t)((st2.tb[b + x / 2] & 0x1F) | ((x & 1) << 5));
-            }
-          rm.tb[n_groups] = (uint8_t)(b | ((g - 1) << 3) | (acc0 << 5));
-          gfirsts |= f0 << n_groups;
-          ++n_groups; b += g;
-          n_mma += 1; n_single += g;
+      const Tc2HostItem& itm = best_items[(size_t)win];
+      for (size_t j = 0; j < itm.steps.size(); ++j) {
+        const Tc2HostStep& hs = itm.steps[j];
+        const int kb = (hs.bytes + 1023) / 1024;
+        if (kb * 1024 > ring_bytes) { set_error("tensor-core step larger than the operand ring"); return DGAN_ERR_UNSUPPORTED; }
+        if (cursor + kb > ring_bytes / 1024) cursor = 0;
+        const int beg = cursor, end = cursor + kb;
+        cursor = end;
+        int dep = TC2_NSLOT;                        // barrier-slot reuse
+        const int kidx = (int)region.size();
+        for (int d = 1; d < TC2_NSLOT && d <= kidx; ++d) {
+          const auto& rg = region[(size_t)(kidx - d)];
+          if (rg.first < end && beg < rg.second) { dep = d; break; }   // latest overlapping step
         }
-        for (int r = 0; r < 2; ++r) {
-          rp[r].w0 = st2.w0;
-          rp[r].w1 = (flags << 8) | ((uint32_t)mp << 16);
-          stream_p[r].push_back(rp[r]);
-        }
-        rm.w0 = (st2.w0 & 0x00FFFFFFu) | ((uint32_t)n_groups << 24);
-        rm.w1 = gfirsts | (flags << 8) | ((uint32_t)mp << 16);
+        region.push_back({beg, end});
+        const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
+        TcRec rm{};
+        rm.w[0] = (uint32_t)beg | ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16);
+        for (int o = 0; o < hs.n_ops; ++o) rm.w[2 + o / 2] |= (uint32_t)hs.ops[o] << (16 * (o & 1));
         stream_m.push_back(rm);
+        for (int r = 0; r < 2; ++r) {
+          TcRec rp{};
+          rp.w[0] = (uint32_t)beg | ((uint32_t)hs.kc << 8) | ((uint32_t)hs.nA << 12) | ((uint32_t)hs.nB << 15) | ((uint32_t)dep << 19);
+          rp.w[1] = (uint32_t)mp;
+          for (int a = 0; a < hs.nA; ++a) rp.w[2 + a / 2] |= (uint32_t)(hs.a_pix[a] & 0xFFFF) << (16 * (a & 1));
+          for (int b = 0; b < hs.nB; ++b) rp.w[4 + b / 4] |= (uint32_t)hs.b_ent[r][b] << (8 * (b & 3));
+          stream_p[r].push_back(rp);
+        }
+        n_mma += hs.n_ops; n_single += hs.n_tile_mmas; n_steps += 1; n_bytes += hs.bytes;
       }
     }
   }
   stream_off[(size_t)n_pairs] = (uint32_t)stream_m.size();
+  std::vector<TcItem2> hdrs(best_items.size());
+  for (size_t i = 0; i < best_items.size(); ++i) hdrs[i] = best_items[i].hdr;
   int rc;
-  if ((rc = tc_upload(allocs, best_items.data(), best_items.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
+  if ((rc = tc_upload(allocs, hdrs.data(), hdrs.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
   for (int r = 0; r < 2; ++r)
     if ((rc = tc_upload(allocs, stream_p[r].data(), stream_p[r].size() * sizeof(TcRec), (void**)&sc.stream_p[r], s))) return rc;
   if ((rc = tc_upload(allocs, stream_m.data(), stream_m.size() * sizeof(TcRec), (void**)&sc.stream_m, s))) return rc;
@@ -695,8 +833,9 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   w2.by_mpairs.push_back({n_mpairs, sc});
   *out = &w2.by_mpairs.back().second;
   if (getenv("DGAN_TC_VERBOSE"))
-    fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d, %d windows, %lld tile-MMAs in %lld merged\n", N, K,
-            w2.h_grid, w2.w_grid, n_mpairs, best_wh, best_ww, (*out)->n_windows, n_single, n_mma);
+    fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d stride %dx%d, %d windows, %lld steps, %.1f MB staged/CTA-set, "
+                    "%lld tile-MMAs in %lld merged\n", N, K, w2.h_grid, w2.w_grid, n_mpairs, sc.wh, sc.ww, sc.sy, sc.sx, sc.n_windows, n_steps,
+            2.0 * n_bytes / 1e6, n_single, n_mma);
   return 0;
 }
 
@@ -742,7 +881,8 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   const int n_mpairs = n_pad / (2 * kRowTile);
   const Tc2Schedule* schp = nullptr;
   const int pairs_avail = st.max_pairs > 0 ? std::min(st.max_pairs, st.num_sms / 2) : st.num_sms / 2;
-  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, pairs_avail, st.allocs, s, &schp))) return rc;
+  const int ring_bytes = tc2_ring_bytes(w.N, epi, (int)sizeof(TOUT));
+  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, pairs_avail, ring_bytes, st.allocs, s, &schp))) return rc;
   const Tc2Schedule& w2s = *schp;
   const int total = w2s.n_windows * n_mpairs;
   const int grid = 2 * w2s.n_pairs;       // pairs without work find -1 in slot 0 and fall through
