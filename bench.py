@@ -349,13 +349,13 @@ def _main(out):
         if args.precision == "fp32":
             peak = None
         traffic = None   # DRAM read+write bytes per launch of that kernel from the committed ncu --set full capture
-        tp = os.path.join(ROOT, "profiles", "r1b_dram_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r1d_dram_traffic.json")
         if os.path.exists(tp) and args.precision == "fp16" and dataset == "mnist" and B * R == 2560:
             with open(tp) as f:
                 traffic = json.load(f)["kernels"].get(dom["kernel"], {}).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak,
                     "unit": "TFLOP/s", "frac": (dom["tflops"] / peak) if peak else None, "traffic": traffic,
-                    "traffic_unit": "bytes/launch (dram__bytes_read+write, profiles/r1b_dram_traffic.json)",
+                    "traffic_unit": "bytes/launch (dram__bytes_read+write, profiles/r1d_dram_traffic.json)",
                     "peak_source": "%s cuBLAS bf16 burst (MEASURED_PEAKS.json)" % peaks["_source"],
                     "operand_format": args.precision}
 
