@@ -6,13 +6,14 @@
 //   * each CTA stages its own 128-row activation tile A and only HALF of each weight tile
 //     (N/2 rows) - the tensor cores read the other half from the peer's shared memory, so
 //     weight traffic per SM is halved;
-//   * one CTA per SM owns all 512 TMEM columns, so a window holds up to 8 accumulators
-//     (2x4 output pixels at N = 64): every staged A tile feeds more MMAs;
-//   * stages are sized per instantiation (A + MAXB half-tiles), 4-8 stages deep.
-// Roles per CTA as in version 1 (TMA producer / MMA issuer / 4 epilogue warps); only the even
-// (leader) CTA issues tcgen05.mma.cta_group::2, commits are multicast to both CTAs, TMA
-// completions of both CTAs land on the leader's "full" barrier (peer-bit mask), and the
-// epilogue warps of both CTAs release the accumulators on the leader's "acc_empty" barrier.
+//   * one CTA per SM owns all 512 TMEM columns: two buffers of 256 (the MMAs of item i+1 overlap the
+//     epilogue of item i), each holding the 1-8 accumulators of a window of output pixels;
+//   * operands live in a circular shared-memory ring of variable-size steps planned on the host
+//     (tc2_get_schedule): per CTA pair one contiguous stream of step records, LPT-assigned.
+// Roles per CTA: TMA producer warp / MMA issuer warp / 8 epilogue warps; only the even (leader) CTA
+// issues tcgen05.mma.cta_group::2, commits are multicast to both CTAs, TMA completions of both CTAs
+// land on the leader's "full" barrier (peer-bit mask), and the epilogue warps of both CTAs release
+// the accumulators on the leader's "acc_empty" barrier.
 #pragma once
 #include "kernels_tc.cuh"
 
@@ -24,12 +25,6 @@ constexpr int TC2_BUF_COLS = 256;            // TMEM columns per accumulator buf
 constexpr int TC2_EPI_WARPS = 8;             // two epilogue warps per TMEM lane quarter
 constexpr int TC2_THREADS = 64 + 32 * TC2_EPI_WARPS;
 
-struct __align__(16) TcStep2 {
-  uint32_t w0;       // in pixel [0,16) | k-chunk [16,24) | n_b [24,32)
-  uint32_t w1;       // bit b: first MMA into that accumulator
-  uint32_t pad[2];
-  uint16_t tb[8];    // weight tile id [0,8) | accumulator index [8,16)
-};
 struct __align__(16) TcItem2 {
   uint16_t q[16];
   uint32_t n_acc, step_beg, n_steps, pad;
@@ -73,8 +68,20 @@ constexpr int TC2_MAX_A = 4, TC2_MAX_BSLOTS = 8, TC2_MAX_OPS = 12, TC2_NSLOT = 8
 constexpr int TC2_REC_BATCH = 16;
 constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // producer + MMA warp rings
 
+// Output staging tiles per CTA: one per epilogue half, or two per half (the next tile is written while the TMA
+// store of the previous one still reads shared memory) for the kernels whose epilogue is the critical path:
+// Linear forward (N = 256: 4 tiles per item, 2-3 items per CTA pair) and the last layer's backward.
+#ifndef DGAN_EPI_DB
+#define DGAN_EPI_DB 0
+#endif
+__host__ __device__ constexpr int tc2_epi_tiles(int n_tile, int epi, int out_bytes) {
+  if (!tc2_tma_epilogue(n_tile, epi, out_bytes)) return 0;
+  if (DGAN_EPI_DB == 2) return 4;
+  if (DGAN_EPI_DB == 1 && ((n_tile == 256 && epi == EPI_BIAS_RELU) || (n_tile == 64 && epi == EPI_MASK))) return 4;
+  return 2;
+}
 __host__ __device__ constexpr int tc2_ring_bytes(int n_tile, int epi, int out_bytes) {
-  const int epi_b = tc2_tma_epilogue(n_tile, epi, out_bytes) ? 2 * TC2_TILE_BYTES : 0;
+  const int epi_b = tc2_epi_tiles(n_tile, epi, out_bytes) * TC2_TILE_BYTES;
   const int raw = ((TC2_SMEM_MAX - 1024 - 256 - TC2_STAGING_BYTES - epi_b) / 1024) * 1024;
   return raw > 255 * 1024 ? 255 * 1024 : raw;
 }
@@ -85,8 +92,8 @@ struct Tc2Cfg {
   static constexpr int ACC_STRIDE = tc2_acc_stride(N_TILE);
   static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (8 / 4 / 2 / 1)
   static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
-  // epilogue staging: one output tile per epilogue half
-  static constexpr int EPI_BYTES = TMA_EPI ? 2 * TC2_TILE_BYTES : 0;
+  static constexpr int EPI_TILES = tc2_epi_tiles(N_TILE, EPI, OUT_BYTES);   // output staging tiles (2 or 4)
+  static constexpr int EPI_BYTES = EPI_TILES * TC2_TILE_BYTES;
   static constexpr int RING_BYTES = tc2_ring_bytes(N_TILE, EPI, OUT_BYTES);          // operand ring (offsets are 8-bit KB)
   static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256;
 };
@@ -133,6 +140,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
@@ -372,7 +380,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int lq = warp & 3;                          // TMEM lanes this warp may access
     const int half = (warp - 2) >> 2;                 // 0 | 1: which of the two warps of this quarter
     const int row = lq * 32 + lane;
-    uint32_t item_count = 0;
+    uint32_t item_count = 0, unit_count = 0;
     long long t_ewait = 0, t_ework = 0;
     const long long t_start = fa.dbg ? clock64() : 0;
     unsigned long long gt_start = 0;
@@ -413,7 +421,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         //      128B-swizzled smem tile -> one TMA store per 128x64 tile; mask tiles arrive by TMA load.
         constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
         const int n_units = n_acc * G;
-        const uint32_t s_out = epi_base + half * TC2_TILE_BYTES;
+        constexpr int TPH = Cfg::EPI_TILES >= 2 ? Cfg::EPI_TILES / 2 : 1;   // staging tiles per epilogue half
         const bool t0 = (warp == 2 + 4 * half) && lane == 0;  // issues this half's bulk copies
         const int row0 = (2 * mp + (int)rank) * kRowTile;
         const uint32_t swz = (uint32_t)(row & 7);
@@ -466,7 +474,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64), r0);
             ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64 + 32), r1);
           }
-          if (t0) ptx::bulk_wait_read0();                  // the previous store has finished reading s_out
+          const uint32_t s_out = epi_base + (uint32_t)(half * TPH + (int)(unit_count & (TPH - 1))) * TC2_TILE_BYTES;
+          ++unit_count;
+          if (t0) { if (TPH == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0(); }   // the store that last read s_out is done
           ptx::named_bar_sync(1 + half, 128);              // s_out free
 #pragma unroll
           for (int c = 0; c < 8; ++c)
