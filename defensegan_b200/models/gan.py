@@ -26,6 +26,7 @@ import numpy as np
 import torch
 
 from .. import _native
+from .. import tf_bundle as _tf_bundle
 from .. import weights as _weights
 from ..utils.config import load_config, packaged_cfg_path
 
@@ -133,23 +134,46 @@ class DefenseGANBase(object):
 
     def load_generator(self, ckpt_path=None):
         """Restore the generator (reference models/gan.py:80-87 -> base_model.py:294-335).
-        `ckpt_path` is a directory holding `generator.npz` or the file itself; default is the
-        model's checkpoint dir.  Returns False (and keeps the random-init weights, like the
-        reference's failed restore, base_model.py:312-317) when nothing is found."""
+        `ckpt_path` is the model's checkpoint dir (default), a `generator.npz`, or a TF checkpoint prefix
+        (`.../GAN.model-20000`).  A directory is searched for `generator.npz` first, then for the latest
+        TensorFlow checkpoint-V2 bundle (`checkpoint` state file / `*.index`), which is read without
+        TensorFlow by `defensegan_b200.tf_bundle` - only the `Generator*` variables, as the reference does.
+        Returns False (and keeps the random-init weights, like the reference's failed restore,
+        base_model.py:312-317) when nothing is found."""
         path = ckpt_path if ckpt_path is not None else self.checkpoint_dir
+        npz, prefix = None, None
         if os.path.isdir(path):
-            path = os.path.join(path, "generator.npz")
-        if not os.path.isfile(path):
+            if os.path.isfile(os.path.join(path, "generator.npz")):
+                npz = os.path.join(path, "generator.npz")
+            else:
+                prefix = _tf_bundle.latest_checkpoint(path)
+        elif os.path.isfile(path):
+            npz = path
+        elif os.path.isfile(path + ".index"):
+            prefix = path
+        if npz is not None:
+            self.set_generator_weights(_weights.load_npz(npz))
+        elif prefix is not None:
+            self.set_generator_weights(_tf_bundle.read_generator_variables(prefix))
+        else:
             if self.verbose:
                 print("[-] No generator checkpoint found at {}; keeping random-init weights".format(path))
             return False
-        self.set_generator_weights(_weights.load_npz(path))
         if self.verbose:
-            print("[*] Generator restored from {}".format(path))
+            print("[*] Generator restored from {}".format(npz or prefix))
         return True
 
-    def save_generator(self, ckpt_path=None):
+    def save_generator(self, ckpt_path=None, fmt="npz", global_step=0):
+        """`fmt="npz"`: `generator.npz`; `fmt="tf"`: a TensorFlow checkpoint-V2 bundle `GAN.model-<step>` plus the
+        `checkpoint` state file, the layout of the reference's saver (base_model.py:383-395)."""
         path = ckpt_path if ckpt_path is not None else self.checkpoint_dir
+        if fmt == "tf":
+            os.makedirs(path, exist_ok=True)
+            name = "GAN.model-%d" % int(global_step)
+            _tf_bundle.write_bundle(os.path.join(path, name), dict(self.weights))
+            with open(os.path.join(path, "checkpoint"), "w") as f:
+                f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (name, name))
+            return os.path.join(path, name)
         if not path.endswith(".npz"):
             os.makedirs(path, exist_ok=True)
             path = os.path.join(path, "generator.npz")

@@ -244,3 +244,117 @@ def test_reconstruct_dataset_cache_format(tmp_path, monkeypatch):
     gan.reconstruct_dataset()
     assert calls == [2, 2, 1, 2, 1, 2, 2]
     assert gan.rec_cache_dir("dev", max_num=100).endswith(os.path.join("recs_rr2_lr0.50000_iters3_num100", "dev"))
+
+
+# ---------------------------------------------------------------------------------------------------
+# f2: TensorFlow checkpoint-V2 bundle reader (no TensorFlow needed)
+# ---------------------------------------------------------------------------------------------------
+def _bundle_tensors():
+    rs = np.random.RandomState(5)
+    t = {"Generator.Input/Generator.Input.W": rs.randn(8, 32).astype("float32"),
+         "Generator.Input/Generator.Input.b": rs.randn(32).astype("float32"),
+         "Generator.2/Generator.2.Filters": rs.randn(5, 5, 4, 8).astype("float32"),
+         "Generator.2/Generator.2.Filters/Adam": rs.randn(5, 5, 4, 8).astype("float32"),
+         "Generator.2/Generator.2.Filters/Adam_1": rs.randn(5, 5, 4, 8).astype("float32"),
+         "Discriminator.1/Discriminator.1.Filters": rs.randn(5, 5, 1, 4).astype("float32"),
+         "global_step": np.asarray(20000, dtype="int64"),
+         "beta1_power": np.asarray(0.5, dtype="float32")}
+    for i in range(40):   # many similar names: exercises prefix compression and restart points
+        t["Discriminator.%02d/Discriminator.%02d.Biases" % (i, i)] = rs.randn(3 + i).astype("float32")
+    return t
+
+
+def test_tf_bundle_roundtrip_prefix_compression_and_blocks(tmp_path):
+    from defensegan_b200 import tf_bundle as B
+    t = _bundle_tensors()
+    for block_size in (262144, 64):          # one data block / many data blocks + a multi-entry index block
+        prefix = str(tmp_path / ("bs%d" % block_size) / "GAN.model-20000")
+        B.write_bundle(prefix, t, block_size=block_size)
+        listed = B.list_bundle(prefix)
+        assert list(listed) == sorted(t, key=lambda s: s.encode()) and listed["global_step"] == (np.dtype("<i8"), ())
+        back = B.read_bundle(prefix)
+        assert set(back) == set(t)
+        for k in t:
+            assert back[k].dtype == t[k].dtype and back[k].shape == t[k].shape and np.array_equal(back[k], t[k])
+        gen = B.read_generator_variables(prefix)
+        assert sorted(gen) == ["Generator.2/Generator.2.Filters", "Generator.Input/Generator.Input.W",
+                               "Generator.Input/Generator.Input.b"]
+        with pytest.raises(KeyError):
+            B.read_bundle(prefix, ["nope"])
+
+
+def test_tf_bundle_matches_independent_crc_and_proto_implementations():
+    """CRC-32C, its masking and the TensorShapeProto wire format against TensorBoard's own implementations
+    (the only TensorFlow-lineage code in this image)."""
+    from defensegan_b200 import tf_bundle as B
+    assert B.crc32c(b"123456789") == 0xE3069283            # CRC-32C check value (RFC 3720)
+    assert B.crc32c(b"\x00" * 32) == 0x8A9136AA and B.crc32c(b"\xff" * 32) == 0x62A8AB43
+    assert B.unmask_crc(B.mask_crc(0xDEADBEEF)) == 0xDEADBEEF
+    tb = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    rs = np.random.RandomState(0)
+    for n in (0, 1, 7, 4096, 10001):
+        blob = rs.bytes(n)
+        assert B.crc32c(blob) == tb.crc32c(blob)
+        assert B.mask_crc(B.crc32c(blob)) == tb.masked_crc32c(blob)
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    for shape in ((), (7,), (5, 5, 128, 256), (1, 0, 300)):
+        msg = shape_pb2.TensorShapeProto()
+        for d in shape:
+            msg.dim.add().size = d
+        assert B.encode_tensor_shape(shape) == msg.SerializeToString()
+        assert B.parse_tensor_shape(msg.SerializeToString()) == tuple(shape)
+        assert tuple(d.size for d in shape_pb2.TensorShapeProto.FromString(B.encode_tensor_shape(shape)).dim) == tuple(shape)
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    for enum, dt in B._DTYPE_OF.items():
+        name = types_pb2.DataType.Name(enum)
+        assert name == {"<f4": "DT_FLOAT", "<f8": "DT_DOUBLE", "<i4": "DT_INT32", "|u1": "DT_UINT8", "<i2": "DT_INT16",
+                        "|i1": "DT_INT8", "<i8": "DT_INT64", "|b1": "DT_BOOL", "<u2": "DT_UINT16", "<f2": "DT_HALF",
+                        "<u4": "DT_UINT32", "<u8": "DT_UINT64"}[dt.str]
+
+
+def test_tf_bundle_detects_corruption(tmp_path):
+    from defensegan_b200 import tf_bundle as B
+    prefix = str(tmp_path / "GAN.model-1")
+    B.write_bundle(prefix, {"Generator.Input/Generator.Input.b": np.arange(64, dtype="float32")})
+    data = prefix + ".data-00000-of-00001"
+    raw = bytearray(open(data, "rb").read())
+    raw[10] ^= 0x40
+    open(data, "wb").write(bytes(raw))
+    with pytest.raises(ValueError, match="checksum"):
+        B.read_bundle(prefix)
+    assert B.read_bundle(prefix, verify_crc=False)["Generator.Input/Generator.Input.b"].shape == (64,)
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[3] ^= 0x01
+    open(prefix + ".index", "wb").write(bytes(idx))
+    with pytest.raises(ValueError):
+        B.read_bundle(prefix)
+    open(prefix + ".index", "wb").write(b"not a table")
+    with pytest.raises(ValueError):
+        B.list_bundle(prefix)
+
+
+def test_load_generator_from_tf_checkpoint_dir(tmp_path):
+    """models/gan.py:80-87: restore the Generator variables of the latest checkpoint in the model's dir."""
+    from defensegan_b200.models.gan import MnistDefenseGAN
+    from defensegan_b200 import tf_bundle as B
+    from defensegan_b200.weights import init_generator_weights
+    src = init_generator_weights("mnist", seed=7)
+    ckpt = tmp_path / "gans" / "mnist"
+    extra = {"Discriminator.1/Discriminator.1.Filters": np.zeros((5, 5, 1, 64), "float32"),
+             "Generator.2/Generator.2.Filters/Adam": np.ones((5, 5, 128, 256), "float32"), "global_step": np.asarray(500, "int64")}
+    B.write_bundle(str(ckpt / "GAN.model-0"), {k: v * 0 for k, v in src.items()})
+    B.write_bundle(str(ckpt / "GAN.model-500"), dict(src, **extra))
+    (ckpt / "checkpoint").write_text('model_checkpoint_path: "GAN.model-500"\nall_model_checkpoint_paths: "GAN.model-0"\n'
+                                     'all_model_checkpoint_paths: "GAN.model-500"\n')
+    assert B.latest_checkpoint(str(ckpt)).endswith("GAN.model-500")
+    gan = MnistDefenseGAN(test_mode=True, verbose=False)
+    assert gan.load_generator(str(ckpt)) is True
+    for k, v in src.items():
+        assert np.array_equal(gan.weights[k], v)
+    (ckpt / "checkpoint").unlink()                       # no state file: highest step wins
+    assert B.latest_checkpoint(str(ckpt)).endswith("GAN.model-500")
+    out = gan.save_generator(str(tmp_path / "export"), fmt="tf", global_step=3)
+    gan2 = MnistDefenseGAN(test_mode=True, verbose=False)
+    assert gan2.load_generator(str(tmp_path / "export")) is True and out.endswith("GAN.model-3")
+    assert all(np.array_equal(gan2.weights[k], v) for k, v in src.items())
+    assert MnistDefenseGAN(test_mode=True, verbose=False).load_generator(str(tmp_path / "empty")) is False
