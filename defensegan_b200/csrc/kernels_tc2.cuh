@@ -58,6 +58,7 @@ __host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out
 // MMA record:
 //   w[0]: ring offset / 1 KB [0,8) | A tiles [8,11) | ops [11,16) | flags [16,18): 1 = first step of an item, 2 = last
 //   w[2..7]: 12 x u16 per MMA: A tile [0,2) | first B slot [2,5) | slots - 1 [5,7) | accumulator [7,10) | first MMA into it [10,11)
+//            | B slot is in the PREVIOUS step's region [11,12) (a weight tile shared by consecutive steps is staged once)
 struct __align__(16) TcRec { uint32_t w[8]; };
 constexpr int TC2_MAX_A = 4, TC2_MAX_BSLOTS = 8, TC2_MAX_OPS = 12, TC2_NSLOT = 8;
 // Merged-N groups: when one input pixel feeds g accumulators that sit side by side in TMEM (acc, acc+1, ...) through
@@ -311,7 +312,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const uint32_t ring = stg_base + TC2_REC_BATCH * (uint32_t)sizeof(TcRec);
       const uint64_t desc0 = make_smem_desc_sw128(smem_base);
       const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
-      uint32_t buf = 0;
+      uint32_t buf = 0, prev_b_lo0 = 0;
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
         __syncwarp();
@@ -334,10 +335,10 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const long long tf1 = fine ? clock64() : 0;
           if (fa.dbg && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_first));
           ptx::tc_fence_after();
+          // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
+          const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
+          const uint32_t b_lo0 = a_lo0 + (uint32_t)nA * (uint32_t)(TC_A_BYTES >> 4);
           if (ptx::elect_one()) {
-            // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
-            const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
-            const uint32_t b_lo0 = a_lo0 + (uint32_t)nA * (uint32_t)(TC_A_BYTES >> 4);
             const uint32_t d0 = tmem_base + buf * TC2_BUF_COLS;
             const uint32_t opw[6] = {r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -346,7 +347,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               const uint32_t e = opw[oi >> 1] >> (16 * (oi & 1));
               const uint32_t first = (e >> 10) & 1u;
               const uint32_t a_lo = a_lo0 + (e & 3u) * (uint32_t)(TC_A_BYTES >> 4);
-              const uint32_t b_lo = b_lo0 + ((e >> 2) & 7u) * (uint32_t)(HALF_B >> 4);
+              const uint32_t b_lo = (((e >> 11) & 1u) ? prev_b_lo0 : b_lo0) + ((e >> 2) & 7u) * (uint32_t)(HALF_B >> 4);
               const uint32_t d = d0 + ((e >> 7) & 7u) * ACC_STRIDE;
               const uint32_t idg = idesc + ((e >> 5) & 3u) * ((uint32_t)(N_TILE >> 3) << 17);   // N = slots * N_TILE
 #pragma unroll
@@ -354,10 +355,12 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idg,
                                   (k > 0 || !first) ? 1u : 0u);
             }
-            ptx::umma_commit_2sm(bar_empty + 8 * slot);           // frees this step's ring region in both CTAs
+            ptx::umma_commit_2sm(bar_empty + 8 * slot);           // this step is consumed (both CTAs); the host planner knows
+                                                                  // which later step may still read its weight tiles
             if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
           }
           __syncwarp();
+          prev_b_lo0 = b_lo0;
           if (flags & 2u) ++item_count;
           if (fine) { t_wait_full += tf1 - tf0; t_issue += clock64() - tf1; }
         }
@@ -571,6 +574,7 @@ struct Tc2HostStep {
   uint8_t b_ent[2][TC2_MAX_BSLOTS] = {{0}, {0}};
   uint16_t ops[TC2_MAX_OPS] = {0};
   int n_tile_mmas = 0;         // un-merged count (statistics)
+  bool uses_prev = false;      // some op reads a weight tile the previous step staged
   int bytes = 0;               // operand bytes staged per CTA
 };
 struct Tc2HostItem {
@@ -584,7 +588,7 @@ struct Tc2HostItem {
 // pixels of a step is staged once.  Within a pixel, runs of consecutive accumulators whose tiles nobody else in
 // the step uses (and whose first-MMA flags agree) become one merged-N MMA.
 static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int N, int K, int max_g, int max_a,
-                           int step_max_bytes, Tc2HostItem* out) {
+                           int step_max_bytes, bool share_prev, Tc2HostItem* out) {
   const int kch = K / 64, half_b = (N / 2) * 128;
   out->hdr = TcItem2{};
   out->hdr.n_acc = (uint32_t)qs.size();
@@ -610,48 +614,78 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
     for (size_t b0 = 0; b0 < g.second.size(); b0 += (size_t)ent_cap)
       px.push_back({g.first, std::vector<std::pair<int, int>>(g.second.begin() + b0,
                                                                g.second.begin() + std::min(g.second.size(), b0 + (size_t)ent_cap))});
-  uint32_t seen = 0;
-  size_t i0 = 0;
-  while (i0 < px.size()) {
-    // ---- greedy group [i0, i1)
-    size_t i1 = i0;
-    std::vector<int> tiles;
-    int n_ent = 0;
-    while (i1 < px.size() && (int)(i1 - i0) < max_a) {
-      int fresh = 0;
-      for (auto& ta : px[i1].second)
-        if (std::find(tiles.begin(), tiles.end(), ta.first) == tiles.end()) ++fresh;
-      const int nA = (int)(i1 - i0) + 1, nB = (int)tiles.size() + fresh;
-      const bool dup_pixel = (i1 > i0 && px[i1].first == px[i1 - 1].first);   // split halves of one pixel stay apart
-      if (i1 > i0 && (dup_pixel || nB > TC2_MAX_BSLOTS || n_ent + (int)px[i1].second.size() > TC2_MAX_OPS ||
-                      nA * TC_A_BYTES + nB * half_b > step_max_bytes))
-        break;
-      for (auto& ta : px[i1].second)
-        if (std::find(tiles.begin(), tiles.end(), ta.first) == tiles.end()) tiles.push_back(ta.first);
-      n_ent += (int)px[i1].second.size();
-      ++i1;
+  // ---- phase 1: greedy groups.  A weight tile staged by the immediately preceding group of the same k-chunk phase is
+  //      still in the ring (the planner keeps that step's region alive one step longer): it is not staged again.
+  struct Group { size_t i0, i1; std::vector<int> staged; };
+  std::vector<Group> groups;
+  {
+    size_t i0 = 0;
+    std::vector<int> prev_staged;
+    while (i0 < px.size()) {
+      size_t i1 = i0;
+      std::vector<int> staged;      // tiles this group loads itself
+      int n_ent = 0;
+      auto have = [&](int t) {
+        return std::find(staged.begin(), staged.end(), t) != staged.end() ||
+               (share_prev && std::find(prev_staged.begin(), prev_staged.end(), t) != prev_staged.end());
+      };
+      while (i1 < px.size() && (int)(i1 - i0) < max_a) {
+        int fresh = 0;
+        std::vector<int> fresh_tiles;
+        for (auto& ta : px[i1].second)
+          if (!have(ta.first) && std::find(fresh_tiles.begin(), fresh_tiles.end(), ta.first) == fresh_tiles.end()) {
+            fresh_tiles.push_back(ta.first); ++fresh;
+          }
+        const int nA = (int)(i1 - i0) + 1, nB = (int)staged.size() + fresh;
+        const bool dup_pixel = (i1 > i0 && px[i1].first == px[i1 - 1].first);   // split halves of one pixel stay apart
+        if (i1 > i0 && (dup_pixel || nB > TC2_MAX_BSLOTS || n_ent + (int)px[i1].second.size() > TC2_MAX_OPS ||
+                        nA * TC_A_BYTES + nB * half_b > step_max_bytes))
+          break;
+        for (int t : fresh_tiles) staged.push_back(t);
+        n_ent += (int)px[i1].second.size();
+        ++i1;
+      }
+      groups.push_back({i0, i1, staged});
+      prev_staged = staged;
+      i0 = i1;
     }
-    // ---- ops + B slots of the group
+  }
+  // ---- phase 2: ops + B slots.  A tile is "single use" (mergeable into an N = g*N_TILE MMA) only if neither another
+  //      pixel of its group nor the next group needs it in the plain half-per-CTA layout.
+  uint32_t seen = 0;
+  int prev_slot_of[32];
+  for (int t = 0; t < 32; ++t) prev_slot_of[t] = -1;
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    const Group& G = groups[gi];
     std::vector<int> use(32, 0);
-    for (size_t i = i0; i < i1; ++i)
+    for (size_t i = G.i0; i < G.i1; ++i)
       for (auto& ta : px[i].second) ++use[ta.first];
+    if (share_prev && gi + 1 < groups.size())
+      for (size_t i = groups[gi + 1].i0; i < groups[gi + 1].i1; ++i)
+        for (auto& ta : px[i].second)
+          if (std::find(G.staged.begin(), G.staged.end(), ta.first) != G.staged.end()) ++use[ta.first];
     Tc2HostStep st;
-    st.nA = (int)(i1 - i0);
+    st.nA = (int)(G.i1 - G.i0);
     int slot_of[32];
     for (int t = 0; t < 32; ++t) slot_of[t] = -1;
-    for (size_t i = i0; i < i1; ++i) {
-      st.a_pix[i - i0] = px[i].first;
+    for (size_t i = G.i0; i < G.i1; ++i) {
+      st.a_pix[i - G.i0] = px[i].first;
       const auto& ent = px[i].second;
       for (size_t e = 0; e < ent.size();) {
-        const int acc0 = ent[e].second;
+        const int acc0 = ent[e].second, t0 = ent[e].first;
         const bool f0 = !(seen & (1u << acc0));
+        const bool own = std::find(G.staged.begin(), G.staged.end(), t0) != G.staged.end();
         size_t g = 1;
-        if (use[ent[e].first] == 1)
+        int slot, from_prev = 0;
+        if (!own) {                                     // staged by the previous step, plain layout
+          slot = prev_slot_of[t0];
+          from_prev = 1;
+          st.uses_prev = true;
+        } else if (use[t0] == 1) {
           while ((int)g < max_g && e + g < ent.size() && ent[e + g].second == acc0 + (int)g && use[ent[e + g].first] == 1 &&
+                 std::find(G.staged.begin(), G.staged.end(), ent[e + g].first) != G.staged.end() &&
                  (!(seen & (1u << ent[e + g].second))) == f0)
             ++g;
-        int slot;
-        if (use[ent[e].first] == 1) {
           slot = st.nB;
           for (int r = 0; r < 2; ++r)
             for (size_t jj = 0; jj < g; ++jj) {
@@ -659,14 +693,14 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
               st.b_ent[r][slot + jj] = (uint8_t)((ent[e + x / 2].first & 0x1F) | ((x & 1) << 5));
             }
           st.nB += (int)g;
-        } else if (slot_of[ent[e].first] >= 0) {
-          slot = slot_of[ent[e].first];
+        } else if (slot_of[t0] >= 0) {
+          slot = slot_of[t0];
         } else {
-          slot = slot_of[ent[e].first] = st.nB;
-          for (int r = 0; r < 2; ++r) st.b_ent[r][slot] = (uint8_t)((ent[e].first & 0x1F) | (r << 5));
+          slot = slot_of[t0] = st.nB;
+          for (int r = 0; r < 2; ++r) st.b_ent[r][slot] = (uint8_t)((t0 & 0x1F) | (r << 5));
           st.nB += 1;
         }
-        st.ops[st.n_ops++] = (uint16_t)((i - i0) | (slot << 2) | ((g - 1) << 5) | (acc0 << 7) | ((f0 ? 1 : 0) << 10));
+        st.ops[st.n_ops++] = (uint16_t)((i - G.i0) | (slot << 2) | ((g - 1) << 5) | (acc0 << 7) | ((f0 ? 1 : 0) << 10) | (from_prev << 11));
         st.n_tile_mmas += (int)g;
         for (size_t jj = 0; jj < g; ++jj) seen |= 1u << ent[e + jj].second;
         e += g;
@@ -674,7 +708,7 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
     }
     st.bytes = st.nA * TC_A_BYTES + st.nB * half_b;
     out->steps.push_back(st);
-    i0 = i1;
+    for (int t = 0; t < 32; ++t) prev_slot_of[t] = slot_of[t];
   }
   // k-chunk outermost: every accumulator then sums its (k-chunk, input pixel) contributions in one canonical order
   // - ascending k-chunk, ascending pixel - whatever the window shape and step grouping, so results do not depend
@@ -738,6 +772,9 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   const int N = w1.N, K = w1.K;
   const bool merge = (N >= 64) && !(getenv("DGAN_MERGE_N") && atoi(getenv("DGAN_MERGE_N")) == 0);
   const int max_g = merge ? std::min(4, 256 / N) : 1;
+  // Reusing the weight tiles of the previous step (its ring region then lives one step longer) cuts 5-15 % of the bytes
+  // of the conv kernels but measured 2 % slower end to end (less ring capacity in flight, fewer merged-N MMAs): opt-in.
+  const bool share_prev = getenv("DGAN_SHARE_PREV") && atoi(getenv("DGAN_SHARE_PREV")) != 0;
   const int max_a = getenv("DGAN_MULTI_A") ? std::max(1, std::min(TC2_MAX_A, atoi(getenv("DGAN_MULTI_A")))) : TC2_MAX_A;
   // Step size: a step is consumed only once all of it has landed, so big steps cost pipeline depth (4 x 48 KB fit the
   // ring); measured on C2: 32 KB (= one A tile per step) 5359, 40 KB 5466, 48-56 KB 5660, 64 KB 5553, 96 KB 5385 images/s.
@@ -756,7 +793,7 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
           if ((sy > 1 || sx > 1) && max_a == 1) continue;
           tc2_enumerate_windows(w2.h_grid, std::max(w2.w_grid, 1), wh, ww, sy, sx, &wins);
           std::vector<Tc2HostItem> items(wins.size());
-          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(w2.tab, wins[i], N, K, max_g, max_a, step_max, &items[i]);
+          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(w2.tab, wins[i], N, K, max_g, max_a, step_max, share_prev, &items[i]);
           std::stable_sort(items.begin(), items.end(), [](const Tc2HostItem& l, const Tc2HostItem& r) { return l.stage_bytes > r.stage_bytes; });
           std::vector<double> icost(items.size());
           for (size_t i = 0; i < items.size(); ++i)
@@ -793,6 +830,7 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
     stream_off[pr] = (uint32_t)stream_m.size();
     // circular operand ring of this CTA pair: sequential allocation, wrap when the step does not fit
     std::vector<std::pair<int, int>> region;     // [begin, end) in KB of every step of this stream
+    std::vector<char> reads_prev;                // step k reads weight tiles from step k-1's region
     int cursor = 0;
     for (size_t k = 0; k < best_lists[pr].size(); ++k) {
       const int win = best_lists[pr][k] / n_mpairs, mp = best_lists[pr][k] % n_mpairs;
@@ -806,13 +844,23 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
         if (cursor + kb > ring_bytes / 1024) cursor = 0;
         const int beg = cursor, end = cursor + kb;
         cursor = end;
-        int dep = TC2_NSLOT;                        // barrier-slot reuse
+        // The producer may overwrite a region once the last step that reads it is consumed: the step itself, or the
+        // next one when that reads weight tiles out of it.  dep = distance to the latest such step among the
+        // overlapping regions (8 = barrier-slot reuse only).
+        int dep = TC2_NSLOT;
         const int kidx = (int)region.size();
         for (int d = 1; d < TC2_NSLOT && d <= kidx; ++d) {
-          const auto& rg = region[(size_t)(kidx - d)];
-          if (rg.first < end && beg < rg.second) { dep = d; break; }   // latest overlapping step
+          const int c = kidx - d;
+          const auto& rg = region[(size_t)c];
+          if (rg.first < end && beg < rg.second) {
+            const bool next_reads = (c + 1 < kidx) ? reads_prev[(size_t)c + 1] != 0 : hs.uses_prev;   // step c+1 (maybe this one)
+            const int last_reader = c + (next_reads ? 1 : 0);
+            if (last_reader >= kidx) { set_error("operand ring too small for the step schedule"); return DGAN_ERR_UNSUPPORTED; }
+            dep = std::min(dep, kidx - last_reader);
+          }
         }
         region.push_back({beg, end});
+        reads_prev.push_back(hs.uses_prev ? 1 : 0);
         const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
         TcRec rm{};
         rm.w[0] = (uint32_t)beg | ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16);
