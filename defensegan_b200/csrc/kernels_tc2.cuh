@@ -444,7 +444,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           {
             float v[64];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]) * out_scale; v[32 + j] = __uint_as_float(r1[j]) * out_scale; }
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }   // out_scale == 1 (checked at launch)
             if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
               const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + g * 64);
 #pragma unroll
@@ -936,6 +936,7 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
     else if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
   }
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
+  if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT)) && out_scale != 1.f) { set_error("fp16 tile epilogue has no output scale"); return DGAN_ERR_UNSUPPORTED; }
   const int n_mpairs = n_pad / (2 * kRowTile);
   const Tc2Schedule* schp = nullptr;
   const int pairs_avail = st.max_pairs > 0 ? std::min(st.max_pairs, st.num_sms / 2) : st.num_sms / 2;
