@@ -954,6 +954,70 @@ int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* lau
 }
 
 /* developer aid (not in the public header): copy the DGAN_TC_DEBUG role-timing counters to the host */
+// Host-only developer/test aid (not in the public header): plan every tensor-core layer-direction of the fp16 path for
+// `n_rows` latent rows on `n_pairs` CTA pairs exactly as dgan_create/dgan_reconstruct would, and validate each plan
+// with tc2_check_plan.  Needs no GPU.  Returns 0, or an error code with the failing direction in dgan_last_error().
+int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int mutate) {
+  using namespace dgan;
+  if (d == nullptr || n_rows <= 0 || n_pairs <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
+  const bool celeba = d->arch == DGAN_ARCH_CELEBA;
+  const int nd = d->net_dim, latent = d->latent_dim;
+  const int n_pad = ((n_rows + 2 * kRowTile - 1) / (2 * kRowTile)) * 2 * kRowTile, n_mpairs = n_pad / (2 * kRowTile);
+  struct Dir { std::string name; int N, K; PairTable tab; int h, w, force_acc, epi, out_bytes; };
+  std::vector<Dir> dirs;
+  dirs.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2});
+  dirs.push_back({"Linear.bwd", latent, 4 * nd, linear_split_pairs(16), 1, TC_LINEAR_SPLIT, 1, EPI_NONE, 4});
+  struct DSpec { int c_in, c_out, h_in, h_used, in_raster; bool relu; };
+  std::vector<DSpec> specs;
+  if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, 4, true}, {2 * nd, nd, 8, 16, 8, true}, {nd, nd, 16, 32, 16, false}};
+  else specs = {{4 * nd, 2 * nd, 4, 7, 4, true}, {2 * nd, nd, 7, 14, 7, true}};
+  int li = 2;
+  for (const DSpec& sp : specs) {
+    const std::string nm = "Generator." + std::to_string(li == 4 ? 5 : li);
+    dirs.push_back({nm + ".fwd", sp.c_out, sp.c_in, deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.h_used, sp.h_used, 0,
+                    sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2});
+    dirs.push_back({nm + ".bwd", sp.c_in, sp.c_out, deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.in_raster, sp.in_raster, 0,
+                    EPI_MASK, 2});
+    ++li;
+  }
+  const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
+  dirs.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2});
+  dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, celeba ? EPI_NONE : EPI_MASK, 2});
+  for (const Dir& dr : dirs) {
+    if (dr.N != 16 && dr.N != 48 && dr.N != 64 && dr.N != 128 && dr.N != 256) { set_error(dr.name + ": unsupported N"); return DGAN_ERR_UNSUPPORTED; }
+    int max_acc = tc2_maxb(dr.N);
+    if (dr.force_acc > 0) max_acc = std::min(max_acc, dr.force_acc);
+    const int ring = tc2_ring_bytes(dr.N, dr.epi, dr.out_bytes);
+    Tc2Plan plan;
+    int rc = tc2_plan(dr.N, dr.K, dr.tab, dr.h, dr.w, max_acc, n_mpairs, n_pairs, ring, &plan);
+    if (rc) { set_error(dr.name + ": " + dgan_last_error()); return rc; }
+    // self-test of the validator: damage the plan of Generator.3 fwd in one specific way; the check must then fail
+    if (mutate != 0 && dr.name == "Generator.3.fwd" && plan.stream_m.size() > 40) {
+      TcRec& m = plan.stream_m[20];
+      TcRec* pp[2] = {&plan.stream_p[0][20], &plan.stream_p[1][20]};
+      switch (mutate) {
+        case 1: m.w[2] ^= 1u << 10; break;                                  // first-MMA flag of an op
+        case 2: m.w[2] ^= 1u << 7; break;                                   // accumulator of an op
+        case 3: pp[0]->w[4] ^= 0x01; break;                                 // weight tile staged by rank 0 only
+        case 4: pp[0]->w[2] ^= 0x01; pp[1]->w[2] ^= 0x01; break;            // input pixel of an A tile
+        case 5: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~(0xFu << 8)) | ((((pp[r]->w[0] >> 8) & 0xF) ^ 1u) << 8); break;   // k-chunk
+        case 6: plan.eitems[0] = -1; break;                                 // epilogue list loses an item
+        case 7: for (size_t i = 0; i < plan.stream_m.size(); ++i)           // every dep -> 8: ring hazards
+                  for (int r = 0; r < 2; ++r) plan.stream_p[r][i].w[0] = (plan.stream_p[r][i].w[0] & ~(0xFu << 19)) | (8u << 19);
+                break;
+        case 8: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~0xFFu) | 0xBFu; break;   // region past the ring
+        case 9: std::swap(plan.stream_m[20], plan.stream_m[21]);            // two steps out of order
+                for (int r = 0; r < 2; ++r) std::swap(plan.stream_p[r][20], plan.stream_p[r][21]);
+                break;
+        default: break;
+      }
+    }
+    std::string err;
+    if ((rc = tc2_check_plan(dr.N, dr.K, dr.tab, n_mpairs, ring, plan, &err))) { set_error(dr.name + ": " + err); return rc; }
+  }
+  return 0;
+}
+
 int dgan_debug_tc_timing(dgan_handle h, unsigned long long* out, int max_launches) {
   if (h == nullptr || out == nullptr || h->tc.dbg == nullptr) return 0;
   const int n = std::min(max_launches, h->tc.dbg_launch);

@@ -765,11 +765,18 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
 // CTA pairs with cost = operand bytes staged + a per-accumulator epilogue charge + a fixed per-item charge;
 // the smallest makespan wins.  Then each pair's items are concatenated into its step streams, the circular operand
 // ring is simulated to give every step its offset and its dependency distance, and everything is uploaded.
-static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int n_pairs, int ring_bytes,
-                            std::vector<void*>* allocs, cudaStream_t s, const Tc2Schedule** out) {
-  for (auto& kv : w2.by_mpairs)
-    if (kv.first == n_mpairs) { *out = &kv.second; return 0; }
-  const int N = w1.N, K = w1.K;
+struct Tc2Plan {               // host result of the planner (what tc2_get_schedule uploads)
+  int shape[4] = {1, 1, 1, 1};   // wh, ww, sy, sx
+  int n_slots = 0, n_pairs = 0;
+  std::vector<TcItem2> hdrs;
+  std::vector<TcRec> stream_p[2], stream_m;
+  std::vector<uint32_t> stream_off;
+  std::vector<int> eitems;
+  long long n_mma = 0, n_single = 0, n_steps = 0, n_bytes = 0;
+};
+
+static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, int max_acc, int n_mpairs, int n_pairs,
+                    int ring_bytes, Tc2Plan* plan) {
   const bool merge = (N >= 64) && !(getenv("DGAN_MERGE_N") && atoi(getenv("DGAN_MERGE_N")) == 0);
   const int max_g = merge ? std::min(4, 256 / N) : 1;
   // Reusing the weight tiles of the previous step (its ring region then lives one step longer) cuts 5-15 % of the bytes
@@ -780,6 +787,9 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   // ring); measured on C2: 32 KB (= one A tile per step) 5359, 40 KB 5466, 48-56 KB 5660, 64 KB 5553, 96 KB 5385 images/s.
   int step_max = std::min((ring_bytes / 2) & ~1023, 48 * 1024);
   if (getenv("DGAN_STEP_MAX_KB")) step_max = std::min((ring_bytes / 2) & ~1023, std::max(32, atoi(getenv("DGAN_STEP_MAX_KB"))) * 1024);
+  // a step that reads the previous step's weight tiles must never wrap onto that step's region: with steps of at
+  // most a third of the ring, the wrapped step ends before its predecessor begins
+  if (share_prev) step_max = std::min(step_max, (ring_bytes / 3) & ~1023);
   double best_cost = 1e300;
   int best_shape[4] = {1, 1, 1, 1};
   std::vector<Tc2HostItem> best_items;
@@ -789,11 +799,11 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
     for (int ww = 1; ww <= 8; ++ww)
       for (int sy = 1; sy <= (wh > 1 ? 2 : 1); ++sy)
         for (int sx = 1; sx <= (ww > 1 ? 2 : 1); ++sx) {
-          if (wh * ww > w2.max_acc || wh > w2.h_grid || ww > std::max(w2.w_grid, 1)) continue;
+          if (wh * ww > max_acc || wh > h_grid || ww > std::max(w_grid, 1)) continue;
           if ((sy > 1 || sx > 1) && max_a == 1) continue;
-          tc2_enumerate_windows(w2.h_grid, std::max(w2.w_grid, 1), wh, ww, sy, sx, &wins);
+          tc2_enumerate_windows(h_grid, std::max(w_grid, 1), wh, ww, sy, sx, &wins);
           std::vector<Tc2HostItem> items(wins.size());
-          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(w2.tab, wins[i], N, K, max_g, max_a, step_max, share_prev, &items[i]);
+          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(tab, wins[i], N, K, max_g, max_a, step_max, share_prev, &items[i]);
           std::stable_sort(items.begin(), items.end(), [](const Tc2HostItem& l, const Tc2HostItem& r) { return l.stage_bytes > r.stage_bytes; });
           std::vector<double> icost(items.size());
           for (size_t i = 0; i < items.size(); ++i)
@@ -816,15 +826,18 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
             best_items.swap(items); best_lists.swap(lists);
           }
         }
-  Tc2Schedule sc;
-  sc.wh = best_shape[0]; sc.ww = best_shape[1]; sc.sy = best_shape[2]; sc.sx = best_shape[3];
-  sc.n_windows = (int)best_items.size(); sc.n_pairs = n_pairs;
+  plan->shape[0] = best_shape[0]; plan->shape[1] = best_shape[1]; plan->shape[2] = best_shape[2]; plan->shape[3] = best_shape[3];
+  plan->n_pairs = n_pairs;
   size_t n_slots = 0;
   for (auto& l : best_lists) n_slots = std::max(n_slots, l.size());
-  sc.n_slots = (int)n_slots;
-  std::vector<int> eitems(n_slots * (size_t)n_pairs, -1);
-  std::vector<uint32_t> stream_off((size_t)n_pairs + 1, 0);
-  std::vector<TcRec> stream_p[2], stream_m;
+  plan->n_slots = (int)n_slots;
+  std::vector<int>& eitems = plan->eitems;
+  eitems.assign(n_slots * (size_t)n_pairs, -1);
+  std::vector<uint32_t>& stream_off = plan->stream_off;
+  stream_off.assign((size_t)n_pairs + 1, 0);
+  std::vector<TcRec>* stream_p = plan->stream_p;
+  std::vector<TcRec>& stream_m = plan->stream_m;
+  stream_p[0].clear(); stream_p[1].clear(); stream_m.clear();
   long long n_mma = 0, n_single = 0, n_steps = 0, n_bytes = 0;
   for (size_t pr = 0; pr < best_lists.size(); ++pr) {
     stream_off[pr] = (uint32_t)stream_m.size();
@@ -849,7 +862,7 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
         // overlapping regions (8 = barrier-slot reuse only).
         int dep = TC2_NSLOT;
         const int kidx = (int)region.size();
-        for (int d = 1; d < TC2_NSLOT && d <= kidx; ++d) {
+        for (int d = 1; d <= TC2_NSLOT && d <= kidx; ++d) {
           const int c = kidx - d;
           const auto& rg = region[(size_t)c];
           if (rg.first < end && beg < rg.second) {
@@ -879,21 +892,171 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
     }
   }
   stream_off[(size_t)n_pairs] = (uint32_t)stream_m.size();
-  std::vector<TcItem2> hdrs(best_items.size());
-  for (size_t i = 0; i < best_items.size(); ++i) hdrs[i] = best_items[i].hdr;
+  plan->hdrs.resize(best_items.size());
+  for (size_t i = 0; i < best_items.size(); ++i) plan->hdrs[i] = best_items[i].hdr;
+  plan->n_mma = n_mma; plan->n_single = n_single; plan->n_steps = n_steps; plan->n_bytes = n_bytes;
+  return 0;
+}
+
+// Independent validation of a plan against the pair table it was built from (host only; used by
+// dgan_debug_check_plans and the CPU tests).  Re-derives from the uploaded records alone:
+//  * every (output pixel, input pixel, tap, k-chunk) contribution of every item happens exactly once, into the right
+//    accumulator, with the weight half-tiles each CTA stages forming exactly the operand the MMA reads;
+//  * the first MMA into an accumulator - and only that one - overwrites it;
+//  * every accumulator sums in the canonical order (k-chunk major, input pixel ascending): results then do not
+//    depend on the schedule (batch-size / sharding invariance);
+//  * ring safety: when a step's loads may start (step k - dep consumed), no earlier step that can still be read
+//    overlaps its region, regions stay inside the ring, dep <= number of barrier slots;
+//  * every (window, row pair) item is assigned to exactly one CTA pair.
+static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int ring_bytes, const Tc2Plan& pl, std::string* err) {
+  auto fail = [&](const std::string& m) { *err = m; return DGAN_ERR_INVALID_ARG; };
+  const int kch = K / 64, half_b = (N / 2) * 128, acc_stride = tc2_acc_stride(N), max_acc = TC2_BUF_COLS / acc_stride;
+  const size_t n_pairs = (size_t)pl.n_pairs;
+  if (pl.stream_off.size() != n_pairs + 1) return fail("stream_off size");
+  if (pl.stream_p[0].size() != pl.stream_m.size() || pl.stream_p[1].size() != pl.stream_m.size()) return fail("stream sizes differ");
+  if (pl.eitems.size() != (size_t)pl.n_slots * n_pairs) return fail("eitems size");
+  std::vector<int> assigned(pl.hdrs.size() * (size_t)n_mpairs, 0);
+  for (const TcItem2& h : pl.hdrs) {
+    if (h.n_acc < 1 || (int)h.n_acc > max_acc) return fail("window with too many accumulators");
+    for (uint32_t a = 0; a < h.n_acc; ++a)
+      if ((size_t)h.q[a] + 1 >= tab.off.size()) return fail("window pixel out of range");
+  }
+  struct Step { int beg, end, nB, kc; bool uses_prev; uint8_t b0[8], b1[8]; };
+  for (size_t pr = 0; pr < n_pairs; ++pr) {
+    const uint32_t r_beg = pl.stream_off[pr], r_end = pl.stream_off[pr + 1];
+    if (r_beg > r_end || r_end > pl.stream_m.size()) return fail("stream_off not monotone");
+    std::vector<Step> steps;
+    int item_k = -1, win = -1, mp = -1;
+    bool in_item = false;
+    uint32_t seen = 0;
+    std::vector<std::pair<int, int>> last_kp;                     // per accumulator: last (kc, p)
+    std::vector<std::vector<std::pair<int, int>>> contrib;        // per accumulator: (p * 32 + tile, kc)
+    size_t item_first_step = 0;
+    for (uint32_t ri = r_beg; ri < r_end; ++ri) {
+      const TcRec &m = pl.stream_m[ri], &p0 = pl.stream_p[0][ri], &p1 = pl.stream_p[1][ri];
+      const int k = (int)steps.size();
+      Step st{};
+      st.beg = (int)(p0.w[0] & 0xFF);
+      const int nA = (int)((p0.w[0] >> 12) & 7), nB = (int)((p0.w[0] >> 15) & 0xF), dep = (int)((p0.w[0] >> 19) & 0xF);
+      st.kc = (int)((p0.w[0] >> 8) & 0xF); st.nB = nB;
+      if (p1.w[0] != p0.w[0] || p1.w[1] != p0.w[1] || p1.w[2] != p0.w[2] || p1.w[3] != p0.w[3]) return fail("producer records of the two ranks disagree");
+      if ((int)(m.w[0] & 0xFF) != st.beg || (int)((m.w[0] >> 8) & 7) != nA) return fail("MMA record disagrees with the producer record");
+      if (nA < 1 || nA > TC2_MAX_A || nB > TC2_MAX_BSLOTS || st.kc >= kch) return fail("step field out of range");
+      st.end = st.beg + (nA * TC_A_BYTES + nB * half_b + 1023) / 1024;
+      if (st.end * 1024 > ring_bytes) return fail("step region outside the ring");
+      if (dep < 1 || dep > TC2_NSLOT) return fail("dep out of range");
+      for (int b = 0; b < 8; ++b) { st.b0[b] = (uint8_t)(p0.w[4 + b / 4] >> (8 * (b & 3))); st.b1[b] = (uint8_t)(p1.w[4 + b / 4] >> (8 * (b & 3))); }
+      const uint32_t flags = (m.w[0] >> 16) & 3u;
+      const int n_ops = (int)((m.w[0] >> 11) & 0x1F);
+      if (n_ops > TC2_MAX_OPS) return fail("too many ops in a step");
+      if (flags & 1u) {
+        if (in_item) return fail("item starts inside an item");
+        in_item = true; ++item_k;
+        if (item_k >= pl.n_slots) return fail("more items than slots");
+        const int e = pl.eitems[(size_t)item_k * n_pairs + pr];
+        if (e < 0) return fail("stream has an item the epilogue list lacks");
+        win = e >> 16; mp = e & 0xFFFF;
+        if ((size_t)win >= pl.hdrs.size() || mp >= n_mpairs) return fail("item index out of range");
+        if (assigned[(size_t)win * n_mpairs + mp]++) return fail("item assigned twice");
+        seen = 0;
+        last_kp.assign(pl.hdrs[win].n_acc, {-1, -1});
+        contrib.assign(pl.hdrs[win].n_acc, {});
+        item_first_step = steps.size();
+      }
+      if (!in_item) return fail("step outside an item");
+      if ((int)(p0.w[1] & 0xFFFF) != mp) return fail("row pair of a step differs from its item");
+      const TcItem2& hdr = pl.hdrs[win];
+      for (int oi = 0; oi < n_ops; ++oi) {
+        const uint32_t e = (m.w[2 + oi / 2] >> (16 * (oi & 1))) & 0xFFFFu;
+        const int a_idx = e & 3, slot = (e >> 2) & 7, g = ((e >> 5) & 3) + 1, acc0 = (e >> 7) & 7;
+        const bool first = (e >> 10) & 1, prev = (e >> 11) & 1;
+        if (a_idx >= nA) return fail("op reads an A tile the step does not stage");
+        if (acc0 + g > (int)hdr.n_acc) return fail("op writes past the window's accumulators");
+        if (g > 1 && (acc_stride != N || g * N > 256)) return fail("merged MMA too wide");
+        const int p = (int)((p0.w[2 + a_idx / 2] >> (16 * (a_idx & 1))) & 0xFFFF);
+        int tiles[4];
+        if (prev) {
+          if (g != 1 || steps.size() == item_first_step) return fail("bad previous-step reference");
+          const Step& ps = steps.back();
+          if (ps.kc != st.kc || slot >= ps.nB) return fail("previous-step reference out of range");
+          if ((ps.b0[slot] & 0x3F) != (ps.b0[slot] & 0x1F) || (ps.b1[slot] & 0x3F) != ((ps.b0[slot] & 0x1F) | 0x20)) return fail("previous-step tile is not in plain layout");
+          tiles[0] = ps.b0[slot] & 0x1F;
+          st.uses_prev = true;
+        } else {
+          if (slot + g > nB) return fail("op reads a B slot the step does not stage");
+          for (int i = 0; i < g; ++i) {
+            const int x0 = 2 * i, x1 = 2 * i + 1;
+            const uint8_t* lo = (x0 / g) ? st.b1 : st.b0; const uint8_t* hi = (x1 / g) ? st.b1 : st.b0;
+            const uint8_t el = lo[slot + x0 % g], eh = hi[slot + x1 % g];
+            if ((el & 0x20) != 0 || (eh & 0x20) == 0 || (el & 0x1F) != (eh & 0x1F)) return fail("staged weight halves do not form the MMA operand");
+            tiles[i] = el & 0x1F;
+          }
+        }
+        for (int i = 0; i < g; ++i) {
+          const int acc = acc0 + i;
+          const bool unseen = !(seen & (1u << acc));
+          if (first != unseen) return fail(first ? "overwrite of a live accumulator" : "accumulate into an uninitialised accumulator");
+          const std::pair<int, int> kp{st.kc, p};
+          if (!(last_kp[acc] < kp)) return fail("accumulation order is not canonical (k-chunk major, pixel ascending)");
+          last_kp[acc] = kp;
+          contrib[acc].push_back({p * 32 + tiles[i], st.kc});
+        }
+        for (int i = 0; i < g; ++i) seen |= 1u << (acc0 + i);
+      }
+      // ring safety
+      if (st.uses_prev && !steps.empty() && steps.back().beg < st.end && st.beg < steps.back().end) return fail("step overlaps the region it reads");
+      for (int c = k - 1; c >= 0 && c >= k - 4 * TC2_NSLOT; --c) {
+        const Step& o = steps[(size_t)c];
+        if (!(o.beg < st.end && st.beg < o.end)) continue;
+        const int last_reader = c + ((c + 1 < k) ? (steps[(size_t)c + 1].uses_prev ? 1 : 0) : (st.uses_prev ? 1 : 0));
+        if (last_reader > k - dep) return fail("ring hazard: a region may be overwritten while it can still be read");
+      }
+      steps.push_back(st);
+      if (flags & 2u) {
+        for (uint32_t a = 0; a < hdr.n_acc; ++a) {
+          std::vector<std::pair<int, int>> want;
+          for (int kc = 0; kc < kch; ++kc)
+            for (int e2 = tab.off[hdr.q[a]]; e2 < tab.off[hdr.q[a] + 1]; ++e2) want.push_back({tab.pairs[e2].x * 32 + tab.pairs[e2].y, kc});
+          std::vector<std::pair<int, int>> got = contrib[a];
+          std::sort(want.begin(), want.end()); std::sort(got.begin(), got.end());
+          if (want != got) return fail("an item's MMAs do not cover exactly its pair list");
+        }
+        in_item = false;
+      }
+    }
+    if (in_item) return fail("stream ends inside an item");
+    for (int kk = item_k + 1; kk < pl.n_slots; ++kk)
+      if (pl.eitems[(size_t)kk * n_pairs + pr] != -1) return fail("epilogue list has an item the stream lacks");
+  }
+  for (int v : assigned)
+    if (v != 1) return fail("an item is not assigned to any CTA pair");
+  return 0;
+}
+
+// Pick (and build on first use) the schedule of one layer-direction for `n_mpairs` row pairs and upload it.
+static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int n_pairs, int ring_bytes,
+                            std::vector<void*>* allocs, cudaStream_t s, const Tc2Schedule** out) {
+  (void)st;
+  for (auto& kv : w2.by_mpairs)
+    if (kv.first == n_mpairs) { *out = &kv.second; return 0; }
+  Tc2Plan plan;
   int rc;
-  if ((rc = tc_upload(allocs, hdrs.data(), hdrs.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
+  if ((rc = tc2_plan(w1.N, w1.K, w2.tab, w2.h_grid, w2.w_grid, w2.max_acc, n_mpairs, n_pairs, ring_bytes, &plan))) return rc;
+  Tc2Schedule sc;
+  sc.wh = plan.shape[0]; sc.ww = plan.shape[1]; sc.sy = plan.shape[2]; sc.sx = plan.shape[3];
+  sc.n_windows = (int)plan.hdrs.size(); sc.n_pairs = n_pairs; sc.n_slots = plan.n_slots;
+  if ((rc = tc_upload(allocs, plan.hdrs.data(), plan.hdrs.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
   for (int r = 0; r < 2; ++r)
-    if ((rc = tc_upload(allocs, stream_p[r].data(), stream_p[r].size() * sizeof(TcRec), (void**)&sc.stream_p[r], s))) return rc;
-  if ((rc = tc_upload(allocs, stream_m.data(), stream_m.size() * sizeof(TcRec), (void**)&sc.stream_m, s))) return rc;
-  if ((rc = tc_upload(allocs, stream_off.data(), stream_off.size() * sizeof(uint32_t), (void**)&sc.stream_off, s))) return rc;
-  if ((rc = tc_upload(allocs, eitems.data(), eitems.size() * sizeof(int), (void**)&sc.eitems, s))) return rc;
+    if ((rc = tc_upload(allocs, plan.stream_p[r].data(), plan.stream_p[r].size() * sizeof(TcRec), (void**)&sc.stream_p[r], s))) return rc;
+  if ((rc = tc_upload(allocs, plan.stream_m.data(), plan.stream_m.size() * sizeof(TcRec), (void**)&sc.stream_m, s))) return rc;
+  if ((rc = tc_upload(allocs, plan.stream_off.data(), plan.stream_off.size() * sizeof(uint32_t), (void**)&sc.stream_off, s))) return rc;
+  if ((rc = tc_upload(allocs, plan.eitems.data(), plan.eitems.size() * sizeof(int), (void**)&sc.eitems, s))) return rc;
   w2.by_mpairs.push_back({n_mpairs, sc});
   *out = &w2.by_mpairs.back().second;
   if (getenv("DGAN_TC_VERBOSE"))
     fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d stride %dx%d, %d windows, %lld steps, %.1f MB staged/CTA-set, "
-                    "%lld tile-MMAs in %lld merged\n", N, K, w2.h_grid, w2.w_grid, n_mpairs, sc.wh, sc.ww, sc.sy, sc.sx, sc.n_windows, n_steps,
-            2.0 * n_bytes / 1e6, n_single, n_mma);
+                    "%lld tile-MMAs in %lld merged\n", w1.N, w1.K, w2.h_grid, w2.w_grid, n_mpairs, sc.wh, sc.ww, sc.sy, sc.sx, sc.n_windows, plan.n_steps,
+            2.0 * plan.n_bytes / 1e6, plan.n_single, plan.n_mma);
   return 0;
 }
 
