@@ -225,6 +225,7 @@ struct Workspace {
   // index 2l = forward of layer l (in, out), 2l+1 = backward of layer l; 2nl = last-layer forward, 2nl+1 = its backward
   std::vector<CUtensorMap> map_in, map_out;
   bool have_maps = false;
+  unsigned* mom_counter = nullptr;     // fp16 path: [n_pad / 128] tickets of the split-K Linear backward's momentum tail
   __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
   int n_loss_parts = 0, n_g_parts = 1;
   size_t loss_stride_n = 1, loss_stride_b = 1;   // loss_part index = n * stride_n + part * stride_b
@@ -251,6 +252,7 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   w.n_g_parts = tc ? TC_LINEAR_SPLIT : 1;
   w.g = (float*)take(np * latent * 4 * w.n_g_parts);
   if (tc) w.z_h = (__half*)take(np * latent * 2);
+  if (tc) w.mom_counter = (unsigned*)take(np / kRowTile * sizeof(unsigned));
   if (tc) w.dblk = (__half*)take((size_t)c->tc_fin.n_blocks * np * 64 * 2);
   w.n_loss_parts = tc ? c->tc_fin.n_blocks : c->fin.n_bands;
   w.loss_stride_n = tc ? 1 : (size_t)w.n_loss_parts;          // fp16 path: [block][n_pad] (coalesced epilogue stores)
@@ -447,7 +449,7 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
 }
 
 // ---- backward-to-z: w.g = J^T dpre (unscaled by 2/HWC; fp16 path additionally x gscale) -----
-struct MomentumArgs { bool fused = false; float lr = 0.f, mu = 0.f; };
+struct MomentumArgs { bool fused = false, tail = false; float lr = 0.f, mu = 0.f; };
 
 static float grad_multiplier(const dgan_ctx* c);
 
@@ -480,9 +482,15 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
       return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b_fused, w.dact_h[0], w.g, w.n_pad, EPI_MOMENTUM, nullptr,
                                     nullptr, 1.f, s, &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
     }
-    if (c->tc.mode == 2)
+    if (c->tc.mode == 2) {
+      TcFinalArgs fa{};
+      if (mom.tail && w.n_g_parts == TC_LINEAR_SPLIT) {      // the CTA that completes a row tile's partial sums applies the momentum update
+        fa.mz = w.z; fa.mv = w.v; fa.mz_h = w.z_h; fa.m_gmul = grad_multiplier(c); fa.m_lr = mom.lr; fa.m_mu = mom.mu;
+        fa.m_counter = w.mom_counter; fa.m_nparts = w.n_g_parts; fa.m_count = (size_t)w.n_pad * c->desc.latent_dim;
+      }
       return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s,
-                                    nullptr, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
+                                    &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
+    }
     return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
   }
   // d(act) -> d(pre) through ReLU + batch-statistics BN of layer l (in place in w.dact[l])
@@ -531,6 +539,7 @@ static int run_init_z(dgan_ctx* c, const Workspace& w, const float* z0, uint64_t
   const size_t total4 = (size_t)w.n_pad * latent / 4;
   // the last layer's block tensor is K-padded to 64 columns; the epilogue only ever writes the 16*C_out valid ones
   if (w.dblk != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.dblk, 0, (size_t)c->tc_fin.n_blocks * w.n_pad * 64 * sizeof(__half), s));
+  if (w.mom_counter != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.mom_counter, 0, (size_t)w.n_pad / kRowTile * sizeof(unsigned), s));
   init_z_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(w.z, w.v, w.z_h, z0, w.n_rows, w.n_pad, latent, seed,
                                                                  sqrtf(1.0f / (float)latent), row_offset * latent);
   DGAN_LAUNCH_CHECK(c);
@@ -883,6 +892,11 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
     if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
     // fused Linear-backward + momentum epilogue exists (EPI_MOMENTUM) but measured slower than split-K + momentum_kernel
     const bool fused = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 && getenv("DGAN_FUSED_MOMENTUM") != nullptr;
+    // DGAN_MOMENTUM_TAIL=1: momentum in the tail of the split-K Linear backward (the CTA completing a row tile's partial
+    // sums applies the update; no separate kernel).  Bit-identical, but measured no faster (Linear bwd 16.7 -> 27.0 us vs
+    // 16.7 + 9.5 us for the momentum kernel: 5631 vs 5616 images/s), so the separate kernel stays the default.
+    const bool tail = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 &&
+                      getenv("DGAN_MOMENTUM_TAIL") && atoi(getenv("DGAN_MOMENTUM_TAIL")) != 0;
     for (Chain& ch : chains) {
       const Workspace& w = ch.w;
       cudaStream_t s = ch.s;
@@ -893,8 +907,9 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
       if (last) continue;
       MomentumArgs mom;
       mom.fused = fused; mom.lr = lr; mom.mu = momentum;
+      mom.tail = !fused && tail;
       if ((rc = run_backward(h, w, s, mom))) return rc;
-      if (!fused) {
+      if (!fused && !mom.tail) {
         const size_t zcount = (size_t)w.n_pad * latent;
         ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
         DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,

@@ -187,6 +187,11 @@ struct TcFinalArgs {
   // EPI_MOMENTUM (Linear backward fused with tf.train.MomentumOptimizer, models/gan.py:389-391):
   float* mz; float* mv; __half* mz_h;   // z, velocity [n_pad][latent] fp32, fp16 copy of z
   float m_gmul, m_lr, m_mu;             // g = gmul * acc;  v <- mu v + g;  z <- z - lr v
+  // split-K Linear backward with the momentum update in its tail: the CTA whose partial sums complete a 128-row tile
+  // (ticket from m_counter[tile]) applies v <- mu v + gmul * sum(parts), z <- z - lr v for that tile (mz/mv/mz_h above)
+  unsigned* m_counter;   // [n_pad / 128] arrival tickets, self-resetting; NULL = plain partial sums
+  int m_nparts;          // partial sums per row tile
+  size_t m_count;        // elements per partial-sum array (n_pad * latent)
   unsigned long long* dbg;  // optional per-CTA role timing (16 counters per CTA), NULL in production
   int dbg_flags;            // timing experiments only: 1 = skip epilogue stores, 2 = skip mask loads, 4 = skip bias
 };

@@ -155,6 +155,12 @@ __device__ __forceinline__ void tma_load_3d_local(uint32_t dst, const CUtensorMa
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
   uint2 v;
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -525,6 +531,61 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_remote(bar_acc_empty + 8 * buf, 0);
+      if (EPI == EPI_NONE && sizeof(TOUT) == 4 && fa.m_counter != nullptr) {
+        // ---- momentum in the tail of the split-K Linear backward.  Every epilogue thread has stored its share of this
+        //      item's partial sums; the CTA that completes the last partial of its 128-row tile applies the update
+        //      (same arithmetic and summation order as momentum_kernel: parts 0, 1, 2, ...).
+        const uint32_t flag_addr = bar_base + 200;
+        const unsigned rt = 2u * (unsigned)mp + rank;
+        __threadfence();
+        ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
+        if (warp == 2 && lane == 0) {
+          const unsigned ticket = atomicAdd(fa.m_counter + rt, 1u);
+          ptx::st_shared_u32(flag_addr, ticket == (unsigned)TC_LINEAR_SPLIT - 1u ? 1u : 0u);
+        }
+        ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
+        if (ptx::ld_shared_u32(flag_addr) != 0u) {
+          __threadfence();
+          const float* __restrict__ gp = reinterpret_cast<const float*>(out);
+          const size_t base = (size_t)rt * kRowTile * N_TILE;
+          const int tid = (warp - 2) * 32 + lane;
+          // 4 float4 positions per thread in flight at a time (the loop is latency-bound: 6 L2 reads per position)
+          constexpr int STRIDE = 4 * 32 * TC2_EPI_WARPS, UNR = 4;
+          for (int e0 = tid * 4; e0 < kRowTile * N_TILE; e0 += UNR * STRIDE) {
+            float4 gs[UNR], vv[UNR], zz[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const size_t i = base + (size_t)(e0 + u * STRIDE);
+              gs[u] = __ldcg(reinterpret_cast<const float4*>(gp + i));
+              vv[u] = *reinterpret_cast<const float4*>(fa.mv + i);
+              zz[u] = *reinterpret_cast<const float4*>(fa.mz + i);
+            }
+            float4 t[TC_LINEAR_SPLIT - 1][UNR];      // all partial sums of the 4 positions in flight together
+#pragma unroll
+            for (int pp = 1; pp < TC_LINEAR_SPLIT; ++pp)
+#pragma unroll
+              for (int u = 0; u < UNR; ++u)
+                t[pp - 1][u] = __ldcg(reinterpret_cast<const float4*>(gp + base + (size_t)(e0 + u * STRIDE) + (size_t)pp * fa.m_count));
+#pragma unroll
+            for (int pp = 1; pp < TC_LINEAR_SPLIT; ++pp)      // fixed order: parts 0, 1, 2, 3 (as momentum_kernel)
+#pragma unroll
+              for (int u = 0; u < UNR; ++u) { gs[u].x += t[pp - 1][u].x; gs[u].y += t[pp - 1][u].y; gs[u].z += t[pp - 1][u].z; gs[u].w += t[pp - 1][u].w; }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const size_t i = base + (size_t)(e0 + u * STRIDE);
+              float4 v4 = vv[u], z4 = zz[u];
+              v4.x = fmaf(fa.m_mu, v4.x, fa.m_gmul * gs[u].x); v4.y = fmaf(fa.m_mu, v4.y, fa.m_gmul * gs[u].y);
+              v4.z = fmaf(fa.m_mu, v4.z, fa.m_gmul * gs[u].z); v4.w = fmaf(fa.m_mu, v4.w, fa.m_gmul * gs[u].w);
+              z4.x -= fa.m_lr * v4.x; z4.y -= fa.m_lr * v4.y; z4.z -= fa.m_lr * v4.z; z4.w -= fa.m_lr * v4.w;
+              *reinterpret_cast<float4*>(fa.mv + i) = v4;
+              *reinterpret_cast<float4*>(fa.mz + i) = z4;
+              if (fa.mz_h != nullptr)
+                *reinterpret_cast<uint2*>(fa.mz_h + i) = make_uint2(pack_half2(z4.x, z4.y), pack_half2(z4.z, z4.w));
+            }
+          }
+          if (tid == 0) fa.m_counter[rt] = 0u;             // ready for the next launch
+        }
+      }
       if (fa.dbg) { t_ewait += te1 - te0; t_ework += clock64() - te1; }
     }
     if (TMA_EPI && lane == 0 && (warp == 2 || warp == 6)) ptx::bulk_wait_all0();   // stores landed before exit
