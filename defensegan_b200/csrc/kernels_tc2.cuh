@@ -194,7 +194,7 @@ __device__ __forceinline__ int tc2_item_at(const int* __restrict__ order, int k,
 template <int N_TILE, int EPI, typename TOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_mask,
+                  const __grid_constant__ CUtensorMap tm_out,
                   const TcItem2* __restrict__ items, const TcRec* __restrict__ stream_p0, const TcRec* __restrict__ stream_p1,
                   const TcRec* __restrict__ stream_m, const uint32_t* __restrict__ stream_off,
                   const int* __restrict__ eitems, int n_slots,
@@ -205,11 +205,10 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   constexpr int HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + Cfg::RING_BYTES;       // [out tile half0][out tile half1][mask half0][mask half1]
+  const uint32_t epi_base = smem_base + Cfg::RING_BYTES;            // output staging tiles: EPI_TILES / 2 per epilogue half
   const uint32_t stg_base = epi_base + Cfg::EPI_BYTES;              // [producer ring][MMA ring] of TcRec
   const uint32_t bar_base = stg_base + TC2_STAGING_BYTES;
-  const uint32_t bar_mask = bar_base + 176;                          // mask_full[2]
-  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160, mask_full[2] @ +176
+  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160, momentum-tail flag @ +200
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
   const uint32_t tmem_slot = bar_base + 160;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -229,7 +228,6 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_acc_full + 8 * b, 1);
       ptx::mbar_init(bar_acc_empty + 8 * b, 2 * TC2_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
-      ptx::mbar_init(bar_mask + 8 * b, 1);
     }
     if (TMA_EPI) ptx::prefetch_tmap(&tm_out);
     ptx::fence_barrier_init();
@@ -1154,7 +1152,7 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   int rc;
   if (pre_a != nullptr) tm_a = *pre_a;          // encoded once per workspace by the caller
   else if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
-  CUtensorMap tm_out = tm_a, tm_mask = tm_a;     // placeholders when unused
+  CUtensorMap tm_out = tm_a;                     // placeholder when unused
   if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT))) {
     if (pre_out != nullptr) tm_out = *pre_out;
     else if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
@@ -1173,10 +1171,10 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
-                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
-                  tm_a, w2m.tm_b, tm_out, tm_mask, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
                   mask_src, out_scale, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
