@@ -540,6 +540,10 @@ static int run_init_z(dgan_ctx* c, const Workspace& w, const float* z0, uint64_t
   // the last layer's block tensor is K-padded to 64 columns; the epilogue only ever writes the 16*C_out valid ones
   if (w.dblk != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.dblk, 0, (size_t)c->tc_fin.n_blocks * w.n_pad * 64 * sizeof(__half), s));
   if (w.mom_counter != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.mom_counter, 0, (size_t)w.n_pad / kRowTile * sizeof(unsigned), s));
+  // fp32 path: the last layer's forward writes dL/dpre for the real rows only while its backward walks all n_pad rows;
+  // the tile-padding rows are never observed, but they must not be read uninitialised
+  if (w.dblk == nullptr && w.n_pad > w.n_rows)
+    DGAN_CUDA_CHECK(cudaMemsetAsync(w.dpre + (size_t)w.n_rows * c->hwc, 0, (size_t)(w.n_pad - w.n_rows) * c->hwc * sizeof(float), s));
   init_z_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(w.z, w.v, w.z_h, z0, w.n_rows, w.n_pad, latent, seed,
                                                                  sqrtf(1.0f / (float)latent), row_offset * latent);
   DGAN_LAUNCH_CHECK(c);

@@ -278,6 +278,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int row0 = (2 * (int)(r0.y & 0xFFFFu) + (int)rank) * kRowTile;
         const long long tw0 = fa.dbg ? clock64() : 0;
         if (it >= dep) ptx::mbar_wait(bar_empty + 8 * ((it - dep) & (TC2_NSLOT - 1)), ((it - dep) >> 3) & 1);   // step it-dep consumed
+        // implied by the wait above (steps are consumed in order); observing every phase of this slot exactly once
+        // before it is re-armed keeps the barrier protocol checkable (compute-sanitizer synccheck)
+        if (dep != TC2_NSLOT && it >= TC2_NSLOT) ptx::mbar_wait(bar_empty + 8 * slot, ((it - TC2_NSLOT) >> 3) & 1);
         if (fa.dbg) t_wait += clock64() - tw0;
         const uint32_t full = bar_full + 8 * slot;
         const uint32_t sa = smem_base + ((r0.x & 0xFFu) << 10);
@@ -301,6 +304,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       }
       __syncwarp();
     }
+    // drain: the last steps' "consumed" signals are otherwise never observed (nobody leaves while MMAs still read smem)
+    for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
     if (fa.dbg && lane == 0) fa.dbg[blockIdx.x * 16 + 0] = (unsigned long long)t_wait;
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -370,6 +375,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
         __syncwarp();
       }
+      // drain: observe the release of the last (up to two) accumulator buffers by the epilogue warps of both CTAs
+      for (uint32_t j = item_count > 2 ? item_count - 2 : 0; j < item_count; ++j) ptx::mbar_wait(bar_acc_empty + 8 * (j & 1), (j >> 1) & 1);
       if (fa.dbg && lane == 0) {
         fa.dbg[blockIdx.x * 16 + 1] = (unsigned long long)t_wait_full;
         fa.dbg[blockIdx.x * 16 + 2] = (unsigned long long)t_wait_acc;
