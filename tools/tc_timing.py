@@ -1,6 +1,9 @@
 """Developer aid: per-role wait/work cycles of the CTA-pair tensor-core kernels (DGAN_TC_DEBUG=1).
-Prints, for each of the first launches of one projection, the mean over CTAs of: producer wait on
-'empty', MMA wait on 'full', MMA wait on 'acc_empty', MMA issue, epilogue wait, epilogue work, total."""
+Prints, for each of the first launches of one projection, the mean over CTAs of: producer wait on ring space,
+MMA wait on 'full', MMA wait on 'acc_empty', MMA issue, whole MMA loop, epilogue work, CTA utilisation, the
+%globaltimer timeline of the launch, and (leader CTAs) when the MMA loop started / first operands landed / loop ended.
+DGAN_TC_DBGFLAGS: 8 = no per-step clocks (unperturbed loop time), 16 = issue no MMAs (delivery-only time),
+1 = skip epilogue stores, 2 = skip mask loads, 32 = skip last-layer target loads."""
 import ctypes
 import os
 import sys
