@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 # Every symbol include/defensegan_b200.h declares.
 ABI_SYMBOLS = [
     "dgan_abi_version", "dgan_last_error", "dgan_num_weights", "dgan_create", "dgan_destroy",
-    "dgan_workspace_bytes", "dgan_reconstruct", "dgan_forward", "dgan_loss_grad",
+    "dgan_workspace_bytes", "dgan_reconstruct", "dgan_sample_z0", "dgan_forward", "dgan_loss_grad",
     "dgan_last_launch_count", "dgan_macs_per_row", "dgan_profile_enable", "dgan_profile_num_kinds",
     "dgan_profile_kind_name", "dgan_profile_read",
 ]
@@ -39,6 +39,15 @@ ABI_SYMBOLS = [
 class dgan_desc(ctypes.Structure):
     _fields_ = [("abi_version", ctypes.c_int32), ("arch", ctypes.c_int32), ("latent_dim", ctypes.c_int32),
                 ("net_dim", ctypes.c_int32), ("use_bn", ctypes.c_int32), ("precision", ctypes.c_int32)]
+
+
+class dgan_rec_params(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("rec_rr", ctypes.c_int32), ("rec_iters", ctypes.c_int32),
+                ("rec_lr", ctypes.c_float), ("momentum", ctypes.c_float), ("decay_lr", ctypes.c_int32),
+                ("seed", ctypes.c_uint64), ("z_row_offset", ctypes.c_uint64)]
+
+
+ABI_VERSION = 2
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -73,6 +82,10 @@ def load_library() -> ctypes.CDLL:
             "%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` (or "
             "defensegan_b200._native.build_library()) first. There is no CPU fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
+    lib.dgan_abi_version.restype = ctypes.c_int
+    if lib.dgan_abi_version() != ABI_VERSION:
+        raise RuntimeError("%s has ABI version %d, this binding needs %d: rebuild it (__graft_entry__.build())"
+                           % (LIB_PATH, lib.dgan_abi_version(), ABI_VERSION))
     vp, i32, u64, f32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_float, ctypes.c_size_t
     lib.dgan_abi_version.restype = i32
     lib.dgan_abi_version.argtypes = []
@@ -87,7 +100,9 @@ def load_library() -> ctypes.CDLL:
     lib.dgan_workspace_bytes.restype = sz
     lib.dgan_workspace_bytes.argtypes = [vp, i32, i32]
     lib.dgan_reconstruct.restype = i32
-    lib.dgan_reconstruct.argtypes = [vp, vp, vp, u64, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, sz, vp]
+    lib.dgan_reconstruct.argtypes = [vp, ctypes.POINTER(dgan_rec_params), vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.dgan_sample_z0.restype = i32
+    lib.dgan_sample_z0.argtypes = [vp, u64, u64, i32, vp, vp]
     lib.dgan_forward.restype = i32
     lib.dgan_forward.argtypes = [vp, vp, i32, vp, vp, sz, vp]
     lib.dgan_loss_grad.restype = i32
@@ -146,19 +161,21 @@ class NativeGenerator:
         self.hwc = self.image_dim[0] * self.image_dim[1] * self.image_dim[2]
         self._handle = ctypes.c_void_p(0)
         self._ws = None
-        desc = dgan_desc(1, ARCH_IDS[arch], self.latent_dim, self.net_dim, int(bool(use_bn)), PRECISIONS[precision])
+        desc = dgan_desc(ABI_VERSION, ARCH_IDS[arch], self.latent_dim, self.net_dim, int(bool(use_bn)), PRECISIONS[precision])
         with torch.cuda.device(self.device):
-            # the handle keeps pointers into (some of) the caller's weights: keep them alive
-            self._weights = [_require_cuda_f32(w.to(self.device), "weight") for w in weights]
+            # the handle copies the weights (on `stream`): they only have to outlive those copies
+            ws = [_require_cuda_f32(w.to(self.device), "weight") for w in weights]
             n_expected = self.lib.dgan_num_weights(ctypes.byref(desc))
-            if len(self._weights) != n_expected:
-                raise ValueError("expected %d weight tensors, got %d" % (n_expected, len(self._weights)))
-            arr = (ctypes.c_void_p * len(self._weights))(*[w.data_ptr() for w in self._weights])
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            if len(ws) != n_expected:
+                raise ValueError("expected %d weight tensors, got %d" % (n_expected, len(ws)))
+            arr = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+            stream = torch.cuda.current_stream(self.device)
             h = ctypes.c_void_p(0)
-            _check(self.lib, self.lib.dgan_create(ctypes.byref(h), ctypes.byref(desc), arr, len(self._weights),
-                                                  ctypes.c_void_p(stream)), "dgan_create")
+            _check(self.lib, self.lib.dgan_create(ctypes.byref(h), ctypes.byref(desc), arr, len(ws),
+                                                  ctypes.c_void_p(stream.cuda_stream)), "dgan_create")
             self._handle = h
+            stream.synchronize()
+            del ws
 
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:
@@ -178,6 +195,10 @@ class NativeGenerator:
         if need == 0:
             raise RuntimeError("dgan_workspace_bytes returned 0 (invalid batch / rec_rr)")
         if self._ws is None or self._ws.numel() < need + 1024:
+            if self._ws is not None:
+                # earlier calls (possibly on other streams) may still use the old block: let them finish before the
+                # caching allocator can hand it to somebody else
+                torch.cuda.synchronize(self.device)
             self._ws = None
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
         base = self._ws.data_ptr()
@@ -208,7 +229,8 @@ class NativeGenerator:
     # -- entry points ----------------------------------------------------------------------
     def reconstruct(self, images: torch.Tensor, rec_rr: int, rec_iters: int, rec_lr: float = 10.0,
                     z_init_val: Optional[torch.Tensor] = None, seed: int = 0, momentum: float = 0.7,
-                    decay_lr: bool = False, out: Optional[torch.Tensor] = None, return_aux: bool = False):
+                    decay_lr: bool = False, out: Optional[torch.Tensor] = None, return_aux: bool = False,
+                    z_row_offset: int = 0):
         x = _require_cuda_f32(images, "images")
         batch = x.shape[0]
         if x.numel() != batch * self.hwc:
@@ -228,14 +250,26 @@ class NativeGenerator:
             idx = torch.empty(batch, dtype=torch.int32, device=self.device)
             ws, need = self._workspace(batch, rec_rr)
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            rc = self.lib.dgan_reconstruct(self._handle, _ptr(x), _ptr(z0), ctypes.c_uint64(seed & (2 ** 64 - 1)), batch,
-                                           rec_rr, rec_iters, float(rec_lr), float(momentum), int(bool(decay_lr)),
-                                           _ptr(rec), _ptr(loss), _ptr(idx), ws, need, ctypes.c_void_p(stream))
+            prm = dgan_rec_params(batch, int(rec_rr), int(rec_iters), float(rec_lr), float(momentum), int(bool(decay_lr)),
+                                  seed & (2 ** 64 - 1), int(z_row_offset))
+            rc = self.lib.dgan_reconstruct(self._handle, ctypes.byref(prm), _ptr(x), _ptr(z0), _ptr(rec), _ptr(loss),
+                                           _ptr(idx), ws, need, ctypes.c_void_p(stream))
             _check(self.lib, rc, "dgan_reconstruct")
         rec = rec.view(images.shape) if out is None else rec
         if return_aux:
             return rec, loss, idx
         return rec
+
+    def sample_z0(self, n_rows: int, seed: int, z_row_offset: int = 0) -> torch.Tensor:
+        """Rows [z_row_offset, z_row_offset + n_rows) of the N(0, 1/latent_dim) Philox stream `seed` - the z0 that
+        reconstruct(..., z_init_val=None, seed=seed) starts from (reference models/gan.py:370-377)."""
+        with torch.cuda.device(self.device):
+            z = torch.empty(int(n_rows), self.latent_dim, dtype=torch.float32, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _check(self.lib, self.lib.dgan_sample_z0(self._handle, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                                     ctypes.c_uint64(int(z_row_offset)), int(n_rows), _ptr(z),
+                                                     ctypes.c_void_p(stream)), "dgan_sample_z0")
+        return z
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         zc = _require_cuda_f32(z, "z")

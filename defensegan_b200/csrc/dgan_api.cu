@@ -327,7 +327,7 @@ template <typename TIN>
 static int launch_final_fwd(dgan_ctx* c, const TIN* hin, const Workspace& w, const float* x, int R, int B,
                             bool want_grad, cudaStream_t s) {
   const FinalLayer& f = c->fin;
-  dim3 grid(f.n_bands, w.n_rows), block(128);
+  dim3 grid(w.n_rows, f.n_bands), block(128);
   const size_t smem = f.fwd_smem;
   float* dpre = want_grad ? w.dpre : nullptr;
   float* lp = x ? w.loss_part : nullptr;
@@ -573,6 +573,20 @@ static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, co
   return tc_launch(c->tc, &c->launches, w1, in, out, n_pad, epi, bias, mask_src, 1.f, s);
 }
 
+// element counts of the weight tensors in creation order (include/defensegan_b200.h, dgan_num_weights)
+static std::vector<size_t> weight_counts(const dgan_desc* d) {
+  const size_t nd = (size_t)d->net_dim, latent = (size_t)d->latent_dim, feat = 16 * 4 * nd;
+  std::vector<size_t> n = {latent * feat, feat};
+  if (d->use_bn) { n.push_back(feat); n.push_back(feat); }
+  std::vector<std::pair<size_t, size_t>> dc = {{4 * nd, 2 * nd}, {2 * nd, nd}};
+  if (d->arch == DGAN_ARCH_CELEBA) { dc.push_back({nd, nd}); dc.push_back({nd, 3}); } else dc.push_back({nd, 1});
+  for (size_t i = 0; i < dc.size(); ++i) {
+    n.push_back(25 * dc[i].first * dc[i].second); n.push_back(dc[i].second);
+    if (d->use_bn && i < 2) { n.push_back(dc[i].second); n.push_back(dc[i].second); }
+  }
+  return n;
+}
+
 static float grad_multiplier(const dgan_ctx* c) {
   float m = 2.0f / (float)c->hwc;  // d/dy mean_{HWC}(y-x)^2
   if (c->desc.precision == DGAN_PREC_FP16) m /= c->tc.grad_scale;
@@ -595,36 +609,32 @@ int dgan_num_weights(const dgan_desc* d) {
   return 2 + 2 * n_deconv + (d->use_bn ? 6 : 0);
 }
 
-int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weights, int n_weights, void* stream) {
-  if (out == nullptr || d == nullptr || weights == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
-  *out = nullptr;
-  if (d->abi_version != DGAN_ABI_VERSION) { set_error("ABI version mismatch"); return DGAN_ERR_INVALID_ARG; }
-  if (d->arch != DGAN_ARCH_MNIST && d->arch != DGAN_ARCH_CELEBA) { set_error("unknown arch"); return DGAN_ERR_INVALID_ARG; }
-  if (d->precision != DGAN_PREC_FP32 && d->precision != DGAN_PREC_FP16) { set_error("unknown precision"); return DGAN_ERR_INVALID_ARG; }
-  if (d->use_bn && d->precision != DGAN_PREC_FP32) {
-    set_error("use_bn=True (batch-statistics BatchNorm, tflib/ops/batchnorm.py:80-93) is built for precision fp32 only");
-    return DGAN_ERR_UNSUPPORTED;
-  }
-  if (d->net_dim <= 0 || d->net_dim % 64 != 0) { set_error("net_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
-  if (d->latent_dim <= 0 || d->latent_dim % 64 != 0) { set_error("latent_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
-  if (n_weights != dgan_num_weights(d)) { set_error("wrong number of weight tensors"); return DGAN_ERR_INVALID_ARG; }
-  for (int i = 0; i < n_weights; ++i)
-    if (weights[i] == nullptr) { set_error("NULL weight pointer"); return DGAN_ERR_INVALID_ARG; }
-  int dev_major = 0, dev = 0;
-  DGAN_CUDA_CHECK(cudaGetDevice(&dev));
-  DGAN_CUDA_CHECK(cudaDeviceGetAttribute(&dev_major, cudaDevAttrComputeCapabilityMajor, dev));
-  if (dev_major != 10) { set_error("defensegan_b200 requires an sm_100 (B200) device"); return DGAN_ERR_UNSUPPORTED; }
-
-  cudaStream_t s = (cudaStream_t)stream;
-  std::unique_ptr<dgan_ctx> c(new (std::nothrow) dgan_ctx());
-  if (!c) { set_error("out of host memory"); return DGAN_ERR_INVALID_ARG; }
+static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weights_in, cudaStream_t s) {
   c->desc = *d;
   const bool celeba = d->arch == DGAN_ARCH_CELEBA;
   const int nd = d->net_dim, latent = d->latent_dim;
   c->H = celeba ? 64 : 28; c->W = c->H; c->C = celeba ? 3 : 1;
   c->hwc = c->H * c->W * c->C;
   int rc = 0;
-  auto fail = [&](int code) { dgan_destroy(c.release()); return code; };
+  auto fail = [](int code) { return code; };   // the caller destroys the half-built handle
+  // The handle owns copies of every weight tensor: the caller may free or reuse `weights_dev` as soon as the
+  // copies enqueued here have run (i.e. after synchronising `stream`).
+  std::vector<const float*> wown;
+  {
+    const std::vector<size_t> counts = weight_counts(d);
+    size_t total = 0;
+    for (size_t n : counts) total += align_up(n * sizeof(float), 256);
+    char* base = nullptr;
+    if ((rc = dev_alloc(c, (void**)&base, total))) return fail(rc);
+    size_t off = 0;
+    for (size_t i = 0; i < counts.size(); ++i) {
+      cudaError_t e = cudaMemcpyAsync(base + off, weights_in[i], counts[i] * sizeof(float), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) { set_error(std::string("weight copy: ") + cudaGetErrorString(e)); return fail(DGAN_ERR_CUDA); }
+      wown.push_back((const float*)(base + off));
+      off += align_up(counts[i] * sizeof(float), 256);
+    }
+  }
+  const float* const* weights = wown.data();
 
   // ---- Linear (Generator.Input): [1][N][latent] -> [16][N][4*nd]
   {
@@ -635,7 +645,7 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     const float* W = weights[0];             // (latent, 16*4nd), column f = pixel*4nd + c
     L.wf = W; L.wf_tile_stride = L.C_out; L.wf_ld = 16 * L.C_out;
     float* Wt = nullptr;                     // [16*4nd][latent]: backward tile q rows = c, cols = latent
-    if ((rc = dev_alloc(c.get(), (void**)&Wt, (size_t)latent * 16 * L.C_out * 4))) return fail(rc);
+    if ((rc = dev_alloc(c, (void**)&Wt, (size_t)latent * 16 * L.C_out * 4))) return fail(rc);
     const size_t total = (size_t)latent * 16 * L.C_out;
     transpose_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, Wt, latent, 16 * L.C_out, total);
     L.wb = Wt; L.wb_tile_stride = L.C_out * latent; L.wb_ld = latent;
@@ -661,7 +671,7 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     const float* F = weights[wi];            // (5,5,C_out,C_in)
     float* Ff = nullptr;                     // [25][C_in][C_out]
     const size_t total = (size_t)kTaps * sp.c_out * sp.c_in;
-    if ((rc = dev_alloc(c.get(), (void**)&Ff, total * 4))) return fail(rc);
+    if ((rc = dev_alloc(c, (void**)&Ff, total * 4))) return fail(rc);
     transpose_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(F, Ff, sp.c_out, sp.c_in, total);
     L.wf = Ff; L.wf_tile_stride = sp.c_in * sp.c_out; L.wf_ld = sp.c_out;
     L.wb = F;  L.wb_tile_stride = sp.c_in * sp.c_out; L.wb_ld = sp.c_in;
@@ -691,8 +701,8 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     c->macs_per_row += (int64_t)ft.pairs.size() * c->fin.C_in * c->fin.C_out;
   }
   for (GemmLayer& L : c->layers) {
-    if ((rc = upload_table(c.get(), L.fwd_host, &L.fwd, s))) return fail(rc);
-    if ((rc = upload_table(c.get(), L.bwd_host, &L.bwd, s))) return fail(rc);
+    if ((rc = upload_table(c, L.fwd_host, &L.fwd, s))) return fail(rc);
+    if ((rc = upload_table(c, L.bwd_host, &L.bwd, s))) return fail(rc);
   }
   // opt in to > 48 KB dynamic shared memory where needed
 #define OPTIN(K, BYTES) DGAN_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)))
@@ -725,7 +735,7 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     if (getenv("DGAN_MAX_PAIRS")) c->tc.max_pairs = atoi(getenv("DGAN_MAX_PAIRS"));
     if (getenv("DGAN_TC_DEBUG")) {   // developer aid: per-CTA role timing of the first launches (tools/tc_timing.py)
       c->tc.dbg_max_launches = 64;
-      if ((rc = dev_alloc(c.get(), (void**)&c->tc.dbg, (size_t)64 * 160 * 16 * sizeof(unsigned long long)))) return fail(rc);
+      if ((rc = dev_alloc(c, (void**)&c->tc.dbg, (size_t)64 * 160 * 16 * sizeof(unsigned long long)))) return fail(rc);
       DGAN_CUDA_CHECK(cudaMemsetAsync(c->tc.dbg, 0, (size_t)64 * 160 * 16 * sizeof(unsigned long long), s));
     }
     c->tc.allocs = &c->allocs;
@@ -779,7 +789,35 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
     c->kind_names.push_back("momentum"); c->kind_macs_per_row.push_back(0.0);
   }
   DGAN_CUDA_CHECK(cudaGetLastError());
-  *out = c.release();
+  return DGAN_OK;
+}
+
+
+int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weights, int n_weights, void* stream) {
+  if (out == nullptr || d == nullptr || weights == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
+  *out = nullptr;
+  if (d->abi_version != DGAN_ABI_VERSION) { set_error("ABI version mismatch"); return DGAN_ERR_INVALID_ARG; }
+  if (d->arch != DGAN_ARCH_MNIST && d->arch != DGAN_ARCH_CELEBA) { set_error("unknown arch"); return DGAN_ERR_INVALID_ARG; }
+  if (d->precision != DGAN_PREC_FP32 && d->precision != DGAN_PREC_FP16) { set_error("unknown precision"); return DGAN_ERR_INVALID_ARG; }
+  if (d->use_bn && d->precision != DGAN_PREC_FP32) {
+    set_error("use_bn=True (batch-statistics BatchNorm, tflib/ops/batchnorm.py:80-93) is built for precision fp32 only");
+    return DGAN_ERR_UNSUPPORTED;
+  }
+  if (d->net_dim <= 0 || d->net_dim % 64 != 0) { set_error("net_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
+  if (d->latent_dim <= 0 || d->latent_dim % 64 != 0) { set_error("latent_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
+  if (n_weights != dgan_num_weights(d)) { set_error("wrong number of weight tensors"); return DGAN_ERR_INVALID_ARG; }
+  for (int i = 0; i < n_weights; ++i)
+    if (weights[i] == nullptr) { set_error("NULL weight pointer"); return DGAN_ERR_INVALID_ARG; }
+  int dev_major = 0, dev = 0;
+  DGAN_CUDA_CHECK(cudaGetDevice(&dev));
+  DGAN_CUDA_CHECK(cudaDeviceGetAttribute(&dev_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (dev_major != 10) { set_error("defensegan_b200 requires an sm_100 (B200) device"); return DGAN_ERR_UNSUPPORTED; }
+
+  dgan_ctx* c = new (std::nothrow) dgan_ctx();
+  if (c == nullptr) { set_error("out of host memory"); return DGAN_ERR_INVALID_ARG; }
+  const int rc = create_impl(c, d, weights, (cudaStream_t)stream);
+  if (rc != DGAN_OK) { dgan_destroy(c); return rc; }   // every failure path frees device memory, streams and events
+  *out = c;
   return DGAN_OK;
 }
 
@@ -852,10 +890,22 @@ int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, con
   return DGAN_OK;
 }
 
-int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uint64_t seed, int batch, int rec_rr,
-                     int rec_iters, float rec_lr, float momentum, int decay_lr, float* rec_dev, float* loss_dev,
-                     int32_t* idx_dev, void* ws, size_t ws_bytes, void* stream) {
-  if (h == nullptr || x_dev == nullptr || rec_dev == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
+int dgan_sample_z0(dgan_handle h, uint64_t seed, uint64_t z_row_offset, int n_rows, float* z_dev, void* stream) {
+  if (h == nullptr || z_dev == nullptr || n_rows <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
+  const int latent = h->desc.latent_dim;
+  const size_t total4 = (size_t)n_rows * latent / 4;
+  init_z_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z_dev, nullptr, nullptr, nullptr, n_rows, n_rows, latent, seed,
+                                                                                      sqrtf(1.0f / (float)latent), (size_t)z_row_offset * latent);
+  DGAN_LAUNCH_CHECK(h);
+  return DGAN_OK;
+}
+
+int dgan_reconstruct(dgan_handle h, const dgan_rec_params* prm, const float* x_dev, const float* z0_dev, float* rec_dev,
+                     float* loss_dev, int32_t* idx_dev, void* ws, size_t ws_bytes, void* stream) {
+  if (h == nullptr || prm == nullptr || x_dev == nullptr || rec_dev == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
+  const int batch = prm->batch, rec_rr = prm->rec_rr, rec_iters = prm->rec_iters, decay_lr = prm->decay_lr;
+  const float rec_lr = prm->rec_lr, momentum = prm->momentum;
+  const uint64_t seed = prm->seed;
   if (batch <= 0 || rec_rr <= 0 || rec_iters <= 0) { set_error("batch, rec_rr and rec_iters must be positive"); return DGAN_ERR_INVALID_ARG; }
   if (ws == nullptr) { set_error("workspace is NULL"); return DGAN_ERR_WORKSPACE; }
   if (((uintptr_t)ws & 1023) != 0) { set_error("workspace must be 1024-byte aligned"); return DGAN_ERR_WORKSPACE; }
@@ -887,7 +937,7 @@ int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uin
   }
   for (Chain& ch : chains) {
     const size_t row_off = (size_t)ch.lo * rec_rr;
-    if ((rc = run_init_z(h, ch.w, z0_dev ? z0_dev + row_off * latent : nullptr, seed, ch.s, row_off))) return rc;
+    if ((rc = run_init_z(h, ch.w, z0_dev ? z0_dev + row_off * latent : nullptr, seed, ch.s, (size_t)prm->z_row_offset + row_off))) return rc;
   }
   const int decay_iter = (int)std::ceil(rec_iters * 0.8);
   for (int t = 0; t < rec_iters; ++t) {

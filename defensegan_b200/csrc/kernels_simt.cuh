@@ -141,7 +141,7 @@ final_fwd_loss_kernel(const TIN* __restrict__ hin, int n_pad, int h_in, int w_in
   float* hs = smem_f + kTaps * C_OUT * C_in;           // [rows*w_in][ldh]
   __shared__ float red[4];
 
-  const int band = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const int band = blockIdx.y, n = blockIdx.x, tid = threadIdx.x;   // rows on grid.x: no 65535 limit
   const int w_out = 2 * w_in, h_out = 2 * h_in;
   const int i0 = band * kBandRows;
   const int o_lo = max(0, (i0 - 2) >> 1);
@@ -209,7 +209,7 @@ final_fwd_loss_kernel(const TIN* __restrict__ hin, int n_pad, int h_in, int w_in
     for (int s = 16; s > 0; s >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, s);
     if ((tid & 31) == 0) red[tid >> 5] = lsum;
     __syncthreads();
-    if (tid == 0) loss_part[(size_t)n * gridDim.x + band] = (red[0] + red[1]) + (red[2] + red[3]);
+    if (tid == 0) loss_part[(size_t)n * gridDim.y + band] = (red[0] + red[1]) + (red[2] + red[3]);
   }
 }
 
@@ -334,7 +334,7 @@ __global__ void init_z_kernel(float* __restrict__ z, float* __restrict__ v, __ha
     }
   }
   *reinterpret_cast<float4*>(z + e) = val;
-  *reinterpret_cast<float4*>(v + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (v != nullptr) *reinterpret_cast<float4*>(v + e) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (z_h != nullptr) store4(z_h + e, val);
 }
 

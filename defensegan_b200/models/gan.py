@@ -30,7 +30,63 @@ from .. import tf_bundle as _tf_bundle
 from .. import weights as _weights
 from ..utils.config import load_config, packaged_cfg_path
 
-__all__ = ["DefenseGANBase", "MnistDefenseGAN", "FmnistDefenseDefenseGAN", "CelebADefenseGAN", "dataset_gan_dict"]
+__all__ = ["RecCache", "DefenseGANBase", "MnistDefenseGAN", "FmnistDefenseDefenseGAN", "CelebADefenseGAN", "dataset_gan_dict"]
+
+
+class RecCache(object):
+    """On-disk cache of one split's reconstructions, in the reference's layout (models/gan.py:466-478,503-507) so that
+    its consumers (blackbox.py:249-259,294-329) keep working:
+
+        <dir>/feats.pkl                         the whole split, one pickled array (written by save_recs)
+        <dir>/pickles/rec_{index:07d}_l{label}.pkl   one pickled [H,W,C] array per image
+
+    `index` = position of the image in the split.  Unreadable or missing entries simply count as misses (the reference
+    tolerates broken cache files the same way, gan.py:486-496,526-534)."""
+
+    def __init__(self, directory, reuse=True):
+        self.directory = directory
+        self.reuse = reuse
+        self.pickle_dir = os.path.join(directory, 'pickles')
+        os.makedirs(self.pickle_dir, exist_ok=True)
+
+    @property
+    def split_path(self):
+        return os.path.join(self.directory, 'feats.pkl')
+
+    def image_path(self, index, label):
+        return os.path.join(self.pickle_dir, 'rec_{:07d}_l{}.pkl'.format(int(index), label))
+
+    @staticmethod
+    def _read(path):
+        try:
+            with open(path, 'rb') as f:
+                return pickle.load(f)
+        except Exception:
+            return None
+
+    def load_split(self):
+        return self._read(self.split_path) if self.reuse else None
+
+    def load_batch(self, first_index, labels):
+        """The batch's reconstructions if EVERY image of it is cached, else None."""
+        if not self.reuse:
+            return None
+        out = []
+        for i, label in enumerate(labels):
+            r = self._read(self.image_path(first_index + i, label))
+            if r is None:
+                return None
+            out.append(r)
+        return np.stack(out) if out else None
+
+    def store_batch(self, first_index, labels, recs):
+        for i, label in enumerate(labels):
+            with open(self.image_path(first_index + i, label), 'wb') as f:
+                pickle.dump(recs[i], f, protocol=pickle.HIGHEST_PROTOCOL)
+
+    def store_split(self, recs):
+        with open(self.split_path, 'wb') as f:
+            pickle.dump(recs, f, pickle.HIGHEST_PROTOCOL)
 
 
 class DefenseGANBase(object):
@@ -110,8 +166,24 @@ class DefenseGANBase(object):
             self.image_dim = [int(v) if v is not None else None for v in self.image_dim]
 
     def _set_checkpoint_dir(self):
-        # reference models/base_model.py:197-232: <output_dir>/gans/<dataset_name>
-        self.checkpoint_dir = os.path.join(str(self.output_dir), "gans", str(self.dataset_name))
+        """Where the model's snapshots live (reference models/base_model.py:197-232, test-mode branch): the directory
+        of an experiment's own `cfg.yml`, else `<output_dir>/<cfg path relative to experiments/cfgs, without .yml>`
+        (`experiments/cfgs/gans/mnist.yml` -> `output/gans/mnist`).  The packaged cfgs map the same way."""
+        cfg_file = str((self.cfg or {}).get('cfg_path', '') or '')
+        if os.path.basename(cfg_file) == 'cfg.yml':
+            self.checkpoint_dir = os.path.dirname(cfg_file)
+            return
+        rel = None
+        norm = cfg_file.replace(os.sep, '/')
+        for marker in ('experiments/cfgs/', '/cfgs/'):
+            if marker in norm:
+                rel = norm.split(marker)[-1]
+                break
+        if rel is None:
+            rel = os.path.join('gans', str(self.dataset_name))
+        if rel.endswith('.yml'):
+            rel = rel[:-4]
+        self.checkpoint_dir = os.path.join(str(self.output_dir), rel)
 
     def _build(self):
         # reference models/gan.py:101-105
@@ -141,6 +213,11 @@ class DefenseGANBase(object):
         Returns False (and keeps the random-init weights, like the reference's failed restore,
         base_model.py:312-317) when nothing is found."""
         path = ckpt_path if ckpt_path is not None else self.checkpoint_dir
+        for suffix in ('.index', '.meta'):                       # a bundle's file name instead of its prefix
+            if path.endswith(suffix):
+                path = path[:-len(suffix)]
+        if '.data-' in os.path.basename(path):
+            path = path[:path.rindex('.data-')]
         npz, prefix = None, None
         if os.path.isdir(path):
             if os.path.isfile(os.path.join(path, "generator.npz")):
@@ -156,8 +233,14 @@ class DefenseGANBase(object):
         elif prefix is not None:
             self.set_generator_weights(_tf_bundle.read_generator_variables(prefix))
         else:
-            if self.verbose:
-                print("[-] No generator checkpoint found at {}; keeping random-init weights".format(path))
+            msg = "[-] No generator checkpoint found at {}; keeping random-init weights".format(path)
+            if self.test_mode:
+                # the reference's callers ignore the return value (blackbox.py:640-642): projecting onto an untrained
+                # generator must not pass silently
+                import warnings
+                warnings.warn(msg, RuntimeWarning, stacklevel=2)
+            elif self.verbose:
+                print(msg)
             return False
         if self.verbose:
             print("[*] Generator restored from {}".format(npz or prefix))
@@ -221,14 +304,20 @@ class DefenseGANBase(object):
             t = t.cuda(non_blocking=True)
         return t.to(torch.float32)
 
+    def _next_seed(self, reconstructor_id=0):
+        """Philox key of the next call's z0 stream (fresh per call, like re-running the initialiser, gan_defense.py:119)."""
+        self._call_counter += 1
+        return (int(self.seed) * 1000003 + int(reconstructor_id) * 7919 + self._call_counter) & (2 ** 63 - 1)
+
     def reconstruct(self, images, batch_size=None, back_prop=True, reconstructor_id=0, z_init_val=None,
-                    return_aux=False, out=None):
+                    return_aux=False, out=None, z_row_offset=0):
         """Defense-GAN projection of `images` onto the generator's range (reference
         models/gan.py:333-449): rec_rr restarts x rec_iters momentum-GD steps on
         ||G(z) - x||^2, returns G(z) of the min-loss restart.  Hyper-parameters are read from the
         object at call time.  Fresh z0 ~ N(0, 1/latent_dim) and zero momentum on every call
         (utils/gan_defense.py:119) unless `z_init_val` [B*rec_rr, latent_dim] is given
-        (models/gan.py:395-397)."""
+        (models/gan.py:395-397).  `z_row_offset` (sharded callers only): index of the first latent row of `images`
+        in the call's z0 stream, so that a batch split over several GPUs draws what one GPU would."""
         x = self._as_cuda(images)
         if x.dim() != 4 or list(x.shape[1:]) != list(self.image_dim):
             raise ValueError("images must be [B,%d,%d,%d], got %s" % (tuple(self.image_dim) + (tuple(x.shape),)))
@@ -236,11 +325,10 @@ class DefenseGANBase(object):
             raise ValueError("batch_size (%d) does not match images.shape[0] (%d)" % (int(batch_size), x.shape[0]))
         z0 = self._as_cuda(z_init_val) if z_init_val is not None else None
         native = self._get_native(x.device)
-        self._call_counter += 1
-        seed = (int(self.seed) * 1000003 + int(reconstructor_id) * 7919 + self._call_counter) & (2 ** 63 - 1)
+        self.last_seed = seed = self._next_seed(reconstructor_id)
         res = native.reconstruct(x, int(self.rec_rr), int(self.rec_iters), float(self.rec_lr), z_init_val=z0, seed=seed,
                                  momentum=float(self.rec_momentum), decay_lr=bool(self.rec_decay_lr), out=out,
-                                 return_aux=return_aux)
+                                 return_aux=return_aux, z_row_offset=int(z_row_offset))
         return res
 
     # -- bulk offline reconstruction + its on-disk cache (reference models/gan.py:451-587, 604-646) --------------
@@ -275,87 +363,54 @@ class DefenseGANBase(object):
         return x
 
     def reconstruct_dataset(self, ckpt_path=None, max_num=-1, max_num_load=-1):
-        """Reconstructs the train/dev/test splits batch by batch, with the reference's per-image pickle
-        cache `pickles/rec_{idx:07d}_l{label}.pkl` and whole-split `feats.pkl`.  Returns
-        `{split: [all_recs, all_targets, orig_imgs]}` (numpy, images `[-1] + image_dim`)."""
+        """Projects the train/dev/test splits batch by batch (fresh z0 and zero momentum per batch, reference
+        models/gan.py:541) behind the reference's two-level result cache (see `RecCache`).  Returns
+        `{split: [all_recs, all_targets, orig_imgs]}` (numpy, images `[-1] + image_dim`), the reference's return value
+        (models/gan.py:451-587)."""
         if not self.initialized:
             self.load_generator(ckpt_path=ckpt_path)
-        rets = {}
-        for split in ['train', 'dev', 'test']:
-            gen_func = getattr(self, '{}_gen_test'.format(split), None)
-            if gen_func is None:
+        limit = max(max_num, max_num_load)
+        shape = [-1] + list(self.image_dim)
+        results = {}
+        for split in ('train', 'dev', 'test'):
+            batches = getattr(self, split + '_gen_test', None)
+            if batches is None:
                 raise RuntimeError("no '{}_gen_test' generator bound: call set_dataset_generators(...) first "
                                    "(dataset readers are outside this package)".format(split))
-            output_dir = self.rec_cache_dir(split, max_num)
-            os.makedirs(output_dir, exist_ok=True)
-            feats_path = os.path.join(output_dir, 'feats.pkl')
-            could_load = False
-            all_recs = []
-            try:
-                if os.path.exists(feats_path) and not self.test_again:
-                    with open(feats_path, 'rb') as f:
-                        all_recs = pickle.load(f)
-                        could_load = True
-                        if self.verbose:
-                            print('[#] Successfully loaded features.')
-            except Exception as e:  # same tolerance as the reference (gan.py:486-496)
-                all_recs = []
-                print('[#] Exception loading features {}'.format(str(e)))
-            all_targets, orig_imgs = [], []
-            ctr = 0
-            sti = time.time()
-            pickle_out_dir = os.path.join(output_dir, 'pickles')
-            os.makedirs(pickle_out_dir, exist_ok=True)
-            template = os.path.join(pickle_out_dir, 'rec_{:07d}_l{}.pkl')
-            for images, targets in gen_func():
-                batch_size = len(images)
-                im_paths = [template.format(ctr * batch_size + i, targets[i]) for i in range(batch_size)]
-                mn = max(max_num, max_num_load)
-                if (mn > -1 and ctr * batch_size > mn) or (self.debug and ctr > 2):
+            cache = RecCache(self.rec_cache_dir(split, max_num), reuse=not self.test_again)
+            whole_split = cache.load_split()
+            recs, targets, originals = [], [], []
+            t_start = time.time()
+            for b, (images, labels) in enumerate(batches()):
+                n = len(images)
+                if (limit > -1 and b * n > limit) or (self.debug and b > 2):
                     break
-                batch_could_load = not self.test_again
-                batch_rec_list = []
-                if batch_could_load:
-                    for imp in im_paths:            # per-image cache
-                        try:
-                            with open(imp, 'rb') as f:
-                                batch_rec_list.append(pickle.load(f))
-                        except Exception:
-                            batch_could_load = False
-                            break
                 x = self._transformed_batch(images)
-                recs = None
-                if batch_could_load and not could_load:
-                    recs = np.stack(batch_rec_list)
-                    all_recs.append(recs)
-                if not (could_load or batch_could_load):
-                    recs = self.reconstruct(x).detach().cpu().numpy()      # fresh z0 / momentum per batch (gan.py:541)
-                    if self.verbose:
-                        print('[#] t:{:.2f} batch: {:d} '.format(time.time() - sti, ctr))
-                    all_recs.append(recs)
-                    for i in range(len(recs)):
-                        with open(im_paths[i], 'wb') as f:
-                            pickle.dump(recs[i], f, protocol=pickle.HIGHEST_PROTOCOL)
-                elif self.verbose:
-                    print('[*] could load batch: {:d}'.format(ctr))
-                all_targets.append(np.asarray(targets))
-                orig_imgs.append(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x))
-                ctr += 1
-            if not could_load:
-                all_recs = np.concatenate(all_recs).reshape([-1] + list(self.image_dim)) if all_recs else \
-                    np.zeros([0] + list(self.image_dim), dtype=np.float32)
-            orig_imgs = np.concatenate(orig_imgs).reshape([-1] + list(self.image_dim)) if orig_imgs else \
-                np.zeros([0] + list(self.image_dim), dtype=np.float32)
-            all_targets = np.concatenate(all_targets) if all_targets else np.zeros([0], dtype=np.int64)
-            rets[split] = [all_recs, all_targets, orig_imgs]
-        return rets
+                if whole_split is None:
+                    r = cache.load_batch(b * n, labels)
+                    if r is None:
+                        r = self.reconstruct(x).detach().cpu().numpy()
+                        cache.store_batch(b * n, labels, r)
+                        if self.verbose:
+                            print('[rec] {} batch {:d}: projected in {:.2f} s'.format(split, b, time.time() - t_start))
+                    recs.append(r)
+                targets.append(np.asarray(labels))
+                originals.append(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x))
+            empty = np.zeros([0] + list(self.image_dim), dtype=np.float32)
+            if whole_split is not None:
+                all_recs = whole_split
+            else:
+                all_recs = np.concatenate(recs).reshape(shape) if recs else empty
+            results[split] = [all_recs,
+                              np.concatenate(targets) if targets else np.zeros([0], dtype=np.int64),
+                              np.concatenate(originals).reshape(shape) if originals else empty]
+        return results
 
     def save_recs(self, rets: Dict, max_num: int = -1) -> None:
-        """Write `feats.pkl` for each split so that the next reconstruct_dataset (and the callers' cache
-        loaders, blackbox.py:249-259,294-329) short-cut.  The reference leaves this to train.py --save_recs."""
-        for split, (all_recs, all_targets, orig_imgs) in rets.items():
-            with open(os.path.join(self.rec_cache_dir(split, max_num), 'feats.pkl'), 'wb') as f:
-                pickle.dump(all_recs, f, pickle.HIGHEST_PROTOCOL)
+        """Write each split's `feats.pkl` so that the next reconstruct_dataset (and the callers' cache loaders,
+        blackbox.py:249-259,294-329) short-cut.  The reference leaves this to train.py --save_recs."""
+        for split, (all_recs, _, _) in rets.items():
+            RecCache(self.rec_cache_dir(split, max_num)).store_split(all_recs)
 
     def save_ds(self):
         """Dump the input-transformed dataset: `data/cache/<dataset>_pkl/<split>/feats.pkl` holding two

@@ -28,7 +28,7 @@ def shard_bounds(n_images: int, world_size: int) -> List[int]:
 
 def sharded_apply(local_fn: Callable, images: torch.Tensor, rec_rr: int, z_init_val: Optional[torch.Tensor] = None,
                   group=None) -> torch.Tensor:
-    """Run `local_fn(images_shard, z0_shard, out_view)` on this rank's shard and all-gather.
+    """Run `local_fn(images_shard, z0_shard, out_view, first_image)` on this rank's shard and all-gather.
 
     `local_fn` must write its [b_local, ...] result into `out_view` (a view of the gather
     buffer).  `images` (and `z_init_val` [B*rec_rr, latent]) hold the FULL batch on every rank.
@@ -42,11 +42,13 @@ def sharded_apply(local_fn: Callable, images: torch.Tensor, rec_rr: int, z_init_
     per = max(bounds[i + 1] - bounds[i] for i in range(world))      # slot size (ragged tail padded)
     row = images[0].numel()
     gather = torch.empty((world, per) + tuple(images.shape[1:]), dtype=images.dtype, device=images.device)
+    if hi <= lo and hasattr(local_fn, "skip"):
+        local_fn.skip()
     if hi > lo:
         z0 = None
         if z_init_val is not None:
             z0 = z_init_val.reshape(n * rec_rr, -1)[lo * rec_rr:hi * rec_rr]
-        local_fn(images[lo:hi], z0, gather[rank, :hi - lo])
+        local_fn(images[lo:hi], z0, gather[rank, :hi - lo], lo)
     if hi - lo < per:
         gather[rank, hi - lo:].zero_()
     if world > 1:
@@ -59,12 +61,16 @@ def sharded_apply(local_fn: Callable, images: torch.Tensor, rec_rr: int, z_init_
 
 def reconstruct_sharded(gan, images: torch.Tensor, z_init_val: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
     """gan.reconstruct over all ranks of `group` (NCCL): identical to the single-GPU result
-    row for row (no BatchNorm)."""
+    row for row (no BatchNorm), with `z_init_val` given or drawn (the shards index one common z0 stream).
+    Ranks with an empty shard still advance the call counter so that later calls stay in step."""
     if bool(gan.use_bn):
         raise RuntimeError("use_bn=True couples all latent rows through batch statistics (SURVEY F2); "
                            "sharding the batch would change the result - run replicas instead")
 
-    def local_fn(x, z0, out_view):
-        gan.reconstruct(x, z_init_val=z0, out=out_view)
+    # every rank advances the model's call counter identically, so all shards draw from ONE Philox stream; the shard's
+    # first row in that stream is (first image) * rec_rr: row for row the single-GPU draw
+    def local_fn(x, z0, out_view, first_image):
+        gan.reconstruct(x, z_init_val=z0, out=out_view, z_row_offset=first_image * int(gan.rec_rr))
 
+    local_fn.skip = gan._next_seed      # a rank without images must still consume this call's seed
     return sharded_apply(local_fn, images, int(gan.rec_rr), z_init_val=z_init_val, group=group)

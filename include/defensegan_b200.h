@@ -6,8 +6,8 @@
  * utils/gan_defense.py:32-179.  This header is the C-ABI that sits directly underneath that
  * Python surface; each entry point cites the reference lines it replaces.
  * Plain pointers and sizes only - no torch types.  All device pointers are owned by the
- * caller; the handle owns only its re-laid-out weight copies.  Nothing is freed across the
- * boundary.  No function synchronises the host: work is enqueued on `stream`.
+ * caller; the handle owns its own copies of the weights (plain and re-laid-out), so the tensors passed
+ * to dgan_create may be freed once `stream` has run the copies.  Nothing is freed across the boundary.  No function synchronises the host: work is enqueued on `stream`.
  *
  * Every function returns 0 on success, a negative dgan_status otherwise; the message is
  * available (thread-local) from dgan_last_error().  No C++ exception crosses the boundary.
@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DGAN_ABI_VERSION 1
+#define DGAN_ABI_VERSION 2
 
 typedef struct dgan_ctx* dgan_handle;
 
@@ -65,8 +65,8 @@ typedef struct dgan_desc {
 int dgan_num_weights(const dgan_desc* desc);
 
 /* Replaces DefenseGANBase.load_generator + the tflib.param registry (models/gan.py:80-87,
- * tflib/__init__.py:7-33): uploads nothing (weights are already on the device) but builds the
- * handle's re-laid-out copies (per-tap tiles, transposes, fp16 copies) on `stream`. */
+ * tflib/__init__.py:7-33): copies the device-resident weights into handle-owned memory and builds the
+ * re-laid-out forms (per-tap tiles, transposes, fp16 copies) and the launch schedules on `stream`. */
 int dgan_create(dgan_handle* out, const dgan_desc* desc, const float* const* weights_dev,
                 int n_weights, void* stream);
 int dgan_destroy(dgan_handle h);
@@ -75,20 +75,39 @@ int dgan_destroy(dgan_handle h);
  * for `batch` images x `rec_rr` restarts. */
 size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr);
 
+/* Hyper-parameters of one projection call: the attributes DefenseGANBase.reconstruct reads from the model object at
+ * call time (models/gan.py:333-349: rec_rr, rec_iters, rec_lr) plus the optimiser constant of gan.py:389-391. */
+typedef struct dgan_rec_params {
+  int32_t batch;          /* images in x_dev */
+  int32_t rec_rr;         /* R: random restarts per image (REC_RR, mnist.yml:7) */
+  int32_t rec_iters;      /* L: gradient steps (REC_ITERS, mnist.yml:5) */
+  float rec_lr;           /* constant: the reference's decay is dead code */
+  float momentum;         /* 0.7 in the reference (gan.py:389-391) */
+  int32_t decay_lr;       /* 0 = reference behaviour; 1 = the evidently intended x0.1 from step ceil(0.8 L) */
+  uint64_t seed;          /* Philox key of the z0 stream when z0_dev == NULL */
+  uint64_t z_row_offset;  /* index of this call's first latent row in that stream: a caller that shards one batch over
+                             several GPUs passes (first image of the shard) * rec_rr so that the draw equals the
+                             single-GPU draw row for row; 0 otherwise */
+} dgan_rec_params;
+
 /* Replaces one sess.run of the op built by DefenseGANBase.reconstruct (models/gan.py:333-449)
  * preceded by tf.local_variables_initializer() (utils/gan_defense.py:119):
  *   x_dev     [batch, H, W, C] fp32 NHWC, already input-transformed
  *   z0_dev    [batch*rec_rr, latent] fp32 (the reference's z_init_val, gan.py:395-397) or NULL:
- *             z0 ~ N(0, 1/latent) from a Philox stream keyed by `seed` (gan.py:370-377)
- *   rec_iters L, rec_lr (constant: the reference's decay is dead code), momentum 0.7
+ *             z0 ~ N(0, 1/latent) from the Philox stream (seed, z_row_offset) (gan.py:370-377)
  *   rec_dev   [batch, H, W, C] fp32: G(z_{L-1}) of the arg-min restart (gan.py:438-449)
  *   loss_dev  [batch] fp32 min per-image MSE, nullable;  idx_dev [batch] int32 chosen restart, nullable
- *   decay_lr  0 = reference behaviour; 1 = intended x0.1 at ceil(0.8 L) (off by default)
- * The whole L-step loop is enqueued on `stream` with no host synchronisation. */
-int dgan_reconstruct(dgan_handle h, const float* x_dev, const float* z0_dev, uint64_t seed,
-                     int batch, int rec_rr, int rec_iters, float rec_lr, float momentum,
-                     int decay_lr, float* rec_dev, float* loss_dev, int32_t* idx_dev,
+ * The whole L-step loop runs on the device: the call enqueues a constant number of kernels on `stream`
+ * (independent of rec_iters) and never synchronises the host. */
+int dgan_reconstruct(dgan_handle h, const dgan_rec_params* params, const float* x_dev,
+                     const float* z0_dev, float* rec_dev, float* loss_dev, int32_t* idx_dev,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* The z_hat initialiser alone (models/gan.py:370-377): z_dev [n_rows, latent] ~ N(0, 1/latent), rows
+ * [z_row_offset, z_row_offset + n_rows) of the Philox stream keyed by `seed` - exactly what dgan_reconstruct
+ * draws when z0_dev == NULL. */
+int dgan_sample_z0(dgan_handle h, uint64_t seed, uint64_t z_row_offset, int n_rows, float* z_dev,
+                   void* stream);
 
 /* generator_fn(z) (models/gan.py:657-665,726-735): y_dev [n_rows, H*W*C] fp32. */
 int dgan_forward(dgan_handle h, const float* z_dev, int n_rows, float* y_dev, void* workspace,

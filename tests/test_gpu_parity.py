@@ -180,13 +180,17 @@ def test_error_paths_through_c_abi(gens):
     rec = torch.empty_like(x)
     small = torch.empty(4096, dtype=torch.uint8, device="cuda")
     base = (small.data_ptr() + 1023) // 1024 * 1024
-    rc = lib.dgan_reconstruct(gen._handle, x.data_ptr(), None, 0, 2, 2, 3, 10.0, 0.7, 0, rec.data_ptr(), None, None,
+    prm = _native.dgan_rec_params(2, 2, 3, 10.0, 0.7, 0, 0, 0)
+    rc = lib.dgan_reconstruct(gen._handle, ctypes.byref(prm), x.data_ptr(), None, rec.data_ptr(), None, None,
                               ctypes.c_void_p(base), 1024, None)
     assert rc == -4 and b"workspace" in lib.dgan_last_error()
-    rc = lib.dgan_reconstruct(gen._handle, x.data_ptr(), None, 0, 0, 2, 3, 10.0, 0.7, 0, rec.data_ptr(), None, None,
+    prm.batch = 0
+    rc = lib.dgan_reconstruct(gen._handle, ctypes.byref(prm), x.data_ptr(), None, rec.data_ptr(), None, None,
                               ctypes.c_void_p(base), 1024, None)
     assert rc == -1
-    d = _native.dgan_desc(1, 0, 128, 64, 1, 1)     # use_bn with fp16 operands: explicit UNSUPPORTED, no fallback
+    assert lib.dgan_reconstruct(gen._handle, None, x.data_ptr(), None, rec.data_ptr(), None, None,
+                                ctypes.c_void_p(base), 1024, None) == -1
+    d = _native.dgan_desc(_native.ABI_VERSION, 0, 128, 64, 1, 1)     # use_bn with fp16 operands: explicit UNSUPPORTED, no fallback
     h = ctypes.c_void_p(0)
     arr = (ctypes.c_void_p * 14)(*([x.data_ptr()] * 14))
     assert lib.dgan_create(ctypes.byref(h), ctypes.byref(d), arr, 14, None) == -3

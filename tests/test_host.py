@@ -24,8 +24,8 @@ def test_library_exports_every_header_symbol():
     for sym in declared:
         assert hasattr(lib, sym), "library does not export %s" % sym
     assert sorted(declared) == sorted(_native.ABI_SYMBOLS)
-    assert lib.dgan_abi_version() == 1
-    d = _native.dgan_desc(1, 0, 128, 64, 0, 0)
+    assert lib.dgan_abi_version() == 2
+    d = _native.dgan_desc(_native.ABI_VERSION, 0, 128, 64, 0, 0)
     import ctypes
     assert lib.dgan_num_weights(ctypes.byref(d)) == 8
     d.arch = 1
@@ -164,13 +164,25 @@ def _gloo_worker(rank, world, port, n_images, rec_rr, ret):
         images = torch.rand(n_images, 2, 2, 1, generator=g)
         z0 = torch.rand(n_images * rec_rr, 8, generator=g)
 
-        def local_fn(x, z, out):
+        def local_fn(x, z, out, first_image):
             # stand-in for the per-rank projection: depends on the image AND its R z0 rows
             out.copy_(x * 2.0 + z.reshape(x.shape[0], rec_rr, -1).sum(dim=(1, 2)).view(-1, 1, 1, 1))
 
         got = sharded_apply(local_fn, images, rec_rr, z_init_val=z0)
         want = images * 2.0 + z0.reshape(n_images, rec_rr, -1).sum(dim=(1, 2)).view(-1, 1, 1, 1)
-        ret[rank] = bool(torch.equal(got, want))
+        ok = bool(torch.equal(got, want))
+
+        # z_init_val=None: every shard must index ONE common z0 stream at (first image) * rec_rr - stand-in for the
+        # native Philox draw: "z0 row r" = r, so the single-device result is image-independent and known
+        def local_rand(x, z, out, first_image):
+            assert z is None
+            rows = first_image * rec_rr + torch.arange(x.shape[0] * rec_rr, dtype=torch.float32)
+            out.copy_(rows.reshape(x.shape[0], rec_rr).sum(dim=1).view(-1, 1, 1, 1).expand_as(x))
+
+        got = sharded_apply(local_rand, images, rec_rr, z_init_val=None)
+        want = torch.arange(n_images * rec_rr, dtype=torch.float32).reshape(n_images, rec_rr).sum(dim=1)
+        ok = ok and bool(torch.equal(got[:, 0, 0, 0], want))
+        ret[rank] = ok
     finally:
         dist.destroy_process_group()
 
@@ -370,7 +382,7 @@ def _check_plans(arch, n_rows, n_pairs=74, net_dim=64, env=None, mutate=0):
     lib.dgan_debug_check_plans.restype = ctypes.c_int
     lib.dgan_debug_check_plans.argtypes = [ctypes.POINTER(_native.dgan_desc), ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.dgan_last_error.restype = ctypes.c_char_p
-    desc = _native.dgan_desc(1, 0 if arch == "mnist" else 1, 128, net_dim, 0, 1)
+    desc = _native.dgan_desc(_native.ABI_VERSION, 0 if arch == "mnist" else 1, 128, net_dim, 0, 1)
     old = {k: os.environ.get(k) for k in (env or {})}
     try:
         for k, v in (env or {}).items():
