@@ -1,0 +1,171 @@
+"""f3: the reference's classifier zoo and the cleverhans helpers its callers use, in PyTorch.
+CPU tests of the host logic; the GPU test at the end is the north_star's "downstream classifier accuracy" clause:
+classifier accuracy on Defense-GAN reconstructions from the fp16 path, the fp32 path and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from defensegan_b200.utils import attacks as A
+from defensegan_b200.utils import network_builder as nb
+from oracle import defensegan_oracle as O
+
+
+def test_model_zoo_shapes_names_and_parameter_counts():
+    """Output shapes / layer names of reference utils/network_builder.py:333-521 (computed there by pushing a dummy
+    batch through tf.nn.conv2d); parameter counts follow from those shapes."""
+    want_flat = {"A": 64 * 12 * 12, "B": 128 * 1 * 1, "C": 64 * 12 * 12, "F": 128 * 1 * 1, "Y": 128 * 2 * 2, "Q": 64 * 5 * 5,
+                 "Z": 128 * 1 * 1}
+    for key, ctor in nb.model_dict.items():
+        torch.manual_seed(0)
+        m = ctor()
+        st = m.fprop(torch.rand(2, 28, 28, 1))
+        assert list(st)[-2:] == ["logits", "probs"] and st["logits"].shape == (2, 10)
+        assert torch.allclose(st["probs"].sum(dim=1), torch.ones(2), atol=1e-5)
+        assert torch.equal(m(torch.zeros(1, 28, 28, 1)), m.get_logits(torch.zeros(1, 28, 28, 1)))
+        if key in want_flat:
+            flat = [l for l in m.layers if isinstance(l, nb.Flatten)][0]
+            assert flat.output_width == want_flat[key], (key, flat.output_width)
+    m = nb.model_a(nb_classes=7, input_shape=(None, 64, 64, 3))
+    assert m(torch.rand(1, 64, 64, 3)).shape == (1, 7)
+
+
+def test_conv2d_follows_tensorflow_same_padding():
+    """TF SAME with an even kernel and stride 2 pads asymmetrically (smaller half first): 28 -> 14 with k=8, s=2 needs a
+    total of 6 = 3 + 3; k=5, s=2 on 28 needs 3 = 1 before + 2 after - PyTorch's symmetric `padding=` cannot express it."""
+    torch.manual_seed(1)
+    layer = nb.Conv2D(4, (5, 5), (2, 2), "SAME")
+    layer.set_input_shape([None, 28, 28, 2])
+    assert layer.get_output_shape() == [None, 14, 14, 4] and layer._pads(28, 28) == (1, 2, 1, 2)
+    x = torch.rand(3, 28, 28, 2)
+    got = layer.fprop(x)
+    # independent definition: out[i, j] = sum_k x[2i + k - 1, 2j + l - 1] w[k, l]
+    xp = F.pad(x.permute(0, 3, 1, 2), (1, 2, 1, 2))
+    want = torch.zeros(3, 14, 14, 4)
+    w = layer.kernels.detach()
+    for i in range(14):
+        for j in range(14):
+            patch = xp[:, :, 2 * i:2 * i + 5, 2 * j:2 * j + 5]                 # [n, ci, k, l]
+            want[:, i, j] = torch.einsum("nckl,klco->no", patch, w)
+    assert torch.allclose(got, want + layer.b.detach(), atol=1e-5)
+    valid = nb.Conv2D(3, (6, 6), (2, 2), "VALID")
+    valid.set_input_shape([None, 14, 14, 2])
+    assert valid.get_output_shape() == [None, 5, 5, 3]
+    # kernels are normalised over (kh, kw, Cin), Linear weights per column (reference :203-208, 222-227)
+    assert torch.allclose((layer.kernels ** 2).sum(dim=(0, 1, 2)), torch.ones(4), atol=1e-4)
+    lin = nb.Linear(5)
+    lin.set_input_shape([None, 11])
+    assert torch.allclose((lin.W ** 2).sum(dim=0), torch.ones(5), atol=1e-4)
+
+
+def test_dropout_is_identity_outside_training_and_keeps_prob_inside():
+    d = nb.Dropout(0.25)            # keep probability, as tf.nn.dropout(x, keep_prob)
+    d.set_input_shape([None, 1000])
+    x = torch.ones(64, 1000)
+    d.eval()
+    assert torch.equal(d.fprop(x), x)
+    d.train()
+    kept = (d.fprop(x) != 0).float().mean().item()
+    assert abs(kept - 0.25) < 0.02
+
+
+def test_fgm_matches_its_definition():
+    torch.manual_seed(2)
+    m = nb.model_e()
+    x = torch.rand(6, 28, 28, 1)
+    y = torch.eye(10)[torch.arange(6) % 10]
+    adv = A.fgm(m, x, y=y, eps=0.1, clip_min=0.0, clip_max=1.0)
+    xg = x.clone().requires_grad_(True)
+    g, = torch.autograd.grad(A.model_loss(y, m(xg), mean=False).sum(), xg)
+    assert torch.allclose(adv, (x + 0.1 * torch.sign(g)).clamp(0, 1))
+    assert float((adv - x).abs().max()) <= 0.1 + 1e-6
+    # y=None uses the model's own predictions (no label leaking): same as passing one-hot(argmax)
+    pred = torch.eye(10)[m(x).argmax(dim=1)]
+    assert torch.equal(A.fgm(m, x, eps=0.1), A.fgm(m, x, y=pred, eps=0.1))
+    # targeted flips the direction; L2 variant has per-example norm eps
+    assert torch.allclose(A.fgm(m, x, y=y, eps=0.1, targeted=True), x - 0.1 * torch.sign(g))
+    l2 = A.fgm(m, x, y=y, eps=0.5, ord=2)
+    assert torch.allclose((l2 - x).flatten(1).norm(dim=1), torch.full((6,), 0.5), atol=1e-4)
+    with pytest.raises(NotImplementedError):
+        A.fgm(m, x, ord=3)
+    assert torch.equal(A.FastGradientMethod(m).generate(x, eps=0.1), A.fgm(m, x, eps=0.1))
+
+
+def _latent_class_data(n, seed, weights, spread=0.35):
+    """10 classes = 10 cluster centres in the MNIST generator's latent space; images are G(centre + noise)."""
+    rs = np.random.RandomState(seed)
+    centres = np.random.RandomState(77).standard_normal((10, 128)).astype("float32") * np.sqrt(1.0 / 128) * 2.0
+    labels = rs.randint(0, 10, size=n)
+    z = (centres[labels] + spread * np.sqrt(1.0 / 128) * rs.standard_normal((n, 128))).astype("float32")
+    with torch.no_grad():
+        x = O.generator_forward("mnist", O.weights_to_torch(weights), torch.as_tensor(z)).numpy()
+    return x.astype("float32"), np.eye(10, dtype="float32")[labels]
+
+
+def test_model_train_and_eval_learn_a_separable_problem():
+    torch.manual_seed(3)
+    w = O.init_generator_weights("mnist")
+    X, Y = _latent_class_data(600, 1, w)
+    Xt, Yt = _latent_class_data(200, 2, w)
+    m = nb.model_e()
+    before = A.model_eval(m, Xt, Yt, {"batch_size": 64})
+    assert A.model_train(m, X, Y, {"nb_epochs": 6, "learning_rate": 1e-3, "batch_size": 50}, rng=np.random.RandomState(0))
+    after = A.model_eval(m, Xt, Yt, {"batch_size": 64})
+    assert after >= 0.9 > before + 0.3
+    with pytest.raises(AssertionError):
+        A.model_eval(m, Xt, Yt, {})
+
+
+@pytest.mark.gpu
+def test_downstream_classifier_accuracy_matches_across_precisions_and_oracle():
+    """north_star: "chosen reconstructions and downstream classifier accuracy must match the reference".  Classifier A
+    (reference utils/network_builder.py:412-427) is trained on synthetic 10-class data, attacked with FGSM (eps 0.3,
+    blackbox.py:530-534) and evaluated through utils.gan_defense.model_eval_gan on Defense-GAN reconstructions of the
+    adversarial images computed by (a) the fp16 tensor-core path, (b) the fp32 CUDA path, (c) the CPU oracle - same z0."""
+    from defensegan_b200.models.gan import MnistDefenseGAN
+    from defensegan_b200.utils.gan_defense import model_eval_gan
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(4)
+    w = O.init_generator_weights("mnist")
+    X, Y = _latent_class_data(2000, 11, w)
+    Xt, Yt = _latent_class_data(48, 12, w)
+    clf = nb.model_a().to(dev)
+    A.model_train(clf, X, Y, {"nb_epochs": 4, "learning_rate": 1e-3, "batch_size": 100}, rng=np.random.RandomState(0))
+    clean = A.model_eval(clf, Xt, Yt, {"batch_size": 48})
+    adv = A.fgm(clf, torch.as_tensor(Xt).to(dev), eps=0.3, clip_min=0.0, clip_max=1.0)
+    attacked = A.model_eval(clf, adv.cpu().numpy(), Yt, {"batch_size": 48})
+    R, L, bs = 10, 200, 24
+    z0 = O.sample_z0(len(Xt) * R, 128, seed=5)
+    recs, accs = {}, {}
+    for precision in ("fp16", "fp32"):
+        gan = MnistDefenseGAN(test_mode=True, verbose=False, precision=precision)
+        gan.rec_rr, gan.rec_iters = R, L
+        out = []
+
+        def predictions(xb, gan=gan, out=out):
+            i = sum(len(o) for o in out)
+            r = gan.reconstruct(xb, z_init_val=torch.as_tensor(z0[i * R:(i + len(xb)) * R]).to(dev))
+            out.append(r.cpu())
+            return clf(r)
+
+        accs[precision], _ = model_eval_gan(None, None, None, predictions=predictions, test_images=adv.cpu().numpy(),
+                                            test_labels=Yt, args={"batch_size": bs})
+        recs[precision] = torch.cat(out).numpy()
+        gan.close()
+    torch.set_num_threads(32)
+    ref = O.reconstruct("mnist", w, adv.cpu().numpy(), R, L, z_init_val=z0)
+    with torch.no_grad():
+        pred_ref = clf(torch.as_tensor(ref["rec"]).to(dev)).argmax(1).cpu().numpy()
+        preds = {p: clf(torch.as_tensor(recs[p]).to(dev)).argmax(1).cpu().numpy() for p in recs}
+    accs["oracle"] = float((pred_ref == Yt.argmax(1)).mean())
+    print("downstream accuracy: clean %.3f, FGSM eps=0.3 %.3f; after Defense-GAN (R=10, L=200): fp16 %.3f, fp32 %.3f, "
+          "CPU oracle %.3f; arg-max agreement with the oracle: fp16 %.3f, fp32 %.3f" % (
+              clean, attacked, accs["fp16"], accs["fp32"], accs["oracle"], (preds["fp16"] == pred_ref).mean(),
+              (preds["fp32"] == pred_ref).mean()))
+    assert clean >= 0.9 and attacked <= clean - 0.2                  # the attack bites ...
+    assert accs["oracle"] >= attacked + 0.1                          # ... and the projection repairs part of it
+    for p in ("fp16", "fp32"):
+        assert abs(accs[p] - accs["oracle"]) <= 1.0 / len(Xt) + 1e-9 + 0.021     # at most one image of 48 differs
+        assert (preds[p] == pred_ref).mean() >= 0.95
+        mse_p = ((recs[p] - adv.cpu().numpy()) ** 2).mean(axis=(1, 2, 3))
+        assert np.abs(mse_p - ref["loss_min"]).max() <= 1e-4
