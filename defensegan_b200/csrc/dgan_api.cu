@@ -172,6 +172,7 @@ struct dgan_ctx {
   // 2 = run the fp16 loop one (L-step, segment) per launch, each timed in isolation.  Never on in a throughput pass.
   int profile = 0;
   unsigned long long* prof_dev = nullptr; size_t prof_cap = 0; int prof_L = 0;
+  unsigned long long* dbg_dev = nullptr; int dbg_ctas = 0;   // per-CTA stall counters of the last profiled loop launch
   int n_rows_cur = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -685,7 +686,7 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
   }
   P.stream_p[0] = dp->stream_p[0]; P.stream_p[1] = dp->stream_p[1]; P.stream_m = dp->stream_m;
   P.stream_off = dp->stream_off; P.eitems = dp->eitems; P.eitem_off = dp->eitem_off; P.dep_off = dp->dep_off; P.deps = dp->deps;
-  P.flags = w.flags; P.status = w.status; P.prof = nullptr;
+  P.flags = w.flags; P.status = w.status; P.prof = nullptr; P.dbg = nullptr;
   P.n_seg = pl.n_seg; P.n_pad = w.n_pad; P.n_mpairs = dp->n_mpairs;
   P.y = w.y; P.loss_part = w.loss_part; P.n_rows = w.n_rows; P.nbx = c->tc_fin.nbx; P.w_out = c->tc_fin.w_out;
   P.gscale = c->tc.grad_scale;
@@ -749,6 +750,15 @@ static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, con
       DGAN_CUDA_CHECK(cudaMemcpyAsync(c->prof_dev, init.data(), need * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
       DGAN_CUDA_CHECK(cudaStreamSynchronize(s));     // `init` dies with this scope (profiling mode only)
       P.prof = c->prof_dev; c->prof_L = rec_iters;
+      const int n_ctas = 2 * dp->n_pairs;
+      if (c->dbg_dev == nullptr || c->dbg_ctas < n_ctas) {
+        if (c->dbg_dev) cudaFree(c->dbg_dev);
+        c->dbg_dev = nullptr; c->dbg_ctas = 0;
+        DGAN_CUDA_CHECK(cudaMalloc((void**)&c->dbg_dev, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long)));
+        c->dbg_ctas = n_ctas;
+      }
+      DGAN_CUDA_CHECK(cudaMemsetAsync(c->dbg_dev, 0, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long), s));
+      P.dbg = c->dbg_dev;
     }
     ProfScope ps(c, (int)c->kind_names.size() - 1, s);
     e = go(P);
@@ -978,6 +988,7 @@ int dgan_destroy(dgan_handle h) {
   if (h == nullptr) return DGAN_OK;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (h->prof_dev) cudaFree(h->prof_dev);
+  if (h->dbg_dev) cudaFree(h->dbg_dev);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return DGAN_OK;
@@ -1153,6 +1164,16 @@ int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* lau
     h->prof_L = 0;
   }
   return DGAN_OK;
+}
+
+// Developer aid (not in the public header): per-CTA stall counters (clock64 ticks, LoopDbg order, 16 per CTA) of the most
+// recent loop launch made under dgan_profile_enable(h, 1).  Returns the number of CTAs copied.
+int dgan_debug_loop_stalls(dgan_handle h, unsigned long long* out, int max_ctas) {
+  if (h == nullptr || out == nullptr || h->dbg_dev == nullptr) return 0;
+  const int n = std::min(max_ctas, h->dbg_ctas);
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, h->dbg_dev, (size_t)n * dgan::DBG_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
 }
 
 // Host-only developer/test aid (not in the public header): plan one L-step of the fp16 path for `n_rows` latent rows on

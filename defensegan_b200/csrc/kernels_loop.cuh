@@ -70,6 +70,7 @@ struct LoopParams {
   uint32_t* flags;                 // zeroed per call
   uint32_t* status;                // [0] != 0: a flag wait timed out (results invalid)
   unsigned long long* prof;        // optional [t][n_seg][2] globaltimer min-start / max-end
+  unsigned long long* dbg;         // optional [CTA][16] stall counters of the roles (clock64 ticks), see LoopDbg
   int n_seg, n_seg_last;           // segments per L-step; segments of the LAST L-step (forward only: SURVEY F4)
   int seg_begin, seg_end;          // segment sub-range of this launch (whole step: 0, n_seg)
   int t_begin, t_end;              // L-steps of this launch
@@ -123,14 +124,19 @@ __device__ __forceinline__ void loop_wait_flag(const uint32_t* flag, uint32_t ta
 
 // "this thread's global writes of the item are done": order them before the flag increment, for readers in both proxies
 __device__ __forceinline__ void loop_publish_fence() {
-  __threadfence();
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   ptx::fence_proxy_async_all();
 }
+
+// per-CTA stall counters written when LoopParams::dbg != NULL (developer aid: tools/loop_stalls.py)
+enum LoopDbg : int { DBG_P_FLAG = 0, DBG_P_RING, DBG_P_TOTAL, DBG_M_FULL, DBG_M_ACC, DBG_M_TOTAL, DBG_E_ACC, DBG_E_TILE, DBG_E_TOTAL,
+                     DBG_S_TILE, DBG_S_DONE, DBG_S_TOTAL, DBG_P_SLOW, DBG_COUNT = 16 };
 
 struct LoopCtx {                     // per-thread view of the CTA's pipeline state handed to the epilogue variants
   uint32_t tmem_base, bar_acc_full, bar_acc_empty, epi_base, bar_base;
   int warp, lane, rank;
-  uint32_t item_count, unit_count;
+  uint32_t item_count, tile_count;
+  long long t_acc, t_tile;          // stall ticks (debug)
 };
 
 // 32 accumulator columns of one row -> (bias | ReLU + mask bits out | mask bits in) -> 16 packed fp16 pairs
@@ -190,7 +196,11 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
   float4 xq_next[FINAL ? (EPI == EPI_FINAL_SIGMOID1 ? 4 : 12) : 1];
   if (FINAL && half < n_acc)     // first block's target pixels: in flight while the MMAs finish
     tc_final_targets<(EPI == EPI_FINAL_SIGMOID1 ? 1 : 3)>(reinterpret_cast<float4(&)[EPI == EPI_FINAL_SIGMOID1 ? 4 : 12]>(xq_next), fa, ip->q[half], (int)n);
-  ptx::mbar_wait(cx.bar_acc_full + 8 * buf, (cx.item_count >> 1) & 1);
+  {
+    const long long tw0 = P.dbg ? clock64() : 0;
+    ptx::mbar_wait(cx.bar_acc_full + 8 * buf, (cx.item_count >> 1) & 1);
+    if (P.dbg) cx.t_acc += clock64() - tw0;
+  }
   ptx::tc_fence_after();
   if (FINAL) {
     constexpr int CO = (EPI == EPI_FINAL_SIGMOID1) ? 1 : 3;
@@ -212,8 +222,10 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
     //      128B-swizzled smem tile -> one TMA store per 128x64 tile.
     constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
     const int n_units = n_acc * G;
-    const bool t0 = (warp == LOOP_EPI_WARP0 + 4 * half) && lane == 0;  // issues this half's bulk copies
-    const int row0 = (2 * mp + rank) * kRowTile;
+    // The staging tile of this epilogue half is handed to the half's STORE WARP (warp 2 + half): it issues the TMA store,
+    // frees the tile when the store has read it, and publishes the item when the item's stores have completed - so no
+    // thread that does arithmetic ever waits for global-memory latency.
+    const uint32_t tile_full = cx.bar_base + 168 + 8 * (uint32_t)half, tile_free = cx.bar_base + 184 + 8 * (uint32_t)half;
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t s_out = cx.epi_base + (uint32_t)half * TC2_TILE_BYTES;
     uint32_t r0[32], r1[32];
@@ -241,18 +253,15 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
         ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64), r0);
         ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64 + 32), r1);
       }
-      ++cx.unit_count;
-      if (t0) ptx::bulk_wait_read0();                  // the store that last read s_out is done
-      ptx::named_bar_sync(1 + half, 128);              // s_out free
+      const long long tw0 = P.dbg ? clock64() : 0;
+      ptx::mbar_wait(tile_free, (cx.tile_count & 1) ^ 1);          // the store that last read s_out is done (first use: free)
+      if (P.dbg) cx.t_tile += clock64() - tw0;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         ptx::st_shared_v4(s_out + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(1 + half, 128);              // tile complete (and this half's mask words of the unit written)
-      if (t0) {
-        ptx::tma_store_3d(&sg.tm_out, s_out, g * 64, row0, q);
-        ptx::bulk_commit();
-      }
+      ptx::mbar_arrive(tile_full);                                  // 128 arrivals: tile (and this unit's mask words) complete
+      ++cx.tile_count;
     }
   } else {
     constexpr int CH = N_TILE >= 32 ? N_TILE / 32 : 1;     // 32-column chunks per accumulator
@@ -278,13 +287,7 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
 
   // ---- publish the item
   if (TMA_EPI) {
-    // the tile stores were issued by lane 0 of this half's first warp: once they (and, through the named barriers
-    // above, the mask words of the half's four warps) are complete, it arrives for the four warps of the half
-    if ((warp == LOOP_EPI_WARP0 + 4 * half) && lane == 0) {
-      ptx::bulk_wait_all0();
-      loop_publish_fence();
-      ptx::red_release_gpu_add(flag, 4u);
-    }
+    // published by the half's store warp once the item's tile stores have completed
   } else if (EPI == EPI_NONE && sizeof(TOUT) == 4 && P.m_counter != nullptr) {
     // ---- momentum in the tail of the split-K Linear backward (tf.train.MomentumOptimizer, models/gan.py:389-391).
     //      Every epilogue thread has stored its share of this item's partial sums; the CTA that completes the last
@@ -378,7 +381,8 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
   const uint32_t epi_base = smem_base + LOOP_RING_BYTES;                       // two output staging tiles
   const uint32_t stg_base = epi_base + LOOP_EPI_TILES * TC2_TILE_BYTES;        // [producer ring][MMA ring] of TcRec
   const uint32_t bar_base = stg_base + TC2_STAGING_BYTES;
-  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160, momentum-tail flag @ +200
+  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160,
+  // tile_full[2] @ +168, tile_free[2] @ +184 (epilogue half <-> store warp), momentum-tail flag @ +200
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
   const uint32_t tmem_slot = bar_base + 160;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -396,6 +400,8 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_acc_full + 8 * b, 1);
       ptx::mbar_init(bar_acc_empty + 8 * b, 2 * TC2_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
+      ptx::mbar_init(bar_base + 168 + 8 * b, 128);                // tile_full[half]: the 4 warps of an epilogue half
+      ptx::mbar_init(bar_base + 184 + 8 * b, 1);                  // tile_free[half]: the half's store warp
     }
     ptx::fence_barrier_init();
   }
@@ -424,11 +430,24 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       const uint32_t rend_max = __ldg(soff + P.seg_end);
       if (2 * rbeg + lane < 2 * rend_max) first = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
     }
+    // dependencies of the replay's first item (the same every replay); later items are described one item ahead by the
+    // records themselves (w[6], w[7] of an item's first step = dependency range of the NEXT item)
+    uint32_t first_d0 = 0, first_cnt = 0;
+    {
+      const uint32_t i0 = __ldg(eoff + P.seg_begin), i1 = __ldg(eoff + P.seg_end);
+      if (i0 < i1) { first_d0 = __ldg(P.dep_off + i0); first_cnt = __ldg(P.dep_off + i0 + 1) - first_d0; }
+    }
+    long long t_flag = 0, t_ring = 0, n_slow = 0;
+    const long long t_p0 = P.dbg ? clock64() : 0;
     for (int t = P.t_begin; t < P.t_end; ++t) {
       const int s_end = min(P.seg_end, (t == P.last_step) ? P.n_seg_last : P.n_seg);
       if (s_end <= P.seg_begin) continue;
       const uint32_t rend = __ldg(soff + s_end);
-      uint32_t item_idx = __ldg(eoff + P.seg_begin);
+      // the item about to start: dependency range, this lane's entry (first 32) and its flag value if already fetched
+      uint32_t cur_d0 = first_d0, cur_cnt = first_cnt, cur_e = 0, cur_f = 0;
+      bool cur_f_valid = false;
+      if (lane < cur_cnt) cur_e = __ldg(P.deps + cur_d0 + lane);
+      uint32_t nxt_d0 = 0, nxt_cnt = 0, nxt_e = 0;
       uint4 mine = first;
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
@@ -437,27 +456,39 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
         for (uint32_t i = 0; i < cnt; ++i, ++it) {
           const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
-          const uint2 r1 = ptx::ld_shared_v2(ring + i * 32u + 16u);
+          const uint4 r1 = ptx::ld_shared_v4(ring + i * 32u + 16u);
           const uint32_t slot = it & (TC2_NSLOT - 1);
           const int kc = (r0.x >> 8) & 0xF, nA = (r0.x >> 12) & 0x7, nB = (r0.x >> 15) & 0xF;
           const uint32_t dep = (r0.x >> 19) & 0xF;
           const int seg = (int)((r0.y >> 16) & 0xFu);
           const LoopSeg& sg = P.seg[seg];
           if ((r0.y >> 20) & 1u) {
-            // first step of an item: everything it stages must have been published
-            const uint32_t d0 = __ldg(P.dep_off + item_idx), d1 = __ldg(P.dep_off + item_idx + 1);
-            for (uint32_t d = d0 + lane; d < d1; d += 32) {
-              const uint32_t e = __ldg(P.deps + d);
-              const uint32_t target = LOOP_ARRIVALS * (uint32_t)((e & LOOP_DEP_PREV) ? t : t + 1);
-              loop_wait_flag(P.flags + (e & ~LOOP_DEP_PREV), target, P.status);
+            // first step of an item: everything it stages must have been published.  Fast path: the flag values were
+            // fetched while the previous item's last step was issued and already satisfy the target.
+            const long long tw0 = P.dbg ? clock64() : 0;
+            if (cur_cnt > 0) {
+              const uint32_t target = LOOP_ARRIVALS * (uint32_t)((cur_e & LOOP_DEP_PREV) ? t : t + 1);
+              const bool ok = (lane >= cur_cnt) || (cur_f_valid && cur_f >= target);
+              if (!__all_sync(0xffffffffu, ok) || cur_cnt > 32u) {
+                ++n_slow;
+                for (uint32_t d = cur_d0 + lane; d < cur_d0 + cur_cnt; d += 32) {
+                  const uint32_t e = __ldg(P.deps + d);
+                  loop_wait_flag(P.flags + (e & ~LOOP_DEP_PREV), LOOP_ARRIVALS * (uint32_t)((e & LOOP_DEP_PREV) ? t : t + 1), P.status);
+                }
+                __syncwarp();
+              }
+              ptx::fence_proxy_async_all();             // acquired generic-proxy view -> the TMA (async proxy) reads below
             }
-            __syncwarp();
-            ptx::fence_proxy_async_all();               // acquired generic-proxy view -> the TMA (async proxy) reads below
-            ++item_idx;
+            if (P.dbg) t_flag += clock64() - tw0;
+            // the NEXT item's dependency range rides in this record: fetch this lane's entry now, its flag at the item's last step
+            nxt_d0 = r1.z; nxt_cnt = r1.w; nxt_e = 0;
+            if (lane < nxt_cnt) nxt_e = __ldg(P.deps + nxt_d0 + lane);
           }
           const int row0 = (2 * (int)(r0.y & 0xFFFFu) + (int)rank) * kRowTile;
+          const long long tr0 = P.dbg ? clock64() : 0;
           if (it >= dep) ptx::mbar_wait(bar_empty + 8 * ((it - dep) & (TC2_NSLOT - 1)), ((it - dep) >> 3) & 1);   // step it-dep consumed
           if (dep != TC2_NSLOT && it >= TC2_NSLOT) ptx::mbar_wait(bar_empty + 8 * slot, ((it - TC2_NSLOT) >> 3) & 1);
+          if (P.dbg) t_ring += clock64() - tr0;
           const uint32_t full = bar_full + 8 * slot;
           const uint32_t sa = smem_base + ((r0.x & 0xFFu) << 10);
           const uint32_t half_b = sg.half_b;
@@ -479,9 +510,21 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
             }
           }
           __syncwarp();
+          if ((r0.y >> 21) & 1u) {
+            // last step of the item issued: look at the next item's flags now, so that the answer is (usually) there by
+            // the time its first step comes up
+            cur_d0 = nxt_d0; cur_cnt = nxt_cnt; cur_e = nxt_e; cur_f = 0; cur_f_valid = true;
+            if (lane < cur_cnt) cur_f = ptx::ld_acquire_gpu(P.flags + (cur_e & ~LOOP_DEP_PREV));
+          }
         }
         __syncwarp();
       }
+    }
+    if (P.dbg && lane == 0) {
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_FLAG] = (unsigned long long)t_flag;
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_RING] = (unsigned long long)t_ring;
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_TOTAL] = (unsigned long long)(clock64() - t_p0);
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_SLOW] = (unsigned long long)n_slow;
     }
     // drain: nobody leaves while MMAs may still read this CTA's shared memory
     for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
@@ -494,6 +537,8 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
       uint32_t it = 0, item_count = 0, buf = 0;
       uint32_t idesc = 0, acc_stride = 0, half_b16 = 0, n_merge = 0;
+      long long t_full = 0, t_acc = 0;
+      const long long t_m0 = P.dbg ? clock64() : 0;
       const uint32_t rbeg = __ldg(soff + P.seg_begin);
       uint4 first = make_uint4(0, 0, 0, 0);
       {
@@ -520,9 +565,13 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
               const LoopSeg& sg = P.seg[r0.y & 0xFu];
               idesc = sg.idesc; acc_stride = sg.acc_stride; half_b16 = sg.half_b >> 4; n_merge = (sg.n_tile >> 3) << 17;
               buf = item_count & 1;
+              const long long ta0 = P.dbg ? clock64() : 0;
               ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
+              if (P.dbg) t_acc += clock64() - ta0;
             }
+            const long long tf0 = P.dbg ? clock64() : 0;
             ptx::mbar_wait(bar_full + 8 * slot, phase);
+            if (P.dbg) t_full += clock64() - tf0;
             ptx::tc_fence_after();
             // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
             const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
@@ -555,6 +604,57 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       }
       // drain: observe the release of the last (up to two) accumulator buffers by the epilogue warps of both CTAs
       for (uint32_t j = item_count > 2 ? item_count - 2 : 0; j < item_count; ++j) ptx::mbar_wait(bar_acc_empty + 8 * (j & 1), (j >> 1) & 1);
+      if (P.dbg && lane == 0) {
+        P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_M_FULL] = (unsigned long long)t_full;
+        P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_M_ACC] = (unsigned long long)t_acc;
+        P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_M_TOTAL] = (unsigned long long)(clock64() - t_m0);
+      }
+    }
+   } else if (lane == 0) {
+    // ===================== store warps (warp 2 + h serves epilogue half h; one lane) =====================
+    // Takes the epilogue half's staged 128x64 fp16 tiles, stores them by TMA, frees the staging tile as soon as the
+    // store has READ it, and publishes the item once its stores have COMPLETED (only the issuing thread can wait for that).
+    const int h = warp - 2;
+    const uint32_t tile_full = bar_base + 168 + 8 * (uint32_t)h, tile_free = bar_base + 184 + 8 * (uint32_t)h;
+    const uint32_t s_out = epi_base + (uint32_t)h * TC2_TILE_BYTES;
+    uint32_t tcount = 0;
+    long long t_tile = 0, t_done = 0;
+    const long long t_s0 = P.dbg ? clock64() : 0;
+    for (int t = P.t_begin; t < P.t_end; ++t) {
+      const int s_end = min(P.seg_end, (t == P.last_step) ? P.n_seg_last : P.n_seg);
+      if (s_end <= P.seg_begin) continue;
+      const uint32_t e_beg = __ldg(eoff + P.seg_begin), e_end = __ldg(eoff + s_end);
+      for (uint32_t k = e_beg; k < e_end; ++k) {
+        const uint2 cur = __ldg(P.eitems + k);
+        const int seg = (int)(cur.x >> 16), win = (int)(cur.x & 0xFFFFu), mp = (int)cur.y;
+        const LoopSeg& sg = P.seg[seg];
+        const uint32_t kind = sg.kind;
+        if (!(kind <= LK_NONE64H)) continue;                       // fp32 / last-layer epilogues store (and publish) themselves
+        const TcItem2* ip = sg.items + win;
+        const int G = (int)(sg.n_tile >> 6), n_units = (int)__ldg(&ip->n_acc) * G;
+        const int row0 = (2 * mp + (int)rank) * kRowTile;
+        for (int u = h; u < n_units; u += 2) {
+          const int q = (int)__ldg(&ip->q[u / G]);
+          const long long tw0 = P.dbg ? clock64() : 0;
+          ptx::mbar_wait(tile_full, tcount & 1);
+          if (P.dbg) t_tile += clock64() - tw0;
+          ptx::tma_store_3d(&sg.tm_out, s_out, (u % G) * 64, row0, q);
+          ptx::bulk_commit();
+          ptx::bulk_wait_read0();
+          ptx::mbar_arrive(tile_free);
+          ++tcount;
+        }
+        const long long tw1 = P.dbg ? clock64() : 0;
+        ptx::bulk_wait_all0();                                      // the item's tiles are in global memory
+        ptx::fence_proxy_async_all();
+        ptx::red_release_gpu_add(P.flags + sg.flag_base + (size_t)mp * sg.n_windows + win, 4u);   // for this half's four warps
+        if (P.dbg) t_done += clock64() - tw1;
+      }
+    }
+    if (P.dbg) {
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_TILE + 0] = (unsigned long long)t_tile;    // (warp 3 overwrites warp 2: same order of magnitude)
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_DONE] = (unsigned long long)t_done;
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_TOTAL] = (unsigned long long)(clock64() - t_s0);
     }
    }
   } else {
@@ -562,7 +662,8 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     // ===================== epilogue (warps 4..11, both CTAs) =====================
     LoopCtx cx;
     cx.tmem_base = tmem_base; cx.bar_acc_full = bar_acc_full; cx.bar_acc_empty = bar_acc_empty; cx.epi_base = epi_base; cx.bar_base = bar_base;
-    cx.warp = warp; cx.lane = lane; cx.rank = (int)rank; cx.item_count = 0; cx.unit_count = 0;
+    cx.warp = warp; cx.lane = lane; cx.rank = (int)rank; cx.item_count = 0; cx.tile_count = 0; cx.t_acc = 0; cx.t_tile = 0;
+    const long long t_e0 = P.dbg ? clock64() : 0;
     TcFinalArgs fa{};
     fa.x = P.x; fa.y = P.y; fa.loss_part = P.loss_part; fa.R = P.R; fa.B = P.B; fa.n_rows = P.n_rows; fa.nbx = P.nbx; fa.w_out = P.w_out;
     fa.gscale = P.gscale; fa.m_gmul = P.m_gmul; fa.m_mu = P.m_mu;
@@ -590,7 +691,11 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         }
       }
     }
-    if (lane == 0 && (warp == LOOP_EPI_WARP0 || warp == LOOP_EPI_WARP0 + 4)) ptx::bulk_wait_all0();   // stores landed before exit
+    if (P.dbg && warp == LOOP_EPI_WARP0 && lane == 0) {
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_E_ACC] = (unsigned long long)cx.t_acc;
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_E_TILE] = (unsigned long long)cx.t_tile;
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_E_TOTAL] = (unsigned long long)(clock64() - t_e0);
+    }
   }
 
   ptx::tc_fence_before();
@@ -738,6 +843,7 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
   plan->n_steps = plan->n_mma = plan->n_bytes = 0;
   for (int pr = 0; pr < n_pairs; ++pr) {
     const size_t stream_beg = plan->stream_m.size();
+    size_t prev_first_rec = (size_t)-1;
     std::vector<int> kb_of;                                    // KB of every step of this pair's stream
     for (int s = 0; s < n_seg; ++s) {
       const LoopSegSpec& sp = specs[(size_t)s];
@@ -766,8 +872,14 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
               if (std::find(dl.begin(), dl.end(), f) == dl.end()) dl.push_back(f);
             }
         }
+        const uint32_t this_d0 = (uint32_t)plan->deps.size();
         plan->deps.insert(plan->deps.end(), dl.begin(), dl.end());
         plan->dep_off.push_back((uint32_t)plan->deps.size());
+        // the first-step record of the PREVIOUS item of this CTA pair announces this item's dependency range, so that the
+        // producer can fetch the flags one item ahead
+        if (prev_first_rec != (size_t)-1)
+          for (int r = 0; r < 2; ++r) { plan->stream_p[r][prev_first_rec].w[6] = this_d0; plan->stream_p[r][prev_first_rec].w[7] = (uint32_t)dl.size(); }
+        prev_first_rec = plan->stream_m.size();
         for (size_t j = 0; j < itm.steps.size(); ++j) {
           const Tc2HostStep& hs = itm.steps[j];
           const int kb = (hs.bytes + 1023) / 1024;
@@ -782,7 +894,7 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
           for (int r = 0; r < 2; ++r) {
             TcRec rp{};
             rp.w[0] = ((uint32_t)hs.kc << 8) | ((uint32_t)hs.nA << 12) | ((uint32_t)hs.nB << 15);   // offset + dep filled below
-            rp.w[1] = (uint32_t)mp | ((uint32_t)s << 16) | ((j == 0 ? 1u : 0u) << 20);
+            rp.w[1] = (uint32_t)mp | ((uint32_t)s << 16) | ((j == 0 ? 1u : 0u) << 20) | ((j + 1 == itm.steps.size() ? 1u : 0u) << 21);
             for (int a = 0; a < hs.nA; ++a) rp.w[2 + a / 2] |= (uint32_t)(hs.a_pix[a] & 0xFFFF) << (16 * (a & 1));
             for (int b = 0; b < hs.nB; ++b) rp.w[4 + b / 4] |= (uint32_t)hs.b_ent[r][b] << (8 * (b & 3));
             plan->stream_p[r].push_back(rp);
@@ -924,7 +1036,15 @@ static int loop_check_plan(const std::vector<LoopSegSpec>& specs, const LoopPlan
       const int s = (int)((p0.w[1] >> 16) & 0xF), mp = (int)(p0.w[1] & 0xFFFF), nA = (int)((p0.w[0] >> 12) & 7);
       if (first) {
         if (e >= pl.eitems.size() || (int)(pl.eitems[e].x >> 16) != s || (int)pl.eitems[e].y != mp) return fail("producer stream and item list disagree");
+        // the record announces the NEXT item's dependency range (none after the pair's last item)
+        const uint32_t lim = pl.eitem_off[(size_t)pr * (n_seg + 1) + n_seg];
+        const uint32_t want_d0 = (e + 1 < lim) ? pl.dep_off[e + 1] : 0u, want_cnt = (e + 1 < lim) ? pl.dep_off[e + 2] - pl.dep_off[e + 1] : 0u;
+        for (int r = 0; r < 2; ++r) {
+          const TcRec& pq = pl.stream_p[r][r0 + k];
+          if (pq.w[7] != want_cnt || (want_cnt != 0 && pq.w[6] != want_d0)) return fail("a record announces the wrong dependency range for the next item");
+        }
       }
+      if ((((p0.w[1] >> 21) & 1u) != 0u) != (((pl.stream_m[r0 + k].w[0] >> 17) & 1u) != 0u)) return fail("last-step marks of producer and MMA records disagree");
       const int in_seg = specs[(size_t)s].in_seg;
       if (in_seg < 0) {
         const uint32_t f = (pl.zflag_base + (uint32_t)mp) | LOOP_DEP_PREV;

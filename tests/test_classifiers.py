@@ -91,6 +91,13 @@ def test_fgm_matches_its_definition():
     assert torch.equal(A.FastGradientMethod(m).generate(x, eps=0.1), A.fgm(m, x, eps=0.1))
 
 
+def _contrast_weights():
+    """The He-init generator maps every latent to an almost uniform grey (pixel std 0.006): scale its filters x3 so that
+    G(z) has real contrast (pixel std 0.29, range 0..1) and classes can be told apart."""
+    w = O.init_generator_weights("mnist")
+    return {k: (v * 3.0 if (k.endswith(".Filters") or k.endswith(".W")) else v) for k, v in w.items()}
+
+
 def _latent_class_data(n, seed, weights, spread=0.35):
     """10 classes = 10 cluster centres in the MNIST generator's latent space; images are G(centre + noise)."""
     rs = np.random.RandomState(seed)
@@ -104,7 +111,7 @@ def _latent_class_data(n, seed, weights, spread=0.35):
 
 def test_model_train_and_eval_learn_a_separable_problem():
     torch.manual_seed(3)
-    w = O.init_generator_weights("mnist")
+    w = _contrast_weights()
     X, Y = _latent_class_data(600, 1, w)
     Xt, Yt = _latent_class_data(200, 2, w)
     m = nb.model_e()
@@ -119,26 +126,27 @@ def test_model_train_and_eval_learn_a_separable_problem():
 @pytest.mark.gpu
 def test_downstream_classifier_accuracy_matches_across_precisions_and_oracle():
     """north_star: "chosen reconstructions and downstream classifier accuracy must match the reference".  Classifier A
-    (reference utils/network_builder.py:412-427) is trained on synthetic 10-class data, attacked with FGSM (eps 0.3,
+    (reference utils/network_builder.py:412-427) is trained on synthetic 10-class data, attacked with FGSM (eps 0.2 on contrast-scaled synthetic data,
     blackbox.py:530-534) and evaluated through utils.gan_defense.model_eval_gan on Defense-GAN reconstructions of the
     adversarial images computed by (a) the fp16 tensor-core path, (b) the fp32 CUDA path, (c) the CPU oracle - same z0."""
     from defensegan_b200.models.gan import MnistDefenseGAN
     from defensegan_b200.utils.gan_defense import model_eval_gan
     dev = torch.device("cuda", 0)
     torch.manual_seed(4)
-    w = O.init_generator_weights("mnist")
+    w = _contrast_weights()
     X, Y = _latent_class_data(2000, 11, w)
     Xt, Yt = _latent_class_data(48, 12, w)
     clf = nb.model_a().to(dev)
     A.model_train(clf, X, Y, {"nb_epochs": 4, "learning_rate": 1e-3, "batch_size": 100}, rng=np.random.RandomState(0))
     clean = A.model_eval(clf, Xt, Yt, {"batch_size": 48})
-    adv = A.fgm(clf, torch.as_tensor(Xt).to(dev), eps=0.3, clip_min=0.0, clip_max=1.0)
+    adv = A.fgm(clf, torch.as_tensor(Xt).to(dev), eps=0.2, clip_min=0.0, clip_max=1.0)
     attacked = A.model_eval(clf, adv.cpu().numpy(), Yt, {"batch_size": 48})
     R, L, bs = 10, 200, 24
     z0 = O.sample_z0(len(Xt) * R, 128, seed=5)
     recs, accs = {}, {}
     for precision in ("fp16", "fp32"):
         gan = MnistDefenseGAN(test_mode=True, verbose=False, precision=precision)
+        gan.set_generator_weights(w)
         gan.rec_rr, gan.rec_iters = R, L
         out = []
 
@@ -158,7 +166,7 @@ def test_downstream_classifier_accuracy_matches_across_precisions_and_oracle():
         pred_ref = clf(torch.as_tensor(ref["rec"]).to(dev)).argmax(1).cpu().numpy()
         preds = {p: clf(torch.as_tensor(recs[p]).to(dev)).argmax(1).cpu().numpy() for p in recs}
     accs["oracle"] = float((pred_ref == Yt.argmax(1)).mean())
-    print("downstream accuracy: clean %.3f, FGSM eps=0.3 %.3f; after Defense-GAN (R=10, L=200): fp16 %.3f, fp32 %.3f, "
+    print("downstream accuracy: clean %.3f, FGSM eps=0.2 %.3f; after Defense-GAN (R=10, L=200): fp16 %.3f, fp32 %.3f, "
           "CPU oracle %.3f; arg-max agreement with the oracle: fp16 %.3f, fp32 %.3f" % (
               clean, attacked, accs["fp16"], accs["fp32"], accs["oracle"], (preds["fp16"] == pred_ref).mean(),
               (preds["fp32"] == pred_ref).mean()))
