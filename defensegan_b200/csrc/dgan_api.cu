@@ -173,6 +173,7 @@ struct dgan_ctx {
   int profile = 0;
   unsigned long long* prof_dev = nullptr; size_t prof_cap = 0; int prof_L = 0;
   unsigned long long* dbg_dev = nullptr; int dbg_ctas = 0;   // per-CTA stall counters of the last profiled loop launch
+  unsigned long long* trace_dev = nullptr; size_t trace_items = 0; const DevPlan* trace_plan = nullptr;   // per-item timestamps of one L-step
   int n_rows_cur = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -623,7 +624,7 @@ static int get_plan(dgan_ctx* c, int n_rows, const DevPlan** out) {
   std::unique_ptr<DevPlan> dp(new DevPlan());
   dp->n_mpairs = n_mpairs; dp->n_pairs = c->n_pairs;
   int rc;
-  if ((rc = loop_plan(c->segs, n_mpairs, c->n_pairs, /*carry_load=*/true, &dp->host))) return rc;
+  if ((rc = loop_plan(c->segs, n_mpairs, c->n_pairs, /*carry_load=*/DGAN_LOOP_CARRY != 0, &dp->host))) return rc;
   const LoopPlan& pl = dp->host;
   for (int s = 0; s < pl.n_seg; ++s)
     if ((rc = upload_vec(c, pl.hdrs[(size_t)s], &dp->items[s]))) return rc;
@@ -686,7 +687,7 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
   }
   P.stream_p[0] = dp->stream_p[0]; P.stream_p[1] = dp->stream_p[1]; P.stream_m = dp->stream_m;
   P.stream_off = dp->stream_off; P.eitems = dp->eitems; P.eitem_off = dp->eitem_off; P.dep_off = dp->dep_off; P.deps = dp->deps;
-  P.flags = w.flags; P.status = w.status; P.prof = nullptr; P.dbg = nullptr;
+  P.flags = w.flags; P.status = w.status; P.prof = nullptr; P.dbg = nullptr; P.trace = nullptr; P.trace_step = -1;
   P.n_seg = pl.n_seg; P.n_pad = w.n_pad; P.n_mpairs = dp->n_mpairs;
   P.y = w.y; P.loss_part = w.loss_part; P.n_rows = w.n_rows; P.nbx = c->tc_fin.nbx; P.w_out = c->tc_fin.w_out;
   P.gscale = c->tc.grad_scale;
@@ -759,6 +760,15 @@ static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, con
       }
       DGAN_CUDA_CHECK(cudaMemsetAsync(c->dbg_dev, 0, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long), s));
       P.dbg = c->dbg_dev;
+      const size_t n_items = dp->host.eitems.size();
+      if (c->trace_dev == nullptr || c->trace_items < n_items) {
+        if (c->trace_dev) cudaFree(c->trace_dev);
+        c->trace_dev = nullptr; c->trace_items = 0;
+        DGAN_CUDA_CHECK(cudaMalloc((void**)&c->trace_dev, n_items * 4 * sizeof(unsigned long long)));
+        c->trace_items = n_items;
+      }
+      DGAN_CUDA_CHECK(cudaMemsetAsync(c->trace_dev, 0, n_items * 4 * sizeof(unsigned long long), s));
+      P.trace = c->trace_dev; P.trace_step = std::max(0, rec_iters - 3); c->trace_plan = dp;
     }
     ProfScope ps(c, (int)c->kind_names.size() - 1, s);
     e = go(P);
@@ -989,6 +999,7 @@ int dgan_destroy(dgan_handle h) {
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (h->prof_dev) cudaFree(h->prof_dev);
   if (h->dbg_dev) cudaFree(h->dbg_dev);
+  if (h->trace_dev) cudaFree(h->trace_dev);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return DGAN_OK;
@@ -1176,6 +1187,40 @@ int dgan_debug_loop_stalls(dgan_handle h, unsigned long long* out, int max_ctas)
   return n;
 }
 
+// Developer aid (not in the public header): the traced L-step of the most recent profiled loop launch.  Per item (in the
+// plan's item order): out[8i..] = {CTA pair, segment, window, row pair, dependency-wait begin, wait end, epilogue begin,
+// epilogue end} (times in ns of %globaltimer); deps_out (if not NULL) receives per item up to `max_deps` item indices it
+// depends on (-1 padded; -2 = the previous L-step's z update).  Returns the number of items.
+int dgan_debug_loop_trace(dgan_handle h, unsigned long long* out, long long* deps_out, int max_deps, int max_items) {
+  if (h == nullptr || out == nullptr || h->trace_dev == nullptr || h->trace_plan == nullptr) return 0;
+  const LoopPlan& pl = h->trace_plan->host;
+  const int n = (int)std::min<size_t>((size_t)max_items, pl.eitems.size());
+  std::vector<unsigned long long> raw((size_t)pl.eitems.size() * 4);
+  cudaDeviceSynchronize();
+  cudaMemcpy(raw.data(), h->trace_dev, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  std::vector<long long> flag2item(pl.n_flags, -1);
+  std::vector<int> pair_of(pl.eitems.size(), 0);
+  for (int pr = 0; pr < pl.n_pairs; ++pr)
+    for (uint32_t e = pl.eitem_off[(size_t)pr * (pl.n_seg + 1)]; e < pl.eitem_off[(size_t)pr * (pl.n_seg + 1) + pl.n_seg]; ++e) pair_of[e] = pr;
+  for (size_t e = 0; e < pl.eitems.size(); ++e) {
+    const uint2 it = pl.eitems[e];
+    const int sg = (int)(it.x >> 16);
+    flag2item[pl.flag_base[(size_t)sg] + it.y * pl.n_windows[(size_t)sg] + (it.x & 0xFFFFu)] = (long long)e;
+  }
+  for (int e = 0; e < n; ++e) {
+    const uint2 it = pl.eitems[(size_t)e];
+    out[(size_t)e * 8 + 0] = (unsigned long long)pair_of[(size_t)e]; out[(size_t)e * 8 + 1] = it.x >> 16; out[(size_t)e * 8 + 2] = it.x & 0xFFFFu; out[(size_t)e * 8 + 3] = it.y;
+    for (int k = 0; k < 4; ++k) out[(size_t)e * 8 + 4 + k] = raw[(size_t)e * 4 + k];
+    if (deps_out != nullptr) {
+      int k = 0;
+      for (uint32_t d = pl.dep_off[(size_t)e]; d < pl.dep_off[(size_t)e + 1] && k < max_deps; ++d, ++k)
+        deps_out[(size_t)e * max_deps + k] = (pl.deps[d] & LOOP_DEP_PREV) ? -2 : flag2item[pl.deps[d]];
+      for (; k < max_deps; ++k) deps_out[(size_t)e * max_deps + k] = -1;
+    }
+  }
+  return n;
+}
+
 // Host-only developer/test aid (not in the public header): plan one L-step of the fp16 path for `n_rows` latent rows on
 // `n_pairs` CTA pairs exactly as dgan_reconstruct would, and validate the plan with loop_check_plan.  Needs no GPU.
 // `mutate` != 0 damages the plan in one specific way first: the check must then fail (self-test of the validator).
@@ -1223,7 +1268,7 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
     segs.push_back(sp);
   }
   LoopPlan plan;
-  int rc = loop_plan(segs, n_mpairs, n_pairs, true, &plan);
+  int rc = loop_plan(segs, n_mpairs, n_pairs, DGAN_LOOP_CARRY != 0, &plan);
   if (rc) return rc;
   if (mutate != 0) {
     // damage the stream of the first CTA pair inside its third segment (Generator.3 fwd on MNIST)

@@ -71,6 +71,8 @@ struct LoopParams {
   uint32_t* status;                // [0] != 0: a flag wait timed out (results invalid)
   unsigned long long* prof;        // optional [t][n_seg][2] globaltimer min-start / max-end
   unsigned long long* dbg;         // optional [CTA][16] stall counters of the roles (clock64 ticks), see LoopDbg
+  unsigned long long* trace;       // optional [items of one L-step][4] globaltimer: dependency wait begin / end, epilogue begin / end
+  int trace_step;                  // the L-step that is traced
   int n_seg, n_seg_last;           // segments per L-step; segments of the LAST L-step (forward only: SURVEY F4)
   int seg_begin, seg_end;          // segment sub-range of this launch (whole step: 0, n_seg)
   int t_begin, t_end;              // L-steps of this launch
@@ -448,6 +450,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       bool cur_f_valid = false;
       if (lane < cur_cnt) cur_e = __ldg(P.deps + cur_d0 + lane);
       uint32_t nxt_d0 = 0, nxt_cnt = 0, nxt_e = 0;
+      uint32_t trace_item = __ldg(eoff + P.seg_begin);          // index of the item about to start (trace only)
       uint4 mine = first;
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
@@ -466,6 +469,8 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
             // first step of an item: everything it stages must have been published.  Fast path: the flag values were
             // fetched while the previous item's last step was issued and already satisfy the target.
             const long long tw0 = P.dbg ? clock64() : 0;
+            const bool tracing = P.trace != nullptr && t == P.trace_step && leader && lane == 0;
+            if (tracing) P.trace[(size_t)trace_item * 4 + 0] = ptx::globaltimer();
             if (cur_cnt > 0) {
               const uint32_t target = LOOP_ARRIVALS * (uint32_t)((cur_e & LOOP_DEP_PREV) ? t : t + 1);
               const bool ok = (lane >= cur_cnt) || (cur_f_valid && cur_f >= target);
@@ -480,6 +485,8 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
               ptx::fence_proxy_async_all();             // acquired generic-proxy view -> the TMA (async proxy) reads below
             }
             if (P.dbg) t_flag += clock64() - tw0;
+            if (tracing) P.trace[(size_t)trace_item * 4 + 1] = ptx::globaltimer();
+            ++trace_item;
             // the NEXT item's dependency range rides in this record: fetch this lane's entry now, its flag at the item's last step
             nxt_d0 = r1.z; nxt_cnt = r1.w; nxt_e = 0;
             if (lane < nxt_cnt) nxt_e = __ldg(P.deps + nxt_d0 + lane);
@@ -686,8 +693,10 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         loop_epilogue_dispatch<ARCH>(P, sg, cx, fa, win, mp, flag);
         if (P.prof != nullptr && warp == LOOP_EPI_WARP0 && lane == 0 && leader) {
           unsigned long long* pr = P.prof + ((size_t)t * P.n_seg + seg) * 2;
+          const unsigned long long te = ptx::globaltimer();
           atomicMin(pr, ts);
-          atomicMax(pr + 1, ptx::globaltimer());
+          atomicMax(pr + 1, te);
+          if (P.trace != nullptr && t == P.trace_step) { P.trace[(size_t)k * 4 + 2] = ts; P.trace[(size_t)k * 4 + 3] = te; }
         }
       }
     }
@@ -740,6 +749,12 @@ struct LoopPlan {
 #endif
 #ifndef DGAN_COST_FIXED_KB
 #define DGAN_COST_FIXED_KB 48.0
+#endif
+#ifndef DGAN_LOOP_ORDER
+#define DGAN_LOOP_ORDER 0        // experiment switch: 0 = row-pair-major item order inside a segment, 1 = LPT (cost-descending) order
+#endif
+#ifndef DGAN_LOOP_CARRY
+#define DGAN_LOOP_CARRY 0        // experiment switch: 1 = a CTA pair's surplus load in one segment is deducted in the next
 #endif
 constexpr int LOOP_STEP_MAX_BYTES = 48 * 1024;    // measured optimum of the operand-ring kernels (round 1): 2 A tiles + weights
 
@@ -852,7 +867,9 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
       std::vector<int> mine = lists[(size_t)s][(size_t)pr];
       // row-pair major: a pair meets the row pairs in the same order in every segment, so what it waits for was
       // produced a whole segment-phase ago; inside a row pair keep the cost-descending order
+#if DGAN_LOOP_ORDER == 0
       std::stable_sort(mine.begin(), mine.end(), [&](int l, int r) { return (l % n_mpairs) < (r % n_mpairs); });
+#endif
       const int half_b = (sp.N / 2) * 128;
       for (int idx : mine) {
         const int win = idx / n_mpairs, mp = idx % n_mpairs;
