@@ -348,9 +348,9 @@ def timed(fn, steps, warmup, dev, flush, distributed):
 def kernel_breakdown(wl, peaks, precision):
     """Per-kernel pass (rank 0; not part of `value`): CUDA events around every launch of the production path.
     fp16: the whole call is ONE persistent kernel - that launch is the roofline's dominant kernel (FLOPs of L forward +
-    L-1 backward passes / its event-timed duration); its segments (layer-directions) are listed twice: as in-kernel
-    %globaltimer spans inside the fused launch (they overlap) and, from a second pass that runs one (L-step, segment)
-    per launch, as isolated per-launch durations (what a kernel-per-layer design pays).  fp32: one kernel per layer."""
+    L-1 backward passes / its event-timed duration); its segments (layer-directions) are listed as in-kernel %globaltimer
+    spans (first item start .. last item end over all CTA pairs, per row-pair group; they overlap).  fp32: one kernel
+    per layer."""
     nat = wl.gan._native
     x_loc = wl.x_full[:wl.B].contiguous()
     z_loc = wl.z0_full[:wl.B * wl.R].contiguous()
@@ -384,8 +384,7 @@ def kernel_breakdown(wl, peaks, precision):
         spans = [k for k in prof1 if not k["kernel"].startswith("projection_loop")]
         for k in spans:
             k["share"] = None          # spans overlap: shares of a sum are meaningless
-        kernels = {"fused_launch": loop, "segment_spans_inside_fused_launch": spans,
-                   "segments_one_launch_each": table(run(2))}
+        kernels = {"fused_launch": loop, "segment_spans_inside_fused_launch": spans}
         dom = loop[0] if loop else max(prof1, key=lambda k: k["avg_us"])
     else:
         dom = max(prof1, key=lambda k: k["share"])

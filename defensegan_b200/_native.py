@@ -223,8 +223,8 @@ class NativeGenerator:
         return int(v.value)
 
     def profile_enable(self, level) -> None:
-        """0 = off; 1 = time every launch of the production path (+ in-kernel segment spans of the fp16 loop kernel);
-        2 = fp16 only: run the loop one (L-step, segment) per launch, each timed in isolation."""
+        """0 = off; 1 = time every launch of the production path (the fp16 loop kernel also records in-kernel segment
+        spans, per-CTA stall counters and a per-item trace: tools/loop_stalls.py, tools/loop_trace.py)."""
         _check(self.lib, self.lib.dgan_profile_enable(self._handle, int(level)), "dgan_profile_enable")
 
     def profile_read(self):

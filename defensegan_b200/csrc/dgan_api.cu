@@ -138,13 +138,13 @@ struct SegBind {
 
 // one L-step plan (kernels_loop.cuh) uploaded for a given number of 256-row pairs
 struct DevPlan {
-  int n_mpairs = 0, n_pairs = 0;
+  int n_mpairs = 0, n_pairs = 0, n_groups = 1;
   dgan::LoopPlan host;
   dgan::TcItem2* items[dgan::LOOP_MAX_SEG] = {nullptr};
   dgan::TcRec* stream_p[2] = {nullptr, nullptr};
   dgan::TcRec* stream_m = nullptr;
   uint32_t *stream_off = nullptr, *eitem_off = nullptr, *dep_off = nullptr, *deps = nullptr;
-  uint2* eitems = nullptr;
+  uint4* eitems = nullptr;
 };
 
 struct dgan_ctx {
@@ -168,10 +168,11 @@ struct dgan_ctx {
   LoopParams lp;                          // launch parameters of the most recent workspace (tensor maps are encoded once)
   const void* lp_ws = nullptr; int lp_rows = -1; const DevPlan* lp_plan = nullptr;
   uint32_t* last_status = nullptr;        // device status word of the most recent loop launch (lives in its workspace)
-  // profiling (dgan_profile_*): 1 = time every launch of the production path and collect in-kernel segment spans;
-  // 2 = run the fp16 loop one (L-step, segment) per launch, each timed in isolation.  Never on in a throughput pass.
+  // profiling (dgan_profile_*): time every launch of the production path; the fp16 loop kernel also records in-kernel
+  // segment spans, per-CTA stall counters and a per-item trace.  Never on in a throughput pass.
   int profile = 0;
-  unsigned long long* prof_dev = nullptr; size_t prof_cap = 0; int prof_L = 0;
+  unsigned long long* prof_dev = nullptr; size_t prof_cap = 0; int prof_L = 0; const DevPlan* prof_plan = nullptr;
+  int loop_passes = 0;                    // generator passes (forward or backward) of the last loop launch: its FLOPs
   unsigned long long* dbg_dev = nullptr; int dbg_ctas = 0;   // per-CTA stall counters of the last profiled loop launch
   unsigned long long* trace_dev = nullptr; size_t trace_items = 0; const DevPlan* trace_plan = nullptr;   // per-item timestamps of one L-step
   int n_rows_cur = 0;
@@ -553,6 +554,7 @@ static int build_segments(dgan_ctx* c) {
     if (sp.kind < 0) { set_error(name + ": no epilogue variant for this layer shape (net_dim 64, latent 64/128/256 only)"); return DGAN_ERR_UNSUPPORTED; }
     sp.tab = &w2.tab; sp.h_grid = w2.h_grid; sp.w_grid = w2.w_grid; sp.max_acc = w2.max_acc; sp.in_seg = in_seg;
     sp.macs_per_row = macs;
+    sp.fwd = (int)c->segs.size() <= (int)c->layers.size();      // Linear + hidden layers + last layer forward
     b.w1 = &w1; b.w2 = &w2; b.epi = epi; b.out_bytes = out_bytes;
     c->segs.push_back(sp); c->binds.push_back(b);
     return 0;
@@ -617,17 +619,18 @@ static int upload_vec(dgan_ctx* c, const std::vector<T>& v, T** dev) {
 // in dgan_workspace_bytes - which a caller needs before its first dgan_reconstruct of a batch size anyway - so that
 // dgan_reconstruct itself never allocates or synchronises (it only falls back to planning here if the caller sized the
 // workspace some other way).
-static int get_plan(dgan_ctx* c, int n_rows, const DevPlan** out) {
+static int get_plan(dgan_ctx* c, int n_rows, int n_groups, const DevPlan** out) {
   const int n_pad = (int)align_up((size_t)std::max(n_rows, 1), 2 * kRowTile), n_mpairs = n_pad / (2 * kRowTile);
+  if (n_mpairs < 2) n_groups = 1;
   for (auto& p : c->plans)
-    if (p->n_mpairs == n_mpairs) { *out = p.get(); return 0; }
+    if (p->n_mpairs == n_mpairs && p->n_groups == n_groups) { *out = p.get(); return 0; }
   std::unique_ptr<DevPlan> dp(new DevPlan());
-  dp->n_mpairs = n_mpairs; dp->n_pairs = c->n_pairs;
+  dp->n_mpairs = n_mpairs; dp->n_pairs = c->n_pairs; dp->n_groups = n_groups;
   int rc;
-  if ((rc = loop_plan(c->segs, n_mpairs, c->n_pairs, /*carry_load=*/DGAN_LOOP_CARRY != 0, &dp->host))) return rc;
+  if ((rc = loop_plan(c->segs, n_mpairs, c->n_pairs, n_groups, &dp->host))) return rc;
   const LoopPlan& pl = dp->host;
-  for (int s = 0; s < pl.n_seg; ++s)
-    if ((rc = upload_vec(c, pl.hdrs[(size_t)s], &dp->items[s]))) return rc;
+  for (int v = 0; v < pl.n_vseg; ++v)
+    if ((rc = upload_vec(c, pl.hdrs[(size_t)v], &dp->items[v]))) return rc;
   for (int r = 0; r < 2; ++r)
     if ((rc = upload_vec(c, pl.stream_p[r], &dp->stream_p[r]))) return rc;
   if ((rc = upload_vec(c, pl.stream_m, &dp->stream_m))) return rc;
@@ -660,10 +663,11 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
       default: *base = w.g; *chan = latent; *pix = TC_LINEAR_SPLIT; break;
     }
   };
-  for (int s = 0; s < pl.n_seg; ++s) {
+  for (int v = 0; v < pl.n_vseg; ++v) {
+    const int s = pl.vseg_phys[(size_t)v];
     const SegBind& b = c->binds[(size_t)s];
     const LoopSegSpec& sp = c->segs[(size_t)s];
-    LoopSeg& g = P.seg[s];
+    LoopSeg& g = P.seg[v];
     const void* base; int chan, pix;
     tensor(b.in_kind, b.in_idx, &base, &chan, &pix);
     if (chan != sp.K) { set_error("internal: segment input channels"); return DGAN_ERR_INVALID_ARG; }
@@ -678,17 +682,17 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
     g.bias = b.bias;
     g.mb_out = b.mb_out_layer >= 0 ? w.maskbits[(size_t)b.mb_out_layer] : nullptr;
     g.mb_in = b.mb_in_layer >= 0 ? w.maskbits[(size_t)b.mb_in_layer] : nullptr;
-    g.items = dp->items[s];
+    g.items = dp->items[v];
     g.n_tile = (uint32_t)sp.N; g.kind = (uint32_t)sp.kind; g.bias_pstride = (uint32_t)b.bias_pstride;
     g.acc_stride = (uint32_t)tc2_acc_stride(sp.N);
     g.idesc = make_idesc_f16(256, sp.N);
     g.half_b = (uint32_t)(sp.N / 2) * 128u;
-    g.flag_base = pl.flag_base[(size_t)s]; g.n_windows = pl.n_windows[(size_t)s];
+    g.phys = (uint32_t)s; g.group = (uint32_t)pl.vseg_group[(size_t)v];
   }
   P.stream_p[0] = dp->stream_p[0]; P.stream_p[1] = dp->stream_p[1]; P.stream_m = dp->stream_m;
   P.stream_off = dp->stream_off; P.eitems = dp->eitems; P.eitem_off = dp->eitem_off; P.dep_off = dp->dep_off; P.deps = dp->deps;
-  P.flags = w.flags; P.status = w.status; P.prof = nullptr; P.dbg = nullptr; P.trace = nullptr; P.trace_step = -1;
-  P.n_seg = pl.n_seg; P.n_pad = w.n_pad; P.n_mpairs = dp->n_mpairs;
+  P.flags = w.flags; P.status = w.status; P.prof = nullptr; P.dbg = nullptr; P.trace = nullptr; P.trace_entry = -2;
+  P.n_groups = pl.n_groups; P.n_vseg = pl.n_vseg; P.n_pad = w.n_pad; P.n_mpairs = dp->n_mpairs;
   P.y = w.y; P.loss_part = w.loss_part; P.n_rows = w.n_rows; P.nbx = c->tc_fin.nbx; P.w_out = c->tc_fin.w_out;
   P.gscale = c->tc.grad_scale;
   P.mz = w.z; P.mv = w.v; P.mz_h = w.z_h; P.m_nparts = w.n_g_parts; P.m_count = (size_t)w.n_pad * c->desc.latent_dim;
@@ -700,83 +704,71 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
 enum LoopMode : int { LOOP_RECONSTRUCT = 0, LOOP_FORWARD = 1, LOOP_LOSS_GRAD = 2 };
 
 // Enqueue the loop kernel: rec_iters L-steps of (forward, loss, backward-to-z, momentum); the final L-step is forward
-// only (the loop returns the pre-update forward of iteration L-1, models/gan.py:419-421).
+// only (the loop returns the pre-update forward of iteration L-1, models/gan.py:419-421).  A projection runs
+// the two-group plan (row pairs half an L-step out of phase, see LoopPlan); dgan_forward / dgan_loss_grad - one
+// evaluation, nothing to overlap - the one-group plan.
 static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, const float* x, int R, int B, int rec_iters,
                        float lr, float mu, int decay_lr, int mode, cudaStream_t s) {
   const DevPlan* dp = nullptr;
   int rc;
-  if ((rc = get_plan(c, w.n_rows, &dp))) return rc;
+  if ((rc = get_plan(c, w.n_rows, mode == LOOP_RECONSTRUCT ? DGAN_LOOP_GROUPS : 1, &dp))) return rc;
   if ((rc = build_params(c, w, ws_base, dp))) return rc;
   LoopParams P = c->lp;
   P.x = x; P.R = R; P.B = B;
   P.m_gmul = grad_multiplier(c); P.m_lr = lr; P.m_mu = mu;
   P.m_counter = (mode == LOOP_RECONSTRUCT) ? w.mom_counter : nullptr;
   P.decay_step = decay_lr ? (int)std::ceil(rec_iters * 0.8) : 0;
-  P.n_seg_last = (mode == LOOP_LOSS_GRAD) ? P.n_seg : c->n_fwd_seg;
   P.last_step = rec_iters - 1;
+  P.n_prog = loop_prog_length(dp->n_groups, rec_iters, mode == LOOP_LOSS_GRAD);
   c->last_status = w.status;
+  c->loop_passes = (mode == LOOP_LOSS_GRAD) ? 2 * rec_iters : 2 * rec_iters - 1;
   const dim3 grid((unsigned)(2 * dp->n_pairs)), block(LOOP_THREADS);
-  auto go = [&](const LoopParams& Q) -> cudaError_t {
-    if (c->desc.arch == DGAN_ARCH_CELEBA) projection_loop_kernel<DGAN_ARCH_CELEBA><<<grid, block, LOOP_SMEM_BYTES, s>>>(Q);
-    else projection_loop_kernel<DGAN_ARCH_MNIST><<<grid, block, LOOP_SMEM_BYTES, s>>>(Q);
-    c->launches++;
-    return cudaGetLastError();
-  };
-  cudaError_t e = cudaSuccess;
-  if (c->profile == 2) {
-    // one (L-step, segment) per launch, each bracketed by events: isolated per-segment durations (their sum exceeds the
-    // fused kernel's time - that difference is what the fusion buys)
-    for (int t = 0; t < rec_iters && e == cudaSuccess; ++t) {
-      const int s_end = (t == rec_iters - 1) ? P.n_seg_last : P.n_seg;
-      for (int sg = 0; sg < s_end && e == cudaSuccess; ++sg) {
-        LoopParams Q = P;
-        Q.t_begin = t; Q.t_end = t + 1; Q.seg_begin = sg; Q.seg_end = sg + 1;
-        ProfScope ps(c, sg, s);
-        e = go(Q);
-      }
+  if (c->profile == 1) {
+    // in-kernel spans: [L-step][virtual segment] {min start, max end} of %globaltimer; per-CTA stall counters; item trace
+    const size_t need = (size_t)rec_iters * P.n_vseg * 2;
+    if (need > c->prof_cap) {
+      if (c->prof_dev) cudaFree(c->prof_dev);
+      c->prof_dev = nullptr; c->prof_cap = 0;
+      DGAN_CUDA_CHECK(cudaMalloc((void**)&c->prof_dev, need * sizeof(unsigned long long)));
+      c->prof_cap = need;
     }
-  } else {
-    P.t_begin = 0; P.t_end = rec_iters; P.seg_begin = 0; P.seg_end = P.n_seg;
-    if (c->profile == 1) {
-      // in-kernel segment spans: [t][segment] {min start, max end} of %globaltimer
-      const size_t need = (size_t)rec_iters * P.n_seg * 2;
-      if (need > c->prof_cap) {
-        if (c->prof_dev) cudaFree(c->prof_dev);
-        c->prof_dev = nullptr; c->prof_cap = 0;
-        DGAN_CUDA_CHECK(cudaMalloc((void**)&c->prof_dev, need * sizeof(unsigned long long)));
-        c->prof_cap = need;
-      }
-      std::vector<unsigned long long> init(need);
-      for (size_t i = 0; i < need; i += 2) { init[i] = ~0ull; init[i + 1] = 0ull; }
-      DGAN_CUDA_CHECK(cudaMemcpyAsync(c->prof_dev, init.data(), need * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
-      DGAN_CUDA_CHECK(cudaStreamSynchronize(s));     // `init` dies with this scope (profiling mode only)
-      P.prof = c->prof_dev; c->prof_L = rec_iters;
-      const int n_ctas = 2 * dp->n_pairs;
-      if (c->dbg_dev == nullptr || c->dbg_ctas < n_ctas) {
-        if (c->dbg_dev) cudaFree(c->dbg_dev);
-        c->dbg_dev = nullptr; c->dbg_ctas = 0;
-        DGAN_CUDA_CHECK(cudaMalloc((void**)&c->dbg_dev, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long)));
-        c->dbg_ctas = n_ctas;
-      }
-      DGAN_CUDA_CHECK(cudaMemsetAsync(c->dbg_dev, 0, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long), s));
-      P.dbg = c->dbg_dev;
-      const size_t n_items = dp->host.eitems.size();
-      if (c->trace_dev == nullptr || c->trace_items < n_items) {
-        if (c->trace_dev) cudaFree(c->trace_dev);
-        c->trace_dev = nullptr; c->trace_items = 0;
-        DGAN_CUDA_CHECK(cudaMalloc((void**)&c->trace_dev, n_items * 4 * sizeof(unsigned long long)));
-        c->trace_items = n_items;
-      }
-      DGAN_CUDA_CHECK(cudaMemsetAsync(c->trace_dev, 0, n_items * 4 * sizeof(unsigned long long), s));
-      P.trace = c->trace_dev; P.trace_step = std::max(0, rec_iters - 3); c->trace_plan = dp;
+    std::vector<unsigned long long> init(need);
+    for (size_t i = 0; i < need; i += 2) { init[i] = ~0ull; init[i + 1] = 0ull; }
+    DGAN_CUDA_CHECK(cudaMemcpyAsync(c->prof_dev, init.data(), need * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    DGAN_CUDA_CHECK(cudaStreamSynchronize(s));     // `init` dies with this scope (profiling mode only)
+    P.prof = c->prof_dev; c->prof_L = rec_iters; c->prof_plan = dp;
+    const int n_ctas = 2 * dp->n_pairs;
+    if (c->dbg_dev == nullptr || c->dbg_ctas < n_ctas) {
+      if (c->dbg_dev) cudaFree(c->dbg_dev);
+      c->dbg_dev = nullptr; c->dbg_ctas = 0;
+      DGAN_CUDA_CHECK(cudaMalloc((void**)&c->dbg_dev, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long)));
+      c->dbg_ctas = n_ctas;
     }
+    DGAN_CUDA_CHECK(cudaMemsetAsync(c->dbg_dev, 0, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long), s));
+    P.dbg = c->dbg_dev;
+    const size_t n_items = dp->host.eitems.size();
+    if (c->trace_dev == nullptr || c->trace_items < n_items) {
+      if (c->trace_dev) cudaFree(c->trace_dev);
+      c->trace_dev = nullptr; c->trace_items = 0;
+      DGAN_CUDA_CHECK(cudaMalloc((void**)&c->trace_dev, n_items * 4 * sizeof(unsigned long long)));
+      c->trace_items = n_items;
+    }
+    DGAN_CUDA_CHECK(cudaMemsetAsync(c->trace_dev, 0, n_items * 4 * sizeof(unsigned long long), s));
+    // two consecutive program entries in the steady state: section 1 then section 2
+    P.trace = c->trace_dev; c->trace_plan = dp;
+    P.trace_entry = std::max(0, ((P.n_prog - 4) | 1));
+  }
+  cudaError_t e;
+  {
     ProfScope ps(c, (int)c->kind_names.size() - 1, s);
-    e = go(P);
+    if (c->desc.arch == DGAN_ARCH_CELEBA) projection_loop_kernel<DGAN_ARCH_CELEBA><<<grid, block, LOOP_SMEM_BYTES, s>>>(P);
+    else projection_loop_kernel<DGAN_ARCH_MNIST><<<grid, block, LOOP_SMEM_BYTES, s>>>(P);
+    c->launches++;
+    e = cudaGetLastError();
   }
   if (e != cudaSuccess) { set_error(std::string("projection_loop launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
   return 0;
 }
-
 
 }  // namespace dgan
 
@@ -1010,7 +1002,7 @@ size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
   if (h->desc.precision == DGAN_PREC_FP16) {
     // plan (and upload) the loop kernel's schedule for this row count now, so that dgan_reconstruct never has to
     const DevPlan* dp = nullptr;
-    if (get_plan(h, batch * rec_rr, &dp) != 0) return 0;
+    if (get_plan(h, batch * rec_rr, DGAN_LOOP_GROUPS, &dp) != 0) return 0;
   }
   return carve(h, batch * rec_rr, nullptr).bytes;
 }
@@ -1130,7 +1122,7 @@ int dgan_profile_enable(dgan_handle h, int enable) {
   if (h == nullptr) return DGAN_ERR_INVALID_ARG;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   h->prof.clear();
-  h->profile = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+  h->profile = enable != 0 ? 1 : 0;
   h->prof_L = 0;
   return DGAN_OK;
 }
@@ -1158,17 +1150,21 @@ int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* lau
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   h->prof.clear();
-  if (tc && h->profile == 1 && h->prof_L > 0 && h->prof_dev != nullptr) {
-    // the fused launch: its FLOPs are L forward + (L - 1) backward passes; its segments are reported as in-kernel spans
-    // (first item start .. last item end over all CTA pairs, summed over the L-steps; spans of neighbouring segments overlap)
-    const int n_seg = (int)h->segs.size(), L = h->prof_L;
-    if (nk == n_seg + 1) flops_per_launch_out[n_seg] *= (double)(2 * L - 1);
-    std::vector<unsigned long long> st((size_t)L * n_seg * 2);
+  if (tc && h->profile == 1 && h->prof_L > 0 && h->prof_dev != nullptr && h->prof_plan != nullptr) {
+    // the fused launch: its FLOPs are those of `loop_passes` generator passes; its segments are reported as in-kernel
+    // spans (first item start .. last item end over all CTA pairs, per row-pair group and L-step; spans of neighbouring
+    // segments - and of the two groups, which run half a step apart - overlap)
+    const LoopPlan& pl = h->prof_plan->host;
+    const int n_phys = (int)h->segs.size(), L = h->prof_L, nv = pl.n_vseg;
+    if (nk == n_phys + 1) flops_per_launch_out[n_phys] *= 0.5 * (double)h->loop_passes;
+    std::vector<unsigned long long> st((size_t)L * nv * 2);
     DGAN_CUDA_CHECK(cudaMemcpy(st.data(), h->prof_dev, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int sg = 0; sg < n_phys && sg < nk; ++sg) flops_per_launch_out[sg] /= (double)pl.n_groups;     // a span covers one group's rows
     for (int t = 0; t < L; ++t)
-      for (int sg = 0; sg < n_seg && sg < nk; ++sg) {
-        const unsigned long long a = st[((size_t)t * n_seg + sg) * 2], b = st[((size_t)t * n_seg + sg) * 2 + 1];
-        if (a == ~0ull || b <= a) continue;
+      for (int v = 0; v < nv; ++v) {
+        const int sg = pl.vseg_phys[(size_t)v];
+        const unsigned long long a = st[((size_t)t * nv + v) * 2], b = st[((size_t)t * nv + v) * 2 + 1];
+        if (sg >= nk || a == ~0ull || b <= a) continue;
         ms_out[sg] += (double)(b - a) * 1e-6;
         launches_out[sg]++;
       }
@@ -1201,14 +1197,12 @@ int dgan_debug_loop_trace(dgan_handle h, unsigned long long* out, long long* dep
   std::vector<long long> flag2item(pl.n_flags, -1);
   std::vector<int> pair_of(pl.eitems.size(), 0);
   for (int pr = 0; pr < pl.n_pairs; ++pr)
-    for (uint32_t e = pl.eitem_off[(size_t)pr * (pl.n_seg + 1)]; e < pl.eitem_off[(size_t)pr * (pl.n_seg + 1) + pl.n_seg]; ++e) pair_of[e] = pr;
-  for (size_t e = 0; e < pl.eitems.size(); ++e) {
-    const uint2 it = pl.eitems[e];
-    const int sg = (int)(it.x >> 16);
-    flag2item[pl.flag_base[(size_t)sg] + it.y * pl.n_windows[(size_t)sg] + (it.x & 0xFFFFu)] = (long long)e;
-  }
+    for (uint32_t e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1)]; e < pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + LOOP_N_SEC]; ++e) pair_of[e] = pr;
+  // the traced entries are sections 1 and 2: map a flag to the item of those sections that publishes it
+  for (int pr = 0; pr < pl.n_pairs; ++pr)
+    for (uint32_t e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + 1]; e < pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + 3]; ++e) flag2item[pl.eitems[e].z] = (long long)e;
   for (int e = 0; e < n; ++e) {
-    const uint2 it = pl.eitems[(size_t)e];
+    const uint4 it = pl.eitems[(size_t)e];
     out[(size_t)e * 8 + 0] = (unsigned long long)pair_of[(size_t)e]; out[(size_t)e * 8 + 1] = it.x >> 16; out[(size_t)e * 8 + 2] = it.x & 0xFFFFu; out[(size_t)e * 8 + 3] = it.y;
     for (int k = 0; k < 4; ++k) out[(size_t)e * 8 + 4 + k] = raw[(size_t)e * 4 + k];
     if (deps_out != nullptr) {
@@ -1225,15 +1219,16 @@ int dgan_debug_loop_trace(dgan_handle h, unsigned long long* out, long long* dep
 // `n_pairs` CTA pairs exactly as dgan_reconstruct would, and validate the plan with loop_check_plan.  Needs no GPU.
 // `mutate` != 0 damages the plan in one specific way first: the check must then fail (self-test of the validator).
 // Returns 0, or an error code with the failing check in dgan_last_error().
-int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int mutate) {
+int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int n_groups, int mutate) {
   using namespace dgan;
   if (d == nullptr || n_rows <= 0 || n_pairs <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
   const bool celeba = d->arch == DGAN_ARCH_CELEBA;
   const int nd = d->net_dim, latent = d->latent_dim;
   const int n_pad = ((n_rows + 2 * kRowTile - 1) / (2 * kRowTile)) * 2 * kRowTile, n_mpairs = n_pad / (2 * kRowTile);
-  struct Dir { std::string name; int N, K; PairTable tab; int h, w, force_acc, epi, out_bytes; };
+  if (n_mpairs < 2) n_groups = 1;
+  struct Dir { std::string name; int N, K; PairTable tab; int h, w, force_acc, epi, out_bytes; bool fwd; };
   std::vector<Dir> fwd, bwd;
-  fwd.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2});
+  fwd.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2, true});
   struct DSpec { int c_in, c_out, h_in, h_used, in_raster; bool relu; };
   std::vector<DSpec> specs;
   if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, 4, true}, {2 * nd, nd, 8, 16, 8, true}, {nd, nd, 16, 32, 16, false}};
@@ -1243,18 +1238,18 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
   for (const DSpec& sp : specs) {
     const std::string nm = "Generator." + std::to_string(li == 4 ? 5 : li);
     fwd.push_back({nm + ".fwd", sp.c_out, sp.c_in, deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.h_used, sp.h_used, 0,
-                   sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2});
+                   sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2, true});
     bwd.push_back({nm + ".bwd", sp.c_in, sp.c_out, deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.in_raster, sp.in_raster, 0,
-                   prev_relu ? EPI_MASK : EPI_NONE, 2});
+                   prev_relu ? EPI_MASK : EPI_NONE, 2, false});
     prev_relu = sp.relu;
     ++li;
   }
   const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
-  fwd.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2});
+  fwd.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2, true});
   std::vector<Dir> dirs = fwd;
-  dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, prev_relu ? EPI_MASK : EPI_NONE, 2});
+  dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, prev_relu ? EPI_MASK : EPI_NONE, 2, false});
   for (size_t i = bwd.size(); i-- > 0;) dirs.push_back(bwd[i]);
-  dirs.push_back({"Linear.bwd", latent, 4 * nd, linear_split_pairs(16), 1, TC_LINEAR_SPLIT, 1, EPI_NONE, 4});
+  dirs.push_back({"Linear.bwd", latent, 4 * nd, linear_split_pairs(16), 1, TC_LINEAR_SPLIT, 1, EPI_NONE, 4, false});
   std::vector<LoopSegSpec> segs;
   for (size_t i = 0; i < dirs.size(); ++i) {
     const Dir& dr = dirs[i];
@@ -1264,26 +1259,28 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
     sp.tab = &dirs[i].tab; sp.h_grid = dr.h; sp.w_grid = dr.w;
     sp.max_acc = tc2_maxb(dr.N);
     if (dr.force_acc > 0) sp.max_acc = std::min(sp.max_acc, dr.force_acc);
-    sp.in_seg = (int)i - 1;
+    sp.in_seg = (int)i - 1; sp.fwd = dr.fwd;
     segs.push_back(sp);
   }
   LoopPlan plan;
-  int rc = loop_plan(segs, n_mpairs, n_pairs, DGAN_LOOP_CARRY != 0, &plan);
+  int rc = loop_plan(segs, n_mpairs, n_pairs, n_groups, &plan);
   if (rc) return rc;
   if (mutate != 0) {
-    // damage the stream of the first CTA pair inside its third segment (Generator.3 fwd on MNIST)
+    // damage the records of the first CTA pair inside section 2 (the forward half of group A, where Generator.3 fwd lives)
     const size_t r0 = plan.stream_off[2], r1 = plan.stream_off[3];
-    if (r1 - r0 < 8) { set_error("plan too small to mutate"); return DGAN_ERR_INVALID_ARG; }
-    const size_t k = r0 + 4;
+    if (r1 - r0 < 12) { set_error("plan too small to mutate"); return DGAN_ERR_INVALID_ARG; }
+    size_t k = r0 + (r1 - r0) / 2;
+    while (k + 2 < r1 && ((plan.stream_m[k].w[0] >> 16) & 3u)) ++k;          // a step in the middle of an item
     TcRec& m = plan.stream_m[k];
     TcRec* pp[2] = {&plan.stream_p[0][k], &plan.stream_p[1][k]};
+    const uint32_t e2 = plan.eitem_off[2];
     switch (mutate) {
       case 1: m.w[2] ^= 1u << 10; break;                                  // first-MMA flag of an op
       case 2: m.w[2] ^= 1u << 7; break;                                   // accumulator of an op
       case 3: pp[0]->w[4] ^= 0x01; break;                                 // weight tile staged by rank 0 only
       case 4: pp[0]->w[2] ^= 0x01; pp[1]->w[2] ^= 0x01; break;            // input pixel of an A tile
       case 5: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~(0xFu << 8)) | ((((pp[r]->w[0] >> 8) & 0xF) ^ 1u) << 8); break;   // k-chunk
-      case 6: plan.eitems[plan.eitem_off[2]].x ^= 1u; break;              // epilogue list names another window
+      case 6: plan.eitems[e2].x ^= 1u; break;                             // epilogue list names another window
       case 7: for (size_t i = 0; i < plan.stream_m.size(); ++i)           // every dep -> 8: ring hazards
                 for (int r = 0; r < 2; ++r) plan.stream_p[r][i].w[0] = (plan.stream_p[r][i].w[0] & ~(0xFu << 19)) | (8u << 19);
               break;
@@ -1291,10 +1288,10 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
       case 9: std::swap(plan.stream_m[k], plan.stream_m[k + 1]);          // two steps out of order
               for (int r = 0; r < 2; ++r) std::swap(plan.stream_p[r][k], plan.stream_p[r][k + 1]);
               break;
-      case 10: plan.deps[plan.dep_off[plan.eitem_off[2]]] ^= 1u; break;   // an item waits for the wrong window
-      case 11: {                                                          // two items of a pair swapped across segments: deadlock / order
-        const uint32_t a = plan.eitem_off[1], b = plan.eitem_off[2];
-        std::swap(plan.eitems[a], plan.eitems[b]);
+      case 10: plan.deps[plan.dep_off[e2 + 1]] ^= 1u; break;              // an item waits for the wrong window
+      case 11: plan.eitems[e2].z += 1u; break;                            // an item publishes another item's flag
+      case 12: {                                                          // the pair's first two items of the section swapped in the item list only
+        std::swap(plan.eitems[e2], plan.eitems[e2 + 1]);
         break;
       }
       default: break;
@@ -1303,19 +1300,14 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
   std::string err;
   if ((rc = loop_check_plan(segs, plan, &err))) { set_error(err); return rc; }
   // summary of the plan (read it with dgan_last_error() after a successful call)
-  std::string sum = "segments:";
-  for (size_t i = 0; i < segs.size(); ++i) {
-    long long steps = 0, items = 0;
-    for (int pr = 0; pr < n_pairs; ++pr) {
-      steps += plan.stream_off[(size_t)pr * (segs.size() + 1) + i + 1] - plan.stream_off[(size_t)pr * (segs.size() + 1) + i];
-      items += plan.eitem_off[(size_t)pr * (segs.size() + 1) + i + 1] - plan.eitem_off[(size_t)pr * (segs.size() + 1) + i];
-    }
-    sum += " [" + segs[i].name + " window " + std::to_string(plan.shape[4 * i]) + "x" + std::to_string(plan.shape[4 * i + 1]) + " stride " +
-           std::to_string(plan.shape[4 * i + 2]) + "x" + std::to_string(plan.shape[4 * i + 3]) + ", " + std::to_string(plan.hdrs[i].size()) +
-           " windows, " + std::to_string(items) + " items, " + std::to_string(steps) + " steps]";
-  }
-  sum += " total " + std::to_string(plan.n_steps) + " steps, " + std::to_string(plan.n_mma) + " MMAs, " +
-         std::to_string(2.0 * plan.n_bytes / 1e6) + " MB staged per L-step, " + std::to_string(plan.deps.size()) + " dependencies, " +
+  std::string sum = std::to_string(plan.n_groups) + " group(s); segments:";
+  for (int v = 0; v < plan.n_vseg; ++v)
+    sum += " [" + std::string(plan.vseg_group[(size_t)v] ? "B." : "A.") + segs[(size_t)plan.vseg_phys[(size_t)v]].name + " window " +
+           std::to_string(plan.shape[4 * v]) + "x" + std::to_string(plan.shape[4 * v + 1]) + " stride " + std::to_string(plan.shape[4 * v + 2]) + "x" +
+           std::to_string(plan.shape[4 * v + 3]) + ", " + std::to_string(plan.hdrs[(size_t)v].size()) + " windows x " +
+           std::to_string(plan.group_mps[(size_t)plan.vseg_group[(size_t)v]].size()) + " row pairs]";
+  sum += " per L-step: " + std::to_string(plan.n_steps) + " steps, " + std::to_string(plan.n_mma) + " MMAs, " +
+         std::to_string(2.0 * plan.n_bytes / 1e6) + " MB staged, " + std::to_string(plan.deps.size()) + " dependencies (all sections), " +
          std::to_string(plan.n_flags) + " flags";
   set_error(sum);
   return 0;

@@ -22,7 +22,8 @@
 
 namespace dgan {
 
-constexpr int LOOP_MAX_SEG = 10;
+constexpr int LOOP_MAX_SEG = 20;      // virtual segments: (row-pair group) x (layer-direction)
+constexpr int LOOP_N_SEC = 4;         // stream sections per CTA pair (see LoopPlan)
 // Warp roles, by warpgroup so that registers can be re-balanced with setmaxnreg: warpgroup 0 = TMA producer (warp 0),
 // MMA issuer (warp 1) and two idle warps, trimmed to LOOP_REGS_CTRL registers; warpgroups 1-2 = the 8 epilogue warps,
 // raised to LOOP_REGS_EPI (the epilogue holds two 32-column TMEM loads in flight while it converts a 64-column unit:
@@ -55,28 +56,54 @@ struct __align__(64) LoopSeg {
   const unsigned long long* mb_in;
   const TcItem2* items;
   uint32_t n_tile, kind, bias_pstride, acc_stride;
-  uint32_t idesc, half_b, flag_base, n_windows;
+  uint32_t idesc, half_b, phys, group;      // phys: layer-direction index (profiling); group: which row-pair group's L-step counter applies
 };
 
+// One entry of the launch's program: run section `sec` of every CTA pair's stream with the given L-step index per row-pair
+// group.  flags bit 0: the operand ring must be drained first (the section's ring plan assumes another predecessor).
+struct LoopProg { int32_t sec, t0, t1, flags; };
+
+// Entry `pi` of the program of a launch over `n_groups` row-pair groups (see LoopPlan for the sections):
+//   two groups:  sec0 [A.fwd(0)],  then for j = 0 .. L-2:  sec1 [A.bwd(j) | B.fwd(j)],  sec2 [A.fwd(j+1) | B.bwd(j)],  then sec3 [B.fwd(L-1)]
+//   one group:   sec2 [fwd(0)],    then for j = 0 .. L-2:  sec1 [bwd(j)],  sec2 [fwd(j+1)]      (+ sec1 [bwd(L-1)] for dgan_loss_grad)
+__host__ __device__ inline LoopProg loop_prog_entry(int n_groups, int n_prog, int pi) {
+  LoopProg e;
+  if (n_groups == 2) {
+    if (pi == 0) { e.sec = 0; e.t0 = 0; e.t1 = -1; e.flags = 0; return e; }
+    if (pi == n_prog - 1) { e.sec = 3; e.t0 = -1; e.t1 = (n_prog - 2) / 2; e.flags = 1; return e; }
+    const int j = (pi - 1) >> 1;
+    if (pi & 1) { e.sec = 1; e.t0 = j; e.t1 = j; e.flags = (j == 0) ? 1 : 0; }
+    else { e.sec = 2; e.t0 = j + 1; e.t1 = j; e.flags = 0; }
+    return e;
+  }
+  if (pi == 0) { e.sec = 2; e.t0 = e.t1 = 0; e.flags = 0; return e; }
+  const int j = (pi - 1) >> 1;
+  e.sec = (pi & 1) ? 1 : 2;
+  e.t0 = e.t1 = (pi & 1) ? j : j + 1;
+  e.flags = 0;
+  return e;
+}
+inline int loop_prog_length(int n_groups, int rec_iters, bool full_last) {
+  return n_groups == 2 ? 2 * rec_iters : 2 * rec_iters - 1 + (full_last ? 1 : 0);
+}
+
 struct LoopParams {
-  LoopSeg seg[LOOP_MAX_SEG];
-  const TcRec* stream_p[2];        // producer records per cluster rank: per CTA pair, the steps of ONE L-step
+  LoopSeg seg[LOOP_MAX_SEG];       // virtual segments
+  const TcRec* stream_p[2];        // producer records per cluster rank: per CTA pair its LOOP_N_SEC sections, back to back
   const TcRec* stream_m;           // MMA records, same indexing
-  const uint32_t* stream_off;      // [n_pairs][n_seg + 1] record offsets (segment boundaries inside a pair's stream)
-  const uint2* eitems;             // items in stream order, all pairs: x = seg << 16 | window, y = row pair
-  const uint32_t* eitem_off;       // [n_pairs][n_seg + 1] item offsets
+  const uint32_t* stream_off;      // [n_pairs][LOOP_N_SEC + 1] record offsets
+  const uint4* eitems;             // items in stream order, all pairs: x = vseg << 16 | window, y = row pair, z = flag index
+  const uint32_t* eitem_off;       // [n_pairs][LOOP_N_SEC + 1] item offsets
   const uint32_t* dep_off;         // [items + 1] -> deps
   const uint32_t* deps;            // flag indices (| LOOP_DEP_PREV)
   uint32_t* flags;                 // zeroed per call
   uint32_t* status;                // [0] != 0: a flag wait timed out (results invalid)
-  unsigned long long* prof;        // optional [t][n_seg][2] globaltimer min-start / max-end
+  unsigned long long* prof;        // optional [t][n_vseg][2] globaltimer min-start / max-end
   unsigned long long* dbg;         // optional [CTA][16] stall counters of the roles (clock64 ticks), see LoopDbg
-  unsigned long long* trace;       // optional [items of one L-step][4] globaltimer: dependency wait begin / end, epilogue begin / end
-  int trace_step;                  // the L-step that is traced
-  int n_seg, n_seg_last;           // segments per L-step; segments of the LAST L-step (forward only: SURVEY F4)
-  int seg_begin, seg_end;          // segment sub-range of this launch (whole step: 0, n_seg)
-  int t_begin, t_end;              // L-steps of this launch
-  int last_step;                   // index of the call's final L-step (rec_iters - 1)
+  unsigned long long* trace;       // optional [items of the traced program entry][4] globaltimer: dependency wait begin / end, epilogue begin / end
+  int trace_entry;                 // the program entries trace_entry and trace_entry + 1 are traced
+  int n_prog, n_groups, n_vseg;    // program length (loop_prog_entry), row-pair groups, virtual segments
+  int last_step;                   // index of the call's final L-step (rec_iters - 1): its forward writes G(z) and the loss
   int n_pad, n_mpairs;
   // last layer / loss (models/gan.py:411-414)
   const float* x; float* y; float* loss_part;
@@ -416,8 +443,8 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const uint32_t* __restrict__ soff = P.stream_off + (size_t)pair * (P.n_seg + 1);
-  const uint32_t* __restrict__ eoff = P.eitem_off + (size_t)pair * (P.n_seg + 1);
+  const uint32_t* __restrict__ soff = P.stream_off + (size_t)pair * (LOOP_N_SEC + 1);
+  const uint32_t* __restrict__ eoff = P.eitem_off + (size_t)pair * (LOOP_N_SEC + 1);
 
   if (warp < LOOP_EPI_WARP0) {
    ptx::setmaxnreg_dec<LOOP_REGS_CTRL>();
@@ -426,32 +453,31 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     const TcRec* __restrict__ stream = rank ? P.stream_p[1] : P.stream_p[0];
     const uint32_t ring = stg_base;
     uint32_t it = 0;                                      // steps issued so far, over all replays (barrier slot / phase)
-    const uint32_t rbeg = __ldg(soff + P.seg_begin);
-    uint4 first = make_uint4(0, 0, 0, 0);                 // the replays all start with the same records
-    {
-      const uint32_t rend_max = __ldg(soff + P.seg_end);
-      if (2 * rbeg + lane < 2 * rend_max) first = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
-    }
-    // dependencies of the replay's first item (the same every replay); later items are described one item ahead by the
-    // records themselves (w[6], w[7] of an item's first step = dependency range of the NEXT item)
-    uint32_t first_d0 = 0, first_cnt = 0;
-    {
-      const uint32_t i0 = __ldg(eoff + P.seg_begin), i1 = __ldg(eoff + P.seg_end);
-      if (i0 < i1) { first_d0 = __ldg(P.dep_off + i0); first_cnt = __ldg(P.dep_off + i0 + 1) - first_d0; }
-    }
     long long t_flag = 0, t_ring = 0, n_slow = 0;
     const long long t_p0 = P.dbg ? clock64() : 0;
-    for (int t = P.t_begin; t < P.t_end; ++t) {
-      const int s_end = min(P.seg_end, (t == P.last_step) ? P.n_seg_last : P.n_seg);
-      if (s_end <= P.seg_begin) continue;
-      const uint32_t rend = __ldg(soff + s_end);
+    for (int pi = 0; pi < P.n_prog; ++pi) {
+      const LoopProg pe = loop_prog_entry(P.n_groups, P.n_prog, pi);
+      const uint32_t rbeg = __ldg(soff + pe.sec), rend = __ldg(soff + pe.sec + 1);
+      if (rbeg >= rend) continue;
+      if (pe.flags & 1) {
+        // the section's ring plan assumes an empty ring: wait until every step issued so far has been consumed
+        for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
+      }
+      // dependencies of the section's first item; later items are described one item ahead by the records themselves
+      // (w[6], w[7] of an item's first step = dependency range of the NEXT item)
+      uint32_t first_d0 = 0, first_cnt = 0;
+      {
+        const uint32_t i0 = __ldg(eoff + pe.sec), i1 = __ldg(eoff + pe.sec + 1);
+        if (i0 < i1) { first_d0 = __ldg(P.dep_off + i0); first_cnt = __ldg(P.dep_off + i0 + 1) - first_d0; }
+      }
+      uint4 mine = make_uint4(0, 0, 0, 0);
+      if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
       // the item about to start: dependency range, this lane's entry (first 32) and its flag value if already fetched
       uint32_t cur_d0 = first_d0, cur_cnt = first_cnt, cur_e = 0, cur_f = 0;
       bool cur_f_valid = false;
       if (lane < cur_cnt) cur_e = __ldg(P.deps + cur_d0 + lane);
       uint32_t nxt_d0 = 0, nxt_cnt = 0, nxt_e = 0;
-      uint32_t trace_item = __ldg(eoff + P.seg_begin);          // index of the item about to start (trace only)
-      uint4 mine = first;
+      uint32_t trace_item = __ldg(eoff + pe.sec);               // index of the item about to start (trace only)
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
         __syncwarp();
@@ -463,13 +489,14 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
           const uint32_t slot = it & (TC2_NSLOT - 1);
           const int kc = (r0.x >> 8) & 0xF, nA = (r0.x >> 12) & 0x7, nB = (r0.x >> 15) & 0xF;
           const uint32_t dep = (r0.x >> 19) & 0xF;
-          const int seg = (int)((r0.y >> 16) & 0xFu);
+          const int seg = (int)((r0.y >> 16) & 0x1Fu);
           const LoopSeg& sg = P.seg[seg];
-          if ((r0.y >> 20) & 1u) {
+          if ((r0.y >> 21) & 1u) {
             // first step of an item: everything it stages must have been published.  Fast path: the flag values were
             // fetched while the previous item's last step was issued and already satisfy the target.
             const long long tw0 = P.dbg ? clock64() : 0;
-            const bool tracing = P.trace != nullptr && t == P.trace_step && leader && lane == 0;
+            const int t = sg.group ? pe.t1 : pe.t0;                       // this item's L-step
+            const bool tracing = P.trace != nullptr && (pi == P.trace_entry || pi == P.trace_entry + 1) && leader && lane == 0;
             if (tracing) P.trace[(size_t)trace_item * 4 + 0] = ptx::globaltimer();
             if (cur_cnt > 0) {
               const uint32_t target = LOOP_ARRIVALS * (uint32_t)((cur_e & LOOP_DEP_PREV) ? t : t + 1);
@@ -517,7 +544,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
             }
           }
           __syncwarp();
-          if ((r0.y >> 21) & 1u) {
+          if ((r0.y >> 22) & 1u) {
             // last step of the item issued: look at the next item's flags now, so that the answer is (usually) there by
             // the time its first step comes up
             cur_d0 = nxt_d0; cur_cnt = nxt_cnt; cur_e = nxt_e; cur_f = 0; cur_f_valid = true;
@@ -546,17 +573,12 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       uint32_t idesc = 0, acc_stride = 0, half_b16 = 0, n_merge = 0;
       long long t_full = 0, t_acc = 0;
       const long long t_m0 = P.dbg ? clock64() : 0;
-      const uint32_t rbeg = __ldg(soff + P.seg_begin);
-      uint4 first = make_uint4(0, 0, 0, 0);
-      {
-        const uint32_t rend_max = __ldg(soff + P.seg_end);
-        if (2 * rbeg + lane < 2 * rend_max) first = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
-      }
-      for (int t = P.t_begin; t < P.t_end; ++t) {
-        const int s_end = min(P.seg_end, (t == P.last_step) ? P.n_seg_last : P.n_seg);
-        if (s_end <= P.seg_begin) continue;
-        const uint32_t rend = __ldg(soff + s_end);
-        uint4 mine = first;
+      for (int pi = 0; pi < P.n_prog; ++pi) {
+        const int sec = loop_prog_entry(P.n_groups, P.n_prog, pi).sec;
+        const uint32_t rbeg = __ldg(soff + sec), rend = __ldg(soff + sec + 1);
+        if (rbeg >= rend) continue;
+        uint4 mine = make_uint4(0, 0, 0, 0);
+        if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
         for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
           ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
           __syncwarp();
@@ -569,7 +591,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
             const int nA = (r0.x >> 8) & 0x7, n_ops = (r0.x >> 11) & 0x1F;
             const uint32_t flags = (r0.x >> 16) & 0x3u;
             if (flags & 1u) {                                   // first step of an item: its accumulator buffer must be drained
-              const LoopSeg& sg = P.seg[r0.y & 0xFu];
+              const LoopSeg& sg = P.seg[r0.y & 0x1Fu];
               idesc = sg.idesc; acc_stride = sg.acc_stride; half_b16 = sg.half_b >> 4; n_merge = (sg.n_tile >> 3) << 17;
               buf = item_count & 1;
               const long long ta0 = P.dbg ? clock64() : 0;
@@ -627,12 +649,11 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     uint32_t tcount = 0;
     long long t_tile = 0, t_done = 0;
     const long long t_s0 = P.dbg ? clock64() : 0;
-    for (int t = P.t_begin; t < P.t_end; ++t) {
-      const int s_end = min(P.seg_end, (t == P.last_step) ? P.n_seg_last : P.n_seg);
-      if (s_end <= P.seg_begin) continue;
-      const uint32_t e_beg = __ldg(eoff + P.seg_begin), e_end = __ldg(eoff + s_end);
+    for (int pi = 0; pi < P.n_prog; ++pi) {
+      const int sec = loop_prog_entry(P.n_groups, P.n_prog, pi).sec;
+      const uint32_t e_beg = __ldg(eoff + sec), e_end = __ldg(eoff + sec + 1);
       for (uint32_t k = e_beg; k < e_end; ++k) {
-        const uint2 cur = __ldg(P.eitems + k);
+        const uint4 cur = __ldg(P.eitems + k);
         const int seg = (int)(cur.x >> 16), win = (int)(cur.x & 0xFFFFu), mp = (int)cur.y;
         const LoopSeg& sg = P.seg[seg];
         const uint32_t kind = sg.kind;
@@ -654,7 +675,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         const long long tw1 = P.dbg ? clock64() : 0;
         ptx::bulk_wait_all0();                                      // the item's tiles are in global memory
         ptx::fence_proxy_async_all();
-        ptx::red_release_gpu_add(P.flags + sg.flag_base + (size_t)mp * sg.n_windows + win, 4u);   // for this half's four warps
+        ptx::red_release_gpu_add(P.flags + cur.z, 4u);   // for this half's four warps
         if (P.dbg) t_done += clock64() - tw1;
       }
     }
@@ -674,29 +695,29 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     TcFinalArgs fa{};
     fa.x = P.x; fa.y = P.y; fa.loss_part = P.loss_part; fa.R = P.R; fa.B = P.B; fa.n_rows = P.n_rows; fa.nbx = P.nbx; fa.w_out = P.w_out;
     fa.gscale = P.gscale; fa.m_gmul = P.m_gmul; fa.m_mu = P.m_mu;
-    for (int t = P.t_begin; t < P.t_end; ++t) {
-      const int s_end = min(P.seg_end, (t == P.last_step) ? P.n_seg_last : P.n_seg);
-      if (s_end <= P.seg_begin) continue;
-      fa.write_y = (t == P.last_step) ? 1 : 0;      // G(z) and the loss are consumed after the final forward only
-      fa.m_lr = (P.decay_step > 0 && t >= P.decay_step) ? P.m_lr * 0.1f : P.m_lr;
-      const uint32_t e_beg = __ldg(eoff + P.seg_begin), e_end = __ldg(eoff + s_end);
-      uint2 nxt = make_uint2(0, 0);
+    for (int pi = 0; pi < P.n_prog; ++pi) {
+      const LoopProg pe = loop_prog_entry(P.n_groups, P.n_prog, pi);
+      const uint32_t e_beg = __ldg(eoff + pe.sec), e_end = __ldg(eoff + pe.sec + 1);
+      uint4 nxt = make_uint4(0, 0, 0, 0);
       if (e_beg < e_end) nxt = __ldg(P.eitems + e_beg);
       for (uint32_t k = e_beg; k < e_end; ++k, ++cx.item_count) {
-        const uint2 cur = nxt;
+        const uint4 cur = nxt;
         if (k + 1 < e_end) nxt = __ldg(P.eitems + k + 1);             // one item ahead
         const int seg = (int)(cur.x >> 16), win = (int)(cur.x & 0xFFFFu), mp = (int)cur.y;
         const LoopSeg& sg = P.seg[seg];
-        uint32_t* flag = P.flags + sg.flag_base + (size_t)mp * sg.n_windows + win;
+        const int t = sg.group ? pe.t1 : pe.t0;                       // this item's L-step
+        fa.write_y = (t == P.last_step) ? 1 : 0;      // G(z) and the loss are consumed after the final forward only
+        fa.m_lr = (P.decay_step > 0 && t >= P.decay_step) ? P.m_lr * 0.1f : P.m_lr;
+        uint32_t* flag = P.flags + cur.z;
         unsigned long long ts = 0;
         if (P.prof != nullptr && warp == LOOP_EPI_WARP0 && lane == 0 && leader) ts = ptx::globaltimer();
         loop_epilogue_dispatch<ARCH>(P, sg, cx, fa, win, mp, flag);
         if (P.prof != nullptr && warp == LOOP_EPI_WARP0 && lane == 0 && leader) {
-          unsigned long long* pr = P.prof + ((size_t)t * P.n_seg + seg) * 2;
+          unsigned long long* pr = P.prof + ((size_t)t * P.n_vseg + seg) * 2;
           const unsigned long long te = ptx::globaltimer();
           atomicMin(pr, ts);
           atomicMax(pr + 1, te);
-          if (P.trace != nullptr && t == P.trace_step) { P.trace[(size_t)k * 4 + 2] = ts; P.trace[(size_t)k * 4 + 3] = te; }
+          if (P.trace != nullptr && (pi == P.trace_entry || pi == P.trace_entry + 1)) { P.trace[(size_t)k * 4 + 2] = ts; P.trace[(size_t)k * 4 + 3] = te; }
         }
       }
     }
@@ -717,9 +738,9 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
 
 
 // ------------------------------------------------------------------------------------------
-// host side: the plan of one L-step
+// host side: the plan
 // ------------------------------------------------------------------------------------------
-struct LoopSegSpec {              // one layer-direction as the planner sees it
+struct LoopSegSpec {              // one layer-direction ("physical segment") as the planner sees it
   std::string name;
   int N = 0, K = 0;               // MMA N (output channels per pixel) and K (input channels per pixel)
   int kind = 0;                   // LoopKind
@@ -727,21 +748,36 @@ struct LoopSegSpec {              // one layer-direction as the planner sees it
   int h_grid = 1, w_grid = 1;     // raster of the output pixels (window shapes)
   int max_acc = 1;                // accumulators per window (TMEM columns / layer-specific cap)
   int in_seg = -1;                // segment whose output this one reads; -1: z, published by the momentum tail
+  bool fwd = true;                // part of the generator forward (+ loss) or of the backward-to-z
   double macs_per_row = 0.0;      // exact in-bounds MACs per latent row (profiling only)
 };
 
+// The plan.  Row pairs are split into `n_groups` groups whose L-steps run HALF A STEP OUT OF PHASE: while group A is in
+// its backward half, group B is in its forward half, and their segments alternate in every CTA pair's stream
+// (A.bwd_0, B.fwd_0, A.bwd_1, B.fwd_1, ...).  Consecutive segments of one group are then separated by a segment of the
+// other group, so the latency of "epilogue -> store completes -> flag -> dependent item's producer" (and of the momentum
+// update at the L-step boundary) is covered by independent work instead of stalling the in-order streams - software
+// pipelining across row-pair groups.  A (group, layer-direction) pair is a VIRTUAL SEGMENT with its own window tiling,
+// items and flags.  Every CTA pair's records are four sections:
+//   section 0 = A.fwd alone (prologue: A's first forward)      section 1 = A.bwd interleaved with B.fwd
+//   section 3 = B.fwd alone (epilogue: B's last forward)       section 2 = A.fwd interleaved with B.bwd
+// and a launch runs  sec0, (sec1, sec2) x (L - 1), sec3.   With one group (small batches, dgan_forward / dgan_loss_grad)
+// sections 1 / 2 are that group's backward / forward and a launch runs  sec2, (sec1, sec2) x (L - 1).
 struct LoopPlan {
-  int n_seg = 0, n_pairs = 0, n_mpairs = 0;
-  std::vector<std::vector<TcItem2>> hdrs;         // per segment: window headers
-  std::vector<int> shape;                         // per segment: wh, ww, sy, sx
-  std::vector<TcRec> stream_p[2], stream_m;       // one L-step, CTA pair after CTA pair
-  std::vector<uint32_t> stream_off;               // [n_pairs][n_seg + 1]
-  std::vector<uint2> eitems;                      // x = seg << 16 | window, y = row pair
-  std::vector<uint32_t> eitem_off;                // [n_pairs][n_seg + 1]
-  std::vector<uint32_t> dep_off, deps;
-  std::vector<uint32_t> flag_base, n_windows;     // per segment
+  int n_phys = 0, n_groups = 1, n_vseg = 0, n_pairs = 0, n_mpairs = 0;
+  std::vector<int> vseg_phys, vseg_group;         // vseg = group * n_phys + phys
+  std::vector<std::vector<int>> group_mps;        // row pairs of each group
+  std::vector<std::vector<TcItem2>> hdrs;         // per vseg: window headers
+  std::vector<int> shape;                         // per vseg: wh, ww, sy, sx
+  std::vector<uint32_t> flag_base, n_windows;     // per vseg: flags [row pair of the group][window]
   uint32_t zflag_base = 0, n_flags = 0;
-  long long n_steps = 0, n_mma = 0, n_bytes = 0;
+  std::vector<int> sec_vsegs[LOOP_N_SEC];         // virtual segments of each section in stream order
+  std::vector<TcRec> stream_p[2], stream_m;       // CTA pair after CTA pair, each: sections 0..3
+  std::vector<uint32_t> stream_off;               // [n_pairs][LOOP_N_SEC + 1]
+  std::vector<uint4> eitems;                      // x = vseg << 16 | window, y = row pair, z = flag index
+  std::vector<uint32_t> eitem_off;                // [n_pairs][LOOP_N_SEC + 1]
+  std::vector<uint32_t> dep_off, deps;
+  long long n_steps = 0, n_mma = 0, n_bytes = 0;  // of sections 1 + 2 (= one L-step of every row pair)
 };
 
 #ifndef DGAN_COST_EPI_KB
@@ -750,29 +786,44 @@ struct LoopPlan {
 #ifndef DGAN_COST_FIXED_KB
 #define DGAN_COST_FIXED_KB 48.0
 #endif
-#ifndef DGAN_LOOP_ORDER
-#define DGAN_LOOP_ORDER 0        // experiment switch: 0 = row-pair-major item order inside a segment, 1 = LPT (cost-descending) order
-#endif
-#ifndef DGAN_LOOP_CARRY
-#define DGAN_LOOP_CARRY 0        // experiment switch: 1 = a CTA pair's surplus load in one segment is deducted in the next
+#ifndef DGAN_LOOP_GROUPS
+#define DGAN_LOOP_GROUPS 2        // row-pair groups of a projection (2 = half an L-step out of phase; 1 = all in phase, for A/B runs)
 #endif
 constexpr int LOOP_STEP_MAX_BYTES = 48 * 1024;    // measured optimum of the operand-ring kernels (round 1): 2 A tiles + weights
 
-// Window tiling of one segment and the assignment of its (window, row pair) items to CTA pairs: every candidate shape
-// (wh x ww accumulators, strides 1 or 2 - stride 2 gathers outputs of equal parity of a stride-2 transposed conv, which
-// share weight tiles) is scored by a longest-processing-time assignment with cost = operand bytes staged + a
-// per-accumulator epilogue charge + a fixed per-item charge; the smallest makespan wins.  `carry` (in/out) is each
-// CTA pair's load imbalance inherited from the previous segment: there is no barrier between segments, so a pair that
-// drew the short straw in one segment takes less of the next.
-static int loop_assign(const LoopSegSpec& sp, int n_mpairs, int n_pairs, std::vector<double>* carry,
-                       std::vector<Tc2HostItem>* items_out, std::vector<std::vector<int>>* lists_out, int shape_out[4]) {
+static double loop_item_cost(const Tc2HostItem& it, int N) {
+  return it.stage_bytes + DGAN_COST_EPI_KB * 1024.0 * it.hdr.n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;
+}
+
+// Longest-processing-time assignment of the (window, row pair) items of one virtual segment to the CTA pairs, on top of
+// the load `load` they already carry (the other virtual segment of the same slot: there is no barrier between them, so
+// they are balanced jointly).  Items come out per CTA pair as (window, index into `mps`).
+static void loop_lpt(const std::vector<Tc2HostItem>& items, int N, int n_mps, std::vector<double>* load,
+                     std::vector<std::vector<std::pair<int, int>>>* lists) {
+  const size_t n_pairs = load->size();
+  lists->assign(n_pairs, {});
+  std::vector<size_t> order(items.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return items[l].stage_bytes > items[r].stage_bytes; });
+  for (size_t oi = 0; oi < order.size(); ++oi)
+    for (int m = 0; m < n_mps; ++m) {                     // cost-descending; the row pair is the fast index
+      size_t best = 0;
+      for (size_t pr = 1; pr < n_pairs; ++pr)
+        if ((*load)[pr] < (*load)[best]) best = pr;
+      (*load)[best] += loop_item_cost(items[order[oi]], N);
+      (*lists)[best].push_back({(int)order[oi], m});
+    }
+}
+
+// Window tiling of one virtual segment: every candidate shape (wh x ww accumulators, strides 1 or 2 - stride 2 gathers
+// outputs of equal parity of a stride-2 transposed conv, which share weight tiles) is scored by the makespan of an LPT
+// assignment of its items (cost = operand bytes staged + a per-accumulator epilogue charge + a fixed per-item charge).
+static int loop_choose_tiling(const LoopSegSpec& sp, int n_mps, int n_pairs, std::vector<Tc2HostItem>* items_out, int shape_out[4]) {
   const int N = sp.N, K = sp.K;
   const int max_g = (N >= 64) ? std::min(4, 256 / N) : 1;
   const int step_max = std::min((LOOP_RING_BYTES / 2) & ~1023, LOOP_STEP_MAX_BYTES);
   double best_cost = 1e300;
   std::vector<Tc2HostItem> best_items;
-  std::vector<std::vector<int>> best_lists;
-  std::vector<double> best_load;
   std::vector<std::vector<int>> wins;
   for (int wh = 1; wh <= 2; ++wh)
     for (int ww = 1; ww <= 8; ++ww)
@@ -783,330 +834,412 @@ static int loop_assign(const LoopSegSpec& sp, int n_mpairs, int n_pairs, std::ve
           if (wins.size() > 0xFFFFu) continue;
           std::vector<Tc2HostItem> items(wins.size());
           for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(*sp.tab, wins[i], N, K, max_g, TC2_MAX_A, step_max, &items[i]);
-          std::stable_sort(items.begin(), items.end(), [](const Tc2HostItem& l, const Tc2HostItem& r) { return l.stage_bytes > r.stage_bytes; });
-          std::vector<double> icost(items.size());
-          for (size_t i = 0; i < items.size(); ++i)
-            icost[i] = items[i].stage_bytes + DGAN_COST_EPI_KB * 1024.0 * items[i].hdr.n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;
-          const long long total = (long long)items.size() * n_mpairs;
-          std::vector<double> load = *carry;
-          std::vector<std::vector<int>> lists((size_t)n_pairs);
-          for (long long idx = 0; idx < total; ++idx) {        // items[] is sorted by cost, mp is the fast index: cost-descending
-            size_t best = 0;
-            for (size_t pr = 1; pr < (size_t)n_pairs; ++pr)
-              if (load[pr] < load[best]) best = pr;
-            load[best] += icost[(size_t)(idx / n_mpairs)];
-            lists[best].push_back((int)idx);
-          }
+          std::vector<double> load((size_t)n_pairs, 0.0);
+          std::vector<std::vector<std::pair<int, int>>> lists;
+          loop_lpt(items, N, n_mps, &load, &lists);
           const double makespan = *std::max_element(load.begin(), load.end());
           if (makespan < best_cost) {
             best_cost = makespan;
             shape_out[0] = wh; shape_out[1] = ww; shape_out[2] = sy; shape_out[3] = sx;
-            best_items.swap(items); best_lists.swap(lists); best_load.swap(load);
+            best_items.swap(items);
           }
         }
   if (best_items.empty()) { set_error("no window tiling for segment " + sp.name); return DGAN_ERR_UNSUPPORTED; }
-  const double lo = *std::min_element(best_load.begin(), best_load.end());
-  for (size_t pr = 0; pr < best_load.size(); ++pr) (*carry)[pr] = best_load[pr] - lo;
   items_out->swap(best_items);
-  lists_out->swap(best_lists);
   return 0;
 }
 
-// Plan one L-step for `n_mpairs` row pairs on `n_pairs` CTA pairs: per segment the window tiling + assignment, then
-// per CTA pair the concatenated step stream (segment-major, row-pair-major inside a segment), the circular operand
-// ring simulated CYCLICALLY (the stream is replayed L times, so a step's dependency distance may reach back into
-// the previous replay), the item list of the epilogue warps and every item's dependency list.
-static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_pairs, bool carry_load, LoopPlan* plan) {
-  const int n_seg = (int)specs.size();
-  if (n_seg < 1 || n_seg > LOOP_MAX_SEG) { set_error("segment count out of range"); return DGAN_ERR_UNSUPPORTED; }
-  if (n_mpairs < 1 || n_pairs < 1) { set_error("nothing to plan"); return DGAN_ERR_INVALID_ARG; }
-  plan->n_seg = n_seg; plan->n_pairs = n_pairs; plan->n_mpairs = n_mpairs;
-  plan->hdrs.assign((size_t)n_seg, {});
-  plan->shape.assign((size_t)4 * n_seg, 1);
-  plan->flag_base.assign((size_t)n_seg, 0);
-  plan->n_windows.assign((size_t)n_seg, 0);
-  std::vector<std::vector<Tc2HostItem>> items((size_t)n_seg);
-  std::vector<std::vector<std::vector<int>>> lists((size_t)n_seg);
-  std::vector<std::vector<int>> pix2win((size_t)n_seg);       // output pixel of a segment -> window that writes it
-  std::vector<double> carry((size_t)n_pairs, 0.0);
+// Plan for `n_mpairs` row pairs on `n_pairs` CTA pairs (see LoopPlan).
+static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_pairs, int n_groups, LoopPlan* plan) {
+  const int n_phys = (int)specs.size();
+  if (n_groups < 1 || n_groups > 2 || n_phys < 1 || n_phys * n_groups > LOOP_MAX_SEG) { set_error("segment count out of range"); return DGAN_ERR_UNSUPPORTED; }
+  if (n_mpairs < n_groups || n_pairs < 1) { set_error("nothing to plan"); return DGAN_ERR_INVALID_ARG; }
+  std::vector<int> fwd_list, bwd_list;
+  for (int s = 0; s < n_phys; ++s) (specs[(size_t)s].fwd ? fwd_list : bwd_list).push_back(s);
+  if (n_groups == 2 && fwd_list.size() != bwd_list.size()) { set_error("forward and backward halves differ in length"); return DGAN_ERR_UNSUPPORTED; }
+  LoopPlan& pl = *plan;
+  pl = LoopPlan{};
+  pl.n_phys = n_phys; pl.n_groups = n_groups; pl.n_vseg = n_phys * n_groups; pl.n_pairs = n_pairs; pl.n_mpairs = n_mpairs;
+  pl.group_mps.assign((size_t)n_groups, {});
+  for (int mp = 0; mp < n_mpairs; ++mp) pl.group_mps[(size_t)(n_groups == 2 && mp >= (n_mpairs + 1) / 2 ? 1 : 0)].push_back(mp);
+  const int nv = pl.n_vseg;
+  pl.vseg_phys.resize((size_t)nv); pl.vseg_group.resize((size_t)nv);
+  pl.hdrs.assign((size_t)nv, {}); pl.shape.assign((size_t)4 * nv, 1);
+  pl.flag_base.assign((size_t)nv, 0); pl.n_windows.assign((size_t)nv, 0);
+  std::vector<std::vector<Tc2HostItem>> items((size_t)nv);
+  std::vector<std::vector<int>> pix2win((size_t)nv);
   int rc;
   uint32_t n_flags = 0;
-  for (int s = 0; s < n_seg; ++s) {
+  for (int v = 0; v < nv; ++v) {
+    const int g = v / n_phys, s = v % n_phys;
+    pl.vseg_phys[(size_t)v] = s; pl.vseg_group[(size_t)v] = g;
     const LoopSegSpec& sp = specs[(size_t)s];
-    if (!carry_load) std::fill(carry.begin(), carry.end(), 0.0);
-    if ((rc = loop_assign(sp, n_mpairs, n_pairs, &carry, &items[(size_t)s], &lists[(size_t)s], &plan->shape[(size_t)4 * s]))) return rc;
-    const size_t nw = items[(size_t)s].size();
-    plan->hdrs[(size_t)s].resize(nw);
-    pix2win[(size_t)s].assign(sp.tab->off.size() - 1, -1);
+    const int n_mps = (int)pl.group_mps[(size_t)g].size();
+    if ((rc = loop_choose_tiling(sp, n_mps, n_pairs, &items[(size_t)v], &pl.shape[(size_t)4 * v]))) return rc;
+    const size_t nw = items[(size_t)v].size();
+    pl.hdrs[(size_t)v].resize(nw);
+    pix2win[(size_t)v].assign(sp.tab->off.size() - 1, -1);
     for (size_t w = 0; w < nw; ++w) {
-      plan->hdrs[(size_t)s][w] = items[(size_t)s][w].hdr;
-      for (uint32_t a = 0; a < items[(size_t)s][w].hdr.n_acc; ++a) pix2win[(size_t)s][items[(size_t)s][w].hdr.q[a]] = (int)w;
+      pl.hdrs[(size_t)v][w] = items[(size_t)v][w].hdr;
+      for (uint32_t a = 0; a < items[(size_t)v][w].hdr.n_acc; ++a) pix2win[(size_t)v][items[(size_t)v][w].hdr.q[a]] = (int)w;
     }
-    plan->flag_base[(size_t)s] = n_flags;
-    plan->n_windows[(size_t)s] = (uint32_t)nw;
-    n_flags += (uint32_t)(nw * (size_t)n_mpairs);
+    pl.flag_base[(size_t)v] = n_flags;
+    pl.n_windows[(size_t)v] = (uint32_t)nw;
+    n_flags += (uint32_t)(nw * (size_t)n_mps);
   }
-  plan->zflag_base = n_flags;
+  pl.zflag_base = n_flags;
   n_flags += (uint32_t)n_mpairs;
-  plan->n_flags = n_flags;
-
+  pl.n_flags = n_flags;
+  // ---- sections
+  auto vs = [&](int g, int s) { return g * n_phys + s; };
+  for (int k = 0; k < LOOP_N_SEC; ++k) pl.sec_vsegs[k].clear();
+  if (n_groups == 2) {
+    for (int s : fwd_list) pl.sec_vsegs[0].push_back(vs(0, s));
+    for (size_t k = 0; k < bwd_list.size(); ++k) { pl.sec_vsegs[1].push_back(vs(0, bwd_list[k])); pl.sec_vsegs[1].push_back(vs(1, fwd_list[k])); }
+    for (size_t k = 0; k < fwd_list.size(); ++k) { pl.sec_vsegs[2].push_back(vs(0, fwd_list[k])); pl.sec_vsegs[2].push_back(vs(1, bwd_list[k])); }
+    for (int s : fwd_list) pl.sec_vsegs[3].push_back(vs(1, s));
+  } else {
+    for (int s : bwd_list) pl.sec_vsegs[1].push_back(vs(0, s));
+    for (int s : fwd_list) pl.sec_vsegs[2].push_back(vs(0, s));
+  }
+  // ---- assignment: per section, slot by slot (a slot = the two virtual segments that run side by side, balanced jointly)
+  std::vector<std::vector<std::vector<std::pair<int, int>>>> lists[LOOP_N_SEC];     // [section][position in section][pair] -> (window, mp index)
+  for (int k = 0; k < LOOP_N_SEC; ++k) {
+    lists[k].resize(pl.sec_vsegs[k].size());
+    std::vector<double> load((size_t)n_pairs, 0.0);
+    for (size_t i = 0; i < pl.sec_vsegs[k].size(); ++i) {
+      const int v = pl.sec_vsegs[k][i];
+      const bool joint = (n_groups == 2 && (k == 1 || k == 2) && (i & 1));     // second member of a slot: on top of the first's load
+      if (!joint) std::fill(load.begin(), load.end(), 0.0);
+      loop_lpt(items[(size_t)v], specs[(size_t)pl.vseg_phys[(size_t)v]].N, (int)pl.group_mps[(size_t)pl.vseg_group[(size_t)v]].size(), &load, &lists[k][i]);
+    }
+  }
+  // ---- emission
   const int ring_kb = LOOP_RING_BYTES / 1024;
-  plan->stream_p[0].clear(); plan->stream_p[1].clear(); plan->stream_m.clear();
-  plan->stream_off.assign((size_t)n_pairs * (n_seg + 1), 0);
-  plan->eitem_off.assign((size_t)n_pairs * (n_seg + 1), 0);
-  plan->eitems.clear(); plan->dep_off.assign(1, 0); plan->deps.clear();
-  plan->n_steps = plan->n_mma = plan->n_bytes = 0;
+  pl.stream_off.assign((size_t)n_pairs * (LOOP_N_SEC + 1), 0);
+  pl.eitem_off.assign((size_t)n_pairs * (LOOP_N_SEC + 1), 0);
+  pl.dep_off.assign(1, 0);
   for (int pr = 0; pr < n_pairs; ++pr) {
-    const size_t stream_beg = plan->stream_m.size();
-    size_t prev_first_rec = (size_t)-1;
-    std::vector<int> kb_of;                                    // KB of every step of this pair's stream
-    for (int s = 0; s < n_seg; ++s) {
-      const LoopSegSpec& sp = specs[(size_t)s];
-      plan->stream_off[(size_t)pr * (n_seg + 1) + s] = (uint32_t)plan->stream_m.size();
-      plan->eitem_off[(size_t)pr * (n_seg + 1) + s] = (uint32_t)plan->eitems.size();
-      std::vector<int> mine = lists[(size_t)s][(size_t)pr];
-      // row-pair major: a pair meets the row pairs in the same order in every segment, so what it waits for was
-      // produced a whole segment-phase ago; inside a row pair keep the cost-descending order
-#if DGAN_LOOP_ORDER == 0
-      std::stable_sort(mine.begin(), mine.end(), [&](int l, int r) { return (l % n_mpairs) < (r % n_mpairs); });
-#endif
-      const int half_b = (sp.N / 2) * 128;
-      for (int idx : mine) {
-        const int win = idx / n_mpairs, mp = idx % n_mpairs;
-        const Tc2HostItem& itm = items[(size_t)s][(size_t)win];
-        plan->eitems.push_back(make_uint2(((uint32_t)s << 16) | (uint32_t)win, (uint32_t)mp));
-        // dependencies: the windows of the producing segment that cover the input pixels this item stages
-        std::vector<uint32_t> dl;
-        if (sp.in_seg < 0) {
-          dl.push_back((plan->zflag_base + (uint32_t)mp) | LOOP_DEP_PREV);
-        } else {
-          const std::vector<int>& p2w = pix2win[(size_t)sp.in_seg];
-          for (const Tc2HostStep& hs : itm.steps)
-            for (int a = 0; a < hs.nA; ++a) {
-              const int p = hs.a_pix[a];
-              if (p < 0 || (size_t)p >= p2w.size() || p2w[(size_t)p] < 0) { set_error(sp.name + ": input pixel without a producer"); return DGAN_ERR_UNSUPPORTED; }
-              const uint32_t f = plan->flag_base[(size_t)sp.in_seg] + (uint32_t)mp * plan->n_windows[(size_t)sp.in_seg] + (uint32_t)p2w[(size_t)p];
-              if (std::find(dl.begin(), dl.end(), f) == dl.end()) dl.push_back(f);
-            }
-        }
-        const uint32_t this_d0 = (uint32_t)plan->deps.size();
-        plan->deps.insert(plan->deps.end(), dl.begin(), dl.end());
-        plan->dep_off.push_back((uint32_t)plan->deps.size());
-        // the first-step record of the PREVIOUS item of this CTA pair announces this item's dependency range, so that the
-        // producer can fetch the flags one item ahead
-        if (prev_first_rec != (size_t)-1)
-          for (int r = 0; r < 2; ++r) { plan->stream_p[r][prev_first_rec].w[6] = this_d0; plan->stream_p[r][prev_first_rec].w[7] = (uint32_t)dl.size(); }
-        prev_first_rec = plan->stream_m.size();
-        for (size_t j = 0; j < itm.steps.size(); ++j) {
-          const Tc2HostStep& hs = itm.steps[j];
-          const int kb = (hs.bytes + 1023) / 1024;
-          if (kb > ring_kb / 2) { set_error("tensor-core step larger than half the operand ring"); return DGAN_ERR_UNSUPPORTED; }
-          kb_of.push_back(kb);
-          const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
-          TcRec rm{};
-          rm.w[0] = ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16);   // ring offset filled below
-          rm.w[1] = (uint32_t)s;
-          for (int o = 0; o < hs.n_ops; ++o) rm.w[2 + o / 2] |= (uint32_t)hs.ops[o] << (16 * (o & 1));
-          plan->stream_m.push_back(rm);
-          for (int r = 0; r < 2; ++r) {
-            TcRec rp{};
-            rp.w[0] = ((uint32_t)hs.kc << 8) | ((uint32_t)hs.nA << 12) | ((uint32_t)hs.nB << 15);   // offset + dep filled below
-            rp.w[1] = (uint32_t)mp | ((uint32_t)s << 16) | ((j == 0 ? 1u : 0u) << 20) | ((j + 1 == itm.steps.size() ? 1u : 0u) << 21);
-            for (int a = 0; a < hs.nA; ++a) rp.w[2 + a / 2] |= (uint32_t)(hs.a_pix[a] & 0xFFFF) << (16 * (a & 1));
-            for (int b = 0; b < hs.nB; ++b) rp.w[4 + b / 4] |= (uint32_t)hs.b_ent[r][b] << (8 * (b & 3));
-            plan->stream_p[r].push_back(rp);
+    std::vector<int> kb_of[LOOP_N_SEC];
+    size_t sec_beg[LOOP_N_SEC + 1];
+    for (int k = 0; k < LOOP_N_SEC; ++k) {
+      sec_beg[k] = pl.stream_m.size();
+      pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + k] = (uint32_t)pl.stream_m.size();
+      pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + k] = (uint32_t)pl.eitems.size();
+      size_t prev_first_rec = (size_t)-1;
+      for (size_t i = 0; i < pl.sec_vsegs[k].size(); ++i) {
+        const int v = pl.sec_vsegs[k][i], g = pl.vseg_group[(size_t)v], s = pl.vseg_phys[(size_t)v];
+        const LoopSegSpec& sp = specs[(size_t)s];
+        std::vector<std::pair<int, int>> mine = lists[k][i][(size_t)pr];
+        // row-pair major: a CTA pair meets the row pairs in the same order in every segment (measured: cost-descending
+        // order instead is 12 % slower); inside a row pair keep the cost-descending order
+        std::stable_sort(mine.begin(), mine.end(), [](const std::pair<int, int>& l, const std::pair<int, int>& r) { return l.second < r.second; });
+        for (const auto& wm : mine) {
+          const int win = wm.first, mi = wm.second, mp = pl.group_mps[(size_t)g][(size_t)mi];
+          const Tc2HostItem& itm = items[(size_t)v][(size_t)win];
+          const uint32_t flag = pl.flag_base[(size_t)v] + (uint32_t)mi * pl.n_windows[(size_t)v] + (uint32_t)win;
+          pl.eitems.push_back(make_uint4(((uint32_t)v << 16) | (uint32_t)win, (uint32_t)mp, flag, 0u));
+          // dependencies: the windows of the producing virtual segment (same group) that cover the staged input pixels
+          std::vector<uint32_t> dl;
+          if (sp.in_seg < 0) {
+            dl.push_back((pl.zflag_base + (uint32_t)mp) | LOOP_DEP_PREV);
+          } else {
+            const int vin = vs(g, sp.in_seg);
+            const std::vector<int>& p2w = pix2win[(size_t)vin];
+            for (const Tc2HostStep& hs : itm.steps)
+              for (int a = 0; a < hs.nA; ++a) {
+                const int p = hs.a_pix[a];
+                if (p < 0 || (size_t)p >= p2w.size() || p2w[(size_t)p] < 0) { set_error(sp.name + ": input pixel without a producer"); return DGAN_ERR_UNSUPPORTED; }
+                const uint32_t f = pl.flag_base[(size_t)vin] + (uint32_t)mi * pl.n_windows[(size_t)vin] + (uint32_t)p2w[(size_t)p];
+                if (std::find(dl.begin(), dl.end(), f) == dl.end()) dl.push_back(f);
+              }
           }
-          plan->n_mma += hs.n_ops; plan->n_steps += 1; plan->n_bytes += hs.bytes;
-          (void)half_b;
+          const uint32_t this_d0 = (uint32_t)pl.deps.size();
+          pl.deps.insert(pl.deps.end(), dl.begin(), dl.end());
+          pl.dep_off.push_back((uint32_t)pl.deps.size());
+          // the first-step record of the PREVIOUS item of this section announces this item's dependency range, so that
+          // the producer can fetch the flags one item ahead
+          if (prev_first_rec != (size_t)-1)
+            for (int r = 0; r < 2; ++r) { pl.stream_p[r][prev_first_rec].w[6] = this_d0; pl.stream_p[r][prev_first_rec].w[7] = (uint32_t)dl.size(); }
+          prev_first_rec = pl.stream_m.size();
+          for (size_t j = 0; j < itm.steps.size(); ++j) {
+            const Tc2HostStep& hs = itm.steps[j];
+            const int kb = (hs.bytes + 1023) / 1024;
+            if (kb > ring_kb / 2) { set_error("tensor-core step larger than half the operand ring"); return DGAN_ERR_UNSUPPORTED; }
+            kb_of[k].push_back(kb);
+            const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
+            TcRec rm{};
+            rm.w[0] = ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16);   // ring offset filled below
+            rm.w[1] = (uint32_t)v;
+            for (int o = 0; o < hs.n_ops; ++o) rm.w[2 + o / 2] |= (uint32_t)hs.ops[o] << (16 * (o & 1));
+            pl.stream_m.push_back(rm);
+            for (int r = 0; r < 2; ++r) {
+              TcRec rp{};
+              rp.w[0] = ((uint32_t)hs.kc << 8) | ((uint32_t)hs.nA << 12) | ((uint32_t)hs.nB << 15);   // offset + dep filled below
+              rp.w[1] = (uint32_t)mp | ((uint32_t)v << 16) | ((j == 0 ? 1u : 0u) << 21) | ((j + 1 == itm.steps.size() ? 1u : 0u) << 22);
+              for (int a = 0; a < hs.nA; ++a) rp.w[2 + a / 2] |= (uint32_t)(hs.a_pix[a] & 0xFFFF) << (16 * (a & 1));
+              for (int b = 0; b < hs.nB; ++b) rp.w[4 + b / 4] |= (uint32_t)hs.b_ent[r][b] << (8 * (b & 3));
+              pl.stream_p[r].push_back(rp);
+            }
+            if (k == 1 || k == 2) { pl.n_mma += hs.n_ops; pl.n_steps += 1; pl.n_bytes += hs.bytes; }
+          }
         }
       }
     }
-    plan->stream_off[(size_t)pr * (n_seg + 1) + n_seg] = (uint32_t)plan->stream_m.size();
-    plan->eitem_off[(size_t)pr * (n_seg + 1) + n_seg] = (uint32_t)plan->eitems.size();
-    // ---- circular operand ring of this CTA pair.  Sequential allocation, wrap when a step does not fit; every replay
-    //      starts at offset 0 so that the records are the same for every L-step.
-    const int n = (int)kb_of.size();
-    std::vector<int> beg((size_t)n), end((size_t)n);
-    int cursor = 0;
-    for (int k = 0; k < n; ++k) {
-      if (cursor + kb_of[(size_t)k] > ring_kb) cursor = 0;
-      beg[(size_t)k] = cursor; end[(size_t)k] = cursor + kb_of[(size_t)k];
-      cursor = end[(size_t)k];
-    }
-    // dep = distance (in steps, across the replay boundary if need be) to the latest earlier step whose region
-    // overlaps this step's: the producer may overwrite the region once that step is consumed (8 = barrier-slot reuse only)
-    for (int k = 0; k < n; ++k) {
-      int dep = TC2_NSLOT;
-      for (int d = 1; d < TC2_NSLOT; ++d) {
-        const int c = ((k - d) % n + n) % n;
-        if (beg[(size_t)c] < end[(size_t)k] && beg[(size_t)k] < end[(size_t)c]) { dep = d; break; }
+    sec_beg[LOOP_N_SEC] = pl.stream_m.size();
+    pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + LOOP_N_SEC] = (uint32_t)pl.stream_m.size();
+    pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + LOOP_N_SEC] = (uint32_t)pl.eitems.size();
+    // ---- circular operand ring of this CTA pair.  Sequential allocation, wrap when a step does not fit.  Sections 1 and 2
+    //      alternate for the whole launch: they are planned as ONE cyclic sequence (a step's dependency distance may reach
+    //      back across the section boundary, also from the start of section 1 to the end of section 2).  Sections 0 and 3
+    //      start on an empty ring (kernel start / explicit drain) and only look back inside themselves.
+    auto plan_ring = [&](const std::vector<int>& kbs, size_t rec0, bool cyclic) {
+      const int n = (int)kbs.size();
+      std::vector<int> beg((size_t)n), end((size_t)n);
+      int cursor = 0;
+      for (int k2 = 0; k2 < n; ++k2) {
+        if (cursor + kbs[(size_t)k2] > ring_kb) cursor = 0;
+        beg[(size_t)k2] = cursor; end[(size_t)k2] = cursor + kbs[(size_t)k2];
+        cursor = end[(size_t)k2];
       }
-      const size_t ri = stream_beg + (size_t)k;
-      plan->stream_m[ri].w[0] |= (uint32_t)beg[(size_t)k];
-      for (int r = 0; r < 2; ++r) plan->stream_p[r][ri].w[0] |= (uint32_t)beg[(size_t)k] | ((uint32_t)dep << 19);
+      // dep = distance (in steps) to the latest earlier step whose region overlaps this step's: the producer may overwrite
+      // the region once that step is consumed (8 = barrier-slot reuse only)
+      for (int k2 = 0; k2 < n; ++k2) {
+        int dep = TC2_NSLOT;
+        for (int d = 1; d < TC2_NSLOT; ++d) {
+          int c = k2 - d;
+          if (c < 0) { if (!cyclic) break; c = (c % n + n) % n; }
+          if (beg[(size_t)c] < end[(size_t)k2] && beg[(size_t)k2] < end[(size_t)c]) { dep = d; break; }
+        }
+        const size_t ri = rec0 + (size_t)k2;
+        pl.stream_m[ri].w[0] |= (uint32_t)beg[(size_t)k2];
+        for (int r = 0; r < 2; ++r) pl.stream_p[r][ri].w[0] |= (uint32_t)beg[(size_t)k2] | ((uint32_t)dep << 19);
+      }
+    };
+    plan_ring(kb_of[0], sec_beg[0], false);
+    {
+      std::vector<int> both = kb_of[1];
+      both.insert(both.end(), kb_of[2].begin(), kb_of[2].end());
+      plan_ring(both, sec_beg[1], true);            // sections 1 and 2 are adjacent in the record arrays
     }
+    plan_ring(kb_of[3], sec_beg[3], false);
   }
   return 0;
+}
+
+// The section sequence of a launch (LoopProg entries): `full_last` = the final L-step also runs its backward half without
+// the momentum update (dgan_loss_grad); otherwise the final L-step is forward only (the loop returns the pre-update
+// forward of iteration L-1, models/gan.py:419-421).
+static std::vector<LoopProg> loop_program(const LoopPlan& pl, int rec_iters, bool full_last) {
+  const int n = loop_prog_length(pl.n_groups, rec_iters, full_last);
+  std::vector<LoopProg> pg((size_t)n);
+  for (int pi = 0; pi < n; ++pi) pg[(size_t)pi] = loop_prog_entry(pl.n_groups, n, pi);
+  return pg;
 }
 
 // Independent validation of a plan (host only; dgan_debug_check_plans and the CPU tests):
-//  * per segment, everything tc2_check_plan re-derives from the records (every (output pixel, input pixel, tap, k-chunk)
-//    contribution exactly once into the right accumulator, first-MMA flags, canonical accumulation order, every item
-//    assigned exactly once);
-//  * the operand ring, cyclically: a step's region overlaps none of the `dep - 1` steps before it (which may still be
-//    unread when its loads start), also across the replay boundary;
-//  * producer, MMA and epilogue streams agree on the item sequence (segment, row pair) of every CTA pair;
-//  * every input pixel an item stages is covered by a dependency on the window (of the producing segment, same row pair)
-//    that writes it, and segment 0 waits for the previous L-step's z update;
-//  * no deadlock: with every CTA pair executing its items in order and an item startable only when its dependencies are
-//    complete, all items of an L-step complete.
+//  * per (section, virtual segment), everything tc2_check_plan re-derives from the records (every (output pixel, input
+//    pixel, tap, k-chunk) contribution exactly once into the right accumulator, first-MMA flags, canonical accumulation
+//    order, every item of the group assigned exactly once);
+//  * the operand ring: a step's region overlaps none of the `dep - 1` steps before it (which may still be unread when its
+//    loads start) - cyclically over sections 1 + 2, linearly inside sections 0 and 3;
+//  * producer, MMA and epilogue streams agree on the item sequence of every CTA pair; every record announces the next
+//    item's dependency range; the flag index of an item is the one its consumers wait for;
+//  * every input pixel an item stages is covered by a dependency on the window (producing virtual segment of the same
+//    group, same row pair) that writes it, and the first segment waits for the previous L-step's z update;
+//  * no deadlock: executing a 3-step launch program with every CTA pair in order and an item startable only when its
+//    dependencies have reached the value it waits for, every item of the program completes.
 static int loop_check_plan(const std::vector<LoopSegSpec>& specs, const LoopPlan& pl, std::string* err) {
   auto fail = [&](const std::string& m) { *err = m; return DGAN_ERR_INVALID_ARG; };
-  const int n_seg = pl.n_seg, n_pairs = pl.n_pairs, n_mpairs = pl.n_mpairs;
-  if ((int)specs.size() != n_seg) return fail("segment count");
-  if (pl.stream_off.size() != (size_t)n_pairs * (n_seg + 1) || pl.eitem_off.size() != pl.stream_off.size()) return fail("offset table size");
+  const int n_phys = pl.n_phys, nv = pl.n_vseg, n_pairs = pl.n_pairs;
+  if ((int)specs.size() != n_phys || nv != n_phys * pl.n_groups) return fail("segment count");
+  if (pl.stream_off.size() != (size_t)n_pairs * (LOOP_N_SEC + 1) || pl.eitem_off.size() != pl.stream_off.size()) return fail("offset table size");
   if (pl.stream_p[0].size() != pl.stream_m.size() || pl.stream_p[1].size() != pl.stream_m.size()) return fail("stream sizes differ");
   if (pl.dep_off.size() != pl.eitems.size() + 1) return fail("dep_off size");
-  // ---- per segment: slice the streams and reuse the single-layer validator
-  for (int s = 0; s < n_seg; ++s) {
-    const LoopSegSpec& sp = specs[(size_t)s];
-    Tc2Plan sub;
-    sub.n_pairs = n_pairs;
-    sub.hdrs = pl.hdrs[(size_t)s];
-    sub.stream_off.assign((size_t)n_pairs + 1, 0);
-    size_t n_slots = 0;
-    for (int pr = 0; pr < n_pairs; ++pr) {
-      const uint32_t e0 = pl.eitem_off[(size_t)pr * (n_seg + 1) + s], e1 = pl.eitem_off[(size_t)pr * (n_seg + 1) + s + 1];
-      if (e0 > e1 || e1 > pl.eitems.size()) return fail("item offsets not monotone");
-      n_slots = std::max(n_slots, (size_t)(e1 - e0));
-    }
-    sub.n_slots = (int)n_slots;
-    sub.eitems.assign(n_slots * (size_t)n_pairs, -1);
-    for (int pr = 0; pr < n_pairs; ++pr) {
-      const uint32_t r0 = pl.stream_off[(size_t)pr * (n_seg + 1) + s], r1 = pl.stream_off[(size_t)pr * (n_seg + 1) + s + 1];
-      if (r0 > r1 || r1 > pl.stream_m.size()) return fail("stream offsets not monotone");
-      sub.stream_off[(size_t)pr] = (uint32_t)sub.stream_m.size();
-      for (uint32_t ri = r0; ri < r1; ++ri) {
-        TcRec m = pl.stream_m[ri], p0 = pl.stream_p[0][ri], p1 = pl.stream_p[1][ri];
-        if ((int)(m.w[1] & 0xF) != s || (int)((p0.w[1] >> 16) & 0xF) != s || (int)((p1.w[1] >> 16) & 0xF) != s) return fail(sp.name + ": record carries another segment's id");
-        if (((p0.w[1] >> 20) & 1u) != ((m.w[0] >> 16) & 1u) || p0.w[1] != p1.w[1]) return fail(sp.name + ": first-step marks of producer and MMA records disagree");
-        p0.w[1] &= 0xFFFFu; p1.w[1] &= 0xFFFFu; m.w[1] = 0;
-        sub.stream_m.push_back(m); sub.stream_p[0].push_back(p0); sub.stream_p[1].push_back(p1);
-      }
-      const uint32_t e0 = pl.eitem_off[(size_t)pr * (n_seg + 1) + s], e1 = pl.eitem_off[(size_t)pr * (n_seg + 1) + s + 1];
-      for (uint32_t e = e0; e < e1; ++e) {
-        const uint2 it = pl.eitems[e];
-        if ((int)(it.x >> 16) != s) return fail(sp.name + ": item list out of segment order");
-        if ((it.x & 0xFFFFu) > 0x7FFFu || it.y > 0xFFFFu) return fail(sp.name + ": item index too large");
-        sub.eitems[(size_t)(e - e0) * n_pairs + pr] = (int)(((it.x & 0xFFFFu) << 16) | it.y);
-      }
-    }
-    sub.stream_off[(size_t)n_pairs] = (uint32_t)sub.stream_m.size();
-    std::string e2;
-    if (tc2_check_plan(sp.N, sp.K, *sp.tab, n_mpairs, LOOP_RING_BYTES, sub, &e2)) return fail(sp.name + ": " + e2);
-  }
-  // ---- cyclic ring check + dependency coverage, per CTA pair
   const int ring_kb = LOOP_RING_BYTES / 1024;
-  std::vector<std::vector<int>> pix2win((size_t)n_seg);
-  for (int s = 0; s < n_seg; ++s) {
-    pix2win[(size_t)s].assign(specs[(size_t)s].tab->off.size() - 1, -1);
-    for (size_t w = 0; w < pl.hdrs[(size_t)s].size(); ++w)
-      for (uint32_t a = 0; a < pl.hdrs[(size_t)s][w].n_acc; ++a) pix2win[(size_t)s][pl.hdrs[(size_t)s][w].q[a]] = (int)w;
+  std::vector<std::vector<int>> pix2win((size_t)nv);
+  for (int v = 0; v < nv; ++v) {
+    pix2win[(size_t)v].assign(specs[(size_t)pl.vseg_phys[(size_t)v]].tab->off.size() - 1, -1);
+    for (size_t w = 0; w < pl.hdrs[(size_t)v].size(); ++w)
+      for (uint32_t a = 0; a < pl.hdrs[(size_t)v][w].n_acc; ++a) pix2win[(size_t)v][pl.hdrs[(size_t)v][w].q[a]] = (int)w;
   }
+  std::vector<int> mp_index((size_t)pl.n_mpairs, -1), mp_group((size_t)pl.n_mpairs, -1);
+  for (int g = 0; g < pl.n_groups; ++g)
+    for (size_t i = 0; i < pl.group_mps[(size_t)g].size(); ++i) { mp_index[(size_t)pl.group_mps[(size_t)g][i]] = (int)i; mp_group[(size_t)pl.group_mps[(size_t)g][i]] = g; }
+  for (int mp = 0; mp < pl.n_mpairs; ++mp)
+    if (mp_index[(size_t)mp] < 0) return fail("a row pair belongs to no group");
+  // ---- per (section, virtual segment): slice and reuse the single-layer validator
+  for (int k = 0; k < LOOP_N_SEC; ++k)
+    for (int v : pl.sec_vsegs[k]) {
+      const LoopSegSpec& sp = specs[(size_t)pl.vseg_phys[(size_t)v]];
+      const int g = pl.vseg_group[(size_t)v], n_mps = (int)pl.group_mps[(size_t)g].size();
+      Tc2Plan sub;
+      sub.n_pairs = n_pairs;
+      sub.hdrs = pl.hdrs[(size_t)v];
+      sub.stream_off.assign((size_t)n_pairs + 1, 0);
+      std::vector<std::vector<int>> per_pair((size_t)n_pairs);
+      for (int pr = 0; pr < n_pairs; ++pr) {
+        const uint32_t r0 = pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + k], r1 = pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + k + 1];
+        if (r0 > r1 || r1 > pl.stream_m.size()) return fail("stream offsets not monotone");
+        sub.stream_off[(size_t)pr] = (uint32_t)sub.stream_m.size();
+        for (uint32_t ri = r0; ri < r1; ++ri) {
+          TcRec m = pl.stream_m[ri], p0 = pl.stream_p[0][ri], p1 = pl.stream_p[1][ri];
+          if ((int)((p0.w[1] >> 16) & 0x1F) != (int)(m.w[1] & 0x1F) || p0.w[1] != p1.w[1]) return fail(sp.name + ": records of one step name different segments");
+          if ((int)(m.w[1] & 0x1F) != v) continue;
+          if (((p0.w[1] >> 21) & 1u) != ((m.w[0] >> 16) & 1u) || ((p0.w[1] >> 22) & 1u) != ((m.w[0] >> 17) & 1u)) return fail(sp.name + ": first/last-step marks of producer and MMA records disagree");
+          const int mp = (int)(p0.w[1] & 0xFFFFu);
+          if (mp >= pl.n_mpairs || mp_group[(size_t)mp] != g) return fail(sp.name + ": a record's row pair is not in its group");
+          p0.w[1] = (uint32_t)mp_index[(size_t)mp]; p1.w[1] = p0.w[1]; m.w[1] = 0;
+          p0.w[6] = p0.w[7] = p1.w[6] = p1.w[7] = 0;
+          sub.stream_m.push_back(m); sub.stream_p[0].push_back(p0); sub.stream_p[1].push_back(p1);
+        }
+        const uint32_t e0 = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + k], e1 = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + k + 1];
+        if (e0 > e1 || e1 > pl.eitems.size()) return fail("item offsets not monotone");
+        for (uint32_t e = e0; e < e1; ++e) {
+          const uint4 it = pl.eitems[e];
+          if ((int)(it.x >> 16) != v) continue;
+          const uint32_t win = it.x & 0xFFFFu;
+          if (win > 0x7FFFu || it.y >= (uint32_t)pl.n_mpairs || mp_group[it.y] != g) return fail(sp.name + ": bad item");
+          if (it.z != pl.flag_base[(size_t)v] + (uint32_t)mp_index[it.y] * pl.n_windows[(size_t)v] + win) return fail(sp.name + ": an item publishes the wrong flag");
+          per_pair[(size_t)pr].push_back((int)((win << 16) | (uint32_t)mp_index[it.y]));
+        }
+      }
+      sub.stream_off[(size_t)n_pairs] = (uint32_t)sub.stream_m.size();
+      size_t n_slots = 0;
+      for (auto& l : per_pair) n_slots = std::max(n_slots, l.size());
+      sub.n_slots = (int)n_slots;
+      sub.eitems.assign(n_slots * (size_t)n_pairs, -1);
+      for (int pr = 0; pr < n_pairs; ++pr)
+        for (size_t i = 0; i < per_pair[(size_t)pr].size(); ++i) sub.eitems[i * (size_t)n_pairs + pr] = per_pair[(size_t)pr][i];
+      std::string e2;
+      if (tc2_check_plan(sp.N, sp.K, *sp.tab, n_mps, LOOP_RING_BYTES, sub, &e2, /*check_ring=*/false)) return fail(sp.name + " (section " + std::to_string(k) + "): " + e2);
+    }
+  // ---- ring, stream/item agreement, dependency coverage: per CTA pair and section
   for (int pr = 0; pr < n_pairs; ++pr) {
-    const uint32_t r0 = pl.stream_off[(size_t)pr * (n_seg + 1)], r1 = pl.stream_off[(size_t)pr * (n_seg + 1) + n_seg];
-    const int n = (int)(r1 - r0);
-    std::vector<int> beg((size_t)n), end((size_t)n), dep((size_t)n);
-    for (int k = 0; k < n; ++k) {
-      const TcRec& p0 = pl.stream_p[0][r0 + k];
-      const int s = (int)((p0.w[1] >> 16) & 0xF);
+    const uint32_t* so = &pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1)];
+    const uint32_t* eo = &pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1)];
+    auto region = [&](uint32_t ri, int* beg, int* end, int* dep) {
+      const TcRec& p0 = pl.stream_p[0][ri];
+      const int v = (int)((p0.w[1] >> 16) & 0x1F);
       const int nA = (int)((p0.w[0] >> 12) & 7), nB = (int)((p0.w[0] >> 15) & 0xF);
-      beg[(size_t)k] = (int)(p0.w[0] & 0xFF);
-      end[(size_t)k] = beg[(size_t)k] + (nA * TC_A_BYTES + nB * (specs[(size_t)s].N / 2) * 128 + 1023) / 1024;
-      dep[(size_t)k] = (int)((p0.w[0] >> 19) & 0xF);
-      if (end[(size_t)k] > ring_kb) return fail("step region outside the ring");
-      if (dep[(size_t)k] < 1 || dep[(size_t)k] > TC2_NSLOT) return fail("dep out of range");
-    }
-    for (int k = 0; k < n; ++k)
-      for (int d = 1; d < dep[(size_t)k]; ++d) {
-        const int c = ((k - d) % n + n) % n;
-        if (beg[(size_t)c] < end[(size_t)k] && beg[(size_t)k] < end[(size_t)c])
-          return fail("ring hazard: a region may be overwritten while it can still be read (cyclic check)");
-      }
-    // dependency coverage: walk the items of the pair in stream order
-    uint32_t e = pl.eitem_off[(size_t)pr * (n_seg + 1)];
-    std::vector<uint32_t> need;
-    for (int k = 0; k <= n; ++k) {
-      const bool first = (k < n) && ((pl.stream_p[0][r0 + k].w[1] >> 20) & 1u);
-      if ((first || k == n) && k > 0) {
-        // close the previous item: compare with its dependency list
-        const uint32_t d0 = pl.dep_off[e], d1 = pl.dep_off[e + 1];
-        for (uint32_t f : need)
-          if (std::find(pl.deps.begin() + d0, pl.deps.begin() + d1, f) == pl.deps.begin() + d1) return fail("an item stages a pixel it has no dependency on");
-        for (uint32_t d = d0; d < d1; ++d)
-          if ((pl.deps[d] & ~LOOP_DEP_PREV) >= pl.n_flags) return fail("dependency index out of range");
-        need.clear();
-        ++e;
-      }
-      if (k == n) break;
-      const TcRec& p0 = pl.stream_p[0][r0 + k];
-      const int s = (int)((p0.w[1] >> 16) & 0xF), mp = (int)(p0.w[1] & 0xFFFF), nA = (int)((p0.w[0] >> 12) & 7);
-      if (first) {
-        if (e >= pl.eitems.size() || (int)(pl.eitems[e].x >> 16) != s || (int)pl.eitems[e].y != mp) return fail("producer stream and item list disagree");
-        // the record announces the NEXT item's dependency range (none after the pair's last item)
-        const uint32_t lim = pl.eitem_off[(size_t)pr * (n_seg + 1) + n_seg];
-        const uint32_t want_d0 = (e + 1 < lim) ? pl.dep_off[e + 1] : 0u, want_cnt = (e + 1 < lim) ? pl.dep_off[e + 2] - pl.dep_off[e + 1] : 0u;
-        for (int r = 0; r < 2; ++r) {
-          const TcRec& pq = pl.stream_p[r][r0 + k];
-          if (pq.w[7] != want_cnt || (want_cnt != 0 && pq.w[6] != want_d0)) return fail("a record announces the wrong dependency range for the next item");
+      *beg = (int)(p0.w[0] & 0xFF);
+      *end = *beg + (nA * TC_A_BYTES + nB * (specs[(size_t)pl.vseg_phys[(size_t)v]].N / 2) * 128 + 1023) / 1024;
+      *dep = (int)((p0.w[0] >> 19) & 0xF);
+    };
+    auto check_ring = [&](uint32_t r0, uint32_t r1, bool cyclic) -> int {
+      const int n = (int)(r1 - r0);
+      for (int k2 = 0; k2 < n; ++k2) {
+        int b, e, d;
+        region(r0 + k2, &b, &e, &d);
+        if (e > ring_kb) return fail("step region outside the ring");
+        if (d < 1 || d > TC2_NSLOT) return fail("dep out of range");
+        if ((pl.stream_m[r0 + k2].w[0] & 0xFF) != (uint32_t)b) return fail("producer and MMA records place a step differently");
+        for (int dd = 1; dd < d; ++dd) {
+          int c = k2 - dd;
+          if (c < 0) { if (!cyclic) break; c = (c % n + n) % n; }
+          int cb, ce, cd;
+          region(r0 + c, &cb, &ce, &cd);
+          if (cb < e && b < ce) return fail("ring hazard: a region may be overwritten while it can still be read");
         }
       }
-      if ((((p0.w[1] >> 21) & 1u) != 0u) != (((pl.stream_m[r0 + k].w[0] >> 17) & 1u) != 0u)) return fail("last-step marks of producer and MMA records disagree");
-      const int in_seg = specs[(size_t)s].in_seg;
-      if (in_seg < 0) {
-        const uint32_t f = (pl.zflag_base + (uint32_t)mp) | LOOP_DEP_PREV;
-        if (std::find(need.begin(), need.end(), f) == need.end()) need.push_back(f);
-      } else {
-        if (in_seg >= s) return fail("a segment reads a later segment's output");
-        for (int a = 0; a < nA; ++a) {
-          const int p = (int)((p0.w[2 + a / 2] >> (16 * (a & 1))) & 0xFFFF);
-          if ((size_t)p >= pix2win[(size_t)in_seg].size() || pix2win[(size_t)in_seg][(size_t)p] < 0) return fail("staged pixel has no producing window");
-          const uint32_t f = pl.flag_base[(size_t)in_seg] + (uint32_t)mp * pl.n_windows[(size_t)in_seg] + (uint32_t)pix2win[(size_t)in_seg][(size_t)p];
+      return 0;
+    };
+    int rc2;
+    if ((rc2 = check_ring(so[0], so[1], false)) || (rc2 = check_ring(so[1], so[3], true)) || (rc2 = check_ring(so[3], so[4], false))) return rc2;
+    for (int k = 0; k < LOOP_N_SEC; ++k) {
+      uint32_t e = eo[k];
+      std::vector<uint32_t> need;
+      const int n = (int)(so[k + 1] - so[k]);
+      for (int k2 = 0; k2 <= n; ++k2) {
+        const bool first = (k2 < n) && ((pl.stream_p[0][so[k] + k2].w[1] >> 21) & 1u);
+        if ((first || k2 == n) && k2 > 0) {
+          const uint32_t d0 = pl.dep_off[e], d1 = pl.dep_off[e + 1];
+          for (uint32_t f : need)
+            if (std::find(pl.deps.begin() + d0, pl.deps.begin() + d1, f) == pl.deps.begin() + d1) return fail("an item stages a pixel it has no dependency on");
+          for (uint32_t d = d0; d < d1; ++d)
+            if ((pl.deps[d] & ~LOOP_DEP_PREV) >= pl.n_flags) return fail("dependency index out of range");
+          need.clear();
+          ++e;
+        }
+        if (k2 == n) break;
+        const TcRec& p0 = pl.stream_p[0][so[k] + k2];
+        const int v = (int)((p0.w[1] >> 16) & 0x1F), mp = (int)(p0.w[1] & 0xFFFF), nA = (int)((p0.w[0] >> 12) & 7);
+        if (v >= nv) return fail("record names an unknown segment");
+        const int g = pl.vseg_group[(size_t)v];
+        if (first) {
+          if (e >= eo[k + 1] || (int)(pl.eitems[e].x >> 16) != v || (int)pl.eitems[e].y != mp) return fail("producer stream and item list disagree");
+          const uint32_t want_d0 = (e + 1 < eo[k + 1]) ? pl.dep_off[e + 1] : 0u, want_cnt = (e + 1 < eo[k + 1]) ? pl.dep_off[e + 2] - pl.dep_off[e + 1] : 0u;
+          for (int r = 0; r < 2; ++r) {
+            const TcRec& pq = pl.stream_p[r][so[k] + k2];
+            if (pq.w[7] != want_cnt || (want_cnt != 0 && pq.w[6] != want_d0)) return fail("a record announces the wrong dependency range for the next item");
+          }
+        }
+        const int in_seg = specs[(size_t)pl.vseg_phys[(size_t)v]].in_seg;
+        if (in_seg < 0) {
+          const uint32_t f = (pl.zflag_base + (uint32_t)mp) | LOOP_DEP_PREV;
           if (std::find(need.begin(), need.end(), f) == need.end()) need.push_back(f);
+        } else {
+          const int vin = g * n_phys + in_seg;
+          for (int a = 0; a < nA; ++a) {
+            const int p = (int)((p0.w[2 + a / 2] >> (16 * (a & 1))) & 0xFFFF);
+            if ((size_t)p >= pix2win[(size_t)vin].size() || pix2win[(size_t)vin][(size_t)p] < 0) return fail("staged pixel has no producing window");
+            const uint32_t f = pl.flag_base[(size_t)vin] + (uint32_t)mp_index[(size_t)mp] * pl.n_windows[(size_t)vin] + (uint32_t)pix2win[(size_t)vin][(size_t)p];
+            if (std::find(need.begin(), need.end(), f) == need.end()) need.push_back(f);
+          }
         }
       }
+      if (e != eo[k + 1]) return fail("item count of a section's stream and its item list differ");
     }
-    if (e != pl.eitem_off[(size_t)pr * (n_seg + 1) + n_seg]) return fail("item count of a pair's stream and its item list differ");
   }
-  // ---- deadlock check: in-order execution per CTA pair, an item starts only when its dependencies are complete
+  // ---- deadlock check over a 3-step launch program.  flag value = completions so far; an item of L-step t waits for
+  //      "dependency completed t + 1 times" (or, for the z update, t times: the momentum tail of L-step t - 1).
   {
-    std::vector<char> done(pl.n_flags, 0);
-    std::vector<uint32_t> head((size_t)n_pairs);
-    for (int pr = 0; pr < n_pairs; ++pr) head[(size_t)pr] = pl.eitem_off[(size_t)pr * (n_seg + 1)];
-    size_t remaining = pl.eitems.size();
+    const int L = 3;
+    const std::vector<LoopProg> pg = loop_program(pl, L, false);
+    std::vector<int> done(pl.n_flags, 0), lin_parts((size_t)pl.n_mpairs * L, 0);
+    const int last_phys = n_phys - 1;          // the Linear backward: its items complete the z update of their row pair
+    int parts_per_mp = 0;
+    for (int v = 0; v < nv; ++v)
+      if (pl.vseg_phys[(size_t)v] == last_phys && pl.vseg_group[(size_t)v] == 0) parts_per_mp = (int)pl.n_windows[(size_t)v];
+    struct Cur { size_t pi; uint32_t e; };
+    std::vector<Cur> cur((size_t)n_pairs, Cur{0, 0});
+    for (int pr = 0; pr < n_pairs; ++pr) cur[(size_t)pr].e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pg[0].sec];
+    size_t remaining = 0;
+    for (const LoopProg& pe : pg)
+      for (int pr = 0; pr < n_pairs; ++pr) remaining += pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pe.sec + 1] - pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pe.sec];
     bool progress = true;
     while (remaining > 0 && progress) {
       progress = false;
       for (int pr = 0; pr < n_pairs; ++pr) {
-        const uint32_t lim = pl.eitem_off[(size_t)pr * (n_seg + 1) + n_seg];
-        while (head[(size_t)pr] < lim) {
-          const uint32_t e = head[(size_t)pr];
+        Cur& c = cur[(size_t)pr];
+        while (c.pi < pg.size()) {
+          const LoopProg& pe = pg[c.pi];
+          const uint32_t lim = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pe.sec + 1];
+          if (c.e >= lim) {
+            ++c.pi;
+            if (c.pi < pg.size()) c.e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pg[c.pi].sec];
+            continue;
+          }
+          const uint4 it = pl.eitems[c.e];
+          const int v = (int)(it.x >> 16), t = pl.vseg_group[(size_t)v] ? pe.t1 : pe.t0;
+          if (t < 0) return fail("the program runs a group's item in a section where that group has no L-step");
           bool ready = true;
-          for (uint32_t d = pl.dep_off[e]; d < pl.dep_off[e + 1] && ready; ++d)
-            if (!(pl.deps[d] & LOOP_DEP_PREV) && !done[pl.deps[d]]) ready = false;
+          for (uint32_t d = pl.dep_off[c.e]; d < pl.dep_off[c.e + 1] && ready; ++d) {
+            const uint32_t f = pl.deps[d] & ~LOOP_DEP_PREV;
+            if (pl.deps[d] & LOOP_DEP_PREV) ready = done[f] >= t;
+            else ready = done[f] >= t + 1;
+          }
           if (!ready) break;
-          const uint2 it = pl.eitems[e];
-          const int s = (int)(it.x >> 16);
-          const uint32_t f = pl.flag_base[(size_t)s] + it.y * pl.n_windows[(size_t)s] + (it.x & 0xFFFFu);
-          if (f >= pl.zflag_base || done[f]) return fail("item flag out of range or completed twice");
-          done[f] = 1;
-          ++head[(size_t)pr]; --remaining; progress = true;
+          if (done[it.z] != t) return fail("an item runs out of L-step order");
+          done[it.z] = t + 1;
+          if (pl.vseg_phys[(size_t)v] == last_phys && t < L - 1) {
+            if (++lin_parts[(size_t)it.y * L + t] == parts_per_mp) done[pl.zflag_base + it.y] = t + 1;
+          }
+          ++c.e; --remaining; progress = true;
         }
       }
     }
     if (remaining > 0) return fail("deadlock: some items can never start (dependency cycle across in-order streams)");
-    for (uint32_t f = 0; f < pl.zflag_base; ++f)
-      if (!done[f]) return fail("an item is missing from the L-step");
   }
   return 0;
 }

@@ -361,7 +361,8 @@ struct Tc2Plan {
 //  * ring safety: when a step's loads may start (step k - dep consumed), no earlier step that can still be read
 //    overlaps its region, regions stay inside the ring, dep <= number of barrier slots;
 //  * every (window, row pair) item is assigned to exactly one CTA pair.
-static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int ring_bytes, const Tc2Plan& pl, std::string* err) {
+static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int ring_bytes, const Tc2Plan& pl, std::string* err,
+                          bool check_ring = true) {
   auto fail = [&](const std::string& m) { *err = m; return DGAN_ERR_INVALID_ARG; };
   const int kch = K / 64, half_b = (N / 2) * 128, acc_stride = tc2_acc_stride(N), max_acc = TC2_BUF_COLS / acc_stride;
   const size_t n_pairs = (size_t)pl.n_pairs;
@@ -449,7 +450,7 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
         for (int i = 0; i < g; ++i) seen |= 1u << (acc0 + i);
       }
       // ring safety inside the segment (the cyclic check over a CTA pair's whole stream is loop_check_plan's)
-      for (int c = k - 1; c >= 0 && c >= k - 4 * TC2_NSLOT; --c) {
+      for (int c = k - 1; check_ring && c >= 0 && c >= k - 4 * TC2_NSLOT; --c) {
         const Step& o = steps[(size_t)c];
         if (!(o.beg < st.end && st.beg < o.end)) continue;
         if (c > k - dep) return fail("ring hazard: a region may be overwritten while it can still be read");

@@ -134,15 +134,13 @@ int dgan_last_status(dgan_handle h, int* status_out);
 int64_t dgan_macs_per_row(dgan_handle h);
 
 /* Device timing for roofline reports (no reference counterpart); never enable it in a timed throughput pass.
- *   level 1: every kernel launch of the production path is bracketed by CUDA events on the launching stream.  For
- *            DGAN_PREC_FP16 that is the single loop kernel (kind "projection_loop ..."); in addition the kernel records,
- *            per L-step and segment (layer-direction), the %globaltimer span from the first item's start to the last
- *            item's end over all CTA pairs - reported under the segment kinds (spans of neighbouring segments overlap).
- *   level 2: DGAN_PREC_FP16 only - the loop is executed one (L-step, segment) per launch, each timed in isolation
- *            (what a layer-per-kernel implementation would cost; the sum exceeds the fused kernel's time).
+ * While enabled (level != 0) every kernel launch of the production path is bracketed by CUDA events on the launching
+ * stream.  For DGAN_PREC_FP16 that is the single loop kernel (kind "projection_loop ..."); in addition the kernel records,
+ * per L-step, row-pair group and segment (layer-direction), the %globaltimer span from the first item's start to the
+ * last item's end over all CTA pairs - reported under the segment kinds (spans of neighbouring segments overlap).
  * dgan_profile_read synchronises on the recorded events and returns, per kind, the summed milliseconds, the launch (or
- * span) count and the algorithmic FLOPs of one launch (2 x exact in-bounds MACs x latent rows of the last call; for the
- * loop kernel x (2 rec_iters - 1) passes). */
+ * span) count and the algorithmic FLOPs of one launch / span (2 x exact in-bounds MACs x latent rows; for the loop kernel
+ * x its 2 rec_iters - 1 generator passes). */
 int dgan_profile_enable(dgan_handle h, int level);
 int dgan_profile_num_kinds(dgan_handle h);
 const char* dgan_profile_kind_name(dgan_handle h, int kind);

@@ -38,6 +38,13 @@ a = np.frombuffer(buf, dtype=np.uint64).reshape(MAXI, 8)[:n].astype(np.int64)
 deps = np.frombuffer(dbuf, dtype=np.int64).reshape(MAXI, MAXD)[:n]
 if out_path:
     np.savez_compressed(out_path, items=a, deps=deps, names=np.array(names))
+keep = a[:, 7] > 0                      # items of the two traced program entries (sections 1 and 2)
+idx_of = -np.ones(n, dtype=np.int64)
+idx_of[np.nonzero(keep)[0]] = np.arange(keep.sum())
+a = a[keep]
+deps = deps[keep]
+deps = np.where(deps >= 0, idx_of[np.clip(deps, 0, n - 1)], deps)
+n = len(a)
 t0 = a[:, 4][a[:, 4] > 0].min()
 pair, seg, win, mp = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
 wb, we, eb, ee = [(a[:, 4 + k] - t0) / 1e3 for k in range(4)]           # us
@@ -47,8 +54,9 @@ print("dependency wait: total %.1f us over %d CTA pairs = %.1f us per pair; item
     wait.sum(), len(set(pair)), wait.sum() / len(set(pair)), (wait > 1).sum()))
 for s in sorted(set(seg)):
     m = seg == s
-    print("  seg %d %-28s items %4d  wait/pair %6.1f us  begin %7.1f..%7.1f  epilogue end %7.1f..%7.1f" % (
-        s, names[s][:28], m.sum(), wait[m].sum() / len(set(pair)), wb[m].min(), wb[m].max(), ee[m].min(), ee[m].max()))
+    nph = len(names) - 1
+    print("  vseg %2d %s.%-26s items %4d  wait/pair %6.1f us  begin %7.1f..%7.1f  epilogue end %7.1f..%7.1f" % (
+        s, "AB"[s // nph], names[s % nph][:26], m.sum(), wait[m].sum() / len(set(pair)), wb[m].min(), wb[m].max(), ee[m].min(), ee[m].max()))
 order = np.argsort(-wait)[:25]
 print("longest waits: item (pair seg win mp) waited us | released by dep item (pair seg win mp) whose epilogue ended at, flag seen at")
 for e in order:
