@@ -336,29 +336,33 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
       const float* __restrict__ gp = reinterpret_cast<const float*>(out);
       const size_t base = (size_t)rt * kRowTile * N_TILE;
       const int tid = (warp - LOOP_EPI_WARP0) * 32 + lane;
-      constexpr int STRIDE = 4 * 32 * TC2_EPI_WARPS, UNR = 4;
+      // latency-bound (every operand is an L2 read): all partial sums, v and z of UNR positions are requested before any
+      // is used - one round trip per iteration instead of one per partial sum
+      constexpr int STRIDE = 4 * 32 * TC2_EPI_WARPS, UNR = 4, MAXP = TC_LINEAR_SPLIT;
       for (int e0 = tid * 4; e0 < kRowTile * N_TILE; e0 += UNR * STRIDE) {
-        float4 gs[UNR], vv[UNR], zz[UNR];
+        float4 gs[MAXP][UNR], vv[UNR], zz[UNR];
+#pragma unroll
+        for (int pp = 0; pp < MAXP; ++pp)
+#pragma unroll
+          for (int k = 0; k < UNR; ++k)
+            gs[pp][k] = (pp < P.m_nparts) ? __ldcg(reinterpret_cast<const float4*>(gp + base + (size_t)(e0 + k * STRIDE) + (size_t)pp * P.m_count))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
           const size_t i = base + (size_t)(e0 + k * STRIDE);
-          gs[k] = __ldcg(reinterpret_cast<const float4*>(gp + i));
           vv[k] = __ldcg(reinterpret_cast<const float4*>(P.mv + i));
           zz[k] = __ldcg(reinterpret_cast<const float4*>(P.mz + i));
         }
-        for (int pp = 1; pp < P.m_nparts; ++pp) {          // fixed order: parts 0, 1, 2, ...
-          float4 tt[UNR];
-#pragma unroll
-          for (int k = 0; k < UNR; ++k) tt[k] = __ldcg(reinterpret_cast<const float4*>(gp + base + (size_t)(e0 + k * STRIDE) + (size_t)pp * P.m_count));
-#pragma unroll
-          for (int k = 0; k < UNR; ++k) { gs[k].x += tt[k].x; gs[k].y += tt[k].y; gs[k].z += tt[k].z; gs[k].w += tt[k].w; }
-        }
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
           const size_t i = base + (size_t)(e0 + k * STRIDE);
+          float4 g4 = gs[0][k];
+#pragma unroll
+          for (int pp = 1; pp < MAXP; ++pp)          // fixed order: parts 0, 1, 2, ... (absent parts add +0)
+            if (pp < P.m_nparts) { g4.x += gs[pp][k].x; g4.y += gs[pp][k].y; g4.z += gs[pp][k].z; g4.w += gs[pp][k].w; }
           float4 v4 = vv[k], z4 = zz[k];
-          v4.x = fmaf(fa.m_mu, v4.x, fa.m_gmul * gs[k].x); v4.y = fmaf(fa.m_mu, v4.y, fa.m_gmul * gs[k].y);
-          v4.z = fmaf(fa.m_mu, v4.z, fa.m_gmul * gs[k].z); v4.w = fmaf(fa.m_mu, v4.w, fa.m_gmul * gs[k].w);
+          v4.x = fmaf(fa.m_mu, v4.x, fa.m_gmul * g4.x); v4.y = fmaf(fa.m_mu, v4.y, fa.m_gmul * g4.y);
+          v4.z = fmaf(fa.m_mu, v4.z, fa.m_gmul * g4.z); v4.w = fmaf(fa.m_mu, v4.w, fa.m_gmul * g4.w);
           z4.x -= fa.m_lr * v4.x; z4.y -= fa.m_lr * v4.y; z4.z -= fa.m_lr * v4.z; z4.w -= fa.m_lr * v4.w;
           *reinterpret_cast<float4*>(P.mv + i) = v4;
           *reinterpret_cast<float4*>(P.mz + i) = z4;
