@@ -138,13 +138,13 @@ struct SegBind {
 
 // one L-step plan (kernels_loop.cuh) uploaded for a given number of 256-row pairs
 struct DevPlan {
-  int n_mpairs = 0, n_pairs = 0, n_groups = 1;
+  int n_mpairs = 0, n_pairs = 0;
   dgan::LoopPlan host;
   dgan::TcItem2* items[dgan::LOOP_MAX_SEG] = {nullptr};
-  dgan::TcRec* stream_p[2] = {nullptr, nullptr};
-  dgan::TcRec* stream_m = nullptr;
-  uint32_t *stream_off = nullptr, *eitem_off = nullptr, *dep_off = nullptr, *deps = nullptr;
-  uint4* eitems = nullptr;
+  dgan::TcRec* tmpl_p[2] = {nullptr, nullptr};
+  dgan::TcRec* tmpl_m = nullptr;
+  uint32_t *win_rec_off = nullptr, *succ_off = nullptr, *succ = nullptr, *need = nullptr;
+  unsigned long long* q_init = nullptr;
 };
 
 struct dgan_ctx {
@@ -175,6 +175,7 @@ struct dgan_ctx {
   int loop_passes = 0;                    // generator passes (forward or backward) of the last loop launch: its FLOPs
   unsigned long long* dbg_dev = nullptr; int dbg_ctas = 0;   // per-CTA stall counters of the last profiled loop launch
   unsigned long long* trace_dev = nullptr; size_t trace_items = 0; const DevPlan* trace_plan = nullptr;   // per-item timestamps of one L-step
+  int trace_step = -1;
   int n_rows_cur = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -252,9 +253,10 @@ struct Workspace {
   __half* z_h = nullptr;
   std::vector<unsigned long long*> maskbits;   // fp16 path: 1-bit ReLU masks per hidden layer output
   unsigned* mom_counter = nullptr;     // fp16 path: [n_pad / 128] tickets of the split-K Linear backward's momentum tail
-  uint32_t* flags = nullptr;           // fp16 path: per-item completion flags of the loop kernel (+ one z flag per row pair)
-  uint32_t* status = nullptr;          // fp16 path: [4] watchdog status of the loop kernel
-  size_t n_flags = 0;
+  // fp16 path, the loop kernel's scheduling state: [status(4) | q_ctl(4) | arrive(n_counters) | depcnt(n_counters)] and the queue
+  uint32_t *status = nullptr, *q_ctl = nullptr, *arrive = nullptr, *depcnt = nullptr;
+  unsigned long long* queue = nullptr;
+  size_t n_counters = 0, q_cap = 0;
   __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
   int n_loss_parts = 0, n_g_parts = 1;
   size_t loss_stride_n = 1, loss_stride_b = 1;   // loss_part index = n * stride_n + part * stride_b
@@ -283,12 +285,16 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   if (tc) w.z_h = (__half*)take(np * latent * 2);
   if (tc) w.mom_counter = (unsigned*)take(np / kRowTile * sizeof(unsigned));
   if (tc) {
-    // one flag per (segment, window, row pair); a window holds at least one output pixel
-    size_t per_mp = 1;
+    // two counters per (segment, window, row pair); a window holds at least one output pixel, which bounds the plan's
+    // needs whatever tiling it picks (the queue capacity follows loop_plan's rule on that bound)
+    size_t per_mp = 0;
     for (const LoopSegSpec& sp : c->segs) per_mp += sp.tab->off.size() - 1;
-    w.n_flags = per_mp * (np / (2 * kRowTile));
-    w.flags = (uint32_t*)take(w.n_flags * sizeof(uint32_t));
-    w.status = (uint32_t*)take(4 * sizeof(uint32_t));
+    w.n_counters = per_mp * (np / (2 * kRowTile));
+    w.status = (uint32_t*)take((8 + 2 * w.n_counters) * sizeof(uint32_t));
+    if (w.status != nullptr) { w.q_ctl = w.status + 4; w.arrive = w.status + 8; w.depcnt = w.arrive + w.n_counters; }
+    w.q_cap = 1024;
+    while (w.q_cap < 4 * (w.n_counters + (size_t)c->n_pairs) + 64) w.q_cap <<= 1;
+    w.queue = (unsigned long long*)take(w.q_cap * sizeof(unsigned long long));
   }
   if (tc) w.dblk = (__half*)take((size_t)c->tc_fin.n_blocks * np * 64 * 2);
   w.n_loss_parts = tc ? c->tc_fin.n_blocks : c->fin.n_bands;
@@ -484,10 +490,6 @@ static int run_init_z(dgan_ctx* c, const Workspace& w, const float* z0, uint64_t
   // the last layer's block tensor is K-padded to 64 columns; the epilogue only ever writes the 16*C_out valid ones
   if (w.dblk != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.dblk, 0, (size_t)c->tc_fin.n_blocks * w.n_pad * 64 * sizeof(__half), s));
   if (w.mom_counter != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.mom_counter, 0, (size_t)w.n_pad / kRowTile * sizeof(unsigned), s));
-  if (w.flags != nullptr) {       // the loop kernel's completion flags and watchdog status start every call at zero
-    DGAN_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, w.n_flags * sizeof(uint32_t), s));
-    DGAN_CUDA_CHECK(cudaMemsetAsync(w.status, 0, 4 * sizeof(uint32_t), s));
-  }
   // fp32 path: the last layer's forward writes dL/dpre for the real rows only while its backward walks all n_pad rows;
   // the tile-padding rows are never observed, but they must not be read uninitialised
   if (w.dblk == nullptr && w.n_pad > w.n_rows)
@@ -619,26 +621,25 @@ static int upload_vec(dgan_ctx* c, const std::vector<T>& v, T** dev) {
 // in dgan_workspace_bytes - which a caller needs before its first dgan_reconstruct of a batch size anyway - so that
 // dgan_reconstruct itself never allocates or synchronises (it only falls back to planning here if the caller sized the
 // workspace some other way).
-static int get_plan(dgan_ctx* c, int n_rows, int n_groups, const DevPlan** out) {
+static int get_plan(dgan_ctx* c, int n_rows, const DevPlan** out) {
   const int n_pad = (int)align_up((size_t)std::max(n_rows, 1), 2 * kRowTile), n_mpairs = n_pad / (2 * kRowTile);
-  if (n_mpairs < 2) n_groups = 1;
   for (auto& p : c->plans)
-    if (p->n_mpairs == n_mpairs && p->n_groups == n_groups) { *out = p.get(); return 0; }
+    if (p->n_mpairs == n_mpairs) { *out = p.get(); return 0; }
   std::unique_ptr<DevPlan> dp(new DevPlan());
-  dp->n_mpairs = n_mpairs; dp->n_pairs = c->n_pairs; dp->n_groups = n_groups;
+  dp->n_mpairs = n_mpairs; dp->n_pairs = c->n_pairs;
   int rc;
-  if ((rc = loop_plan(c->segs, n_mpairs, c->n_pairs, n_groups, &dp->host))) return rc;
+  if ((rc = loop_plan(c->segs, n_mpairs, c->n_pairs, &dp->host))) return rc;
   const LoopPlan& pl = dp->host;
-  for (int v = 0; v < pl.n_vseg; ++v)
+  for (int v = 0; v < pl.n_seg; ++v)
     if ((rc = upload_vec(c, pl.hdrs[(size_t)v], &dp->items[v]))) return rc;
   for (int r = 0; r < 2; ++r)
-    if ((rc = upload_vec(c, pl.stream_p[r], &dp->stream_p[r]))) return rc;
-  if ((rc = upload_vec(c, pl.stream_m, &dp->stream_m))) return rc;
-  if ((rc = upload_vec(c, pl.stream_off, &dp->stream_off))) return rc;
-  if ((rc = upload_vec(c, pl.eitems, &dp->eitems))) return rc;
-  if ((rc = upload_vec(c, pl.eitem_off, &dp->eitem_off))) return rc;
-  if ((rc = upload_vec(c, pl.dep_off, &dp->dep_off))) return rc;
-  if ((rc = upload_vec(c, pl.deps, &dp->deps))) return rc;
+    if ((rc = upload_vec(c, pl.tmpl_p[r], &dp->tmpl_p[r]))) return rc;
+  if ((rc = upload_vec(c, pl.tmpl_m, &dp->tmpl_m))) return rc;
+  if ((rc = upload_vec(c, pl.win_rec_off, &dp->win_rec_off))) return rc;
+  if ((rc = upload_vec(c, pl.succ_off, &dp->succ_off))) return rc;
+  if ((rc = upload_vec(c, pl.succ, &dp->succ))) return rc;
+  if ((rc = upload_vec(c, pl.need, &dp->need))) return rc;
+  if ((rc = upload_vec(c, pl.q_init, &dp->q_init))) return rc;
   c->plans.push_back(std::move(dp));
   *out = c->plans.back().get();
   return 0;
@@ -651,7 +652,7 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
   LoopParams& P = c->lp;
   P = LoopParams{};
   const LoopPlan& pl = dp->host;
-  if (pl.n_flags > w.n_flags) { set_error("internal: flag array smaller than the plan needs"); return DGAN_ERR_WORKSPACE; }
+  if (pl.n_item_slots > w.n_counters || pl.q_cap > w.q_cap) { set_error("internal: scheduling state smaller than the plan needs"); return DGAN_ERR_WORKSPACE; }
   int rc;
   auto tensor = [&](int kind, int idx, const void** base, int* chan, int* pix) {
     const int latent = c->desc.latent_dim;
@@ -663,8 +664,8 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
       default: *base = w.g; *chan = latent; *pix = TC_LINEAR_SPLIT; break;
     }
   };
-  for (int v = 0; v < pl.n_vseg; ++v) {
-    const int s = pl.vseg_phys[(size_t)v];
+  for (int v = 0; v < pl.n_seg; ++v) {
+    const int s = v;
     const SegBind& b = c->binds[(size_t)s];
     const LoopSegSpec& sp = c->segs[(size_t)s];
     LoopSeg& g = P.seg[v];
@@ -687,16 +688,19 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
     g.acc_stride = (uint32_t)tc2_acc_stride(sp.N);
     g.idesc = make_idesc_f16(256, sp.N);
     g.half_b = (uint32_t)(sp.N / 2) * 128u;
-    g.phys = (uint32_t)s; g.group = (uint32_t)pl.vseg_group[(size_t)v];
+    g.win_base = pl.win_base[(size_t)v]; g.item_base = pl.item_base[(size_t)v]; g.n_windows = pl.n_windows[(size_t)v];
   }
-  P.stream_p[0] = dp->stream_p[0]; P.stream_p[1] = dp->stream_p[1]; P.stream_m = dp->stream_m;
-  P.stream_off = dp->stream_off; P.eitems = dp->eitems; P.eitem_off = dp->eitem_off; P.dep_off = dp->dep_off; P.deps = dp->deps;
-  P.flags = w.flags; P.status = w.status; P.prof = nullptr; P.dbg = nullptr; P.trace = nullptr; P.trace_entry = -2;
-  P.n_groups = pl.n_groups; P.n_vseg = pl.n_vseg; P.n_pad = w.n_pad; P.n_mpairs = dp->n_mpairs;
+  P.tmpl_p[0] = dp->tmpl_p[0]; P.tmpl_p[1] = dp->tmpl_p[1]; P.tmpl_m = dp->tmpl_m;
+  P.win_rec_off = dp->win_rec_off; P.succ_off = dp->succ_off; P.succ = dp->succ; P.need = dp->need;
+  P.queue = w.queue; P.q_ctl = w.q_ctl; P.arrive = w.arrive; P.depcnt = w.depcnt;
+  P.q_cap = pl.q_cap; P.q_shift = 0;
+  while ((1u << P.q_shift) < pl.q_cap) ++P.q_shift;
+  P.q_init = (uint32_t)pl.q_init.size(); P.n_pairs = (uint32_t)dp->n_pairs;
+  P.status = w.status; P.prof = nullptr; P.dbg = nullptr; P.trace = nullptr; P.trace_step = -1;
+  P.n_seg = pl.n_seg; P.n_fwd = pl.n_fwd; P.n_pad = w.n_pad; P.n_mpairs = dp->n_mpairs;
   P.y = w.y; P.loss_part = w.loss_part; P.n_rows = w.n_rows; P.nbx = c->tc_fin.nbx; P.w_out = c->tc_fin.w_out;
   P.gscale = c->tc.grad_scale;
   P.mz = w.z; P.mv = w.v; P.mz_h = w.z_h; P.m_nparts = w.n_g_parts; P.m_count = (size_t)w.n_pad * c->desc.latent_dim;
-  P.zflag_base = pl.zflag_base;
   c->lp_ws = ws_base; c->lp_rows = w.n_rows; c->lp_plan = dp;
   return 0;
 }
@@ -704,28 +708,37 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
 enum LoopMode : int { LOOP_RECONSTRUCT = 0, LOOP_FORWARD = 1, LOOP_LOSS_GRAD = 2 };
 
 // Enqueue the loop kernel: rec_iters L-steps of (forward, loss, backward-to-z, momentum); the final L-step is forward
-// only (the loop returns the pre-update forward of iteration L-1, models/gan.py:419-421).  A projection runs
-// the two-group plan (row pairs half an L-step out of phase, see LoopPlan); dgan_forward / dgan_loss_grad - one
-// evaluation, nothing to overlap - the one-group plan.
+// only (the loop returns the pre-update forward of iteration L-1, models/gan.py:419-421) except for
+// dgan_loss_grad, which wants the gradient of its one evaluation.  Three small memory operations put the scheduling
+// state in its initial condition first: counters zero, queue slots unwritten, the first segment's items of L-step 0 ready.
 static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, const float* x, int R, int B, int rec_iters,
                        float lr, float mu, int decay_lr, int mode, cudaStream_t s) {
   const DevPlan* dp = nullptr;
   int rc;
-  if ((rc = get_plan(c, w.n_rows, mode == LOOP_RECONSTRUCT ? DGAN_LOOP_GROUPS : 1, &dp))) return rc;
+  if (rec_iters < 1 || rec_iters > 0xFFFF) { set_error("rec_iters must be in [1, 65535] on the fp16 path"); return DGAN_ERR_INVALID_ARG; }
+  if ((rc = get_plan(c, w.n_rows, &dp))) return rc;
   if ((rc = build_params(c, w, ws_base, dp))) return rc;
+  const LoopPlan& pl = dp->host;
   LoopParams P = c->lp;
   P.x = x; P.R = R; P.B = B;
   P.m_gmul = grad_multiplier(c); P.m_lr = lr; P.m_mu = mu;
   P.m_counter = (mode == LOOP_RECONSTRUCT) ? w.mom_counter : nullptr;
   P.decay_step = decay_lr ? (int)std::ceil(rec_iters * 0.8) : 0;
   P.last_step = rec_iters - 1;
-  P.n_prog = loop_prog_length(dp->n_groups, rec_iters, mode == LOOP_LOSS_GRAD);
+  P.full_last = (mode == LOOP_LOSS_GRAD) ? 1 : 0;
+  const unsigned long long total = loop_total_items(pl, rec_iters, mode == LOOP_LOSS_GRAD);
+  if (total + (unsigned long long)dp->n_pairs >= 0xFFFFFFFFull) { set_error("too many work items for one launch (batch x rec_rr x rec_iters)"); return DGAN_ERR_UNSUPPORTED; }
+  P.n_items_total = (uint32_t)total;
+  DGAN_CUDA_CHECK(cudaMemsetAsync(w.status, 0, (8 + 2 * (size_t)pl.n_item_slots) * sizeof(uint32_t), s));
+  DGAN_CUDA_CHECK(cudaMemsetAsync(w.queue, 0xFF, (size_t)pl.q_cap * sizeof(unsigned long long), s));
+  DGAN_CUDA_CHECK(cudaMemcpyAsync(w.queue, dp->q_init, pl.q_init.size() * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+  if (w.mom_counter != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.mom_counter, 0, (size_t)w.n_pad / kRowTile * sizeof(unsigned), s));
   c->last_status = w.status;
   c->loop_passes = (mode == LOOP_LOSS_GRAD) ? 2 * rec_iters : 2 * rec_iters - 1;
   const dim3 grid((unsigned)(2 * dp->n_pairs)), block(LOOP_THREADS);
   if (c->profile == 1) {
-    // in-kernel spans: [L-step][virtual segment] {min start, max end} of %globaltimer; per-CTA stall counters; item trace
-    const size_t need = (size_t)rec_iters * P.n_vseg * 2;
+    // in-kernel spans: [L-step][segment] {min start, max end} of %globaltimer; per-CTA stall counters; item trace of one L-step
+    const size_t need = (size_t)rec_iters * P.n_seg * 2;
     if (need > c->prof_cap) {
       if (c->prof_dev) cudaFree(c->prof_dev);
       c->prof_dev = nullptr; c->prof_cap = 0;
@@ -746,7 +759,7 @@ static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, con
     }
     DGAN_CUDA_CHECK(cudaMemsetAsync(c->dbg_dev, 0, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long), s));
     P.dbg = c->dbg_dev;
-    const size_t n_items = dp->host.eitems.size();
+    const size_t n_items = pl.n_item_slots;
     if (c->trace_dev == nullptr || c->trace_items < n_items) {
       if (c->trace_dev) cudaFree(c->trace_dev);
       c->trace_dev = nullptr; c->trace_items = 0;
@@ -754,9 +767,9 @@ static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, con
       c->trace_items = n_items;
     }
     DGAN_CUDA_CHECK(cudaMemsetAsync(c->trace_dev, 0, n_items * 4 * sizeof(unsigned long long), s));
-    // two consecutive program entries in the steady state: section 1 then section 2
     P.trace = c->trace_dev; c->trace_plan = dp;
-    P.trace_entry = std::max(0, ((P.n_prog - 4) | 1));
+    P.trace_step = std::max(0, rec_iters - 3);         // an L-step in the steady state
+    c->trace_step = P.trace_step;
   }
   cudaError_t e;
   {
@@ -1002,7 +1015,7 @@ size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
   if (h->desc.precision == DGAN_PREC_FP16) {
     // plan (and upload) the loop kernel's schedule for this row count now, so that dgan_reconstruct never has to
     const DevPlan* dp = nullptr;
-    if (get_plan(h, batch * rec_rr, DGAN_LOOP_GROUPS, &dp) != 0) return 0;
+    if (get_plan(h, batch * rec_rr, &dp) != 0) return 0;
   }
   return carve(h, batch * rec_rr, nullptr).bytes;
 }
@@ -1152,18 +1165,16 @@ int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* lau
   h->prof.clear();
   if (tc && h->profile == 1 && h->prof_L > 0 && h->prof_dev != nullptr && h->prof_plan != nullptr) {
     // the fused launch: its FLOPs are those of `loop_passes` generator passes; its segments are reported as in-kernel
-    // spans (first item start .. last item end over all CTA pairs, per row-pair group and L-step; spans of neighbouring
-    // segments - and of the two groups, which run half a step apart - overlap)
+    // spans (first item start .. last item end over all CTA pairs, per L-step; items of neighbouring segments - and of
+    // different row pairs, which drift apart - overlap, so the spans add up to more than the launch)
     const LoopPlan& pl = h->prof_plan->host;
-    const int n_phys = (int)h->segs.size(), L = h->prof_L, nv = pl.n_vseg;
-    if (nk == n_phys + 1) flops_per_launch_out[n_phys] *= 0.5 * (double)h->loop_passes;
-    std::vector<unsigned long long> st((size_t)L * nv * 2);
+    const int n_seg = pl.n_seg, L = h->prof_L;
+    if (nk == n_seg + 1) flops_per_launch_out[n_seg] *= 0.5 * (double)h->loop_passes;
+    std::vector<unsigned long long> st((size_t)L * n_seg * 2);
     DGAN_CUDA_CHECK(cudaMemcpy(st.data(), h->prof_dev, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (int sg = 0; sg < n_phys && sg < nk; ++sg) flops_per_launch_out[sg] /= (double)pl.n_groups;     // a span covers one group's rows
     for (int t = 0; t < L; ++t)
-      for (int v = 0; v < nv; ++v) {
-        const int sg = pl.vseg_phys[(size_t)v];
-        const unsigned long long a = st[((size_t)t * nv + v) * 2], b = st[((size_t)t * nv + v) * 2 + 1];
+      for (int sg = 0; sg < n_seg; ++sg) {
+        const unsigned long long a = st[((size_t)t * n_seg + sg) * 2], b = st[((size_t)t * n_seg + sg) * 2 + 1];
         if (sg >= nk || a == ~0ull || b <= a) continue;
         ms_out[sg] += (double)(b - a) * 1e-6;
         launches_out[sg]++;
@@ -1183,32 +1194,40 @@ int dgan_debug_loop_stalls(dgan_handle h, unsigned long long* out, int max_ctas)
   return n;
 }
 
-// Developer aid (not in the public header): the traced L-step of the most recent profiled loop launch.  Per item (in the
-// plan's item order): out[8i..] = {CTA pair, segment, window, row pair, dependency-wait begin, wait end, epilogue begin,
-// epilogue end} (times in ns of %globaltimer); deps_out (if not NULL) receives per item up to `max_deps` item indices it
-// depends on (-1 padded; -2 = the previous L-step's z update).  Returns the number of items.
+// Developer aid (not in the public header): the traced L-step of the most recent profiled loop launch.  Per item (segment
+// after segment, row pair major, window minor): out[8i..] = {CTA pair, segment, window, row pair, time the item was taken
+// from the queue, time its operands' first MMA step could start (accumulator buffer free), epilogue begin, epilogue end}
+// (ns of %globaltimer; 0 = not recorded).  deps_out (if not NULL) receives per item up to `max_deps` indices of the items
+// it waits for (-1 padded; -2 = the previous L-step's z update).  Returns the number of items.
 int dgan_debug_loop_trace(dgan_handle h, unsigned long long* out, long long* deps_out, int max_deps, int max_items) {
   if (h == nullptr || out == nullptr || h->trace_dev == nullptr || h->trace_plan == nullptr) return 0;
   const LoopPlan& pl = h->trace_plan->host;
-  const int n = (int)std::min<size_t>((size_t)max_items, pl.eitems.size());
-  std::vector<unsigned long long> raw((size_t)pl.eitems.size() * 4);
+  const size_t n_all = pl.n_item_slots;
+  const int n = (int)std::min<size_t>((size_t)max_items, n_all);
+  std::vector<unsigned long long> raw(n_all * 4);
   cudaDeviceSynchronize();
   cudaMemcpy(raw.data(), h->trace_dev, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  std::vector<long long> flag2item(pl.n_flags, -1);
-  std::vector<int> pair_of(pl.eitems.size(), 0);
-  for (int pr = 0; pr < pl.n_pairs; ++pr)
-    for (uint32_t e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1)]; e < pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + LOOP_N_SEC]; ++e) pair_of[e] = pr;
-  // the traced entries are sections 1 and 2: map a flag to the item of those sections that publishes it
-  for (int pr = 0; pr < pl.n_pairs; ++pr)
-    for (uint32_t e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + 1]; e < pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + 3]; ++e) flag2item[pl.eitems[e].z] = (long long)e;
+  // inverse of the successor lists: the windows an item waits for
+  std::vector<std::vector<uint32_t>> preds(pl.n_win);
+  for (int sg = 0; sg + 1 < pl.n_seg; ++sg)
+    for (uint32_t w = 0; w < pl.n_windows[(size_t)sg]; ++w)
+      for (uint32_t si = pl.succ_off[pl.win_base[(size_t)sg] + w]; si < pl.succ_off[pl.win_base[(size_t)sg] + w + 1]; ++si)
+        preds[pl.win_base[pl.succ[si] >> 16] + (pl.succ[si] & 0xFFFFu)].push_back(w);
+  int sg = 0;
   for (int e = 0; e < n; ++e) {
-    const uint4 it = pl.eitems[(size_t)e];
-    out[(size_t)e * 8 + 0] = (unsigned long long)pair_of[(size_t)e]; out[(size_t)e * 8 + 1] = it.x >> 16; out[(size_t)e * 8 + 2] = it.x & 0xFFFFu; out[(size_t)e * 8 + 3] = it.y;
-    for (int k = 0; k < 4; ++k) out[(size_t)e * 8 + 4 + k] = raw[(size_t)e * 4 + k];
+    while (sg + 1 < pl.n_seg && (uint32_t)e >= pl.item_base[(size_t)sg + 1]) ++sg;
+    const uint32_t local = (uint32_t)e - pl.item_base[(size_t)sg], mp = local / pl.n_windows[(size_t)sg], win = local % pl.n_windows[(size_t)sg];
+    out[(size_t)e * 8 + 0] = raw[(size_t)e * 4 + 0] >> 48; out[(size_t)e * 8 + 1] = (unsigned long long)sg; out[(size_t)e * 8 + 2] = win; out[(size_t)e * 8 + 3] = mp;
+    out[(size_t)e * 8 + 4] = raw[(size_t)e * 4 + 0] & 0xFFFFFFFFFFFFull;
+    for (int k = 1; k < 4; ++k) out[(size_t)e * 8 + 4 + k] = raw[(size_t)e * 4 + k];
     if (deps_out != nullptr) {
       int k = 0;
-      for (uint32_t d = pl.dep_off[(size_t)e]; d < pl.dep_off[(size_t)e + 1] && k < max_deps; ++d, ++k)
-        deps_out[(size_t)e * max_deps + k] = (pl.deps[d] & LOOP_DEP_PREV) ? -2 : flag2item[pl.deps[d]];
+      if (sg == 0) deps_out[(size_t)e * max_deps + k++] = -2;
+      else
+        for (uint32_t u : preds[pl.win_base[(size_t)sg] + win]) {
+          if (k >= max_deps) break;
+          deps_out[(size_t)e * max_deps + k++] = (long long)(pl.item_base[(size_t)sg - 1] + mp * pl.n_windows[(size_t)sg - 1] + u);
+        }
       for (; k < max_deps; ++k) deps_out[(size_t)e * max_deps + k] = -1;
     }
   }
@@ -1219,13 +1238,12 @@ int dgan_debug_loop_trace(dgan_handle h, unsigned long long* out, long long* dep
 // `n_pairs` CTA pairs exactly as dgan_reconstruct would, and validate the plan with loop_check_plan.  Needs no GPU.
 // `mutate` != 0 damages the plan in one specific way first: the check must then fail (self-test of the validator).
 // Returns 0, or an error code with the failing check in dgan_last_error().
-int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int n_groups, int mutate) {
+int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int mutate) {
   using namespace dgan;
   if (d == nullptr || n_rows <= 0 || n_pairs <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
   const bool celeba = d->arch == DGAN_ARCH_CELEBA;
   const int nd = d->net_dim, latent = d->latent_dim;
   const int n_pad = ((n_rows + 2 * kRowTile - 1) / (2 * kRowTile)) * 2 * kRowTile, n_mpairs = n_pad / (2 * kRowTile);
-  if (n_mpairs < 2) n_groups = 1;
   struct Dir { std::string name; int N, K; PairTable tab; int h, w, force_acc, epi, out_bytes; bool fwd; };
   std::vector<Dir> fwd, bwd;
   fwd.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2, true});
@@ -1263,52 +1281,52 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int n_gr
     segs.push_back(sp);
   }
   LoopPlan plan;
-  int rc = loop_plan(segs, n_mpairs, n_pairs, n_groups, &plan);
+  int rc = loop_plan(segs, n_mpairs, n_pairs, &plan);
   if (rc) return rc;
   if (mutate != 0) {
-    // damage the records of the first CTA pair inside section 2 (the forward half of group A, where Generator.3 fwd lives)
-    const size_t r0 = plan.stream_off[2], r1 = plan.stream_off[3];
-    if (r1 - r0 < 12) { set_error("plan too small to mutate"); return DGAN_ERR_INVALID_ARG; }
-    size_t k = r0 + (r1 - r0) / 2;
-    while (k + 2 < r1 && ((plan.stream_m[k].w[0] >> 16) & 3u)) ++k;          // a step in the middle of an item
-    TcRec& m = plan.stream_m[k];
-    TcRec* pp[2] = {&plan.stream_p[0][k], &plan.stream_p[1][k]};
-    const uint32_t e2 = plan.eitem_off[2];
+    // damage a step in the middle of a multi-step window of Generator.3 fwd (segment 2) - or a table entry next to it
+    const int sg = 2;
+    uint32_t win = 0;
+    for (uint32_t w = 0; w < plan.n_windows[sg]; ++w)
+      if (plan.win_rec_off[plan.win_base[sg] + w + 1] - plan.win_rec_off[plan.win_base[sg] + w] >= 3) { win = w; break; }
+    const uint32_t wi = plan.win_base[sg] + win;
+    const size_t r0 = plan.win_rec_off[wi], r1 = plan.win_rec_off[wi + 1];
+    if (r1 - r0 < 3) { set_error("plan too small to mutate"); return DGAN_ERR_INVALID_ARG; }
+    const size_t k = r0 + 1;
+    TcRec& m = plan.tmpl_m[k];
+    TcRec* pp[2] = {&plan.tmpl_p[0][k], &plan.tmpl_p[1][k]};
     switch (mutate) {
       case 1: m.w[2] ^= 1u << 10; break;                                  // first-MMA flag of an op
       case 2: m.w[2] ^= 1u << 7; break;                                   // accumulator of an op
       case 3: pp[0]->w[4] ^= 0x01; break;                                 // weight tile staged by rank 0 only
       case 4: pp[0]->w[2] ^= 0x01; pp[1]->w[2] ^= 0x01; break;            // input pixel of an A tile
       case 5: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~(0xFu << 8)) | ((((pp[r]->w[0] >> 8) & 0xF) ^ 1u) << 8); break;   // k-chunk
-      case 6: plan.eitems[e2].x ^= 1u; break;                             // epilogue list names another window
-      case 7: for (size_t i = 0; i < plan.stream_m.size(); ++i)           // every dep -> 8: ring hazards
-                for (int r = 0; r < 2; ++r) plan.stream_p[r][i].w[0] = (plan.stream_p[r][i].w[0] & ~(0xFu << 19)) | (8u << 19);
+      case 6: plan.win_rec_off[wi + 1] -= 1; break;                       // a window loses its last step to its neighbour
+      case 7: m.w[0] ^= 1u << 18; break;                                  // MMA warp and producer disagree on the step's size (ring placement)
+      case 8: for (int r = 0; r < 2; ++r) pp[r]->w[0] |= 0xBFu; break;    // a run-time field is not blank
+      case 9: std::swap(plan.tmpl_m[k], plan.tmpl_m[k + 1]);              // two steps out of order
+              for (int r = 0; r < 2; ++r) std::swap(plan.tmpl_p[r][k], plan.tmpl_p[r][k + 1]);
               break;
-      case 8: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~0xFFu) | 0xBFu; m.w[0] = (m.w[0] & ~0xFFu) | 0xBFu; break;   // region past the ring
-      case 9: std::swap(plan.stream_m[k], plan.stream_m[k + 1]);          // two steps out of order
-              for (int r = 0; r < 2; ++r) std::swap(plan.stream_p[r][k], plan.stream_p[r][k + 1]);
-              break;
-      case 10: plan.deps[plan.dep_off[e2 + 1]] ^= 1u; break;              // an item waits for the wrong window
-      case 11: plan.eitems[e2].z += 1u; break;                            // an item publishes another item's flag
-      case 12: {                                                          // the pair's first two items of the section swapped in the item list only
-        std::swap(plan.eitems[e2], plan.eitems[e2 + 1]);
-        break;
-      }
+      case 10: plan.need[wi] += 1; break;                                 // an item waits for one completion too many: never ready
+      case 11: plan.succ[plan.succ_off[wi]] ^= 1u; break;                 // an item wakes the wrong window
+      case 12: plan.succ_off[wi + 1] -= 1; plan.succ_off[wi] += 0; for (uint32_t j = wi + 1; j < plan.n_win; ++j) { if (j > wi + 1) plan.succ_off[j] -= 1; } plan.succ_off[plan.n_win] -= 1;
+               plan.succ.erase(plan.succ.begin() + plan.succ_off[wi + 1]); break;      // a successor is missing
+      case 13: plan.q_init.pop_back(); break;                             // a first-segment item is never started
+      case 14: plan.q_cap = 64; break;                                    // queue too small for what can be ready at once
       default: break;
     }
   }
   std::string err;
   if ((rc = loop_check_plan(segs, plan, &err))) { set_error(err); return rc; }
   // summary of the plan (read it with dgan_last_error() after a successful call)
-  std::string sum = std::to_string(plan.n_groups) + " group(s); segments:";
-  for (int v = 0; v < plan.n_vseg; ++v)
-    sum += " [" + std::string(plan.vseg_group[(size_t)v] ? "B." : "A.") + segs[(size_t)plan.vseg_phys[(size_t)v]].name + " window " +
+  std::string sum = "segments:";
+  for (int v = 0; v < plan.n_seg; ++v)
+    sum += " [" + segs[(size_t)v].name + " window " +
            std::to_string(plan.shape[4 * v]) + "x" + std::to_string(plan.shape[4 * v + 1]) + " stride " + std::to_string(plan.shape[4 * v + 2]) + "x" +
-           std::to_string(plan.shape[4 * v + 3]) + ", " + std::to_string(plan.hdrs[(size_t)v].size()) + " windows x " +
-           std::to_string(plan.group_mps[(size_t)plan.vseg_group[(size_t)v]].size()) + " row pairs]";
-  sum += " per L-step: " + std::to_string(plan.n_steps) + " steps, " + std::to_string(plan.n_mma) + " MMAs, " +
-         std::to_string(2.0 * plan.n_bytes / 1e6) + " MB staged, " + std::to_string(plan.deps.size()) + " dependencies (all sections), " +
-         std::to_string(plan.n_flags) + " flags";
+           std::to_string(plan.shape[4 * v + 3]) + ", " + std::to_string(plan.hdrs[(size_t)v].size()) + " windows]";
+  sum += " x " + std::to_string(plan.n_mpairs) + " row pairs; per L-step: " + std::to_string(plan.n_steps) + " steps, " + std::to_string(plan.n_mma) + " MMAs, " +
+         std::to_string(2.0 * plan.n_bytes / 1e6) + " MB staged, " + std::to_string((size_t)(plan.win_fwd + plan.win_bwd) * plan.n_mpairs) + " items, " +
+         std::to_string(plan.succ.size()) + " graph edges per row pair, queue capacity " + std::to_string(plan.q_cap);
   set_error(sum);
   return 0;
 }

@@ -1,41 +1,49 @@
-// The projection loop as ONE persistent kernel (DGAN_PREC_FP16).
+// The projection loop as ONE persistent kernel (DGAN_PREC_FP16) with dataflow scheduling.
 //
 // Round 1 ran every layer-direction of an L-step as its own persistent tcgen05 kernel: 9 launches per step, 1798 per
 // call, each paying ~2 us of launch gap, ~1.5 us until its first operands landed and 2-6 us of un-overlapped last
 // epilogue - a quarter of the step.  Here the whole call - L x (generator forward, loss, backward-to-z, momentum) -
-// is one launch: 74 CTA pairs (one per TPC, all co-resident) each walk a host-planned stream of
-// (segment, window, row pair) items for one L-step and replay it L times.  A "segment" is one layer-direction
-// (Linear fwd, Generator.2 fwd, ..., Linear bwd); its items are exactly those of the per-layer kernels (same windows,
-// same step records, same canonical accumulation order, hence the same bits).  What used to be a grid-wide kernel
-// boundary is now a per-item dependency: the epilogue of an item publishes "window w of row pair mp is written" in
-// a global flag word (release), and the TMA producer of a consuming item waits (acquire) for exactly the windows
-// whose pixels it stages.  Rows are independent (no BatchNorm on this path), so dependencies never cross row pairs
-// and the tail of one layer overlaps the head of the next; the momentum update is applied by the CTA that completes
-// a row tile's last Linear-backward partial sum and releases that row pair's next L-step.
+// is one launch of 74 co-resident CTA pairs (one per TPC).
 //
-// Deadlock freedom: every CTA pair processes its items in an order consistent with (L-step, segment), an item only
-// waits for items of the previous segment (or the previous L-step's update), no role that signals ever waits on a
-// flag, and the grid is sized to the number of co-resident clusters.  The host proves it for each plan by simulating
-// the streams (loop_check_plan), and every flag wait has a time-out that raises a status word instead of hanging.
+// Work is cut into ITEMS: (segment = layer-direction, window of 1-8 output pixels, row pair of 256 latent rows, L-step).
+// The steps of an item (what to stage, which MMAs to issue) are the same host-planned records as in round 1, so every
+// accumulator still sums its contributions in one canonical order and the bits do not depend on the schedule.  What is
+// new is WHO runs an item and WHEN: items form a dataflow graph (an item needs the windows of the previous segment that
+// cover the pixels it stages - same row pair, rows are independent - and the first segment needs the row pair's momentum
+// update of the previous L-step).  A global ready queue holds the items whose inputs are complete; a CTA pair that
+// finishes issuing an item pops the next one.  When the stores of an item have completed, the warp that observes the last
+// of them bumps the arrival counter of each successor and pushes those that became ready.  Static per-CTA streams with
+// flags (the first version of this kernel, profiles/r2_loop_trace_1group.md) lost 30 % of the time to head-of-line
+// blocking: an in-order stream cannot cover the publish latency at segment and L-step boundaries, and at 10 row pairs
+// there is no static order that gives every dependency an independent separator.  With the queue, row pairs drift apart by
+// themselves and a CTA pair only idles when nothing at all is ready.
+//
+// Deadlock freedom: only ready items are ever taken, an item's completion never waits on anything but its own stores, and
+// the kernel ends through sentinels pushed when the last item has completed; the grid is sized to the co-resident
+// clusters (a CTA pair that is never scheduled would only leave items to the others).  Queue pops have a time-out that
+// raises a status word instead of hanging.
 #pragma once
 #include "kernels_tc2.cuh"
 
 namespace dgan {
 
-constexpr int LOOP_MAX_SEG = 20;      // virtual segments: (row-pair group) x (layer-direction)
-constexpr int LOOP_N_SEC = 4;         // stream sections per CTA pair (see LoopPlan)
+constexpr int LOOP_MAX_SEG = 10;
 // Warp roles, by warpgroup so that registers can be re-balanced with setmaxnreg: warpgroup 0 = TMA producer (warp 0),
-// MMA issuer (warp 1) and two idle warps, trimmed to LOOP_REGS_CTRL registers; warpgroups 1-2 = the 8 epilogue warps,
-// raised to LOOP_REGS_EPI (the epilogue holds two 32-column TMEM loads in flight while it converts a 64-column unit:
-// at the launch-time 168 registers it spilled about a kilobyte per thread).
+// MMA issuer (warp 1) and the two store warps, trimmed to LOOP_REGS_CTRL registers; warpgroups 1-2 = the 8 epilogue
+// warps, raised to LOOP_REGS_EPI (the epilogue holds two 32-column TMEM loads in flight while it converts a 64-column
+// unit: at the launch-time 168 registers it spilled about a kilobyte per thread).
 constexpr int LOOP_THREADS = 128 + 32 * TC2_EPI_WARPS;
 constexpr int LOOP_EPI_WARP0 = 4;
-constexpr int LOOP_REGS_CTRL = 64, LOOP_REGS_EPI = 216;      // 128*64 + 256*216 <= 384*168 (the launch-time pool)
+constexpr int LOOP_REGS_CTRL = 104, LOOP_REGS_EPI = 200;     // 128*104 + 256*200 = 384*168 (the launch-time pool)
 constexpr int LOOP_EPI_TILES = 2;                                              // one output staging tile per epilogue half
 constexpr int LOOP_RING_BYTES = tc2_ring_bytes(64, EPI_BIAS_RELU, 2);           // operand ring next to those tiles
-constexpr int LOOP_SMEM_BYTES = LOOP_RING_BYTES + LOOP_EPI_TILES * TC2_TILE_BYTES + TC2_STAGING_BYTES + 1024 + 256;
-constexpr uint32_t LOOP_ARRIVALS = 2 * TC2_EPI_WARPS;      // flag increments per item and L-step: 8 epilogue warps x 2 CTAs
-constexpr uint32_t LOOP_DEP_PREV = 0x80000000u;             // dependency on the PREVIOUS L-step's value of the flag (z update)
+constexpr int LOOP_BAR_BYTES = 512;                                            // mbarriers + mailbox
+constexpr int LOOP_SMEM_BYTES = LOOP_RING_BYTES + LOOP_EPI_TILES * TC2_TILE_BYTES + TC2_STAGING_BYTES + 1024 + LOOP_BAR_BYTES;
+static_assert(LOOP_SMEM_BYTES <= TC2_SMEM_MAX, "shared memory budget");
+constexpr int LOOP_MAIL = 8;                                // items a CTA pair's producer may run ahead of its slowest role
+constexpr uint32_t LOOP_SENTINEL = 0x000F0000u;             // queue entry (segment 15) that ends a CTA pair
+constexpr uint32_t LOOP_LAP_SHIFT = 20, LOOP_LAP_MASK = 0x7FFu;   // entries carry the lap of their queue index (bits 20..30 of lo)
+constexpr unsigned long long LOOP_EMPTY = ~0ull;            // queue slot not written yet (lap field 0xFFF matches no lap)
 
 // epilogue variants (N_TILE, epilogue, output type) that occur in the two generators
 enum LoopKind : int {
@@ -54,56 +62,36 @@ struct __align__(64) LoopSeg {
   const float* bias;
   unsigned long long* mb_out;
   const unsigned long long* mb_in;
-  const TcItem2* items;
+  const TcItem2* items;            // window headers
   uint32_t n_tile, kind, bias_pstride, acc_stride;
-  uint32_t idesc, half_b, phys, group;      // phys: layer-direction index (profiling); group: which row-pair group's L-step counter applies
+  uint32_t idesc, half_b;
+  uint32_t win_base;               // index of window 0 in the per-window tables (record offsets, successors, needs)
+  uint32_t item_base, n_windows;   // item (window w, row pair mp) = item_base + mp * n_windows + w in the counter arrays
 };
 
-// One entry of the launch's program: run section `sec` of every CTA pair's stream with the given L-step index per row-pair
-// group.  flags bit 0: the operand ring must be drained first (the section's ring plan assumes another predecessor).
-struct LoopProg { int32_t sec, t0, t1, flags; };
-
-// Entry `pi` of the program of a launch over `n_groups` row-pair groups (see LoopPlan for the sections):
-//   two groups:  sec0 [A.fwd(0)],  then for j = 0 .. L-2:  sec1 [A.bwd(j) | B.fwd(j)],  sec2 [A.fwd(j+1) | B.bwd(j)],  then sec3 [B.fwd(L-1)]
-//   one group:   sec2 [fwd(0)],    then for j = 0 .. L-2:  sec1 [bwd(j)],  sec2 [fwd(j+1)]      (+ sec1 [bwd(L-1)] for dgan_loss_grad)
-__host__ __device__ inline LoopProg loop_prog_entry(int n_groups, int n_prog, int pi) {
-  LoopProg e;
-  if (n_groups == 2) {
-    if (pi == 0) { e.sec = 0; e.t0 = 0; e.t1 = -1; e.flags = 0; return e; }
-    if (pi == n_prog - 1) { e.sec = 3; e.t0 = -1; e.t1 = (n_prog - 2) / 2; e.flags = 1; return e; }
-    const int j = (pi - 1) >> 1;
-    if (pi & 1) { e.sec = 1; e.t0 = j; e.t1 = j; e.flags = (j == 0) ? 1 : 0; }
-    else { e.sec = 2; e.t0 = j + 1; e.t1 = j; e.flags = 0; }
-    return e;
-  }
-  if (pi == 0) { e.sec = 2; e.t0 = e.t1 = 0; e.flags = 0; return e; }
-  const int j = (pi - 1) >> 1;
-  e.sec = (pi & 1) ? 1 : 2;
-  e.t0 = e.t1 = (pi & 1) ? j : j + 1;
-  e.flags = 0;
-  return e;
-}
-inline int loop_prog_length(int n_groups, int rec_iters, bool full_last) {
-  return n_groups == 2 ? 2 * rec_iters : 2 * rec_iters - 1 + (full_last ? 1 : 0);
-}
-
 struct LoopParams {
-  LoopSeg seg[LOOP_MAX_SEG];       // virtual segments
-  const TcRec* stream_p[2];        // producer records per cluster rank: per CTA pair its LOOP_N_SEC sections, back to back
-  const TcRec* stream_m;           // MMA records, same indexing
-  const uint32_t* stream_off;      // [n_pairs][LOOP_N_SEC + 1] record offsets
-  const uint4* eitems;             // items in stream order, all pairs: x = vseg << 16 | window, y = row pair, z = flag index
-  const uint32_t* eitem_off;       // [n_pairs][LOOP_N_SEC + 1] item offsets
-  const uint32_t* dep_off;         // [items + 1] -> deps
-  const uint32_t* deps;            // flag indices (| LOOP_DEP_PREV)
-  uint32_t* flags;                 // zeroed per call
-  uint32_t* status;                // [0] != 0: a flag wait timed out (results invalid)
-  unsigned long long* prof;        // optional [t][n_vseg][2] globaltimer min-start / max-end
+  LoopSeg seg[LOOP_MAX_SEG];
+  const TcRec* tmpl_p[2];          // producer step records per cluster rank: per (segment, window), windows back to back
+  const TcRec* tmpl_m;             // MMA step records, same indexing
+  const uint32_t* win_rec_off;     // [windows + 1] record offsets
+  const uint32_t* succ_off;        // [windows + 1] -> succ
+  const uint32_t* succ;            // successors of a window: (segment << 16 | window) in the consuming segment, same row pair
+  const uint32_t* need;            // [windows] completions of producing items a window waits for, per L-step
+  unsigned long long* queue;       // ready queue: lo = lap << 20 | segment << 16 | window, hi = row pair | L-step << 16
+  uint32_t* q_ctl;                 // [0] popped, [1] pushed, [2] completed items
+  uint32_t* arrive;                // per item: completions of its epilogue parts (4 store warps or 16 epilogue warps per execution)
+  uint32_t* depcnt;                // per item: completions of the items it waits for
+  uint32_t* status;                // [0] != 0: a queue pop timed out (results invalid)
+  unsigned long long* prof;        // optional [L-step][n_seg][2] globaltimer min-start / max-end of the epilogues
   unsigned long long* dbg;         // optional [CTA][16] stall counters of the roles (clock64 ticks), see LoopDbg
-  unsigned long long* trace;       // optional [items of the traced program entry][4] globaltimer: dependency wait begin / end, epilogue begin / end
-  int trace_entry;                 // the program entries trace_entry and trace_entry + 1 are traced
-  int n_prog, n_groups, n_vseg;    // program length (loop_prog_entry), row-pair groups, virtual segments
+  unsigned long long* trace;       // optional [item slot][4]: pop time | CTA pair << 48, accumulator granted, epilogue begin, epilogue end (L-step trace_step)
+  uint32_t q_cap, q_shift, n_pairs; // queue capacity = 1 << q_shift
+  uint32_t q_init;                 // entries the host placed in the queue (the first segment's items of L-step 0): pushes start behind them
+  int trace_step;
+  uint32_t n_items_total;          // items of the whole launch: the completion of the last one pushes the sentinels
+  int n_seg, n_fwd;                // segments; the first n_fwd are the generator forward (+ loss)
   int last_step;                   // index of the call's final L-step (rec_iters - 1): its forward writes G(z) and the loss
+  int full_last;                   // 1: the final L-step also runs its backward half (dgan_loss_grad); 0: forward only
   int n_pad, n_mpairs;
   // last layer / loss (models/gan.py:411-414)
   const float* x; float* y; float* loss_part;
@@ -115,17 +103,21 @@ struct LoopParams {
   unsigned* m_counter;             // [n_pad / 128] tickets; NULL = leave the partial sums (dgan_loss_grad)
   int m_nparts, decay_step;        // decay_step > 0: lr x0.1 from that L-step on (opt-in)
   size_t m_count;
-  uint32_t zflag_base;
 };
 
 namespace ptx {
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -135,34 +127,82 @@ __device__ __forceinline__ unsigned long long globaltimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t local_addr, uint32_t cta, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.b32 [ra], %2;\n\t}" ::"r"(local_addr), "r"(cta), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t local_bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope (peer's writes)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAITC_DONE;\n\t"
+      "bra WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
 }  // namespace ptx
 
-// Spin until *flag >= target (acquire).  A wait that lasts seconds means a broken plan or a faulted peer: raise the
-// status word and fall through (every later wait then falls through as well) instead of hanging the GPU.
-__device__ __forceinline__ void loop_wait_flag(const uint32_t* flag, uint32_t target, uint32_t* status) {
-  if (ptx::ld_acquire_gpu(flag) >= target) return;
-  const unsigned long long t0 = ptx::globaltimer();
-  uint32_t spins = 0;
-  while (ptx::ld_acquire_gpu(flag) < target) {
-    if ((++spins & 255u) == 0u) {
-      if (*reinterpret_cast<volatile uint32_t*>(status) != 0u) return;
-      if (ptx::globaltimer() - t0 > 4000000000ull) { atomicExch(status, 1u); return; }
-    }
-  }
-}
-
-// "this thread's global writes of the item are done": order them before the flag increment, for readers in both proxies
+// "this thread's global writes of the item are done": order them before the completion counters, for readers in both proxies
 __device__ __forceinline__ void loop_publish_fence() {
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
   ptx::fence_proxy_async_all();
 }
 
 // per-CTA stall counters written when LoopParams::dbg != NULL (developer aid: tools/loop_stalls.py)
-enum LoopDbg : int { DBG_P_FLAG = 0, DBG_P_RING, DBG_P_TOTAL, DBG_M_FULL, DBG_M_ACC, DBG_M_TOTAL, DBG_E_ACC, DBG_E_TILE, DBG_E_TOTAL,
-                     DBG_S_TILE, DBG_S_DONE, DBG_S_TOTAL, DBG_P_SLOW, DBG_COUNT = 16 };
+enum LoopDbg : int { DBG_P_POP = 0, DBG_P_RING, DBG_P_TOTAL, DBG_M_FULL, DBG_M_ACC, DBG_M_TOTAL, DBG_E_ACC, DBG_E_TILE, DBG_E_TOTAL,
+                     DBG_S_TILE, DBG_S_DONE, DBG_S_TOTAL, DBG_P_ITEMS, DBG_M_MAIL, DBG_COUNT = 16 };
+
+// shared-memory control block of a CTA (offsets from bar_base)
+constexpr uint32_t LB_FULL = 0, LB_EMPTY = 64, LB_ACC_FULL = 128, LB_ACC_EMPTY = 144, LB_TMEM = 160, LB_TILE_FULL = 168,
+                   LB_TILE_FREE = 184, LB_MOM = 200, LB_MAIL_FULL = 256, LB_MAIL_EMPTY = 320, LB_MAIL_DATA = 384;
+
+struct LoopItem { uint32_t seg, win, mp, t; };
+__device__ __forceinline__ LoopItem loop_unpack(uint32_t lo, uint32_t hi) {
+  LoopItem it;
+  it.seg = (lo >> 16) & 0xFu; it.win = lo & 0xFFFFu; it.mp = hi & 0xFFFFu; it.t = hi >> 16;
+  return it;
+}
+
+// Append a ready item to the queue.
+__device__ __forceinline__ void loop_push(const LoopParams& P, uint32_t lo, uint32_t hi) {
+  const uint32_t idx = atomicAdd(P.q_ctl + 1, 1u) + P.q_init;
+  const uint32_t lap = (idx >> P.q_shift) & LOOP_LAP_MASK;
+  ptx::st_release_gpu_u64(P.queue + (idx & (P.q_cap - 1u)), ((unsigned long long)hi << 32) | lo | (lap << LOOP_LAP_SHIFT));
+}
+
+// The item (seg, win, mp) of L-step t has completed (all its stores are in global memory): count it and wake what it
+// unblocks.  Called by a converged warp; the successor list is processed one successor per lane.
+__device__ __forceinline__ void loop_complete(const LoopParams& P, const LoopSeg& sg, uint32_t seg, uint32_t win, uint32_t mp, uint32_t t, int lane) {
+  const uint32_t wi = sg.win_base + win;
+  const uint32_t s0 = __ldg(P.succ_off + wi), s1 = __ldg(P.succ_off + wi + 1);
+  // the backward half of the final L-step is never run: the loop returns the pre-update forward (models/gan.py:419-421)
+  const bool stop = ((int)seg == P.n_fwd - 1) && ((int)t == P.last_step) && !P.full_last;
+  if (!stop)
+    for (uint32_t s = s0 + (uint32_t)lane; s < s1; s += 32) {
+      const uint32_t e = __ldg(P.succ + s);
+      const LoopSeg& sn = P.seg[e >> 16];
+      const uint32_t w2 = e & 0xFFFFu;
+      const uint32_t c = ptx::atom_add_acq_rel_gpu(P.depcnt + sn.item_base + mp * sn.n_windows + w2, 1u) + 1u;
+      if (c == __ldg(P.need + sn.win_base + w2) * (t + 1u)) loop_push(P, e, mp | (t << 16));
+    }
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t d = atomicAdd(P.q_ctl + 2, 1u) + 1u;
+    if (d == P.n_items_total)
+      for (uint32_t k = 0; k < P.n_pairs; ++k) loop_push(P, LOOP_SENTINEL, 0u);
+  }
+}
 
 struct LoopCtx {                     // per-thread view of the CTA's pipeline state handed to the epilogue variants
-  uint32_t tmem_base, bar_acc_full, bar_acc_empty, epi_base, bar_base;
+  uint32_t tmem_base, bar_base, epi_base;
   int warp, lane, rank;
   uint32_t item_count, tile_count;
   long long t_acc, t_tile;          // stall ticks (debug)
@@ -200,11 +240,12 @@ __device__ __forceinline__ void loop_convert_half(const uint32_t (&r)[32], const
 
 // ------------------------------------------------------------------------------------------
 // One item's epilogue.  Same arithmetic as the per-layer kernels of round 1 (the code below is that epilogue,
-// parameterised at run time by the segment); ends by releasing the accumulator buffer and publishing the item.
+// parameterised at run time by the segment); ends by releasing the accumulator buffer and reporting completion.
 // ------------------------------------------------------------------------------------------
 template <int N_TILE, int EPI, typename TOUT>
 __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const LoopSeg& sg, LoopCtx& cx, const TcFinalArgs& fa,
-                                                   int win, int mp, uint32_t* flag) {
+                                                   const LoopItem it) {
+  const int win = (int)it.win, mp = (int)it.mp;
   constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, (int)sizeof(TOUT));
   constexpr int ACC_STRIDE = tc2_acc_stride(N_TILE);
   constexpr bool FINAL = (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3);
@@ -227,7 +268,7 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
     tc_final_targets<(EPI == EPI_FINAL_SIGMOID1 ? 1 : 3)>(reinterpret_cast<float4(&)[EPI == EPI_FINAL_SIGMOID1 ? 4 : 12]>(xq_next), fa, ip->q[half], (int)n);
   {
     const long long tw0 = P.dbg ? clock64() : 0;
-    ptx::mbar_wait(cx.bar_acc_full + 8 * buf, (cx.item_count >> 1) & 1);
+    ptx::mbar_wait(cx.bar_base + LB_ACC_FULL + 8 * buf, (cx.item_count >> 1) & 1);
     if (P.dbg) cx.t_acc += clock64() - tw0;
   }
   ptx::tc_fence_after();
@@ -249,12 +290,12 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
   } else if (TMA_EPI) {
     // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 ->
     //      128B-swizzled smem tile -> one TMA store per 128x64 tile.
-    constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
+    constexpr int G = N_TILE >= 64 ? N_TILE / 64 : 1;   // 64-column groups per accumulator
     const int n_units = n_acc * G;
     // The staging tile of this epilogue half is handed to the half's STORE WARP (warp 2 + half): it issues the TMA store,
-    // frees the tile when the store has read it, and publishes the item when the item's stores have completed - so no
-    // thread that does arithmetic ever waits for global-memory latency.
-    const uint32_t tile_full = cx.bar_base + 168 + 8 * (uint32_t)half, tile_free = cx.bar_base + 184 + 8 * (uint32_t)half;
+    // frees the tile when the store has read it, and reports the item's completion when its stores have completed - so
+    // no thread that does arithmetic ever waits for global-memory latency.
+    const uint32_t tile_full = cx.bar_base + LB_TILE_FULL + 8 * (uint32_t)half, tile_free = cx.bar_base + LB_TILE_FREE + 8 * (uint32_t)half;
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t s_out = cx.epi_base + (uint32_t)half * TC2_TILE_BYTES;
     uint32_t r0[32], r1[32];
@@ -312,98 +353,136 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
   // ---- hand the accumulator buffer back to the MMA warp
   ptx::tc_fence_before();
   __syncwarp();
-  if (lane == 0) ptx::mbar_arrive_remote(cx.bar_acc_empty + 8 * buf, 0);
+  if (lane == 0) ptx::mbar_arrive_remote(cx.bar_base + LB_ACC_EMPTY + 8 * buf, 0);
 
-  // ---- publish the item
+  // ---- completion
   if (TMA_EPI) {
-    // published by the half's store warp once the item's tile stores have completed
-  } else if (EPI == EPI_NONE && sizeof(TOUT) == 4 && P.m_counter != nullptr) {
-    // ---- momentum in the tail of the split-K Linear backward (tf.train.MomentumOptimizer, models/gan.py:389-391).
-    //      Every epilogue thread has stored its share of this item's partial sums; the CTA that completes the last
-    //      partial of its 128-row tile applies v <- mu v + g, z <- z - lr v (parts summed in the fixed order 0, 1, 2, ...)
-    //      and releases the row pair's next L-step.
-    const uint32_t flag_addr = cx.bar_base + 200;
-    const unsigned rt = 2u * (unsigned)mp + (unsigned)rank;
-    __threadfence();
-    ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
-    if (warp == LOOP_EPI_WARP0 && lane == 0) {
-      const unsigned ticket = atomicAdd(P.m_counter + rt, 1u);
-      ptx::st_shared_u32(flag_addr, ticket == (unsigned)P.m_nparts - 1u ? 1u : 0u);
-    }
-    ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
-    if (ptx::ld_shared_u32(flag_addr) != 0u) {
+    // reported by the half's store warp once the item's tile stores have completed
+  } else {
+    uint32_t* arrive = P.arrive + sg.item_base + (uint32_t)mp * sg.n_windows + (uint32_t)win;
+    if (EPI == EPI_NONE && sizeof(TOUT) == 4 && P.m_counter != nullptr) {
+      // ---- momentum in the tail of the split-K Linear backward (tf.train.MomentumOptimizer, models/gan.py:389-391).
+      //      Every epilogue thread has stored its share of this item's partial sums; the CTA that completes the last
+      //      partial of its 128-row tile applies v <- mu v + g, z <- z - lr v (parts summed in the fixed order 0, 1, 2, ...)
+      //      and releases the row pair's next L-step.
+      const uint32_t flag_addr = cx.bar_base + LB_MOM;
+      const unsigned rt = 2u * (unsigned)mp + (unsigned)rank;
       __threadfence();
-      const float* __restrict__ gp = reinterpret_cast<const float*>(out);
-      const size_t base = (size_t)rt * kRowTile * N_TILE;
-      const int tid = (warp - LOOP_EPI_WARP0) * 32 + lane;
-      // latency-bound (every operand is an L2 read): all partial sums, v and z of UNR positions are requested before any
-      // is used - one round trip per iteration instead of one per partial sum
-      constexpr int STRIDE = 4 * 32 * TC2_EPI_WARPS, UNR = 4, MAXP = TC_LINEAR_SPLIT;
-      for (int e0 = tid * 4; e0 < kRowTile * N_TILE; e0 += UNR * STRIDE) {
-        float4 gs[MAXP][UNR], vv[UNR], zz[UNR];
-#pragma unroll
-        for (int pp = 0; pp < MAXP; ++pp)
-#pragma unroll
-          for (int k = 0; k < UNR; ++k)
-            gs[pp][k] = (pp < P.m_nparts) ? __ldcg(reinterpret_cast<const float4*>(gp + base + (size_t)(e0 + k * STRIDE) + (size_t)pp * P.m_count))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) {
-          const size_t i = base + (size_t)(e0 + k * STRIDE);
-          vv[k] = __ldcg(reinterpret_cast<const float4*>(P.mv + i));
-          zz[k] = __ldcg(reinterpret_cast<const float4*>(P.mz + i));
-        }
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) {
-          const size_t i = base + (size_t)(e0 + k * STRIDE);
-          float4 g4 = gs[0][k];
-#pragma unroll
-          for (int pp = 1; pp < MAXP; ++pp)          // fixed order: parts 0, 1, 2, ... (absent parts add +0)
-            if (pp < P.m_nparts) { g4.x += gs[pp][k].x; g4.y += gs[pp][k].y; g4.z += gs[pp][k].z; g4.w += gs[pp][k].w; }
-          float4 v4 = vv[k], z4 = zz[k];
-          v4.x = fmaf(fa.m_mu, v4.x, fa.m_gmul * g4.x); v4.y = fmaf(fa.m_mu, v4.y, fa.m_gmul * g4.y);
-          v4.z = fmaf(fa.m_mu, v4.z, fa.m_gmul * g4.z); v4.w = fmaf(fa.m_mu, v4.w, fa.m_gmul * g4.w);
-          z4.x -= fa.m_lr * v4.x; z4.y -= fa.m_lr * v4.y; z4.z -= fa.m_lr * v4.z; z4.w -= fa.m_lr * v4.w;
-          *reinterpret_cast<float4*>(P.mv + i) = v4;
-          *reinterpret_cast<float4*>(P.mz + i) = z4;
-          *reinterpret_cast<uint2*>(P.mz_h + i) = make_uint2(pack_half2(z4.x, z4.y), pack_half2(z4.z, z4.w));
-        }
-      }
-      loop_publish_fence();
       ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
       if (warp == LOOP_EPI_WARP0 && lane == 0) {
-        P.m_counter[rt] = 0u;                            // ready for the next L-step's tickets
+        const unsigned ticket = atomicAdd(P.m_counter + rt, 1u);
+        ptx::st_shared_u32(flag_addr, ticket == (unsigned)P.m_nparts - 1u ? 1u : 0u);
+      }
+      ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
+      if (ptx::ld_shared_u32(flag_addr) != 0u) {
         __threadfence();
-        ptx::red_release_gpu_add(P.flags + P.zflag_base + mp, LOOP_ARRIVALS / 2);   // this 128-row tile's half of z[mp]
+        const float* __restrict__ gp = reinterpret_cast<const float*>(out);
+        const size_t base = (size_t)rt * kRowTile * N_TILE;
+        const int tid = (warp - LOOP_EPI_WARP0) * 32 + lane;
+        // latency-bound (every operand is an L2 read): all partial sums, v and z of UNR positions are requested before any
+        // is used - one round trip per iteration instead of one per partial sum
+        constexpr int STRIDE = 4 * 32 * TC2_EPI_WARPS, UNR = 2, MAXP = TC_LINEAR_SPLIT;
+        for (int e0 = tid * 4; e0 < kRowTile * N_TILE; e0 += UNR * STRIDE) {
+          float4 gs[MAXP][UNR], vv[UNR], zz[UNR];
+#pragma unroll
+          for (int pp = 0; pp < MAXP; ++pp)
+#pragma unroll
+            for (int k = 0; k < UNR; ++k)
+              gs[pp][k] = (pp < P.m_nparts) ? __ldcg(reinterpret_cast<const float4*>(gp + base + (size_t)(e0 + k * STRIDE) + (size_t)pp * P.m_count))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < UNR; ++k) {
+            const size_t i = base + (size_t)(e0 + k * STRIDE);
+            vv[k] = __ldcg(reinterpret_cast<const float4*>(P.mv + i));
+            zz[k] = __ldcg(reinterpret_cast<const float4*>(P.mz + i));
+          }
+#pragma unroll
+          for (int k = 0; k < UNR; ++k) {
+            const size_t i = base + (size_t)(e0 + k * STRIDE);
+            float4 g4 = gs[0][k];
+#pragma unroll
+            for (int pp = 1; pp < MAXP; ++pp)          // fixed order: parts 0, 1, 2, ... (absent parts add +0)
+              if (pp < P.m_nparts) { g4.x += gs[pp][k].x; g4.y += gs[pp][k].y; g4.z += gs[pp][k].z; g4.w += gs[pp][k].w; }
+            float4 v4 = vv[k], z4 = zz[k];
+            v4.x = fmaf(fa.m_mu, v4.x, fa.m_gmul * g4.x); v4.y = fmaf(fa.m_mu, v4.y, fa.m_gmul * g4.y);
+            v4.z = fmaf(fa.m_mu, v4.z, fa.m_gmul * g4.z); v4.w = fmaf(fa.m_mu, v4.w, fa.m_gmul * g4.w);
+            z4.x -= fa.m_lr * v4.x; z4.y -= fa.m_lr * v4.y; z4.z -= fa.m_lr * v4.z; z4.w -= fa.m_lr * v4.w;
+            *reinterpret_cast<float4*>(P.mv + i) = v4;
+            *reinterpret_cast<float4*>(P.mz + i) = z4;
+            *reinterpret_cast<uint2*>(P.mz_h + i) = make_uint2(pack_half2(z4.x, z4.y), pack_half2(z4.z, z4.w));
+          }
+        }
+        loop_publish_fence();
+        ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
+        if (warp == LOOP_EPI_WARP0) {
+          if (lane == 0) P.m_counter[rt] = 0u;                 // ready for the next L-step's tickets
+          // z of this 128-row tile is updated: the row pair's next Linear forward waits for both tiles
+          if ((int)it.t < P.last_step) {
+            const LoopSeg& s0g = P.seg[0];
+            for (uint32_t w2 = (uint32_t)lane; w2 < s0g.n_windows; w2 += 32) {
+              const uint32_t c = ptx::atom_add_acq_rel_gpu(P.depcnt + s0g.item_base + (uint32_t)mp * s0g.n_windows + w2, 1u) + 1u;
+              if (c == __ldg(P.need + s0g.win_base + w2) * (it.t + 1u)) loop_push(P, w2, (uint32_t)mp | ((it.t + 1u) << 16));
+            }
+          }
+        }
       }
     }
-    // (nothing waits on the partial sums themselves except through the ticket)
-  } else {
+    // every epilogue warp of both CTAs reports its share of the item; the last one wakes the successors
     loop_publish_fence();
     __syncwarp();
-    if (lane == 0) ptx::red_release_gpu_add(flag, 1u);
+    uint32_t old = 0;
+    if (lane == 0) old = ptx::atom_add_acq_rel_gpu(arrive, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old + 1u == (2u * TC2_EPI_WARPS) * (it.t + 1u)) loop_complete(P, sg, it.seg, it.win, it.mp, it.t, lane);
   }
 }
 
 template <int ARCH>
 __device__ __forceinline__ void loop_epilogue_dispatch(const LoopParams& P, const LoopSeg& sg, LoopCtx& cx, const TcFinalArgs& fa,
-                                                       int win, int mp, uint32_t* flag) {
+                                                       const LoopItem it) {
   switch (sg.kind) {
-    case LK_BR256: loop_epilogue_item<256, EPI_BIAS_RELU, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_BR128: loop_epilogue_item<128, EPI_BIAS_RELU, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_BR64: loop_epilogue_item<64, EPI_BIAS_RELU, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_MASK64: loop_epilogue_item<64, EPI_MASK, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_MASK128: loop_epilogue_item<128, EPI_MASK, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_MASK256: loop_epilogue_item<256, EPI_MASK, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_NONE64F: loop_epilogue_item<64, EPI_NONE, float>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_NONE128F: loop_epilogue_item<128, EPI_NONE, float>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_NONE256F: loop_epilogue_item<256, EPI_NONE, float>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_B64: if (ARCH == DGAN_ARCH_CELEBA) loop_epilogue_item<64, EPI_BIAS, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_NONE64H: if (ARCH == DGAN_ARCH_CELEBA) loop_epilogue_item<64, EPI_NONE, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_FINAL48: if (ARCH == DGAN_ARCH_CELEBA) loop_epilogue_item<48, EPI_FINAL_TANH3, __half>(P, sg, cx, fa, win, mp, flag); break;
-    case LK_FINAL16: if (ARCH == DGAN_ARCH_MNIST) loop_epilogue_item<16, EPI_FINAL_SIGMOID1, __half>(P, sg, cx, fa, win, mp, flag); break;
+    case LK_BR256: loop_epilogue_item<256, EPI_BIAS_RELU, __half>(P, sg, cx, fa, it); break;
+    case LK_BR128: loop_epilogue_item<128, EPI_BIAS_RELU, __half>(P, sg, cx, fa, it); break;
+    case LK_BR64: loop_epilogue_item<64, EPI_BIAS_RELU, __half>(P, sg, cx, fa, it); break;
+    case LK_MASK64: loop_epilogue_item<64, EPI_MASK, __half>(P, sg, cx, fa, it); break;
+    case LK_MASK128: loop_epilogue_item<128, EPI_MASK, __half>(P, sg, cx, fa, it); break;
+    case LK_MASK256: loop_epilogue_item<256, EPI_MASK, __half>(P, sg, cx, fa, it); break;
+    case LK_NONE64F: loop_epilogue_item<64, EPI_NONE, float>(P, sg, cx, fa, it); break;
+    case LK_NONE128F: loop_epilogue_item<128, EPI_NONE, float>(P, sg, cx, fa, it); break;
+    case LK_NONE256F: loop_epilogue_item<256, EPI_NONE, float>(P, sg, cx, fa, it); break;
+    case LK_B64: if (ARCH == DGAN_ARCH_CELEBA) loop_epilogue_item<64, EPI_BIAS, __half>(P, sg, cx, fa, it); break;
+    case LK_NONE64H: if (ARCH == DGAN_ARCH_CELEBA) loop_epilogue_item<64, EPI_NONE, __half>(P, sg, cx, fa, it); break;
+    case LK_FINAL48: if (ARCH == DGAN_ARCH_CELEBA) loop_epilogue_item<48, EPI_FINAL_TANH3, __half>(P, sg, cx, fa, it); break;
+    case LK_FINAL16: if (ARCH == DGAN_ARCH_MNIST) loop_epilogue_item<16, EPI_FINAL_SIGMOID1, __half>(P, sg, cx, fa, it); break;
     default: break;
   }
+}
+
+// The circular operand ring, allocated at run time: steps take consecutive regions (wrapping when one does not fit); a
+// region may be overwritten once the latest earlier step that overlaps it has been consumed.  Producer warps of both CTAs
+// and the MMA warp run this same function on the same step sequence, so they agree on every offset.  Lanes 0..7 hold the
+// regions of the last 8 steps (barrier slots).  Returns the step's offset in KB; `dep` = distance to the step to wait for
+// (8 = only the barrier slot's previous user).
+struct LoopRing {
+  uint32_t cursor = 0, beg_l = 0, end_l = 0;     // beg_l / end_l: this lane's slot (lanes 0..7)
+};
+__device__ __forceinline__ uint32_t loop_ring_alloc(LoopRing& r, uint32_t it, uint32_t kb, int lane, uint32_t* dep) {
+  constexpr uint32_t RING_KB = LOOP_RING_BYTES / 1024;
+  if (r.cursor + kb > RING_KB) r.cursor = 0;
+  const uint32_t beg = r.cursor, end = beg + kb;
+  r.cursor = end;
+  const uint32_t slot = it & (TC2_NSLOT - 1);
+  // slot j holds step it - ((slot - j) & 7) (j != slot) - valid if that step exists
+  const uint32_t dist = (slot - (uint32_t)lane) & (TC2_NSLOT - 1);
+  const bool overlap = lane < TC2_NSLOT && dist != 0 && dist <= it && r.beg_l < end && beg < r.end_l;
+  const uint32_t mask = __ballot_sync(0xffffffffu, overlap);
+  uint32_t d = TC2_NSLOT;
+#pragma unroll
+  for (uint32_t k = TC2_NSLOT - 1; k >= 1; --k)
+    if ((mask >> ((slot - k) & (TC2_NSLOT - 1))) & 1u) d = k;
+  *dep = d;
+  if ((uint32_t)lane == slot) { r.beg_l = beg; r.end_l = end; }
+  return beg;
 }
 
 template <int ARCH>
@@ -413,17 +492,15 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + LOOP_RING_BYTES;                       // two output staging tiles
   const uint32_t stg_base = epi_base + LOOP_EPI_TILES * TC2_TILE_BYTES;        // [producer ring][MMA ring] of TcRec
-  const uint32_t bar_base = stg_base + TC2_STAGING_BYTES;
-  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160,
-  // tile_full[2] @ +168, tile_free[2] @ +184 (epilogue half <-> store warp), momentum-tail flag @ +200
-  const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
-  const uint32_t tmem_slot = bar_base + 160;
+  const uint32_t bar_base = stg_base + TC2_STAGING_BYTES;                      // control block, LB_* offsets
+  const uint32_t bar_full = bar_base + LB_FULL, bar_empty = bar_base + LB_EMPTY;
+  const uint32_t bar_acc_full = bar_base + LB_ACC_FULL, bar_acc_empty = bar_base + LB_ACC_EMPTY;
+  const uint32_t tmem_slot = bar_base + LB_TMEM;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC2_NSLOT; ++s) {
@@ -433,8 +510,14 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_acc_full + 8 * b, 1);
       ptx::mbar_init(bar_acc_empty + 8 * b, 2 * TC2_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
-      ptx::mbar_init(bar_base + 168 + 8 * b, 128);                // tile_full[half]: the 4 warps of an epilogue half
-      ptx::mbar_init(bar_base + 184 + 8 * b, 1);                  // tile_free[half]: the half's store warp
+      ptx::mbar_init(bar_base + LB_TILE_FULL + 8 * b, 128);       // the 4 warps of an epilogue half
+      ptx::mbar_init(bar_base + LB_TILE_FREE + 8 * b, 1);         // the half's store warp
+    }
+    for (int m = 0; m < LOOP_MAIL; ++m) {
+      ptx::mbar_init(bar_base + LB_MAIL_FULL + 8 * m, 1);         // the leader's producer, once per item (in both CTAs)
+      // readers of a mailbox slot, both CTAs (used on the leader only): MMA warp + 2 store warps + 8 epilogue warps of the
+      // leader, producer warp + 2 store warps + 8 epilogue warps of the peer
+      ptx::mbar_init(bar_base + LB_MAIL_EMPTY + 8 * m, 2 * (3 + TC2_EPI_WARPS));
     }
     ptx::fence_barrier_init();
   }
@@ -447,41 +530,88 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const uint32_t* __restrict__ soff = P.stream_off + (size_t)pair * (LOOP_N_SEC + 1);
-  const uint32_t* __restrict__ eoff = P.eitem_off + (size_t)pair * (LOOP_N_SEC + 1);
+  // Every role of both CTAs learns the pair's k-th item from mailbox slot k % LOOP_MAIL (written by the leader's producer).
+  auto mail_read = [&](uint32_t k, bool cluster_acquire) -> LoopItem {
+    const uint32_t m = k & (LOOP_MAIL - 1), par = (k / LOOP_MAIL) & 1;
+    if (cluster_acquire) ptx::mbar_wait_cluster(bar_base + LB_MAIL_FULL + 8 * m, par);
+    else ptx::mbar_wait(bar_base + LB_MAIL_FULL + 8 * m, par);
+    const uint32_t lo = ptx::ld_shared_u32(bar_base + LB_MAIL_DATA + 8 * m), hi = ptx::ld_shared_u32(bar_base + LB_MAIL_DATA + 8 * m + 4);
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive_remote(bar_base + LB_MAIL_EMPTY + 8 * m, 0);      // this warp is done with the slot
+    LoopItem it = loop_unpack(lo, hi);
+    if ((lo & 0xF0000u) == LOOP_SENTINEL) it.seg = 0xFFFFu;
+    return it;
+  };
 
   if (warp < LOOP_EPI_WARP0) {
    ptx::setmaxnreg_dec<LOOP_REGS_CTRL>();
    if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    const TcRec* __restrict__ stream = rank ? P.stream_p[1] : P.stream_p[0];
+    const TcRec* __restrict__ stream = rank ? P.tmpl_p[1] : P.tmpl_p[0];
     const uint32_t ring = stg_base;
-    uint32_t it = 0;                                      // steps issued so far, over all replays (barrier slot / phase)
-    long long t_flag = 0, t_ring = 0, n_slow = 0;
+    uint32_t it = 0;                                      // steps issued so far (barrier slot / phase)
+    LoopRing rs;
+    long long t_pop = 0, t_ring = 0, n_items = 0;
     const long long t_p0 = P.dbg ? clock64() : 0;
-    for (int pi = 0; pi < P.n_prog; ++pi) {
-      const LoopProg pe = loop_prog_entry(P.n_groups, P.n_prog, pi);
-      const uint32_t rbeg = __ldg(soff + pe.sec), rend = __ldg(soff + pe.sec + 1);
-      if (rbeg >= rend) continue;
-      if (pe.flags & 1) {
-        // the section's ring plan assumes an empty ring: wait until every step issued so far has been consumed
-        for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
+    for (uint32_t k = 0;; ++k) {
+      LoopItem cur;
+      if (leader) {
+        // ---- take the next ready item and tell everybody (both CTAs)
+        const uint32_t m = k & (LOOP_MAIL - 1);
+        const long long tw0 = P.dbg ? clock64() : 0;
+        if (k >= LOOP_MAIL) ptx::mbar_wait_cluster(bar_base + LB_MAIL_EMPTY + 8 * m, ((k / LOOP_MAIL) - 1) & 1);   // slot read by all 22 warps
+        uint32_t lo = 0, hi = 0;
+        if (lane == 0) {
+          const uint32_t idx = atomicAdd(P.q_ctl, 1u);
+          const unsigned long long* slot_p = P.queue + (idx & (P.q_cap - 1u));
+          const uint32_t lap = (idx >> P.q_shift) & LOOP_LAP_MASK;
+          unsigned long long e = ptx::ld_acquire_gpu_u64(slot_p);
+          if ((((uint32_t)e >> LOOP_LAP_SHIFT) & 0xFFFu) != lap) {
+            const unsigned long long t0 = ptx::globaltimer();
+            uint32_t spins = 0;
+            while (e = ptx::ld_acquire_gpu_u64(slot_p), (((uint32_t)e >> LOOP_LAP_SHIFT) & 0xFFFu) != lap) {
+              if ((++spins & 255u) == 0u) {
+                // nothing became ready for seconds: a broken plan or a faulted peer - give up instead of hanging the GPU
+                if (*reinterpret_cast<volatile uint32_t*>(P.status) != 0u || ptx::globaltimer() - t0 > 4000000000ull) {
+                  atomicExch(P.status, 1u);
+                  e = LOOP_SENTINEL;
+                  break;
+                }
+              }
+            }
+          }
+          e &= ~((unsigned long long)0xFFFu << LOOP_LAP_SHIFT);
+          lo = (uint32_t)e; hi = (uint32_t)(e >> 32);
+        }
+        lo = __shfl_sync(0xffffffffu, lo, 0); hi = __shfl_sync(0xffffffffu, hi, 0);
+        if (P.dbg) t_pop += clock64() - tw0;
+        if (lane == 0) {
+          ptx::st_shared_u32(bar_base + LB_MAIL_DATA + 8 * m, lo); ptx::st_shared_u32(bar_base + LB_MAIL_DATA + 8 * m + 4, hi);
+          ptx::st_shared_cluster_u32(bar_base + LB_MAIL_DATA + 8 * m, 1, lo); ptx::st_shared_cluster_u32(bar_base + LB_MAIL_DATA + 8 * m + 4, 1, hi);
+          ptx::mbar_arrive_remote_release(bar_base + LB_MAIL_FULL + 8 * m, 0);
+          ptx::mbar_arrive_remote_release(bar_base + LB_MAIL_FULL + 8 * m, 1);
+        }
+        __syncwarp();
+        cur = loop_unpack(lo, hi);
+        if ((lo & 0xF0000u) == LOOP_SENTINEL) break;
+        if (P.trace != nullptr && (int)cur.t == P.trace_step && lane == 0)
+          P.trace[(size_t)(P.seg[cur.seg].item_base + cur.mp * P.seg[cur.seg].n_windows + cur.win) * 4] =
+              (ptx::globaltimer() & 0xFFFFFFFFFFFFull) | ((unsigned long long)(blockIdx.x >> 1) << 48);
+        ptx::fence_proxy_async_all();                   // acquired generic-proxy view -> the TMA (async proxy) reads below
+      } else {
+        cur = mail_read(k, true);
+        if (cur.seg == 0xFFFFu) break;
+        ptx::fence_proxy_async_all();
       }
-      // dependencies of the section's first item; later items are described one item ahead by the records themselves
-      // (w[6], w[7] of an item's first step = dependency range of the NEXT item)
-      uint32_t first_d0 = 0, first_cnt = 0;
-      {
-        const uint32_t i0 = __ldg(eoff + pe.sec), i1 = __ldg(eoff + pe.sec + 1);
-        if (i0 < i1) { first_d0 = __ldg(P.dep_off + i0); first_cnt = __ldg(P.dep_off + i0 + 1) - first_d0; }
-      }
+      ++n_items;
+      const LoopSeg& sg = P.seg[cur.seg];
+      const uint32_t wi = sg.win_base + cur.win;
+      const uint32_t rbeg = __ldg(P.win_rec_off + wi), rend = __ldg(P.win_rec_off + wi + 1);
+      const uint32_t half_b = sg.half_b;
+      const int n_half = (int)(sg.n_tile >> 1);
+      const int row0 = (2 * (int)cur.mp + (int)rank) * kRowTile;
       uint4 mine = make_uint4(0, 0, 0, 0);
       if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
-      // the item about to start: dependency range, this lane's entry (first 32) and its flag value if already fetched
-      uint32_t cur_d0 = first_d0, cur_cnt = first_cnt, cur_e = 0, cur_f = 0;
-      bool cur_f_valid = false;
-      if (lane < cur_cnt) cur_e = __ldg(P.deps + cur_d0 + lane);
-      uint32_t nxt_d0 = 0, nxt_cnt = 0, nxt_e = 0;
-      uint32_t trace_item = __ldg(eoff + pe.sec);               // index of the item about to start (trace only)
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
         __syncwarp();
@@ -489,48 +619,17 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
         for (uint32_t i = 0; i < cnt; ++i, ++it) {
           const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
-          const uint4 r1 = ptx::ld_shared_v4(ring + i * 32u + 16u);
+          const uint2 r1 = ptx::ld_shared_v2(ring + i * 32u + 16u);
           const uint32_t slot = it & (TC2_NSLOT - 1);
           const int kc = (r0.x >> 8) & 0xF, nA = (r0.x >> 12) & 0x7, nB = (r0.x >> 15) & 0xF;
-          const uint32_t dep = (r0.x >> 19) & 0xF;
-          const int seg = (int)((r0.y >> 16) & 0x1Fu);
-          const LoopSeg& sg = P.seg[seg];
-          if ((r0.y >> 21) & 1u) {
-            // first step of an item: everything it stages must have been published.  Fast path: the flag values were
-            // fetched while the previous item's last step was issued and already satisfy the target.
-            const long long tw0 = P.dbg ? clock64() : 0;
-            const int t = sg.group ? pe.t1 : pe.t0;                       // this item's L-step
-            const bool tracing = P.trace != nullptr && (pi == P.trace_entry || pi == P.trace_entry + 1) && leader && lane == 0;
-            if (tracing) P.trace[(size_t)trace_item * 4 + 0] = ptx::globaltimer();
-            if (cur_cnt > 0) {
-              const uint32_t target = LOOP_ARRIVALS * (uint32_t)((cur_e & LOOP_DEP_PREV) ? t : t + 1);
-              const bool ok = (lane >= cur_cnt) || (cur_f_valid && cur_f >= target);
-              if (!__all_sync(0xffffffffu, ok) || cur_cnt > 32u) {
-                ++n_slow;
-                for (uint32_t d = cur_d0 + lane; d < cur_d0 + cur_cnt; d += 32) {
-                  const uint32_t e = __ldg(P.deps + d);
-                  loop_wait_flag(P.flags + (e & ~LOOP_DEP_PREV), LOOP_ARRIVALS * (uint32_t)((e & LOOP_DEP_PREV) ? t : t + 1), P.status);
-                }
-                __syncwarp();
-              }
-              ptx::fence_proxy_async_all();             // acquired generic-proxy view -> the TMA (async proxy) reads below
-            }
-            if (P.dbg) t_flag += clock64() - tw0;
-            if (tracing) P.trace[(size_t)trace_item * 4 + 1] = ptx::globaltimer();
-            ++trace_item;
-            // the NEXT item's dependency range rides in this record: fetch this lane's entry now, its flag at the item's last step
-            nxt_d0 = r1.z; nxt_cnt = r1.w; nxt_e = 0;
-            if (lane < nxt_cnt) nxt_e = __ldg(P.deps + nxt_d0 + lane);
-          }
-          const int row0 = (2 * (int)(r0.y & 0xFFFFu) + (int)rank) * kRowTile;
+          uint32_t dep;
+          const uint32_t off_kb = loop_ring_alloc(rs, it, ((uint32_t)nA * TC_A_BYTES + (uint32_t)nB * half_b + 1023u) >> 10, lane, &dep);
           const long long tr0 = P.dbg ? clock64() : 0;
           if (it >= dep) ptx::mbar_wait(bar_empty + 8 * ((it - dep) & (TC2_NSLOT - 1)), ((it - dep) >> 3) & 1);   // step it-dep consumed
           if (dep != TC2_NSLOT && it >= TC2_NSLOT) ptx::mbar_wait(bar_empty + 8 * slot, ((it - TC2_NSLOT) >> 3) & 1);
           if (P.dbg) t_ring += clock64() - tr0;
           const uint32_t full = bar_full + 8 * slot;
-          const uint32_t sa = smem_base + ((r0.x & 0xFFu) << 10);
-          const uint32_t half_b = sg.half_b;
-          const int n_half = (int)(sg.n_tile >> 1);
+          const uint32_t sa = smem_base + (off_kb << 10);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(full, 2u * ((uint32_t)nA * TC_A_BYTES + (uint32_t)nB * half_b));
 #pragma unroll
@@ -548,41 +647,48 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
             }
           }
           __syncwarp();
-          if ((r0.y >> 22) & 1u) {
-            // last step of the item issued: look at the next item's flags now, so that the answer is (usually) there by
-            // the time its first step comes up
-            cur_d0 = nxt_d0; cur_cnt = nxt_cnt; cur_e = nxt_e; cur_f = 0; cur_f_valid = true;
-            if (lane < cur_cnt) cur_f = ptx::ld_acquire_gpu(P.flags + (cur_e & ~LOOP_DEP_PREV));
-          }
         }
         __syncwarp();
       }
     }
-    if (P.dbg && lane == 0) {
-      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_FLAG] = (unsigned long long)t_flag;
-      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_RING] = (unsigned long long)t_ring;
-      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_TOTAL] = (unsigned long long)(clock64() - t_p0);
-      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_SLOW] = (unsigned long long)n_slow;
-    }
     // drain: nobody leaves while MMAs may still read this CTA's shared memory
     for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
-  } else if (warp == 1) {
+    if (P.dbg && lane == 0) {
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_POP] = (unsigned long long)t_pop;
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_RING] = (unsigned long long)t_ring;
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_TOTAL] = (unsigned long long)(clock64() - t_p0);
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_ITEMS] = (unsigned long long)n_items;
+    }
+   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      const TcRec* __restrict__ stream = P.stream_m;
+      const TcRec* __restrict__ stream = P.tmpl_m;
       const uint32_t ring = stg_base + TC2_REC_BATCH * (uint32_t)sizeof(TcRec);
       const uint64_t desc0 = make_smem_desc_sw128(smem_base);
       const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
-      uint32_t it = 0, item_count = 0, buf = 0;
-      uint32_t idesc = 0, acc_stride = 0, half_b16 = 0, n_merge = 0;
-      long long t_full = 0, t_acc = 0;
+      uint32_t it = 0, item_count = 0;
+      LoopRing rs;
+      long long t_full = 0, t_acc = 0, t_mail = 0;
       const long long t_m0 = P.dbg ? clock64() : 0;
-      for (int pi = 0; pi < P.n_prog; ++pi) {
-        const int sec = loop_prog_entry(P.n_groups, P.n_prog, pi).sec;
-        const uint32_t rbeg = __ldg(soff + sec), rend = __ldg(soff + sec + 1);
-        if (rbeg >= rend) continue;
+      for (uint32_t k = 0;; ++k) {
+        const long long tm0 = P.dbg ? clock64() : 0;
+        const LoopItem cur = mail_read(k, false);
+        if (P.dbg) t_mail += clock64() - tm0;
+        if (cur.seg == 0xFFFFu) break;
+        const LoopSeg& sg = P.seg[cur.seg];
+        const uint32_t idesc = sg.idesc, acc_stride = sg.acc_stride, half_b = sg.half_b, half_b16 = half_b >> 4, n_merge = (sg.n_tile >> 3) << 17;
+        const uint32_t wi = sg.win_base + cur.win;
+        const uint32_t rbeg = __ldg(P.win_rec_off + wi), rend = __ldg(P.win_rec_off + wi + 1);
+        const uint32_t buf = item_count & 1;
         uint4 mine = make_uint4(0, 0, 0, 0);
         if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
+        {                                                       // the item's accumulator buffer must be drained
+          const long long ta0 = P.dbg ? clock64() : 0;
+          ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
+          if (P.dbg) t_acc += clock64() - ta0;
+          if (P.trace != nullptr && (int)cur.t == P.trace_step && lane == 0)
+            P.trace[(size_t)(sg.item_base + cur.mp * sg.n_windows + cur.win) * 4 + 1] = ptx::globaltimer();
+        }
         for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
           ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
           __syncwarp();
@@ -592,22 +698,16 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
             const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
             const uint4 r1 = ptx::ld_shared_v4(ring + i * 32u + 16u);
             const uint32_t slot = it & (TC2_NSLOT - 1), phase = (it >> 3) & 1;
-            const int nA = (r0.x >> 8) & 0x7, n_ops = (r0.x >> 11) & 0x1F;
-            const uint32_t flags = (r0.x >> 16) & 0x3u;
-            if (flags & 1u) {                                   // first step of an item: its accumulator buffer must be drained
-              const LoopSeg& sg = P.seg[r0.y & 0x1Fu];
-              idesc = sg.idesc; acc_stride = sg.acc_stride; half_b16 = sg.half_b >> 4; n_merge = (sg.n_tile >> 3) << 17;
-              buf = item_count & 1;
-              const long long ta0 = P.dbg ? clock64() : 0;
-              ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
-              if (P.dbg) t_acc += clock64() - ta0;
-            }
+            const int nA = (r0.x >> 8) & 0x7, n_ops = (r0.x >> 11) & 0x1F, nB = (r0.x >> 18) & 0xF;
+            const bool last = (base + i + 1 == rend);
+            uint32_t dep;
+            const uint32_t off_kb = loop_ring_alloc(rs, it, ((uint32_t)nA * TC_A_BYTES + (uint32_t)nB * half_b + 1023u) >> 10, lane, &dep);
             const long long tf0 = P.dbg ? clock64() : 0;
             ptx::mbar_wait(bar_full + 8 * slot, phase);
             if (P.dbg) t_full += clock64() - tf0;
             ptx::tc_fence_after();
             // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
-            const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
+            const uint32_t a_lo0 = desc_lo0 + (off_kb << 6);
             const uint32_t b_lo0 = a_lo0 + (uint32_t)nA * (uint32_t)(TC_A_BYTES >> 4);
             if (ptx::elect_one()) {
               const uint32_t d0 = tmem_base + buf * TC2_BUF_COLS;
@@ -622,49 +722,49 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
                 const uint32_t d = d0 + ((e >> 7) & 7u) * acc_stride;
                 const uint32_t idg = idesc + ((e >> 5) & 3u) * n_merge;   // N = slots * N_TILE
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idg,
-                                    (k > 0 || !first_mma) ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk)
+                  ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * kk), ((uint64_t)desc_hi << 32) | (b_lo + 2u * kk), idg,
+                                    (kk > 0 || !first_mma) ? 1u : 0u);
               }
               ptx::umma_commit_2sm(bar_empty + 8 * slot);           // this step is consumed (both CTAs)
-              if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
+              if (last) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
             }
             __syncwarp();
-            if (flags & 2u) ++item_count;
           }
           __syncwarp();
         }
+        ++item_count;
       }
       // drain: observe the release of the last (up to two) accumulator buffers by the epilogue warps of both CTAs
       for (uint32_t j = item_count > 2 ? item_count - 2 : 0; j < item_count; ++j) ptx::mbar_wait(bar_acc_empty + 8 * (j & 1), (j >> 1) & 1);
       if (P.dbg && lane == 0) {
         P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_M_FULL] = (unsigned long long)t_full;
         P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_M_ACC] = (unsigned long long)t_acc;
+        P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_M_MAIL] = (unsigned long long)t_mail;
         P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_M_TOTAL] = (unsigned long long)(clock64() - t_m0);
       }
     }
-   } else if (lane == 0) {
-    // ===================== store warps (warp 2 + h serves epilogue half h; one lane) =====================
-    // Takes the epilogue half's staged 128x64 fp16 tiles, stores them by TMA, frees the staging tile as soon as the
-    // store has READ it, and publishes the item once its stores have COMPLETED (only the issuing thread can wait for that).
+   } else {
+    // ===================== store warps (warp 2 + h serves epilogue half h) =====================
+    // Takes the epilogue half's staged 128x64 fp16 tiles, stores them by TMA (lane 0), frees the staging tile as soon as
+    // the store has READ it, and reports the item's completion once its stores have COMPLETED (only the issuing thread
+    // can wait for that); the warp that reports the last of an item's four parts wakes its successors.
     const int h = warp - 2;
-    const uint32_t tile_full = bar_base + 168 + 8 * (uint32_t)h, tile_free = bar_base + 184 + 8 * (uint32_t)h;
+    const uint32_t tile_full = bar_base + LB_TILE_FULL + 8 * (uint32_t)h, tile_free = bar_base + LB_TILE_FREE + 8 * (uint32_t)h;
     const uint32_t s_out = epi_base + (uint32_t)h * TC2_TILE_BYTES;
     uint32_t tcount = 0;
     long long t_tile = 0, t_done = 0;
     const long long t_s0 = P.dbg ? clock64() : 0;
-    for (int pi = 0; pi < P.n_prog; ++pi) {
-      const int sec = loop_prog_entry(P.n_groups, P.n_prog, pi).sec;
-      const uint32_t e_beg = __ldg(eoff + sec), e_end = __ldg(eoff + sec + 1);
-      for (uint32_t k = e_beg; k < e_end; ++k) {
-        const uint4 cur = __ldg(P.eitems + k);
-        const int seg = (int)(cur.x >> 16), win = (int)(cur.x & 0xFFFFu), mp = (int)cur.y;
-        const LoopSeg& sg = P.seg[seg];
-        const uint32_t kind = sg.kind;
-        if (!(kind <= LK_NONE64H)) continue;                       // fp32 / last-layer epilogues store (and publish) themselves
-        const TcItem2* ip = sg.items + win;
-        const int G = (int)(sg.n_tile >> 6), n_units = (int)__ldg(&ip->n_acc) * G;
-        const int row0 = (2 * mp + (int)rank) * kRowTile;
+    for (uint32_t k = 0;; ++k) {
+      const LoopItem cur = mail_read(k, !leader);
+      if (cur.seg == 0xFFFFu) break;
+      const LoopSeg& sg = P.seg[cur.seg];
+      if (!(sg.kind <= LK_NONE64H)) continue;                    // fp32 / last-layer epilogues store (and report) themselves
+      const TcItem2* ip = sg.items + cur.win;
+      const int G = (int)(sg.n_tile >> 6), n_units = (int)__ldg(&ip->n_acc) * G;
+      const int row0 = (2 * (int)cur.mp + (int)rank) * kRowTile;
+      uint32_t old = 0;
+      if (lane == 0) {
         for (int u = h; u < n_units; u += 2) {
           const int q = (int)__ldg(&ip->q[u / G]);
           const long long tw0 = P.dbg ? clock64() : 0;
@@ -677,14 +777,16 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
           ++tcount;
         }
         const long long tw1 = P.dbg ? clock64() : 0;
-        ptx::bulk_wait_all0();                                      // the item's tiles are in global memory
-        ptx::fence_proxy_async_all();
-        ptx::red_release_gpu_add(P.flags + cur.z, 4u);   // for this half's four warps
+        ptx::bulk_wait_all0();                                    // the item's tiles are in global memory
+        loop_publish_fence();
+        old = ptx::atom_add_acq_rel_gpu(P.arrive + sg.item_base + cur.mp * sg.n_windows + cur.win, 1u);
         if (P.dbg) t_done += clock64() - tw1;
       }
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old + 1u == 4u * (cur.t + 1u)) loop_complete(P, sg, cur.seg, cur.win, cur.mp, cur.t, lane);   // 2 halves x 2 CTAs per execution
     }
-    if (P.dbg) {
-      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_TILE + 0] = (unsigned long long)t_tile;    // (warp 3 overwrites warp 2: same order of magnitude)
+    if (P.dbg && lane == 0) {
+      P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_TILE] = (unsigned long long)t_tile;    // (warp 3 overwrites warp 2: same order of magnitude)
       P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_DONE] = (unsigned long long)t_done;
       P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_TOTAL] = (unsigned long long)(clock64() - t_s0);
     }
@@ -693,35 +795,30 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     ptx::setmaxnreg_inc<LOOP_REGS_EPI>();
     // ===================== epilogue (warps 4..11, both CTAs) =====================
     LoopCtx cx;
-    cx.tmem_base = tmem_base; cx.bar_acc_full = bar_acc_full; cx.bar_acc_empty = bar_acc_empty; cx.epi_base = epi_base; cx.bar_base = bar_base;
+    cx.tmem_base = tmem_base; cx.bar_base = bar_base; cx.epi_base = epi_base;
     cx.warp = warp; cx.lane = lane; cx.rank = (int)rank; cx.item_count = 0; cx.tile_count = 0; cx.t_acc = 0; cx.t_tile = 0;
     const long long t_e0 = P.dbg ? clock64() : 0;
     TcFinalArgs fa{};
     fa.x = P.x; fa.y = P.y; fa.loss_part = P.loss_part; fa.R = P.R; fa.B = P.B; fa.n_rows = P.n_rows; fa.nbx = P.nbx; fa.w_out = P.w_out;
     fa.gscale = P.gscale; fa.m_gmul = P.m_gmul; fa.m_mu = P.m_mu;
-    for (int pi = 0; pi < P.n_prog; ++pi) {
-      const LoopProg pe = loop_prog_entry(P.n_groups, P.n_prog, pi);
-      const uint32_t e_beg = __ldg(eoff + pe.sec), e_end = __ldg(eoff + pe.sec + 1);
-      uint4 nxt = make_uint4(0, 0, 0, 0);
-      if (e_beg < e_end) nxt = __ldg(P.eitems + e_beg);
-      for (uint32_t k = e_beg; k < e_end; ++k, ++cx.item_count) {
-        const uint4 cur = nxt;
-        if (k + 1 < e_end) nxt = __ldg(P.eitems + k + 1);             // one item ahead
-        const int seg = (int)(cur.x >> 16), win = (int)(cur.x & 0xFFFFu), mp = (int)cur.y;
-        const LoopSeg& sg = P.seg[seg];
-        const int t = sg.group ? pe.t1 : pe.t0;                       // this item's L-step
-        fa.write_y = (t == P.last_step) ? 1 : 0;      // G(z) and the loss are consumed after the final forward only
-        fa.m_lr = (P.decay_step > 0 && t >= P.decay_step) ? P.m_lr * 0.1f : P.m_lr;
-        uint32_t* flag = P.flags + cur.z;
-        unsigned long long ts = 0;
-        if (P.prof != nullptr && warp == LOOP_EPI_WARP0 && lane == 0 && leader) ts = ptx::globaltimer();
-        loop_epilogue_dispatch<ARCH>(P, sg, cx, fa, win, mp, flag);
-        if (P.prof != nullptr && warp == LOOP_EPI_WARP0 && lane == 0 && leader) {
-          unsigned long long* pr = P.prof + ((size_t)t * P.n_vseg + seg) * 2;
-          const unsigned long long te = ptx::globaltimer();
-          atomicMin(pr, ts);
-          atomicMax(pr + 1, te);
-          if (P.trace != nullptr && (pi == P.trace_entry || pi == P.trace_entry + 1)) { P.trace[(size_t)k * 4 + 2] = ts; P.trace[(size_t)k * 4 + 3] = te; }
+    for (uint32_t k = 0;; ++k, ++cx.item_count) {
+      const LoopItem cur = mail_read(k, !leader);
+      if (cur.seg == 0xFFFFu) break;
+      const LoopSeg& sg = P.seg[cur.seg];
+      const int t = (int)cur.t;
+      fa.write_y = (t == P.last_step) ? 1 : 0;      // G(z) and the loss are consumed after the final forward only
+      fa.m_lr = (P.decay_step > 0 && t >= P.decay_step) ? P.m_lr * 0.1f : P.m_lr;
+      unsigned long long ts = 0;
+      if (P.prof != nullptr && warp == LOOP_EPI_WARP0 && lane == 0 && leader) ts = ptx::globaltimer();
+      loop_epilogue_dispatch<ARCH>(P, sg, cx, fa, cur);
+      if (P.prof != nullptr && warp == LOOP_EPI_WARP0 && lane == 0 && leader) {
+        const unsigned long long te = ptx::globaltimer();
+        unsigned long long* pr = P.prof + ((size_t)t * P.n_seg + cur.seg) * 2;
+        atomicMin(pr, ts);
+        atomicMax(pr + 1, te);
+        if (P.trace != nullptr && t == P.trace_step) {
+          unsigned long long* tr = P.trace + (size_t)(sg.item_base + cur.mp * sg.n_windows + cur.win) * 4;
+          tr[2] = ts; tr[3] = te;
         }
       }
     }
@@ -740,48 +837,36 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
   }
 }
 
-
 // ------------------------------------------------------------------------------------------
 // host side: the plan
 // ------------------------------------------------------------------------------------------
-struct LoopSegSpec {              // one layer-direction ("physical segment") as the planner sees it
+struct LoopSegSpec {              // one layer-direction as the planner sees it
   std::string name;
   int N = 0, K = 0;               // MMA N (output channels per pixel) and K (input channels per pixel)
   int kind = 0;                   // LoopKind
   const PairTable* tab = nullptr; // (input pixel, weight tile) contributions of every output pixel
   int h_grid = 1, w_grid = 1;     // raster of the output pixels (window shapes)
   int max_acc = 1;                // accumulators per window (TMEM columns / layer-specific cap)
-  int in_seg = -1;                // segment whose output this one reads; -1: z, published by the momentum tail
+  int in_seg = -1;                // segment whose output this one reads; -1: z, released by the momentum tail
   bool fwd = true;                // part of the generator forward (+ loss) or of the backward-to-z
   double macs_per_row = 0.0;      // exact in-bounds MACs per latent row (profiling only)
 };
 
-// The plan.  Row pairs are split into `n_groups` groups whose L-steps run HALF A STEP OUT OF PHASE: while group A is in
-// its backward half, group B is in its forward half, and their segments alternate in every CTA pair's stream
-// (A.bwd_0, B.fwd_0, A.bwd_1, B.fwd_1, ...).  Consecutive segments of one group are then separated by a segment of the
-// other group, so the latency of "epilogue -> store completes -> flag -> dependent item's producer" (and of the momentum
-// update at the L-step boundary) is covered by independent work instead of stalling the in-order streams - software
-// pipelining across row-pair groups.  A (group, layer-direction) pair is a VIRTUAL SEGMENT with its own window tiling,
-// items and flags.  Every CTA pair's records are four sections:
-//   section 0 = A.fwd alone (prologue: A's first forward)      section 1 = A.bwd interleaved with B.fwd
-//   section 3 = B.fwd alone (epilogue: B's last forward)       section 2 = A.fwd interleaved with B.bwd
-// and a launch runs  sec0, (sec1, sec2) x (L - 1), sec3.   With one group (small batches, dgan_forward / dgan_loss_grad)
-// sections 1 / 2 are that group's backward / forward and a launch runs  sec2, (sec1, sec2) x (L - 1).
+// The plan of one L-step: per segment its window tiling and per window its step records (templates: the row pair and the
+// ring placement are filled in at run time), plus the dataflow graph between windows of consecutive segments.
 struct LoopPlan {
-  int n_phys = 0, n_groups = 1, n_vseg = 0, n_pairs = 0, n_mpairs = 0;
-  std::vector<int> vseg_phys, vseg_group;         // vseg = group * n_phys + phys
-  std::vector<std::vector<int>> group_mps;        // row pairs of each group
-  std::vector<std::vector<TcItem2>> hdrs;         // per vseg: window headers
-  std::vector<int> shape;                         // per vseg: wh, ww, sy, sx
-  std::vector<uint32_t> flag_base, n_windows;     // per vseg: flags [row pair of the group][window]
-  uint32_t zflag_base = 0, n_flags = 0;
-  std::vector<int> sec_vsegs[LOOP_N_SEC];         // virtual segments of each section in stream order
-  std::vector<TcRec> stream_p[2], stream_m;       // CTA pair after CTA pair, each: sections 0..3
-  std::vector<uint32_t> stream_off;               // [n_pairs][LOOP_N_SEC + 1]
-  std::vector<uint4> eitems;                      // x = vseg << 16 | window, y = row pair, z = flag index
-  std::vector<uint32_t> eitem_off;                // [n_pairs][LOOP_N_SEC + 1]
-  std::vector<uint32_t> dep_off, deps;
-  long long n_steps = 0, n_mma = 0, n_bytes = 0;  // of sections 1 + 2 (= one L-step of every row pair)
+  int n_seg = 0, n_fwd = 0, n_pairs = 0, n_mpairs = 0;
+  std::vector<std::vector<TcItem2>> hdrs;         // per segment: window headers
+  std::vector<int> shape;                         // per segment: wh, ww, sy, sx
+  std::vector<uint32_t> win_base, item_base, n_windows;     // per segment
+  uint32_t n_win = 0, n_item_slots = 0;           // windows of all segments; counters = windows x row pairs
+  std::vector<TcRec> tmpl_p[2], tmpl_m;           // windows back to back in (segment, window) order
+  std::vector<uint32_t> win_rec_off;              // [n_win + 1]
+  std::vector<uint32_t> succ_off, succ, need;     // [n_win + 1], successor entries (segment << 16 | window), [n_win]
+  std::vector<unsigned long long> q_init;         // the queue's initial content: the first segment's items of L-step 0
+  uint32_t win_fwd = 0, win_bwd = 0;              // windows of the forward / backward half
+  uint32_t q_cap = 0;
+  long long n_steps = 0, n_mma = 0, n_bytes = 0;  // of one L-step of every row pair
 };
 
 #ifndef DGAN_COST_EPI_KB
@@ -790,38 +875,17 @@ struct LoopPlan {
 #ifndef DGAN_COST_FIXED_KB
 #define DGAN_COST_FIXED_KB 48.0
 #endif
-#ifndef DGAN_LOOP_GROUPS
-#define DGAN_LOOP_GROUPS 2        // row-pair groups of a projection (2 = half an L-step out of phase; 1 = all in phase, for A/B runs)
-#endif
 constexpr int LOOP_STEP_MAX_BYTES = 48 * 1024;    // measured optimum of the operand-ring kernels (round 1): 2 A tiles + weights
+constexpr uint32_t LOOP_TAIL_NEED = 2;            // the first segment waits for the momentum tails of the row pair's two 128-row tiles
 
 static double loop_item_cost(const Tc2HostItem& it, int N) {
   return it.stage_bytes + DGAN_COST_EPI_KB * 1024.0 * it.hdr.n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;
 }
 
-// Longest-processing-time assignment of the (window, row pair) items of one virtual segment to the CTA pairs, on top of
-// the load `load` they already carry (the other virtual segment of the same slot: there is no barrier between them, so
-// they are balanced jointly).  Items come out per CTA pair as (window, index into `mps`).
-static void loop_lpt(const std::vector<Tc2HostItem>& items, int N, int n_mps, std::vector<double>* load,
-                     std::vector<std::vector<std::pair<int, int>>>* lists) {
-  const size_t n_pairs = load->size();
-  lists->assign(n_pairs, {});
-  std::vector<size_t> order(items.size());
-  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return items[l].stage_bytes > items[r].stage_bytes; });
-  for (size_t oi = 0; oi < order.size(); ++oi)
-    for (int m = 0; m < n_mps; ++m) {                     // cost-descending; the row pair is the fast index
-      size_t best = 0;
-      for (size_t pr = 1; pr < n_pairs; ++pr)
-        if ((*load)[pr] < (*load)[best]) best = pr;
-      (*load)[best] += loop_item_cost(items[order[oi]], N);
-      (*lists)[best].push_back({(int)order[oi], m});
-    }
-}
-
-// Window tiling of one virtual segment: every candidate shape (wh x ww accumulators, strides 1 or 2 - stride 2 gathers
-// outputs of equal parity of a stride-2 transposed conv, which share weight tiles) is scored by the makespan of an LPT
-// assignment of its items (cost = operand bytes staged + a per-accumulator epilogue charge + a fixed per-item charge).
+// Window tiling of one segment: every candidate shape (wh x ww accumulators, strides 1 or 2 - stride 2 gathers outputs of
+// equal parity of a stride-2 transposed conv, which share weight tiles) is scored by the makespan of a greedy
+// longest-first assignment of its items to the CTA pairs (cost = operand bytes staged + a per-accumulator epilogue
+// charge + a fixed per-item charge): total cost matters most, the makespan term keeps the items fine enough to balance.
 static int loop_choose_tiling(const LoopSegSpec& sp, int n_mps, int n_pairs, std::vector<Tc2HostItem>* items_out, int shape_out[4]) {
   const int N = sp.N, K = sp.K;
   const int max_g = (N >= 64) ? std::min(4, 256 / N) : 1;
@@ -838,9 +902,17 @@ static int loop_choose_tiling(const LoopSegSpec& sp, int n_mps, int n_pairs, std
           if (wins.size() > 0xFFFFu) continue;
           std::vector<Tc2HostItem> items(wins.size());
           for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(*sp.tab, wins[i], N, K, max_g, TC2_MAX_A, step_max, &items[i]);
+          std::vector<size_t> order(items.size());
+          for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+          std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return items[l].stage_bytes > items[r].stage_bytes; });
           std::vector<double> load((size_t)n_pairs, 0.0);
-          std::vector<std::vector<std::pair<int, int>>> lists;
-          loop_lpt(items, N, n_mps, &load, &lists);
+          for (size_t oi = 0; oi < order.size(); ++oi)
+            for (int m = 0; m < n_mps; ++m) {
+              size_t best = 0;
+              for (size_t pr = 1; pr < load.size(); ++pr)
+                if (load[pr] < load[best]) best = pr;
+              load[best] += loop_item_cost(items[order[oi]], N);
+            }
           const double makespan = *std::max_element(load.begin(), load.end());
           if (makespan < best_cost) {
             best_cost = makespan;
@@ -853,397 +925,300 @@ static int loop_choose_tiling(const LoopSegSpec& sp, int n_mps, int n_pairs, std
   return 0;
 }
 
-// Plan for `n_mpairs` row pairs on `n_pairs` CTA pairs (see LoopPlan).
-static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_pairs, int n_groups, LoopPlan* plan) {
-  const int n_phys = (int)specs.size();
-  if (n_groups < 1 || n_groups > 2 || n_phys < 1 || n_phys * n_groups > LOOP_MAX_SEG) { set_error("segment count out of range"); return DGAN_ERR_UNSUPPORTED; }
-  if (n_mpairs < n_groups || n_pairs < 1) { set_error("nothing to plan"); return DGAN_ERR_INVALID_ARG; }
-  std::vector<int> fwd_list, bwd_list;
-  for (int s = 0; s < n_phys; ++s) (specs[(size_t)s].fwd ? fwd_list : bwd_list).push_back(s);
-  if (n_groups == 2 && fwd_list.size() != bwd_list.size()) { set_error("forward and backward halves differ in length"); return DGAN_ERR_UNSUPPORTED; }
+// Plan for `n_mpairs` row pairs on `n_pairs` CTA pairs.
+static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_pairs, LoopPlan* plan) {
+  const int n_seg = (int)specs.size();
+  if (n_seg < 1 || n_seg > LOOP_MAX_SEG) { set_error("segment count out of range"); return DGAN_ERR_UNSUPPORTED; }
+  if (n_mpairs < 1 || n_mpairs > 0xFFFF || n_pairs < 1) { set_error("nothing to plan"); return DGAN_ERR_INVALID_ARG; }
   LoopPlan& pl = *plan;
   pl = LoopPlan{};
-  pl.n_phys = n_phys; pl.n_groups = n_groups; pl.n_vseg = n_phys * n_groups; pl.n_pairs = n_pairs; pl.n_mpairs = n_mpairs;
-  pl.group_mps.assign((size_t)n_groups, {});
-  for (int mp = 0; mp < n_mpairs; ++mp) pl.group_mps[(size_t)(n_groups == 2 && mp >= (n_mpairs + 1) / 2 ? 1 : 0)].push_back(mp);
-  const int nv = pl.n_vseg;
-  pl.vseg_phys.resize((size_t)nv); pl.vseg_group.resize((size_t)nv);
-  pl.hdrs.assign((size_t)nv, {}); pl.shape.assign((size_t)4 * nv, 1);
-  pl.flag_base.assign((size_t)nv, 0); pl.n_windows.assign((size_t)nv, 0);
-  std::vector<std::vector<Tc2HostItem>> items((size_t)nv);
-  std::vector<std::vector<int>> pix2win((size_t)nv);
-  int rc;
-  uint32_t n_flags = 0;
-  for (int v = 0; v < nv; ++v) {
-    const int g = v / n_phys, s = v % n_phys;
-    pl.vseg_phys[(size_t)v] = s; pl.vseg_group[(size_t)v] = g;
-    const LoopSegSpec& sp = specs[(size_t)s];
-    const int n_mps = (int)pl.group_mps[(size_t)g].size();
-    if ((rc = loop_choose_tiling(sp, n_mps, n_pairs, &items[(size_t)v], &pl.shape[(size_t)4 * v]))) return rc;
-    const size_t nw = items[(size_t)v].size();
-    pl.hdrs[(size_t)v].resize(nw);
-    pix2win[(size_t)v].assign(sp.tab->off.size() - 1, -1);
-    for (size_t w = 0; w < nw; ++w) {
-      pl.hdrs[(size_t)v][w] = items[(size_t)v][w].hdr;
-      for (uint32_t a = 0; a < items[(size_t)v][w].hdr.n_acc; ++a) pix2win[(size_t)v][items[(size_t)v][w].hdr.q[a]] = (int)w;
-    }
-    pl.flag_base[(size_t)v] = n_flags;
-    pl.n_windows[(size_t)v] = (uint32_t)nw;
-    n_flags += (uint32_t)(nw * (size_t)n_mps);
+  pl.n_seg = n_seg; pl.n_pairs = n_pairs; pl.n_mpairs = n_mpairs;
+  for (int s = 0; s < n_seg; ++s) {
+    if (specs[(size_t)s].fwd) { if (pl.n_fwd != s) { set_error("forward segments must come first"); return DGAN_ERR_UNSUPPORTED; } pl.n_fwd = s + 1; }
+    if (specs[(size_t)s].in_seg != s - 1) { set_error("segments must form a chain"); return DGAN_ERR_UNSUPPORTED; }
   }
-  pl.zflag_base = n_flags;
-  n_flags += (uint32_t)n_mpairs;
-  pl.n_flags = n_flags;
-  // ---- sections
-  auto vs = [&](int g, int s) { return g * n_phys + s; };
-  for (int k = 0; k < LOOP_N_SEC; ++k) pl.sec_vsegs[k].clear();
-  if (n_groups == 2) {
-    for (int s : fwd_list) pl.sec_vsegs[0].push_back(vs(0, s));
-    for (size_t k = 0; k < bwd_list.size(); ++k) { pl.sec_vsegs[1].push_back(vs(0, bwd_list[k])); pl.sec_vsegs[1].push_back(vs(1, fwd_list[k])); }
-    for (size_t k = 0; k < fwd_list.size(); ++k) { pl.sec_vsegs[2].push_back(vs(0, fwd_list[k])); pl.sec_vsegs[2].push_back(vs(1, bwd_list[k])); }
-    for (int s : fwd_list) pl.sec_vsegs[3].push_back(vs(1, s));
-  } else {
-    for (int s : bwd_list) pl.sec_vsegs[1].push_back(vs(0, s));
-    for (int s : fwd_list) pl.sec_vsegs[2].push_back(vs(0, s));
-  }
-  // ---- assignment: per section, slot by slot (a slot = the two virtual segments that run side by side, balanced jointly)
-  std::vector<std::vector<std::vector<std::pair<int, int>>>> lists[LOOP_N_SEC];     // [section][position in section][pair] -> (window, mp index)
-  for (int k = 0; k < LOOP_N_SEC; ++k) {
-    lists[k].resize(pl.sec_vsegs[k].size());
-    std::vector<double> load((size_t)n_pairs, 0.0);
-    for (size_t i = 0; i < pl.sec_vsegs[k].size(); ++i) {
-      const int v = pl.sec_vsegs[k][i];
-      const bool joint = (n_groups == 2 && (k == 1 || k == 2) && (i & 1));     // second member of a slot: on top of the first's load
-      if (!joint) std::fill(load.begin(), load.end(), 0.0);
-      loop_lpt(items[(size_t)v], specs[(size_t)pl.vseg_phys[(size_t)v]].N, (int)pl.group_mps[(size_t)pl.vseg_group[(size_t)v]].size(), &load, &lists[k][i]);
-    }
-  }
-  // ---- emission
+  pl.hdrs.assign((size_t)n_seg, {}); pl.shape.assign((size_t)4 * n_seg, 1);
+  pl.win_base.assign((size_t)n_seg, 0); pl.item_base.assign((size_t)n_seg, 0); pl.n_windows.assign((size_t)n_seg, 0);
+  std::vector<std::vector<Tc2HostItem>> items((size_t)n_seg);
+  std::vector<std::vector<int>> pix2win((size_t)n_seg);
   const int ring_kb = LOOP_RING_BYTES / 1024;
-  pl.stream_off.assign((size_t)n_pairs * (LOOP_N_SEC + 1), 0);
-  pl.eitem_off.assign((size_t)n_pairs * (LOOP_N_SEC + 1), 0);
-  pl.dep_off.assign(1, 0);
-  for (int pr = 0; pr < n_pairs; ++pr) {
-    std::vector<int> kb_of[LOOP_N_SEC];
-    size_t sec_beg[LOOP_N_SEC + 1];
-    for (int k = 0; k < LOOP_N_SEC; ++k) {
-      sec_beg[k] = pl.stream_m.size();
-      pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + k] = (uint32_t)pl.stream_m.size();
-      pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + k] = (uint32_t)pl.eitems.size();
-      size_t prev_first_rec = (size_t)-1;
-      for (size_t i = 0; i < pl.sec_vsegs[k].size(); ++i) {
-        const int v = pl.sec_vsegs[k][i], g = pl.vseg_group[(size_t)v], s = pl.vseg_phys[(size_t)v];
-        const LoopSegSpec& sp = specs[(size_t)s];
-        std::vector<std::pair<int, int>> mine = lists[k][i][(size_t)pr];
-        // row-pair major: a CTA pair meets the row pairs in the same order in every segment (measured: cost-descending
-        // order instead is 12 % slower); inside a row pair keep the cost-descending order
-        std::stable_sort(mine.begin(), mine.end(), [](const std::pair<int, int>& l, const std::pair<int, int>& r) { return l.second < r.second; });
-        for (const auto& wm : mine) {
-          const int win = wm.first, mi = wm.second, mp = pl.group_mps[(size_t)g][(size_t)mi];
-          const Tc2HostItem& itm = items[(size_t)v][(size_t)win];
-          const uint32_t flag = pl.flag_base[(size_t)v] + (uint32_t)mi * pl.n_windows[(size_t)v] + (uint32_t)win;
-          pl.eitems.push_back(make_uint4(((uint32_t)v << 16) | (uint32_t)win, (uint32_t)mp, flag, 0u));
-          // dependencies: the windows of the producing virtual segment (same group) that cover the staged input pixels
-          std::vector<uint32_t> dl;
-          if (sp.in_seg < 0) {
-            dl.push_back((pl.zflag_base + (uint32_t)mp) | LOOP_DEP_PREV);
-          } else {
-            const int vin = vs(g, sp.in_seg);
-            const std::vector<int>& p2w = pix2win[(size_t)vin];
-            for (const Tc2HostStep& hs : itm.steps)
-              for (int a = 0; a < hs.nA; ++a) {
-                const int p = hs.a_pix[a];
-                if (p < 0 || (size_t)p >= p2w.size() || p2w[(size_t)p] < 0) { set_error(sp.name + ": input pixel without a producer"); return DGAN_ERR_UNSUPPORTED; }
-                const uint32_t f = pl.flag_base[(size_t)vin] + (uint32_t)mi * pl.n_windows[(size_t)vin] + (uint32_t)p2w[(size_t)p];
-                if (std::find(dl.begin(), dl.end(), f) == dl.end()) dl.push_back(f);
-              }
-          }
-          const uint32_t this_d0 = (uint32_t)pl.deps.size();
-          pl.deps.insert(pl.deps.end(), dl.begin(), dl.end());
-          pl.dep_off.push_back((uint32_t)pl.deps.size());
-          // the first-step record of the PREVIOUS item of this section announces this item's dependency range, so that
-          // the producer can fetch the flags one item ahead
-          if (prev_first_rec != (size_t)-1)
-            for (int r = 0; r < 2; ++r) { pl.stream_p[r][prev_first_rec].w[6] = this_d0; pl.stream_p[r][prev_first_rec].w[7] = (uint32_t)dl.size(); }
-          prev_first_rec = pl.stream_m.size();
-          for (size_t j = 0; j < itm.steps.size(); ++j) {
-            const Tc2HostStep& hs = itm.steps[j];
-            const int kb = (hs.bytes + 1023) / 1024;
-            if (kb > ring_kb / 2) { set_error("tensor-core step larger than half the operand ring"); return DGAN_ERR_UNSUPPORTED; }
-            kb_of[k].push_back(kb);
-            const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
-            TcRec rm{};
-            rm.w[0] = ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16);   // ring offset filled below
-            rm.w[1] = (uint32_t)v;
-            for (int o = 0; o < hs.n_ops; ++o) rm.w[2 + o / 2] |= (uint32_t)hs.ops[o] << (16 * (o & 1));
-            pl.stream_m.push_back(rm);
-            for (int r = 0; r < 2; ++r) {
-              TcRec rp{};
-              rp.w[0] = ((uint32_t)hs.kc << 8) | ((uint32_t)hs.nA << 12) | ((uint32_t)hs.nB << 15);   // offset + dep filled below
-              rp.w[1] = (uint32_t)mp | ((uint32_t)v << 16) | ((j == 0 ? 1u : 0u) << 21) | ((j + 1 == itm.steps.size() ? 1u : 0u) << 22);
-              for (int a = 0; a < hs.nA; ++a) rp.w[2 + a / 2] |= (uint32_t)(hs.a_pix[a] & 0xFFFF) << (16 * (a & 1));
-              for (int b = 0; b < hs.nB; ++b) rp.w[4 + b / 4] |= (uint32_t)hs.b_ent[r][b] << (8 * (b & 3));
-              pl.stream_p[r].push_back(rp);
-            }
-            if (k == 1 || k == 2) { pl.n_mma += hs.n_ops; pl.n_steps += 1; pl.n_bytes += hs.bytes; }
-          }
-        }
-      }
+  int rc;
+  for (int s = 0; s < n_seg; ++s) {
+    const LoopSegSpec& sp = specs[(size_t)s];
+    if ((rc = loop_choose_tiling(sp, n_mpairs, n_pairs, &items[(size_t)s], &pl.shape[(size_t)4 * s]))) return rc;
+    const size_t nw = items[(size_t)s].size();
+    pl.hdrs[(size_t)s].resize(nw);
+    pix2win[(size_t)s].assign(sp.tab->off.size() - 1, -1);
+    for (size_t w = 0; w < nw; ++w) {
+      pl.hdrs[(size_t)s][w] = items[(size_t)s][w].hdr;
+      for (uint32_t a = 0; a < items[(size_t)s][w].hdr.n_acc; ++a) pix2win[(size_t)s][items[(size_t)s][w].hdr.q[a]] = (int)w;
     }
-    sec_beg[LOOP_N_SEC] = pl.stream_m.size();
-    pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + LOOP_N_SEC] = (uint32_t)pl.stream_m.size();
-    pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + LOOP_N_SEC] = (uint32_t)pl.eitems.size();
-    // ---- circular operand ring of this CTA pair.  Sequential allocation, wrap when a step does not fit.  Sections 1 and 2
-    //      alternate for the whole launch: they are planned as ONE cyclic sequence (a step's dependency distance may reach
-    //      back across the section boundary, also from the start of section 1 to the end of section 2).  Sections 0 and 3
-    //      start on an empty ring (kernel start / explicit drain) and only look back inside themselves.
-    auto plan_ring = [&](const std::vector<int>& kbs, size_t rec0, bool cyclic) {
-      const int n = (int)kbs.size();
-      std::vector<int> beg((size_t)n), end((size_t)n);
-      int cursor = 0;
-      for (int k2 = 0; k2 < n; ++k2) {
-        if (cursor + kbs[(size_t)k2] > ring_kb) cursor = 0;
-        beg[(size_t)k2] = cursor; end[(size_t)k2] = cursor + kbs[(size_t)k2];
-        cursor = end[(size_t)k2];
-      }
-      // dep = distance (in steps) to the latest earlier step whose region overlaps this step's: the producer may overwrite
-      // the region once that step is consumed (8 = barrier-slot reuse only)
-      for (int k2 = 0; k2 < n; ++k2) {
-        int dep = TC2_NSLOT;
-        for (int d = 1; d < TC2_NSLOT; ++d) {
-          int c = k2 - d;
-          if (c < 0) { if (!cyclic) break; c = (c % n + n) % n; }
-          if (beg[(size_t)c] < end[(size_t)k2] && beg[(size_t)k2] < end[(size_t)c]) { dep = d; break; }
-        }
-        const size_t ri = rec0 + (size_t)k2;
-        pl.stream_m[ri].w[0] |= (uint32_t)beg[(size_t)k2];
-        for (int r = 0; r < 2; ++r) pl.stream_p[r][ri].w[0] |= (uint32_t)beg[(size_t)k2] | ((uint32_t)dep << 19);
-      }
-    };
-    plan_ring(kb_of[0], sec_beg[0], false);
-    {
-      std::vector<int> both = kb_of[1];
-      both.insert(both.end(), kb_of[2].begin(), kb_of[2].end());
-      plan_ring(both, sec_beg[1], true);            // sections 1 and 2 are adjacent in the record arrays
-    }
-    plan_ring(kb_of[3], sec_beg[3], false);
+    pl.win_base[(size_t)s] = pl.n_win;
+    pl.item_base[(size_t)s] = pl.n_item_slots;
+    pl.n_windows[(size_t)s] = (uint32_t)nw;
+    pl.n_win += (uint32_t)nw;
+    pl.n_item_slots += (uint32_t)(nw * (size_t)n_mpairs);
+    (sp.fwd ? pl.win_fwd : pl.win_bwd) += (uint32_t)nw;
   }
+  // ---- step records (templates) and the dependency sets: the windows of the previous segment that write the pixels an
+  //      item stages
+  std::vector<std::vector<uint32_t>> deps(pl.n_win);
+  pl.win_rec_off.assign(1, 0);
+  for (int s = 0; s < n_seg; ++s) {
+    const LoopSegSpec& sp = specs[(size_t)s];
+    for (size_t w = 0; w < items[(size_t)s].size(); ++w) {
+      const Tc2HostItem& itm = items[(size_t)s][w];
+      std::vector<uint32_t>& dl = deps[pl.win_base[(size_t)s] + w];
+      if (itm.steps.empty()) { set_error(sp.name + ": a window without steps"); return DGAN_ERR_UNSUPPORTED; }
+      for (size_t j = 0; j < itm.steps.size(); ++j) {
+        const Tc2HostStep& hs = itm.steps[j];
+        const int kb = (hs.bytes + 1023) / 1024;
+        if (kb > ring_kb / 2) { set_error("tensor-core step larger than half the operand ring"); return DGAN_ERR_UNSUPPORTED; }
+        if (sp.in_seg >= 0)
+          for (int a = 0; a < hs.nA; ++a) {
+            const std::vector<int>& p2w = pix2win[(size_t)sp.in_seg];
+            const int p = hs.a_pix[a];
+            if (p < 0 || (size_t)p >= p2w.size() || p2w[(size_t)p] < 0) { set_error(sp.name + ": input pixel without a producer"); return DGAN_ERR_UNSUPPORTED; }
+            if (std::find(dl.begin(), dl.end(), (uint32_t)p2w[(size_t)p]) == dl.end()) dl.push_back((uint32_t)p2w[(size_t)p]);
+          }
+        const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
+        TcRec rm{};
+        rm.w[0] = ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16) | ((uint32_t)hs.nB << 18);
+        for (int o = 0; o < hs.n_ops; ++o) rm.w[2 + o / 2] |= (uint32_t)hs.ops[o] << (16 * (o & 1));
+        pl.tmpl_m.push_back(rm);
+        for (int r = 0; r < 2; ++r) {
+          TcRec rp{};
+          rp.w[0] = ((uint32_t)hs.kc << 8) | ((uint32_t)hs.nA << 12) | ((uint32_t)hs.nB << 15);
+          for (int a = 0; a < hs.nA; ++a) rp.w[2 + a / 2] |= (uint32_t)(hs.a_pix[a] & 0xFFFF) << (16 * (a & 1));
+          for (int b = 0; b < hs.nB; ++b) rp.w[4 + b / 4] |= (uint32_t)hs.b_ent[r][b] << (8 * (b & 3));
+          pl.tmpl_p[r].push_back(rp);
+        }
+        pl.n_mma += (long long)hs.n_ops * n_mpairs; pl.n_steps += n_mpairs; pl.n_bytes += (long long)hs.bytes * n_mpairs;
+      }
+      pl.win_rec_off.push_back((uint32_t)pl.tmpl_m.size());
+    }
+  }
+  // ---- the graph: need = size of the dependency set; successors = its inverse
+  pl.need.assign(pl.n_win, 0);
+  std::vector<std::vector<uint32_t>> succ(pl.n_win);
+  for (int s = 0; s < n_seg; ++s)
+    for (uint32_t w = 0; w < pl.n_windows[(size_t)s]; ++w) {
+      const uint32_t wi = pl.win_base[(size_t)s] + w;
+      if (specs[(size_t)s].in_seg < 0) { pl.need[wi] = LOOP_TAIL_NEED; continue; }
+      pl.need[wi] = (uint32_t)deps[wi].size();
+      for (uint32_t u : deps[wi]) succ[pl.win_base[(size_t)specs[(size_t)s].in_seg] + u].push_back(((uint32_t)s << 16) | w);
+    }
+  pl.succ_off.assign(1, 0);
+  for (uint32_t wi = 0; wi < pl.n_win; ++wi) {
+    pl.succ.insert(pl.succ.end(), succ[wi].begin(), succ[wi].end());
+    pl.succ_off.push_back((uint32_t)pl.succ.size());
+  }
+  if (pl.succ.empty()) pl.succ.push_back(0);
+  // ---- the queue.  At any time a row pair has ready items of ONE L-step only (its next L-step is released by its last
+  //      Linear-backward tail), so ready-but-untaken entries never exceed windows-per-step x row pairs (+ the sentinels).
+  //      Entries carry the lap of their index, so a slot needs no reset; 4x head-room keeps a slot from being rewritten
+  //      before its previous entry has been read.
+  {
+    const unsigned long long bound = 4ull * ((unsigned long long)(pl.win_fwd + pl.win_bwd) * (unsigned long long)n_mpairs + (unsigned long long)n_pairs) + 64ull;
+    uint32_t cap = 1024;
+    while (cap < bound && cap < (1u << 30)) cap <<= 1;
+    if (cap < bound) { set_error("ready queue too large"); return DGAN_ERR_UNSUPPORTED; }
+    pl.q_cap = cap;
+  }
+  for (uint32_t w = 0; w < pl.n_windows[0]; ++w)            // window-major: the first pops spread over the row pairs
+    for (int mp = 0; mp < n_mpairs; ++mp) pl.q_init.push_back(((unsigned long long)(uint32_t)mp << 32) | w);
   return 0;
 }
 
-// The section sequence of a launch (LoopProg entries): `full_last` = the final L-step also runs its backward half without
-// the momentum update (dgan_loss_grad); otherwise the final L-step is forward only (the loop returns the pre-update
-// forward of iteration L-1, models/gan.py:419-421).
-static std::vector<LoopProg> loop_program(const LoopPlan& pl, int rec_iters, bool full_last) {
-  const int n = loop_prog_length(pl.n_groups, rec_iters, full_last);
-  std::vector<LoopProg> pg((size_t)n);
-  for (int pi = 0; pi < n; ++pi) pg[(size_t)pi] = loop_prog_entry(pl.n_groups, n, pi);
-  return pg;
+// Items of a launch over `rec_iters` L-steps (the final L-step is forward only unless `full_last`).
+static inline unsigned long long loop_total_items(const LoopPlan& pl, int rec_iters, bool full_last) {
+  return (unsigned long long)pl.n_mpairs * ((unsigned long long)rec_iters * pl.win_fwd + (unsigned long long)(rec_iters - (full_last ? 0 : 1)) * pl.win_bwd);
 }
 
+// Host twin of loop_ring_alloc (the ring placement the kernel computes at run time).
+struct LoopRingHost {
+  int cursor = 0;
+  std::vector<std::pair<int, int>> hist;          // regions of all steps so far
+  int alloc(int kb, int* dep) {
+    const int ring_kb = LOOP_RING_BYTES / 1024;
+    if (cursor + kb > ring_kb) cursor = 0;
+    const int beg = cursor, end = beg + kb;
+    cursor = end;
+    int d = TC2_NSLOT;
+    for (int k = TC2_NSLOT - 1; k >= 1; --k) {
+      const int c = (int)hist.size() - k;
+      if (c >= 0 && hist[(size_t)c].first < end && beg < hist[(size_t)c].second) d = k;
+    }
+    *dep = d;
+    hist.push_back({beg, end});
+    return beg;
+  }
+};
+
 // Independent validation of a plan (host only; dgan_debug_check_plans and the CPU tests):
-//  * per (section, virtual segment), everything tc2_check_plan re-derives from the records (every (output pixel, input
-//    pixel, tap, k-chunk) contribution exactly once into the right accumulator, first-MMA flags, canonical accumulation
-//    order, every item of the group assigned exactly once);
-//  * the operand ring: a step's region overlaps none of the `dep - 1` steps before it (which may still be unread when its
-//    loads start) - cyclically over sections 1 + 2, linearly inside sections 0 and 3;
-//  * producer, MMA and epilogue streams agree on the item sequence of every CTA pair; every record announces the next
-//    item's dependency range; the flag index of an item is the one its consumers wait for;
-//  * every input pixel an item stages is covered by a dependency on the window (producing virtual segment of the same
-//    group, same row pair) that writes it, and the first segment waits for the previous L-step's z update;
-//  * no deadlock: executing a 3-step launch program with every CTA pair in order and an item startable only when its
-//    dependencies have reached the value it waits for, every item of the program completes.
+//  * per segment, everything tc2_check_plan re-derives from the records of its windows (every (output pixel, input pixel,
+//    tap, k-chunk) contribution exactly once into the right accumulator, first-MMA flags, canonical accumulation order,
+//    every window present exactly once);
+//  * the run-time ring placement, replayed over a pseudo-random item sequence: regions stay inside the ring and a region
+//    is only reused after the wait the kernel performs covers every step that overlaps it;
+//  * the graph: every pixel a window stages is written by a window in its dependency set, `need` equals that set's size,
+//    the successor lists are exactly the inverse of the dependency sets;
+//  * liveness: executing the dataflow rules of the kernel (loop_complete, the momentum tail) for 3 L-steps in a
+//    pseudo-random order runs every item exactly once per L-step, in L-step order, and pushes exactly the expected number
+//    of queue entries; the queue never holds more than a quarter of its capacity.
 static int loop_check_plan(const std::vector<LoopSegSpec>& specs, const LoopPlan& pl, std::string* err) {
   auto fail = [&](const std::string& m) { *err = m; return DGAN_ERR_INVALID_ARG; };
-  const int n_phys = pl.n_phys, nv = pl.n_vseg, n_pairs = pl.n_pairs;
-  if ((int)specs.size() != n_phys || nv != n_phys * pl.n_groups) return fail("segment count");
-  if (pl.stream_off.size() != (size_t)n_pairs * (LOOP_N_SEC + 1) || pl.eitem_off.size() != pl.stream_off.size()) return fail("offset table size");
-  if (pl.stream_p[0].size() != pl.stream_m.size() || pl.stream_p[1].size() != pl.stream_m.size()) return fail("stream sizes differ");
-  if (pl.dep_off.size() != pl.eitems.size() + 1) return fail("dep_off size");
-  const int ring_kb = LOOP_RING_BYTES / 1024;
-  std::vector<std::vector<int>> pix2win((size_t)nv);
-  for (int v = 0; v < nv; ++v) {
-    pix2win[(size_t)v].assign(specs[(size_t)pl.vseg_phys[(size_t)v]].tab->off.size() - 1, -1);
-    for (size_t w = 0; w < pl.hdrs[(size_t)v].size(); ++w)
-      for (uint32_t a = 0; a < pl.hdrs[(size_t)v][w].n_acc; ++a) pix2win[(size_t)v][pl.hdrs[(size_t)v][w].q[a]] = (int)w;
+  const int n_seg = pl.n_seg;
+  if ((int)specs.size() != n_seg || n_seg < 1 || n_seg > LOOP_MAX_SEG) return fail("segment count");
+  if (pl.tmpl_p[0].size() != pl.tmpl_m.size() || pl.tmpl_p[1].size() != pl.tmpl_m.size()) return fail("record arrays differ in size");
+  if (pl.win_rec_off.size() != (size_t)pl.n_win + 1 || pl.succ_off.size() != (size_t)pl.n_win + 1 || pl.need.size() != pl.n_win) return fail("per-window table size");
+  if (pl.win_rec_off.back() != pl.tmpl_m.size()) return fail("record offsets do not cover the records");
+  uint32_t wsum = 0, isum = 0, wf = 0, wb = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    if (pl.win_base[(size_t)s] != wsum || pl.item_base[(size_t)s] != isum || pl.n_windows[(size_t)s] != pl.hdrs[(size_t)s].size()) return fail("segment bases");
+    if (pl.n_windows[(size_t)s] == 0 || pl.n_windows[(size_t)s] > 0xFFFFu) return fail("window count of a segment");
+    wsum += pl.n_windows[(size_t)s]; isum += pl.n_windows[(size_t)s] * (uint32_t)pl.n_mpairs;
+    (specs[(size_t)s].fwd ? wf : wb) += pl.n_windows[(size_t)s];
+    if (specs[(size_t)s].fwd != (s < pl.n_fwd)) return fail("forward segments must come first");
+    if (specs[(size_t)s].in_seg != s - 1) return fail("segments must form a chain");
   }
-  std::vector<int> mp_index((size_t)pl.n_mpairs, -1), mp_group((size_t)pl.n_mpairs, -1);
-  for (int g = 0; g < pl.n_groups; ++g)
-    for (size_t i = 0; i < pl.group_mps[(size_t)g].size(); ++i) { mp_index[(size_t)pl.group_mps[(size_t)g][i]] = (int)i; mp_group[(size_t)pl.group_mps[(size_t)g][i]] = g; }
-  for (int mp = 0; mp < pl.n_mpairs; ++mp)
-    if (mp_index[(size_t)mp] < 0) return fail("a row pair belongs to no group");
-  // ---- per (section, virtual segment): slice and reuse the single-layer validator
-  for (int k = 0; k < LOOP_N_SEC; ++k)
-    for (int v : pl.sec_vsegs[k]) {
-      const LoopSegSpec& sp = specs[(size_t)pl.vseg_phys[(size_t)v]];
-      const int g = pl.vseg_group[(size_t)v], n_mps = (int)pl.group_mps[(size_t)g].size();
-      Tc2Plan sub;
-      sub.n_pairs = n_pairs;
-      sub.hdrs = pl.hdrs[(size_t)v];
-      sub.stream_off.assign((size_t)n_pairs + 1, 0);
-      std::vector<std::vector<int>> per_pair((size_t)n_pairs);
-      for (int pr = 0; pr < n_pairs; ++pr) {
-        const uint32_t r0 = pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + k], r1 = pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1) + k + 1];
-        if (r0 > r1 || r1 > pl.stream_m.size()) return fail("stream offsets not monotone");
-        sub.stream_off[(size_t)pr] = (uint32_t)sub.stream_m.size();
-        for (uint32_t ri = r0; ri < r1; ++ri) {
-          TcRec m = pl.stream_m[ri], p0 = pl.stream_p[0][ri], p1 = pl.stream_p[1][ri];
-          if ((int)((p0.w[1] >> 16) & 0x1F) != (int)(m.w[1] & 0x1F) || p0.w[1] != p1.w[1]) return fail(sp.name + ": records of one step name different segments");
-          if ((int)(m.w[1] & 0x1F) != v) continue;
-          if (((p0.w[1] >> 21) & 1u) != ((m.w[0] >> 16) & 1u) || ((p0.w[1] >> 22) & 1u) != ((m.w[0] >> 17) & 1u)) return fail(sp.name + ": first/last-step marks of producer and MMA records disagree");
-          const int mp = (int)(p0.w[1] & 0xFFFFu);
-          if (mp >= pl.n_mpairs || mp_group[(size_t)mp] != g) return fail(sp.name + ": a record's row pair is not in its group");
-          p0.w[1] = (uint32_t)mp_index[(size_t)mp]; p1.w[1] = p0.w[1]; m.w[1] = 0;
-          p0.w[6] = p0.w[7] = p1.w[6] = p1.w[7] = 0;
-          sub.stream_m.push_back(m); sub.stream_p[0].push_back(p0); sub.stream_p[1].push_back(p1);
-        }
-        const uint32_t e0 = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + k], e1 = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + k + 1];
-        if (e0 > e1 || e1 > pl.eitems.size()) return fail("item offsets not monotone");
-        for (uint32_t e = e0; e < e1; ++e) {
-          const uint4 it = pl.eitems[e];
-          if ((int)(it.x >> 16) != v) continue;
-          const uint32_t win = it.x & 0xFFFFu;
-          if (win > 0x7FFFu || it.y >= (uint32_t)pl.n_mpairs || mp_group[it.y] != g) return fail(sp.name + ": bad item");
-          if (it.z != pl.flag_base[(size_t)v] + (uint32_t)mp_index[it.y] * pl.n_windows[(size_t)v] + win) return fail(sp.name + ": an item publishes the wrong flag");
-          per_pair[(size_t)pr].push_back((int)((win << 16) | (uint32_t)mp_index[it.y]));
-        }
+  if (wsum != pl.n_win || isum != pl.n_item_slots || wf != pl.win_fwd || wb != pl.win_bwd) return fail("window totals");
+  std::vector<std::vector<int>> pix2win((size_t)n_seg);
+  for (int s = 0; s < n_seg; ++s) {
+    pix2win[(size_t)s].assign(specs[(size_t)s].tab->off.size() - 1, -1);
+    for (size_t w = 0; w < pl.hdrs[(size_t)s].size(); ++w)
+      for (uint32_t a = 0; a < pl.hdrs[(size_t)s][w].n_acc; ++a) {
+        const uint32_t q = pl.hdrs[(size_t)s][w].q[a];
+        if ((size_t)q >= pix2win[(size_t)s].size()) return fail(specs[(size_t)s].name + ": window pixel out of range");
+        if (pix2win[(size_t)s][q] != -1) return fail(specs[(size_t)s].name + ": an output pixel belongs to two windows");
+        pix2win[(size_t)s][q] = (int)w;
       }
-      sub.stream_off[(size_t)n_pairs] = (uint32_t)sub.stream_m.size();
-      size_t n_slots = 0;
-      for (auto& l : per_pair) n_slots = std::max(n_slots, l.size());
-      sub.n_slots = (int)n_slots;
-      sub.eitems.assign(n_slots * (size_t)n_pairs, -1);
-      for (int pr = 0; pr < n_pairs; ++pr)
-        for (size_t i = 0; i < per_pair[(size_t)pr].size(); ++i) sub.eitems[i * (size_t)n_pairs + pr] = per_pair[(size_t)pr][i];
-      std::string e2;
-      if (tc2_check_plan(sp.N, sp.K, *sp.tab, n_mps, LOOP_RING_BYTES, sub, &e2, /*check_ring=*/false)) return fail(sp.name + " (section " + std::to_string(k) + "): " + e2);
+    for (int v : pix2win[(size_t)s])
+      if (v < 0) return fail(specs[(size_t)s].name + ": an output pixel belongs to no window");
+  }
+  // ---- records: one pseudo CTA pair that runs every window of the segment once for row pair 0
+  for (int s = 0; s < n_seg; ++s) {
+    const LoopSegSpec& sp = specs[(size_t)s];
+    Tc2Plan sub;
+    sub.n_pairs = 1;
+    sub.hdrs = pl.hdrs[(size_t)s];
+    sub.stream_off = {0u, 0u};
+    sub.n_slots = (int)pl.n_windows[(size_t)s];
+    for (uint32_t w = 0; w < pl.n_windows[(size_t)s]; ++w) {
+      const uint32_t r0 = pl.win_rec_off[pl.win_base[(size_t)s] + w], r1 = pl.win_rec_off[pl.win_base[(size_t)s] + w + 1];
+      if (r0 >= r1 || r1 > pl.tmpl_m.size()) return fail(sp.name + ": record offsets not increasing");
+      for (uint32_t ri = r0; ri < r1; ++ri) {
+        TcRec m = pl.tmpl_m[ri], p0 = pl.tmpl_p[0][ri], p1 = pl.tmpl_p[1][ri];
+        if ((p0.w[0] & 0xFFu) != 0 || (m.w[0] & 0xFFu) != 0 || ((p0.w[0] >> 19) & 0xFu) != 0 || p0.w[1] != 0 || p1.w[1] != 0 || m.w[1] != 0)
+          return fail(sp.name + ": template record carries run-time fields");
+        if (((m.w[0] >> 18) & 0xFu) != ((p0.w[0] >> 15) & 0xFu)) return fail(sp.name + ": MMA record's weight-slot count differs from the producer's");
+        if ((((m.w[0] >> 16) & 1u) != 0) != (ri == r0) || (((m.w[0] >> 17) & 1u) != 0) != (ri + 1 == r1)) return fail(sp.name + ": first/last-step marks do not match the window's record range");
+        m.w[0] &= ~(0xFu << 18);                            // tc2_check_plan's format: no slot count in the MMA record,
+        p0.w[0] |= (uint32_t)TC2_NSLOT << 19; p1.w[0] |= (uint32_t)TC2_NSLOT << 19;     // a dep distance in the producer's
+        sub.stream_m.push_back(m); sub.stream_p[0].push_back(p0); sub.stream_p[1].push_back(p1);
+      }
+      sub.eitems.push_back((int)(w << 16));
     }
-  // ---- ring, stream/item agreement, dependency coverage: per CTA pair and section
-  for (int pr = 0; pr < n_pairs; ++pr) {
-    const uint32_t* so = &pl.stream_off[(size_t)pr * (LOOP_N_SEC + 1)];
-    const uint32_t* eo = &pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1)];
-    auto region = [&](uint32_t ri, int* beg, int* end, int* dep) {
-      const TcRec& p0 = pl.stream_p[0][ri];
-      const int v = (int)((p0.w[1] >> 16) & 0x1F);
-      const int nA = (int)((p0.w[0] >> 12) & 7), nB = (int)((p0.w[0] >> 15) & 0xF);
-      *beg = (int)(p0.w[0] & 0xFF);
-      *end = *beg + (nA * TC_A_BYTES + nB * (specs[(size_t)pl.vseg_phys[(size_t)v]].N / 2) * 128 + 1023) / 1024;
-      *dep = (int)((p0.w[0] >> 19) & 0xF);
-    };
-    auto check_ring = [&](uint32_t r0, uint32_t r1, bool cyclic) -> int {
-      const int n = (int)(r1 - r0);
-      for (int k2 = 0; k2 < n; ++k2) {
-        int b, e, d;
-        region(r0 + k2, &b, &e, &d);
-        if (e > ring_kb) return fail("step region outside the ring");
-        if (d < 1 || d > TC2_NSLOT) return fail("dep out of range");
-        if ((pl.stream_m[r0 + k2].w[0] & 0xFF) != (uint32_t)b) return fail("producer and MMA records place a step differently");
-        for (int dd = 1; dd < d; ++dd) {
-          int c = k2 - dd;
-          if (c < 0) { if (!cyclic) break; c = (c % n + n) % n; }
-          int cb, ce, cd;
-          region(r0 + c, &cb, &ce, &cd);
-          if (cb < e && b < ce) return fail("ring hazard: a region may be overwritten while it can still be read");
+    sub.stream_off[1] = (uint32_t)sub.stream_m.size();
+    std::string e2;
+    if (tc2_check_plan(sp.N, sp.K, *sp.tab, 1, LOOP_RING_BYTES, sub, &e2, /*check_ring=*/false)) return fail(sp.name + ": " + e2);
+  }
+  // ---- graph
+  std::vector<std::vector<uint32_t>> deps(pl.n_win);
+  for (int s = 0; s < n_seg; ++s)
+    for (uint32_t w = 0; w < pl.n_windows[(size_t)s]; ++w) {
+      const uint32_t wi = pl.win_base[(size_t)s] + w;
+      if (specs[(size_t)s].in_seg < 0) {
+        if (pl.need[wi] != LOOP_TAIL_NEED) return fail("first segment must wait for the row pair's two momentum tails");
+        continue;
+      }
+      std::vector<uint32_t>& dl = deps[wi];
+      for (uint32_t ri = pl.win_rec_off[wi]; ri < pl.win_rec_off[wi + 1]; ++ri) {
+        const TcRec& p0 = pl.tmpl_p[0][ri];
+        const int nA = (int)((p0.w[0] >> 12) & 7);
+        for (int a = 0; a < nA; ++a) {
+          const int p = (int)((p0.w[2 + a / 2] >> (16 * (a & 1))) & 0xFFFF);
+          const std::vector<int>& p2w = pix2win[(size_t)specs[(size_t)s].in_seg];
+          if ((size_t)p >= p2w.size()) return fail("staged pixel out of range");
+          if (std::find(dl.begin(), dl.end(), (uint32_t)p2w[(size_t)p]) == dl.end()) dl.push_back((uint32_t)p2w[(size_t)p]);
         }
       }
-      return 0;
-    };
-    int rc2;
-    if ((rc2 = check_ring(so[0], so[1], false)) || (rc2 = check_ring(so[1], so[3], true)) || (rc2 = check_ring(so[3], so[4], false))) return rc2;
-    for (int k = 0; k < LOOP_N_SEC; ++k) {
-      uint32_t e = eo[k];
-      std::vector<uint32_t> need;
-      const int n = (int)(so[k + 1] - so[k]);
-      for (int k2 = 0; k2 <= n; ++k2) {
-        const bool first = (k2 < n) && ((pl.stream_p[0][so[k] + k2].w[1] >> 21) & 1u);
-        if ((first || k2 == n) && k2 > 0) {
-          const uint32_t d0 = pl.dep_off[e], d1 = pl.dep_off[e + 1];
-          for (uint32_t f : need)
-            if (std::find(pl.deps.begin() + d0, pl.deps.begin() + d1, f) == pl.deps.begin() + d1) return fail("an item stages a pixel it has no dependency on");
-          for (uint32_t d = d0; d < d1; ++d)
-            if ((pl.deps[d] & ~LOOP_DEP_PREV) >= pl.n_flags) return fail("dependency index out of range");
-          need.clear();
-          ++e;
-        }
-        if (k2 == n) break;
-        const TcRec& p0 = pl.stream_p[0][so[k] + k2];
-        const int v = (int)((p0.w[1] >> 16) & 0x1F), mp = (int)(p0.w[1] & 0xFFFF), nA = (int)((p0.w[0] >> 12) & 7);
-        if (v >= nv) return fail("record names an unknown segment");
-        const int g = pl.vseg_group[(size_t)v];
-        if (first) {
-          if (e >= eo[k + 1] || (int)(pl.eitems[e].x >> 16) != v || (int)pl.eitems[e].y != mp) return fail("producer stream and item list disagree");
-          const uint32_t want_d0 = (e + 1 < eo[k + 1]) ? pl.dep_off[e + 1] : 0u, want_cnt = (e + 1 < eo[k + 1]) ? pl.dep_off[e + 2] - pl.dep_off[e + 1] : 0u;
-          for (int r = 0; r < 2; ++r) {
-            const TcRec& pq = pl.stream_p[r][so[k] + k2];
-            if (pq.w[7] != want_cnt || (want_cnt != 0 && pq.w[6] != want_d0)) return fail("a record announces the wrong dependency range for the next item");
-          }
-        }
-        const int in_seg = specs[(size_t)pl.vseg_phys[(size_t)v]].in_seg;
-        if (in_seg < 0) {
-          const uint32_t f = (pl.zflag_base + (uint32_t)mp) | LOOP_DEP_PREV;
-          if (std::find(need.begin(), need.end(), f) == need.end()) need.push_back(f);
-        } else {
-          const int vin = g * n_phys + in_seg;
-          for (int a = 0; a < nA; ++a) {
-            const int p = (int)((p0.w[2 + a / 2] >> (16 * (a & 1))) & 0xFFFF);
-            if ((size_t)p >= pix2win[(size_t)vin].size() || pix2win[(size_t)vin][(size_t)p] < 0) return fail("staged pixel has no producing window");
-            const uint32_t f = pl.flag_base[(size_t)vin] + (uint32_t)mp_index[(size_t)mp] * pl.n_windows[(size_t)vin] + (uint32_t)pix2win[(size_t)vin][(size_t)p];
-            if (std::find(need.begin(), need.end(), f) == need.end()) need.push_back(f);
-          }
-        }
-      }
-      if (e != eo[k + 1]) return fail("item count of a section's stream and its item list differ");
+      if (pl.need[wi] != dl.size()) return fail(specs[(size_t)s].name + ": `need` differs from the number of windows that write the staged pixels");
+    }
+  {
+    std::vector<std::vector<uint32_t>> inv(pl.n_win);
+    for (int s = 0; s < n_seg; ++s)
+      for (uint32_t w = 0; w < pl.n_windows[(size_t)s]; ++w)
+        for (uint32_t u : deps[pl.win_base[(size_t)s] + w]) inv[pl.win_base[(size_t)specs[(size_t)s].in_seg] + u].push_back(((uint32_t)s << 16) | w);
+    for (uint32_t wi = 0; wi < pl.n_win; ++wi) {
+      if (pl.succ_off[wi] > pl.succ_off[wi + 1] || pl.succ_off[wi + 1] > pl.succ.size()) return fail("successor offsets");
+      std::vector<uint32_t> got(pl.succ.begin() + pl.succ_off[wi], pl.succ.begin() + pl.succ_off[wi + 1]);
+      std::sort(got.begin(), got.end()); std::sort(inv[wi].begin(), inv[wi].end());
+      if (got != inv[wi]) return fail("a successor list is not the inverse of the dependency sets");
     }
   }
-  // ---- deadlock check over a 3-step launch program.  flag value = completions so far; an item of L-step t waits for
-  //      "dependency completed t + 1 times" (or, for the z update, t times: the momentum tail of L-step t - 1).
+  // ---- queue capacity and initial content
+  if (pl.q_cap == 0 || (pl.q_cap & (pl.q_cap - 1)) != 0) return fail("queue capacity must be a power of two");
+  if (pl.q_init.size() != (size_t)pl.n_windows[0] * (size_t)pl.n_mpairs) return fail("initial queue content");
+  {
+    std::vector<int> seen((size_t)pl.n_windows[0] * (size_t)pl.n_mpairs, 0);
+    for (unsigned long long e : pl.q_init) {
+      const uint32_t lo = (uint32_t)e, hi = (uint32_t)(e >> 32);
+      if ((lo >> 16) != 0 || (lo & 0xFFFFu) >= pl.n_windows[0] || (hi >> 16) != 0 || (hi & 0xFFFFu) >= (uint32_t)pl.n_mpairs) return fail("initial queue entry is not a first-segment item of L-step 0");
+      if (seen[(size_t)(hi & 0xFFFFu) * pl.n_windows[0] + (lo & 0xFFFFu)]++) return fail("initial queue entry twice");
+    }
+  }
+  // ---- liveness and queue bound: replay the kernel's dataflow rules for 3 L-steps, taking ready items in a pseudo-random
+  //      order; the ring placement is replayed along the way for one pseudo CTA pair that runs everything
   {
     const int L = 3;
-    const std::vector<LoopProg> pg = loop_program(pl, L, false);
-    std::vector<int> done(pl.n_flags, 0), lin_parts((size_t)pl.n_mpairs * L, 0);
-    const int last_phys = n_phys - 1;          // the Linear backward: its items complete the z update of their row pair
-    int parts_per_mp = 0;
-    for (int v = 0; v < nv; ++v)
-      if (pl.vseg_phys[(size_t)v] == last_phys && pl.vseg_group[(size_t)v] == 0) parts_per_mp = (int)pl.n_windows[(size_t)v];
-    struct Cur { size_t pi; uint32_t e; };
-    std::vector<Cur> cur((size_t)n_pairs, Cur{0, 0});
-    for (int pr = 0; pr < n_pairs; ++pr) cur[(size_t)pr].e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pg[0].sec];
-    size_t remaining = 0;
-    for (const LoopProg& pe : pg)
-      for (int pr = 0; pr < n_pairs; ++pr) remaining += pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pe.sec + 1] - pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pe.sec];
-    bool progress = true;
-    while (remaining > 0 && progress) {
-      progress = false;
-      for (int pr = 0; pr < n_pairs; ++pr) {
-        Cur& c = cur[(size_t)pr];
-        while (c.pi < pg.size()) {
-          const LoopProg& pe = pg[c.pi];
-          const uint32_t lim = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pe.sec + 1];
-          if (c.e >= lim) {
-            ++c.pi;
-            if (c.pi < pg.size()) c.e = pl.eitem_off[(size_t)pr * (LOOP_N_SEC + 1) + pg[c.pi].sec];
-            continue;
-          }
-          const uint4 it = pl.eitems[c.e];
-          const int v = (int)(it.x >> 16), t = pl.vseg_group[(size_t)v] ? pe.t1 : pe.t0;
-          if (t < 0) return fail("the program runs a group's item in a section where that group has no L-step");
-          bool ready = true;
-          for (uint32_t d = pl.dep_off[c.e]; d < pl.dep_off[c.e + 1] && ready; ++d) {
-            const uint32_t f = pl.deps[d] & ~LOOP_DEP_PREV;
-            if (pl.deps[d] & LOOP_DEP_PREV) ready = done[f] >= t;
-            else ready = done[f] >= t + 1;
-          }
-          if (!ready) break;
-          if (done[it.z] != t) return fail("an item runs out of L-step order");
-          done[it.z] = t + 1;
-          if (pl.vseg_phys[(size_t)v] == last_phys && t < L - 1) {
-            if (++lin_parts[(size_t)it.y * L + t] == parts_per_mp) done[pl.zflag_base + it.y] = t + 1;
-          }
-          ++c.e; --remaining; progress = true;
-        }
+    std::vector<uint32_t> depcnt(pl.n_item_slots, 0), runs(pl.n_item_slots, 0), tails((size_t)pl.n_mpairs, 0);
+    std::vector<unsigned long long> ready(pl.q_init.begin(), pl.q_init.end());
+    unsigned long long pushed = ready.size(), executed = 0;
+    size_t max_ready = ready.size();
+    uint32_t rng = 12345u;
+    LoopRingHost ring;
+    const int ring_kb = LOOP_RING_BYTES / 1024;
+    while (!ready.empty()) {
+      rng = rng * 1664525u + 1013904223u;
+      const size_t pick = (size_t)(rng >> 8) % ready.size();
+      const unsigned long long e = ready[pick];
+      ready[pick] = ready.back(); ready.pop_back();
+      const uint32_t seg = (uint32_t)e >> 16, win = (uint32_t)e & 0xFFFFu, mp = (uint32_t)(e >> 32) & 0xFFFFu, t = (uint32_t)(e >> 48);
+      if ((int)seg >= n_seg || win >= pl.n_windows[seg] || (int)mp >= pl.n_mpairs || (int)t >= L) return fail("replay: bad queue entry");
+      const uint32_t slot = pl.item_base[seg] + mp * pl.n_windows[seg] + win;
+      if (runs[slot] != t) return fail("replay: an item runs twice or out of L-step order");
+      runs[slot] = t + 1; ++executed;
+      for (uint32_t ri = pl.win_rec_off[pl.win_base[seg] + win]; ri < pl.win_rec_off[pl.win_base[seg] + win + 1]; ++ri) {
+        const TcRec& p0 = pl.tmpl_p[0][ri];
+        const int kb = ((int)((p0.w[0] >> 12) & 7) * TC_A_BYTES + (int)((p0.w[0] >> 15) & 0xF) * (specs[seg].N / 2) * 128 + 1023) / 1024;
+        int dep;
+        const int beg = ring.alloc(kb, &dep);
+        if (beg < 0 || beg + kb > ring_kb) return fail("replay: step region outside the ring");
+        const int k = (int)ring.hist.size() - 1;
+        for (int c = k - 1; c >= 0 && c > k - dep && c > k - TC2_NSLOT; --c)
+          if (ring.hist[(size_t)c].first < beg + kb && beg < ring.hist[(size_t)c].second) return fail("replay: ring hazard");
       }
+      const bool stop = ((int)seg == pl.n_fwd - 1) && ((int)t == L - 1);
+      if (!stop)
+        for (uint32_t si = pl.succ_off[pl.win_base[seg] + win]; si < pl.succ_off[pl.win_base[seg] + win + 1]; ++si) {
+          const uint32_t s2 = pl.succ[si] >> 16, w2 = pl.succ[si] & 0xFFFFu;
+          const uint32_t c = ++depcnt[pl.item_base[s2] + mp * pl.n_windows[s2] + w2];
+          if (c == pl.need[pl.win_base[s2] + w2] * (t + 1)) { ready.push_back(((unsigned long long)(mp | (t << 16)) << 32) | pl.succ[si]); ++pushed; }
+        }
+      if ((int)seg == n_seg - 1 && (int)t < L - 1 && ++tails[mp] == pl.n_windows[seg] * (t + 1)) {
+        // all split-K parts of the row pair are in: both 128-row tiles run their momentum tail
+        for (uint32_t tile = 0; tile < LOOP_TAIL_NEED; ++tile)
+          for (uint32_t w2 = 0; w2 < pl.n_windows[0]; ++w2) {
+            const uint32_t c = ++depcnt[pl.item_base[0] + mp * pl.n_windows[0] + w2];
+            if (c == pl.need[pl.win_base[0] + w2] * (t + 1)) { ready.push_back(((unsigned long long)(mp | ((t + 1) << 16)) << 32) | w2); ++pushed; }
+          }
+      }
+      max_ready = std::max(max_ready, ready.size());
     }
-    if (remaining > 0) return fail("deadlock: some items can never start (dependency cycle across in-order streams)");
+    if (executed != loop_total_items(pl, L, false)) return fail("replay: not every item ran (an item never became ready)");
+    if (pushed != executed) return fail("replay: queue entries and executed items differ");
+    if (4 * (max_ready + (size_t)pl.n_pairs) > pl.q_cap) return fail("replay: the ready queue may hold more than a quarter of its capacity");
   }
   return 0;
 }

@@ -1,7 +1,7 @@
 """Where the roles of the persistent loop kernel spend their time (developer aid).
 Runs one projection under profile level 1 and prints, per role, the share of its loop spent waiting:
-producer (dependency flags / ring space), MMA issuer (operands / accumulator buffers), epilogue (accumulators / staging
-tile), store warp (tiles / store completion).   Usage: python tools/loop_stalls.py [dataset] [B] [L]"""
+producer (ready queue empty / ring space), MMA issuer (mailbox / operands / accumulator buffers), epilogue (accumulators /
+staging tile), store warp (tiles / store completion).   Usage: python tools/loop_stalls.py [dataset] [B] [L]"""
 import ctypes
 import os
 import sys
@@ -33,7 +33,7 @@ lib.dgan_debug_loop_stalls.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_
 buf = (ctypes.c_uint64 * (16 * 512))()
 n = lib.dgan_debug_loop_stalls(nat._handle, buf, 512)
 a = np.frombuffer(buf, dtype=np.uint64).reshape(512, 16)[:n].astype(np.float64)
-names = ["P_FLAG", "P_RING", "P_TOTAL", "M_FULL", "M_ACC", "M_TOTAL", "E_ACC", "E_TILE", "E_TOTAL", "S_TILE", "S_DONE", "S_TOTAL", "P_SLOW"]
+names = ["P_POP", "P_RING", "P_TOTAL", "M_FULL", "M_ACC", "M_TOTAL", "E_ACC", "E_TILE", "E_TOTAL", "S_TILE", "S_DONE", "S_TOTAL", "P_ITEMS", "M_MAIL"]
 lead = a[0::2]
 print("CTAs", n, "L", L, "status", nat.last_status())
 for k in prof:
@@ -41,8 +41,9 @@ for k in prof:
         print("  %-60s %9.1f us x %d" % (k["name"], 1e3 * k["ms"] / k["launches"], k["launches"]))
 tot = a[:, 2].mean()
 print("ticks per L-step (producer loop): %.0f" % (tot / L))
-for grp, keys, total in (("producer", (0, 1), 2), ("MMA (leader CTAs)", (3, 4), 5), ("epilogue", (6, 7), 8), ("store warp", (9, 10), 11)):
-    src = lead if grp.startswith("MMA") else a
+for grp, keys, total in (("producer (leader CTAs)", (0, 1), 2), ("MMA (leader CTAs)", (13, 3, 4), 5), ("epilogue", (6, 7), 8), ("store warp", (9, 10), 11)):
+    src = lead if "leader" in grp else a
     t = src[:, total].mean()
     print("%-18s total %10.0f ticks  " % (grp, t) + "  ".join("%s %5.1f%% (max %5.1f%%)" % (names[k], 100 * src[:, k].mean() / t, 100 * (src[:, k] / src[:, total]).max()) for k in keys))
-print("producer slow-path dependency waits per CTA per L-step: %.1f" % (a[:, 12].mean() / L))
+items = lead[:, 12]
+print("items per CTA pair: mean %.0f  min %.0f  max %.0f   (per L-step: %.1f)" % (items.mean(), items.min(), items.max(), items.mean() / L))
