@@ -729,7 +729,7 @@ static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, con
   const unsigned long long total = loop_total_items(pl, rec_iters, mode == LOOP_LOSS_GRAD);
   if (total + (unsigned long long)dp->n_pairs >= 0xFFFFFFFFull) { set_error("too many work items for one launch (batch x rec_rr x rec_iters)"); return DGAN_ERR_UNSUPPORTED; }
   P.n_items_total = (uint32_t)total;
-  DGAN_CUDA_CHECK(cudaMemsetAsync(w.status, 0, (8 + 2 * (size_t)pl.n_item_slots) * sizeof(uint32_t), s));
+  DGAN_CUDA_CHECK(cudaMemsetAsync(w.status, 0, (8 + 2 * w.n_counters) * sizeof(uint32_t), s));
   DGAN_CUDA_CHECK(cudaMemsetAsync(w.queue, 0xFF, (size_t)pl.q_cap * sizeof(unsigned long long), s));
   DGAN_CUDA_CHECK(cudaMemcpyAsync(w.queue, dp->q_init, pl.q_init.size() * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
   if (w.mom_counter != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.mom_counter, 0, (size_t)w.n_pad / kRowTile * sizeof(unsigned), s));

@@ -1,6 +1,7 @@
-"""Trace of one steady-state L-step of the persistent loop kernel (developer aid): for every item when its producer started
-waiting for its dependencies, when the wait ended, and when its epilogue began / ended; prints where the dependency
-waits are and which producing item each long wait was for.   Usage: python tools/loop_trace.py [dataset] [B] [L] [out.npz]"""
+"""Trace of one steady-state L-step of the persistent loop kernel (developer aid): for every item when a CTA pair took it
+from the ready queue, when its accumulator buffer was granted, and when its epilogue began / ended; prints per segment
+the ready -> taken -> done latencies and, per CTA pair, how much of the step it spent without an item in flight.
+Usage: python tools/loop_trace.py [dataset] [B] [L] [out.npz]"""
 import ctypes
 import os
 import sys
@@ -38,38 +39,49 @@ a = np.frombuffer(buf, dtype=np.uint64).reshape(MAXI, 8)[:n].astype(np.int64)
 deps = np.frombuffer(dbuf, dtype=np.int64).reshape(MAXI, MAXD)[:n]
 if out_path:
     np.savez_compressed(out_path, items=a, deps=deps, names=np.array(names))
-keep = a[:, 7] > 0                      # items of the two traced program entries (sections 1 and 2)
+keep = a[:, 7] > 0                      # items of the traced L-step
 idx_of = -np.ones(n, dtype=np.int64)
 idx_of[np.nonzero(keep)[0]] = np.arange(keep.sum())
 a = a[keep]
 deps = deps[keep]
 deps = np.where(deps >= 0, idx_of[np.clip(deps, 0, n - 1)], deps)
 n = len(a)
-t0 = a[:, 4][a[:, 4] > 0].min()
+t0 = a[:, 4][a[:, 4] > 0].min() & ((1 << 48) - 1)
 pair, seg, win, mp = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
-wb, we, eb, ee = [(a[:, 4 + k] - t0) / 1e3 for k in range(4)]           # us
-wait = we - wb
-print("items %d, traced step spans %.1f us (first wait begin -> last epilogue end)" % (n, ee.max()))
-print("dependency wait: total %.1f us over %d CTA pairs = %.1f us per pair; items waiting > 1 us: %d" % (
-    wait.sum(), len(set(pair)), wait.sum() / len(set(pair)), (wait > 1).sum()))
-for s in sorted(set(seg)):
-    m = seg == s
-    nph = len(names) - 1
-    print("  vseg %2d %s.%-26s items %4d  wait/pair %6.1f us  begin %7.1f..%7.1f  epilogue end %7.1f..%7.1f" % (
-        s, "AB"[s // nph], names[s % nph][:26], m.sum(), wait[m].sum() / len(set(pair)), wb[m].min(), wb[m].max(), ee[m].min(), ee[m].max()))
-order = np.argsort(-wait)[:25]
-print("longest waits: item (pair seg win mp) waited us | released by dep item (pair seg win mp) whose epilogue ended at, flag seen at")
-for e in order:
+pop, acc, eb, ee = [((a[:, 4 + k] & ((1 << 48) - 1)) - t0) / 1e3 for k in range(4)]           # us
+# ready time of an item = latest epilogue end among the items it waits for (store completion and queue hops come on top)
+ready = np.full(n, np.nan)
+for e in range(n):
     d = deps[e][deps[e] >= 0]
-    if len(d) == 0:
-        print("  %5d (%2d %d %3d %2d) %6.1f us | z update of the previous L-step" % (e, pair[e], seg[e], win[e], mp[e], wait[e]))
-        continue
-    last = d[np.argmax(ee[d])]
-    print("  %5d (%2d %d %3d %2d) %6.1f us [%.1f -> %.1f] | %5d (%2d %d %3d %2d) epilogue %.1f..%.1f" % (
-        e, pair[e], seg[e], win[e], mp[e], wait[e], wb[e], we[e], last, pair[last], seg[last], win[last], mp[last], eb[last], ee[last]))
-# per pair timeline summary
-busy = np.zeros(int(pair.max()) + 1)
-for p in range(len(busy)):
-    m = pair == p
-    busy[p] = wait[m].sum()
-print("per-pair dependency wait: min %.1f median %.1f max %.1f us" % (busy.min(), np.median(busy), busy.max()))
+    if len(d):
+        ready[e] = ee[d].max()
+lat = pop - ready
+print("items %d on %d CTA pairs, traced step spans %.1f us (first pop -> last epilogue end)" % (n, len(set(pair)), ee.max()))
+print("%-28s %5s %9s %9s %9s %9s %9s" % ("segment", "items", "pop-ready", "acc-pop", "epi-acc", "epi", "pop..end"))
+for sg in sorted(set(seg)):
+    m = seg == sg
+    print("%-28s %5d %9.1f %9.1f %9.1f %9.1f %9.1f   pops %7.1f..%7.1f  ends %7.1f..%7.1f" % (
+        names[sg][:28], m.sum(), np.nanmean(lat[m]) if np.isfinite(lat[m]).any() else float("nan"), (acc[m] - pop[m]).mean(),
+        (eb[m] - acc[m]).mean(), (ee[m] - eb[m]).mean(), (ee[m] - pop[m]).mean(), pop[m].min(), pop[m].max(), ee[m].min(), ee[m].max()))
+# per CTA pair: the union of [pop, epilogue end] intervals vs the span of the traced step
+span = ee.max() - pop.min()
+idle = []
+for p in sorted(set(pair)):
+    m = np.nonzero(pair == p)[0]
+    iv = sorted(zip(pop[m], ee[m]))
+    covered, cur_b, cur_e = 0.0, iv[0][0], iv[0][1]
+    for b_, e_ in iv[1:]:
+        if b_ > cur_e:
+            covered += cur_e - cur_b
+            cur_b, cur_e = b_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    covered += cur_e - cur_b
+    idle.append(span - covered)
+idle = np.array(idle)
+print("time without an item in flight per CTA pair: min %.1f median %.1f max %.1f us of %.1f us" % (idle.min(), np.median(idle), idle.max(), span))
+cnt = np.bincount(pair.astype(np.int64))
+print("items per CTA pair: min %d median %d max %d" % (cnt[cnt > 0].min(), np.median(cnt[cnt > 0]), cnt.max()))
+for m_ in sorted(set(mp)):
+    m = mp == m_
+    print("  row pair %2d: step runs %7.1f .. %7.1f us" % (m_, pop[m].min(), ee[m].max()))
