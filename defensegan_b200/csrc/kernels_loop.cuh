@@ -18,6 +18,12 @@
 // there is no static order that gives every dependency an independent separator.  With the queue, row pairs drift apart by
 // themselves and a CTA pair only idles when nothing at all is ready.
 //
+// Taking an item costs a chain of global round trips (queue index, queue slot, record offsets - about 2.5 us).  It is
+// paid by a FETCHER warp (the peer CTA's otherwise idle warp 1), which runs up to LOOP_AHEAD items ahead of the pair's TMA
+// producer and hands items - with their record range - to every role of both CTAs through a shared-memory mailbox; the
+// producer and the MMA issuer peek one mailbox entry ahead to have the next item's first records in registers when the
+// current item ends.
+//
 // Deadlock freedom: only ready items are ever taken, an item's completion never waits on anything but its own stores, and
 // the kernel ends through sentinels pushed when the last item has completed; the grid is sized to the co-resident
 // clusters (a CTA pair that is never scheduled would only leave items to the others).  Queue pops have a time-out that
@@ -40,7 +46,8 @@ constexpr int LOOP_RING_BYTES = tc2_ring_bytes(64, EPI_BIAS_RELU, 2);           
 constexpr int LOOP_BAR_BYTES = 512;                                            // mbarriers + mailbox
 constexpr int LOOP_SMEM_BYTES = LOOP_RING_BYTES + LOOP_EPI_TILES * TC2_TILE_BYTES + TC2_STAGING_BYTES + 1024 + LOOP_BAR_BYTES;
 static_assert(LOOP_SMEM_BYTES <= TC2_SMEM_MAX, "shared memory budget");
-constexpr int LOOP_MAIL = 8;                                // items a CTA pair's producer may run ahead of its slowest role
+constexpr int LOOP_MAIL = 8;                                // mailbox slots: items the fetcher may run ahead of the pair's slowest role
+constexpr int LOOP_AHEAD = 2;                               // items the fetcher may hold beyond the one the producer is issuing
 constexpr uint32_t LOOP_SENTINEL = 0x000F0000u;             // queue entry (segment 15) that ends a CTA pair
 constexpr uint32_t LOOP_LAP_SHIFT = 20, LOOP_LAP_MASK = 0x7FFu;   // entries carry the lap of their queue index (bits 20..30 of lo)
 constexpr unsigned long long LOOP_EMPTY = ~0ull;            // queue slot not written yet (lap field 0xFFF matches no lap)
@@ -139,6 +146,19 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t local_bar, u
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar), "r"(cta) : "memory");
 }
+__device__ __forceinline__ bool mbar_test_cluster(uint32_t bar, uint32_t parity) {   // non-blocking, acquire at cluster scope
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint32_t ld_shared_volatile_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope (peer's writes)
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -158,16 +178,18 @@ __device__ __forceinline__ void loop_publish_fence() {
 
 // per-CTA stall counters written when LoopParams::dbg != NULL (developer aid: tools/loop_stalls.py)
 enum LoopDbg : int { DBG_P_POP = 0, DBG_P_RING, DBG_P_TOTAL, DBG_M_FULL, DBG_M_ACC, DBG_M_TOTAL, DBG_E_ACC, DBG_E_TILE, DBG_E_TOTAL,
-                     DBG_S_TILE, DBG_S_DONE, DBG_S_TOTAL, DBG_P_ITEMS, DBG_M_MAIL, DBG_COUNT = 16 };
+                     DBG_S_TILE, DBG_S_DONE, DBG_S_TOTAL, DBG_P_ITEMS, DBG_M_MAIL, DBG_F_QUEUE, DBG_F_CREDIT, DBG_COUNT = 16 };
 
 // shared-memory control block of a CTA (offsets from bar_base)
 constexpr uint32_t LB_FULL = 0, LB_EMPTY = 64, LB_ACC_FULL = 128, LB_ACC_EMPTY = 144, LB_TMEM = 160, LB_TILE_FULL = 168,
-                   LB_TILE_FREE = 184, LB_MOM = 200, LB_MAIL_FULL = 256, LB_MAIL_EMPTY = 320, LB_MAIL_DATA = 384;
+                   LB_TILE_FREE = 184, LB_MOM = 200, LB_CREDIT = 204, LB_MAIL_FULL = 208, LB_MAIL_EMPTY = 272, LB_MAIL_DATA = 384;
+static_assert(LB_MAIL_DATA + 16 * LOOP_MAIL <= LOOP_BAR_BYTES, "control block");
 
-struct LoopItem { uint32_t seg, win, mp, t; };
+struct LoopItem { uint32_t seg, win, mp, t, rbeg, rend; };    // rbeg..rend: the window's step records
 __device__ __forceinline__ LoopItem loop_unpack(uint32_t lo, uint32_t hi) {
   LoopItem it;
   it.seg = (lo >> 16) & 0xFu; it.win = lo & 0xFFFFu; it.mp = hi & 0xFFFFu; it.t = hi >> 16;
+  it.rbeg = it.rend = 0;
   return it;
 }
 
@@ -178,20 +200,33 @@ __device__ __forceinline__ void loop_push(const LoopParams& P, uint32_t lo, uint
   ptx::st_release_gpu_u64(P.queue + (idx & (P.q_cap - 1u)), ((unsigned long long)hi << 32) | lo | (lap << LOOP_LAP_SHIFT));
 }
 
-// The item (seg, win, mp) of L-step t has completed (all its stores are in global memory): count it and wake what it
-// unblocks.  Called by a converged warp; the successor list is processed one successor per lane.
-__device__ __forceinline__ void loop_complete(const LoopParams& P, const LoopSeg& sg, uint32_t seg, uint32_t win, uint32_t mp, uint32_t t, int lane) {
+// Successors of a window, fetched ahead of the item's completion (one per lane; windows with more than 32 successors
+// loop in loop_complete): everything loop_complete needs from global memory that does not depend on the stores.
+struct LoopSucc { uint32_t s0, s1, e, need; };
+__device__ __forceinline__ LoopSucc loop_succ_prefetch(const LoopParams& P, const LoopSeg& sg, uint32_t win, int lane) {
+  LoopSucc q;
   const uint32_t wi = sg.win_base + win;
-  const uint32_t s0 = __ldg(P.succ_off + wi), s1 = __ldg(P.succ_off + wi + 1);
+  q.s0 = __ldg(P.succ_off + wi); q.s1 = __ldg(P.succ_off + wi + 1);
+  q.e = 0; q.need = 0;
+  if (q.s0 + (uint32_t)lane < q.s1) {
+    q.e = __ldg(P.succ + q.s0 + lane);
+    q.need = __ldg(P.need + P.seg[q.e >> 16].win_base + (q.e & 0xFFFFu));
+  }
+  return q;
+}
+
+// The item (seg, win, mp) of L-step t has completed (all its stores are in global memory): count it and wake what it
+// unblocks.  Called by a converged warp.
+__device__ __forceinline__ void loop_complete(const LoopParams& P, uint32_t seg, uint32_t mp, uint32_t t, int lane, const LoopSucc q) {
   // the backward half of the final L-step is never run: the loop returns the pre-update forward (models/gan.py:419-421)
   const bool stop = ((int)seg == P.n_fwd - 1) && ((int)t == P.last_step) && !P.full_last;
   if (!stop)
-    for (uint32_t s = s0 + (uint32_t)lane; s < s1; s += 32) {
-      const uint32_t e = __ldg(P.succ + s);
+    for (uint32_t s = q.s0 + (uint32_t)lane; s < q.s1; s += 32) {
+      uint32_t e = q.e, need = q.need;
+      if (s >= q.s0 + 32u) { e = __ldg(P.succ + s); need = __ldg(P.need + P.seg[e >> 16].win_base + (e & 0xFFFFu)); }
       const LoopSeg& sn = P.seg[e >> 16];
-      const uint32_t w2 = e & 0xFFFFu;
-      const uint32_t c = ptx::atom_add_acq_rel_gpu(P.depcnt + sn.item_base + mp * sn.n_windows + w2, 1u) + 1u;
-      if (c == __ldg(P.need + sn.win_base + w2) * (t + 1u)) loop_push(P, e, mp | (t << 16));
+      const uint32_t c = ptx::atom_add_acq_rel_gpu(P.depcnt + sn.item_base + mp * sn.n_windows + (e & 0xFFFFu), 1u) + 1u;
+      if (c == need * (t + 1u)) loop_push(P, e, mp | (t << 16));
     }
   __syncwarp();
   if (lane == 0) {
@@ -428,12 +463,13 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
       }
     }
     // every epilogue warp of both CTAs reports its share of the item; the last one wakes the successors
+    const LoopSucc sq = loop_succ_prefetch(P, sg, it.win, lane);
     loop_publish_fence();
     __syncwarp();
     uint32_t old = 0;
     if (lane == 0) old = ptx::atom_add_acq_rel_gpu(arrive, 1u);
     old = __shfl_sync(0xffffffffu, old, 0);
-    if (old + 1u == (2u * TC2_EPI_WARPS) * (it.t + 1u)) loop_complete(P, sg, it.seg, it.win, it.mp, it.t, lane);
+    if (old + 1u == (2u * TC2_EPI_WARPS) * (it.t + 1u)) loop_complete(P, it.seg, it.mp, it.t, lane, sq);
   }
 }
 
@@ -514,11 +550,12 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       ptx::mbar_init(bar_base + LB_TILE_FREE + 8 * b, 1);         // the half's store warp
     }
     for (int m = 0; m < LOOP_MAIL; ++m) {
-      ptx::mbar_init(bar_base + LB_MAIL_FULL + 8 * m, 1);         // the leader's producer, once per item (in both CTAs)
-      // readers of a mailbox slot, both CTAs (used on the leader only): MMA warp + 2 store warps + 8 epilogue warps of the
-      // leader, producer warp + 2 store warps + 8 epilogue warps of the peer
-      ptx::mbar_init(bar_base + LB_MAIL_EMPTY + 8 * m, 2 * (3 + TC2_EPI_WARPS));
+      ptx::mbar_init(bar_base + LB_MAIL_FULL + 8 * m, 1);         // the fetcher, once per item (in both CTAs)
+      // readers of a mailbox slot, both CTAs (used on the peer CTA, where the fetcher lives): producer + 2 store warps +
+      // 8 epilogue warps of each CTA, and the leader's MMA warp
+      ptx::mbar_init(bar_base + LB_MAIL_EMPTY + 8 * m, 2 * (3 + TC2_EPI_WARPS) + 1);
     }
+    ptx::st_shared_u32(bar_base + LB_CREDIT, 0u);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -530,17 +567,26 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // Every role of both CTAs learns the pair's k-th item from mailbox slot k % LOOP_MAIL (written by the leader's producer).
-  auto mail_read = [&](uint32_t k, bool cluster_acquire) -> LoopItem {
-    const uint32_t m = k & (LOOP_MAIL - 1), par = (k / LOOP_MAIL) & 1;
-    if (cluster_acquire) ptx::mbar_wait_cluster(bar_base + LB_MAIL_FULL + 8 * m, par);
-    else ptx::mbar_wait(bar_base + LB_MAIL_FULL + 8 * m, par);
-    const uint32_t lo = ptx::ld_shared_u32(bar_base + LB_MAIL_DATA + 8 * m), hi = ptx::ld_shared_u32(bar_base + LB_MAIL_DATA + 8 * m + 4);
+  // Every role of both CTAs learns the pair's k-th item from mailbox slot k % LOOP_MAIL (written by the fetcher, which lives
+  // in the peer CTA: the leader's roles acquire at cluster scope).
+  auto mail_take = [&](uint32_t k) -> LoopItem {                   // the slot is known to be full
+    const uint32_t m = k & (LOOP_MAIL - 1);
+    const uint4 d = ptx::ld_shared_v4(bar_base + LB_MAIL_DATA + 16 * m);
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive_remote(bar_base + LB_MAIL_EMPTY + 8 * m, 0);      // this warp is done with the slot
-    LoopItem it = loop_unpack(lo, hi);
-    if ((lo & 0xF0000u) == LOOP_SENTINEL) it.seg = 0xFFFFu;
+    if (lane == 0) ptx::mbar_arrive_remote(bar_base + LB_MAIL_EMPTY + 8 * m, 1);      // this warp is done with the slot
+    LoopItem it = loop_unpack(d.x, d.y);
+    it.rbeg = d.z; it.rend = d.w;
+    if ((d.x & 0xF0000u) == LOOP_SENTINEL) it.seg = 0xFFFFu;
     return it;
+  };
+  auto mail_read = [&](uint32_t k) -> LoopItem {
+    const uint32_t m = k & (LOOP_MAIL - 1), par = (k / LOOP_MAIL) & 1;
+    if (leader) ptx::mbar_wait_cluster(bar_base + LB_MAIL_FULL + 8 * m, par);
+    else ptx::mbar_wait(bar_base + LB_MAIL_FULL + 8 * m, par);
+    return mail_take(k);
+  };
+  auto mail_ready = [&](uint32_t k) -> bool {                      // non-blocking
+    return ptx::mbar_test_cluster(bar_base + LB_MAIL_FULL + 8 * (k & (LOOP_MAIL - 1)), (k / LOOP_MAIL) & 1);
   };
 
   if (warp < LOOP_EPI_WARP0) {
@@ -553,69 +599,37 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     LoopRing rs;
     long long t_pop = 0, t_ring = 0, n_items = 0;
     const long long t_p0 = P.dbg ? clock64() : 0;
-    for (uint32_t k = 0;; ++k) {
-      LoopItem cur;
-      if (leader) {
-        // ---- take the next ready item and tell everybody (both CTAs)
-        const uint32_t m = k & (LOOP_MAIL - 1);
-        const long long tw0 = P.dbg ? clock64() : 0;
-        if (k >= LOOP_MAIL) ptx::mbar_wait_cluster(bar_base + LB_MAIL_EMPTY + 8 * m, ((k / LOOP_MAIL) - 1) & 1);   // slot read by all 22 warps
-        uint32_t lo = 0, hi = 0;
-        if (lane == 0) {
-          const uint32_t idx = atomicAdd(P.q_ctl, 1u);
-          const unsigned long long* slot_p = P.queue + (idx & (P.q_cap - 1u));
-          const uint32_t lap = (idx >> P.q_shift) & LOOP_LAP_MASK;
-          unsigned long long e = ptx::ld_acquire_gpu_u64(slot_p);
-          if ((((uint32_t)e >> LOOP_LAP_SHIFT) & 0xFFFu) != lap) {
-            const unsigned long long t0 = ptx::globaltimer();
-            uint32_t spins = 0;
-            while (e = ptx::ld_acquire_gpu_u64(slot_p), (((uint32_t)e >> LOOP_LAP_SHIFT) & 0xFFFu) != lap) {
-              if ((++spins & 255u) == 0u) {
-                // nothing became ready for seconds: a broken plan or a faulted peer - give up instead of hanging the GPU
-                if (*reinterpret_cast<volatile uint32_t*>(P.status) != 0u || ptx::globaltimer() - t0 > 4000000000ull) {
-                  atomicExch(P.status, 1u);
-                  e = LOOP_SENTINEL;
-                  break;
-                }
-              }
-            }
-          }
-          e &= ~((unsigned long long)0xFFFu << LOOP_LAP_SHIFT);
-          lo = (uint32_t)e; hi = (uint32_t)(e >> 32);
-        }
-        lo = __shfl_sync(0xffffffffu, lo, 0); hi = __shfl_sync(0xffffffffu, hi, 0);
-        if (P.dbg) t_pop += clock64() - tw0;
-        if (lane == 0) {
-          ptx::st_shared_u32(bar_base + LB_MAIL_DATA + 8 * m, lo); ptx::st_shared_u32(bar_base + LB_MAIL_DATA + 8 * m + 4, hi);
-          ptx::st_shared_cluster_u32(bar_base + LB_MAIL_DATA + 8 * m, 1, lo); ptx::st_shared_cluster_u32(bar_base + LB_MAIL_DATA + 8 * m + 4, 1, hi);
-          ptx::mbar_arrive_remote_release(bar_base + LB_MAIL_FULL + 8 * m, 0);
-          ptx::mbar_arrive_remote_release(bar_base + LB_MAIL_FULL + 8 * m, 1);
-        }
-        __syncwarp();
-        cur = loop_unpack(lo, hi);
-        if ((lo & 0xF0000u) == LOOP_SENTINEL) break;
-        if (P.trace != nullptr && (int)cur.t == P.trace_step && lane == 0)
-          P.trace[(size_t)(P.seg[cur.seg].item_base + cur.mp * P.seg[cur.seg].n_windows + cur.win) * 4] =
-              (ptx::globaltimer() & 0xFFFFFFFFFFFFull) | ((unsigned long long)(blockIdx.x >> 1) << 48);
-        ptx::fence_proxy_async_all();                   // acquired generic-proxy view -> the TMA (async proxy) reads below
-      } else {
-        cur = mail_read(k, true);
-        if (cur.seg == 0xFFFFu) break;
-        ptx::fence_proxy_async_all();
-      }
+    LoopItem cur, nxt;
+    uint4 mine = make_uint4(0, 0, 0, 0), mine_nxt = make_uint4(0, 0, 0, 0);
+    bool have_nxt = false;
+    {
+      const long long tw0 = P.dbg ? clock64() : 0;
+      cur = mail_read(0);
+      if (P.dbg) t_pop += clock64() - tw0;
+      if (cur.seg != 0xFFFFu && 2 * cur.rbeg + lane < 2 * cur.rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + cur.rbeg) + lane);
+    }
+    for (uint32_t k = 0; cur.seg != 0xFFFFu; ++k) {
+      if (leader && lane == 0) ptx::st_shared_cluster_u32(bar_base + LB_CREDIT, 1, k + 1);      // the fetcher may move on
+      ptx::fence_proxy_async_all();                   // acquired generic-proxy view -> the TMA (async proxy) reads below
+      if (P.trace != nullptr && (int)cur.t == P.trace_step && lane == 0 && leader)
+        P.trace[(size_t)(P.seg[cur.seg].item_base + cur.mp * P.seg[cur.seg].n_windows + cur.win) * 4] =
+            (ptx::globaltimer() & 0xFFFFFFFFFFFFull) | ((unsigned long long)(blockIdx.x >> 1) << 48);
       ++n_items;
       const LoopSeg& sg = P.seg[cur.seg];
-      const uint32_t wi = sg.win_base + cur.win;
-      const uint32_t rbeg = __ldg(P.win_rec_off + wi), rend = __ldg(P.win_rec_off + wi + 1);
+      const uint32_t rbeg = cur.rbeg, rend = cur.rend;
       const uint32_t half_b = sg.half_b;
       const int n_half = (int)(sg.n_tile >> 1);
       const int row0 = (2 * (int)cur.mp + (int)rank) * kRowTile;
-      uint4 mine = make_uint4(0, 0, 0, 0);
-      if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
         __syncwarp();
         if (2 * (base + TC2_REC_BATCH) + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH) + lane);
+        // the next item, if the fetcher already has it: its first records travel while this item's loads are issued
+        if (!have_nxt && mail_ready(k + 1)) {
+          nxt = mail_take(k + 1);
+          have_nxt = true;
+          if (nxt.seg != 0xFFFFu && 2 * nxt.rbeg + lane < 2 * nxt.rend) mine_nxt = __ldg(reinterpret_cast<const uint4*>(stream + nxt.rbeg) + lane);
+        }
         const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
         for (uint32_t i = 0; i < cnt; ++i, ++it) {
           const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
@@ -650,6 +664,13 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         }
         __syncwarp();
       }
+      if (!have_nxt) {
+        const long long tw0 = P.dbg ? clock64() : 0;
+        nxt = mail_read(k + 1);
+        if (P.dbg) t_pop += clock64() - tw0;
+        if (nxt.seg != 0xFFFFu && 2 * nxt.rbeg + lane < 2 * nxt.rend) mine_nxt = __ldg(reinterpret_cast<const uint4*>(stream + nxt.rbeg) + lane);
+      }
+      cur = nxt; mine = mine_nxt; have_nxt = false;
     }
     // drain: nobody leaves while MMAs may still read this CTA's shared memory
     for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
@@ -660,8 +681,63 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_P_ITEMS] = (unsigned long long)n_items;
     }
    } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader) {
+    if (!leader) {
+      // ===================== fetcher (peer CTA's warp 1): ready queue -> mailbox of both CTAs =====================
+      long long t_wait = 0, t_credit = 0;
+      for (uint32_t k = 0;; ++k) {
+        const uint32_t m = k & (LOOP_MAIL - 1);
+        // not further than LOOP_AHEAD items beyond the one the producer is issuing (an item held here is an item no other
+        // CTA pair can take), and the mailbox slot must have been read by everybody
+        {
+          const long long tw0 = P.dbg ? clock64() : 0;
+          while (k > ptx::ld_shared_volatile_u32(bar_base + LB_CREDIT) + LOOP_AHEAD) __nanosleep(20);
+          if (k >= LOOP_MAIL) ptx::mbar_wait_cluster(bar_base + LB_MAIL_EMPTY + 8 * m, ((k / LOOP_MAIL) - 1) & 1);
+          if (P.dbg) t_credit += clock64() - tw0;
+        }
+        uint32_t lo = 0, hi = 0, rbeg = 0, rend = 0;
+        const long long tw1 = P.dbg ? clock64() : 0;
+        if (lane == 0) {
+          const uint32_t idx = atomicAdd(P.q_ctl, 1u);
+          const unsigned long long* slot_p = P.queue + (idx & (P.q_cap - 1u));
+          const uint32_t lap = (idx >> P.q_shift) & LOOP_LAP_MASK;
+          unsigned long long e = ptx::ld_acquire_gpu_u64(slot_p);
+          if ((((uint32_t)e >> LOOP_LAP_SHIFT) & 0xFFFu) != lap) {
+            const unsigned long long t0 = ptx::globaltimer();
+            uint32_t spins = 0;
+            while (e = ptx::ld_acquire_gpu_u64(slot_p), (((uint32_t)e >> LOOP_LAP_SHIFT) & 0xFFFu) != lap) {
+              if ((++spins & 255u) == 0u) {
+                // nothing became ready for seconds: a broken plan or a faulted peer - give up instead of hanging the GPU
+                if (*reinterpret_cast<volatile uint32_t*>(P.status) != 0u || ptx::globaltimer() - t0 > 4000000000ull) {
+                  atomicExch(P.status, 1u);
+                  e = LOOP_SENTINEL;
+                  break;
+                }
+              }
+            }
+          }
+          e &= ~((unsigned long long)0xFFFu << LOOP_LAP_SHIFT);
+          lo = (uint32_t)e; hi = (uint32_t)(e >> 32);
+          if ((lo & 0xF0000u) != LOOP_SENTINEL) {
+            const uint32_t wi = P.seg[lo >> 16].win_base + (lo & 0xFFFFu);
+            rbeg = __ldg(P.win_rec_off + wi); rend = __ldg(P.win_rec_off + wi + 1);
+          }
+          const uint32_t da = bar_base + LB_MAIL_DATA + 16 * m;
+          ptx::st_shared_u32(da, lo); ptx::st_shared_u32(da + 4, hi); ptx::st_shared_u32(da + 8, rbeg); ptx::st_shared_u32(da + 12, rend);
+          ptx::st_shared_cluster_u32(da, 0, lo); ptx::st_shared_cluster_u32(da + 4, 0, hi);
+          ptx::st_shared_cluster_u32(da + 8, 0, rbeg); ptx::st_shared_cluster_u32(da + 12, 0, rend);
+          ptx::mbar_arrive_remote_release(bar_base + LB_MAIL_FULL + 8 * m, 0);
+          ptx::mbar_arrive_remote_release(bar_base + LB_MAIL_FULL + 8 * m, 1);
+        }
+        lo = __shfl_sync(0xffffffffu, lo, 0);
+        if (P.dbg) t_wait += clock64() - tw1;
+        if ((lo & 0xF0000u) == LOOP_SENTINEL) break;
+      }
+      if (P.dbg && lane == 0) {
+        P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_F_QUEUE] = (unsigned long long)t_wait;
+        P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_F_CREDIT] = (unsigned long long)t_credit;
+      }
+    } else {
+      // ===================== MMA issuer (leader CTA only) =====================
       const TcRec* __restrict__ stream = P.tmpl_m;
       const uint32_t ring = stg_base + TC2_REC_BATCH * (uint32_t)sizeof(TcRec);
       const uint64_t desc0 = make_smem_desc_sw128(smem_base);
@@ -670,18 +746,20 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       LoopRing rs;
       long long t_full = 0, t_acc = 0, t_mail = 0;
       const long long t_m0 = P.dbg ? clock64() : 0;
-      for (uint32_t k = 0;; ++k) {
+      LoopItem cur, nxt;
+      uint4 mine = make_uint4(0, 0, 0, 0), mine_nxt = make_uint4(0, 0, 0, 0);
+      bool have_nxt = false;
+      {
         const long long tm0 = P.dbg ? clock64() : 0;
-        const LoopItem cur = mail_read(k, false);
+        cur = mail_read(0);
         if (P.dbg) t_mail += clock64() - tm0;
-        if (cur.seg == 0xFFFFu) break;
+        if (cur.seg != 0xFFFFu && 2 * cur.rbeg + lane < 2 * cur.rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + cur.rbeg) + lane);
+      }
+      for (uint32_t k = 0; cur.seg != 0xFFFFu; ++k) {
         const LoopSeg& sg = P.seg[cur.seg];
         const uint32_t idesc = sg.idesc, acc_stride = sg.acc_stride, half_b = sg.half_b, half_b16 = half_b >> 4, n_merge = (sg.n_tile >> 3) << 17;
-        const uint32_t wi = sg.win_base + cur.win;
-        const uint32_t rbeg = __ldg(P.win_rec_off + wi), rend = __ldg(P.win_rec_off + wi + 1);
+        const uint32_t rbeg = cur.rbeg, rend = cur.rend;
         const uint32_t buf = item_count & 1;
-        uint4 mine = make_uint4(0, 0, 0, 0);
-        if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);
         {                                                       // the item's accumulator buffer must be drained
           const long long ta0 = P.dbg ? clock64() : 0;
           ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
@@ -693,6 +771,11 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
           ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
           __syncwarp();
           if (2 * (base + TC2_REC_BATCH) + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH) + lane);
+          if (!have_nxt && mail_ready(k + 1)) {
+            nxt = mail_take(k + 1);
+            have_nxt = true;
+            if (nxt.seg != 0xFFFFu && 2 * nxt.rbeg + lane < 2 * nxt.rend) mine_nxt = __ldg(reinterpret_cast<const uint4*>(stream + nxt.rbeg) + lane);
+          }
           const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
           for (uint32_t i = 0; i < cnt; ++i, ++it) {
             const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
@@ -734,6 +817,13 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
           __syncwarp();
         }
         ++item_count;
+        if (!have_nxt) {
+          const long long tm0 = P.dbg ? clock64() : 0;
+          nxt = mail_read(k + 1);
+          if (P.dbg) t_mail += clock64() - tm0;
+          if (nxt.seg != 0xFFFFu && 2 * nxt.rbeg + lane < 2 * nxt.rend) mine_nxt = __ldg(reinterpret_cast<const uint4*>(stream + nxt.rbeg) + lane);
+        }
+        cur = nxt; mine = mine_nxt; have_nxt = false;
       }
       // drain: observe the release of the last (up to two) accumulator buffers by the epilogue warps of both CTAs
       for (uint32_t j = item_count > 2 ? item_count - 2 : 0; j < item_count; ++j) ptx::mbar_wait(bar_acc_empty + 8 * (j & 1), (j >> 1) & 1);
@@ -756,13 +846,14 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     long long t_tile = 0, t_done = 0;
     const long long t_s0 = P.dbg ? clock64() : 0;
     for (uint32_t k = 0;; ++k) {
-      const LoopItem cur = mail_read(k, !leader);
+      const LoopItem cur = mail_read(k);
       if (cur.seg == 0xFFFFu) break;
       const LoopSeg& sg = P.seg[cur.seg];
       if (!(sg.kind <= LK_NONE64H)) continue;                    // fp32 / last-layer epilogues store (and report) themselves
       const TcItem2* ip = sg.items + cur.win;
       const int G = (int)(sg.n_tile >> 6), n_units = (int)__ldg(&ip->n_acc) * G;
       const int row0 = (2 * (int)cur.mp + (int)rank) * kRowTile;
+      const LoopSucc sq = loop_succ_prefetch(P, sg, cur.win, lane);     // in flight while the tiles are stored
       uint32_t old = 0;
       if (lane == 0) {
         for (int u = h; u < n_units; u += 2) {
@@ -783,7 +874,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         if (P.dbg) t_done += clock64() - tw1;
       }
       old = __shfl_sync(0xffffffffu, old, 0);
-      if (old + 1u == 4u * (cur.t + 1u)) loop_complete(P, sg, cur.seg, cur.win, cur.mp, cur.t, lane);   // 2 halves x 2 CTAs per execution
+      if (old + 1u == 4u * (cur.t + 1u)) loop_complete(P, cur.seg, cur.mp, cur.t, lane, sq);   // 2 halves x 2 CTAs per execution
     }
     if (P.dbg && lane == 0) {
       P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_TILE] = (unsigned long long)t_tile;    // (warp 3 overwrites warp 2: same order of magnitude)
@@ -802,7 +893,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
     fa.x = P.x; fa.y = P.y; fa.loss_part = P.loss_part; fa.R = P.R; fa.B = P.B; fa.n_rows = P.n_rows; fa.nbx = P.nbx; fa.w_out = P.w_out;
     fa.gscale = P.gscale; fa.m_gmul = P.m_gmul; fa.m_mu = P.m_mu;
     for (uint32_t k = 0;; ++k, ++cx.item_count) {
-      const LoopItem cur = mail_read(k, !leader);
+      const LoopItem cur = mail_read(k);
       if (cur.seg == 0xFFFFu) break;
       const LoopSeg& sg = P.seg[cur.seg];
       const int t = (int)cur.t;

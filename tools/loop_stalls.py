@@ -33,7 +33,7 @@ lib.dgan_debug_loop_stalls.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_
 buf = (ctypes.c_uint64 * (16 * 512))()
 n = lib.dgan_debug_loop_stalls(nat._handle, buf, 512)
 a = np.frombuffer(buf, dtype=np.uint64).reshape(512, 16)[:n].astype(np.float64)
-names = ["P_POP", "P_RING", "P_TOTAL", "M_FULL", "M_ACC", "M_TOTAL", "E_ACC", "E_TILE", "E_TOTAL", "S_TILE", "S_DONE", "S_TOTAL", "P_ITEMS", "M_MAIL"]
+names = ["P_POP", "P_RING", "P_TOTAL", "M_FULL", "M_ACC", "M_TOTAL", "E_ACC", "E_TILE", "E_TOTAL", "S_TILE", "S_DONE", "S_TOTAL", "P_ITEMS", "M_MAIL", "F_QUEUE", "F_CREDIT"]
 lead = a[0::2]
 print("CTAs", n, "L", L, "status", nat.last_status())
 for k in prof:
@@ -45,5 +45,8 @@ for grp, keys, total in (("producer (leader CTAs)", (0, 1), 2), ("MMA (leader CT
     src = lead if "leader" in grp else a
     t = src[:, total].mean()
     print("%-18s total %10.0f ticks  " % (grp, t) + "  ".join("%s %5.1f%% (max %5.1f%%)" % (names[k], 100 * src[:, k].mean() / t, 100 * (src[:, k] / src[:, total]).max()) for k in keys))
+peer = a[1::2]
+print("fetcher (peer CTAs): waiting for a ready item %5.1f%%, for credit / a free mailbox slot %5.1f%% of the kernel" % (
+    100 * peer[:, 14].mean() / lead[:, 2].mean(), 100 * peer[:, 15].mean() / lead[:, 2].mean()))
 items = lead[:, 12]
 print("items per CTA pair: mean %.0f  min %.0f  max %.0f   (per L-step: %.1f)" % (items.mean(), items.min(), items.max(), items.mean() / L))
