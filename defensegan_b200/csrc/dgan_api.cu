@@ -253,8 +253,8 @@ struct Workspace {
   __half* z_h = nullptr;
   std::vector<unsigned long long*> maskbits;   // fp16 path: 1-bit ReLU masks per hidden layer output
   unsigned* mom_counter = nullptr;     // fp16 path: [n_pad / 128] tickets of the split-K Linear backward's momentum tail
-  // fp16 path, the loop kernel's scheduling state: [status(4) | q_ctl(4) | arrive(n_counters) | depcnt(n_counters)] and the queue
-  uint32_t *status = nullptr, *q_ctl = nullptr, *arrive = nullptr, *depcnt = nullptr;
+  // fp16 path, the loop kernel's scheduling state: [status(4) | q_ctl(4) | depcnt(n_counters)] and the queue
+  uint32_t *status = nullptr, *q_ctl = nullptr, *depcnt = nullptr;
   unsigned long long* queue = nullptr;
   size_t n_counters = 0, q_cap = 0;
   __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
@@ -285,13 +285,13 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   if (tc) w.z_h = (__half*)take(np * latent * 2);
   if (tc) w.mom_counter = (unsigned*)take(np / kRowTile * sizeof(unsigned));
   if (tc) {
-    // two counters per (segment, window, row pair); a window holds at least one output pixel, which bounds the plan's
+    // one counter per (segment, window, row pair); a window holds at least one output pixel, which bounds the plan's
     // needs whatever tiling it picks (the queue capacity follows loop_plan's rule on that bound)
     size_t per_mp = 0;
     for (const LoopSegSpec& sp : c->segs) per_mp += sp.tab->off.size() - 1;
     w.n_counters = per_mp * (np / (2 * kRowTile));
-    w.status = (uint32_t*)take((8 + 2 * w.n_counters) * sizeof(uint32_t));
-    if (w.status != nullptr) { w.q_ctl = w.status + 4; w.arrive = w.status + 8; w.depcnt = w.arrive + w.n_counters; }
+    w.status = (uint32_t*)take((8 + w.n_counters) * sizeof(uint32_t));
+    if (w.status != nullptr) { w.q_ctl = w.status + 4; w.depcnt = w.status + 8; }
     w.q_cap = 1024;
     while (w.q_cap < 4 * (w.n_counters + (size_t)c->n_pairs) + 64) w.q_cap <<= 1;
     w.queue = (unsigned long long*)take(w.q_cap * sizeof(unsigned long long));
@@ -692,7 +692,7 @@ static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, co
   }
   P.tmpl_p[0] = dp->tmpl_p[0]; P.tmpl_p[1] = dp->tmpl_p[1]; P.tmpl_m = dp->tmpl_m;
   P.win_rec_off = dp->win_rec_off; P.succ_off = dp->succ_off; P.succ = dp->succ; P.need = dp->need;
-  P.queue = w.queue; P.q_ctl = w.q_ctl; P.arrive = w.arrive; P.depcnt = w.depcnt;
+  P.queue = w.queue; P.q_ctl = w.q_ctl; P.depcnt = w.depcnt;
   P.q_cap = pl.q_cap; P.q_shift = 0;
   while ((1u << P.q_shift) < pl.q_cap) ++P.q_shift;
   P.q_init = (uint32_t)pl.q_init.size(); P.n_pairs = (uint32_t)dp->n_pairs;
@@ -726,10 +726,10 @@ static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, con
   P.decay_step = decay_lr ? (int)std::ceil(rec_iters * 0.8) : 0;
   P.last_step = rec_iters - 1;
   P.full_last = (mode == LOOP_LOSS_GRAD) ? 1 : 0;
-  const unsigned long long total = loop_total_items(pl, rec_iters, mode == LOOP_LOSS_GRAD);
+  const unsigned long long total = loop_total_parts(c->segs, pl, rec_iters, mode == LOOP_LOSS_GRAD);
   if (total + (unsigned long long)dp->n_pairs >= 0xFFFFFFFFull) { set_error("too many work items for one launch (batch x rec_rr x rec_iters)"); return DGAN_ERR_UNSUPPORTED; }
-  P.n_items_total = (uint32_t)total;
-  DGAN_CUDA_CHECK(cudaMemsetAsync(w.status, 0, (8 + 2 * w.n_counters) * sizeof(uint32_t), s));
+  P.n_parts_total = (uint32_t)total;
+  DGAN_CUDA_CHECK(cudaMemsetAsync(w.status, 0, (8 + w.n_counters) * sizeof(uint32_t), s));
   DGAN_CUDA_CHECK(cudaMemsetAsync(w.queue, 0xFF, (size_t)pl.q_cap * sizeof(unsigned long long), s));
   DGAN_CUDA_CHECK(cudaMemcpyAsync(w.queue, dp->q_init, pl.q_init.size() * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
   if (w.mom_counter != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.mom_counter, 0, (size_t)w.n_pad / kRowTile * sizeof(unsigned), s));
@@ -1323,7 +1323,8 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
   for (int v = 0; v < plan.n_seg; ++v)
     sum += " [" + segs[(size_t)v].name + " window " +
            std::to_string(plan.shape[4 * v]) + "x" + std::to_string(plan.shape[4 * v + 1]) + " stride " + std::to_string(plan.shape[4 * v + 2]) + "x" +
-           std::to_string(plan.shape[4 * v + 3]) + ", " + std::to_string(plan.hdrs[(size_t)v].size()) + " windows]";
+           std::to_string(plan.shape[4 * v + 3]) + ", " + std::to_string(plan.hdrs[(size_t)v].size()) + " windows, cost " +
+           std::to_string((int)(plan.cost_total[(size_t)v] / 1024)) + " KB, largest item " + std::to_string((int)(plan.cost_max[(size_t)v] / 1024)) + " KB]";
   sum += " x " + std::to_string(plan.n_mpairs) + " row pairs; per L-step: " + std::to_string(plan.n_steps) + " steps, " + std::to_string(plan.n_mma) + " MMAs, " +
          std::to_string(2.0 * plan.n_bytes / 1e6) + " MB staged, " + std::to_string((size_t)(plan.win_fwd + plan.win_bwd) * plan.n_mpairs) + " items, " +
          std::to_string(plan.succ.size()) + " graph edges per row pair, queue capacity " + std::to_string(plan.q_cap);

@@ -47,7 +47,9 @@ constexpr int LOOP_BAR_BYTES = 512;                                            /
 constexpr int LOOP_SMEM_BYTES = LOOP_RING_BYTES + LOOP_EPI_TILES * TC2_TILE_BYTES + TC2_STAGING_BYTES + 1024 + LOOP_BAR_BYTES;
 static_assert(LOOP_SMEM_BYTES <= TC2_SMEM_MAX, "shared memory budget");
 constexpr int LOOP_MAIL = 8;                                // mailbox slots: items the fetcher may run ahead of the pair's slowest role
-constexpr int LOOP_AHEAD = 2;                               // items the fetcher may hold beyond the one the producer is issuing
+constexpr int LOOP_AHEAD = 2;                               // items the fetcher may hold beyond the one the producer is issuing - while
+                                                            // the queue has a backlog; when other pairs are waiting for work it only
+                                                            // takes the next item once the producer has issued the current one
 constexpr uint32_t LOOP_SENTINEL = 0x000F0000u;             // queue entry (segment 15) that ends a CTA pair
 constexpr uint32_t LOOP_LAP_SHIFT = 20, LOOP_LAP_MASK = 0x7FFu;   // entries carry the lap of their queue index (bits 20..30 of lo)
 constexpr unsigned long long LOOP_EMPTY = ~0ull;            // queue slot not written yet (lap field 0xFFF matches no lap)
@@ -86,8 +88,7 @@ struct LoopParams {
   const uint32_t* need;            // [windows] completions of producing items a window waits for, per L-step
   unsigned long long* queue;       // ready queue: lo = lap << 20 | segment << 16 | window, hi = row pair | L-step << 16
   uint32_t* q_ctl;                 // [0] popped, [1] pushed, [2] completed items
-  uint32_t* arrive;                // per item: completions of its epilogue parts (4 store warps or 16 epilogue warps per execution)
-  uint32_t* depcnt;                // per item: completions of the items it waits for
+  uint32_t* depcnt;                // per item: completed parts of the items it waits for
   uint32_t* status;                // [0] != 0: a queue pop timed out (results invalid)
   unsigned long long* prof;        // optional [L-step][n_seg][2] globaltimer min-start / max-end of the epilogues
   unsigned long long* dbg;         // optional [CTA][16] stall counters of the roles (clock64 ticks), see LoopDbg
@@ -95,7 +96,7 @@ struct LoopParams {
   uint32_t q_cap, q_shift, n_pairs; // queue capacity = 1 << q_shift
   uint32_t q_init;                 // entries the host placed in the queue (the first segment's items of L-step 0): pushes start behind them
   int trace_step;
-  uint32_t n_items_total;          // items of the whole launch: the completion of the last one pushes the sentinels
+  uint32_t n_parts_total;          // item parts of the whole launch: the completion of the last one pushes the sentinels
   int n_seg, n_fwd;                // segments; the first n_fwd are the generator forward (+ loss)
   int last_step;                   // index of the call's final L-step (rec_iters - 1): its forward writes G(z) and the loss
   int full_last;                   // 1: the final L-step also runs its backward half (dgan_loss_grad); 0: forward only
@@ -215,8 +216,10 @@ __device__ __forceinline__ LoopSucc loop_succ_prefetch(const LoopParams& P, cons
   return q;
 }
 
-// The item (seg, win, mp) of L-step t has completed (all its stores are in global memory): count it and wake what it
-// unblocks.  Called by a converged warp.
+// One PART of the item (seg, win, mp) of L-step t has completed (this warp's share of its stores is in global memory): an
+// item has 4 parts (the store warps of both CTAs) when its epilogue stores by TMA, else 16 (the epilogue warps).  Every part
+// bumps the successors' counters itself - `need` is in parts - so the last part to finish wakes them without a second
+// round trip through an arrival counter.  Called by a converged warp.
 __device__ __forceinline__ void loop_complete(const LoopParams& P, uint32_t seg, uint32_t mp, uint32_t t, int lane, const LoopSucc q) {
   // the backward half of the final L-step is never run: the loop returns the pre-update forward (models/gan.py:419-421)
   const bool stop = ((int)seg == P.n_fwd - 1) && ((int)t == P.last_step) && !P.full_last;
@@ -231,7 +234,7 @@ __device__ __forceinline__ void loop_complete(const LoopParams& P, uint32_t seg,
   __syncwarp();
   if (lane == 0) {
     const uint32_t d = atomicAdd(P.q_ctl + 2, 1u) + 1u;
-    if (d == P.n_items_total)
+    if (d == P.n_parts_total)
       for (uint32_t k = 0; k < P.n_pairs; ++k) loop_push(P, LOOP_SENTINEL, 0u);
   }
 }
@@ -394,7 +397,6 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
   if (TMA_EPI) {
     // reported by the half's store warp once the item's tile stores have completed
   } else {
-    uint32_t* arrive = P.arrive + sg.item_base + (uint32_t)mp * sg.n_windows + (uint32_t)win;
     if (EPI == EPI_NONE && sizeof(TOUT) == 4 && P.m_counter != nullptr) {
       // ---- momentum in the tail of the split-K Linear backward (tf.train.MomentumOptimizer, models/gan.py:389-391).
       //      Every epilogue thread has stored its share of this item's partial sums; the CTA that completes the last
@@ -462,14 +464,11 @@ __device__ __forceinline__ void loop_epilogue_item(const LoopParams& P, const Lo
         }
       }
     }
-    // every epilogue warp of both CTAs reports its share of the item; the last one wakes the successors
+    // every epilogue warp of both CTAs reports its share of the item; the last one to do so wakes the successors
     const LoopSucc sq = loop_succ_prefetch(P, sg, it.win, lane);
     loop_publish_fence();
     __syncwarp();
-    uint32_t old = 0;
-    if (lane == 0) old = ptx::atom_add_acq_rel_gpu(arrive, 1u);
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old + 1u == (2u * TC2_EPI_WARPS) * (it.t + 1u)) loop_complete(P, it.seg, it.mp, it.t, lane, sq);
+    loop_complete(P, it.seg, it.mp, it.t, lane, sq);
   }
 }
 
@@ -609,7 +608,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       if (cur.seg != 0xFFFFu && 2 * cur.rbeg + lane < 2 * cur.rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + cur.rbeg) + lane);
     }
     for (uint32_t k = 0; cur.seg != 0xFFFFu; ++k) {
-      if (leader && lane == 0) ptx::st_shared_cluster_u32(bar_base + LB_CREDIT, 1, k + 1);      // the fetcher may move on
+      if (leader && lane == 0) ptx::st_shared_cluster_u32(bar_base + LB_CREDIT, 1, 2 * k + 1);  // item k started (fetcher's credit)
       ptx::fence_proxy_async_all();                   // acquired generic-proxy view -> the TMA (async proxy) reads below
       if (P.trace != nullptr && (int)cur.t == P.trace_step && lane == 0 && leader)
         P.trace[(size_t)(P.seg[cur.seg].item_base + cur.mp * P.seg[cur.seg].n_windows + cur.win) * 4] =
@@ -664,6 +663,7 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         }
         __syncwarp();
       }
+      if (leader && lane == 0) ptx::st_shared_cluster_u32(bar_base + LB_CREDIT, 1, 2 * k + 2);  // item k issued
       if (!have_nxt) {
         const long long tw0 = P.dbg ? clock64() : 0;
         nxt = mail_read(k + 1);
@@ -690,7 +690,16 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         // CTA pair can take), and the mailbox slot must have been read by everybody
         {
           const long long tw0 = P.dbg ? clock64() : 0;
-          while (k > ptx::ld_shared_volatile_u32(bar_base + LB_CREDIT) + LOOP_AHEAD) __nanosleep(20);
+          // credit = 2j+1: the producer has started item j; 2j+2: it has issued all of item j's loads
+          for (;;) {
+            const uint32_t credit = ptx::ld_shared_volatile_u32(bar_base + LB_CREDIT);
+            if (2 * k <= credit) break;                                   // item k-1 fully issued (or k = 0): always allowed
+            if (2 * k <= credit + 1 + 2 * (uint32_t)LOOP_AHEAD) {         // within the look-ahead window: only with a backlog
+              const uint32_t claimed = *reinterpret_cast<volatile uint32_t*>(P.q_ctl), pushed = *reinterpret_cast<volatile uint32_t*>(P.q_ctl + 1) + P.q_init;
+              if ((int)(pushed - claimed) > (int)P.n_pairs) break;
+            }
+            __nanosleep(40);
+          }
           if (k >= LOOP_MAIL) ptx::mbar_wait_cluster(bar_base + LB_MAIL_EMPTY + 8 * m, ((k / LOOP_MAIL) - 1) & 1);
           if (P.dbg) t_credit += clock64() - tw0;
         }
@@ -854,7 +863,6 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
       const int G = (int)(sg.n_tile >> 6), n_units = (int)__ldg(&ip->n_acc) * G;
       const int row0 = (2 * (int)cur.mp + (int)rank) * kRowTile;
       const LoopSucc sq = loop_succ_prefetch(P, sg, cur.win, lane);     // in flight while the tiles are stored
-      uint32_t old = 0;
       if (lane == 0) {
         for (int u = h; u < n_units; u += 2) {
           const int q = (int)__ldg(&ip->q[u / G]);
@@ -870,11 +878,10 @@ projection_loop_kernel(const __grid_constant__ LoopParams P) {
         const long long tw1 = P.dbg ? clock64() : 0;
         ptx::bulk_wait_all0();                                    // the item's tiles are in global memory
         loop_publish_fence();
-        old = ptx::atom_add_acq_rel_gpu(P.arrive + sg.item_base + cur.mp * sg.n_windows + cur.win, 1u);
         if (P.dbg) t_done += clock64() - tw1;
       }
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old + 1u == 4u * (cur.t + 1u)) loop_complete(P, cur.seg, cur.mp, cur.t, lane, sq);   // 2 halves x 2 CTAs per execution
+      __syncwarp();
+      loop_complete(P, cur.seg, cur.mp, cur.t, lane, sq);         // one of the item's 4 parts (2 halves x 2 CTAs)
     }
     if (P.dbg && lane == 0) {
       P.dbg[(size_t)blockIdx.x * DBG_COUNT + DBG_S_TILE] = (unsigned long long)t_tile;    // (warp 3 overwrites warp 2: same order of magnitude)
@@ -949,6 +956,7 @@ struct LoopPlan {
   int n_seg = 0, n_fwd = 0, n_pairs = 0, n_mpairs = 0;
   std::vector<std::vector<TcItem2>> hdrs;         // per segment: window headers
   std::vector<int> shape;                         // per segment: wh, ww, sy, sx
+  std::vector<double> cost_total, cost_max;       // per segment: planner's cost of one row pair's items / of its largest item (bytes)
   std::vector<uint32_t> win_base, item_base, n_windows;     // per segment
   uint32_t n_win = 0, n_item_slots = 0;           // windows of all segments; counters = windows x row pairs
   std::vector<TcRec> tmpl_p[2], tmpl_m;           // windows back to back in (segment, window) order
@@ -968,19 +976,32 @@ struct LoopPlan {
 #endif
 constexpr int LOOP_STEP_MAX_BYTES = 48 * 1024;    // measured optimum of the operand-ring kernels (round 1): 2 A tiles + weights
 constexpr uint32_t LOOP_TAIL_NEED = 2;            // the first segment waits for the momentum tails of the row pair's two 128-row tiles
+constexpr uint32_t LOOP_PARTS_TMA = 4, LOOP_PARTS_WARPS = 2 * TC2_EPI_WARPS;     // completion parts of an item (see loop_complete)
+static inline uint32_t loop_parts_of(int kind) { return kind <= LK_NONE64H ? LOOP_PARTS_TMA : LOOP_PARTS_WARPS; }
 
 static double loop_item_cost(const Tc2HostItem& it, int N) {
   return it.stage_bytes + DGAN_COST_EPI_KB * 1024.0 * it.hdr.n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;
 }
 
-// Window tiling of one segment: every candidate shape (wh x ww accumulators, strides 1 or 2 - stride 2 gathers outputs of
-// equal parity of a stride-2 transposed conv, which share weight tiles) is scored by the makespan of a greedy
-// longest-first assignment of its items to the CTA pairs (cost = operand bytes staged + a per-accumulator epilogue
-// charge + a fixed per-item charge): total cost matters most, the makespan term keeps the items fine enough to balance.
-static int loop_choose_tiling(const LoopSegSpec& sp, int n_mps, int n_pairs, std::vector<Tc2HostItem>* items_out, int shape_out[4]) {
+// Window tiling of one segment.  Every candidate shape (wh x ww accumulators, strides 1 or 2 - stride 2 gathers outputs
+// of equal parity of a stride-2 transposed conv, which share weight tiles) is scored by a proxy of what it adds to the
+// L-step:  (sum of item costs) x row pairs / CTA pairs   - its share of the machine's time when everything is busy -
+//   plus  alpha x (largest item cost)                    - what it adds to a row pair's critical path (a row pair's
+// segments run one after the other, and with few row pairs in flight the chain, not the machine, sets the pace).
+// Item cost = operand bytes staged + a per-accumulator epilogue charge + a fixed per-item charge.
+#ifndef DGAN_TILE_ALPHA
+#define DGAN_TILE_ALPHA 1.0
+#endif
+static double loop_tile_alpha() {
+  const char* e = std::getenv("DGAN_TILE_ALPHA");        // developer knob (planner experiments)
+  return e ? std::atof(e) : (double)DGAN_TILE_ALPHA;
+}
+static int loop_choose_tiling(const LoopSegSpec& sp, int n_mps, int n_pairs, std::vector<Tc2HostItem>* items_out, int shape_out[4],
+                              double* total_out = nullptr, double* max_out = nullptr) {
   const int N = sp.N, K = sp.K;
   const int max_g = (N >= 64) ? std::min(4, 256 / N) : 1;
   const int step_max = std::min((LOOP_RING_BYTES / 2) & ~1023, LOOP_STEP_MAX_BYTES);
+  const double alpha = loop_tile_alpha();
   double best_cost = 1e300;
   std::vector<Tc2HostItem> best_items;
   std::vector<std::vector<int>> wins;
@@ -992,23 +1013,19 @@ static int loop_choose_tiling(const LoopSegSpec& sp, int n_mps, int n_pairs, std
           tc2_enumerate_windows(sp.h_grid, std::max(sp.w_grid, 1), wh, ww, sy, sx, &wins);
           if (wins.size() > 0xFFFFu) continue;
           std::vector<Tc2HostItem> items(wins.size());
-          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(*sp.tab, wins[i], N, K, max_g, TC2_MAX_A, step_max, &items[i]);
-          std::vector<size_t> order(items.size());
-          for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-          std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return items[l].stage_bytes > items[r].stage_bytes; });
-          std::vector<double> load((size_t)n_pairs, 0.0);
-          for (size_t oi = 0; oi < order.size(); ++oi)
-            for (int m = 0; m < n_mps; ++m) {
-              size_t best = 0;
-              for (size_t pr = 1; pr < load.size(); ++pr)
-                if (load[pr] < load[best]) best = pr;
-              load[best] += loop_item_cost(items[order[oi]], N);
-            }
-          const double makespan = *std::max_element(load.begin(), load.end());
-          if (makespan < best_cost) {
-            best_cost = makespan;
+          double total = 0.0, largest = 0.0;
+          for (size_t i = 0; i < wins.size(); ++i) {
+            tc2_build_item(*sp.tab, wins[i], N, K, max_g, TC2_MAX_A, step_max, &items[i]);
+            const double c = loop_item_cost(items[i], N);
+            total += c; largest = std::max(largest, c);
+          }
+          const double score = total * (double)n_mps / (double)n_pairs + alpha * largest;
+          if (score < best_cost) {
+            best_cost = score;
             shape_out[0] = wh; shape_out[1] = ww; shape_out[2] = sy; shape_out[3] = sx;
             best_items.swap(items);
+            if (total_out) *total_out = total;
+            if (max_out) *max_out = largest;
           }
         }
   if (best_items.empty()) { set_error("no window tiling for segment " + sp.name); return DGAN_ERR_UNSUPPORTED; }
@@ -1029,6 +1046,7 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
     if (specs[(size_t)s].in_seg != s - 1) { set_error("segments must form a chain"); return DGAN_ERR_UNSUPPORTED; }
   }
   pl.hdrs.assign((size_t)n_seg, {}); pl.shape.assign((size_t)4 * n_seg, 1);
+  pl.cost_total.assign((size_t)n_seg, 0.0); pl.cost_max.assign((size_t)n_seg, 0.0);
   pl.win_base.assign((size_t)n_seg, 0); pl.item_base.assign((size_t)n_seg, 0); pl.n_windows.assign((size_t)n_seg, 0);
   std::vector<std::vector<Tc2HostItem>> items((size_t)n_seg);
   std::vector<std::vector<int>> pix2win((size_t)n_seg);
@@ -1036,7 +1054,7 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
   int rc;
   for (int s = 0; s < n_seg; ++s) {
     const LoopSegSpec& sp = specs[(size_t)s];
-    if ((rc = loop_choose_tiling(sp, n_mpairs, n_pairs, &items[(size_t)s], &pl.shape[(size_t)4 * s]))) return rc;
+    if ((rc = loop_choose_tiling(sp, n_mpairs, n_pairs, &items[(size_t)s], &pl.shape[(size_t)4 * s], &pl.cost_total[(size_t)s], &pl.cost_max[(size_t)s]))) return rc;
     const size_t nw = items[(size_t)s].size();
     pl.hdrs[(size_t)s].resize(nw);
     pix2win[(size_t)s].assign(sp.tab->off.size() - 1, -1);
@@ -1096,7 +1114,7 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
     for (uint32_t w = 0; w < pl.n_windows[(size_t)s]; ++w) {
       const uint32_t wi = pl.win_base[(size_t)s] + w;
       if (specs[(size_t)s].in_seg < 0) { pl.need[wi] = LOOP_TAIL_NEED; continue; }
-      pl.need[wi] = (uint32_t)deps[wi].size();
+      pl.need[wi] = (uint32_t)deps[wi].size() * loop_parts_of(specs[(size_t)specs[(size_t)s].in_seg].kind);
       for (uint32_t u : deps[wi]) succ[pl.win_base[(size_t)specs[(size_t)s].in_seg] + u].push_back(((uint32_t)s << 16) | w);
     }
   pl.succ_off.assign(1, 0);
@@ -1121,9 +1139,15 @@ static int loop_plan(const std::vector<LoopSegSpec>& specs, int n_mpairs, int n_
   return 0;
 }
 
-// Items of a launch over `rec_iters` L-steps (the final L-step is forward only unless `full_last`).
+// Items of a launch over `rec_iters` L-steps (the final L-step is forward only unless `full_last`), and their parts.
 static inline unsigned long long loop_total_items(const LoopPlan& pl, int rec_iters, bool full_last) {
   return (unsigned long long)pl.n_mpairs * ((unsigned long long)rec_iters * pl.win_fwd + (unsigned long long)(rec_iters - (full_last ? 0 : 1)) * pl.win_bwd);
+}
+static inline unsigned long long loop_total_parts(const std::vector<LoopSegSpec>& specs, const LoopPlan& pl, int rec_iters, bool full_last) {
+  unsigned long long n = 0;
+  for (int s = 0; s < pl.n_seg; ++s)
+    n += (unsigned long long)pl.n_windows[(size_t)s] * loop_parts_of(specs[(size_t)s].kind) * (unsigned long long)(specs[(size_t)s].fwd ? rec_iters : rec_iters - (full_last ? 0 : 1));
+  return n * (unsigned long long)pl.n_mpairs;
 }
 
 // Host twin of loop_ring_alloc (the ring placement the kernel computes at run time).
@@ -1234,7 +1258,7 @@ static int loop_check_plan(const std::vector<LoopSegSpec>& specs, const LoopPlan
           if (std::find(dl.begin(), dl.end(), (uint32_t)p2w[(size_t)p]) == dl.end()) dl.push_back((uint32_t)p2w[(size_t)p]);
         }
       }
-      if (pl.need[wi] != dl.size()) return fail(specs[(size_t)s].name + ": `need` differs from the number of windows that write the staged pixels");
+      if (pl.need[wi] != dl.size() * loop_parts_of(specs[(size_t)specs[(size_t)s].in_seg].kind)) return fail(specs[(size_t)s].name + ": `need` differs from the number of windows that write the staged pixels");
     }
   {
     std::vector<std::vector<uint32_t>> inv(pl.n_win);
@@ -1292,11 +1316,12 @@ static int loop_check_plan(const std::vector<LoopSegSpec>& specs, const LoopPlan
       }
       const bool stop = ((int)seg == pl.n_fwd - 1) && ((int)t == L - 1);
       if (!stop)
-        for (uint32_t si = pl.succ_off[pl.win_base[seg] + win]; si < pl.succ_off[pl.win_base[seg] + win + 1]; ++si) {
-          const uint32_t s2 = pl.succ[si] >> 16, w2 = pl.succ[si] & 0xFFFFu;
-          const uint32_t c = ++depcnt[pl.item_base[s2] + mp * pl.n_windows[s2] + w2];
-          if (c == pl.need[pl.win_base[s2] + w2] * (t + 1)) { ready.push_back(((unsigned long long)(mp | (t << 16)) << 32) | pl.succ[si]); ++pushed; }
-        }
+        for (uint32_t part = 0; part < loop_parts_of(specs[seg].kind); ++part)
+          for (uint32_t si = pl.succ_off[pl.win_base[seg] + win]; si < pl.succ_off[pl.win_base[seg] + win + 1]; ++si) {
+            const uint32_t s2 = pl.succ[si] >> 16, w2 = pl.succ[si] & 0xFFFFu;
+            const uint32_t c = ++depcnt[pl.item_base[s2] + mp * pl.n_windows[s2] + w2];
+            if (c == pl.need[pl.win_base[s2] + w2] * (t + 1)) { ready.push_back(((unsigned long long)(mp | (t << 16)) << 32) | pl.succ[si]); ++pushed; }
+          }
       if ((int)seg == n_seg - 1 && (int)t < L - 1 && ++tails[mp] == pl.n_windows[seg] * (t + 1)) {
         // all split-K parts of the row pair are in: both 128-row tiles run their momentum tail
         for (uint32_t tile = 0; tile < LOOP_TAIL_NEED; ++tile)
