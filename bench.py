@@ -148,15 +148,13 @@ def _cpu_worker_run(job):
 
 class CpuPort:
     """The oracle restatement of the reference's TF1 CPU path (oracle/defensegan_oracle.py, fp32) on the host cores.
-    One torch process stops scaling near 16 threads on these small per-step tensors (tens of rows).  Splitting the
-    sample's images over several worker processes (DGAN_CPU_PROCS) is supported, but on the pool's GPU boxes it measured
-    SLOWER (8 x 16 threads: 1.8 images/s against 3.6 for 1 x 16; 128 logical CPUs are visible, the container's CPU share
-    evidently is not), so the default is one process - cores used = procs x threads is reported next to cores present."""
+    One torch process stops scaling near 16 threads on these small per-step tensors (tens of rows), so the sample's
+    images are split over `procs` worker processes of `threads` threads each - cores used = procs x threads."""
 
     def __init__(self, sample_images):
         self.cores_present = os.cpu_count() or 1
         self.threads = int(os.environ.get("DGAN_CPU_THREADS", min(self.cores_present, 16)))
-        want = int(os.environ.get("DGAN_CPU_PROCS", 1))
+        want = int(os.environ.get("DGAN_CPU_PROCS", max(1, self.cores_present // self.threads)))
         self.procs = max(1, min(want, sample_images))
         self.pool = None
         if self.procs > 1:
@@ -346,49 +344,28 @@ def timed(fn, steps, warmup, dev, flush, distributed):
 
 
 def kernel_breakdown(wl, peaks, precision):
-    """Per-kernel pass (rank 0; not part of `value`): CUDA events around every launch of the production path.
-    fp16: the whole call is ONE persistent kernel - that launch is the roofline's dominant kernel (FLOPs of L forward +
-    L-1 backward passes / its event-timed duration); its segments (layer-directions) are listed as in-kernel %globaltimer
-    spans (first item start .. last item end over all CTA pairs, per row-pair group; they overlap).  fp32: one kernel
-    per layer."""
+    """Per-kernel CUDA-event pass (rank 0; not part of `value`): [{kernel, launches, avg_us, share, tflops}], roofline."""
     nat = wl.gan._native
     x_loc = wl.x_full[:wl.B].contiguous()
     z_loc = wl.z0_full[:wl.B * wl.R].contiguous()
-
-    def run(level):
-        nat.profile_enable(level)
-        wl.gan.reconstruct(x_loc, z_init_val=z_loc)
-        torch.cuda.synchronize(wl.dev)
-        prof = nat.profile_read()
-        nat.profile_enable(0)
-        return prof
-
-    def table(prof):
-        tot_ms = sum(k["ms"] for k in prof) or 1.0
-        out = []
-        for k in prof:
-            if k["launches"] == 0:
-                continue
-            avg_ms = k["ms"] / k["launches"]
-            tf = k["flops_per_launch"] / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-            out.append({"kernel": k["name"], "launches": k["launches"], "avg_us": round(avg_ms * 1e3, 2),
-                        "share": round(k["ms"] / tot_ms, 4), "tflops": round(tf, 2), "flops_per_launch": k["flops_per_launch"]})
-        return out
-
-    prof1 = table(run(1))
-    if not prof1:
+    nat.profile_enable(True)
+    wl.gan.reconstruct(x_loc, z_init_val=z_loc)
+    torch.cuda.synchronize(wl.dev)
+    prof = nat.profile_read()
+    nat.profile_enable(False)
+    tot_ms = sum(k["ms"] for k in prof) or 1.0
+    kernels = []
+    for k in prof:
+        if k["launches"] == 0:
+            continue
+        avg_ms = k["ms"] / k["launches"]
+        tf = k["flops_per_launch"] / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        kernels.append({"kernel": k["name"], "launches": k["launches"], "avg_us": round(avg_ms * 1e3, 2),
+                        "share": round(k["ms"] / tot_ms, 4), "tflops": round(tf, 2)})
+    if not kernels:
         return None, None
-    kernels = {"production_path": prof1}
-    if precision == "fp16":
-        loop = [k for k in prof1 if k["kernel"].startswith("projection_loop")]
-        spans = [k for k in prof1 if not k["kernel"].startswith("projection_loop")]
-        for k in spans:
-            k["share"] = None          # spans overlap: shares of a sum are meaningless
-        kernels = {"fused_launch": loop, "segment_spans_inside_fused_launch": spans}
-        dom = loop[0] if loop else max(prof1, key=lambda k: k["avg_us"])
-    else:
-        dom = max(prof1, key=lambda k: k["share"])
-    # a kernel that runs for milliseconds settles at the power-capped clock: the sustained figure is its peak;
+    dom = max(kernels, key=lambda k: k["share"])
+    # a kernel that runs for tens of milliseconds settles at the power-capped clock: the sustained figure is its peak;
     # a sub-millisecond kernel timed alone is compared with the burst figure (B200_PROFILING.md)
     long_running = dom["avg_us"] >= 5000.0
     peak = peaks["bf16_tflops_sustained" if long_running else "bf16_tflops"] if precision == "fp16" else None
@@ -397,18 +374,16 @@ def kernel_breakdown(wl, peaks, precision):
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-        ent = tj.get("workloads", {}).get("%s/%d/%s" % (wl.dataset, wl.B * wl.R, precision), {})
-        ent = ent.get(dom["kernel"].split(" ")[0])
+        ent = tj.get("workloads", {}).get("%s/%d/%s" % (wl.dataset, wl.B * wl.R, precision), {}).get(dom["kernel"])
         if ent:
             traffic, tsrc = ent.get("dram_bytes_per_launch"), ent.get("source")
     roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
                 "frac": (dom["tflops"] / peak) if peak else None, "traffic": traffic,
                 "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum; %s)" % (tsrc or "no ncu capture for this workload"),
                 "peak_source": "%s cuBLAS bf16 %s (MEASURED_PEAKS.json; fp16 and bf16 share the kind::f16 rate)" % (
-                    peaks["_source"], ("sustained: the kernel runs for %.1f ms" % (dom["avg_us"] / 1e3)) if long_running else "burst"),
-                "frac_of_burst_peak": (dom["tflops"] / peaks["bf16_tflops"]) if precision == "fp16" else None,
-                "operand_format": precision, "flops_per_launch": dom["flops_per_launch"],
-                "avg_launch_us": dom["avg_us"]}
+                    peaks["_source"], "sustained: the kernel runs for %.1f ms" % (dom["avg_us"] / 1e3) if long_running else "burst"),
+                "operand_format": precision,
+                "flops_per_launch": next(k["flops_per_launch"] for k in prof if k["name"] == dom["kernel"])}
     return kernels, roofline
 
 

@@ -31,7 +31,7 @@ NVCC_FLAGS = [
 ABI_SYMBOLS = [
     "dgan_abi_version", "dgan_last_error", "dgan_num_weights", "dgan_create", "dgan_destroy",
     "dgan_workspace_bytes", "dgan_reconstruct", "dgan_sample_z0", "dgan_forward", "dgan_loss_grad",
-    "dgan_last_launch_count", "dgan_last_status", "dgan_macs_per_row", "dgan_profile_enable", "dgan_profile_num_kinds",
+    "dgan_last_launch_count", "dgan_macs_per_row", "dgan_profile_enable", "dgan_profile_num_kinds",
     "dgan_profile_kind_name", "dgan_profile_read",
 ]
 
@@ -109,8 +109,6 @@ def load_library() -> ctypes.CDLL:
     lib.dgan_loss_grad.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.dgan_last_launch_count.restype = ctypes.c_int64
     lib.dgan_last_launch_count.argtypes = [vp]
-    lib.dgan_last_status.restype = i32
-    lib.dgan_last_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     lib.dgan_macs_per_row.restype = ctypes.c_int64
     lib.dgan_macs_per_row.argtypes = [vp]
     lib.dgan_profile_enable.restype = i32
@@ -215,17 +213,8 @@ class NativeGenerator:
     def last_launch_count(self) -> int:
         return int(self.lib.dgan_last_launch_count(self._handle))
 
-    def last_status(self) -> int:
-        """Device status word of the most recent loop-kernel launch (synchronises): 0 = fine; non-zero = one of its
-        dependency waits timed out and that call's results are invalid."""
-        v = ctypes.c_int(0)
-        _check(self.lib, self.lib.dgan_last_status(self._handle, ctypes.byref(v)), "dgan_last_status")
-        return int(v.value)
-
-    def profile_enable(self, level) -> None:
-        """0 = off; 1 = time every launch of the production path (the fp16 loop kernel also records in-kernel segment
-        spans, per-CTA stall counters and a per-item trace: tools/loop_stalls.py, tools/loop_trace.py)."""
-        _check(self.lib, self.lib.dgan_profile_enable(self._handle, int(level)), "dgan_profile_enable")
+    def profile_enable(self, on: bool) -> None:
+        _check(self.lib, self.lib.dgan_profile_enable(self._handle, int(bool(on))), "dgan_profile_enable")
 
     def profile_read(self):
         """[{name, ms, launches, flops_per_launch}] for the launches recorded since profile_enable(True)."""

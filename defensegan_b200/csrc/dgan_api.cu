@@ -13,7 +13,6 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc2.cuh"
-#include "kernels_loop.cuh"
 
 namespace dgan {
 
@@ -110,6 +109,7 @@ struct GemmLayer {
   // fp16 K-major tiles for the tensor-core path (kernels_tc.cuh): [tile][N rows][K cols]
   TcWeights tc_f, tc_b;
   TcWeights2 tc2_f, tc2_b;
+  TcWeights2 tc2_b_fused;          // Linear only: un-split dz with the momentum update in the epilogue
 };
 
 struct FinalLayer {
@@ -124,29 +124,6 @@ struct FinalLayer {
 
 using namespace dgan;
 
-// which workspace tensor a segment of the fp16 loop kernel reads / writes
-enum SegTensor : int { T_ZH = 0, T_ACT, T_DACT, T_DBLK, T_GPART };
-struct SegBind {
-  int in_kind = T_ZH, in_idx = 0, out_kind = T_ACT, out_idx = 0;
-  const dgan::TcWeights* w1 = nullptr;
-  const dgan::TcWeights2* w2 = nullptr;
-  const float* bias = nullptr;
-  int bias_pstride = 0;
-  int mb_out_layer = -1, mb_in_layer = -1;   // hidden layer whose 1-bit ReLU masks the epilogue writes / reads
-  int epi = 0, out_bytes = 2;
-};
-
-// one L-step plan (kernels_loop.cuh) uploaded for a given number of 256-row pairs
-struct DevPlan {
-  int n_mpairs = 0, n_pairs = 0;
-  dgan::LoopPlan host;
-  dgan::TcItem2* items[dgan::LOOP_MAX_SEG] = {nullptr};
-  dgan::TcRec* tmpl_p[2] = {nullptr, nullptr};
-  dgan::TcRec* tmpl_m = nullptr;
-  uint32_t *win_rec_off = nullptr, *succ_off = nullptr, *succ = nullptr, *need = nullptr;
-  unsigned long long* q_init = nullptr;
-};
-
 struct dgan_ctx {
   dgan_desc desc;
   int H = 0, W = 0, C = 0, hwc = 0;
@@ -159,23 +136,15 @@ struct dgan_ctx {
   TcState tc;
   TcFinal tc_fin;
   TcWeights2 tc2_fin_f, tc2_fin_b;
-  // fp16 path: the persistent projection-loop kernel
-  std::vector<LoopSegSpec> segs;          // segments of one L-step in execution order
-  std::vector<SegBind> binds;
-  int n_fwd_seg = 0;                      // segments 0 .. n_fwd_seg-1 are the generator forward (+ loss)
-  int n_pairs = 0;                        // co-resident CTA pairs (clusters of 2) the kernel is launched with
-  std::vector<std::unique_ptr<DevPlan>> plans;
-  LoopParams lp;                          // launch parameters of the most recent workspace (tensor maps are encoded once)
-  const void* lp_ws = nullptr; int lp_rows = -1; const DevPlan* lp_plan = nullptr;
-  uint32_t* last_status = nullptr;        // device status word of the most recent loop launch (lives in its workspace)
-  // profiling (dgan_profile_*): time every launch of the production path; the fp16 loop kernel also records in-kernel
-  // segment spans, per-CTA stall counters and a per-item trace.  Never on in a throughput pass.
-  int profile = 0;
-  unsigned long long* prof_dev = nullptr; size_t prof_cap = 0; int prof_L = 0; const DevPlan* prof_plan = nullptr;
-  int loop_passes = 0;                    // generator passes (forward or backward) of the last loop launch: its FLOPs
-  unsigned long long* dbg_dev = nullptr; int dbg_ctas = 0;   // per-CTA stall counters of the last profiled loop launch
-  unsigned long long* trace_dev = nullptr; size_t trace_items = 0; const DevPlan* trace_plan = nullptr;   // per-item timestamps of one L-step
-  int trace_step = -1;
+  // optional per-launch CUDA-event timing (dgan_profile_*): serialises nothing by itself but
+  // adds two event records per launch, so it is never enabled in a timed benchmark pass
+  // the images of a call are split into `n_chains` independent dependency chains on separate streams so that
+  // one chain's kernel tails / launch gaps are filled by the other's CTAs
+  int n_chains = 1;
+  std::vector<cudaStream_t> chain_streams;
+  std::vector<cudaEvent_t> chain_events;
+  cudaEvent_t fork_event = nullptr;
+  bool profile = false;
   int n_rows_cur = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -187,7 +156,7 @@ namespace dgan {
 
 struct ProfScope {
   dgan_ctx* c; cudaStream_t s; bool on; dgan_ctx::ProfRec r;
-  ProfScope(dgan_ctx* c_, int kind, cudaStream_t s_) : c(c_), s(s_), on(c_->profile != 0) {
+  ProfScope(dgan_ctx* c_, int kind, cudaStream_t s_) : c(c_), s(s_), on(c_->profile) {
     if (!on) return;
     r.kind = kind;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
@@ -252,11 +221,11 @@ struct Workspace {
   std::vector<__half*> act_h, dact_h;  // fp16 path
   __half* z_h = nullptr;
   std::vector<unsigned long long*> maskbits;   // fp16 path: 1-bit ReLU masks per hidden layer output
+  // fp16 CTA-pair path: TMA descriptors of every launch site, encoded once per workspace
+  // index 2l = forward of layer l (in, out), 2l+1 = backward of layer l; 2nl = last-layer forward, 2nl+1 = its backward
+  std::vector<CUtensorMap> map_in, map_out;
+  bool have_maps = false;
   unsigned* mom_counter = nullptr;     // fp16 path: [n_pad / 128] tickets of the split-K Linear backward's momentum tail
-  // fp16 path, the loop kernel's scheduling state: [status(4) | q_ctl(4) | depcnt(n_counters)] and the queue
-  uint32_t *status = nullptr, *q_ctl = nullptr, *depcnt = nullptr;
-  unsigned long long* queue = nullptr;
-  size_t n_counters = 0, q_cap = 0;
   __half* dblk = nullptr;              // fp16 path: [n_blocks][n_pad][64] scaled dL/dpre of the last layer
   int n_loss_parts = 0, n_g_parts = 1;
   size_t loss_stride_n = 1, loss_stride_b = 1;   // loss_part index = n * stride_n + part * stride_b
@@ -284,18 +253,6 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
   w.g = (float*)take(np * latent * 4 * w.n_g_parts);
   if (tc) w.z_h = (__half*)take(np * latent * 2);
   if (tc) w.mom_counter = (unsigned*)take(np / kRowTile * sizeof(unsigned));
-  if (tc) {
-    // one counter per (segment, window, row pair); a window holds at least one output pixel, which bounds the plan's
-    // needs whatever tiling it picks (the queue capacity follows loop_plan's rule on that bound)
-    size_t per_mp = 0;
-    for (const LoopSegSpec& sp : c->segs) per_mp += sp.tab->off.size() - 1;
-    w.n_counters = per_mp * (np / (2 * kRowTile));
-    w.status = (uint32_t*)take((8 + w.n_counters) * sizeof(uint32_t));
-    if (w.status != nullptr) { w.q_ctl = w.status + 4; w.depcnt = w.status + 8; }
-    w.q_cap = 1024;
-    while (w.q_cap < 4 * (w.n_counters + (size_t)c->n_pairs) + 64) w.q_cap <<= 1;
-    w.queue = (unsigned long long*)take(w.q_cap * sizeof(unsigned long long));
-  }
   if (tc) w.dblk = (__half*)take((size_t)c->tc_fin.n_blocks * np * 64 * 2);
   w.n_loss_parts = tc ? c->tc_fin.n_blocks : c->fin.n_bands;
   w.loss_stride_n = tc ? 1 : (size_t)w.n_loss_parts;          // fp16 path: [block][n_pad] (coalesced epilogue stores)
@@ -401,11 +358,63 @@ static int launch_final_bwd(dgan_ctx* c, const Workspace& w, const TOUT* mask_sr
   return 0;
 }
 
-// ---- one generator forward (+ loss and dL/dpre when x != null), fp32 path ------------------
+static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
+                      int epi, const float* bias, const __half* mask_src, cudaStream_t s,
+                      unsigned long long* mb_out = nullptr, const unsigned long long* mb_in = nullptr,
+                      const CUtensorMap* pre_a = nullptr, const CUtensorMap* pre_out = nullptr);
+
+// Encode the TMA descriptors of all launch sites for this workspace (once per call instead of per launch).
+static int build_maps(dgan_ctx* c, Workspace& w) {
+  if (c->desc.precision != DGAN_PREC_FP16 || c->tc.mode != 2) return 0;
+  const int nl = (int)c->layers.size();
+  w.map_in.assign((size_t)2 * nl + 2, CUtensorMap{});
+  w.map_out.assign((size_t)2 * nl + 2, CUtensorMap{});
+  int rc;
+  auto mk = [&](CUtensorMap* m, const void* base, int K, int P) {
+    return tc_make_map(c->tc, m, base, (uint64_t)K, (uint64_t)w.n_pad, (uint64_t)P, 128);
+  };
+  for (int l = 0; l < nl; ++l) {
+    const GemmLayer& L = c->layers[l];
+    const void* fin = (l == 0) ? (const void*)w.z_h : (const void*)w.act_h[l - 1];
+    if ((rc = mk(&w.map_in[2 * l], fin, L.C_in, L.P_in))) return rc;
+    if ((rc = mk(&w.map_out[2 * l], w.act_h[l], L.C_out, L.P_out))) return rc;
+    if ((rc = mk(&w.map_in[2 * l + 1], w.dact_h[l], L.C_out, L.P_out))) return rc;
+    if (l >= 1 && (rc = mk(&w.map_out[2 * l + 1], w.dact_h[l - 1], L.C_in, L.P_in))) return rc;
+  }
+  const GemmLayer& last = c->layers[nl - 1];
+  if ((rc = mk(&w.map_in[2 * nl], w.act_h[nl - 1], c->fin.C_in, last.P_out))) return rc;
+  if ((rc = mk(&w.map_in[2 * nl + 1], w.dblk, 64, c->tc_fin.n_blocks))) return rc;
+  if ((rc = mk(&w.map_out[2 * nl + 1], w.dact_h[nl - 1], last.C_out, last.P_out))) return rc;
+  w.have_maps = true;
+  return 0;
+}
+
+// ---- one generator forward (+ loss and dL/dpre when x != null) ---------------------------
 static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, int B, bool want_grad,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool want_y = true) {
   int rc;
   const int nl = (int)c->layers.size();
+  if (c->desc.precision == DGAN_PREC_FP16) {
+    const __half* in = w.z_h;
+    for (int l = 0; l < nl; ++l) {
+      const GemmLayer& L = c->layers[l];
+      ProfScope ps(c, 2 * l, s);
+      if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, nullptr, s,
+                           (L.relu && want_grad) ? w.maskbits[l] : nullptr, nullptr,
+                           w.have_maps ? &w.map_in[2 * l] : nullptr, w.have_maps ? &w.map_out[2 * l] : nullptr)))
+        return rc;
+      in = w.act_h[l];
+    }
+    ProfScope ps(c, 2 * nl, s);
+    TcFinalArgs fa{};
+    fa.x = x; fa.y = w.y; fa.loss_part = w.loss_part; fa.R = R; fa.B = B; fa.n_rows = w.n_rows;
+    fa.nbx = c->tc_fin.nbx; fa.w_out = c->tc_fin.w_out; fa.gscale = c->tc.grad_scale; fa.write_y = want_y ? 1 : 0;
+    if (c->tc.mode == 2)
+      return tc2_launch_impl<__half>(c->tc, &c->launches, c->tc_fin.f, c->tc2_fin_f, in, w.dblk, w.n_pad,
+                                     c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, c->fin.bias, nullptr, 1.f, s, &fa,
+                                     w.have_maps ? &w.map_in[2 * nl] : nullptr, nullptr);
+    return tc_launch_final_fwd(c->tc, &c->launches, c->tc_fin, in, w.dblk, w.n_pad, c->fin.bias, fa, s);
+  }
   const float* in = w.z;
   for (int l = 0; l < nl; ++l) {
     const GemmLayer& L = c->layers[l];
@@ -439,10 +448,51 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
   return launch_final_fwd<float>(c, in, w, x, R, B, want_grad, s);
 }
 
-// ---- backward-to-z, fp32 path: w.g = J^T dpre (unscaled by 2/HWC) -----
-static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s) {
+// ---- backward-to-z: w.g = J^T dpre (unscaled by 2/HWC; fp16 path additionally x gscale) -----
+struct MomentumArgs { bool fused = false, tail = false; float lr = 0.f, mu = 0.f; };
+
+static float grad_multiplier(const dgan_ctx* c);
+
+static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, MomentumArgs mom = MomentumArgs()) {
   int rc;
   const int nl = (int)c->layers.size();
+  if (c->desc.precision == DGAN_PREC_FP16) {
+    const GemmLayer& last = c->layers[nl - 1];
+    {
+      ProfScope ps(c, 2 * nl + 1, s);
+      if ((rc = tcx_launch(c, c->tc_fin.b, c->tc2_fin_b, w.dblk, w.dact_h[nl - 1], w.n_pad, last.relu ? EPI_MASK : EPI_NONE,
+                           nullptr, last.relu ? w.act_h[nl - 1] : nullptr, s, nullptr, last.relu ? w.maskbits[nl - 1] : nullptr,
+                           w.have_maps ? &w.map_in[2 * nl + 1] : nullptr, w.have_maps ? &w.map_out[2 * nl + 1] : nullptr)))
+        return rc;
+    }
+    for (int l = nl - 1; l >= 1; --l) {
+      const GemmLayer& L = c->layers[l];
+      const bool mask = c->layers[l - 1].relu;
+      ProfScope ps(c, 2 * l + 1, s);
+      if ((rc = tcx_launch(c, L.tc_b, L.tc2_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad, mask ? EPI_MASK : EPI_NONE, nullptr,
+                           mask ? w.act_h[l - 1] : nullptr, s, nullptr, mask ? w.maskbits[l - 1] : nullptr,
+                           w.have_maps ? &w.map_in[2 * l + 1] : nullptr, w.have_maps ? &w.map_out[2 * l + 1] : nullptr)))
+        return rc;
+    }
+    const GemmLayer& L0 = c->layers[0];
+    ProfScope ps(c, 1, s);
+    if (c->tc.mode == 2 && mom.fused) {
+      TcFinalArgs fa{};
+      fa.mz = w.z; fa.mv = w.v; fa.mz_h = w.z_h; fa.m_gmul = grad_multiplier(c); fa.m_lr = mom.lr; fa.m_mu = mom.mu;
+      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b_fused, w.dact_h[0], w.g, w.n_pad, EPI_MOMENTUM, nullptr,
+                                    nullptr, 1.f, s, &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
+    }
+    if (c->tc.mode == 2) {
+      TcFinalArgs fa{};
+      if (mom.tail && w.n_g_parts == TC_LINEAR_SPLIT) {      // the CTA that completes a row tile's partial sums applies the momentum update
+        fa.mz = w.z; fa.mv = w.v; fa.mz_h = w.z_h; fa.m_gmul = grad_multiplier(c); fa.m_lr = mom.lr; fa.m_mu = mom.mu;
+        fa.m_counter = w.mom_counter; fa.m_nparts = w.n_g_parts; fa.m_count = (size_t)w.n_pad * c->desc.latent_dim;
+      }
+      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s,
+                                    &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
+    }
+    return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
+  }
   // d(act) -> d(pre) through ReLU + batch-statistics BN of layer l (in place in w.dact[l])
   auto bn_backward = [&](int l) -> int {
     const GemmLayer& L = c->layers[l];
@@ -511,6 +561,18 @@ static int check_ws(const dgan_ctx* c, int n_rows, void* ws, size_t ws_bytes, Wo
   return 0;
 }
 
+// tensor-core launch, dispatching on the kernel generation
+static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
+                      int epi, const float* bias, const __half* mask_src, cudaStream_t s, unsigned long long* mb_out,
+                      const unsigned long long* mb_in, const CUtensorMap* pre_a, const CUtensorMap* pre_out) {
+  if (c->tc.mode == 2) {
+    TcFinalArgs fa{};
+    fa.mb_out = mb_out; fa.mb_in = mb_in;
+    return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, mask_src, 1.f, s, &fa, pre_a, pre_out);
+  }
+  return tc_launch(c->tc, &c->launches, w1, in, out, n_pad, epi, bias, mask_src, 1.f, s);
+}
+
 // element counts of the weight tensors in creation order (include/defensegan_b200.h, dgan_num_weights)
 static std::vector<size_t> weight_counts(const dgan_desc* d) {
   const size_t nd = (size_t)d->net_dim, latent = (size_t)d->latent_dim, feat = 16 * 4 * nd;
@@ -529,258 +591,6 @@ static float grad_multiplier(const dgan_ctx* c) {
   float m = 2.0f / (float)c->hwc;  // d/dy mean_{HWC}(y-x)^2
   if (c->desc.precision == DGAN_PREC_FP16) m /= c->tc.grad_scale;
   return m;
-}
-
-// ---------------------------------------------------------------------------------------
-// fp16 path: the persistent projection-loop kernel (kernels_loop.cuh)
-// ---------------------------------------------------------------------------------------
-static int loop_kind_of(int N, int epi, int out_bytes) {
-  if (epi == EPI_FINAL_SIGMOID1) return LK_FINAL16;
-  if (epi == EPI_FINAL_TANH3) return LK_FINAL48;
-  if (out_bytes == 4) return N == 64 ? LK_NONE64F : (N == 128 ? LK_NONE128F : (N == 256 ? LK_NONE256F : -1));
-  if (epi == EPI_BIAS_RELU) return N == 64 ? LK_BR64 : (N == 128 ? LK_BR128 : (N == 256 ? LK_BR256 : -1));
-  if (epi == EPI_MASK) return N == 64 ? LK_MASK64 : (N == 128 ? LK_MASK128 : (N == 256 ? LK_MASK256 : -1));
-  if (epi == EPI_BIAS) return N == 64 ? LK_B64 : -1;
-  if (epi == EPI_NONE) return N == 64 ? LK_NONE64H : -1;
-  return -1;
-}
-
-// The segments of one L-step in execution order: generator forward, last layer + loss, then backward-to-z.
-static int build_segments(dgan_ctx* c) {
-  const int nl = (int)c->layers.size();
-  c->segs.clear(); c->binds.clear();
-  auto add = [&](const std::string& name, const TcWeights& w1, const TcWeights2& w2, int epi, int out_bytes, int in_seg,
-                 double macs, SegBind b) -> int {
-    LoopSegSpec sp;
-    sp.name = name; sp.N = w1.N; sp.K = w1.K; sp.kind = loop_kind_of(w1.N, epi, out_bytes);
-    if (sp.kind < 0) { set_error(name + ": no epilogue variant for this layer shape (net_dim 64, latent 64/128/256 only)"); return DGAN_ERR_UNSUPPORTED; }
-    sp.tab = &w2.tab; sp.h_grid = w2.h_grid; sp.w_grid = w2.w_grid; sp.max_acc = w2.max_acc; sp.in_seg = in_seg;
-    sp.macs_per_row = macs;
-    sp.fwd = (int)c->segs.size() <= (int)c->layers.size();      // Linear + hidden layers + last layer forward
-    b.w1 = &w1; b.w2 = &w2; b.epi = epi; b.out_bytes = out_bytes;
-    c->segs.push_back(sp); c->binds.push_back(b);
-    return 0;
-  };
-  static const char* lname[] = {"Linear", "Generator.2", "Generator.3", "Generator.5"};
-  const std::string fname = c->desc.arch == DGAN_ARCH_CELEBA ? "Generator.6" : "Generator.5";
-  int rc;
-  double conv_macs = 0;
-  for (int l = 0; l < nl; ++l) {
-    const GemmLayer& L = c->layers[l];
-    const double macs = (double)L.fwd_host.pairs.size() * L.C_in * L.C_out;
-    conv_macs += macs;
-    SegBind b;
-    b.in_kind = l == 0 ? T_ZH : T_ACT; b.in_idx = l - 1; b.out_kind = T_ACT; b.out_idx = l;
-    b.bias = L.bias; b.bias_pstride = L.bias_pstride; b.mb_out_layer = L.relu ? l : -1;
-    if ((rc = add(std::string(lname[l]) + ".fwd", L.tc_f, L.tc2_f, L.relu ? EPI_BIAS_RELU : EPI_BIAS, 2, l - 1, macs, b))) return rc;
-  }
-  const double fin_macs = (double)c->macs_per_row - conv_macs;
-  {
-    SegBind b;
-    b.in_kind = T_ACT; b.in_idx = nl - 1; b.out_kind = T_DBLK; b.bias = c->fin.bias;
-    if ((rc = add(fname + "+loss.fwd", c->tc_fin.f, c->tc2_fin_f, c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, 2, nl - 1, fin_macs, b))) return rc;
-  }
-  c->n_fwd_seg = nl + 1;
-  {
-    const bool relu = c->layers[nl - 1].relu;
-    SegBind b;
-    b.in_kind = T_DBLK; b.out_kind = T_DACT; b.out_idx = nl - 1; b.mb_in_layer = relu ? nl - 1 : -1;
-    if ((rc = add(fname + ".bwd", c->tc_fin.b, c->tc2_fin_b, relu ? EPI_MASK : EPI_NONE, 2, nl, fin_macs, b))) return rc;
-  }
-  for (int l = nl - 1; l >= 1; --l) {
-    const GemmLayer& L = c->layers[l];
-    const bool relu = c->layers[l - 1].relu;
-    SegBind b;
-    b.in_kind = T_DACT; b.in_idx = l; b.out_kind = T_DACT; b.out_idx = l - 1; b.mb_in_layer = relu ? l - 1 : -1;
-    if ((rc = add(std::string(lname[l]) + ".bwd", L.tc_b, L.tc2_b, relu ? EPI_MASK : EPI_NONE, 2, (int)c->segs.size() - 1,
-                  (double)L.fwd_host.pairs.size() * L.C_in * L.C_out, b)))
-      return rc;
-  }
-  {
-    const GemmLayer& L0 = c->layers[0];
-    SegBind b;
-    b.in_kind = T_DACT; b.in_idx = 0; b.out_kind = T_GPART;
-    if ((rc = add("Linear.bwd+momentum", L0.tc_b, L0.tc2_b, EPI_NONE, 4, (int)c->segs.size() - 1,
-                  (double)L0.fwd_host.pairs.size() * L0.C_in * L0.C_out, b)))
-      return rc;
-  }
-  if ((int)c->segs.size() > LOOP_MAX_SEG) { set_error("too many segments"); return DGAN_ERR_UNSUPPORTED; }
-  return 0;
-}
-
-template <typename T>
-static int upload_vec(dgan_ctx* c, const std::vector<T>& v, T** dev) {
-  const size_t bytes = std::max<size_t>(1, v.size()) * sizeof(T);
-  DGAN_CUDA_CHECK(cudaMalloc((void**)dev, bytes));
-  c->allocs.push_back(*dev);
-  if (!v.empty()) DGAN_CUDA_CHECK(cudaMemcpy(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return 0;
-}
-
-// Plan (or fetch) the L-step schedule for `n_rows` latent rows.  Planning allocates and copies synchronously: it happens
-// in dgan_workspace_bytes - which a caller needs before its first dgan_reconstruct of a batch size anyway - so that
-// dgan_reconstruct itself never allocates or synchronises (it only falls back to planning here if the caller sized the
-// workspace some other way).
-static int get_plan(dgan_ctx* c, int n_rows, const DevPlan** out) {
-  const int n_pad = (int)align_up((size_t)std::max(n_rows, 1), 2 * kRowTile), n_mpairs = n_pad / (2 * kRowTile);
-  for (auto& p : c->plans)
-    if (p->n_mpairs == n_mpairs) { *out = p.get(); return 0; }
-  std::unique_ptr<DevPlan> dp(new DevPlan());
-  dp->n_mpairs = n_mpairs; dp->n_pairs = c->n_pairs;
-  int rc;
-  if ((rc = loop_plan(c->segs, n_mpairs, c->n_pairs, &dp->host))) return rc;
-  const LoopPlan& pl = dp->host;
-  for (int v = 0; v < pl.n_seg; ++v)
-    if ((rc = upload_vec(c, pl.hdrs[(size_t)v], &dp->items[v]))) return rc;
-  for (int r = 0; r < 2; ++r)
-    if ((rc = upload_vec(c, pl.tmpl_p[r], &dp->tmpl_p[r]))) return rc;
-  if ((rc = upload_vec(c, pl.tmpl_m, &dp->tmpl_m))) return rc;
-  if ((rc = upload_vec(c, pl.win_rec_off, &dp->win_rec_off))) return rc;
-  if ((rc = upload_vec(c, pl.succ_off, &dp->succ_off))) return rc;
-  if ((rc = upload_vec(c, pl.succ, &dp->succ))) return rc;
-  if ((rc = upload_vec(c, pl.need, &dp->need))) return rc;
-  if ((rc = upload_vec(c, pl.q_init, &dp->q_init))) return rc;
-  c->plans.push_back(std::move(dp));
-  *out = c->plans.back().get();
-  return 0;
-}
-
-// Launch parameters for this workspace: per segment the TMA descriptors of its input / weight / output tensors and its
-// epilogue bindings.  Encoded once per (workspace, row count); later calls only patch the per-call scalars.
-static int build_params(dgan_ctx* c, const Workspace& w, const void* ws_base, const DevPlan* dp) {
-  if (c->lp_ws == ws_base && c->lp_rows == w.n_rows && c->lp_plan == dp) return 0;
-  LoopParams& P = c->lp;
-  P = LoopParams{};
-  const LoopPlan& pl = dp->host;
-  if (pl.n_item_slots > w.n_counters || pl.q_cap > w.q_cap) { set_error("internal: scheduling state smaller than the plan needs"); return DGAN_ERR_WORKSPACE; }
-  int rc;
-  auto tensor = [&](int kind, int idx, const void** base, int* chan, int* pix) {
-    const int latent = c->desc.latent_dim;
-    switch (kind) {
-      case T_ZH: *base = w.z_h; *chan = latent; *pix = 1; break;
-      case T_ACT: *base = w.act_h[(size_t)idx]; *chan = c->layers[(size_t)idx].C_out; *pix = c->layers[(size_t)idx].P_out; break;
-      case T_DACT: *base = w.dact_h[(size_t)idx]; *chan = c->layers[(size_t)idx].C_out; *pix = c->layers[(size_t)idx].P_out; break;
-      case T_DBLK: *base = w.dblk; *chan = 64; *pix = c->tc_fin.n_blocks; break;
-      default: *base = w.g; *chan = latent; *pix = TC_LINEAR_SPLIT; break;
-    }
-  };
-  for (int v = 0; v < pl.n_seg; ++v) {
-    const int s = v;
-    const SegBind& b = c->binds[(size_t)s];
-    const LoopSegSpec& sp = c->segs[(size_t)s];
-    LoopSeg& g = P.seg[v];
-    const void* base; int chan, pix;
-    tensor(b.in_kind, b.in_idx, &base, &chan, &pix);
-    if (chan != sp.K) { set_error("internal: segment input channels"); return DGAN_ERR_INVALID_ARG; }
-    if ((rc = tc_make_map(c->tc, &g.tm_a, base, (uint64_t)chan, (uint64_t)w.n_pad, (uint64_t)pix, 128))) return rc;
-    g.tm_b = b.w2->tm_b;
-    tensor(b.out_kind, b.out_idx, &base, &chan, &pix);
-    g.out = const_cast<void*>(base);
-    g.tm_out = g.tm_a;                                  // placeholder for the epilogues that do not store by TMA
-    if (tc2_tma_epilogue(sp.N, b.epi, b.out_bytes) &&
-        (rc = tc_make_map(c->tc, &g.tm_out, base, (uint64_t)chan, (uint64_t)w.n_pad, (uint64_t)pix, 128)))
-      return rc;
-    g.bias = b.bias;
-    g.mb_out = b.mb_out_layer >= 0 ? w.maskbits[(size_t)b.mb_out_layer] : nullptr;
-    g.mb_in = b.mb_in_layer >= 0 ? w.maskbits[(size_t)b.mb_in_layer] : nullptr;
-    g.items = dp->items[v];
-    g.n_tile = (uint32_t)sp.N; g.kind = (uint32_t)sp.kind; g.bias_pstride = (uint32_t)b.bias_pstride;
-    g.acc_stride = (uint32_t)tc2_acc_stride(sp.N);
-    g.idesc = make_idesc_f16(256, sp.N);
-    g.half_b = (uint32_t)(sp.N / 2) * 128u;
-    g.win_base = pl.win_base[(size_t)v]; g.item_base = pl.item_base[(size_t)v]; g.n_windows = pl.n_windows[(size_t)v];
-  }
-  P.tmpl_p[0] = dp->tmpl_p[0]; P.tmpl_p[1] = dp->tmpl_p[1]; P.tmpl_m = dp->tmpl_m;
-  P.win_rec_off = dp->win_rec_off; P.succ_off = dp->succ_off; P.succ = dp->succ; P.need = dp->need;
-  P.queue = w.queue; P.q_ctl = w.q_ctl; P.depcnt = w.depcnt;
-  P.q_cap = pl.q_cap; P.q_shift = 0;
-  while ((1u << P.q_shift) < pl.q_cap) ++P.q_shift;
-  P.q_init = (uint32_t)pl.q_init.size(); P.n_pairs = (uint32_t)dp->n_pairs;
-  P.status = w.status; P.prof = nullptr; P.dbg = nullptr; P.trace = nullptr; P.trace_step = -1;
-  P.n_seg = pl.n_seg; P.n_fwd = pl.n_fwd; P.n_pad = w.n_pad; P.n_mpairs = dp->n_mpairs;
-  P.y = w.y; P.loss_part = w.loss_part; P.n_rows = w.n_rows; P.nbx = c->tc_fin.nbx; P.w_out = c->tc_fin.w_out;
-  P.gscale = c->tc.grad_scale;
-  P.mz = w.z; P.mv = w.v; P.mz_h = w.z_h; P.m_nparts = w.n_g_parts; P.m_count = (size_t)w.n_pad * c->desc.latent_dim;
-  c->lp_ws = ws_base; c->lp_rows = w.n_rows; c->lp_plan = dp;
-  return 0;
-}
-
-enum LoopMode : int { LOOP_RECONSTRUCT = 0, LOOP_FORWARD = 1, LOOP_LOSS_GRAD = 2 };
-
-// Enqueue the loop kernel: rec_iters L-steps of (forward, loss, backward-to-z, momentum); the final L-step is forward
-// only (the loop returns the pre-update forward of iteration L-1, models/gan.py:419-421) except for
-// dgan_loss_grad, which wants the gradient of its one evaluation.  Three small memory operations put the scheduling
-// state in its initial condition first: counters zero, queue slots unwritten, the first segment's items of L-step 0 ready.
-static int launch_loop(dgan_ctx* c, const Workspace& w, const void* ws_base, const float* x, int R, int B, int rec_iters,
-                       float lr, float mu, int decay_lr, int mode, cudaStream_t s) {
-  const DevPlan* dp = nullptr;
-  int rc;
-  if (rec_iters < 1 || rec_iters > 0xFFFF) { set_error("rec_iters must be in [1, 65535] on the fp16 path"); return DGAN_ERR_INVALID_ARG; }
-  if ((rc = get_plan(c, w.n_rows, &dp))) return rc;
-  if ((rc = build_params(c, w, ws_base, dp))) return rc;
-  const LoopPlan& pl = dp->host;
-  LoopParams P = c->lp;
-  P.x = x; P.R = R; P.B = B;
-  P.m_gmul = grad_multiplier(c); P.m_lr = lr; P.m_mu = mu;
-  P.m_counter = (mode == LOOP_RECONSTRUCT) ? w.mom_counter : nullptr;
-  P.decay_step = decay_lr ? (int)std::ceil(rec_iters * 0.8) : 0;
-  P.last_step = rec_iters - 1;
-  P.full_last = (mode == LOOP_LOSS_GRAD) ? 1 : 0;
-  const unsigned long long total = loop_total_parts(c->segs, pl, rec_iters, mode == LOOP_LOSS_GRAD);
-  if (total + (unsigned long long)dp->n_pairs >= 0xFFFFFFFFull) { set_error("too many work items for one launch (batch x rec_rr x rec_iters)"); return DGAN_ERR_UNSUPPORTED; }
-  P.n_parts_total = (uint32_t)total;
-  DGAN_CUDA_CHECK(cudaMemsetAsync(w.status, 0, (8 + w.n_counters) * sizeof(uint32_t), s));
-  DGAN_CUDA_CHECK(cudaMemsetAsync(w.queue, 0xFF, (size_t)pl.q_cap * sizeof(unsigned long long), s));
-  DGAN_CUDA_CHECK(cudaMemcpyAsync(w.queue, dp->q_init, pl.q_init.size() * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-  if (w.mom_counter != nullptr) DGAN_CUDA_CHECK(cudaMemsetAsync(w.mom_counter, 0, (size_t)w.n_pad / kRowTile * sizeof(unsigned), s));
-  c->last_status = w.status;
-  c->loop_passes = (mode == LOOP_LOSS_GRAD) ? 2 * rec_iters : 2 * rec_iters - 1;
-  const dim3 grid((unsigned)(2 * dp->n_pairs)), block(LOOP_THREADS);
-  if (c->profile == 1) {
-    // in-kernel spans: [L-step][segment] {min start, max end} of %globaltimer; per-CTA stall counters; item trace of one L-step
-    const size_t need = (size_t)rec_iters * P.n_seg * 2;
-    if (need > c->prof_cap) {
-      if (c->prof_dev) cudaFree(c->prof_dev);
-      c->prof_dev = nullptr; c->prof_cap = 0;
-      DGAN_CUDA_CHECK(cudaMalloc((void**)&c->prof_dev, need * sizeof(unsigned long long)));
-      c->prof_cap = need;
-    }
-    std::vector<unsigned long long> init(need);
-    for (size_t i = 0; i < need; i += 2) { init[i] = ~0ull; init[i + 1] = 0ull; }
-    DGAN_CUDA_CHECK(cudaMemcpyAsync(c->prof_dev, init.data(), need * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
-    DGAN_CUDA_CHECK(cudaStreamSynchronize(s));     // `init` dies with this scope (profiling mode only)
-    P.prof = c->prof_dev; c->prof_L = rec_iters; c->prof_plan = dp;
-    const int n_ctas = 2 * dp->n_pairs;
-    if (c->dbg_dev == nullptr || c->dbg_ctas < n_ctas) {
-      if (c->dbg_dev) cudaFree(c->dbg_dev);
-      c->dbg_dev = nullptr; c->dbg_ctas = 0;
-      DGAN_CUDA_CHECK(cudaMalloc((void**)&c->dbg_dev, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long)));
-      c->dbg_ctas = n_ctas;
-    }
-    DGAN_CUDA_CHECK(cudaMemsetAsync(c->dbg_dev, 0, (size_t)n_ctas * DBG_COUNT * sizeof(unsigned long long), s));
-    P.dbg = c->dbg_dev;
-    const size_t n_items = pl.n_item_slots;
-    if (c->trace_dev == nullptr || c->trace_items < n_items) {
-      if (c->trace_dev) cudaFree(c->trace_dev);
-      c->trace_dev = nullptr; c->trace_items = 0;
-      DGAN_CUDA_CHECK(cudaMalloc((void**)&c->trace_dev, n_items * 4 * sizeof(unsigned long long)));
-      c->trace_items = n_items;
-    }
-    DGAN_CUDA_CHECK(cudaMemsetAsync(c->trace_dev, 0, n_items * 4 * sizeof(unsigned long long), s));
-    P.trace = c->trace_dev; c->trace_plan = dp;
-    P.trace_step = std::max(0, rec_iters - 3);         // an L-step in the steady state
-    c->trace_step = P.trace_step;
-  }
-  cudaError_t e;
-  {
-    ProfScope ps(c, (int)c->kind_names.size() - 1, s);
-    if (c->desc.arch == DGAN_ARCH_CELEBA) projection_loop_kernel<DGAN_ARCH_CELEBA><<<grid, block, LOOP_SMEM_BYTES, s>>>(P);
-    else projection_loop_kernel<DGAN_ARCH_MNIST><<<grid, block, LOOP_SMEM_BYTES, s>>>(P);
-    c->launches++;
-    e = cudaGetLastError();
-  }
-  if (e != cudaSuccess) { set_error(std::string("projection_loop launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
-  return 0;
 }
 
 }  // namespace dgan
@@ -919,45 +729,56 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
     if ((rc = tc_build_final(c->tc, &c->tc_fin, c->fin.w, c->fin.h_in, c->fin.w_in, c->fin.C_in, c->fin.C_out,
                              c->fin.act, &c->allocs, s)))
       return fail(rc);
-    for (size_t l = 0; l < c->layers.size(); ++l) {
-      GemmLayer& L = c->layers[l];
-      if ((rc = tc2_build_direction(c->tc, L.tc_f, &L.tc2_f, L.fwd_host, L.h_used, L.w_used, 0))) return fail(rc);
-      if (l == 0) {
-        const PairTable split = linear_split_pairs(L.P_out);
-        if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, split, 1, TC_LINEAR_SPLIT, 1))) return fail(rc);
-      } else if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, L.bwd_host, L.h_in, L.w_in, 0))) {
-        return fail(rc);
+    const char* mode_env = getenv("DGAN_TC_MODE");
+    c->tc.mode = (mode_env && mode_env[0] == '1') ? 1 : 2;
+    if (getenv("DGAN_TC_DBGFLAGS")) c->tc.dbg_flags = atoi(getenv("DGAN_TC_DBGFLAGS"));
+    if (getenv("DGAN_MAX_PAIRS")) c->tc.max_pairs = atoi(getenv("DGAN_MAX_PAIRS"));
+    if (getenv("DGAN_TC_DEBUG")) {   // developer aid: per-CTA role timing of the first launches (tools/tc_timing.py)
+      c->tc.dbg_max_launches = 64;
+      if ((rc = dev_alloc(c, (void**)&c->tc.dbg, (size_t)64 * 160 * 16 * sizeof(unsigned long long)))) return fail(rc);
+      DGAN_CUDA_CHECK(cudaMemsetAsync(c->tc.dbg, 0, (size_t)64 * 160 * 16 * sizeof(unsigned long long), s));
+    }
+    c->tc.allocs = &c->allocs;
+    if (c->tc.mode == 2) {
+      if ((rc = tc2_optin_all())) return fail(rc);
+      for (size_t l = 0; l < c->layers.size(); ++l) {
+        GemmLayer& L = c->layers[l];
+        if ((rc = tc2_build_direction(c->tc, L.tc_f, &L.tc2_f, L.fwd_host, L.h_used, L.w_used, 0, &c->allocs, s))) return fail(rc);
+        if (l == 0) {
+          const PairTable split = linear_split_pairs(L.P_out);
+          if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, split, 1, TC_LINEAR_SPLIT, 1, &c->allocs, s))) return fail(rc);
+          if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b_fused, L.bwd_host, 1, 1, 1, &c->allocs, s))) return fail(rc);
+        } else if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, L.bwd_host, L.h_in, L.w_in, 0, &c->allocs, s))) {
+          return fail(rc);
+        }
       }
+      const PairTable ft = final_block_fwd_pairs(c->fin.h_in, c->fin.w_in), bt = final_block_bwd_pairs(c->fin.h_in, c->fin.w_in);
+      if ((rc = tc2_build_direction(c->tc, c->tc_fin.f, &c->tc2_fin_f, ft, c->fin.h_in / 2, c->fin.w_in / 2, 0, &c->allocs, s))) return fail(rc);
+      if ((rc = tc2_build_direction(c->tc, c->tc_fin.b, &c->tc2_fin_b, bt, c->fin.h_in, c->fin.w_in, 0, &c->allocs, s))) return fail(rc);
     }
-    const PairTable ft = final_block_fwd_pairs(c->fin.h_in, c->fin.w_in), bt = final_block_bwd_pairs(c->fin.h_in, c->fin.w_in);
-    if ((rc = tc2_build_direction(c->tc, c->tc_fin.f, &c->tc2_fin_f, ft, c->fin.h_in / 2, c->fin.w_in / 2, 0))) return fail(rc);
-    if ((rc = tc2_build_direction(c->tc, c->tc_fin.b, &c->tc2_fin_b, bt, c->fin.h_in, c->fin.w_in, 0))) return fail(rc);
-    if ((rc = build_segments(c))) return fail(rc);
-    // the loop kernel: opt in to its shared memory and size the grid to the clusters that can be co-resident (its CTA
-    // pairs wait on each other's flags, so every one of them must be on an SM)
-    DGAN_CUDA_CHECK(cudaFuncSetAttribute(projection_loop_kernel<DGAN_ARCH_MNIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM_BYTES));
-    DGAN_CUDA_CHECK(cudaFuncSetAttribute(projection_loop_kernel<DGAN_ARCH_CELEBA>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM_BYTES));
-    {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(2 * (c->tc.num_sms / 2))); cfg.blockDim = dim3(LOOP_THREADS); cfg.dynamicSmemBytes = LOOP_SMEM_BYTES;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      int n_clusters = 0;
-      cudaError_t qe = celeba ? cudaOccupancyMaxActiveClusters(&n_clusters, projection_loop_kernel<DGAN_ARCH_CELEBA>, &cfg)
-                              : cudaOccupancyMaxActiveClusters(&n_clusters, projection_loop_kernel<DGAN_ARCH_MNIST>, &cfg);
-      if (qe != cudaSuccess) { (void)cudaGetLastError(); n_clusters = c->tc.num_sms / 2; }
-      c->n_pairs = std::max(1, std::min(n_clusters, c->tc.num_sms / 2));
+  }
+  {
+    const char* ch_env = getenv("DGAN_CHAINS");
+    // measured (tools/enqueue_time.py, bench): 2 chains alternate kernels instead of overlapping them (each persistent
+    // kernel takes all 74 CTA pairs) - no gain, so the default stays 1; DGAN_CHAINS=k keeps the experiment available
+    c->n_chains = ch_env ? std::max(1, std::min(8, atoi(ch_env))) : 1;
+    if (d->use_bn) c->n_chains = 1;      // batch statistics couple all rows of a call
+    for (int k = 1; k < c->n_chains; ++k) {
+      cudaStream_t st; cudaEvent_t ev;
+      DGAN_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      DGAN_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      c->chain_streams.push_back(st); c->chain_events.push_back(ev);
     }
-    for (const LoopSegSpec& sp : c->segs) { c->kind_names.push_back(sp.name); c->kind_macs_per_row.push_back(sp.macs_per_row); }
-    c->kind_names.push_back("projection_loop (all segments, all L-steps, one launch)");
-    c->kind_macs_per_row.push_back((double)c->macs_per_row);
-  } else {
-    static const char* lname[] = {"Linear", "Generator.2", "Generator.3", "Generator.5"};
+    DGAN_CUDA_CHECK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
+  }
+  {
+    static const char* lname_m[] = {"Linear", "Generator.2", "Generator.3"};
+    static const char* lname_c[] = {"Linear", "Generator.2", "Generator.3", "Generator.5"};
     for (size_t l = 0; l < c->layers.size(); ++l) {
+      const std::string nm = celeba ? lname_c[l] : lname_m[l];
       const double macs = (double)c->layers[l].fwd_host.pairs.size() * c->layers[l].C_in * c->layers[l].C_out;
-      c->kind_names.push_back(std::string(lname[l]) + ".fwd"); c->kind_macs_per_row.push_back(macs);
-      c->kind_names.push_back(std::string(lname[l]) + ".bwd"); c->kind_macs_per_row.push_back(macs);
+      c->kind_names.push_back(nm + ".fwd"); c->kind_macs_per_row.push_back(macs);
+      c->kind_names.push_back(nm + ".bwd"); c->kind_macs_per_row.push_back(macs);
     }
     double fmacs = 0;
     for (const GemmLayer& L : c->layers) fmacs += (double)L.fwd_host.pairs.size() * L.C_in * L.C_out;
@@ -970,6 +791,7 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
   DGAN_CUDA_CHECK(cudaGetLastError());
   return DGAN_OK;
 }
+
 
 int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weights, int n_weights, void* stream) {
   if (out == nullptr || d == nullptr || weights == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
@@ -1002,51 +824,45 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
 int dgan_destroy(dgan_handle h) {
   if (h == nullptr) return DGAN_OK;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-  if (h->prof_dev) cudaFree(h->prof_dev);
-  if (h->dbg_dev) cudaFree(h->dbg_dev);
-  if (h->trace_dev) cudaFree(h->trace_dev);
+  for (cudaStream_t st : h->chain_streams) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : h->chain_events) cudaEventDestroy(ev);
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return DGAN_OK;
 }
 
+// images [lo, hi) of chain k when `batch` images are split into n balanced contiguous chains
+static inline void chain_bounds(int batch, int n, int k, int* lo, int* hi) {
+  const int base = batch / n, extra = batch % n;
+  *lo = k * base + std::min(k, extra);
+  *hi = *lo + base + (k < extra ? 1 : 0);
+}
+
 size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
   if (h == nullptr || batch <= 0 || rec_rr <= 0) return 0;
-  if (h->desc.precision == DGAN_PREC_FP16) {
-    // plan (and upload) the loop kernel's schedule for this row count now, so that dgan_reconstruct never has to
-    const DevPlan* dp = nullptr;
-    if (get_plan(h, batch * rec_rr, &dp) != 0) return 0;
+  const int n = std::min(h->n_chains, batch);
+  size_t total = 0;
+  for (int k = 0; k < n; ++k) {
+    int lo, hi;
+    chain_bounds(batch, n, k, &lo, &hi);
+    total += carve(h, (hi - lo) * rec_rr, nullptr).bytes;
   }
-  return carve(h, batch * rec_rr, nullptr).bytes;
+  return std::max(total, carve(h, batch * rec_rr, nullptr).bytes);   // dgan_forward / dgan_loss_grad use one chain
 }
 
 int64_t dgan_last_launch_count(dgan_handle h) { return h ? h->last_launches : 0; }
 int64_t dgan_macs_per_row(dgan_handle h) { return h ? h->macs_per_row : 0; }
-
-int dgan_last_status(dgan_handle h, int* status_out) {
-  if (h == nullptr || status_out == nullptr) return DGAN_ERR_INVALID_ARG;
-  *status_out = 0;
-  if (h->last_status == nullptr) return DGAN_OK;
-  uint32_t v = 0;
-  DGAN_CUDA_CHECK(cudaMemcpy(&v, h->last_status, sizeof(v), cudaMemcpyDeviceToHost));   // synchronises with the device
-  *status_out = (int)v;
-  if (v != 0) set_error("projection_loop: a dependency wait timed out (status " + std::to_string(v) + "); results of that call are invalid");
-  return DGAN_OK;
-}
 
 int dgan_forward(dgan_handle h, const float* z_dev, int n_rows, float* y_dev, void* ws, size_t ws_bytes, void* stream) {
   if (h == nullptr || z_dev == nullptr || y_dev == nullptr || n_rows <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   Workspace w;
   int rc;
-  const int64_t launches0 = h->launches;
   if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
   if ((rc = run_init_z(h, w, z_dev, 0, s))) return rc;
-  if (h->desc.precision == DGAN_PREC_FP16) rc = launch_loop(h, w, ws, nullptr, 1, 1, 1, 0.f, 0.f, 0, LOOP_FORWARD, s);
-  else rc = run_forward(h, w, nullptr, 1, 1, false, s);
-  if (rc) return rc;
+  if ((rc = run_forward(h, w, nullptr, 1, 1, false, s))) return rc;
   DGAN_CUDA_CHECK(cudaMemcpyAsync(y_dev, w.y, (size_t)n_rows * h->hwc * 4, cudaMemcpyDeviceToDevice, s));
-  h->last_launches = h->launches - launches0;
   return DGAN_OK;
 }
 
@@ -1059,12 +875,8 @@ int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, con
   int rc;
   if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
   if ((rc = run_init_z(h, w, z_dev, 0, s))) return rc;
-  if (h->desc.precision == DGAN_PREC_FP16) {
-    if ((rc = launch_loop(h, w, ws, x_dev, rec_rr, batch, 1, 0.f, 0.f, 0, LOOP_LOSS_GRAD, s))) return rc;
-  } else {
-    if ((rc = run_forward(h, w, x_dev, rec_rr, batch, true, s))) return rc;
-    if ((rc = run_backward(h, w, s))) return rc;
-  }
+  if ((rc = run_forward(h, w, x_dev, rec_rr, batch, true, s))) return rc;
+  if ((rc = run_backward(h, w, s))) return rc;
   loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, w.loss_stride_n, w.loss_stride_b, 1.0f / (float)h->hwc, n_rows, w.loss);
   DGAN_LAUNCH_CHECK(h);
   if (y_dev) DGAN_CUDA_CHECK(cudaMemcpyAsync(y_dev, w.y, (size_t)n_rows * h->hwc * 4, cudaMemcpyDeviceToDevice, s));
@@ -1091,42 +903,88 @@ int dgan_sample_z0(dgan_handle h, uint64_t seed, uint64_t z_row_offset, int n_ro
 int dgan_reconstruct(dgan_handle h, const dgan_rec_params* prm, const float* x_dev, const float* z0_dev, float* rec_dev,
                      float* loss_dev, int32_t* idx_dev, void* ws, size_t ws_bytes, void* stream) {
   if (h == nullptr || prm == nullptr || x_dev == nullptr || rec_dev == nullptr) { set_error("NULL argument"); return DGAN_ERR_INVALID_ARG; }
-  const int batch = prm->batch, rec_rr = prm->rec_rr, rec_iters = prm->rec_iters;
+  const int batch = prm->batch, rec_rr = prm->rec_rr, rec_iters = prm->rec_iters, decay_lr = prm->decay_lr;
+  const float rec_lr = prm->rec_lr, momentum = prm->momentum;
+  const uint64_t seed = prm->seed;
   if (batch <= 0 || rec_rr <= 0 || rec_iters <= 0) { set_error("batch, rec_rr and rec_iters must be positive"); return DGAN_ERR_INVALID_ARG; }
-  cudaStream_t s = (cudaStream_t)stream;
-  const int n_rows = batch * rec_rr;
-  Workspace w;
+  if (ws == nullptr) { set_error("workspace is NULL"); return DGAN_ERR_WORKSPACE; }
+  if (((uintptr_t)ws & 1023) != 0) { set_error("workspace must be 1024-byte aligned"); return DGAN_ERR_WORKSPACE; }
+  if (dgan_workspace_bytes(h, batch, rec_rr) > ws_bytes) {
+    set_error("workspace too small: need " + std::to_string(dgan_workspace_bytes(h, batch, rec_rr)) + " bytes, got " + std::to_string(ws_bytes));
+    return DGAN_ERR_WORKSPACE;
+  }
+  cudaStream_t s0 = (cudaStream_t)stream;
+  const int n_chains = h->profile ? 1 : std::min(h->n_chains, batch);   // per-kernel timing wants one chain
+  const int latent = h->desc.latent_dim;
+  struct Chain { Workspace w; cudaStream_t s; int lo, hi; };
+  std::vector<Chain> chains((size_t)n_chains);
+  size_t off = 0;
+  for (int k = 0; k < n_chains; ++k) {
+    Chain& ch = chains[(size_t)k];
+    chain_bounds(batch, n_chains, k, &ch.lo, &ch.hi);
+    ch.w = carve(h, (ch.hi - ch.lo) * rec_rr, (char*)ws + off);
+    off += ch.w.bytes;
+    int mrc;
+    if ((mrc = build_maps(h, ch.w))) return mrc;
+    ch.s = (k == 0) ? s0 : h->chain_streams[(size_t)k - 1];
+  }
   int rc;
-  if ((rc = check_ws(h, n_rows, ws, ws_bytes, &w))) return rc;
   const int64_t launches0 = h->launches;
-  h->n_rows_cur = n_rows;
-  if ((rc = run_init_z(h, w, z0_dev, prm->seed, s, (size_t)prm->z_row_offset))) return rc;
-  if (h->desc.precision == DGAN_PREC_FP16) {
-    // the whole L-step loop is one persistent kernel (kernels_loop.cuh)
-    if ((rc = launch_loop(h, w, ws, x_dev, rec_rr, batch, rec_iters, prm->rec_lr, prm->momentum, prm->decay_lr, LOOP_RECONSTRUCT, s))) return rc;
-  } else {
-    const int decay_iter = (int)std::ceil(rec_iters * 0.8);
-    const int latent = h->desc.latent_dim;
-    for (int t = 0; t < rec_iters; ++t) {
-      const bool last = (t == rec_iters - 1);
-      float lr = prm->rec_lr;
-      if (prm->decay_lr && t >= decay_iter) lr = prm->rec_lr * 0.1f;
+  h->n_rows_cur = batch * rec_rr;
+  if (n_chains > 1) {
+    DGAN_CUDA_CHECK(cudaEventRecord(h->fork_event, s0));
+    for (int k = 1; k < n_chains; ++k) DGAN_CUDA_CHECK(cudaStreamWaitEvent(chains[(size_t)k].s, h->fork_event, 0));
+  }
+  for (Chain& ch : chains) {
+    const size_t row_off = (size_t)ch.lo * rec_rr;
+    if ((rc = run_init_z(h, ch.w, z0_dev ? z0_dev + row_off * latent : nullptr, seed, ch.s, (size_t)prm->z_row_offset + row_off))) return rc;
+  }
+  const int decay_iter = (int)std::ceil(rec_iters * 0.8);
+  for (int t = 0; t < rec_iters; ++t) {
+    const bool last = (t == rec_iters - 1);
+    float lr = rec_lr;
+    if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
+    // fused Linear-backward + momentum epilogue exists (EPI_MOMENTUM) but measured slower than split-K + momentum_kernel
+    const bool fused = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 && getenv("DGAN_FUSED_MOMENTUM") != nullptr;
+    // DGAN_MOMENTUM_TAIL=1: momentum in the tail of the split-K Linear backward (the CTA completing a row tile's partial
+    // sums applies the update; no separate kernel).  Bit-identical, but measured no faster (Linear bwd 16.7 -> 27.0 us vs
+    // 16.7 + 9.5 us for the momentum kernel: 5631 vs 5616 images/s), so the separate kernel stays the default.
+    const bool tail = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 &&
+                      getenv("DGAN_MOMENTUM_TAIL") && atoi(getenv("DGAN_MOMENTUM_TAIL")) != 0;
+    for (Chain& ch : chains) {
+      const Workspace& w = ch.w;
+      cudaStream_t s = ch.s;
+      const float* x = x_dev + (size_t)ch.lo * h->hwc;
       // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
       // the L-th update is never observed, so its backward pass is not run.
-      if ((rc = run_forward(h, w, x_dev, rec_rr, batch, !last, s))) return rc;
+      if ((rc = run_forward(h, w, x, rec_rr, ch.hi - ch.lo, !last, s, /*want_y=*/last))) return rc;
       if (last) continue;
-      if ((rc = run_backward(h, w, s))) return rc;
-      const size_t zcount = (size_t)w.n_pad * latent;
-      ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
-      DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
-                                 (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, prm->momentum, zcount, w.z_h));
-      DGAN_LAUNCH_CHECK(h);
+      MomentumArgs mom;
+      mom.fused = fused; mom.lr = lr; mom.mu = momentum;
+      mom.tail = !fused && tail;
+      if ((rc = run_backward(h, w, s, mom))) return rc;
+      if (!fused && !mom.tail) {
+        const size_t zcount = (size_t)w.n_pad * latent;
+        ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
+        DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
+                                   (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
+        DGAN_LAUNCH_CHECK(h);
+      }
     }
   }
-  loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, w.loss_stride_n, w.loss_stride_b, 1.0f / (float)h->hwc, n_rows, w.loss);
-  DGAN_LAUNCH_CHECK(h);
-  select_kernel<<<batch, 256, 0, s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev, loss_dev, idx_dev);
-  DGAN_LAUNCH_CHECK(h);
+  for (Chain& ch : chains) {
+    const Workspace& w = ch.w;
+    const int nb = ch.hi - ch.lo, n_rows = nb * rec_rr;
+    loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, ch.s>>>(w.loss_part, w.n_loss_parts, w.loss_stride_n, w.loss_stride_b, 1.0f / (float)h->hwc, n_rows, w.loss);
+    DGAN_LAUNCH_CHECK(h);
+    select_kernel<<<nb, 256, 0, ch.s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev + (size_t)ch.lo * h->hwc,
+                                         loss_dev ? loss_dev + ch.lo : nullptr, idx_dev ? idx_dev + ch.lo : nullptr);
+    DGAN_LAUNCH_CHECK(h);
+  }
+  for (int k = 1; k < n_chains; ++k) {
+    DGAN_CUDA_CHECK(cudaEventRecord(h->chain_events[(size_t)k - 1], chains[(size_t)k].s));
+    DGAN_CUDA_CHECK(cudaStreamWaitEvent(s0, h->chain_events[(size_t)k - 1], 0));
+  }
   h->last_launches = h->launches - launches0;
   return DGAN_OK;
 }
@@ -1135,8 +993,7 @@ int dgan_profile_enable(dgan_handle h, int enable) {
   if (h == nullptr) return DGAN_ERR_INVALID_ARG;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   h->prof.clear();
-  h->profile = enable != 0 ? 1 : 0;
-  h->prof_L = 0;
+  h->profile = enable != 0;
   return DGAN_OK;
 }
 
@@ -1150,7 +1007,6 @@ const char* dgan_profile_kind_name(dgan_handle h, int kind) {
 int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* launches_out, double* flops_per_launch_out) {
   if (h == nullptr || ms_out == nullptr || launches_out == nullptr || flops_per_launch_out == nullptr) return DGAN_ERR_INVALID_ARG;
   const int nk = std::min(max_kinds, (int)h->kind_names.size());
-  const bool tc = h->desc.precision == DGAN_PREC_FP16;
   for (int k = 0; k < nk; ++k) {
     ms_out[k] = 0.0; launches_out[k] = 0;
     flops_per_launch_out[k] = 2.0 * h->kind_macs_per_row[k] * (double)h->n_rows_cur;
@@ -1163,173 +1019,80 @@ int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* lau
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   h->prof.clear();
-  if (tc && h->profile == 1 && h->prof_L > 0 && h->prof_dev != nullptr && h->prof_plan != nullptr) {
-    // the fused launch: its FLOPs are those of `loop_passes` generator passes; its segments are reported as in-kernel
-    // spans (first item start .. last item end over all CTA pairs, per L-step; items of neighbouring segments - and of
-    // different row pairs, which drift apart - overlap, so the spans add up to more than the launch)
-    const LoopPlan& pl = h->prof_plan->host;
-    const int n_seg = pl.n_seg, L = h->prof_L;
-    if (nk == n_seg + 1) flops_per_launch_out[n_seg] *= 0.5 * (double)h->loop_passes;
-    std::vector<unsigned long long> st((size_t)L * n_seg * 2);
-    DGAN_CUDA_CHECK(cudaMemcpy(st.data(), h->prof_dev, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (int t = 0; t < L; ++t)
-      for (int sg = 0; sg < n_seg; ++sg) {
-        const unsigned long long a = st[((size_t)t * n_seg + sg) * 2], b = st[((size_t)t * n_seg + sg) * 2 + 1];
-        if (sg >= nk || a == ~0ull || b <= a) continue;
-        ms_out[sg] += (double)(b - a) * 1e-6;
-        launches_out[sg]++;
-      }
-    h->prof_L = 0;
-  }
   return DGAN_OK;
 }
 
-// Developer aid (not in the public header): per-CTA stall counters (clock64 ticks, LoopDbg order, 16 per CTA) of the most
-// recent loop launch made under dgan_profile_enable(h, 1).  Returns the number of CTAs copied.
-int dgan_debug_loop_stalls(dgan_handle h, unsigned long long* out, int max_ctas) {
-  if (h == nullptr || out == nullptr || h->dbg_dev == nullptr) return 0;
-  const int n = std::min(max_ctas, h->dbg_ctas);
-  cudaDeviceSynchronize();
-  cudaMemcpy(out, h->dbg_dev, (size_t)n * dgan::DBG_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  return n;
-}
-
-// Developer aid (not in the public header): the traced L-step of the most recent profiled loop launch.  Per item (segment
-// after segment, row pair major, window minor): out[8i..] = {CTA pair, segment, window, row pair, time the item was taken
-// from the queue, time its operands' first MMA step could start (accumulator buffer free), epilogue begin, epilogue end}
-// (ns of %globaltimer; 0 = not recorded).  deps_out (if not NULL) receives per item up to `max_deps` indices of the items
-// it waits for (-1 padded; -2 = the previous L-step's z update).  Returns the number of items.
-int dgan_debug_loop_trace(dgan_handle h, unsigned long long* out, long long* deps_out, int max_deps, int max_items) {
-  if (h == nullptr || out == nullptr || h->trace_dev == nullptr || h->trace_plan == nullptr) return 0;
-  const LoopPlan& pl = h->trace_plan->host;
-  const size_t n_all = pl.n_item_slots;
-  const int n = (int)std::min<size_t>((size_t)max_items, n_all);
-  std::vector<unsigned long long> raw(n_all * 4);
-  cudaDeviceSynchronize();
-  cudaMemcpy(raw.data(), h->trace_dev, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  // inverse of the successor lists: the windows an item waits for
-  std::vector<std::vector<uint32_t>> preds(pl.n_win);
-  for (int sg = 0; sg + 1 < pl.n_seg; ++sg)
-    for (uint32_t w = 0; w < pl.n_windows[(size_t)sg]; ++w)
-      for (uint32_t si = pl.succ_off[pl.win_base[(size_t)sg] + w]; si < pl.succ_off[pl.win_base[(size_t)sg] + w + 1]; ++si)
-        preds[pl.win_base[pl.succ[si] >> 16] + (pl.succ[si] & 0xFFFFu)].push_back(w);
-  int sg = 0;
-  for (int e = 0; e < n; ++e) {
-    while (sg + 1 < pl.n_seg && (uint32_t)e >= pl.item_base[(size_t)sg + 1]) ++sg;
-    const uint32_t local = (uint32_t)e - pl.item_base[(size_t)sg], mp = local / pl.n_windows[(size_t)sg], win = local % pl.n_windows[(size_t)sg];
-    out[(size_t)e * 8 + 0] = raw[(size_t)e * 4 + 0] >> 48; out[(size_t)e * 8 + 1] = (unsigned long long)sg; out[(size_t)e * 8 + 2] = win; out[(size_t)e * 8 + 3] = mp;
-    out[(size_t)e * 8 + 4] = raw[(size_t)e * 4 + 0] & 0xFFFFFFFFFFFFull;
-    for (int k = 1; k < 4; ++k) out[(size_t)e * 8 + 4 + k] = raw[(size_t)e * 4 + k];
-    if (deps_out != nullptr) {
-      int k = 0;
-      if (sg == 0) deps_out[(size_t)e * max_deps + k++] = -2;
-      else
-        for (uint32_t u : preds[pl.win_base[(size_t)sg] + win]) {
-          if (k >= max_deps) break;
-          deps_out[(size_t)e * max_deps + k++] = (long long)(pl.item_base[(size_t)sg - 1] + mp * pl.n_windows[(size_t)sg - 1] + u);
-        }
-      for (; k < max_deps; ++k) deps_out[(size_t)e * max_deps + k] = -1;
-    }
-  }
-  return n;
-}
-
-// Host-only developer/test aid (not in the public header): plan one L-step of the fp16 path for `n_rows` latent rows on
-// `n_pairs` CTA pairs exactly as dgan_reconstruct would, and validate the plan with loop_check_plan.  Needs no GPU.
-// `mutate` != 0 damages the plan in one specific way first: the check must then fail (self-test of the validator).
-// Returns 0, or an error code with the failing check in dgan_last_error().
+/* developer aid (not in the public header): copy the DGAN_TC_DEBUG role-timing counters to the host */
+// Host-only developer/test aid (not in the public header): plan every tensor-core layer-direction of the fp16 path for
+// `n_rows` latent rows on `n_pairs` CTA pairs exactly as dgan_create/dgan_reconstruct would, and validate each plan
+// with tc2_check_plan.  Needs no GPU.  Returns 0, or an error code with the failing direction in dgan_last_error().
 int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int mutate) {
   using namespace dgan;
   if (d == nullptr || n_rows <= 0 || n_pairs <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
   const bool celeba = d->arch == DGAN_ARCH_CELEBA;
   const int nd = d->net_dim, latent = d->latent_dim;
   const int n_pad = ((n_rows + 2 * kRowTile - 1) / (2 * kRowTile)) * 2 * kRowTile, n_mpairs = n_pad / (2 * kRowTile);
-  struct Dir { std::string name; int N, K; PairTable tab; int h, w, force_acc, epi, out_bytes; bool fwd; };
-  std::vector<Dir> fwd, bwd;
-  fwd.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2, true});
+  struct Dir { std::string name; int N, K; PairTable tab; int h, w, force_acc, epi, out_bytes; };
+  std::vector<Dir> dirs;
+  dirs.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2});
+  dirs.push_back({"Linear.bwd", latent, 4 * nd, linear_split_pairs(16), 1, TC_LINEAR_SPLIT, 1, EPI_NONE, 4});
   struct DSpec { int c_in, c_out, h_in, h_used, in_raster; bool relu; };
   std::vector<DSpec> specs;
   if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, 4, true}, {2 * nd, nd, 8, 16, 8, true}, {nd, nd, 16, 32, 16, false}};
   else specs = {{4 * nd, 2 * nd, 4, 7, 4, true}, {2 * nd, nd, 7, 14, 7, true}};
   int li = 2;
-  bool prev_relu = true;     // the Linear's output goes through a ReLU
   for (const DSpec& sp : specs) {
     const std::string nm = "Generator." + std::to_string(li == 4 ? 5 : li);
-    fwd.push_back({nm + ".fwd", sp.c_out, sp.c_in, deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.h_used, sp.h_used, 0,
-                   sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2, true});
-    bwd.push_back({nm + ".bwd", sp.c_in, sp.c_out, deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.in_raster, sp.in_raster, 0,
-                   prev_relu ? EPI_MASK : EPI_NONE, 2, false});
-    prev_relu = sp.relu;
+    dirs.push_back({nm + ".fwd", sp.c_out, sp.c_in, deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.h_used, sp.h_used, 0,
+                    sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2});
+    dirs.push_back({nm + ".bwd", sp.c_in, sp.c_out, deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.in_raster, sp.in_raster, 0,
+                    EPI_MASK, 2});
     ++li;
   }
   const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
-  fwd.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2, true});
-  std::vector<Dir> dirs = fwd;
-  dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, prev_relu ? EPI_MASK : EPI_NONE, 2, false});
-  for (size_t i = bwd.size(); i-- > 0;) dirs.push_back(bwd[i]);
-  dirs.push_back({"Linear.bwd", latent, 4 * nd, linear_split_pairs(16), 1, TC_LINEAR_SPLIT, 1, EPI_NONE, 4, false});
-  std::vector<LoopSegSpec> segs;
-  for (size_t i = 0; i < dirs.size(); ++i) {
-    const Dir& dr = dirs[i];
-    LoopSegSpec sp;
-    sp.name = dr.name; sp.N = dr.N; sp.K = dr.K; sp.kind = loop_kind_of(dr.N, dr.epi, dr.out_bytes);
-    if (sp.kind < 0) { set_error(dr.name + ": unsupported layer shape"); return DGAN_ERR_UNSUPPORTED; }
-    sp.tab = &dirs[i].tab; sp.h_grid = dr.h; sp.w_grid = dr.w;
-    sp.max_acc = tc2_maxb(dr.N);
-    if (dr.force_acc > 0) sp.max_acc = std::min(sp.max_acc, dr.force_acc);
-    sp.in_seg = (int)i - 1; sp.fwd = dr.fwd;
-    segs.push_back(sp);
-  }
-  LoopPlan plan;
-  int rc = loop_plan(segs, n_mpairs, n_pairs, &plan);
-  if (rc) return rc;
-  if (mutate != 0) {
-    // damage a step in the middle of a multi-step window of Generator.3 fwd (segment 2) - or a table entry next to it
-    const int sg = 2;
-    uint32_t win = 0;
-    for (uint32_t w = 0; w < plan.n_windows[sg]; ++w)
-      if (plan.win_rec_off[plan.win_base[sg] + w + 1] - plan.win_rec_off[plan.win_base[sg] + w] >= 3) { win = w; break; }
-    const uint32_t wi = plan.win_base[sg] + win;
-    const size_t r0 = plan.win_rec_off[wi], r1 = plan.win_rec_off[wi + 1];
-    if (r1 - r0 < 3) { set_error("plan too small to mutate"); return DGAN_ERR_INVALID_ARG; }
-    const size_t k = r0 + 1;
-    TcRec& m = plan.tmpl_m[k];
-    TcRec* pp[2] = {&plan.tmpl_p[0][k], &plan.tmpl_p[1][k]};
-    switch (mutate) {
-      case 1: m.w[2] ^= 1u << 10; break;                                  // first-MMA flag of an op
-      case 2: m.w[2] ^= 1u << 7; break;                                   // accumulator of an op
-      case 3: pp[0]->w[4] ^= 0x01; break;                                 // weight tile staged by rank 0 only
-      case 4: pp[0]->w[2] ^= 0x01; pp[1]->w[2] ^= 0x01; break;            // input pixel of an A tile
-      case 5: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~(0xFu << 8)) | ((((pp[r]->w[0] >> 8) & 0xF) ^ 1u) << 8); break;   // k-chunk
-      case 6: plan.win_rec_off[wi + 1] -= 1; break;                       // a window loses its last step to its neighbour
-      case 7: m.w[0] ^= 1u << 18; break;                                  // MMA warp and producer disagree on the step's size (ring placement)
-      case 8: for (int r = 0; r < 2; ++r) pp[r]->w[0] |= 0xBFu; break;    // a run-time field is not blank
-      case 9: std::swap(plan.tmpl_m[k], plan.tmpl_m[k + 1]);              // two steps out of order
-              for (int r = 0; r < 2; ++r) std::swap(plan.tmpl_p[r][k], plan.tmpl_p[r][k + 1]);
-              break;
-      case 10: plan.need[wi] += 1; break;                                 // an item waits for one completion too many: never ready
-      case 11: plan.succ[plan.succ_off[wi]] ^= 1u; break;                 // an item wakes the wrong window
-      case 12: plan.succ_off[wi + 1] -= 1; plan.succ_off[wi] += 0; for (uint32_t j = wi + 1; j < plan.n_win; ++j) { if (j > wi + 1) plan.succ_off[j] -= 1; } plan.succ_off[plan.n_win] -= 1;
-               plan.succ.erase(plan.succ.begin() + plan.succ_off[wi + 1]); break;      // a successor is missing
-      case 13: plan.q_init.pop_back(); break;                             // a first-segment item is never started
-      case 14: plan.q_cap = 64; break;                                    // queue too small for what can be ready at once
-      default: break;
+  dirs.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2});
+  dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, celeba ? EPI_NONE : EPI_MASK, 2});
+  for (const Dir& dr : dirs) {
+    if (dr.N != 16 && dr.N != 48 && dr.N != 64 && dr.N != 128 && dr.N != 256) { set_error(dr.name + ": unsupported N"); return DGAN_ERR_UNSUPPORTED; }
+    int max_acc = tc2_maxb(dr.N);
+    if (dr.force_acc > 0) max_acc = std::min(max_acc, dr.force_acc);
+    const int ring = tc2_ring_bytes(dr.N, dr.epi, dr.out_bytes);
+    Tc2Plan plan;
+    int rc = tc2_plan(dr.N, dr.K, dr.tab, dr.h, dr.w, max_acc, n_mpairs, n_pairs, ring, &plan);
+    if (rc) { set_error(dr.name + ": " + dgan_last_error()); return rc; }
+    // self-test of the validator: damage the plan of Generator.3 fwd in one specific way; the check must then fail
+    if (mutate != 0 && dr.name == "Generator.3.fwd" && plan.stream_m.size() > 40) {
+      TcRec& m = plan.stream_m[20];
+      TcRec* pp[2] = {&plan.stream_p[0][20], &plan.stream_p[1][20]};
+      switch (mutate) {
+        case 1: m.w[2] ^= 1u << 10; break;                                  // first-MMA flag of an op
+        case 2: m.w[2] ^= 1u << 7; break;                                   // accumulator of an op
+        case 3: pp[0]->w[4] ^= 0x01; break;                                 // weight tile staged by rank 0 only
+        case 4: pp[0]->w[2] ^= 0x01; pp[1]->w[2] ^= 0x01; break;            // input pixel of an A tile
+        case 5: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~(0xFu << 8)) | ((((pp[r]->w[0] >> 8) & 0xF) ^ 1u) << 8); break;   // k-chunk
+        case 6: plan.eitems[0] = -1; break;                                 // epilogue list loses an item
+        case 7: for (size_t i = 0; i < plan.stream_m.size(); ++i)           // every dep -> 8: ring hazards
+                  for (int r = 0; r < 2; ++r) plan.stream_p[r][i].w[0] = (plan.stream_p[r][i].w[0] & ~(0xFu << 19)) | (8u << 19);
+                break;
+        case 8: for (int r = 0; r < 2; ++r) pp[r]->w[0] = (pp[r]->w[0] & ~0xFFu) | 0xBFu; break;   // region past the ring
+        case 9: std::swap(plan.stream_m[20], plan.stream_m[21]);            // two steps out of order
+                for (int r = 0; r < 2; ++r) std::swap(plan.stream_p[r][20], plan.stream_p[r][21]);
+                break;
+        default: break;
+      }
     }
+    std::string err;
+    if ((rc = tc2_check_plan(dr.N, dr.K, dr.tab, n_mpairs, ring, plan, &err))) { set_error(dr.name + ": " + err); return rc; }
   }
-  std::string err;
-  if ((rc = loop_check_plan(segs, plan, &err))) { set_error(err); return rc; }
-  // summary of the plan (read it with dgan_last_error() after a successful call)
-  std::string sum = "segments:";
-  for (int v = 0; v < plan.n_seg; ++v)
-    sum += " [" + segs[(size_t)v].name + " window " +
-           std::to_string(plan.shape[4 * v]) + "x" + std::to_string(plan.shape[4 * v + 1]) + " stride " + std::to_string(plan.shape[4 * v + 2]) + "x" +
-           std::to_string(plan.shape[4 * v + 3]) + ", " + std::to_string(plan.hdrs[(size_t)v].size()) + " windows, cost " +
-           std::to_string((int)(plan.cost_total[(size_t)v] / 1024)) + " KB, largest item " + std::to_string((int)(plan.cost_max[(size_t)v] / 1024)) + " KB]";
-  sum += " x " + std::to_string(plan.n_mpairs) + " row pairs; per L-step: " + std::to_string(plan.n_steps) + " steps, " + std::to_string(plan.n_mma) + " MMAs, " +
-         std::to_string(2.0 * plan.n_bytes / 1e6) + " MB staged, " + std::to_string((size_t)(plan.win_fwd + plan.win_bwd) * plan.n_mpairs) + " items, " +
-         std::to_string(plan.succ.size()) + " graph edges per row pair, queue capacity " + std::to_string(plan.q_cap);
-  set_error(sum);
   return 0;
+}
+
+int dgan_debug_tc_timing(dgan_handle h, unsigned long long* out, int max_launches) {
+  if (h == nullptr || out == nullptr || h->tc.dbg == nullptr) return 0;
+  const int n = std::min(max_launches, h->tc.dbg_launch);
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, h->tc.dbg, (size_t)n * 160 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
 }
 
 }  // extern "C"

@@ -1,18 +1,19 @@
-// CTA-pair (cta_group::2) pixel-graph GEMM: record formats, PTX wrappers and the host-side step builder.
+// Tensor-core path, version 2: CTA-pair (cta_group::2) pixel-graph GEMM.
 //
-// ncu on the first tensor-core kernel (profiles/r1a_*) showed it bound by L2->SM delivery (~7-8 TB/s with the tensor
-// pipe ~29 % busy): every CTA streamed its own copy of every weight tile.  Here two CTAs on the two SMs of a TPC form
-// one MMA of M = 256 latent rows:
-//   * each CTA stages its own 128-row activation tile A and only HALF of each weight tile (N/2 rows) - the tensor
-//     cores read the other half from the peer's shared memory, so weight traffic per SM is halved;
-//   * one CTA per SM owns all 512 TMEM columns: two buffers of 256 (the MMAs of item i+1 overlap the epilogue of item
-//     i), each holding the 1-8 accumulators of a window of output pixels;
-//   * operands live in a circular shared-memory ring of variable-size steps planned on the host: per CTA pair one
-//     contiguous stream of step records.
-// Roles per CTA: TMA producer warp / MMA issuer warp / 8 epilogue warps; only the even (leader) CTA issues
-// tcgen05.mma.cta_group::2, commits are multicast to both CTAs, TMA completions of both CTAs land on the leader's
-// "full" barrier (peer-bit mask), and the epilogue warps of both CTAs release the accumulators on the leader's
-// "acc_empty" barrier.  The kernel itself (kernels_loop.cuh) runs the whole projection loop in one launch.
+// ncu on version 1 (profiles/r1a_*) showed the tcgen05 kernels bound by L2->SM delivery
+// (~7-8 TB/s with the tensor pipe ~29 % busy): every CTA streamed its own copy of every weight
+// tile.  Here two CTAs on the two SMs of a TPC form one MMA of M = 256 latent rows:
+//   * each CTA stages its own 128-row activation tile A and only HALF of each weight tile
+//     (N/2 rows) - the tensor cores read the other half from the peer's shared memory, so
+//     weight traffic per SM is halved;
+//   * one CTA per SM owns all 512 TMEM columns: two buffers of 256 (the MMAs of item i+1 overlap the
+//     epilogue of item i), each holding the 1-8 accumulators of a window of output pixels;
+//   * operands live in a circular shared-memory ring of variable-size steps planned on the host
+//     (tc2_get_schedule): per CTA pair one contiguous stream of step records, LPT-assigned.
+// Roles per CTA: TMA producer warp / MMA issuer warp / 8 epilogue warps; only the even (leader) CTA
+// issues tcgen05.mma.cta_group::2, commits are multicast to both CTAs, TMA completions of both CTAs
+// land on the leader's "full" barrier (peer-bit mask), and the epilogue warps of both CTAs release
+// the accumulators on the leader's "acc_empty" barrier.
 #pragma once
 #include "kernels_tc.cuh"
 
@@ -51,13 +52,13 @@ __host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out
 // producer record (per cluster rank):
 //   w[0]: ring offset / 1 KB [0,8) | k-chunk [8,12) | A tiles [12,15) | B slots [15,19) | dep [19,23)
 //         dep = D: the region overlaps that of step k-D (or D = 8, barrier-slot reuse): wait until step k-D is consumed
-//   w[1]: row pair mp [0,16) | segment (layer-direction) [16,20) | first step of an item [20,21): wait for its dependencies
+//   w[1]: row pair mp [0,16)
 //   w[2..3]: 4 x u16 input pixel of A tile i
 //   w[4..5]: 8 x u8 per B slot: weight tile [0,5) | half (row offset N/2) [5,6)
 // MMA record:
 //   w[0]: ring offset / 1 KB [0,8) | A tiles [8,11) | ops [11,16) | flags [16,18): 1 = first step of an item, 2 = last
-//   w[1]: segment [0,4)
 //   w[2..7]: 12 x u16 per MMA: A tile [0,2) | first B slot [2,5) | slots - 1 [5,7) | accumulator [7,10) | first MMA into it [10,11)
+//            | B slot is in the PREVIOUS step's region [11,12) (a weight tile shared by consecutive steps is staged once)
 struct __align__(16) TcRec { uint32_t w[8]; };
 constexpr int TC2_MAX_A = 4, TC2_MAX_BSLOTS = 8, TC2_MAX_OPS = 12, TC2_NSLOT = 8;
 // Merged-N groups: when one input pixel feeds g accumulators that sit side by side in TMEM (acc, acc+1, ...) through
@@ -68,15 +69,35 @@ constexpr int TC2_MAX_A = 4, TC2_MAX_BSLOTS = 8, TC2_MAX_OPS = 12, TC2_NSLOT = 8
 constexpr int TC2_REC_BATCH = 16;
 constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // producer + MMA warp rings
 
-// Output staging tiles per CTA: one per epilogue half (double-buffering them was measured: no gain).
+// Output staging tiles per CTA: one per epilogue half, or two per half (the next tile is written while the TMA
+// store of the previous one still reads shared memory) for the kernels whose epilogue is the critical path:
+// Linear forward (N = 256: 4 tiles per item, 2-3 items per CTA pair) and the last layer's backward.
+#ifndef DGAN_EPI_DB
+#define DGAN_EPI_DB 0
+#endif
 __host__ __device__ constexpr int tc2_epi_tiles(int n_tile, int epi, int out_bytes) {
-  return tc2_tma_epilogue(n_tile, epi, out_bytes) ? 2 : 0;
+  if (!tc2_tma_epilogue(n_tile, epi, out_bytes)) return 0;
+  if (DGAN_EPI_DB == 2) return 4;
+  if (DGAN_EPI_DB == 1 && ((n_tile == 256 && epi == EPI_BIAS_RELU) || (n_tile == 64 && epi == EPI_MASK))) return 4;
+  return 2;
 }
 __host__ __device__ constexpr int tc2_ring_bytes(int n_tile, int epi, int out_bytes) {
   const int epi_b = tc2_epi_tiles(n_tile, epi, out_bytes) * TC2_TILE_BYTES;
   const int raw = ((TC2_SMEM_MAX - 1024 - 256 - TC2_STAGING_BYTES - epi_b) / 1024) * 1024;
-  return raw > 255 * 1024 ? 255 * 1024 : raw;        // ring offsets are 8-bit KB
+  return raw > 255 * 1024 ? 255 * 1024 : raw;
 }
+
+template <int N_TILE, int EPI = EPI_NONE, int OUT_BYTES = 2>
+struct Tc2Cfg {
+  static constexpr int HALF_B = (N_TILE / 2) * 128;                      // bytes of this CTA's half weight tile
+  static constexpr int ACC_STRIDE = tc2_acc_stride(N_TILE);
+  static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (8 / 4 / 2 / 1)
+  static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
+  static constexpr int EPI_TILES = tc2_epi_tiles(N_TILE, EPI, OUT_BYTES);   // output staging tiles (2 or 4)
+  static constexpr int EPI_BYTES = EPI_TILES * TC2_TILE_BYTES;
+  static constexpr int RING_BYTES = tc2_ring_bytes(N_TILE, EPI, OUT_BYTES);          // operand ring (offsets are 8-bit KB)
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256;
+};
 
 namespace ptx {
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -164,13 +185,450 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 }
 }  // namespace ptx
 
+// k-th item (window << 16 | row pair) of CTA pair `pair` from the host-computed table [slot][pair] (-1 = no more work).
+// The host assigns items largest-first to the least-loaded pair (LPT) with the cost model of tc2_get_schedule.
+__device__ __forceinline__ int tc2_item_at(const int* __restrict__ order, int k, int pair, int n_pairs, int n_slots) {
+  return k < n_slots ? __ldg(order + (size_t)k * n_pairs + pair) : -1;
+}
+
+template <int N_TILE, int EPI, typename TOUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const __grid_constant__ CUtensorMap tm_out,
+                  const TcItem2* __restrict__ items, const TcRec* __restrict__ stream_p0, const TcRec* __restrict__ stream_p1,
+                  const TcRec* __restrict__ stream_m, const uint32_t* __restrict__ stream_off,
+                  const int* __restrict__ eitems, int n_slots,
+                  TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
+                  const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
+  using Cfg = Tc2Cfg<N_TILE, EPI, (int)sizeof(TOUT)>;
+  constexpr bool TMA_EPI = Cfg::TMA_EPI;
+  constexpr int HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + Cfg::RING_BYTES;            // output staging tiles: EPI_TILES / 2 per epilogue half
+  const uint32_t stg_base = epi_base + Cfg::EPI_BYTES;              // [producer ring][MMA ring] of TcRec
+  const uint32_t bar_base = stg_base + TC2_STAGING_BYTES;
+  // full[s] @ +8s (s<8), empty[s] @ +64+8s, acc_full[2] @ +128, acc_empty[2] @ +144, tmem slot @ +160, momentum-tail flag @ +200
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
+  const uint32_t tmem_slot = bar_base + 160;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_b);
+    for (int s = 0; s < TC2_NSLOT; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);    // leader's producer arrive.expect_tx (bytes of both CTAs)
+      ptx::mbar_init(bar_empty + 8 * s, 1);   // one multicast commit per CTA
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar_acc_full + 8 * b, 1);
+      ptx::mbar_init(bar_acc_empty + 8 * b, 2 * TC2_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
+    }
+    if (TMA_EPI) ptx::prefetch_tmap(&tm_out);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                     // barriers of BOTH CTAs initialised before any remote signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // The schedule tables are constants: fetch each role's first entries before the PDL wait so their latency
+  // overlaps the previous kernel's tail as well.
+  uint32_t rbeg = 0, rend = 0;
+  uint4 mine = make_uint4(0, 0, 0, 0);
+  int item_first = -1;
+  const TcRec* __restrict__ stream = warp == 1 ? stream_m : (rank ? stream_p1 : stream_p0);
+  if (warp <= 1) {
+    rbeg = __ldg(stream_off + pair); rend = __ldg(stream_off + pair + 1);
+    if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);   // lane = 16-byte half
+  } else {
+    item_first = tc2_item_at(eitems, 0, pair, n_pairs, n_slots);
+  }
+  // everything above overlapped the previous kernel's tail (PDL); from here on we read what it wrote
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    // The whole warp walks the step list convergently; every table value is loaded from a
+    // warp-uniform address so the TMA operands live in uniform registers (no per-instruction
+    // R2UR/ELECT loop), and one elected lane issues.
+    uint32_t it = 0;
+    long long t_wait = 0;
+    const uint32_t ring = stg_base;
+    for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
+      ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
+      __syncwarp();
+      if (2 * (base + TC2_REC_BATCH) + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH) + lane);
+      const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
+      for (uint32_t i = 0; i < cnt; ++i, ++it) {
+        const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
+        const uint2 r1 = ptx::ld_shared_v2(ring + i * 32u + 16u);
+        const uint32_t slot = it & (TC2_NSLOT - 1);
+        const int kc = (r0.x >> 8) & 0xF, nA = (r0.x >> 12) & 0x7, nB = (r0.x >> 15) & 0xF;
+        const uint32_t dep = (r0.x >> 19) & 0xF;
+        const int row0 = (2 * (int)(r0.y & 0xFFFFu) + (int)rank) * kRowTile;
+        const long long tw0 = fa.dbg ? clock64() : 0;
+        if (it >= dep) ptx::mbar_wait(bar_empty + 8 * ((it - dep) & (TC2_NSLOT - 1)), ((it - dep) >> 3) & 1);   // step it-dep consumed
+        // implied by the wait above (steps are consumed in order); observing every phase of this slot exactly once
+        // before it is re-armed keeps the barrier protocol checkable (compute-sanitizer synccheck)
+        if (dep != TC2_NSLOT && it >= TC2_NSLOT) ptx::mbar_wait(bar_empty + 8 * slot, ((it - TC2_NSLOT) >> 3) & 1);
+        if (fa.dbg) t_wait += clock64() - tw0;
+        const uint32_t full = bar_full + 8 * slot;
+        const uint32_t sa = smem_base + ((r0.x & 0xFFu) << 10);
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_expect_tx(full, 2u * (uint32_t)(nA * TC_A_BYTES + nB * HALF_B));
+#pragma unroll
+          for (int a = 0; a < TC2_MAX_A; ++a) {
+            if (a >= nA) break;
+            const int p = (int)((((a < 2) ? r0.z : r0.w) >> (16 * (a & 1))) & 0xFFFFu);
+            ptx::tma_load_3d_2sm(sa + a * TC_A_BYTES, &tm_a, full, kc * 64, row0, p);
+          }
+          const uint32_t sb = sa + nA * TC_A_BYTES;
+#pragma unroll
+          for (int b = 0; b < TC2_MAX_BSLOTS; ++b) {
+            if (b >= nB) break;
+            const uint32_t e = ((b < 4) ? r1.x : r1.y) >> (8 * (b & 3));
+            ptx::tma_load_3d_2sm(sb + b * HALF_B, &tm_b, full, kc * 64, (int)((e >> 5) & 1u) * (N_TILE / 2), (int)(e & 0x1Fu));
+          }
+        }
+        __syncwarp();
+      }
+      __syncwarp();
+    }
+    // drain: the last steps' "consumed" signals are otherwise never observed (nobody leaves while MMAs still read smem)
+    for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
+    if (fa.dbg && lane == 0) fa.dbg[blockIdx.x * 16 + 0] = (unsigned long long)t_wait;
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_f16(256, N_TILE);
+      uint32_t it = 0, item_count = 0;
+      long long t_wait_full = 0, t_wait_acc = 0, t_issue = 0;
+      const bool fine = fa.dbg != nullptr && !(fa.dbg_flags & 8);   // per-step clocks (perturbs the loop)
+      const bool no_mma = (fa.dbg_flags & 16) != 0;                 // timing experiment: commits only
+      const long long t_mma_start = fa.dbg ? clock64() : 0;
+      unsigned long long gt_mma0 = 0, gt_first = 0;
+      if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_mma0));
+      const uint32_t ring = stg_base + TC2_REC_BATCH * (uint32_t)sizeof(TcRec);
+      const uint64_t desc0 = make_smem_desc_sw128(smem_base);
+      const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
+      uint32_t buf = 0, prev_b_lo0 = 0;
+      for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
+        ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
+        __syncwarp();
+        if (2 * (base + TC2_REC_BATCH) + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + base + TC2_REC_BATCH) + lane);
+        const uint32_t cnt = min((uint32_t)TC2_REC_BATCH, rend - base);
+        for (uint32_t i = 0; i < cnt; ++i, ++it) {
+          const uint4 r0 = ptx::ld_shared_v4(ring + i * 32u);
+          const uint4 r1 = ptx::ld_shared_v4(ring + i * 32u + 16u);
+          const uint32_t slot = it & (TC2_NSLOT - 1), phase = (it >> 3) & 1;
+          const int nA = (r0.x >> 8) & 0x7, n_ops = (r0.x >> 11) & 0x1F;
+          const uint32_t flags = (r0.x >> 16) & 0x3u;
+          if (flags & 1u) {                                   // first step of an item: its accumulator buffer must be drained
+            buf = item_count & 1;
+            const long long ta0 = fine ? clock64() : 0;
+            ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
+            if (fine) t_wait_acc += clock64() - ta0;
+          }
+          const long long tf0 = fine ? clock64() : 0;
+          ptx::mbar_wait(bar_full + 8 * slot, phase);
+          const long long tf1 = fine ? clock64() : 0;
+          if (fa.dbg && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_first));
+          ptx::tc_fence_after();
+          // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
+          const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
+          const uint32_t b_lo0 = a_lo0 + (uint32_t)nA * (uint32_t)(TC_A_BYTES >> 4);
+          if (ptx::elect_one()) {
+            const uint32_t d0 = tmem_base + buf * TC2_BUF_COLS;
+            const uint32_t opw[6] = {r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int oi = 0; oi < TC2_MAX_OPS; ++oi) {
+              if (oi >= (no_mma ? 0 : n_ops)) break;
+              const uint32_t e = opw[oi >> 1] >> (16 * (oi & 1));
+              const uint32_t first = (e >> 10) & 1u;
+              const uint32_t a_lo = a_lo0 + (e & 3u) * (uint32_t)(TC_A_BYTES >> 4);
+              const uint32_t b_lo = (((e >> 11) & 1u) ? prev_b_lo0 : b_lo0) + ((e >> 2) & 7u) * (uint32_t)(HALF_B >> 4);
+              const uint32_t d = d0 + ((e >> 7) & 7u) * ACC_STRIDE;
+              const uint32_t idg = idesc + ((e >> 5) & 3u) * ((uint32_t)(N_TILE >> 3) << 17);   // N = slots * N_TILE
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idg,
+                                  (k > 0 || !first) ? 1u : 0u);
+            }
+            ptx::umma_commit_2sm(bar_empty + 8 * slot);           // this step is consumed (both CTAs); the host planner knows
+                                                                  // which later step may still read its weight tiles
+            if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
+          }
+          __syncwarp();
+          prev_b_lo0 = b_lo0;
+          if (flags & 2u) ++item_count;
+          if (fine) { t_wait_full += tf1 - tf0; t_issue += clock64() - tf1; }
+        }
+        __syncwarp();
+      }
+      // drain: observe the release of the last (up to two) accumulator buffers by the epilogue warps of both CTAs
+      for (uint32_t j = item_count > 2 ? item_count - 2 : 0; j < item_count; ++j) ptx::mbar_wait(bar_acc_empty + 8 * (j & 1), (j >> 1) & 1);
+      if (fa.dbg && lane == 0) {
+        fa.dbg[blockIdx.x * 16 + 1] = (unsigned long long)t_wait_full;
+        fa.dbg[blockIdx.x * 16 + 2] = (unsigned long long)t_wait_acc;
+        fa.dbg[blockIdx.x * 16 + 3] = (unsigned long long)t_issue;
+        fa.dbg[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_mma_start);   // MMA warp: whole item loop
+        unsigned long long gt_mma1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_mma1));
+        fa.dbg[blockIdx.x * 16 + 8] = gt_mma0; fa.dbg[blockIdx.x * 16 + 9] = gt_mma1; fa.dbg[blockIdx.x * 16 + 10] = gt_first;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    // Two warps per TMEM lane quarter split the (accumulator, 32-column chunk) units of an item;
+    // the TMEM load of a warp's next unit is in flight while it converts and stores the current one.
+    const int lq = warp & 3;                          // TMEM lanes this warp may access
+    const int half = (warp - 2) >> 2;                 // 0 | 1: which of the two warps of this quarter
+    const int row = lq * 32 + lane;
+    uint32_t item_count = 0, unit_count = 0;
+    long long t_ewait = 0, t_ework = 0;
+    const long long t_start = fa.dbg ? clock64() : 0;
+    unsigned long long gt_start = 0;
+    if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
+    for (int kk = 0, item_e = item_first, item_next; item_e >= 0; ++kk, ++item_count, item_e = item_next) {
+      item_next = tc2_item_at(eitems, kk + 1, pair, n_pairs, n_slots);      // (window << 16 | row pair), one item ahead
+      const int win = item_e >> 16, mp = item_e & 0xFFFF;
+      const TcItem2* ip = items + win;
+      const int n_acc = (int)ip->n_acc;
+      const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
+      const uint32_t buf = item_count & 1;
+      const uint32_t tbuf = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * TC2_BUF_COLS;
+      constexpr bool FINAL = (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3);
+      float4 xq_next[FINAL ? (EPI == EPI_FINAL_SIGMOID1 ? 4 : 12) : 1];
+      if (FINAL && half < n_acc)     // first block's target pixels: in flight while the MMAs finish
+        tc_final_targets<(EPI == EPI_FINAL_SIGMOID1 ? 1 : 3)>(reinterpret_cast<float4(&)[EPI == EPI_FINAL_SIGMOID1 ? 4 : 12]>(xq_next), fa, ip->q[half], (int)n);
+      const long long te0 = fa.dbg ? clock64() : 0;
+      ptx::mbar_wait(bar_acc_full + 8 * buf, (item_count >> 1) & 1);
+      const long long te1 = fa.dbg ? clock64() : 0;
+      ptx::tc_fence_after();
+      if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
+        constexpr int CO = (EPI == EPI_FINAL_SIGMOID1) ? 1 : 3;
+        float4 xq[4 * CO];
+        for (int a = half; a < n_acc; a += 2) {
+#pragma unroll
+          for (int j = 0; j < 4 * CO; ++j) xq[j] = xq_next[j];
+          if (a + 2 < n_acc) tc_final_targets<CO>(reinterpret_cast<float4(&)[4 * CO]>(xq_next), fa, ip->q[a + 2], (int)n);   // next block's targets in flight
+          const uint32_t taddr = tbuf + (uint32_t)(a * ACC_STRIDE);
+          if (EPI == EPI_FINAL_SIGMOID1)
+            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out),
+                                              reinterpret_cast<const float4(&)[4]>(xq));
+          else
+            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out),
+                                           reinterpret_cast<const float4(&)[12]>(xq));
+        }
+      } else if (TMA_EPI) {
+        // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 ->
+        //      128B-swizzled smem tile -> one TMA store per 128x64 tile; mask tiles arrive by TMA load.
+        constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
+        const int n_units = n_acc * G;
+        constexpr int TPH = Cfg::EPI_TILES >= 2 ? Cfg::EPI_TILES / 2 : 1;   // staging tiles per epilogue half
+        const bool t0 = (warp == 2 + 4 * half) && lane == 0;  // issues this half's bulk copies
+        const int row0 = (2 * mp + (int)rank) * kRowTile;
+        const uint32_t swz = (uint32_t)(row & 7);
+        uint32_t r0[32], r1[32];
+        unsigned long long mbits = ~0ull, mbits_next = ~0ull;
+        if (half < n_units) {
+          const int a = half / G, g = half % G;
+          if (EPI == EPI_MASK) mbits_next = __ldg(fa.mb_in + ((size_t)ip->q[a] * n_pad + n) * G + g);
+          ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64), r0);
+          ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64 + 32), r1);
+        }
+        for (int u = half; u < n_units; u += 2) {
+          const int a = u / G, g = u % G, q = ip->q[a];
+          mbits = mbits_next;
+          ptx::tmem_ld_wait();
+          uint32_t pk[32];
+          {
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }   // out_scale == 1 (checked at launch)
+            if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
+              const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + g * 64);
+#pragma unroll
+              for (int j4 = 0; j4 < 16; ++j4) {
+                const float4 b = __ldg(bp + j4);
+                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+              }
+              if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+            }
+            if (EPI == EPI_BIAS_RELU && fa.mb_out != nullptr) {
+              unsigned long long bits = 0ull;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) bits |= (unsigned long long)(v[j] > 0.f) << j;
+              fa.mb_out[((size_t)q * n_pad + n) * G + g] = bits;
+            }
+            if (EPI == EPI_MASK) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j)
+                if (!((mbits >> j) & 1ull)) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pk[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+          }
+          if (u + 2 < n_units) {                           // next unit's accumulator columns: in flight during the store phase
+            const int a2 = (u + 2) / G, g2 = (u + 2) % G;
+            if (EPI == EPI_MASK) mbits_next = __ldg(fa.mb_in + ((size_t)ip->q[a2] * n_pad + n) * G + g2);
+            ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64), r0);
+            ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64 + 32), r1);
+          }
+          const uint32_t s_out = epi_base + (uint32_t)(half * TPH + (int)(unit_count & (TPH - 1))) * TC2_TILE_BYTES;
+          ++unit_count;
+          if (t0) { if (TPH == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0(); }   // the store that last read s_out is done
+          ptx::named_bar_sync(1 + half, 128);              // s_out free
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::st_shared_v4(s_out + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1 + half, 128);              // tile complete
+          if (t0) {
+            ptx::tma_store_3d(&tm_out, s_out, g * 64, row0, q);
+            ptx::bulk_commit();
+          }
+        }
+      } else {
+        constexpr int CH = N_TILE >= 32 ? N_TILE / 32 : 1;     // 32-column chunks per accumulator
+        const int n_units = n_acc * CH;
+        uint32_t rA[32], rB[32];
+        uint4 mA[4], mB[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mA[j] = make_uint4(0, 0, 0, 0); mB[j] = make_uint4(0, 0, 0, 0); }
+        int u = half;
+        if (u < n_units) {
+          ptx::tmem_ld32(tbuf + (uint32_t)((u / CH) * ACC_STRIDE + (u % CH) * 32), rA);
+          if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mA, mask_src, ip->q[u / CH], (u % CH) * 32, n, n_pad);
+        }
+        for (; u < n_units; u += 4) {
+          ptx::tmem_ld_wait();
+          if (u + 2 < n_units) {
+            ptx::tmem_ld32(tbuf + (uint32_t)(((u + 2) / CH) * ACC_STRIDE + ((u + 2) % CH) * 32), rB);
+            if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mB, mask_src, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad);
+          }
+          if (EPI == EPI_MOMENTUM) tc_momentum_chunk(rA, (u % CH) * 32, n, N_TILE, fa);
+          else tc_store_chunk<N_TILE, EPI, TOUT>(rA, mA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
+          if (u + 2 < n_units) {
+            ptx::tmem_ld_wait();
+            if (u + 4 < n_units) {
+              ptx::tmem_ld32(tbuf + (uint32_t)(((u + 4) / CH) * ACC_STRIDE + ((u + 4) % CH) * 32), rA);
+              if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mA, mask_src, ip->q[(u + 4) / CH], ((u + 4) % CH) * 32, n, n_pad);
+            }
+            if (EPI == EPI_MOMENTUM) tc_momentum_chunk(rB, ((u + 2) % CH) * 32, n, N_TILE, fa);
+            else tc_store_chunk<N_TILE, EPI, TOUT>(rB, mB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote(bar_acc_empty + 8 * buf, 0);
+      if (EPI == EPI_NONE && sizeof(TOUT) == 4 && fa.m_counter != nullptr) {
+        // ---- momentum in the tail of the split-K Linear backward.  Every epilogue thread has stored its share of this
+        //      item's partial sums; the CTA that completes the last partial of its 128-row tile applies the update
+        //      (same arithmetic and summation order as momentum_kernel: parts 0, 1, 2, ...).
+        const uint32_t flag_addr = bar_base + 200;
+        const unsigned rt = 2u * (unsigned)mp + rank;
+        __threadfence();
+        ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
+        if (warp == 2 && lane == 0) {
+          const unsigned ticket = atomicAdd(fa.m_counter + rt, 1u);
+          ptx::st_shared_u32(flag_addr, ticket == (unsigned)TC_LINEAR_SPLIT - 1u ? 1u : 0u);
+        }
+        ptx::named_bar_sync(3, 32 * TC2_EPI_WARPS);
+        if (ptx::ld_shared_u32(flag_addr) != 0u) {
+          __threadfence();
+          const float* __restrict__ gp = reinterpret_cast<const float*>(out);
+          const size_t base = (size_t)rt * kRowTile * N_TILE;
+          const int tid = (warp - 2) * 32 + lane;
+          // 4 float4 positions per thread in flight at a time (the loop is latency-bound: 6 L2 reads per position)
+          constexpr int STRIDE = 4 * 32 * TC2_EPI_WARPS, UNR = 4;
+          for (int e0 = tid * 4; e0 < kRowTile * N_TILE; e0 += UNR * STRIDE) {
+            float4 gs[UNR], vv[UNR], zz[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const size_t i = base + (size_t)(e0 + u * STRIDE);
+              gs[u] = __ldcg(reinterpret_cast<const float4*>(gp + i));
+              vv[u] = *reinterpret_cast<const float4*>(fa.mv + i);
+              zz[u] = *reinterpret_cast<const float4*>(fa.mz + i);
+            }
+            float4 t[TC_LINEAR_SPLIT - 1][UNR];      // all partial sums of the 4 positions in flight together
+#pragma unroll
+            for (int pp = 1; pp < TC_LINEAR_SPLIT; ++pp)
+#pragma unroll
+              for (int u = 0; u < UNR; ++u)
+                t[pp - 1][u] = __ldcg(reinterpret_cast<const float4*>(gp + base + (size_t)(e0 + u * STRIDE) + (size_t)pp * fa.m_count));
+#pragma unroll
+            for (int pp = 1; pp < TC_LINEAR_SPLIT; ++pp)      // fixed order: parts 0, 1, 2, 3 (as momentum_kernel)
+#pragma unroll
+              for (int u = 0; u < UNR; ++u) { gs[u].x += t[pp - 1][u].x; gs[u].y += t[pp - 1][u].y; gs[u].z += t[pp - 1][u].z; gs[u].w += t[pp - 1][u].w; }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const size_t i = base + (size_t)(e0 + u * STRIDE);
+              float4 v4 = vv[u], z4 = zz[u];
+              v4.x = fmaf(fa.m_mu, v4.x, fa.m_gmul * gs[u].x); v4.y = fmaf(fa.m_mu, v4.y, fa.m_gmul * gs[u].y);
+              v4.z = fmaf(fa.m_mu, v4.z, fa.m_gmul * gs[u].z); v4.w = fmaf(fa.m_mu, v4.w, fa.m_gmul * gs[u].w);
+              z4.x -= fa.m_lr * v4.x; z4.y -= fa.m_lr * v4.y; z4.z -= fa.m_lr * v4.z; z4.w -= fa.m_lr * v4.w;
+              *reinterpret_cast<float4*>(fa.mv + i) = v4;
+              *reinterpret_cast<float4*>(fa.mz + i) = z4;
+              if (fa.mz_h != nullptr)
+                *reinterpret_cast<uint2*>(fa.mz_h + i) = make_uint2(pack_half2(z4.x, z4.y), pack_half2(z4.z, z4.w));
+            }
+          }
+          if (tid == 0) fa.m_counter[rt] = 0u;             // ready for the next launch
+        }
+      }
+      if (fa.dbg) { t_ewait += te1 - te0; t_ework += clock64() - te1; }
+    }
+    if (TMA_EPI && lane == 0 && (warp == 2 || warp == 6)) ptx::bulk_wait_all0();   // stores landed before exit
+    if (fa.dbg && warp == 2 && lane == 0) {
+      fa.dbg[blockIdx.x * 16 + 5] = (unsigned long long)t_ework;
+      unsigned long long gt_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+      fa.dbg[blockIdx.x * 16 + 6] = gt_start;      // ns, after the PDL wait
+      fa.dbg[blockIdx.x * 16 + 7] = gt_end;        // ns, after this CTA's last epilogue
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();     // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+struct Tc2Schedule {           // one window tiling of a layer-direction + its item -> CTA-pair assignment, uploaded
+  TcItem2* items = nullptr;
+  TcRec* stream_p[2] = {nullptr, nullptr};   // producer records per cluster rank; per CTA pair: its items' steps, concatenated
+  TcRec* stream_m = nullptr;       // MMA records, same indexing
+  uint32_t* stream_off = nullptr;  // [n_pairs + 1] record offsets into the streams
+  int* eitems = nullptr;           // [n_slots][n_pairs] (window << 16 | row pair) for the epilogue warps, or -1
+  int n_slots = 0, n_pairs = 0;
+  int n_windows = 0;
+  int wh = 0, ww = 0, sy = 1, sx = 1;
+};
 struct TcWeights2 {
-  CUtensorMap tm_b;            // box {64, N/2, 1}: one CTA's half of a weight tile
-  PairTable tab;               // host copy of the layer's (input pixel, tap) contributions
+  CUtensorMap tm_b;            // box {64, N/2, 1}
+  PairTable tab;               // host copy: schedules are built lazily per batch size
   int h_grid = 0, w_grid = 0, max_acc = 1;
+  mutable std::vector<std::pair<int, Tc2Schedule>> by_mpairs;   // chosen schedule per n_mpairs (lazy cache)
 };
 
 static int tc2_maxb(int N) { return TC2_BUF_COLS / tc2_acc_stride(N); }
@@ -182,6 +640,7 @@ struct Tc2HostStep {
   uint8_t b_ent[2][TC2_MAX_BSLOTS] = {{0}, {0}};
   uint16_t ops[TC2_MAX_OPS] = {0};
   int n_tile_mmas = 0;         // un-merged count (statistics)
+  bool uses_prev = false;      // some op reads a weight tile the previous step staged
   int bytes = 0;               // operand bytes staged per CTA
 };
 struct Tc2HostItem {
@@ -192,11 +651,10 @@ struct Tc2HostItem {
 
 // Steps of one window (accumulator a <-> output pixel qs[a]).  Input pixels are taken in ascending order and packed
 // greedily into steps of <= max_a A tiles (max_a = 1: one input pixel per step); a weight tile needed by several
-// pixels of a step is staged once.  (Re-using the weight tiles of the PREVIOUS step as well was measured in round 1:
-// 5-15 % fewer bytes, but 2 % slower - less ring capacity in flight, fewer merged-N MMAs - and is gone.)  Within a pixel, runs of consecutive accumulators whose tiles nobody else in
+// pixels of a step is staged once.  Within a pixel, runs of consecutive accumulators whose tiles nobody else in
 // the step uses (and whose first-MMA flags agree) become one merged-N MMA.
 static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int N, int K, int max_g, int max_a,
-                           int step_max_bytes, Tc2HostItem* out) {
+                           int step_max_bytes, bool share_prev, Tc2HostItem* out) {
   const int kch = K / 64, half_b = (N / 2) * 128;
   out->hdr = TcItem2{};
   out->hdr.n_acc = (uint32_t)qs.size();
@@ -222,16 +680,21 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
     for (size_t b0 = 0; b0 < g.second.size(); b0 += (size_t)ent_cap)
       px.push_back({g.first, std::vector<std::pair<int, int>>(g.second.begin() + b0,
                                                                g.second.begin() + std::min(g.second.size(), b0 + (size_t)ent_cap))});
-  // ---- phase 1: greedy groups
+  // ---- phase 1: greedy groups.  A weight tile staged by the immediately preceding group of the same k-chunk phase is
+  //      still in the ring (the planner keeps that step's region alive one step longer): it is not staged again.
   struct Group { size_t i0, i1; std::vector<int> staged; };
   std::vector<Group> groups;
   {
     size_t i0 = 0;
+    std::vector<int> prev_staged;
     while (i0 < px.size()) {
       size_t i1 = i0;
       std::vector<int> staged;      // tiles this group loads itself
       int n_ent = 0;
-      auto have = [&](int t) { return std::find(staged.begin(), staged.end(), t) != staged.end(); };
+      auto have = [&](int t) {
+        return std::find(staged.begin(), staged.end(), t) != staged.end() ||
+               (share_prev && std::find(prev_staged.begin(), prev_staged.end(), t) != prev_staged.end());
+      };
       while (i1 < px.size() && (int)(i1 - i0) < max_a) {
         int fresh = 0;
         std::vector<int> fresh_tiles;
@@ -249,17 +712,24 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
         ++i1;
       }
       groups.push_back({i0, i1, staged});
+      prev_staged = staged;
       i0 = i1;
     }
   }
-  // ---- phase 2: ops + B slots.  A tile is "single use" (mergeable into an N = g*N_TILE MMA) only if no other pixel of
-  //      its group needs it in the plain half-per-CTA layout.
+  // ---- phase 2: ops + B slots.  A tile is "single use" (mergeable into an N = g*N_TILE MMA) only if neither another
+  //      pixel of its group nor the next group needs it in the plain half-per-CTA layout.
   uint32_t seen = 0;
+  int prev_slot_of[32];
+  for (int t = 0; t < 32; ++t) prev_slot_of[t] = -1;
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     const Group& G = groups[gi];
     std::vector<int> use(32, 0);
     for (size_t i = G.i0; i < G.i1; ++i)
       for (auto& ta : px[i].second) ++use[ta.first];
+    if (share_prev && gi + 1 < groups.size())
+      for (size_t i = groups[gi + 1].i0; i < groups[gi + 1].i1; ++i)
+        for (auto& ta : px[i].second)
+          if (std::find(G.staged.begin(), G.staged.end(), ta.first) != G.staged.end()) ++use[ta.first];
     Tc2HostStep st;
     st.nA = (int)(G.i1 - G.i0);
     int slot_of[32];
@@ -270,9 +740,14 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
       for (size_t e = 0; e < ent.size();) {
         const int acc0 = ent[e].second, t0 = ent[e].first;
         const bool f0 = !(seen & (1u << acc0));
+        const bool own = std::find(G.staged.begin(), G.staged.end(), t0) != G.staged.end();
         size_t g = 1;
-        int slot;
-        if (use[t0] == 1) {
+        int slot, from_prev = 0;
+        if (!own) {                                     // staged by the previous step, plain layout
+          slot = prev_slot_of[t0];
+          from_prev = 1;
+          st.uses_prev = true;
+        } else if (use[t0] == 1) {
           while ((int)g < max_g && e + g < ent.size() && ent[e + g].second == acc0 + (int)g && use[ent[e + g].first] == 1 &&
                  std::find(G.staged.begin(), G.staged.end(), ent[e + g].first) != G.staged.end() &&
                  (!(seen & (1u << ent[e + g].second))) == f0)
@@ -291,7 +766,7 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
           for (int r = 0; r < 2; ++r) st.b_ent[r][slot] = (uint8_t)((t0 & 0x1F) | (r << 5));
           st.nB += 1;
         }
-        st.ops[st.n_ops++] = (uint16_t)((i - G.i0) | (slot << 2) | ((g - 1) << 5) | (acc0 << 7) | ((f0 ? 1 : 0) << 10));
+        st.ops[st.n_ops++] = (uint16_t)((i - G.i0) | (slot << 2) | ((g - 1) << 5) | (acc0 << 7) | ((f0 ? 1 : 0) << 10) | (from_prev << 11));
         st.n_tile_mmas += (int)g;
         for (size_t jj = 0; jj < g; ++jj) seen |= 1u << ent[e + jj].second;
         e += g;
@@ -299,6 +774,7 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
     }
     st.bytes = st.nA * TC_A_BYTES + st.nB * half_b;
     out->steps.push_back(st);
+    for (int t = 0; t < 32; ++t) prev_slot_of[t] = slot_of[t];
   }
   // k-chunk outermost: every accumulator then sums its (k-chunk, input pixel) contributions in one canonical order
   // - ascending k-chunk, ascending pixel - whatever the window shape and step grouping, so results do not depend
@@ -334,7 +810,8 @@ static void tc2_enumerate_windows(int h_grid, int w_grid, int wh, int ww, int sy
 }
 
 static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2, const PairTable& tab, int h_grid,
-                               int w_grid, int force_max_acc) {
+                               int w_grid, int force_max_acc, std::vector<void*>* allocs, cudaStream_t s) {
+  (void)allocs; (void)s;
   const int N = w1.N, K = w1.K;
   int max_acc = tc2_maxb(N);
   if (force_max_acc > 0) max_acc = std::min(max_acc, force_max_acc);
@@ -342,14 +819,150 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
   return tc_make_map(st, &w2->tm_b, w1.w, (uint64_t)K, (uint64_t)N, (uint64_t)w1.n_tiles, (uint32_t)(N / 2));
 }
 
-// One segment's slice of a plan in the form the validator below reads (kernels_loop.cuh builds these views).
-struct Tc2Plan {
+#ifndef DGAN_COST_EPI_KB
+#define DGAN_COST_EPI_KB 24.0
+#endif
+#ifndef DGAN_COST_FIXED_KB
+#define DGAN_COST_FIXED_KB 48.0
+#endif
+
+// Pick (and build on first use) the window tiling for `n_mpairs` row pairs on `n_pairs` CTA pairs: every candidate
+// shape (wh x ww accumulators, strides 1 or 2) is scored by an LPT assignment of its items (window, row pair) to the
+// CTA pairs with cost = operand bytes staged + a per-accumulator epilogue charge + a fixed per-item charge;
+// the smallest makespan wins.  Then each pair's items are concatenated into its step streams, the circular operand
+// ring is simulated to give every step its offset and its dependency distance, and everything is uploaded.
+struct Tc2Plan {               // host result of the planner (what tc2_get_schedule uploads)
+  int shape[4] = {1, 1, 1, 1};   // wh, ww, sy, sx
   int n_slots = 0, n_pairs = 0;
   std::vector<TcItem2> hdrs;
   std::vector<TcRec> stream_p[2], stream_m;
   std::vector<uint32_t> stream_off;
-  std::vector<int> eitems;       // [n_slots][n_pairs] (window << 16 | row pair), -1 = none
+  std::vector<int> eitems;
+  long long n_mma = 0, n_single = 0, n_steps = 0, n_bytes = 0;
 };
+
+static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, int max_acc, int n_mpairs, int n_pairs,
+                    int ring_bytes, Tc2Plan* plan) {
+  const bool merge = (N >= 64) && !(getenv("DGAN_MERGE_N") && atoi(getenv("DGAN_MERGE_N")) == 0);
+  const int max_g = merge ? std::min(4, 256 / N) : 1;
+  // Reusing the weight tiles of the previous step (its ring region then lives one step longer) cuts 5-15 % of the bytes
+  // of the conv kernels but measured 2 % slower end to end (less ring capacity in flight, fewer merged-N MMAs): opt-in.
+  const bool share_prev = getenv("DGAN_SHARE_PREV") && atoi(getenv("DGAN_SHARE_PREV")) != 0;
+  const int max_a = getenv("DGAN_MULTI_A") ? std::max(1, std::min(TC2_MAX_A, atoi(getenv("DGAN_MULTI_A")))) : TC2_MAX_A;
+  // Step size: a step is consumed only once all of it has landed, so big steps cost pipeline depth (4 x 48 KB fit the
+  // ring); measured on C2: 32 KB (= one A tile per step) 5359, 40 KB 5466, 48-56 KB 5660, 64 KB 5553, 96 KB 5385 images/s.
+  int step_max = std::min((ring_bytes / 2) & ~1023, 48 * 1024);
+  if (getenv("DGAN_STEP_MAX_KB")) step_max = std::min((ring_bytes / 2) & ~1023, std::max(32, atoi(getenv("DGAN_STEP_MAX_KB"))) * 1024);
+  // a step that reads the previous step's weight tiles must never wrap onto that step's region: with steps of at
+  // most a third of the ring, the wrapped step ends before its predecessor begins
+  if (share_prev) step_max = std::min(step_max, (ring_bytes / 3) & ~1023);
+  double best_cost = 1e300;
+  int best_shape[4] = {1, 1, 1, 1};
+  std::vector<Tc2HostItem> best_items;
+  std::vector<std::vector<int>> best_lists;
+  std::vector<std::vector<int>> wins;
+  for (int wh = 1; wh <= 2; ++wh)
+    for (int ww = 1; ww <= 8; ++ww)
+      for (int sy = 1; sy <= (wh > 1 ? 2 : 1); ++sy)
+        for (int sx = 1; sx <= (ww > 1 ? 2 : 1); ++sx) {
+          if (wh * ww > max_acc || wh > h_grid || ww > std::max(w_grid, 1)) continue;
+          if ((sy > 1 || sx > 1) && max_a == 1) continue;
+          tc2_enumerate_windows(h_grid, std::max(w_grid, 1), wh, ww, sy, sx, &wins);
+          std::vector<Tc2HostItem> items(wins.size());
+          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(tab, wins[i], N, K, max_g, max_a, step_max, share_prev, &items[i]);
+          std::stable_sort(items.begin(), items.end(), [](const Tc2HostItem& l, const Tc2HostItem& r) { return l.stage_bytes > r.stage_bytes; });
+          std::vector<double> icost(items.size());
+          for (size_t i = 0; i < items.size(); ++i)
+            icost[i] = items[i].stage_bytes + DGAN_COST_EPI_KB * 1024.0 * items[i].hdr.n_acc * std::max(1, N / 64) + DGAN_COST_FIXED_KB * 1024.0;
+          // LPT: items (window, mp) largest-first, each to the currently least-loaded CTA pair
+          const long long total = (long long)items.size() * n_mpairs;
+          std::vector<double> load((size_t)n_pairs, 0.0);
+          std::vector<std::vector<int>> lists((size_t)n_pairs);
+          for (long long idx = 0; idx < total; ++idx) {        // items[] is sorted by cost, mp is the fast index: cost-descending
+            size_t best = 0;
+            for (size_t pr = 1; pr < (size_t)n_pairs; ++pr)
+              if (load[pr] < load[best]) best = pr;
+            load[best] += icost[(size_t)(idx / n_mpairs)];
+            lists[best].push_back((int)idx);
+          }
+          const double makespan = *std::max_element(load.begin(), load.end());
+          if (makespan < best_cost) {
+            best_cost = makespan;
+            best_shape[0] = wh; best_shape[1] = ww; best_shape[2] = sy; best_shape[3] = sx;
+            best_items.swap(items); best_lists.swap(lists);
+          }
+        }
+  plan->shape[0] = best_shape[0]; plan->shape[1] = best_shape[1]; plan->shape[2] = best_shape[2]; plan->shape[3] = best_shape[3];
+  plan->n_pairs = n_pairs;
+  size_t n_slots = 0;
+  for (auto& l : best_lists) n_slots = std::max(n_slots, l.size());
+  plan->n_slots = (int)n_slots;
+  std::vector<int>& eitems = plan->eitems;
+  eitems.assign(n_slots * (size_t)n_pairs, -1);
+  std::vector<uint32_t>& stream_off = plan->stream_off;
+  stream_off.assign((size_t)n_pairs + 1, 0);
+  std::vector<TcRec>* stream_p = plan->stream_p;
+  std::vector<TcRec>& stream_m = plan->stream_m;
+  stream_p[0].clear(); stream_p[1].clear(); stream_m.clear();
+  long long n_mma = 0, n_single = 0, n_steps = 0, n_bytes = 0;
+  for (size_t pr = 0; pr < best_lists.size(); ++pr) {
+    stream_off[pr] = (uint32_t)stream_m.size();
+    // circular operand ring of this CTA pair: sequential allocation, wrap when the step does not fit
+    std::vector<std::pair<int, int>> region;     // [begin, end) in KB of every step of this stream
+    std::vector<char> reads_prev;                // step k reads weight tiles from step k-1's region
+    int cursor = 0;
+    for (size_t k = 0; k < best_lists[pr].size(); ++k) {
+      const int win = best_lists[pr][k] / n_mpairs, mp = best_lists[pr][k] % n_mpairs;
+      if (win > 0x7FFF || mp > 0xFFFF) { set_error("tensor-core schedule limits exceeded"); return DGAN_ERR_UNSUPPORTED; }
+      eitems[k * (size_t)n_pairs + pr] = (win << 16) | mp;
+      const Tc2HostItem& itm = best_items[(size_t)win];
+      for (size_t j = 0; j < itm.steps.size(); ++j) {
+        const Tc2HostStep& hs = itm.steps[j];
+        const int kb = (hs.bytes + 1023) / 1024;
+        if (kb * 1024 > ring_bytes) { set_error("tensor-core step larger than the operand ring"); return DGAN_ERR_UNSUPPORTED; }
+        if (cursor + kb > ring_bytes / 1024) cursor = 0;
+        const int beg = cursor, end = cursor + kb;
+        cursor = end;
+        // The producer may overwrite a region once the last step that reads it is consumed: the step itself, or the
+        // next one when that reads weight tiles out of it.  dep = distance to the latest such step among the
+        // overlapping regions (8 = barrier-slot reuse only).
+        int dep = TC2_NSLOT;
+        const int kidx = (int)region.size();
+        for (int d = 1; d <= TC2_NSLOT && d <= kidx; ++d) {
+          const int c = kidx - d;
+          const auto& rg = region[(size_t)c];
+          if (rg.first < end && beg < rg.second) {
+            const bool next_reads = (c + 1 < kidx) ? reads_prev[(size_t)c + 1] != 0 : hs.uses_prev;   // step c+1 (maybe this one)
+            const int last_reader = c + (next_reads ? 1 : 0);
+            if (last_reader >= kidx) { set_error("operand ring too small for the step schedule"); return DGAN_ERR_UNSUPPORTED; }
+            dep = std::min(dep, kidx - last_reader);
+          }
+        }
+        region.push_back({beg, end});
+        reads_prev.push_back(hs.uses_prev ? 1 : 0);
+        const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
+        TcRec rm{};
+        rm.w[0] = (uint32_t)beg | ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16);
+        for (int o = 0; o < hs.n_ops; ++o) rm.w[2 + o / 2] |= (uint32_t)hs.ops[o] << (16 * (o & 1));
+        stream_m.push_back(rm);
+        for (int r = 0; r < 2; ++r) {
+          TcRec rp{};
+          rp.w[0] = (uint32_t)beg | ((uint32_t)hs.kc << 8) | ((uint32_t)hs.nA << 12) | ((uint32_t)hs.nB << 15) | ((uint32_t)dep << 19);
+          rp.w[1] = (uint32_t)mp;
+          for (int a = 0; a < hs.nA; ++a) rp.w[2 + a / 2] |= (uint32_t)(hs.a_pix[a] & 0xFFFF) << (16 * (a & 1));
+          for (int b = 0; b < hs.nB; ++b) rp.w[4 + b / 4] |= (uint32_t)hs.b_ent[r][b] << (8 * (b & 3));
+          stream_p[r].push_back(rp);
+        }
+        n_mma += hs.n_ops; n_single += hs.n_tile_mmas; n_steps += 1; n_bytes += hs.bytes;
+      }
+    }
+  }
+  stream_off[(size_t)n_pairs] = (uint32_t)stream_m.size();
+  plan->hdrs.resize(best_items.size());
+  for (size_t i = 0; i < best_items.size(); ++i) plan->hdrs[i] = best_items[i].hdr;
+  plan->n_mma = n_mma; plan->n_single = n_single; plan->n_steps = n_steps; plan->n_bytes = n_bytes;
+  return 0;
+}
 
 // Independent validation of a plan against the pair table it was built from (host only; used by
 // dgan_debug_check_plans and the CPU tests).  Re-derives from the uploaded records alone:
@@ -361,8 +974,7 @@ struct Tc2Plan {
 //  * ring safety: when a step's loads may start (step k - dep consumed), no earlier step that can still be read
 //    overlaps its region, regions stay inside the ring, dep <= number of barrier slots;
 //  * every (window, row pair) item is assigned to exactly one CTA pair.
-static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int ring_bytes, const Tc2Plan& pl, std::string* err,
-                          bool check_ring = true) {
+static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int ring_bytes, const Tc2Plan& pl, std::string* err) {
   auto fail = [&](const std::string& m) { *err = m; return DGAN_ERR_INVALID_ARG; };
   const int kch = K / 64, half_b = (N / 2) * 128, acc_stride = tc2_acc_stride(N), max_acc = TC2_BUF_COLS / acc_stride;
   const size_t n_pairs = (size_t)pl.n_pairs;
@@ -375,7 +987,7 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
     for (uint32_t a = 0; a < h.n_acc; ++a)
       if ((size_t)h.q[a] + 1 >= tab.off.size()) return fail("window pixel out of range");
   }
-  struct Step { int beg, end, nB, kc; uint8_t b0[8], b1[8]; };
+  struct Step { int beg, end, nB, kc; bool uses_prev; uint8_t b0[8], b1[8]; };
   for (size_t pr = 0; pr < n_pairs; ++pr) {
     const uint32_t r_beg = pl.stream_off[pr], r_end = pl.stream_off[pr + 1];
     if (r_beg > r_end || r_end > pl.stream_m.size()) return fail("stream_off not monotone");
@@ -385,6 +997,7 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
     uint32_t seen = 0;
     std::vector<std::pair<int, int>> last_kp;                     // per accumulator: last (kc, p)
     std::vector<std::vector<std::pair<int, int>>> contrib;        // per accumulator: (p * 32 + tile, kc)
+    size_t item_first_step = 0;
     for (uint32_t ri = r_beg; ri < r_end; ++ri) {
       const TcRec &m = pl.stream_m[ri], &p0 = pl.stream_p[0][ri], &p1 = pl.stream_p[1][ri];
       const int k = (int)steps.size();
@@ -414,6 +1027,7 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
         seen = 0;
         last_kp.assign(pl.hdrs[win].n_acc, {-1, -1});
         contrib.assign(pl.hdrs[win].n_acc, {});
+        item_first_step = steps.size();
       }
       if (!in_item) return fail("step outside an item");
       if ((int)(p0.w[1] & 0xFFFF) != mp) return fail("row pair of a step differs from its item");
@@ -427,8 +1041,14 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
         if (g > 1 && (acc_stride != N || g * N > 256)) return fail("merged MMA too wide");
         const int p = (int)((p0.w[2 + a_idx / 2] >> (16 * (a_idx & 1))) & 0xFFFF);
         int tiles[4];
-        if (prev) return fail("op refers to a previous step's weight tiles (not supported)");
-        {
+        if (prev) {
+          if (g != 1 || steps.size() == item_first_step) return fail("bad previous-step reference");
+          const Step& ps = steps.back();
+          if (ps.kc != st.kc || slot >= ps.nB) return fail("previous-step reference out of range");
+          if ((ps.b0[slot] & 0x3F) != (ps.b0[slot] & 0x1F) || (ps.b1[slot] & 0x3F) != ((ps.b0[slot] & 0x1F) | 0x20)) return fail("previous-step tile is not in plain layout");
+          tiles[0] = ps.b0[slot] & 0x1F;
+          st.uses_prev = true;
+        } else {
           if (slot + g > nB) return fail("op reads a B slot the step does not stage");
           for (int i = 0; i < g; ++i) {
             const int x0 = 2 * i, x1 = 2 * i + 1;
@@ -449,11 +1069,13 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
         }
         for (int i = 0; i < g; ++i) seen |= 1u << (acc0 + i);
       }
-      // ring safety inside the segment (the cyclic check over a CTA pair's whole stream is loop_check_plan's)
-      for (int c = k - 1; check_ring && c >= 0 && c >= k - 4 * TC2_NSLOT; --c) {
+      // ring safety
+      if (st.uses_prev && !steps.empty() && steps.back().beg < st.end && st.beg < steps.back().end) return fail("step overlaps the region it reads");
+      for (int c = k - 1; c >= 0 && c >= k - 4 * TC2_NSLOT; --c) {
         const Step& o = steps[(size_t)c];
         if (!(o.beg < st.end && st.beg < o.end)) continue;
-        if (c > k - dep) return fail("ring hazard: a region may be overwritten while it can still be read");
+        const int last_reader = c + ((c + 1 < k) ? (steps[(size_t)c + 1].uses_prev ? 1 : 0) : (st.uses_prev ? 1 : 0));
+        if (last_reader > k - dep) return fail("ring hazard: a region may be overwritten while it can still be read");
       }
       steps.push_back(st);
       if (flags & 2u) {
@@ -474,6 +1096,113 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
   }
   for (int v : assigned)
     if (v != 1) return fail("an item is not assigned to any CTA pair");
+  return 0;
+}
+
+// Pick (and build on first use) the schedule of one layer-direction for `n_mpairs` row pairs and upload it.
+static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int n_pairs, int ring_bytes,
+                            std::vector<void*>* allocs, cudaStream_t s, const Tc2Schedule** out) {
+  (void)st;
+  for (auto& kv : w2.by_mpairs)
+    if (kv.first == n_mpairs) { *out = &kv.second; return 0; }
+  Tc2Plan plan;
+  int rc;
+  if ((rc = tc2_plan(w1.N, w1.K, w2.tab, w2.h_grid, w2.w_grid, w2.max_acc, n_mpairs, n_pairs, ring_bytes, &plan))) return rc;
+  Tc2Schedule sc;
+  sc.wh = plan.shape[0]; sc.ww = plan.shape[1]; sc.sy = plan.shape[2]; sc.sx = plan.shape[3];
+  sc.n_windows = (int)plan.hdrs.size(); sc.n_pairs = n_pairs; sc.n_slots = plan.n_slots;
+  if ((rc = tc_upload(allocs, plan.hdrs.data(), plan.hdrs.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
+  for (int r = 0; r < 2; ++r)
+    if ((rc = tc_upload(allocs, plan.stream_p[r].data(), plan.stream_p[r].size() * sizeof(TcRec), (void**)&sc.stream_p[r], s))) return rc;
+  if ((rc = tc_upload(allocs, plan.stream_m.data(), plan.stream_m.size() * sizeof(TcRec), (void**)&sc.stream_m, s))) return rc;
+  if ((rc = tc_upload(allocs, plan.stream_off.data(), plan.stream_off.size() * sizeof(uint32_t), (void**)&sc.stream_off, s))) return rc;
+  if ((rc = tc_upload(allocs, plan.eitems.data(), plan.eitems.size() * sizeof(int), (void**)&sc.eitems, s))) return rc;
+  w2.by_mpairs.push_back({n_mpairs, sc});
+  *out = &w2.by_mpairs.back().second;
+  if (getenv("DGAN_TC_VERBOSE"))
+    fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d stride %dx%d, %d windows, %lld steps, %.1f MB staged/CTA-set, "
+                    "%lld tile-MMAs in %lld merged\n", w1.N, w1.K, w2.h_grid, w2.w_grid, n_mpairs, sc.wh, sc.ww, sc.sy, sc.sx, sc.n_windows, plan.n_steps,
+            2.0 * plan.n_bytes / 1e6, plan.n_single, plan.n_mma);
+  return 0;
+}
+
+template <int NT, int EP, typename TOUT>
+static cudaError_t tc2_optin() {
+  return cudaFuncSetAttribute(tc_bsgemm2_kernel<NT, EP, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES);
+}
+
+static int tc2_optin_all() {
+#define TC2_OPTIN(NT, EP, T) DGAN_CUDA_CHECK((tc2_optin<NT, EP, T>()))
+  TC2_OPTIN(64, EPI_BIAS_RELU, __half); TC2_OPTIN(128, EPI_BIAS_RELU, __half); TC2_OPTIN(256, EPI_BIAS_RELU, __half);
+  TC2_OPTIN(64, EPI_BIAS, __half); TC2_OPTIN(128, EPI_BIAS, __half); TC2_OPTIN(256, EPI_BIAS, __half);
+  TC2_OPTIN(64, EPI_MASK, __half); TC2_OPTIN(128, EPI_MASK, __half); TC2_OPTIN(256, EPI_MASK, __half);
+  TC2_OPTIN(64, EPI_NONE, __half); TC2_OPTIN(128, EPI_NONE, __half); TC2_OPTIN(256, EPI_NONE, __half);
+  TC2_OPTIN(64, EPI_NONE, float); TC2_OPTIN(128, EPI_NONE, float); TC2_OPTIN(256, EPI_NONE, float);
+  TC2_OPTIN(64, EPI_MOMENTUM, float); TC2_OPTIN(128, EPI_MOMENTUM, float); TC2_OPTIN(256, EPI_MOMENTUM, float);
+  TC2_OPTIN(16, EPI_FINAL_SIGMOID1, __half); TC2_OPTIN(48, EPI_FINAL_TANH3, __half);
+#undef TC2_OPTIN
+  return 0;
+}
+
+template <typename TOUT>
+static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const TcWeights2& w2m, const __half* in,
+                           TOUT* out, int n_pad, int epi, const float* bias, const __half* mask_src, float out_scale,
+                           cudaStream_t s, const TcFinalArgs* final_args = nullptr, const CUtensorMap* pre_a = nullptr,
+                           const CUtensorMap* pre_out = nullptr) {
+  TcFinalArgs fa{};
+  if (final_args) fa = *final_args;
+  fa.dbg = nullptr;
+  fa.dbg_flags = st.dbg_flags;
+  if (st.dbg != nullptr && st.dbg_launch < st.dbg_max_launches) fa.dbg = st.dbg + (size_t)(st.dbg_launch++) * 160 * 16;
+  CUtensorMap tm_a;
+  int rc;
+  if (pre_a != nullptr) tm_a = *pre_a;          // encoded once per workspace by the caller
+  else if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
+  CUtensorMap tm_out = tm_a;                     // placeholder when unused
+  if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT))) {
+    if (pre_out != nullptr) tm_out = *pre_out;
+    else if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
+  }
+  if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
+  if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT)) && out_scale != 1.f) { set_error("fp16 tile epilogue has no output scale"); return DGAN_ERR_UNSUPPORTED; }
+  const int n_mpairs = n_pad / (2 * kRowTile);
+  const Tc2Schedule* schp = nullptr;
+  const int pairs_avail = st.max_pairs > 0 ? std::min(st.max_pairs, st.num_sms / 2) : st.num_sms / 2;
+  const int ring_bytes = tc2_ring_bytes(w.N, epi, (int)sizeof(TOUT));
+  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, pairs_avail, ring_bytes, st.allocs, s, &schp))) return rc;
+  const Tc2Schedule& w2s = *schp;
+  const int total = w2s.n_windows * n_mpairs;
+  const int grid = 2 * w2s.n_pairs;       // pairs without work find -1 in slot 0 and fall through
+  (void)total;
+  cudaError_t le = cudaSuccess;
+#define TC2_GO(NT, EP)                                                                                                 \
+  le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+#define TC2_GO_H(NT, EP)                                                                                               \
+  le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
+                  mask_src, out_scale, fa)
+#define TC2_BY_N(EP)                    \
+  do {                                  \
+    if (w.N == 64) TC2_GO(64, EP);      \
+    else if (w.N == 128) TC2_GO(128, EP); \
+    else TC2_GO(256, EP);               \
+  } while (0)
+  if (sizeof(TOUT) == 4 && epi == EPI_MOMENTUM) { TC2_BY_N(EPI_MOMENTUM); }
+  else if (sizeof(TOUT) == 4) { TC2_BY_N(EPI_NONE); }
+  else if (epi == EPI_FINAL_SIGMOID1) { TC2_GO_H(16, EPI_FINAL_SIGMOID1); }
+  else if (epi == EPI_FINAL_TANH3) { TC2_GO_H(48, EPI_FINAL_TANH3); }
+  else if (epi == EPI_BIAS_RELU) { TC2_BY_N(EPI_BIAS_RELU); }
+  else if (epi == EPI_BIAS) { TC2_BY_N(EPI_BIAS); }
+  else if (epi == EPI_MASK) { TC2_BY_N(EPI_MASK); }
+  else { TC2_BY_N(EPI_NONE); }
+#undef TC2_BY_N
+#undef TC2_GO
+#undef TC2_GO_H
+  (*launches)++;
+  cudaError_t e = (le != cudaSuccess) ? le : cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("tc_bsgemm2 launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
   return 0;
 }
 

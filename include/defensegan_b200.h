@@ -119,29 +119,19 @@ int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, con
                    float* y_dev, float* loss_dev, float* grad_dev, void* workspace,
                    size_t workspace_bytes, void* stream);
 
-/* Kernel launches enqueued by the most recent dgan_reconstruct / dgan_forward on this handle.  With DGAN_PREC_FP16 the
- * whole L-step loop is ONE persistent kernel, so a projection is 4 launches (z0 initialiser, loop, per-row loss, arg-min
- * select) whatever rec_iters is. */
+/* Kernel launches enqueued by the most recent dgan_reconstruct on this handle. */
 int64_t dgan_last_launch_count(dgan_handle h);
-
-/* Diagnostic (synchronises with the device): status word of the most recent fp16 loop-kernel launch.  *status_out == 0
- * after a healthy call; non-zero means one of the kernel's inter-CTA dependency waits timed out (the kernel then runs to
- * completion instead of hanging, but that call's results are invalid) - dgan_last_error() says so. */
-int dgan_last_status(dgan_handle h, int* status_out);
 
 /* Algorithmic multiply-accumulates of one generator forward per latent row (exact in-bounds
  * taps); backward-to-z has the same count. */
 int64_t dgan_macs_per_row(dgan_handle h);
 
-/* Device timing for roofline reports (no reference counterpart); never enable it in a timed throughput pass.
- * While enabled (level != 0) every kernel launch of the production path is bracketed by CUDA events on the launching
- * stream.  For DGAN_PREC_FP16 that is the single loop kernel (kind "projection_loop ..."); in addition the kernel records,
- * per L-step, row-pair group and segment (layer-direction), the %globaltimer span from the first item's start to the
- * last item's end over all CTA pairs - reported under the segment kinds (spans of neighbouring segments overlap).
- * dgan_profile_read synchronises on the recorded events and returns, per kind, the summed milliseconds, the launch (or
- * span) count and the algorithmic FLOPs of one launch / span (2 x exact in-bounds MACs x latent rows; for the loop kernel
- * x its 2 rec_iters - 1 generator passes). */
-int dgan_profile_enable(dgan_handle h, int level);
+/* Per-kernel device timing for roofline reports (no reference counterpart).  While enabled every
+ * kernel launch of dgan_reconstruct is bracketed by CUDA events on the launching stream; never
+ * enable it in a timed throughput pass.  dgan_profile_read synchronises on the recorded events
+ * and returns, per kernel kind (layer x direction), the summed milliseconds, the launch count and
+ * the algorithmic FLOPs of one launch (2 x exact in-bounds MACs x latent rows of the last call). */
+int dgan_profile_enable(dgan_handle h, int enable);
 int dgan_profile_num_kinds(dgan_handle h);
 const char* dgan_profile_kind_name(dgan_handle h, int kind);
 int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* launches_out,
