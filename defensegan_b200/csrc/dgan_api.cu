@@ -1052,6 +1052,7 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
   const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
   dirs.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2});
   dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, celeba ? EPI_NONE : EPI_MASK, 2});
+  std::string summary; long long ta = 0, tb = 0;
   for (const Dir& dr : dirs) {
     if (dr.N != 16 && dr.N != 48 && dr.N != 64 && dr.N != 128 && dr.N != 256) { set_error(dr.name + ": unsupported N"); return DGAN_ERR_UNSUPPORTED; }
     int max_acc = tc2_maxb(dr.N);
@@ -1083,7 +1084,14 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
     }
     std::string err;
     if ((rc = tc2_check_plan(dr.N, dr.K, dr.tab, n_mpairs, ring, plan, &err))) { set_error(dr.name + ": " + err); return rc; }
+    {
+      long long a = 0, b = 0;
+      for (const TcRec& r : plan.stream_p[0]) { a += (long long)((r.w[0] >> 12) & 7) * TC_A_BYTES; b += (long long)((r.w[0] >> 15) & 0xF) * (dr.N / 2) * 128; }
+      summary += dr.name + ": A " + std::to_string(2 * a / 1000000) + " MB, B " + std::to_string(2 * b / 1000000) + " MB, items " + std::to_string(plan.hdrs.size() * (size_t)n_mpairs) + "; ";
+      ta += 2 * a; tb += 2 * b;
+    }
   }
+  set_error(summary + "total A " + std::to_string(ta / 1000000) + " MB, B " + std::to_string(tb / 1000000) + " MB");
   return 0;
 }
 
