@@ -109,7 +109,6 @@ struct GemmLayer {
   // fp16 K-major tiles for the tensor-core path (kernels_tc.cuh): [tile][N rows][K cols]
   TcWeights tc_f, tc_b;
   TcWeights2 tc2_f, tc2_b;
-  TcWeights2 tc2_b_fused;          // Linear only: un-split dz with the momentum update in the epilogue
 };
 
 struct FinalLayer {
@@ -138,12 +137,6 @@ struct dgan_ctx {
   TcWeights2 tc2_fin_f, tc2_fin_b;
   // optional per-launch CUDA-event timing (dgan_profile_*): serialises nothing by itself but
   // adds two event records per launch, so it is never enabled in a timed benchmark pass
-  // the images of a call are split into `n_chains` independent dependency chains on separate streams so that
-  // one chain's kernel tails / launch gaps are filled by the other's CTAs
-  int n_chains = 1;
-  std::vector<cudaStream_t> chain_streams;
-  std::vector<cudaEvent_t> chain_events;
-  cudaEvent_t fork_event = nullptr;
   bool profile = false;
   int n_rows_cur = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -359,13 +352,13 @@ static int launch_final_bwd(dgan_ctx* c, const Workspace& w, const TOUT* mask_sr
 }
 
 static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
-                      int epi, const float* bias, const __half* mask_src, cudaStream_t s,
+                      int epi, const float* bias, cudaStream_t s,
                       unsigned long long* mb_out = nullptr, const unsigned long long* mb_in = nullptr,
                       const CUtensorMap* pre_a = nullptr, const CUtensorMap* pre_out = nullptr);
 
 // Encode the TMA descriptors of all launch sites for this workspace (once per call instead of per launch).
 static int build_maps(dgan_ctx* c, Workspace& w) {
-  if (c->desc.precision != DGAN_PREC_FP16 || c->tc.mode != 2) return 0;
+  if (c->desc.precision != DGAN_PREC_FP16) return 0;
   const int nl = (int)c->layers.size();
   w.map_in.assign((size_t)2 * nl + 2, CUtensorMap{});
   w.map_out.assign((size_t)2 * nl + 2, CUtensorMap{});
@@ -399,7 +392,7 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     for (int l = 0; l < nl; ++l) {
       const GemmLayer& L = c->layers[l];
       ProfScope ps(c, 2 * l, s);
-      if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, nullptr, s,
+      if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, s,
                            (L.relu && want_grad) ? w.maskbits[l] : nullptr, nullptr,
                            w.have_maps ? &w.map_in[2 * l] : nullptr, w.have_maps ? &w.map_out[2 * l] : nullptr)))
         return rc;
@@ -409,11 +402,9 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     TcFinalArgs fa{};
     fa.x = x; fa.y = w.y; fa.loss_part = w.loss_part; fa.R = R; fa.B = B; fa.n_rows = w.n_rows;
     fa.nbx = c->tc_fin.nbx; fa.w_out = c->tc_fin.w_out; fa.gscale = c->tc.grad_scale; fa.write_y = want_y ? 1 : 0;
-    if (c->tc.mode == 2)
-      return tc2_launch_impl<__half>(c->tc, &c->launches, c->tc_fin.f, c->tc2_fin_f, in, w.dblk, w.n_pad,
-                                     c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, c->fin.bias, nullptr, 1.f, s, &fa,
-                                     w.have_maps ? &w.map_in[2 * nl] : nullptr, nullptr);
-    return tc_launch_final_fwd(c->tc, &c->launches, c->tc_fin, in, w.dblk, w.n_pad, c->fin.bias, fa, s);
+    return tc2_launch_impl<__half>(c->tc, &c->launches, c->tc_fin.f, c->tc2_fin_f, in, w.dblk, w.n_pad,
+                                   c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, c->fin.bias, s, &fa,
+                                   w.have_maps ? &w.map_in[2 * nl] : nullptr, nullptr);
   }
   const float* in = w.z;
   for (int l = 0; l < nl; ++l) {
@@ -449,7 +440,7 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
 }
 
 // ---- backward-to-z: w.g = J^T dpre (unscaled by 2/HWC; fp16 path additionally x gscale) -----
-struct MomentumArgs { bool fused = false, tail = false; float lr = 0.f, mu = 0.f; };
+struct MomentumArgs { bool tail = false; float lr = 0.f, mu = 0.f; };   // tail: update z in the Linear backward's tail
 
 static float grad_multiplier(const dgan_ctx* c);
 
@@ -461,7 +452,7 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
     {
       ProfScope ps(c, 2 * nl + 1, s);
       if ((rc = tcx_launch(c, c->tc_fin.b, c->tc2_fin_b, w.dblk, w.dact_h[nl - 1], w.n_pad, last.relu ? EPI_MASK : EPI_NONE,
-                           nullptr, last.relu ? w.act_h[nl - 1] : nullptr, s, nullptr, last.relu ? w.maskbits[nl - 1] : nullptr,
+                           nullptr, s, nullptr, last.relu ? w.maskbits[nl - 1] : nullptr,
                            w.have_maps ? &w.map_in[2 * nl + 1] : nullptr, w.have_maps ? &w.map_out[2 * nl + 1] : nullptr)))
         return rc;
     }
@@ -470,28 +461,19 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
       const bool mask = c->layers[l - 1].relu;
       ProfScope ps(c, 2 * l + 1, s);
       if ((rc = tcx_launch(c, L.tc_b, L.tc2_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad, mask ? EPI_MASK : EPI_NONE, nullptr,
-                           mask ? w.act_h[l - 1] : nullptr, s, nullptr, mask ? w.maskbits[l - 1] : nullptr,
+                           s, nullptr, mask ? w.maskbits[l - 1] : nullptr,
                            w.have_maps ? &w.map_in[2 * l + 1] : nullptr, w.have_maps ? &w.map_out[2 * l + 1] : nullptr)))
         return rc;
     }
     const GemmLayer& L0 = c->layers[0];
     ProfScope ps(c, 1, s);
-    if (c->tc.mode == 2 && mom.fused) {
-      TcFinalArgs fa{};
+    TcFinalArgs fa{};
+    if (mom.tail) {      // the CTA that completes a row tile's partial sums applies the momentum update
       fa.mz = w.z; fa.mv = w.v; fa.mz_h = w.z_h; fa.m_gmul = grad_multiplier(c); fa.m_lr = mom.lr; fa.m_mu = mom.mu;
-      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b_fused, w.dact_h[0], w.g, w.n_pad, EPI_MOMENTUM, nullptr,
-                                    nullptr, 1.f, s, &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
+      fa.m_counter = w.mom_counter; fa.m_nparts = w.n_g_parts; fa.m_count = (size_t)w.n_pad * c->desc.latent_dim;
     }
-    if (c->tc.mode == 2) {
-      TcFinalArgs fa{};
-      if (mom.tail && w.n_g_parts == TC_LINEAR_SPLIT) {      // the CTA that completes a row tile's partial sums applies the momentum update
-        fa.mz = w.z; fa.mv = w.v; fa.mz_h = w.z_h; fa.m_gmul = grad_multiplier(c); fa.m_lr = mom.lr; fa.m_mu = mom.mu;
-        fa.m_counter = w.mom_counter; fa.m_nparts = w.n_g_parts; fa.m_count = (size_t)w.n_pad * c->desc.latent_dim;
-      }
-      return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, nullptr, 1.f, s,
-                                    &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
-    }
-    return tc_launch_f32out(c->tc, &c->launches, L0.tc_b, w.dact_h[0], w.g, w.n_pad, s);
+    return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, s,
+                                  &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
   }
   // d(act) -> d(pre) through ReLU + batch-statistics BN of layer l (in place in w.dact[l])
   auto bn_backward = [&](int l) -> int {
@@ -561,16 +543,13 @@ static int check_ws(const dgan_ctx* c, int n_rows, void* ws, size_t ws_bytes, Wo
   return 0;
 }
 
-// tensor-core launch, dispatching on the kernel generation
+// one hidden layer-direction on the tensor cores
 static int tcx_launch(dgan_ctx* c, const TcWeights& w1, const TcWeights2& w2, const __half* in, __half* out, int n_pad,
-                      int epi, const float* bias, const __half* mask_src, cudaStream_t s, unsigned long long* mb_out,
+                      int epi, const float* bias, cudaStream_t s, unsigned long long* mb_out,
                       const unsigned long long* mb_in, const CUtensorMap* pre_a, const CUtensorMap* pre_out) {
-  if (c->tc.mode == 2) {
-    TcFinalArgs fa{};
-    fa.mb_out = mb_out; fa.mb_in = mb_in;
-    return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, mask_src, 1.f, s, &fa, pre_a, pre_out);
-  }
-  return tc_launch(c->tc, &c->launches, w1, in, out, n_pad, epi, bias, mask_src, 1.f, s);
+  TcFinalArgs fa{};
+  fa.mb_out = mb_out; fa.mb_in = mb_in;
+  return tc2_launch_impl<__half>(c->tc, &c->launches, w1, w2, in, out, n_pad, epi, bias, s, &fa, pre_a, pre_out);
 }
 
 // element counts of the weight tensors in creation order (include/defensegan_b200.h, dgan_num_weights)
@@ -729,17 +708,8 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
     if ((rc = tc_build_final(c->tc, &c->tc_fin, c->fin.w, c->fin.h_in, c->fin.w_in, c->fin.C_in, c->fin.C_out,
                              c->fin.act, &c->allocs, s)))
       return fail(rc);
-    const char* mode_env = getenv("DGAN_TC_MODE");
-    c->tc.mode = (mode_env && mode_env[0] == '1') ? 1 : 2;
-    if (getenv("DGAN_TC_DBGFLAGS")) c->tc.dbg_flags = atoi(getenv("DGAN_TC_DBGFLAGS"));
-    if (getenv("DGAN_MAX_PAIRS")) c->tc.max_pairs = atoi(getenv("DGAN_MAX_PAIRS"));
-    if (getenv("DGAN_TC_DEBUG")) {   // developer aid: per-CTA role timing of the first launches (tools/tc_timing.py)
-      c->tc.dbg_max_launches = 64;
-      if ((rc = dev_alloc(c, (void**)&c->tc.dbg, (size_t)64 * 160 * 16 * sizeof(unsigned long long)))) return fail(rc);
-      DGAN_CUDA_CHECK(cudaMemsetAsync(c->tc.dbg, 0, (size_t)64 * 160 * 16 * sizeof(unsigned long long), s));
-    }
     c->tc.allocs = &c->allocs;
-    if (c->tc.mode == 2) {
+    {
       if ((rc = tc2_optin_all())) return fail(rc);
       for (size_t l = 0; l < c->layers.size(); ++l) {
         GemmLayer& L = c->layers[l];
@@ -747,7 +717,6 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
         if (l == 0) {
           const PairTable split = linear_split_pairs(L.P_out);
           if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, split, 1, TC_LINEAR_SPLIT, 1, &c->allocs, s))) return fail(rc);
-          if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b_fused, L.bwd_host, 1, 1, 1, &c->allocs, s))) return fail(rc);
         } else if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, L.bwd_host, L.h_in, L.w_in, 0, &c->allocs, s))) {
           return fail(rc);
         }
@@ -756,20 +725,6 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
       if ((rc = tc2_build_direction(c->tc, c->tc_fin.f, &c->tc2_fin_f, ft, c->fin.h_in / 2, c->fin.w_in / 2, 0, &c->allocs, s))) return fail(rc);
       if ((rc = tc2_build_direction(c->tc, c->tc_fin.b, &c->tc2_fin_b, bt, c->fin.h_in, c->fin.w_in, 0, &c->allocs, s))) return fail(rc);
     }
-  }
-  {
-    const char* ch_env = getenv("DGAN_CHAINS");
-    // measured (tools/enqueue_time.py, bench): 2 chains alternate kernels instead of overlapping them (each persistent
-    // kernel takes all 74 CTA pairs) - no gain, so the default stays 1; DGAN_CHAINS=k keeps the experiment available
-    c->n_chains = ch_env ? std::max(1, std::min(8, atoi(ch_env))) : 1;
-    if (d->use_bn) c->n_chains = 1;      // batch statistics couple all rows of a call
-    for (int k = 1; k < c->n_chains; ++k) {
-      cudaStream_t st; cudaEvent_t ev;
-      DGAN_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-      DGAN_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      c->chain_streams.push_back(st); c->chain_events.push_back(ev);
-    }
-    DGAN_CUDA_CHECK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
   }
   {
     static const char* lname_m[] = {"Linear", "Generator.2", "Generator.3"};
@@ -824,31 +779,14 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
 int dgan_destroy(dgan_handle h) {
   if (h == nullptr) return DGAN_OK;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-  for (cudaStream_t st : h->chain_streams) cudaStreamDestroy(st);
-  for (cudaEvent_t ev : h->chain_events) cudaEventDestroy(ev);
-  if (h->fork_event) cudaEventDestroy(h->fork_event);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return DGAN_OK;
 }
 
-// images [lo, hi) of chain k when `batch` images are split into n balanced contiguous chains
-static inline void chain_bounds(int batch, int n, int k, int* lo, int* hi) {
-  const int base = batch / n, extra = batch % n;
-  *lo = k * base + std::min(k, extra);
-  *hi = *lo + base + (k < extra ? 1 : 0);
-}
-
 size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
   if (h == nullptr || batch <= 0 || rec_rr <= 0) return 0;
-  const int n = std::min(h->n_chains, batch);
-  size_t total = 0;
-  for (int k = 0; k < n; ++k) {
-    int lo, hi;
-    chain_bounds(batch, n, k, &lo, &hi);
-    total += carve(h, (hi - lo) * rec_rr, nullptr).bytes;
-  }
-  return std::max(total, carve(h, batch * rec_rr, nullptr).bytes);   // dgan_forward / dgan_loss_grad use one chain
+  return carve(h, batch * rec_rr, nullptr).bytes;
 }
 
 int64_t dgan_last_launch_count(dgan_handle h) { return h ? h->last_launches : 0; }
@@ -913,77 +851,44 @@ int dgan_reconstruct(dgan_handle h, const dgan_rec_params* prm, const float* x_d
     set_error("workspace too small: need " + std::to_string(dgan_workspace_bytes(h, batch, rec_rr)) + " bytes, got " + std::to_string(ws_bytes));
     return DGAN_ERR_WORKSPACE;
   }
-  cudaStream_t s0 = (cudaStream_t)stream;
-  const int n_chains = h->profile ? 1 : std::min(h->n_chains, batch);   // per-kernel timing wants one chain
+  cudaStream_t s = (cudaStream_t)stream;
   const int latent = h->desc.latent_dim;
-  struct Chain { Workspace w; cudaStream_t s; int lo, hi; };
-  std::vector<Chain> chains((size_t)n_chains);
-  size_t off = 0;
-  for (int k = 0; k < n_chains; ++k) {
-    Chain& ch = chains[(size_t)k];
-    chain_bounds(batch, n_chains, k, &ch.lo, &ch.hi);
-    ch.w = carve(h, (ch.hi - ch.lo) * rec_rr, (char*)ws + off);
-    off += ch.w.bytes;
-    int mrc;
-    if ((mrc = build_maps(h, ch.w))) return mrc;
-    ch.s = (k == 0) ? s0 : h->chain_streams[(size_t)k - 1];
-  }
+  Workspace w = carve(h, batch * rec_rr, ws);
   int rc;
+  if ((rc = build_maps(h, w))) return rc;
   const int64_t launches0 = h->launches;
   h->n_rows_cur = batch * rec_rr;
-  if (n_chains > 1) {
-    DGAN_CUDA_CHECK(cudaEventRecord(h->fork_event, s0));
-    for (int k = 1; k < n_chains; ++k) DGAN_CUDA_CHECK(cudaStreamWaitEvent(chains[(size_t)k].s, h->fork_event, 0));
-  }
-  for (Chain& ch : chains) {
-    const size_t row_off = (size_t)ch.lo * rec_rr;
-    if ((rc = run_init_z(h, ch.w, z0_dev ? z0_dev + row_off * latent : nullptr, seed, ch.s, (size_t)prm->z_row_offset + row_off))) return rc;
-  }
+  if ((rc = run_init_z(h, w, z0_dev, seed, s, (size_t)prm->z_row_offset))) return rc;
   const int decay_iter = (int)std::ceil(rec_iters * 0.8);
+  // fp16: the momentum update (tf.train.MomentumOptimizer, models/gan.py:389-391) runs in the tail of the split-K Linear
+  // backward - the CTA that completes a 128-row tile's partial sums applies it - so an L-step is 8 launches; bit-identical
+  // to the separate kernel the fp32 path uses (same arithmetic, parts summed in the same order)
+  const bool tail = h->desc.precision == DGAN_PREC_FP16;
   for (int t = 0; t < rec_iters; ++t) {
     const bool last = (t == rec_iters - 1);
     float lr = rec_lr;
     if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
-    // fused Linear-backward + momentum epilogue exists (EPI_MOMENTUM) but measured slower than split-K + momentum_kernel
-    const bool fused = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 && getenv("DGAN_FUSED_MOMENTUM") != nullptr;
-    // DGAN_MOMENTUM_TAIL=1: momentum in the tail of the split-K Linear backward (the CTA completing a row tile's partial
-    // sums applies the update; no separate kernel).  Bit-identical, but measured no faster (Linear bwd 16.7 -> 27.0 us vs
-    // 16.7 + 9.5 us for the momentum kernel: 5631 vs 5616 images/s), so the separate kernel stays the default.
-    const bool tail = h->desc.precision == DGAN_PREC_FP16 && h->tc.mode == 2 &&
-                      getenv("DGAN_MOMENTUM_TAIL") && atoi(getenv("DGAN_MOMENTUM_TAIL")) != 0;
-    for (Chain& ch : chains) {
-      const Workspace& w = ch.w;
-      cudaStream_t s = ch.s;
-      const float* x = x_dev + (size_t)ch.lo * h->hwc;
-      // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
-      // the L-th update is never observed, so its backward pass is not run.
-      if ((rc = run_forward(h, w, x, rec_rr, ch.hi - ch.lo, !last, s, /*want_y=*/last))) return rc;
-      if (last) continue;
-      MomentumArgs mom;
-      mom.fused = fused; mom.lr = lr; mom.mu = momentum;
-      mom.tail = !fused && tail;
-      if ((rc = run_backward(h, w, s, mom))) return rc;
-      if (!fused && !mom.tail) {
-        const size_t zcount = (size_t)w.n_pad * latent;
-        ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
-        DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
-                                   (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
-        DGAN_LAUNCH_CHECK(h);
-      }
+    // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
+    // the L-th update is never observed, so its backward pass is not run.
+    if ((rc = run_forward(h, w, x_dev, rec_rr, batch, !last, s, /*want_y=*/last))) return rc;
+    if (last) continue;
+    MomentumArgs mom;
+    mom.lr = lr; mom.mu = momentum; mom.tail = tail;
+    if ((rc = run_backward(h, w, s, mom))) return rc;
+    if (!tail) {
+      const size_t zcount = (size_t)w.n_pad * latent;
+      ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
+      DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
+                                 (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
+      DGAN_LAUNCH_CHECK(h);
     }
   }
-  for (Chain& ch : chains) {
-    const Workspace& w = ch.w;
-    const int nb = ch.hi - ch.lo, n_rows = nb * rec_rr;
-    loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, ch.s>>>(w.loss_part, w.n_loss_parts, w.loss_stride_n, w.loss_stride_b, 1.0f / (float)h->hwc, n_rows, w.loss);
+  {
+    const int n_rows = batch * rec_rr;
+    loss_finish_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(w.loss_part, w.n_loss_parts, w.loss_stride_n, w.loss_stride_b, 1.0f / (float)h->hwc, n_rows, w.loss);
     DGAN_LAUNCH_CHECK(h);
-    select_kernel<<<nb, 256, 0, ch.s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev + (size_t)ch.lo * h->hwc,
-                                         loss_dev ? loss_dev + ch.lo : nullptr, idx_dev ? idx_dev + ch.lo : nullptr);
+    select_kernel<<<batch, 256, 0, s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev, loss_dev, idx_dev);
     DGAN_LAUNCH_CHECK(h);
-  }
-  for (int k = 1; k < n_chains; ++k) {
-    DGAN_CUDA_CHECK(cudaEventRecord(h->chain_events[(size_t)k - 1], chains[(size_t)k].s));
-    DGAN_CUDA_CHECK(cudaStreamWaitEvent(s0, h->chain_events[(size_t)k - 1], 0));
   }
   h->last_launches = h->launches - launches0;
   return DGAN_OK;
@@ -1052,7 +957,6 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
   const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
   dirs.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2});
   dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, celeba ? EPI_NONE : EPI_MASK, 2});
-  std::string summary; long long ta = 0, tb = 0;
   for (const Dir& dr : dirs) {
     if (dr.N != 16 && dr.N != 48 && dr.N != 64 && dr.N != 128 && dr.N != 256) { set_error(dr.name + ": unsupported N"); return DGAN_ERR_UNSUPPORTED; }
     int max_acc = tc2_maxb(dr.N);
@@ -1084,23 +988,8 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
     }
     std::string err;
     if ((rc = tc2_check_plan(dr.N, dr.K, dr.tab, n_mpairs, ring, plan, &err))) { set_error(dr.name + ": " + err); return rc; }
-    {
-      long long a = 0, b = 0;
-      for (const TcRec& r : plan.stream_p[0]) { a += (long long)((r.w[0] >> 12) & 7) * TC_A_BYTES; b += (long long)((r.w[0] >> 15) & 0xF) * (dr.N / 2) * 128; }
-      summary += dr.name + ": A " + std::to_string(2 * a / 1000000) + " MB, B " + std::to_string(2 * b / 1000000) + " MB, items " + std::to_string(plan.hdrs.size() * (size_t)n_mpairs) + "; ";
-      ta += 2 * a; tb += 2 * b;
-    }
   }
-  set_error(summary + "total A " + std::to_string(ta / 1000000) + " MB, B " + std::to_string(tb / 1000000) + " MB");
   return 0;
-}
-
-int dgan_debug_tc_timing(dgan_handle h, unsigned long long* out, int max_launches) {
-  if (h == nullptr || out == nullptr || h->tc.dbg == nullptr) return 0;
-  const int n = std::min(max_launches, h->tc.dbg_launch);
-  cudaDeviceSynchronize();
-  cudaMemcpy(out, h->tc.dbg, (size_t)n * 160 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  return n;
 }
 
 }  // extern "C"

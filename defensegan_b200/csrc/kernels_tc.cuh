@@ -1,20 +1,14 @@
-// Tensor-core path (DGAN_PREC_FP16): the pixel-graph GEMM of kernels_simt.cuh on tcgen05.
+// Tensor-core path (DGAN_PREC_FP16): shared pieces of the pixel-graph GEMM on tcgen05.
 //
 //   out[q][n][:] = epi( sum_{(p,t) in pairs(q)} in[p][n][:] x W_t )        fp16 operands, fp32 accumulate
 //
-// One CTA = one 128-row tile of latent rows (MMA M = 128) x one *window* of output pixels whose
-// fp32 accumulators live side by side in TMEM (n_acc x N columns <= 256, so two CTAs share an
-// SM and one CTA's epilogue overlaps the other's MMAs).  The conv geometry is data, not code:
-// the host turns each layer's pair table into per-window *step* lists; a step = one input-pixel
-// activation tile A (128 rows x 64 channels, TMA -> 128B-swizzled smem) plus the <=4 weight tiles
-// B_t (N x 64) of the taps that connect that input pixel to the window, and issues
-// n_b x 4 tcgen05.mma (K = 16 each).  Only in-bounds taps are listed, so exactly the
+// Activations are pixel-major [P][N rows][C] fp16, so one input pixel x 128 latent rows x 64 channels is a dense
+// 16 KB box = one TMA box = one 128B-swizzled K-major UMMA operand; weights are stored per tap as [N][K] fp16
+// tiles.  The conv geometry is data, not code: only in-bounds (input pixel, tap) pairs are listed, so exactly the
 // algorithmic MACs are issued - no zero-insertion, no padding rows, no im2col buffer.
-//
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
-// elected lane), warps 2-5 = epilogue (tcgen05.ld -> bias/ReLU/mask -> fp16 -> global).
-// smem full/empty mbarrier ring between producer and MMA warp; tcgen05.commit releases stages
-// and signals the epilogue; acc_empty hands TMEM back to the MMA warp.
+// This header holds the PTX wrappers, the UMMA descriptors, the epilogue arithmetic (bias / ReLU / mask / last layer +
+// sigmoid|tanh + MSE + dL/dpre) and the weight re-layout; the CTA-pair kernel that uses them and its
+// host-side planning are in kernels_tc2.cuh.
 #pragma once
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
 
@@ -22,45 +16,21 @@
 
 namespace dgan {
 
-constexpr int TC_STAGES = 2;
-constexpr int TC_A_BYTES = 128 * 128;        // 128 rows x 64 fp16
-constexpr int TC_STAGE_BYTES = 48 * 1024;    // A + up to 32 KB of weight tiles
-constexpr int TC_MAXB = 4;
-constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = 128 * 128;        // one activation tile: 128 rows x 64 fp16
 constexpr int TC_LINEAR_SPLIT = 4;           // partial sums of the Linear backward (dz)
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-
-struct __align__(16) TcStep {
-  uint32_t w0;     // in pixel p [0,16) | k-chunk [16,24) | n_b [24,32)
-  uint32_t w1;     // bit b: B tile b is the first MMA into its accumulator (overwrite instead of accumulate)
-  uint32_t tb[2];  // byte b: weight tile id (5 bits) | accumulator index (3 bits) << 5
-};
-struct __align__(16) TcItem {
-  uint16_t q[8];   // output pixel of accumulator a
-  uint32_t n_acc, step_beg, n_steps, pad;
-};
 
 // One direction (forward or backward) of one layer on the tensor-core path.
 struct TcWeights {
   __half* w = nullptr;          // [tiles][N][K] fp16, K contiguous
-  CUtensorMap tm_b;             // 3-D map over w, box {64, N, 1}, SWIZZLE_128B
-  TcItem* items = nullptr;
-  TcStep* steps = nullptr;
-  int n_windows = 0, n_steps_total = 0;
   int N = 0, K = 0, P_in = 0, P_out = 0, n_tiles = 0;
   int bias_pstride = 0;
 };
 
 struct TcState {
-  int mode = 2;                 // 1 = one CTA per MMA (kernels_tc.cuh), 2 = CTA pairs (kernels_tc2.cuh)
   float grad_scale = 64.f;      // fp16 gradient scaling (undone in the z update)
   void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
-  unsigned long long* dbg = nullptr;   // DGAN_TC_DEBUG=1: [launch][cta][16] role-timing counters
-  int dbg_launch = 0, dbg_max_launches = 0, dbg_flags = 0;
   std::vector<void*>* allocs = nullptr;   // the handle's allocation list (lazily built schedules are freed with it)
   int num_sms = 148;
-  int max_pairs = 0;            // cap on CTA pairs per launch (0 = all SMs); used with multi-chain execution
 };
 
 struct TcLayerSpec {
@@ -172,7 +142,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // the block's pre-activations), so that the output non-linearity, the squared error, its
 // derivative and the per-row loss partial are all lane-local in the epilogue
 // (models/dataset_models.py:68-69,161-163; models/gan.py:411-414).
-enum TcEpilogue : int { EPI_FINAL_SIGMOID1 = 8, EPI_FINAL_TANH3 = 9, EPI_MOMENTUM = 10 };
+enum TcEpilogue : int { EPI_FINAL_SIGMOID1 = 8, EPI_FINAL_TANH3 = 9 };
 
 struct TcFinalArgs {
   const float* x;        // [B][H*W*C] target images (NULL: forward only)
@@ -187,22 +157,20 @@ struct TcFinalArgs {
   // (tf.nn.relu's gradient passes where the forward output was > 0).
   unsigned long long* mb_out;
   const unsigned long long* mb_in;
-  // EPI_MOMENTUM (Linear backward fused with tf.train.MomentumOptimizer, models/gan.py:389-391):
+  // split-K Linear backward with the momentum update (tf.train.MomentumOptimizer, models/gan.py:389-391) in its tail:
+  // the CTA whose partial sums complete a 128-row tile (ticket from m_counter[tile]) applies
+  // v <- mu v + gmul * sum(parts), z <- z - lr v for that tile
   float* mz; float* mv; __half* mz_h;   // z, velocity [n_pad][latent] fp32, fp16 copy of z
-  float m_gmul, m_lr, m_mu;             // g = gmul * acc;  v <- mu v + g;  z <- z - lr v
-  // split-K Linear backward with the momentum update in its tail: the CTA whose partial sums complete a 128-row tile
-  // (ticket from m_counter[tile]) applies v <- mu v + gmul * sum(parts), z <- z - lr v for that tile (mz/mv/mz_h above)
+  float m_gmul, m_lr, m_mu;
   unsigned* m_counter;   // [n_pad / 128] arrival tickets, self-resetting; NULL = plain partial sums
   int m_nparts;          // partial sums per row tile
   size_t m_count;        // elements per partial-sum array (n_pad * latent)
-  unsigned long long* dbg;  // optional per-CTA role timing (16 counters per CTA), NULL in production
-  int dbg_flags;            // timing experiments only: 1 = skip epilogue stores, 2 = skip mask loads, 4 = skip bias
 };
 
 // Target pixels (4x4 block of image n / R) of one row: loaded one accumulator ahead of their use.
 template <int C_OUT>
 __device__ __forceinline__ void tc_final_targets(float4 (&xq)[4 * C_OUT], const TcFinalArgs& fa, int blk, int n) {
-  if (fa.x == nullptr || (fa.dbg_flags & 32)) return;   // flag 32: timing experiment without the target loads
+  if (fa.x == nullptr) return;
   const int by = blk / fa.nbx, bx = blk % fa.nbx;
   const int hwc = fa.w_out * fa.w_out * C_OUT;
   const int img = min(n / fa.R, fa.B - 1);
@@ -263,7 +231,7 @@ __device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalA
 #pragma unroll
     for (int e2 = 0; e2 < 2 * C_OUT; ++e2) packed[li * 2 * C_OUT + e2] = pack_half2(dv[2 * e2], dv[2 * e2 + 1]);
   }
-  if (fa.x != nullptr && !((fa.dbg_flags & 1) && lsum != 12345.678f)) {   // flag 1: timing experiment without the stores
+  if (fa.x != nullptr) {
     uint4* dp = reinterpret_cast<uint4*>(dblk + ((size_t)blk * n_pad + n) * 64);
 #pragma unroll
     for (int j4 = 0; j4 < NV / 8; ++j4)   // the K-padding columns [NV, 64) stay zero (cleared once per call)
@@ -272,45 +240,14 @@ __device__ __forceinline__ void tc_final_epilogue(uint32_t taddr, const TcFinalA
   }
 }
 
-// dz chunk (32 latent dims of one row, in registers) -> momentum update of z and v in place
-__device__ __forceinline__ void tc_momentum_chunk(const uint32_t (&r)[32], int c0, size_t n, int latent, const TcFinalArgs& fa) {
-  float4* __restrict__ vp = reinterpret_cast<float4*>(fa.mv + n * latent + c0);
-  float4* __restrict__ zp = reinterpret_cast<float4*>(fa.mz + n * latent + c0);
-  uint2* __restrict__ hp = reinterpret_cast<uint2*>(fa.mz_h + n * latent + c0);
-  float4 vv[8], zz[8];
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) { vv[j4] = vp[j4]; zz[j4] = zp[j4]; }   // all loads in flight before any store
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    float4 v = vv[j4], z = zz[j4];
-    v.x = fmaf(fa.m_mu, v.x, fa.m_gmul * __uint_as_float(r[j4 * 4 + 0]));
-    v.y = fmaf(fa.m_mu, v.y, fa.m_gmul * __uint_as_float(r[j4 * 4 + 1]));
-    v.z = fmaf(fa.m_mu, v.z, fa.m_gmul * __uint_as_float(r[j4 * 4 + 2]));
-    v.w = fmaf(fa.m_mu, v.w, fa.m_gmul * __uint_as_float(r[j4 * 4 + 3]));
-    z.x -= fa.m_lr * v.x; z.y -= fa.m_lr * v.y; z.z -= fa.m_lr * v.z; z.w -= fa.m_lr * v.w;
-    vp[j4] = v; zp[j4] = z;
-    hp[j4] = make_uint2(pack_half2(z.x, z.y), pack_half2(z.z, z.w));
-  }
-}
-
 // One 32-column chunk of an accumulator (already in registers) -> epilogue -> out[q][n][c0..c0+32)
-// ReLU-mask words (32 fp16 = 4 x uint4) of one chunk: loaded one unit ahead of their use
-template <int N_TILE>
-__device__ __forceinline__ void tc_load_mask(uint4 (&mv)[4], const __half* __restrict__ mask_src, int q, int c0, size_t n,
-                                             int n_pad) {
-  const uint4* mp = reinterpret_cast<const uint4*>(mask_src + ((size_t)q * n_pad + n) * N_TILE + c0);
-#pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) mv[j4] = __ldg(mp + j4);
-}
-
 template <int N_TILE, int EPI, typename TOUT>
-__device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], const uint4 (&mv)[4], int q, int c0, size_t n,
-                                               int n_pad, TOUT* __restrict__ out, const float* __restrict__ bias,
-                                               int bias_pstride, float out_scale, int dbg_flags = 0) {
+__device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], int q, int c0, size_t n, int n_pad,
+                                               TOUT* __restrict__ out, const float* __restrict__ bias, int bias_pstride) {
   const size_t orow = ((size_t)q * n_pad + n) * N_TILE;
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
     const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + c0);
 #pragma unroll
@@ -323,19 +260,6 @@ __device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], const ui
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
   }
-  if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const uint32_t mw[4] = {mv[j4].x, mv[j4].y, mv[j4].z, mv[j4].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
-        if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
-        if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
-      }
-    }
-  }
-  if ((dbg_flags & 1) && v[0] != 12345.678f) return;   // timing experiment: no stores
   if (sizeof(TOUT) == 2) {
     uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
 #pragma unroll
@@ -346,218 +270,6 @@ __device__ __forceinline__ void tc_store_chunk(const uint32_t (&r)[32], const ui
     float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-  }
-}
-
-// One accumulator (128 lanes x N_TILE fp32 columns at `taddr`) -> bias/ReLU | ReLU-mask | none ->
-// fp16 (or fp32) row of out[q][n][0..N_TILE).  Each thread owns one latent row (TMEM lane).
-template <int N_TILE, int EPI, typename TOUT>
-__device__ __forceinline__ void tc_generic_epilogue(uint32_t taddr, int q, size_t n, int n_pad, TOUT* __restrict__ out,
-                                                    const float* __restrict__ bias, int bias_pstride,
-                                                    const __half* __restrict__ mask_src, float out_scale) {
-  const size_t orow = ((size_t)q * n_pad + n) * N_TILE;
-#pragma unroll 1
-  for (int c0 = 0; c0 + 32 <= N_TILE; c0 += 32) {
-    uint32_t r[32];
-    ptx::tmem_ld32(taddr + (uint32_t)c0, r);
-    ptx::tmem_ld_wait();
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
-    if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
-      const float* bp = bias + (size_t)q * bias_pstride + c0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] += __ldg(bp + j);
-        if (EPI == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
-      }
-    }
-    if (EPI == EPI_MASK) {   // ReLU gradient: pass where the forward activation was > 0
-      const uint4* mp = reinterpret_cast<const uint4*>(mask_src + orow + c0);
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const uint4 mv = __ldg(mp + j4);
-        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __half2 h = *reinterpret_cast<const __half2*>(&mw[e]);
-          if (!(__low2float(h) > 0.f)) v[j4 * 8 + e * 2] = 0.f;
-          if (!(__high2float(h) > 0.f)) v[j4 * 8 + e * 2 + 1] = 0.f;
-        }
-      }
-    }
-    if (sizeof(TOUT) == 2) {
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + orow + c0);
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4)
-        op[j4] = make_uint4(pack_half2(v[j4 * 8 + 0], v[j4 * 8 + 1]), pack_half2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
-                            pack_half2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_half2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
-    } else {
-      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow + c0);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// the kernel
-// ------------------------------------------------------------------------------------------
-template <int N_TILE, int EPI, typename TOUT>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-tc_bsgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const TcItem* __restrict__ items, const TcStep* __restrict__ steps, int n_windows, int n_mtiles,
-                 TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
-                 const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
-  constexpr int B_BYTES = N_TILE * 128;
-  constexpr int ACC_STRIDE = N_TILE < 64 ? 64 : N_TILE;   // TMEM columns between accumulators
-  static_assert(TC_A_BYTES + TC_MAXB * 64 * 128 <= TC_STAGE_BYTES, "stage too small");
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
-  // barriers: full[s] @ +8s, empty[s] @ +32+8s, acc_full @ +64, acc_empty @ +72, tmem ptr @ +80
-  const uint32_t bar_full = bar_base, bar_empty = bar_base + 32, bar_acc_full = bar_base + 64, bar_acc_empty = bar_base + 72;
-  const uint32_t tmem_slot = bar_base + 80;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_items = n_windows * n_mtiles;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_a);
-    ptx::prefetch_tmap(&tm_b);
-    for (int s = 0; s < TC_STAGES; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_empty + 8 * s, 1);
-    }
-    ptx::mbar_init(bar_acc_full, 1);
-    ptx::mbar_init(bar_acc_empty, 128);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, TC_TMEM_COLS);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    uint32_t it = 0;
-    for (int item_idx = blockIdx.x; item_idx < total_items; item_idx += gridDim.x) {
-      const int win = item_idx / n_mtiles, m = item_idx % n_mtiles;
-      const TcItem* ip = items + win;
-      const uint32_t step_beg = ip->step_beg, n_steps = ip->n_steps;
-      for (uint32_t s0 = 0; s0 < n_steps; s0 += 32) {
-        uint4 mine = make_uint4(0, 0, 0, 0);
-        if (s0 + lane < n_steps) mine = *reinterpret_cast<const uint4*>(steps + step_beg + s0 + lane);
-        const uint32_t cnt = min(32u, n_steps - s0);
-        for (uint32_t i = 0; i < cnt; ++i) {
-          const uint32_t w0 = __shfl_sync(0xffffffffu, mine.x, i);
-          const uint32_t tb0 = __shfl_sync(0xffffffffu, mine.z, i);
-          if (lane == 0) {
-            const uint32_t stage = it % TC_STAGES, phase = (it / TC_STAGES) & 1;
-            const int p = w0 & 0xFFFF, kc = (w0 >> 16) & 0xFF, nb = (w0 >> 24) & 0xFF;
-            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            const uint32_t full = bar_full + 8 * stage;
-            ptx::mbar_expect_tx(full, TC_A_BYTES + nb * B_BYTES);
-            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-            ptx::tma_load_3d(sa, &tm_a, full, kc * 64, m * kRowTile, p);
-            for (int b = 0; b < nb; ++b) {
-              const int tile = (tb0 >> (8 * b)) & 0x1F;
-              ptx::tma_load_3d(sa + TC_A_BYTES + b * B_BYTES, &tm_b, full, kc * 64, 0, tile);
-            }
-          }
-          ++it;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_f16(128, N_TILE);
-    uint32_t it = 0, item_count = 0;
-    for (int item_idx = blockIdx.x; item_idx < total_items; item_idx += gridDim.x, ++item_count) {
-      const int win = item_idx / n_mtiles;
-      const TcItem* ip = items + win;
-      const uint32_t step_beg = ip->step_beg, n_steps = ip->n_steps;
-      if (lane == 0) {
-        ptx::mbar_wait(bar_acc_empty, (item_count & 1) ^ 1);   // epilogue has drained the accumulators
-        ptx::tc_fence_after();
-      }
-      __syncwarp();
-      for (uint32_t s0 = 0; s0 < n_steps; s0 += 32) {
-        uint4 mine = make_uint4(0, 0, 0, 0);
-        if (s0 + lane < n_steps) mine = *reinterpret_cast<const uint4*>(steps + step_beg + s0 + lane);
-        const uint32_t cnt = min(32u, n_steps - s0);
-        for (uint32_t i = 0; i < cnt; ++i) {
-          const uint32_t w0 = __shfl_sync(0xffffffffu, mine.x, i);
-          const uint32_t w1 = __shfl_sync(0xffffffffu, mine.y, i);
-          const uint32_t tb0 = __shfl_sync(0xffffffffu, mine.z, i);
-          if (lane == 0) {
-            const uint32_t stage = it % TC_STAGES, phase = (it / TC_STAGES) & 1;
-            const int nb = (w0 >> 24) & 0xFF;
-            ptx::mbar_wait(bar_full + 8 * stage, phase);
-            ptx::tc_fence_after();
-            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-            const uint64_t a_desc = make_smem_desc_sw128(sa);
-            for (int b = 0; b < nb; ++b) {
-              const int acc = (tb0 >> (8 * b + 5)) & 0x7;
-              const uint32_t first = (w1 >> b) & 1u;
-              const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES + b * B_BYTES);
-              const uint32_t d = tmem_base + acc * ACC_STRIDE;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 64-wide swizzle atom: +32 bytes each
-                ptx::umma_f16(d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (k > 0 || !first) ? 1u : 0u);
-            }
-            ptx::umma_commit(bar_empty + 8 * stage);            // frees the smem stage when the MMAs retire
-          }
-          ++it;
-        }
-      }
-      if (lane == 0) ptx::umma_commit(bar_acc_full);            // accumulators complete -> epilogue
-      __syncwarp();
-    }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int lq = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = lq * 32 + lane;
-    uint32_t item_count = 0;
-    for (int item_idx = blockIdx.x; item_idx < total_items; item_idx += gridDim.x, ++item_count) {
-      const int win = item_idx / n_mtiles, m = item_idx % n_mtiles;
-      const TcItem* ip = items + win;
-      const int n_acc = (int)ip->n_acc;
-      ptx::mbar_wait(bar_acc_full, item_count & 1);
-      ptx::tc_fence_after();
-      if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
-        for (int a = 0; a < n_acc; ++a) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * ACC_STRIDE);
-          if (EPI == EPI_FINAL_SIGMOID1) {
-            float4 xq[4];
-            tc_final_targets<1>(xq, fa, ip->q[a], m * kRowTile + row);
-            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out), xq);
-          } else {
-            float4 xq[12];
-            tc_final_targets<3>(xq, fa, ip->q[a], m * kRowTile + row);
-            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], m * kRowTile + row, n_pad, reinterpret_cast<__half*>(out), xq);
-          }
-        }
-      } else {
-        for (int a = 0; a < n_acc; ++a)
-          tc_generic_epilogue<N_TILE, EPI, TOUT>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * ACC_STRIDE), ip->q[a],
-                                                 (size_t)m * kRowTile + row, n_pad, out, bias, bias_pstride, mask_src, out_scale);
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(bar_acc_empty);
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -604,66 +316,6 @@ static int tc_make_map(const TcState& st, CUtensorMap* map, const void* base, ui
   return 0;
 }
 
-// Turn a pair table into windows (items) + steps.  `w_grid`/`h_grid`: the output pixels form an
-// h_grid x w_grid raster (1 x P for the Linear directions); windows are 2x2 (4 accumulators),
-// 1x2 (2) or single pixels depending on how many N-wide accumulators fit in 256 TMEM columns.
-static void tc_build_schedule(const PairTable& tab, int h_grid, int w_grid, int N, int K, std::vector<TcItem>* items,
-                              std::vector<TcStep>* steps, int force_max_acc = 0) {
-  int max_acc = std::max(1, std::min(4, TC_TMEM_COLS / std::max(N, 64)));
-  if (force_max_acc > 0) max_acc = std::min(max_acc, force_max_acc);
-  const int wh = (max_acc >= 4) ? 2 : 1, ww = (max_acc >= 2) ? 2 : 1;
-  const int kch = K / 64;
-  for (int y0 = 0; y0 < h_grid; y0 += wh)
-    for (int x0 = 0; x0 < w_grid; x0 += ww) {
-      TcItem item{};
-      std::vector<int> qs;
-      for (int dy = 0; dy < wh && y0 + dy < h_grid; ++dy)
-        for (int dx = 0; dx < ww && x0 + dx < w_grid; ++dx) qs.push_back((y0 + dy) * w_grid + x0 + dx);
-      item.n_acc = (uint32_t)qs.size();
-      for (size_t a = 0; a < qs.size(); ++a) item.q[a] = (uint16_t)qs[a];
-      item.step_beg = (uint32_t)steps->size();
-      // group the window's (p, tile, acc) contributions by input pixel
-      std::vector<std::pair<int, std::vector<std::pair<int, int>>>> by_p;
-      for (size_t a = 0; a < qs.size(); ++a)
-        for (int e = tab.off[qs[a]]; e < tab.off[qs[a] + 1]; ++e) {
-          const int p = tab.pairs[e].x, t = tab.pairs[e].y;
-          size_t g = 0;
-          for (; g < by_p.size(); ++g)
-            if (by_p[g].first == p) break;
-          if (g == by_p.size()) by_p.push_back({p, {}});
-          by_p[g].second.push_back({t, (int)a});
-        }
-      std::sort(by_p.begin(), by_p.end(), [](const auto& l, const auto& r) { return l.first < r.first; });
-      uint32_t seen = 0;
-      for (auto& g : by_p)
-        for (size_t b0 = 0; b0 < g.second.size(); b0 += TC_MAXB) {
-          const size_t nb = std::min((size_t)TC_MAXB, g.second.size() - b0);
-          // the weight tiles of a step must fit the stage: nb * N * 128 B <= 32 KB
-          const size_t fit = std::max<size_t>(1, (TC_STAGE_BYTES - TC_A_BYTES) / ((size_t)N * 128));
-          for (size_t b1 = 0; b1 < nb; b1 += fit) {
-            const size_t nbb = std::min(fit, nb - b1);
-            for (int kc = 0; kc < kch; ++kc) {
-              TcStep s{};
-              s.w0 = (uint32_t)g.first | ((uint32_t)kc << 16) | ((uint32_t)nbb << 24);
-              uint32_t firsts = 0;
-              for (size_t b = 0; b < nbb; ++b) {
-                const auto& ta = g.second[b0 + b1 + b];
-                reinterpret_cast<uint8_t*>(s.tb)[b] = (uint8_t)((ta.first & 0x1F) | (ta.second << 5));
-                if (!(seen & (1u << ta.second))) firsts |= 1u << b;
-              }
-              // an accumulator is overwritten only by its very first MMA: k-chunk 0 of the first
-              // step that touches it (`seen` is updated after the k-chunk loop)
-              s.w1 = (kc == 0) ? firsts : 0;
-              steps->push_back(s);
-            }
-            for (size_t b = 0; b < nbb; ++b) seen |= 1u << g.second[b0 + b1 + b].second;
-          }
-        }
-      item.n_steps = (uint32_t)steps->size() - item.step_beg;
-      items->push_back(item);
-    }
-}
-
 static int tc_upload(std::vector<void*>* allocs, const void* host, size_t bytes, void** dev, cudaStream_t s) {
   DGAN_CUDA_CHECK(cudaMalloc(dev, bytes));
   allocs->push_back(*dev);
@@ -673,24 +325,13 @@ static int tc_upload(std::vector<void*>* allocs, const void* host, size_t bytes,
   return 0;
 }
 
-static int tc_build_direction(TcState& st, TcWeights* w, const PairTable& tab, int h_grid, int w_grid, int N, int K,
-                              int n_tiles, int P_in, int P_out, std::vector<void*>* allocs, cudaStream_t s,
-                              int force_max_acc) {
+static int tc_set_direction(TcWeights* w, int N, int K, int n_tiles, int P_in, int P_out) {
   if (N != 16 && N != 48 && N != 64 && N != 128 && N != 256) { set_error("tensor-core path needs 64/128/256 output channels per pixel"); return DGAN_ERR_UNSUPPORTED; }
   if (K % 64 != 0) { set_error("tensor-core path needs input channels in multiples of 64"); return DGAN_ERR_UNSUPPORTED; }
   if (n_tiles > 32 || P_in > 65535 || P_out > 65535) { set_error("tensor-core schedule limits exceeded"); return DGAN_ERR_UNSUPPORTED; }
   w->N = N; w->K = K; w->P_in = P_in; w->P_out = P_out; w->n_tiles = n_tiles;
-  std::vector<TcItem> items;
-  std::vector<TcStep> steps;
-  tc_build_schedule(tab, h_grid, w_grid, N, K, &items, &steps, force_max_acc);
-  w->n_windows = (int)items.size();
-  w->n_steps_total = (int)steps.size();
-  int rc;
-  if ((rc = tc_upload(allocs, items.data(), items.size() * sizeof(TcItem), (void**)&w->items, s))) return rc;
-  if ((rc = tc_upload(allocs, steps.data(), steps.size() * sizeof(TcStep), (void**)&w->steps, s))) return rc;
-  return tc_make_map(st, &w->tm_b, w->w, (uint64_t)K, (uint64_t)N, (uint64_t)n_tiles, (uint32_t)N);
+  return 0;
 }
-
 
 // ---- the generator's last layer as block GEMMs ---------------------------------------------
 // Image pixels are grouped into 4x4 blocks; block (by,bx) receives from the 4x4 input pixels
@@ -776,10 +417,6 @@ struct TcFinal {
   int n_blocks = 0, nbx = 0, w_out = 0, C_out = 0, act = 0;
 };
 
-static int tc_build_direction(TcState& st, TcWeights* w, const PairTable& tab, int h_grid, int w_grid, int N, int K,
-                              int n_tiles, int P_in, int P_out, std::vector<void*>* allocs, cudaStream_t s,
-                              int force_max_acc = 0);
-
 static int tc_build_final(TcState& st, TcFinal* tf, const float* F, int h_in, int w_in, int C_in, int C_out, int act,
                           std::vector<void*>* allocs, cudaStream_t s) {
   if (C_in != 64) { set_error("tensor-core final layer needs net_dim == 64"); return DGAN_ERR_UNSUPPORTED; }
@@ -791,9 +428,9 @@ static int tc_build_final(TcState& st, TcFinal* tf, const float* F, int h_in, in
   tc_final_tiles_kernel<<<16, 256, 0, s>>>(F, C_out, C_in, tf->f.w, tf->b.w);
   DGAN_CUDA_CHECK(cudaGetLastError());
   int rc;
-  const PairTable ft = final_block_fwd_pairs(h_in, w_in), bt = final_block_bwd_pairs(h_in, w_in);
-  if ((rc = tc_build_direction(st, &tf->f, ft, h_in / 2, w_in / 2, nrow, C_in, 16, h_in * w_in, tf->n_blocks, allocs, s))) return rc;
-  if ((rc = tc_build_direction(st, &tf->b, bt, h_in, w_in, C_in, 64, 16, tf->n_blocks, h_in * w_in, allocs, s))) return rc;
+  (void)st;
+  if ((rc = tc_set_direction(&tf->f, nrow, C_in, 16, h_in * w_in, tf->n_blocks))) return rc;
+  if ((rc = tc_set_direction(&tf->b, C_in, 64, 16, tf->n_blocks, h_in * w_in))) return rc;
   return 0;
 }
 
@@ -827,88 +464,13 @@ static int tc_build(TcState& st, std::vector<TcLayerSpec>& specs, int latent, st
     DGAN_CUDA_CHECK(cudaGetLastError());
     sp.out_f->w = wf; sp.out_b->w = wb;
     sp.out_f->bias_pstride = sp.bias_pstride;
-    // forward: outputs on the h_used x w_used raster; N = C_out, K = C_in
-    if ((rc = tc_build_direction(st, sp.out_f, *sp.fwd, sp.h_used, sp.w_used, sp.C_out, sp.C_in, n_tiles, sp.P_in,
-                                 sp.P_out, allocs, s)))
-      return rc;
-    // backward: outputs on the h_in x w_in raster; N = C_in, K = C_out
-    if (linear) {
-      // dz = sum over the 16 pixels: split the sum into TC_LINEAR_SPLIT partial outputs (more CTAs;
-      // the z update adds the partials in a fixed order)
-      const PairTable split = linear_split_pairs(sp.P_out);
-      if ((rc = tc_build_direction(st, sp.out_b, split, 1, TC_LINEAR_SPLIT, sp.C_in, sp.C_out, n_tiles, sp.P_out,
-                                   TC_LINEAR_SPLIT, allocs, s, /*force_max_acc=*/1)))
-        return rc;
-    } else if ((rc = tc_build_direction(st, sp.out_b, *sp.bwd, sp.h_in, sp.w_in, sp.C_in, sp.C_out, n_tiles, sp.P_out,
-                                        sp.P_in, allocs, s)))
-      return rc;
+    // forward: N = C_out, K = C_in;  backward: N = C_in, K = C_out (the Linear's dz is summed over its 16 pixels as
+    // TC_LINEAR_SPLIT partial outputs: more items, and the z update adds the partials in a fixed order)
+    if ((rc = tc_set_direction(sp.out_f, sp.C_out, sp.C_in, n_tiles, sp.P_in, sp.P_out))) return rc;
+    if ((rc = tc_set_direction(sp.out_b, sp.C_in, sp.C_out, n_tiles, sp.P_out, linear ? TC_LINEAR_SPLIT : sp.P_in))) return rc;
   }
-#define TC_OPTIN(NT, EP, T) \
-  DGAN_CUDA_CHECK(cudaFuncSetAttribute(tc_bsgemm_kernel<NT, EP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))
-  TC_OPTIN(64, EPI_BIAS_RELU, __half); TC_OPTIN(128, EPI_BIAS_RELU, __half); TC_OPTIN(256, EPI_BIAS_RELU, __half);
-  TC_OPTIN(64, EPI_BIAS, __half); TC_OPTIN(128, EPI_BIAS, __half); TC_OPTIN(256, EPI_BIAS, __half);
-  TC_OPTIN(64, EPI_MASK, __half); TC_OPTIN(128, EPI_MASK, __half); TC_OPTIN(256, EPI_MASK, __half);
-  TC_OPTIN(64, EPI_NONE, __half); TC_OPTIN(128, EPI_NONE, __half); TC_OPTIN(256, EPI_NONE, __half);
-  TC_OPTIN(64, EPI_NONE, float); TC_OPTIN(128, EPI_NONE, float); TC_OPTIN(256, EPI_NONE, float);
-  TC_OPTIN(16, EPI_FINAL_SIGMOID1, __half); TC_OPTIN(48, EPI_FINAL_TANH3, __half);
-#undef TC_OPTIN
+  (void)latent;
   return 0;
-}
-
-template <typename TOUT>
-static int tc_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const __half* in, TOUT* out, int n_pad,
-                          int epi, const float* bias, const __half* mask_src, float out_scale, cudaStream_t s,
-                          const TcFinalArgs* final_args = nullptr) {
-  TcFinalArgs fa{};
-  if (final_args) fa = *final_args;
-  CUtensorMap tm_a;
-  int rc;
-  if ((rc = tc_make_map(st, &tm_a, in, (uint64_t)w.K, (uint64_t)n_pad, (uint64_t)w.P_in, 128))) return rc;
-  const int n_mtiles = n_pad / kRowTile;
-  const int total = w.n_windows * n_mtiles;
-  const int grid = std::min(total, 2 * st.num_sms);
-#define TC_GO(NT, EP)                                                                                              \
-  tc_bsgemm_kernel<NT, EP, TOUT><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_a, w.tm_b, w.items, w.steps, w.n_windows, \
-                                                                         n_mtiles, out, n_pad, bias, w.bias_pstride, \
-                                                                         mask_src, out_scale, fa)
-#define TC_GO_FINAL(NT, EP)                                                                                             \
-  tc_bsgemm_kernel<NT, EP, __half><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_a, w.tm_b, w.items, w.steps, w.n_windows, \
-                                                                           n_mtiles, reinterpret_cast<__half*>(out),  \
-                                                                           n_pad, bias, 0, mask_src, out_scale, fa)
-#define TC_BY_N(EP)                                         \
-  do {                                                      \
-    if (w.N == 64) TC_GO(64, EP);                           \
-    else if (w.N == 128) TC_GO(128, EP);                    \
-    else TC_GO(256, EP);                                    \
-  } while (0)
-  if (sizeof(TOUT) == 4) { TC_BY_N(EPI_NONE); }
-  else if (epi == EPI_FINAL_SIGMOID1) { if (sizeof(TOUT) == 2) TC_GO_FINAL(16, EPI_FINAL_SIGMOID1); }
-  else if (epi == EPI_FINAL_TANH3) { if (sizeof(TOUT) == 2) TC_GO_FINAL(48, EPI_FINAL_TANH3); }
-  else if (epi == EPI_BIAS_RELU) { TC_BY_N(EPI_BIAS_RELU); }
-  else if (epi == EPI_BIAS) { TC_BY_N(EPI_BIAS); }
-  else if (epi == EPI_MASK) { TC_BY_N(EPI_MASK); }
-  else { TC_BY_N(EPI_NONE); }
-#undef TC_BY_N
-#undef TC_GO
-#undef TC_GO_FINAL
-  (*launches)++;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error(std::string("tc_bsgemm launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
-  return 0;
-}
-
-static int tc_launch(TcState& st, int64_t* launches, const TcWeights& w, const __half* in, __half* out, int n_pad, int epi,
-                     const float* bias, const __half* mask_src, float out_scale, cudaStream_t s) {
-  return tc_launch_impl<__half>(st, launches, w, in, out, n_pad, epi, bias, mask_src, out_scale, s);
-}
-static int tc_launch_final_fwd(TcState& st, int64_t* launches, const TcFinal& tf, const __half* in, __half* dblk, int n_pad,
-                               const float* bias, const TcFinalArgs& fa, cudaStream_t s) {
-  return tc_launch_impl<__half>(st, launches, tf.f, in, dblk, n_pad, tf.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3,
-                                bias, nullptr, 1.f, s, &fa);
-}
-static int tc_launch_f32out(TcState& st, int64_t* launches, const TcWeights& w, const __half* in, float* out, int n_pad,
-                            cudaStream_t s) {
-  return tc_launch_impl<float>(st, launches, w, in, out, n_pad, EPI_NONE, nullptr, nullptr, 1.f, s);
 }
 
 }  // namespace dgan

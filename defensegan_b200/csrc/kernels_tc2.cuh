@@ -58,7 +58,6 @@ __host__ __device__ constexpr bool tc2_tma_epilogue(int n_tile, int epi, int out
 // MMA record:
 //   w[0]: ring offset / 1 KB [0,8) | A tiles [8,11) | ops [11,16) | flags [16,18): 1 = first step of an item, 2 = last
 //   w[2..7]: 12 x u16 per MMA: A tile [0,2) | first B slot [2,5) | slots - 1 [5,7) | accumulator [7,10) | first MMA into it [10,11)
-//            | B slot is in the PREVIOUS step's region [11,12) (a weight tile shared by consecutive steps is staged once)
 struct __align__(16) TcRec { uint32_t w[8]; };
 constexpr int TC2_MAX_A = 4, TC2_MAX_BSLOTS = 8, TC2_MAX_OPS = 12, TC2_NSLOT = 8;
 // Merged-N groups: when one input pixel feeds g accumulators that sit side by side in TMEM (acc, acc+1, ...) through
@@ -69,17 +68,10 @@ constexpr int TC2_MAX_A = 4, TC2_MAX_BSLOTS = 8, TC2_MAX_OPS = 12, TC2_NSLOT = 8
 constexpr int TC2_REC_BATCH = 16;
 constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // producer + MMA warp rings
 
-// Output staging tiles per CTA: one per epilogue half, or two per half (the next tile is written while the TMA
-// store of the previous one still reads shared memory) for the kernels whose epilogue is the critical path:
-// Linear forward (N = 256: 4 tiles per item, 2-3 items per CTA pair) and the last layer's backward.
-#ifndef DGAN_EPI_DB
-#define DGAN_EPI_DB 0
-#endif
+// Output staging tiles per CTA: one per epilogue half (two per half - the next tile written while the store of the
+// previous one still reads shared memory - was measured in round 1: no gain).
 __host__ __device__ constexpr int tc2_epi_tiles(int n_tile, int epi, int out_bytes) {
-  if (!tc2_tma_epilogue(n_tile, epi, out_bytes)) return 0;
-  if (DGAN_EPI_DB == 2) return 4;
-  if (DGAN_EPI_DB == 1 && ((n_tile == 256 && epi == EPI_BIAS_RELU) || (n_tile == 64 && epi == EPI_MASK))) return 4;
-  return 2;
+  return tc2_tma_epilogue(n_tile, epi, out_bytes) ? 2 : 0;
 }
 __host__ __device__ constexpr int tc2_ring_bytes(int n_tile, int epi, int out_bytes) {
   const int epi_b = tc2_epi_tiles(n_tile, epi, out_bytes) * TC2_TILE_BYTES;
@@ -93,7 +85,7 @@ struct Tc2Cfg {
   static constexpr int ACC_STRIDE = tc2_acc_stride(N_TILE);
   static constexpr int MAXB = TC2_BUF_COLS / ACC_STRIDE;                  // = accumulators per window (8 / 4 / 2 / 1)
   static constexpr bool TMA_EPI = tc2_tma_epilogue(N_TILE, EPI, OUT_BYTES);
-  static constexpr int EPI_TILES = tc2_epi_tiles(N_TILE, EPI, OUT_BYTES);   // output staging tiles (2 or 4)
+  static constexpr int EPI_TILES = tc2_epi_tiles(N_TILE, EPI, OUT_BYTES);   // output staging tiles (0 or 2)
   static constexpr int EPI_BYTES = EPI_TILES * TC2_TILE_BYTES;
   static constexpr int RING_BYTES = tc2_ring_bytes(N_TILE, EPI, OUT_BYTES);          // operand ring (offsets are 8-bit KB)
   static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256;
@@ -198,8 +190,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   const TcItem2* __restrict__ items, const TcRec* __restrict__ stream_p0, const TcRec* __restrict__ stream_p1,
                   const TcRec* __restrict__ stream_m, const uint32_t* __restrict__ stream_off,
                   const int* __restrict__ eitems, int n_slots,
-                  TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride,
-                  const __half* __restrict__ mask_src, float out_scale, const TcFinalArgs fa) {
+                  TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride, const TcFinalArgs fa) {
   using Cfg = Tc2Cfg<N_TILE, EPI, (int)sizeof(TOUT)>;
   constexpr bool TMA_EPI = Cfg::TMA_EPI;
   constexpr int HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
@@ -262,7 +253,6 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // warp-uniform address so the TMA operands live in uniform registers (no per-instruction
     // R2UR/ELECT loop), and one elected lane issues.
     uint32_t it = 0;
-    long long t_wait = 0;
     const uint32_t ring = stg_base;
     for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
       ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
@@ -276,12 +266,10 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int kc = (r0.x >> 8) & 0xF, nA = (r0.x >> 12) & 0x7, nB = (r0.x >> 15) & 0xF;
         const uint32_t dep = (r0.x >> 19) & 0xF;
         const int row0 = (2 * (int)(r0.y & 0xFFFFu) + (int)rank) * kRowTile;
-        const long long tw0 = fa.dbg ? clock64() : 0;
         if (it >= dep) ptx::mbar_wait(bar_empty + 8 * ((it - dep) & (TC2_NSLOT - 1)), ((it - dep) >> 3) & 1);   // step it-dep consumed
         // implied by the wait above (steps are consumed in order); observing every phase of this slot exactly once
         // before it is re-armed keeps the barrier protocol checkable (compute-sanitizer synccheck)
         if (dep != TC2_NSLOT && it >= TC2_NSLOT) ptx::mbar_wait(bar_empty + 8 * slot, ((it - TC2_NSLOT) >> 3) & 1);
-        if (fa.dbg) t_wait += clock64() - tw0;
         const uint32_t full = bar_full + 8 * slot;
         const uint32_t sa = smem_base + ((r0.x & 0xFFu) << 10);
         if (ptx::elect_one()) {
@@ -306,22 +294,15 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     // drain: the last steps' "consumed" signals are otherwise never observed (nobody leaves while MMAs still read smem)
     for (uint32_t j = it > TC2_NSLOT ? it - TC2_NSLOT : 0; j < it; ++j) ptx::mbar_wait(bar_empty + 8 * (j & (TC2_NSLOT - 1)), (j >> 3) & 1);
-    if (fa.dbg && lane == 0) fa.dbg[blockIdx.x * 16 + 0] = (unsigned long long)t_wait;
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       constexpr uint32_t idesc = make_idesc_f16(256, N_TILE);
       uint32_t it = 0, item_count = 0;
-      long long t_wait_full = 0, t_wait_acc = 0, t_issue = 0;
-      const bool fine = fa.dbg != nullptr && !(fa.dbg_flags & 8);   // per-step clocks (perturbs the loop)
-      const bool no_mma = (fa.dbg_flags & 16) != 0;                 // timing experiment: commits only
-      const long long t_mma_start = fa.dbg ? clock64() : 0;
-      unsigned long long gt_mma0 = 0, gt_first = 0;
-      if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_mma0));
       const uint32_t ring = stg_base + TC2_REC_BATCH * (uint32_t)sizeof(TcRec);
       const uint64_t desc0 = make_smem_desc_sw128(smem_base);
       const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
-      uint32_t buf = 0, prev_b_lo0 = 0;
+      uint32_t buf = 0;
       for (uint32_t base = rbeg; base < rend; base += TC2_REC_BATCH) {
         ptx::st_shared_v4(ring + lane * 16u, mine.x, mine.y, mine.z, mine.w);
         __syncwarp();
@@ -335,14 +316,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const uint32_t flags = (r0.x >> 16) & 0x3u;
           if (flags & 1u) {                                   // first step of an item: its accumulator buffer must be drained
             buf = item_count & 1;
-            const long long ta0 = fine ? clock64() : 0;
             ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
-            if (fine) t_wait_acc += clock64() - ta0;
           }
-          const long long tf0 = fine ? clock64() : 0;
           ptx::mbar_wait(bar_full + 8 * slot, phase);
-          const long long tf1 = fine ? clock64() : 0;
-          if (fa.dbg && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_first));
           ptx::tc_fence_after();
           // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
           const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
@@ -352,11 +328,11 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const uint32_t opw[6] = {r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int oi = 0; oi < TC2_MAX_OPS; ++oi) {
-              if (oi >= (no_mma ? 0 : n_ops)) break;
+              if (oi >= n_ops) break;
               const uint32_t e = opw[oi >> 1] >> (16 * (oi & 1));
               const uint32_t first = (e >> 10) & 1u;
               const uint32_t a_lo = a_lo0 + (e & 3u) * (uint32_t)(TC_A_BYTES >> 4);
-              const uint32_t b_lo = (((e >> 11) & 1u) ? prev_b_lo0 : b_lo0) + ((e >> 2) & 7u) * (uint32_t)(HALF_B >> 4);
+              const uint32_t b_lo = b_lo0 + ((e >> 2) & 7u) * (uint32_t)(HALF_B >> 4);
               const uint32_t d = d0 + ((e >> 7) & 7u) * ACC_STRIDE;
               const uint32_t idg = idesc + ((e >> 5) & 3u) * ((uint32_t)(N_TILE >> 3) << 17);   // N = slots * N_TILE
 #pragma unroll
@@ -364,28 +340,16 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idg,
                                   (k > 0 || !first) ? 1u : 0u);
             }
-            ptx::umma_commit_2sm(bar_empty + 8 * slot);           // this step is consumed (both CTAs); the host planner knows
-                                                                  // which later step may still read its weight tiles
+            ptx::umma_commit_2sm(bar_empty + 8 * slot);           // this step is consumed (both CTAs)
             if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
           }
           __syncwarp();
-          prev_b_lo0 = b_lo0;
           if (flags & 2u) ++item_count;
-          if (fine) { t_wait_full += tf1 - tf0; t_issue += clock64() - tf1; }
         }
         __syncwarp();
       }
       // drain: observe the release of the last (up to two) accumulator buffers by the epilogue warps of both CTAs
       for (uint32_t j = item_count > 2 ? item_count - 2 : 0; j < item_count; ++j) ptx::mbar_wait(bar_acc_empty + 8 * (j & 1), (j >> 1) & 1);
-      if (fa.dbg && lane == 0) {
-        fa.dbg[blockIdx.x * 16 + 1] = (unsigned long long)t_wait_full;
-        fa.dbg[blockIdx.x * 16 + 2] = (unsigned long long)t_wait_acc;
-        fa.dbg[blockIdx.x * 16 + 3] = (unsigned long long)t_issue;
-        fa.dbg[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_mma_start);   // MMA warp: whole item loop
-        unsigned long long gt_mma1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_mma1));
-        fa.dbg[blockIdx.x * 16 + 8] = gt_mma0; fa.dbg[blockIdx.x * 16 + 9] = gt_mma1; fa.dbg[blockIdx.x * 16 + 10] = gt_first;
-      }
     }
   } else {
     // ===================== epilogue (warps 2..9, both CTAs) =====================
@@ -394,11 +358,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int lq = warp & 3;                          // TMEM lanes this warp may access
     const int half = (warp - 2) >> 2;                 // 0 | 1: which of the two warps of this quarter
     const int row = lq * 32 + lane;
-    uint32_t item_count = 0, unit_count = 0;
-    long long t_ewait = 0, t_ework = 0;
-    const long long t_start = fa.dbg ? clock64() : 0;
-    unsigned long long gt_start = 0;
-    if (fa.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
+    uint32_t item_count = 0;
     for (int kk = 0, item_e = item_first, item_next; item_e >= 0; ++kk, ++item_count, item_e = item_next) {
       item_next = tc2_item_at(eitems, kk + 1, pair, n_pairs, n_slots);      // (window << 16 | row pair), one item ahead
       const int win = item_e >> 16, mp = item_e & 0xFFFF;
@@ -411,9 +371,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       float4 xq_next[FINAL ? (EPI == EPI_FINAL_SIGMOID1 ? 4 : 12) : 1];
       if (FINAL && half < n_acc)     // first block's target pixels: in flight while the MMAs finish
         tc_final_targets<(EPI == EPI_FINAL_SIGMOID1 ? 1 : 3)>(reinterpret_cast<float4(&)[EPI == EPI_FINAL_SIGMOID1 ? 4 : 12]>(xq_next), fa, ip->q[half], (int)n);
-      const long long te0 = fa.dbg ? clock64() : 0;
       ptx::mbar_wait(bar_acc_full + 8 * buf, (item_count >> 1) & 1);
-      const long long te1 = fa.dbg ? clock64() : 0;
       ptx::tc_fence_after();
       if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
         constexpr int CO = (EPI == EPI_FINAL_SIGMOID1) ? 1 : 3;
@@ -432,10 +390,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
       } else if (TMA_EPI) {
         // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 ->
-        //      128B-swizzled smem tile -> one TMA store per 128x64 tile; mask tiles arrive by TMA load.
+        //      128B-swizzled smem tile -> one TMA store per 128x64 tile.
         constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
         const int n_units = n_acc * G;
-        constexpr int TPH = Cfg::EPI_TILES >= 2 ? Cfg::EPI_TILES / 2 : 1;   // staging tiles per epilogue half
         const bool t0 = (warp == 2 + 4 * half) && lane == 0;  // issues this half's bulk copies
         const int row0 = (2 * mp + (int)rank) * kRowTile;
         const uint32_t swz = (uint32_t)(row & 7);
@@ -455,7 +412,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           {
             float v[64];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }   // out_scale == 1 (checked at launch)
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
             if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
               const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + g * 64);
 #pragma unroll
@@ -488,9 +445,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64), r0);
             ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64 + 32), r1);
           }
-          const uint32_t s_out = epi_base + (uint32_t)(half * TPH + (int)(unit_count & (TPH - 1))) * TC2_TILE_BYTES;
-          ++unit_count;
-          if (t0) { if (TPH == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0(); }   // the store that last read s_out is done
+          const uint32_t s_out = epi_base + (uint32_t)half * TC2_TILE_BYTES;
+          if (t0) ptx::bulk_wait_read0();                  // the store that last read s_out is done
           ptx::named_bar_sync(1 + half, 128);              // s_out free
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -506,30 +462,16 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         constexpr int CH = N_TILE >= 32 ? N_TILE / 32 : 1;     // 32-column chunks per accumulator
         const int n_units = n_acc * CH;
         uint32_t rA[32], rB[32];
-        uint4 mA[4], mB[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { mA[j] = make_uint4(0, 0, 0, 0); mB[j] = make_uint4(0, 0, 0, 0); }
         int u = half;
-        if (u < n_units) {
-          ptx::tmem_ld32(tbuf + (uint32_t)((u / CH) * ACC_STRIDE + (u % CH) * 32), rA);
-          if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mA, mask_src, ip->q[u / CH], (u % CH) * 32, n, n_pad);
-        }
+        if (u < n_units) ptx::tmem_ld32(tbuf + (uint32_t)((u / CH) * ACC_STRIDE + (u % CH) * 32), rA);
         for (; u < n_units; u += 4) {
           ptx::tmem_ld_wait();
-          if (u + 2 < n_units) {
-            ptx::tmem_ld32(tbuf + (uint32_t)(((u + 2) / CH) * ACC_STRIDE + ((u + 2) % CH) * 32), rB);
-            if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mB, mask_src, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad);
-          }
-          if (EPI == EPI_MOMENTUM) tc_momentum_chunk(rA, (u % CH) * 32, n, N_TILE, fa);
-          else tc_store_chunk<N_TILE, EPI, TOUT>(rA, mA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
+          if (u + 2 < n_units) ptx::tmem_ld32(tbuf + (uint32_t)(((u + 2) / CH) * ACC_STRIDE + ((u + 2) % CH) * 32), rB);
+          tc_store_chunk<N_TILE, EPI, TOUT>(rA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride);
           if (u + 2 < n_units) {
             ptx::tmem_ld_wait();
-            if (u + 4 < n_units) {
-              ptx::tmem_ld32(tbuf + (uint32_t)(((u + 4) / CH) * ACC_STRIDE + ((u + 4) % CH) * 32), rA);
-              if (EPI == EPI_MASK && !(fa.dbg_flags & 2)) tc_load_mask<N_TILE>(mA, mask_src, ip->q[(u + 4) / CH], ((u + 4) % CH) * 32, n, n_pad);
-            }
-            if (EPI == EPI_MOMENTUM) tc_momentum_chunk(rB, ((u + 2) % CH) * 32, n, N_TILE, fa);
-            else tc_store_chunk<N_TILE, EPI, TOUT>(rB, mB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride, out_scale, fa.dbg_flags);
+            if (u + 4 < n_units) ptx::tmem_ld32(tbuf + (uint32_t)(((u + 4) / CH) * ACC_STRIDE + ((u + 4) % CH) * 32), rA);
+            tc_store_chunk<N_TILE, EPI, TOUT>(rB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride);
           }
         }
       }
@@ -591,16 +533,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (tid == 0) fa.m_counter[rt] = 0u;             // ready for the next launch
         }
       }
-      if (fa.dbg) { t_ewait += te1 - te0; t_ework += clock64() - te1; }
     }
     if (TMA_EPI && lane == 0 && (warp == 2 || warp == 6)) ptx::bulk_wait_all0();   // stores landed before exit
-    if (fa.dbg && warp == 2 && lane == 0) {
-      fa.dbg[blockIdx.x * 16 + 5] = (unsigned long long)t_ework;
-      unsigned long long gt_end;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
-      fa.dbg[blockIdx.x * 16 + 6] = gt_start;      // ns, after the PDL wait
-      fa.dbg[blockIdx.x * 16 + 7] = gt_end;        // ns, after this CTA's last epilogue
-    }
   }
 
   ptx::tc_fence_before();
@@ -640,7 +574,6 @@ struct Tc2HostStep {
   uint8_t b_ent[2][TC2_MAX_BSLOTS] = {{0}, {0}};
   uint16_t ops[TC2_MAX_OPS] = {0};
   int n_tile_mmas = 0;         // un-merged count (statistics)
-  bool uses_prev = false;      // some op reads a weight tile the previous step staged
   int bytes = 0;               // operand bytes staged per CTA
 };
 struct Tc2HostItem {
@@ -654,7 +587,7 @@ struct Tc2HostItem {
 // pixels of a step is staged once.  Within a pixel, runs of consecutive accumulators whose tiles nobody else in
 // the step uses (and whose first-MMA flags agree) become one merged-N MMA.
 static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int N, int K, int max_g, int max_a,
-                           int step_max_bytes, bool share_prev, Tc2HostItem* out) {
+                           int step_max_bytes, Tc2HostItem* out) {
   const int kch = K / 64, half_b = (N / 2) * 128;
   out->hdr = TcItem2{};
   out->hdr.n_acc = (uint32_t)qs.size();
@@ -680,21 +613,17 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
     for (size_t b0 = 0; b0 < g.second.size(); b0 += (size_t)ent_cap)
       px.push_back({g.first, std::vector<std::pair<int, int>>(g.second.begin() + b0,
                                                                g.second.begin() + std::min(g.second.size(), b0 + (size_t)ent_cap))});
-  // ---- phase 1: greedy groups.  A weight tile staged by the immediately preceding group of the same k-chunk phase is
-  //      still in the ring (the planner keeps that step's region alive one step longer): it is not staged again.
+  // ---- phase 1: greedy groups.  (Re-using the weight tiles of the PREVIOUS step as well was measured in round 1:
+  //      5-15 % fewer bytes, but 2 % slower - less ring capacity in flight, fewer merged-N MMAs - and is gone.)
   struct Group { size_t i0, i1; std::vector<int> staged; };
   std::vector<Group> groups;
   {
     size_t i0 = 0;
-    std::vector<int> prev_staged;
     while (i0 < px.size()) {
       size_t i1 = i0;
       std::vector<int> staged;      // tiles this group loads itself
       int n_ent = 0;
-      auto have = [&](int t) {
-        return std::find(staged.begin(), staged.end(), t) != staged.end() ||
-               (share_prev && std::find(prev_staged.begin(), prev_staged.end(), t) != prev_staged.end());
-      };
+      auto have = [&](int t) { return std::find(staged.begin(), staged.end(), t) != staged.end(); };
       while (i1 < px.size() && (int)(i1 - i0) < max_a) {
         int fresh = 0;
         std::vector<int> fresh_tiles;
@@ -712,24 +641,17 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
         ++i1;
       }
       groups.push_back({i0, i1, staged});
-      prev_staged = staged;
       i0 = i1;
     }
   }
-  // ---- phase 2: ops + B slots.  A tile is "single use" (mergeable into an N = g*N_TILE MMA) only if neither another
-  //      pixel of its group nor the next group needs it in the plain half-per-CTA layout.
+  // ---- phase 2: ops + B slots.  A tile is "single use" (mergeable into an N = g*N_TILE MMA) only if no other pixel of
+  //      its group needs it in the plain half-per-CTA layout.
   uint32_t seen = 0;
-  int prev_slot_of[32];
-  for (int t = 0; t < 32; ++t) prev_slot_of[t] = -1;
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     const Group& G = groups[gi];
     std::vector<int> use(32, 0);
     for (size_t i = G.i0; i < G.i1; ++i)
       for (auto& ta : px[i].second) ++use[ta.first];
-    if (share_prev && gi + 1 < groups.size())
-      for (size_t i = groups[gi + 1].i0; i < groups[gi + 1].i1; ++i)
-        for (auto& ta : px[i].second)
-          if (std::find(G.staged.begin(), G.staged.end(), ta.first) != G.staged.end()) ++use[ta.first];
     Tc2HostStep st;
     st.nA = (int)(G.i1 - G.i0);
     int slot_of[32];
@@ -740,14 +662,9 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
       for (size_t e = 0; e < ent.size();) {
         const int acc0 = ent[e].second, t0 = ent[e].first;
         const bool f0 = !(seen & (1u << acc0));
-        const bool own = std::find(G.staged.begin(), G.staged.end(), t0) != G.staged.end();
         size_t g = 1;
-        int slot, from_prev = 0;
-        if (!own) {                                     // staged by the previous step, plain layout
-          slot = prev_slot_of[t0];
-          from_prev = 1;
-          st.uses_prev = true;
-        } else if (use[t0] == 1) {
+        int slot;
+        if (use[t0] == 1) {
           while ((int)g < max_g && e + g < ent.size() && ent[e + g].second == acc0 + (int)g && use[ent[e + g].first] == 1 &&
                  std::find(G.staged.begin(), G.staged.end(), ent[e + g].first) != G.staged.end() &&
                  (!(seen & (1u << ent[e + g].second))) == f0)
@@ -766,7 +683,7 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
           for (int r = 0; r < 2; ++r) st.b_ent[r][slot] = (uint8_t)((t0 & 0x1F) | (r << 5));
           st.nB += 1;
         }
-        st.ops[st.n_ops++] = (uint16_t)((i - G.i0) | (slot << 2) | ((g - 1) << 5) | (acc0 << 7) | ((f0 ? 1 : 0) << 10) | (from_prev << 11));
+        st.ops[st.n_ops++] = (uint16_t)((i - G.i0) | (slot << 2) | ((g - 1) << 5) | (acc0 << 7) | ((f0 ? 1 : 0) << 10));
         st.n_tile_mmas += (int)g;
         for (size_t jj = 0; jj < g; ++jj) seen |= 1u << ent[e + jj].second;
         e += g;
@@ -774,7 +691,6 @@ static void tc2_build_item(const PairTable& tab, const std::vector<int>& qs, int
     }
     st.bytes = st.nA * TC_A_BYTES + st.nB * half_b;
     out->steps.push_back(st);
-    for (int t = 0; t < 32; ++t) prev_slot_of[t] = slot_of[t];
   }
   // k-chunk outermost: every accumulator then sums its (k-chunk, input pixel) contributions in one canonical order
   // - ascending k-chunk, ascending pixel - whatever the window shape and step grouping, so results do not depend
@@ -843,19 +759,11 @@ struct Tc2Plan {               // host result of the planner (what tc2_get_sched
 
 static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, int max_acc, int n_mpairs, int n_pairs,
                     int ring_bytes, Tc2Plan* plan) {
-  const bool merge = (N >= 64) && !(getenv("DGAN_MERGE_N") && atoi(getenv("DGAN_MERGE_N")) == 0);
-  const int max_g = merge ? std::min(4, 256 / N) : 1;
-  // Reusing the weight tiles of the previous step (its ring region then lives one step longer) cuts 5-15 % of the bytes
-  // of the conv kernels but measured 2 % slower end to end (less ring capacity in flight, fewer merged-N MMAs): opt-in.
-  const bool share_prev = getenv("DGAN_SHARE_PREV") && atoi(getenv("DGAN_SHARE_PREV")) != 0;
-  const int max_a = getenv("DGAN_MULTI_A") ? std::max(1, std::min(TC2_MAX_A, atoi(getenv("DGAN_MULTI_A")))) : TC2_MAX_A;
+  const int max_g = (N >= 64) ? std::min(4, 256 / N) : 1;      // merged-N MMAs (see TC2_MAX_A above)
+  const int max_a = TC2_MAX_A;
   // Step size: a step is consumed only once all of it has landed, so big steps cost pipeline depth (4 x 48 KB fit the
   // ring); measured on C2: 32 KB (= one A tile per step) 5359, 40 KB 5466, 48-56 KB 5660, 64 KB 5553, 96 KB 5385 images/s.
-  int step_max = std::min((ring_bytes / 2) & ~1023, 48 * 1024);
-  if (getenv("DGAN_STEP_MAX_KB")) step_max = std::min((ring_bytes / 2) & ~1023, std::max(32, atoi(getenv("DGAN_STEP_MAX_KB"))) * 1024);
-  // a step that reads the previous step's weight tiles must never wrap onto that step's region: with steps of at
-  // most a third of the ring, the wrapped step ends before its predecessor begins
-  if (share_prev) step_max = std::min(step_max, (ring_bytes / 3) & ~1023);
+  const int step_max = std::min((ring_bytes / 2) & ~1023, 48 * 1024);
   double best_cost = 1e300;
   int best_shape[4] = {1, 1, 1, 1};
   std::vector<Tc2HostItem> best_items;
@@ -866,10 +774,9 @@ static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, 
       for (int sy = 1; sy <= (wh > 1 ? 2 : 1); ++sy)
         for (int sx = 1; sx <= (ww > 1 ? 2 : 1); ++sx) {
           if (wh * ww > max_acc || wh > h_grid || ww > std::max(w_grid, 1)) continue;
-          if ((sy > 1 || sx > 1) && max_a == 1) continue;
           tc2_enumerate_windows(h_grid, std::max(w_grid, 1), wh, ww, sy, sx, &wins);
           std::vector<Tc2HostItem> items(wins.size());
-          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(tab, wins[i], N, K, max_g, max_a, step_max, share_prev, &items[i]);
+          for (size_t i = 0; i < wins.size(); ++i) tc2_build_item(tab, wins[i], N, K, max_g, max_a, step_max, &items[i]);
           std::stable_sort(items.begin(), items.end(), [](const Tc2HostItem& l, const Tc2HostItem& r) { return l.stage_bytes > r.stage_bytes; });
           std::vector<double> icost(items.size());
           for (size_t i = 0; i < items.size(); ++i)
@@ -909,7 +816,6 @@ static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, 
     stream_off[pr] = (uint32_t)stream_m.size();
     // circular operand ring of this CTA pair: sequential allocation, wrap when the step does not fit
     std::vector<std::pair<int, int>> region;     // [begin, end) in KB of every step of this stream
-    std::vector<char> reads_prev;                // step k reads weight tiles from step k-1's region
     int cursor = 0;
     for (size_t k = 0; k < best_lists[pr].size(); ++k) {
       const int win = best_lists[pr][k] / n_mpairs, mp = best_lists[pr][k] % n_mpairs;
@@ -923,23 +829,15 @@ static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, 
         if (cursor + kb > ring_bytes / 1024) cursor = 0;
         const int beg = cursor, end = cursor + kb;
         cursor = end;
-        // The producer may overwrite a region once the last step that reads it is consumed: the step itself, or the
-        // next one when that reads weight tiles out of it.  dep = distance to the latest such step among the
-        // overlapping regions (8 = barrier-slot reuse only).
+        // The producer may overwrite a region once the step that used it is consumed: dep = distance to the latest
+        // earlier step whose region overlaps this one (8 = barrier-slot reuse only).
         int dep = TC2_NSLOT;
         const int kidx = (int)region.size();
         for (int d = 1; d <= TC2_NSLOT && d <= kidx; ++d) {
-          const int c = kidx - d;
-          const auto& rg = region[(size_t)c];
-          if (rg.first < end && beg < rg.second) {
-            const bool next_reads = (c + 1 < kidx) ? reads_prev[(size_t)c + 1] != 0 : hs.uses_prev;   // step c+1 (maybe this one)
-            const int last_reader = c + (next_reads ? 1 : 0);
-            if (last_reader >= kidx) { set_error("operand ring too small for the step schedule"); return DGAN_ERR_UNSUPPORTED; }
-            dep = std::min(dep, kidx - last_reader);
-          }
+          const auto& rg = region[(size_t)(kidx - d)];
+          if (rg.first < end && beg < rg.second) { dep = d; break; }
         }
         region.push_back({beg, end});
-        reads_prev.push_back(hs.uses_prev ? 1 : 0);
         const uint32_t flags = (j == 0 ? 1u : 0u) | (j + 1 == itm.steps.size() ? 2u : 0u);
         TcRec rm{};
         rm.w[0] = (uint32_t)beg | ((uint32_t)hs.nA << 8) | ((uint32_t)hs.n_ops << 11) | (flags << 16);
@@ -987,7 +885,7 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
     for (uint32_t a = 0; a < h.n_acc; ++a)
       if ((size_t)h.q[a] + 1 >= tab.off.size()) return fail("window pixel out of range");
   }
-  struct Step { int beg, end, nB, kc; bool uses_prev; uint8_t b0[8], b1[8]; };
+  struct Step { int beg, end, nB, kc; uint8_t b0[8], b1[8]; };
   for (size_t pr = 0; pr < n_pairs; ++pr) {
     const uint32_t r_beg = pl.stream_off[pr], r_end = pl.stream_off[pr + 1];
     if (r_beg > r_end || r_end > pl.stream_m.size()) return fail("stream_off not monotone");
@@ -997,7 +895,6 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
     uint32_t seen = 0;
     std::vector<std::pair<int, int>> last_kp;                     // per accumulator: last (kc, p)
     std::vector<std::vector<std::pair<int, int>>> contrib;        // per accumulator: (p * 32 + tile, kc)
-    size_t item_first_step = 0;
     for (uint32_t ri = r_beg; ri < r_end; ++ri) {
       const TcRec &m = pl.stream_m[ri], &p0 = pl.stream_p[0][ri], &p1 = pl.stream_p[1][ri];
       const int k = (int)steps.size();
@@ -1027,7 +924,6 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
         seen = 0;
         last_kp.assign(pl.hdrs[win].n_acc, {-1, -1});
         contrib.assign(pl.hdrs[win].n_acc, {});
-        item_first_step = steps.size();
       }
       if (!in_item) return fail("step outside an item");
       if ((int)(p0.w[1] & 0xFFFF) != mp) return fail("row pair of a step differs from its item");
@@ -1041,14 +937,8 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
         if (g > 1 && (acc_stride != N || g * N > 256)) return fail("merged MMA too wide");
         const int p = (int)((p0.w[2 + a_idx / 2] >> (16 * (a_idx & 1))) & 0xFFFF);
         int tiles[4];
-        if (prev) {
-          if (g != 1 || steps.size() == item_first_step) return fail("bad previous-step reference");
-          const Step& ps = steps.back();
-          if (ps.kc != st.kc || slot >= ps.nB) return fail("previous-step reference out of range");
-          if ((ps.b0[slot] & 0x3F) != (ps.b0[slot] & 0x1F) || (ps.b1[slot] & 0x3F) != ((ps.b0[slot] & 0x1F) | 0x20)) return fail("previous-step tile is not in plain layout");
-          tiles[0] = ps.b0[slot] & 0x1F;
-          st.uses_prev = true;
-        } else {
+        if (prev) return fail("op refers to a previous step's weight tiles (not supported)");
+        {
           if (slot + g > nB) return fail("op reads a B slot the step does not stage");
           for (int i = 0; i < g; ++i) {
             const int x0 = 2 * i, x1 = 2 * i + 1;
@@ -1070,12 +960,10 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
         for (int i = 0; i < g; ++i) seen |= 1u << (acc0 + i);
       }
       // ring safety
-      if (st.uses_prev && !steps.empty() && steps.back().beg < st.end && st.beg < steps.back().end) return fail("step overlaps the region it reads");
       for (int c = k - 1; c >= 0 && c >= k - 4 * TC2_NSLOT; --c) {
         const Step& o = steps[(size_t)c];
         if (!(o.beg < st.end && st.beg < o.end)) continue;
-        const int last_reader = c + ((c + 1 < k) ? (steps[(size_t)c + 1].uses_prev ? 1 : 0) : (st.uses_prev ? 1 : 0));
-        if (last_reader > k - dep) return fail("ring hazard: a region may be overwritten while it can still be read");
+        if (c > k - dep) return fail("ring hazard: a region may be overwritten while it can still be read");
       }
       steps.push_back(st);
       if (flags & 2u) {
@@ -1119,10 +1007,6 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   if ((rc = tc_upload(allocs, plan.eitems.data(), plan.eitems.size() * sizeof(int), (void**)&sc.eitems, s))) return rc;
   w2.by_mpairs.push_back({n_mpairs, sc});
   *out = &w2.by_mpairs.back().second;
-  if (getenv("DGAN_TC_VERBOSE"))
-    fprintf(stderr, "[dgan] schedule N=%d K=%d grid %dx%d n_mpairs=%d -> window %dx%d stride %dx%d, %d windows, %lld steps, %.1f MB staged/CTA-set, "
-                    "%lld tile-MMAs in %lld merged\n", w1.N, w1.K, w2.h_grid, w2.w_grid, n_mpairs, sc.wh, sc.ww, sc.sy, sc.sx, sc.n_windows, plan.n_steps,
-            2.0 * plan.n_bytes / 1e6, plan.n_single, plan.n_mma);
   return 0;
 }
 
@@ -1139,7 +1023,6 @@ static int tc2_optin_all() {
   TC2_OPTIN(64, EPI_MASK, __half); TC2_OPTIN(128, EPI_MASK, __half); TC2_OPTIN(256, EPI_MASK, __half);
   TC2_OPTIN(64, EPI_NONE, __half); TC2_OPTIN(128, EPI_NONE, __half); TC2_OPTIN(256, EPI_NONE, __half);
   TC2_OPTIN(64, EPI_NONE, float); TC2_OPTIN(128, EPI_NONE, float); TC2_OPTIN(256, EPI_NONE, float);
-  TC2_OPTIN(64, EPI_MOMENTUM, float); TC2_OPTIN(128, EPI_MOMENTUM, float); TC2_OPTIN(256, EPI_MOMENTUM, float);
   TC2_OPTIN(16, EPI_FINAL_SIGMOID1, __half); TC2_OPTIN(48, EPI_FINAL_TANH3, __half);
 #undef TC2_OPTIN
   return 0;
@@ -1147,14 +1030,10 @@ static int tc2_optin_all() {
 
 template <typename TOUT>
 static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, const TcWeights2& w2m, const __half* in,
-                           TOUT* out, int n_pad, int epi, const float* bias, const __half* mask_src, float out_scale,
-                           cudaStream_t s, const TcFinalArgs* final_args = nullptr, const CUtensorMap* pre_a = nullptr,
+                           TOUT* out, int n_pad, int epi, const float* bias, cudaStream_t s, const TcFinalArgs* final_args = nullptr, const CUtensorMap* pre_a = nullptr,
                            const CUtensorMap* pre_out = nullptr) {
   TcFinalArgs fa{};
   if (final_args) fa = *final_args;
-  fa.dbg = nullptr;
-  fa.dbg_flags = st.dbg_flags;
-  if (st.dbg != nullptr && st.dbg_launch < st.dbg_max_launches) fa.dbg = st.dbg + (size_t)(st.dbg_launch++) * 160 * 16;
   CUtensorMap tm_a;
   int rc;
   if (pre_a != nullptr) tm_a = *pre_a;          // encoded once per workspace by the caller
@@ -1165,32 +1044,27 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
     else if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
   }
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
-  if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT)) && out_scale != 1.f) { set_error("fp16 tile epilogue has no output scale"); return DGAN_ERR_UNSUPPORTED; }
   const int n_mpairs = n_pad / (2 * kRowTile);
   const Tc2Schedule* schp = nullptr;
-  const int pairs_avail = st.max_pairs > 0 ? std::min(st.max_pairs, st.num_sms / 2) : st.num_sms / 2;
+  const int pairs_avail = st.num_sms / 2;
   const int ring_bytes = tc2_ring_bytes(w.N, epi, (int)sizeof(TOUT));
   if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, pairs_avail, ring_bytes, st.allocs, s, &schp))) return rc;
   const Tc2Schedule& w2s = *schp;
-  const int total = w2s.n_windows * n_mpairs;
   const int grid = 2 * w2s.n_pairs;       // pairs without work find -1 in slot 0 and fall through
-  (void)total;
   cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
-                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, mask_src, out_scale, fa)
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
-                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, \
-                  mask_src, out_scale, fa)
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
     if (w.N == 64) TC2_GO(64, EP);      \
     else if (w.N == 128) TC2_GO(128, EP); \
     else TC2_GO(256, EP);               \
   } while (0)
-  if (sizeof(TOUT) == 4 && epi == EPI_MOMENTUM) { TC2_BY_N(EPI_MOMENTUM); }
-  else if (sizeof(TOUT) == 4) { TC2_BY_N(EPI_NONE); }
+  if (sizeof(TOUT) == 4) { TC2_BY_N(EPI_NONE); }
   else if (epi == EPI_FINAL_SIGMOID1) { TC2_GO_H(16, EPI_FINAL_SIGMOID1); }
   else if (epi == EPI_FINAL_TANH3) { TC2_GO_H(48, EPI_FINAL_TANH3); }
   else if (epi == EPI_BIAS_RELU) { TC2_BY_N(EPI_BIAS_RELU); }

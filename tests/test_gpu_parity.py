@@ -245,21 +245,6 @@ def test_shape_fuzz_ragged_sizes(gens):
             assert np.abs(loss.cpu().numpy() - ref["loss_min"]).max() <= max(t["loss"], 1e-5)
 
 
-def test_first_generation_tensor_core_kernel_still_correct(golden_dir, monkeypatch):
-    """DGAN_TC_MODE=1 selects the one-CTA-per-MMA kernel (kernels_tc.cuh) kept as an A/B fallback."""
-    from defensegan_b200 import _native
-    monkeypatch.setenv("DGAN_TC_MODE", "1")
-    g = np.load(os.path.join(golden_dir, "mnist_c1.npz"))
-    w = O.init_generator_weights("mnist")
-    dev = torch.device("cuda", 0)
-    gen = _native.NativeGenerator("mnist", [torch.as_tensor(v).to(dev) for v in w.values()], precision="fp16", device=dev)
-    rec, loss, idx = gen.reconstruct(torch.tensor(g["images"]).cuda(), int(g["R"]), int(g["L"]), float(g["lr"]),
-                                     z_init_val=torch.tensor(g["z0"]).cuda(), return_aux=True)
-    np.testing.assert_array_equal(idx.cpu().numpy(), g["idx64"])
-    assert np.abs(rec.cpu().numpy() - g["rec64"]).max() <= TOL["fp16"]["rec"]
-    gen.close()
-
-
 def test_sharded_api_single_rank_and_random_z0_statistics():
     """parallel.reconstruct_sharded degenerates to the single-GPU call without a process group; the Philox z0
     (models/gan.py:370-377: N(0, 1/latent_dim)) does not depend on how rows are tiled."""
