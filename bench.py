@@ -148,13 +148,15 @@ def _cpu_worker_run(job):
 
 class CpuPort:
     """The oracle restatement of the reference's TF1 CPU path (oracle/defensegan_oracle.py, fp32) on the host cores.
-    One torch process stops scaling near 16 threads on these small per-step tensors (tens of rows), so the sample's
-    images are split over `procs` worker processes of `threads` threads each - cores used = procs x threads."""
+    One torch process stops scaling near 16 threads on these small per-step tensors (tens of rows).  Splitting the
+    sample's images over several worker processes (DGAN_CPU_PROCS) is supported, but on the pool's GPU boxes it measured
+    SLOWER (8 x 16 threads: 1.8 images/s against 3.0-3.6 for 1 x 16; 128 logical CPUs are visible, the container's CPU
+    share evidently is not), so the default is one process - cores used = procs x threads is reported next to cores present."""
 
     def __init__(self, sample_images):
         self.cores_present = os.cpu_count() or 1
         self.threads = int(os.environ.get("DGAN_CPU_THREADS", min(self.cores_present, 16)))
-        want = int(os.environ.get("DGAN_CPU_PROCS", max(1, self.cores_present // self.threads)))
+        want = int(os.environ.get("DGAN_CPU_PROCS", 1))
         self.procs = max(1, min(want, sample_images))
         self.pool = None
         if self.procs > 1:
