@@ -711,8 +711,6 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
     c->tc.allocs = &c->allocs;
     {
       if ((rc = tc2_optin_all())) return fail(rc);
-      c->tc.quad_capacity = tc2_quad_capacity(c->tc.num_sms);
-      if (getenv("DGAN_CS")) c->tc.cluster_override = atoi(getenv("DGAN_CS"));       // TEMPORARY: A/B runs of the multicast clusters
       for (size_t l = 0; l < c->layers.size(); ++l) {
         GemmLayer& L = c->layers[l];
         if ((rc = tc2_build_direction(c->tc, L.tc_f, &L.tc2_f, L.fwd_host, L.h_used, L.w_used, 0, &c->allocs, s))) return fail(rc);

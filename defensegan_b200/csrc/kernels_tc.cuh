@@ -31,8 +31,6 @@ struct TcState {
   void* encode_fn = nullptr;    // cuTensorMapEncodeTiled
   std::vector<void*>* allocs = nullptr;   // the handle's allocation list (lazily built schedules are freed with it)
   int num_sms = 148;
-  int quad_capacity = 0;        // co-resident clusters of two CTA pairs (0: never use them)
-  int cluster_override = 0;     // development: force 2 or 4 CTAs per cluster
 };
 
 struct TcLayerSpec {

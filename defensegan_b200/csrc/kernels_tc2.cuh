@@ -107,13 +107,6 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// The same, delivered to this CTA and to the CTA of the same parity in every other pair of the cluster named in `mask`
-// (same shared-memory offset everywhere); each destination's bytes are credited to the even CTA of ITS pair.
-__device__ __forceinline__ void tma_load_3d_2sm_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }
@@ -123,9 +116,9 @@ __device__ __forceinline__ void tmem_relinquish_2sm() {
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {   // arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -190,20 +183,14 @@ __device__ __forceinline__ int tc2_item_at(const int* __restrict__ order, int k,
   return k < n_slots ? __ldg(order + (size_t)k * n_pairs + pair) : -1;
 }
 
-// CS = CTAs per cluster: 2 = one CTA pair per work stream; 4 = two pairs walk ONE stream in lockstep on two different row
-// pairs (pair j of the cluster takes row pair 2g + j of the stream's group g): they need the same weight tiles at the same
-// step, so pair 0 loads each half-tile once with TMA multicast into both pairs' rings - the weight traffic (38 % of the
-// bytes staged at configs[1]) is halved.  A step's ring slot is free again when BOTH pairs have consumed it.  With an odd
-// number of row pairs the last group's second pair recomputes the first pair's rows (identical stores, no update).
-template <int N_TILE, int EPI, typename TOUT, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+template <int N_TILE, int EPI, typename TOUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_out,
                   const TcItem2* __restrict__ items, const TcRec* __restrict__ stream_p0, const TcRec* __restrict__ stream_p1,
                   const TcRec* __restrict__ stream_m, const uint32_t* __restrict__ stream_off,
                   const int* __restrict__ eitems, int n_slots,
                   TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride, const TcFinalArgs fa) {
-  static_assert(CS == 2 || CS == 4, "cluster of one or two CTA pairs");
   using Cfg = Tc2Cfg<N_TILE, EPI, (int)sizeof(TOUT)>;
   constexpr bool TMA_EPI = Cfg::TMA_EPI;
   constexpr int HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
@@ -218,21 +205,16 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = ptx::cluster_ctarank();
-  const uint32_t rank = crank & 1u;                 // within the CTA pair
-  const uint32_t cpair = crank >> 1;                // pair within the cluster (0 when CS == 2)
+  const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
-  const int pair = blockIdx.x / CS, n_pairs = gridDim.x / CS;      // work stream of this cluster
-  constexpr uint16_t MASK_ALL = (uint16_t)((1u << CS) - 1u);
-  const uint16_t mask_pair = (uint16_t)(3u << (2 * cpair));
-  const int n_mpairs = n_pad / (2 * kRowTile);
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
     for (int s = 0; s < TC2_NSLOT; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);    // leader's producer arrive.expect_tx (bytes of both CTAs)
-      ptx::mbar_init(bar_empty + 8 * s, CS / 2);   // one multicast commit per CTA pair of the cluster
+      ptx::mbar_init(bar_empty + 8 * s, 1);   // one multicast commit per CTA
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_acc_full + 8 * b, 1);
@@ -283,8 +265,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const uint32_t slot = it & (TC2_NSLOT - 1);
         const int kc = (r0.x >> 8) & 0xF, nA = (r0.x >> 12) & 0x7, nB = (r0.x >> 15) & 0xF;
         const uint32_t dep = (r0.x >> 19) & 0xF;
-        const int mp = (CS == 2) ? (int)(r0.y & 0xFFFFu) : min(2 * (int)(r0.y & 0xFFFFu) + (int)cpair, n_mpairs - 1);
-        const int row0 = (2 * mp + (int)rank) * kRowTile;
+        const int row0 = (2 * (int)(r0.y & 0xFFFFu) + (int)rank) * kRowTile;
         if (it >= dep) ptx::mbar_wait(bar_empty + 8 * ((it - dep) & (TC2_NSLOT - 1)), ((it - dep) >> 3) & 1);   // step it-dep consumed
         // implied by the wait above (steps are consumed in order); observing every phase of this slot exactly once
         // before it is re-armed keeps the barrier protocol checkable (compute-sanitizer synccheck)
@@ -304,9 +285,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           for (int b = 0; b < TC2_MAX_BSLOTS; ++b) {
             if (b >= nB) break;
             const uint32_t e = ((b < 4) ? r1.x : r1.y) >> (8 * (b & 3));
-            if (CS == 2) ptx::tma_load_3d_2sm(sb + b * HALF_B, &tm_b, full, kc * 64, (int)((e >> 5) & 1u) * (N_TILE / 2), (int)(e & 0x1Fu));
-            else if (cpair == 0) ptx::tma_load_3d_2sm_mc(sb + b * HALF_B, &tm_b, full, kc * 64, (int)((e >> 5) & 1u) * (N_TILE / 2), (int)(e & 0x1Fu),
-                                                         (uint16_t)(5u << rank));     // this CTA and its counterpart in the other pair
+            ptx::tma_load_3d_2sm(sb + b * HALF_B, &tm_b, full, kc * 64, (int)((e >> 5) & 1u) * (N_TILE / 2), (int)(e & 0x1Fu));
           }
         }
         __syncwarp();
@@ -361,8 +340,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 ptx::umma_f16_2sm(d, ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), ((uint64_t)desc_hi << 32) | (b_lo + 2u * k), idg,
                                   (k > 0 || !first) ? 1u : 0u);
             }
-            ptx::umma_commit_2sm(bar_empty + 8 * slot, MASK_ALL);      // this pair has consumed the step (told to the whole cluster)
-            if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf, mask_pair);   // last step: accumulators complete in both CTAs
+            ptx::umma_commit_2sm(bar_empty + 8 * slot);           // this step is consumed (both CTAs)
+            if (flags & 2u) ptx::umma_commit_2sm(bar_acc_full + 8 * buf);   // last step: accumulators complete in both CTAs
           }
           __syncwarp();
           if (flags & 2u) ++item_count;
@@ -382,9 +361,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     uint32_t item_count = 0;
     for (int kk = 0, item_e = item_first, item_next; item_e >= 0; ++kk, ++item_count, item_e = item_next) {
       item_next = tc2_item_at(eitems, kk + 1, pair, n_pairs, n_slots);      // (window << 16 | row pair), one item ahead
-      const int win = item_e >> 16, grp = item_e & 0xFFFF;
-      const int mp = (CS == 2) ? grp : min(2 * grp + (int)cpair, n_mpairs - 1);
-      const bool dup = (CS == 4) && (2 * grp + (int)cpair > n_mpairs - 1);     // recomputing the other pair's rows: identical stores, no update
+      const int win = item_e >> 16, mp = item_e & 0xFFFF;
       const TcItem2* ip = items + win;
       const int n_acc = (int)ip->n_acc;
       const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
@@ -500,8 +477,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_remote(bar_acc_empty + 8 * buf, 2 * cpair);
-      if (EPI == EPI_NONE && sizeof(TOUT) == 4 && fa.m_counter != nullptr && !dup) {
+      if (lane == 0) ptx::mbar_arrive_remote(bar_acc_empty + 8 * buf, 0);
+      if (EPI == EPI_NONE && sizeof(TOUT) == 4 && fa.m_counter != nullptr) {
         // ---- momentum in the tail of the split-K Linear backward.  Every epilogue thread has stored its share of this
         //      item's partial sums; the CTA that completes the last partial of its 128-row tile applies the update
         //      (same arithmetic and summation order as momentum_kernel: parts 0, 1, 2, ...).
@@ -577,10 +554,9 @@ struct Tc2Schedule {           // one window tiling of a layer-direction + its i
   TcRec* stream_m = nullptr;       // MMA records, same indexing
   uint32_t* stream_off = nullptr;  // [n_pairs + 1] record offsets into the streams
   int* eitems = nullptr;           // [n_slots][n_pairs] (window << 16 | row pair) for the epilogue warps, or -1
-  int n_slots = 0, n_pairs = 0;    // n_pairs: work streams = clusters launched
+  int n_slots = 0, n_pairs = 0;
   int n_windows = 0;
   int wh = 0, ww = 0, sy = 1, sx = 1;
-  int cs = 2;                      // CTAs per cluster: 2, or 4 = two pairs per stream on row pairs 2g, 2g + 1 (weight multicast)
 };
 struct TcWeights2 {
   CUtensorMap tm_b;            // box {64, N/2, 1}
@@ -1012,26 +988,15 @@ static int tc2_check_plan(int N, int K, const PairTable& tab, int n_mpairs, int 
 }
 
 // Pick (and build on first use) the schedule of one layer-direction for `n_mpairs` row pairs and upload it.
-// Two pairs per stream (weight multicast) when the row pairs pair up: with an odd count the last group's second pair only
-// repeats the first one's work, which costs more than the multicast saves unless there are many groups.
-static int tc2_cluster_size(const TcState& st, int n_mpairs) {
-  if (st.cluster_override == 2 || st.cluster_override == 4) return st.cluster_override;
-  if (st.quad_capacity < 1 || n_mpairs < 2) return 2;
-  return (n_mpairs % 2 == 0 || n_mpairs >= 19) ? 4 : 2;
-}
-
-static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int ring_bytes,
+static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& w2, int n_mpairs, int n_pairs, int ring_bytes,
                             std::vector<void*>* allocs, cudaStream_t s, const Tc2Schedule** out) {
+  (void)st;
   for (auto& kv : w2.by_mpairs)
     if (kv.first == n_mpairs) { *out = &kv.second; return 0; }
-  const int cs = tc2_cluster_size(st, n_mpairs);
-  const int n_groups = cs == 4 ? (n_mpairs + 1) / 2 : n_mpairs;
-  const int n_pairs = cs == 4 ? st.quad_capacity : st.num_sms / 2;
   Tc2Plan plan;
   int rc;
-  if ((rc = tc2_plan(w1.N, w1.K, w2.tab, w2.h_grid, w2.w_grid, w2.max_acc, n_groups, n_pairs, ring_bytes, &plan))) return rc;
+  if ((rc = tc2_plan(w1.N, w1.K, w2.tab, w2.h_grid, w2.w_grid, w2.max_acc, n_mpairs, n_pairs, ring_bytes, &plan))) return rc;
   Tc2Schedule sc;
-  sc.cs = cs;
   sc.wh = plan.shape[0]; sc.ww = plan.shape[1]; sc.sy = plan.shape[2]; sc.sx = plan.shape[3];
   sc.n_windows = (int)plan.hdrs.size(); sc.n_pairs = n_pairs; sc.n_slots = plan.n_slots;
   if ((rc = tc_upload(allocs, plan.hdrs.data(), plan.hdrs.size() * sizeof(TcItem2), (void**)&sc.items, s))) return rc;
@@ -1047,25 +1012,8 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
 
 template <int NT, int EP, typename TOUT>
 static cudaError_t tc2_optin() {
-  cudaError_t e = cudaFuncSetAttribute(tc_bsgemm2_kernel<NT, EP, TOUT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tc_bsgemm2_kernel<NT, EP, TOUT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(tc_bsgemm2_kernel<NT, EP, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES);
-}
-
-// Clusters of 4 CTAs (two pairs) that can be co-resident: a GPC whose SM count is not a multiple of 4 leaves SMs unused.
-static int tc2_quad_capacity(int num_sms) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(4 * (num_sms / 4))); cfg.blockDim = dim3(TC2_THREADS);
-  cfg.dynamicSmemBytes = Tc2Cfg<64, EPI_BIAS_RELU, 2>::SMEM_BYTES;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, tc_bsgemm2_kernel<64, EPI_BIAS_RELU, __half, 4>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
-  return n;
 }
 
 static int tc2_optin_all() {
@@ -1098,24 +1046,18 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
   const int n_mpairs = n_pad / (2 * kRowTile);
   const Tc2Schedule* schp = nullptr;
+  const int pairs_avail = st.num_sms / 2;
   const int ring_bytes = tc2_ring_bytes(w.N, epi, (int)sizeof(TOUT));
-  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, ring_bytes, st.allocs, s, &schp))) return rc;
+  if ((rc = tc2_get_schedule(st, w, w2m, n_mpairs, pairs_avail, ring_bytes, st.allocs, s, &schp))) return rc;
   const Tc2Schedule& w2s = *schp;
-  const int grid = w2s.cs * w2s.n_pairs;  // clusters without work find -1 in slot 0 and fall through
+  const int grid = 2 * w2s.n_pairs;       // pairs without work find -1 in slot 0 and fall through
   cudaError_t le = cudaSuccess;
-#define TC2_GO_CS(NT, EP, T, OUTP, BSTRIDE, CSV)                                                                         \
-  le = launch_pdl(tc_bsgemm2_kernel<NT, EP, T, CSV>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(T)>::SMEM_BYTES, s, \
-                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, OUTP, n_pad, bias, BSTRIDE, fa)
-#define TC2_GO(NT, EP)                                                                \
-  do {                                                                                \
-    if (w2s.cs == 4) TC2_GO_CS(NT, EP, TOUT, out, w.bias_pstride, 4);                 \
-    else TC2_GO_CS(NT, EP, TOUT, out, w.bias_pstride, 2);                             \
-  } while (0)
-#define TC2_GO_H(NT, EP)                                                              \
-  do {                                                                                \
-    if (w2s.cs == 4) TC2_GO_CS(NT, EP, __half, reinterpret_cast<__half*>(out), 0, 4); \
-    else TC2_GO_CS(NT, EP, __half, reinterpret_cast<__half*>(out), 0, 2);             \
-  } while (0)
+#define TC2_GO(NT, EP)                                                                                                 \
+  le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, fa)
+#define TC2_GO_H(NT, EP)                                                                                               \
+  le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
     if (w.N == 64) TC2_GO(64, EP);      \
@@ -1132,7 +1074,6 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
 #undef TC2_BY_N
 #undef TC2_GO
 #undef TC2_GO_H
-#undef TC2_GO_CS
   (*launches)++;
   cudaError_t e = (le != cudaSuccess) ? le : cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("tc_bsgemm2 launch: ") + cudaGetErrorString(e)); return DGAN_ERR_CUDA; }
