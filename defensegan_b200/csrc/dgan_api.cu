@@ -784,8 +784,32 @@ int dgan_destroy(dgan_handle h) {
   return DGAN_OK;
 }
 
+// fp16 path: plan and upload the schedules of every layer-direction for this many latent rows (cached in the handle).
+// Planning allocates and synchronises; it happens here - a caller needs the workspace size before its first
+// dgan_reconstruct of a batch size anyway - so that dgan_reconstruct itself only enqueues kernels.
+static int plan_all(dgan_ctx* c, int n_rows) {
+  if (c->desc.precision != DGAN_PREC_FP16) return 0;
+  const int n_pad = (int)align_up((size_t)std::max(n_rows, 1), 2 * kRowTile), n_mpairs = n_pad / (2 * kRowTile);
+  const int n_pairs = c->tc.num_sms / 2;
+  const Tc2Schedule* sc = nullptr;
+  int rc;
+  auto one = [&](const TcWeights& w1, const TcWeights2& w2, int epi, int out_bytes) {
+    return tc2_get_schedule(c->tc, w1, w2, n_mpairs, n_pairs, tc2_ring_bytes(w1.N, epi, out_bytes), c->tc.allocs, (cudaStream_t)0, &sc);
+  };
+  const int nl = (int)c->layers.size();
+  for (int l = 0; l < nl; ++l) {
+    const GemmLayer& L = c->layers[(size_t)l];
+    if ((rc = one(L.tc_f, L.tc2_f, L.relu ? EPI_BIAS_RELU : EPI_BIAS, 2))) return rc;
+    if (l == 0) { if ((rc = one(L.tc_b, L.tc2_b, EPI_NONE, 4))) return rc; }
+    else if ((rc = one(L.tc_b, L.tc2_b, c->layers[(size_t)l - 1].relu ? EPI_MASK : EPI_NONE, 2))) return rc;
+  }
+  if ((rc = one(c->tc_fin.f, c->tc2_fin_f, c->tc_fin.C_out == 1 ? EPI_FINAL_SIGMOID1 : EPI_FINAL_TANH3, 2))) return rc;
+  return one(c->tc_fin.b, c->tc2_fin_b, c->layers[(size_t)nl - 1].relu ? EPI_MASK : EPI_NONE, 2);
+}
+
 size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
   if (h == nullptr || batch <= 0 || rec_rr <= 0) return 0;
+  if (plan_all(h, batch * rec_rr) != 0) return 0;
   return carve(h, batch * rec_rr, nullptr).bytes;
 }
 
