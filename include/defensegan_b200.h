@@ -72,7 +72,8 @@ int dgan_create(dgan_handle* out, const dgan_desc* desc, const float* const* wei
 int dgan_destroy(dgan_handle h);
 
 /* Bytes of caller-owned scratch needed by dgan_reconstruct / dgan_forward / dgan_loss_grad
- * for `batch` images x `rec_rr` restarts. */
+ * for `batch` images x `rec_rr` restarts.  Also plans and uploads the launch schedules for that many latent rows
+ * (cached in the handle; this is where the one-time allocation and synchronisation of a batch size happen). */
 size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr);
 
 /* Hyper-parameters of one projection call: the attributes DefenseGANBase.reconstruct reads from the model object at
@@ -97,8 +98,8 @@ typedef struct dgan_rec_params {
  *             z0 ~ N(0, 1/latent) from the Philox stream (seed, z_row_offset) (gan.py:370-377)
  *   rec_dev   [batch, H, W, C] fp32: G(z_{L-1}) of the arg-min restart (gan.py:438-449)
  *   loss_dev  [batch] fp32 min per-image MSE, nullable;  idx_dev [batch] int32 chosen restart, nullable
- * The whole L-step loop runs on the device: the call enqueues a constant number of kernels on `stream`
- * (independent of rec_iters) and never synchronises the host. */
+ * The call enqueues the whole L-step loop on `stream` (8 kernels per L-step with DGAN_PREC_FP16) and never
+ * synchronises the host; it does not allocate either once dgan_workspace_bytes has been called for this batch x rec_rr. */
 int dgan_reconstruct(dgan_handle h, const dgan_rec_params* params, const float* x_dev,
                      const float* z0_dev, float* rec_dev, float* loss_dev, int32_t* idx_dev,
                      void* workspace, size_t workspace_bytes, void* stream);
