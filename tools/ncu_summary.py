@@ -9,7 +9,8 @@ KEYS = [
     ("launch__grid_size", "grid"),
     ("launch__registers_per_thread", "regs/thread"),
     ("sm__cycles_elapsed.max", "SM cycles"),
-    ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (realtime)"),
+    ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (realtime; reads low on .2CTA kernels)"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor-memory pipe active % (92 % on cuBLAS bf16 at peak: profiles/r2_tensor_pipe_calibration.md)"),
     ("sm__inst_executed_pipe_uniform.sum", "uniform-pipe inst (UTCHMMA/UTMALDG issue)"),
     ("dram__bytes_read.sum", "DRAM read"),
     ("dram__bytes_write.sum", "DRAM write"),
