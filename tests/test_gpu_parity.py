@@ -245,6 +245,26 @@ def test_shape_fuzz_ragged_sizes(gens):
             assert np.abs(loss.cpu().numpy() - ref["loss_min"]).max() <= max(t["loss"], 1e-5)
 
 
+def test_launch_count_and_no_allocation_in_steady_state(gens):
+    """What dgan_reconstruct enqueues: z0 initialiser + 4 forward kernels per L-step + 4 backward kernels (the last of them
+    applies the momentum update in its tail) per L-step but the last + loss sum + arg-min select; and once a
+    batch size has been planned (dgan_workspace_bytes, first call) a call neither allocates nor frees device memory."""
+    for arch, per_step in (("mnist", 8), ("celeba", 10)):
+        w, gen = gens(arch, "fp16")
+        B, R = 3, 2
+        x = torch.tensor(O.synthetic_images(arch, w, B)).cuda()
+        z0 = torch.tensor(O.sample_z0(B * R, 128)).cuda()
+        for L in (1, 2, 7):
+            gen.reconstruct(x, R, L, 1.0, z_init_val=z0)
+            assert gen.last_launch_count == 1 + per_step // 2 + (L - 1) * per_step + 2, (arch, L, gen.last_launch_count)
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        for _ in range(3):
+            gen.reconstruct(x, R, 7, 1.0, z_init_val=z0)
+        torch.cuda.synchronize()
+        assert torch.cuda.mem_get_info()[0] == free0
+
+
 def test_sharded_api_single_rank_and_random_z0_statistics():
     """parallel.reconstruct_sharded degenerates to the single-GPU call without a process group; the Philox z0
     (models/gan.py:370-377: N(0, 1/latent_dim)) does not depend on how rows are tiled."""
