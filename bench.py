@@ -448,6 +448,7 @@ def _main(out):
     ms = timed(wl.step, args.steps, 0, dev, flush, distributed)
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = wl.gan._native.last_launch_count
+    enqueues_per_call = wl.gan._native.last_enqueue_count
     value = wl.B_global * args.steps / (ms / 1000.0)
 
     # ---- end-to-end through the public API with HOST buffers (`e2e`) ------------------------------------
@@ -512,6 +513,7 @@ def _main(out):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io},
             "gpu_launches": int(launches_per_step) * args.steps * world,
             "gpu_launches_per_call": int(launches_per_step),
+            "host_enqueues_per_call": int(enqueues_per_call),
             "clocks": clocks,
             "algorithmic": {"gflop_per_image": gflop_per_image, "tflops_whole_step": step_tflops,
                             "frac_of_sustained_bf16_peak": step_tflops / (world * peaks["bf16_tflops_sustained"]),

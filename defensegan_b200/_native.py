@@ -31,7 +31,7 @@ NVCC_FLAGS = [
 ABI_SYMBOLS = [
     "dgan_abi_version", "dgan_last_error", "dgan_num_weights", "dgan_create", "dgan_destroy",
     "dgan_workspace_bytes", "dgan_reconstruct", "dgan_sample_z0", "dgan_forward", "dgan_loss_grad",
-    "dgan_last_launch_count", "dgan_macs_per_row", "dgan_profile_enable", "dgan_profile_num_kinds",
+    "dgan_last_launch_count", "dgan_last_enqueue_count", "dgan_macs_per_row", "dgan_profile_enable", "dgan_profile_num_kinds",
     "dgan_profile_kind_name", "dgan_profile_read",
 ]
 
@@ -109,6 +109,8 @@ def load_library() -> ctypes.CDLL:
     lib.dgan_loss_grad.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.dgan_last_launch_count.restype = ctypes.c_int64
     lib.dgan_last_launch_count.argtypes = [vp]
+    lib.dgan_last_enqueue_count.restype = ctypes.c_int64
+    lib.dgan_last_enqueue_count.argtypes = [vp]
     lib.dgan_macs_per_row.restype = ctypes.c_int64
     lib.dgan_macs_per_row.argtypes = [vp]
     lib.dgan_profile_enable.restype = i32
@@ -212,6 +214,11 @@ class NativeGenerator:
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.dgan_last_launch_count(self._handle))
+
+    @property
+    def last_enqueue_count(self) -> int:
+        """Stream operations the host issued for the last reconstruct (the L-step loop is one CUDA-graph launch)."""
+        return int(self.lib.dgan_last_enqueue_count(self._handle))
 
     def profile_enable(self, on: bool) -> None:
         _check(self.lib, self.lib.dgan_profile_enable(self._handle, int(bool(on))), "dgan_profile_enable")

@@ -139,6 +139,15 @@ struct dgan_ctx {
   // adds two event records per launch, so it is never enabled in a timed benchmark pass
   bool profile = false;
   int n_rows_cur = 0;
+  // The L-step loop of a projection as a CUDA graph: captured once per (workspace, batch, R, L, lr, momentum, decay) on a
+  // private stream, replayed with one cudaGraphLaunch per call.
+  struct LoopGraph {
+    const void* ws; int batch, rec_rr, rec_iters, decay_lr; float rec_lr, momentum;
+    cudaGraphExec_t exec; int64_t kernels;
+  };
+  std::vector<LoopGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
+  int64_t last_enqueues = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<std::string> kind_names;
@@ -223,6 +232,7 @@ struct Workspace {
   int n_loss_parts = 0, n_g_parts = 1;
   size_t loss_stride_n = 1, loss_stride_b = 1;   // loss_part index = n * stride_n + part * stride_b
   float *y = nullptr, *dpre = nullptr, *loss_part = nullptr, *loss = nullptr;
+  float* x = nullptr;                  // [batch][H*W*C] copy of the call's images (the captured loop reads them from here)
   size_t bytes = 0;
 };
 
@@ -269,6 +279,7 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
       }
     }
   }
+  w.x = (float*)take(np * c->hwc * 4);     // batch <= n_pad
   w.y = (float*)take(np * c->hwc * 4);
   w.dpre = (float*)take(np * c->hwc * 4);
   w.loss_part = (float*)take(np * w.n_loss_parts * 4);
@@ -743,6 +754,7 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
     c->kind_names.push_back(fn + ".bwd"); c->kind_macs_per_row.push_back(fmacs);
     c->kind_names.push_back("momentum"); c->kind_macs_per_row.push_back(0.0);
   }
+  DGAN_CUDA_CHECK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
   DGAN_CUDA_CHECK(cudaGetLastError());
   return DGAN_OK;
 }
@@ -779,6 +791,8 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
 int dgan_destroy(dgan_handle h) {
   if (h == nullptr) return DGAN_OK;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return DGAN_OK;
@@ -814,6 +828,7 @@ size_t dgan_workspace_bytes(dgan_handle h, int batch, int rec_rr) {
 }
 
 int64_t dgan_last_launch_count(dgan_handle h) { return h ? h->last_launches : 0; }
+int64_t dgan_last_enqueue_count(dgan_handle h) { return h ? h->last_enqueues : 0; }
 int64_t dgan_macs_per_row(dgan_handle h) { return h ? h->macs_per_row : 0; }
 
 int dgan_forward(dgan_handle h, const float* z_dev, int n_rows, float* y_dev, void* ws, size_t ws_bytes, void* stream) {
@@ -881,31 +896,75 @@ int dgan_reconstruct(dgan_handle h, const dgan_rec_params* prm, const float* x_d
   int rc;
   if ((rc = build_maps(h, w))) return rc;
   const int64_t launches0 = h->launches;
+  int64_t enqueues = 0;
   h->n_rows_cur = batch * rec_rr;
   if ((rc = run_init_z(h, w, z0_dev, seed, s, (size_t)prm->z_row_offset))) return rc;
-  const int decay_iter = (int)std::ceil(rec_iters * 0.8);
-  // fp16: the momentum update (tf.train.MomentumOptimizer, models/gan.py:389-391) runs in the tail of the split-K Linear
-  // backward - the CTA that completes a 128-row tile's partial sums applies it - so an L-step is 8 launches; bit-identical
-  // to the separate kernel the fp32 path uses (same arithmetic, parts summed in the same order)
-  const bool tail = h->desc.precision == DGAN_PREC_FP16;
-  for (int t = 0; t < rec_iters; ++t) {
-    const bool last = (t == rec_iters - 1);
-    float lr = rec_lr;
-    if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
-    // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
-    // the L-th update is never observed, so its backward pass is not run.
-    if ((rc = run_forward(h, w, x_dev, rec_rr, batch, !last, s, /*want_y=*/last))) return rc;
-    if (last) continue;
-    MomentumArgs mom;
-    mom.lr = lr; mom.mu = momentum; mom.tail = tail;
-    if ((rc = run_backward(h, w, s, mom))) return rc;
-    if (!tail) {
-      const size_t zcount = (size_t)w.n_pad * latent;
-      ProfScope ps(h, 2 * (int)h->layers.size() + 2, s);
-      DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, s, w.z, w.v,
-                                 (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
-      DGAN_LAUNCH_CHECK(h);
+  DGAN_CUDA_CHECK(cudaMemcpyAsync(w.x, x_dev, (size_t)batch * h->hwc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  enqueues += (h->launches - launches0) + 1;
+  // The L-step loop (a function of the workspace and the hyper-parameters only): everything it reads or writes lives in
+  // the workspace, so it can be captured once and replayed.
+  auto enqueue_loop = [&](cudaStream_t ls) -> int {
+    const int decay_iter = (int)std::ceil(rec_iters * 0.8);
+    // fp16: the momentum update (tf.train.MomentumOptimizer, models/gan.py:389-391) runs in the tail of the split-K Linear
+    // backward - the CTA that completes a 128-row tile's partial sums applies it - so an L-step is 8 launches; bit-identical
+    // to the separate kernel the fp32 path uses (same arithmetic, parts summed in the same order)
+    const bool tail = h->desc.precision == DGAN_PREC_FP16;
+    for (int t = 0; t < rec_iters; ++t) {
+      const bool last = (t == rec_iters - 1);
+      float lr = rec_lr;
+      if (decay_lr) lr = rec_lr * std::pow(0.1f, (float)(t / decay_iter));
+      // The loop returns the pre-update forward of iteration L-1 (models/gan.py:419-421):
+      // the L-th update is never observed, so its backward pass is not run.
+      int r2;
+      if ((r2 = run_forward(h, w, w.x, rec_rr, batch, !last, ls, /*want_y=*/last))) return r2;
+      if (last) continue;
+      MomentumArgs mom;
+      mom.lr = lr; mom.mu = momentum; mom.tail = tail;
+      if ((r2 = run_backward(h, w, ls, mom))) return r2;
+      if (!tail) {
+        const size_t zcount = (size_t)w.n_pad * latent;
+        ProfScope ps(h, 2 * (int)h->layers.size() + 2, ls);
+        DGAN_CUDA_CHECK(launch_pdl(momentum_kernel, dim3((unsigned)((zcount + 255) / 256)), dim3(256), 0, ls, w.z, w.v,
+                                   (const float*)w.g, w.n_g_parts, grad_multiplier(h), lr, momentum, zcount, w.z_h));
+        DGAN_LAUNCH_CHECK(h);
+      }
     }
+    return 0;
+  };
+  bool replayed = false;
+  if (!h->profile && h->cap_stream != nullptr) {      // per-kernel event timing needs the plain launches
+    dgan_ctx::LoopGraph* g = nullptr;
+    for (auto& e : h->graphs)
+      if (e.ws == ws && e.batch == batch && e.rec_rr == rec_rr && e.rec_iters == rec_iters && e.decay_lr == decay_lr &&
+          e.rec_lr == rec_lr && e.momentum == momentum) { g = &e; break; }
+    if (g == nullptr) {
+      const int64_t k0 = h->launches;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int crc = enqueue_loop(h->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+        cudaGraphExec_t exec = nullptr;
+        if (crc == 0 && ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+          h->graphs.push_back({ws, batch, rec_rr, rec_iters, decay_lr, rec_lr, momentum, exec, h->launches - k0});
+          g = &h->graphs.back();
+        }
+        if (graph) cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();                     // a failed capture falls back to plain launches below
+      h->launches = k0;                       // captured nodes are counted when they run
+    }
+    if (g != nullptr) {
+      DGAN_CUDA_CHECK(cudaGraphLaunch(g->exec, s));
+      h->launches += g->kernels;
+      enqueues += 1;
+      replayed = true;
+    }
+  }
+  if (!replayed) {
+    const int64_t k0 = h->launches;
+    if ((rc = enqueue_loop(s))) return rc;
+    enqueues += h->launches - k0;
   }
   {
     const int n_rows = batch * rec_rr;
@@ -913,7 +972,9 @@ int dgan_reconstruct(dgan_handle h, const dgan_rec_params* prm, const float* x_d
     DGAN_LAUNCH_CHECK(h);
     select_kernel<<<batch, 256, 0, s>>>(w.loss, w.y, rec_rr, h->hwc, rec_dev, loss_dev, idx_dev);
     DGAN_LAUNCH_CHECK(h);
+    enqueues += 2;
   }
+  h->last_enqueues = enqueues;
   h->last_launches = h->launches - launches0;
   return DGAN_OK;
 }

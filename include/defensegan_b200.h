@@ -120,8 +120,13 @@ int dgan_loss_grad(dgan_handle h, const float* x_dev, int batch, int rec_rr, con
                    float* y_dev, float* loss_dev, float* grad_dev, void* workspace,
                    size_t workspace_bytes, void* stream);
 
-/* Kernel launches enqueued by the most recent dgan_reconstruct on this handle. */
+/* Kernels run by the most recent dgan_reconstruct on this handle (1 + 8 L - 4 + 2 with DGAN_PREC_FP16 on the MNIST stack). */
 int64_t dgan_last_launch_count(dgan_handle h);
+
+/* Stream operations the HOST issued for it.  The L-step loop only touches the workspace, so it is captured into a CUDA
+ * graph the first time a (workspace, batch, rec_rr, rec_iters, rec_lr, momentum, decay_lr) combination is seen and replayed
+ * with one cudaGraphLaunch afterwards: z0 initialiser (+ its memsets), image copy, graph, loss sum, arg-min select. */
+int64_t dgan_last_enqueue_count(dgan_handle h);
 
 /* Algorithmic multiply-accumulates of one generator forward per latent row (exact in-bounds
  * taps); backward-to-z has the same count. */

@@ -259,8 +259,12 @@ def test_launch_count_and_no_allocation_in_steady_state(gens):
             assert gen.last_launch_count == 1 + per_step // 2 + (L - 1) * per_step + 2, (arch, L, gen.last_launch_count)
         torch.cuda.synchronize()
         free0 = torch.cuda.mem_get_info()[0]
+        want = gen.reconstruct(x, R, 7, 1.0, z_init_val=z0).clone()
         for _ in range(3):
-            gen.reconstruct(x, R, 7, 1.0, z_init_val=z0)
+            got = gen.reconstruct(x, R, 7, 1.0, z_init_val=z0)
+            # the L-step loop is replayed as one CUDA graph: z0 init (+ memsets), image copy, graph, loss sum, select
+            assert gen.last_enqueue_count <= 10 and gen.last_launch_count == 1 + per_step // 2 + 6 * per_step + 2
+            assert torch.equal(got, want)
         torch.cuda.synchronize()
         assert torch.cuda.mem_get_info()[0] == free0
 
