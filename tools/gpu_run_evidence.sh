@@ -1,5 +1,5 @@
 #!/bin/bash
-# final evidence run of round 2: launch list of the bench command, ncu --set full of one L-step, bench lines, GPU tests
+# evidence run (what profiles/r2_* were produced with): launch list of the bench command, ncu --set full of one L-step, bench lines, GPU tests
 set -u
 mkdir -p gpurun_out
 T=${1:-r2n}
