@@ -519,6 +519,11 @@ def _main(out):
                             "frac_of_sustained_bf16_peak": step_tflops / (world * peaks["bf16_tflops_sustained"]),
                             "frac_of_burst_bf16_peak": step_tflops / (world * peaks["bf16_tflops"])},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+            "kernel_timing": None if not kernels else {
+                "sum_of_kernel_us_per_call": round(sum(k["avg_us"] * k["launches"] for k in kernels), 1),
+                "live_us_per_call": round(1e3 * ms / args.steps, 1),
+                "note": "per-kernel times are CUDA events around each plain launch (graph replay off, no PDL overlap of "
+                        "neighbouring kernels), so their sum exceeds the live call; shares, not sums, carry over"},
             "extra_configs": extra, "weak_scaling_base": weak_base, "reference_batch_size": small_batch,
         }
         out.emit(json.dumps(line))
