@@ -269,6 +269,25 @@ def test_launch_count_and_no_allocation_in_steady_state(gens):
         assert torch.cuda.mem_get_info()[0] == free0
 
 
+def test_graph_cache_survives_many_configurations(gens):
+    """The captured L-step loops are cached per (workspace, batch, R, L, lr, momentum, decay) with a small bound: cycling
+    through more configurations than the cache holds keeps giving the results of a cold handle's first call."""
+    w, gen = gens("mnist", "fp16")
+    x = torch.tensor(O.synthetic_images("mnist", w, 4)).cuda()
+    z0 = torch.tensor(O.sample_z0(4 * 2, 128)).cuda()
+    first = {}
+    for sweep in range(2):
+        for L in range(1, 12):                                   # 11 loop lengths > 8 cached graphs
+            for lr in (1.0, 2.0) if L == 3 else (1.0,):
+                rec = gen.reconstruct(x, 2, L, lr, z_init_val=z0).clone()
+                if sweep == 0:
+                    first[(L, lr)] = rec
+                else:
+                    assert torch.equal(rec, first[(L, lr)]), (L, lr)
+    ref = O.reconstruct("mnist", w, x.cpu().numpy(), 2, 11, rec_lr=1.0, z_init_val=z0.cpu().numpy())
+    assert np.abs(first[(11, 1.0)].cpu().numpy() - ref["rec"]).max() <= TOL["fp16"]["rec"]
+
+
 def test_sharded_api_single_rank_and_random_z0_statistics():
     """parallel.reconstruct_sharded degenerates to the single-GPU call without a process group; the Philox z0
     (models/gan.py:370-377: N(0, 1/latent_dim)) does not depend on how rows are tiled."""
