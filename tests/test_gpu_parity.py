@@ -257,9 +257,10 @@ def test_launch_count_and_no_allocation_in_steady_state(gens):
         for L in (1, 2, 7):
             gen.reconstruct(x, R, L, 1.0, z_init_val=z0)
             assert gen.last_launch_count == 1 + per_step // 2 + (L - 1) * per_step + 2, (arch, L, gen.last_launch_count)
+        want = gen.reconstruct(x, R, 7, 1.0, z_init_val=z0).clone()
+        assert torch.equal(gen.reconstruct(x, R, 7, 1.0, z_init_val=z0), want)      # (also warms torch's own allocator)
         torch.cuda.synchronize()
         free0 = torch.cuda.mem_get_info()[0]
-        want = gen.reconstruct(x, R, 7, 1.0, z_init_val=z0).clone()
         for _ in range(3):
             got = gen.reconstruct(x, R, 7, 1.0, z_init_val=z0)
             # the L-step loop is replayed as one CUDA graph: z0 init (+ memsets), image copy, graph, loss sum, select
