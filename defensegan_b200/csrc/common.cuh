@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <numeric>
 
 #include "../../include/defensegan_b200.h"
 

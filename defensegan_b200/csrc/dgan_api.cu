@@ -374,21 +374,21 @@ static int build_maps(dgan_ctx* c, Workspace& w) {
   w.map_in.assign((size_t)2 * nl + 2, CUtensorMap{});
   w.map_out.assign((size_t)2 * nl + 2, CUtensorMap{});
   int rc;
-  auto mk = [&](CUtensorMap* m, const void* base, int K, int P) {
-    return tc_make_map(c->tc, m, base, (uint64_t)K, (uint64_t)w.n_pad, (uint64_t)P, 128);
+  auto mk = [&](CUtensorMap* m, const void* base, int K, int P, uint32_t box_rows = 128) {
+    return tc_make_map(c->tc, m, base, (uint64_t)K, (uint64_t)w.n_pad, (uint64_t)P, box_rows);
   };
   for (int l = 0; l < nl; ++l) {
     const GemmLayer& L = c->layers[l];
     const void* fin = (l == 0) ? (const void*)w.z_h : (const void*)w.act_h[l - 1];
     if ((rc = mk(&w.map_in[2 * l], fin, L.C_in, L.P_in))) return rc;
-    if ((rc = mk(&w.map_out[2 * l], w.act_h[l], L.C_out, L.P_out))) return rc;
+    if ((rc = mk(&w.map_out[2 * l], w.act_h[l], L.C_out, L.P_out, TC2_STORE_ROWS))) return rc;
     if ((rc = mk(&w.map_in[2 * l + 1], w.dact_h[l], L.C_out, L.P_out))) return rc;
-    if (l >= 1 && (rc = mk(&w.map_out[2 * l + 1], w.dact_h[l - 1], L.C_in, L.P_in))) return rc;
+    if (l >= 1 && (rc = mk(&w.map_out[2 * l + 1], w.dact_h[l - 1], L.C_in, L.P_in, TC2_STORE_ROWS))) return rc;
   }
   const GemmLayer& last = c->layers[nl - 1];
   if ((rc = mk(&w.map_in[2 * nl], w.act_h[nl - 1], c->fin.C_in, last.P_out))) return rc;
   if ((rc = mk(&w.map_in[2 * nl + 1], w.dblk, 64, c->tc_fin.n_blocks))) return rc;
-  if ((rc = mk(&w.map_out[2 * nl + 1], w.dact_h[nl - 1], last.C_out, last.P_out))) return rc;
+  if ((rc = mk(&w.map_out[2 * nl + 1], w.dact_h[nl - 1], last.C_out, last.P_out, TC2_STORE_ROWS))) return rc;
   w.have_maps = true;
   return 0;
 }
@@ -588,6 +588,37 @@ static float grad_multiplier(const dgan_ctx* c) {
 // =========================================================================================
 // C ABI
 // =========================================================================================
+namespace {
+struct PlanDir { std::string name; int N, K; dgan::PairTable tab; int h, w, force_acc, epi, out_bytes; };
+// every tensor-core layer-direction of the fp16 path, as create_impl sets it up (host only)
+std::vector<PlanDir> plan_dirs(const dgan_desc* d) {
+  using namespace dgan;
+  typedef PlanDir Dir;
+  const bool celeba = d->arch == DGAN_ARCH_CELEBA;
+  const int nd = d->net_dim, latent = d->latent_dim;
+  std::vector<Dir> dirs;
+  dirs.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2});
+  dirs.push_back({"Linear.bwd", latent, 4 * nd, linear_split_pairs(16), 1, TC_LINEAR_SPLIT, 1, EPI_NONE, 4});
+  struct DSpec { int c_in, c_out, h_in, h_used, in_raster; bool relu; };
+  std::vector<DSpec> specs;
+  if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, 4, true}, {2 * nd, nd, 8, 16, 8, true}, {nd, nd, 16, 32, 16, false}};
+  else specs = {{4 * nd, 2 * nd, 4, 7, 4, true}, {2 * nd, nd, 7, 14, 7, true}};
+  int li = 2;
+  for (const DSpec& sp : specs) {
+    const std::string nm = "Generator." + std::to_string(li == 4 ? 5 : li);
+    dirs.push_back({nm + ".fwd", sp.c_out, sp.c_in, deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.h_used, sp.h_used, 0,
+                    sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2});
+    dirs.push_back({nm + ".bwd", sp.c_in, sp.c_out, deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.in_raster, sp.in_raster, 0,
+                    EPI_MASK, 2});
+    ++li;
+  }
+  const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
+  dirs.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2});
+  dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, celeba ? EPI_NONE : EPI_MASK, 2});
+  return dirs;
+}
+}  // namespace
+
 extern "C" {
 
 int dgan_abi_version(void) { return DGAN_ABI_VERSION; }
@@ -1012,36 +1043,15 @@ int dgan_profile_read(dgan_handle h, int max_kinds, double* ms_out, int64_t* lau
   return DGAN_OK;
 }
 
-/* developer aid (not in the public header): copy the DGAN_TC_DEBUG role-timing counters to the host */
 // Host-only developer/test aid (not in the public header): plan every tensor-core layer-direction of the fp16 path for
 // `n_rows` latent rows on `n_pairs` CTA pairs exactly as dgan_create/dgan_reconstruct would, and validate each plan
 // with tc2_check_plan.  Needs no GPU.  Returns 0, or an error code with the failing direction in dgan_last_error().
 int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int mutate) {
   using namespace dgan;
   if (d == nullptr || n_rows <= 0 || n_pairs <= 0) { set_error("invalid argument"); return DGAN_ERR_INVALID_ARG; }
-  const bool celeba = d->arch == DGAN_ARCH_CELEBA;
-  const int nd = d->net_dim, latent = d->latent_dim;
   const int n_pad = ((n_rows + 2 * kRowTile - 1) / (2 * kRowTile)) * 2 * kRowTile, n_mpairs = n_pad / (2 * kRowTile);
-  struct Dir { std::string name; int N, K; PairTable tab; int h, w, force_acc, epi, out_bytes; };
-  std::vector<Dir> dirs;
-  dirs.push_back({"Linear.fwd", 4 * nd, latent, linear_fwd_pairs(16), 4, 4, 0, EPI_BIAS_RELU, 2});
-  dirs.push_back({"Linear.bwd", latent, 4 * nd, linear_split_pairs(16), 1, TC_LINEAR_SPLIT, 1, EPI_NONE, 4});
-  struct DSpec { int c_in, c_out, h_in, h_used, in_raster; bool relu; };
-  std::vector<DSpec> specs;
-  if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, 4, true}, {2 * nd, nd, 8, 16, 8, true}, {nd, nd, 16, 32, 16, false}};
-  else specs = {{4 * nd, 2 * nd, 4, 7, 4, true}, {2 * nd, nd, 7, 14, 7, true}};
-  int li = 2;
-  for (const DSpec& sp : specs) {
-    const std::string nm = "Generator." + std::to_string(li == 4 ? 5 : li);
-    dirs.push_back({nm + ".fwd", sp.c_out, sp.c_in, deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.h_used, sp.h_used, 0,
-                    sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2});
-    dirs.push_back({nm + ".bwd", sp.c_in, sp.c_out, deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.in_raster, sp.in_raster, 0,
-                    EPI_MASK, 2});
-    ++li;
-  }
-  const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
-  dirs.push_back({"last.fwd", 16 * c_img, nd, final_block_fwd_pairs(fh, fh), fh / 2, fh / 2, 0, celeba ? EPI_FINAL_TANH3 : EPI_FINAL_SIGMOID1, 2});
-  dirs.push_back({"last.bwd", nd, 64, final_block_bwd_pairs(fh, fh), fh, fh, 0, celeba ? EPI_NONE : EPI_MASK, 2});
+  typedef PlanDir Dir;
+  const std::vector<Dir> dirs = plan_dirs(d);
   for (const Dir& dr : dirs) {
     if (dr.N != 16 && dr.N != 48 && dr.N != 64 && dr.N != 128 && dr.N != 256) { set_error(dr.name + ": unsupported N"); return DGAN_ERR_UNSUPPORTED; }
     int max_acc = tc2_maxb(dr.N);
@@ -1075,6 +1085,39 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
     if ((rc = tc2_check_plan(dr.N, dr.K, dr.tab, n_mpairs, ring, plan, &err))) { set_error(dr.name + ": " + err); return rc; }
   }
   return 0;
+}
+
+
+// Host-only developer aid (not in the public header): the plan of every layer-direction in numbers - window shape, items,
+// steps, MMAs, operand bytes staged from L2 into shared memory (both CTAs of every pair) - as text.  Returns the length.
+int dgan_debug_plan_stats(const dgan_desc* d, int n_rows, int n_pairs, char* buf, int buf_len) {
+  using namespace dgan;
+  if (d == nullptr || n_rows <= 0 || n_pairs <= 0 || buf == nullptr || buf_len <= 0) { set_error("invalid argument"); return -1; }
+  const int n_pad = ((n_rows + 2 * kRowTile - 1) / (2 * kRowTile)) * 2 * kRowTile, n_mpairs = n_pad / (2 * kRowTile);
+  std::string out = "direction | N | K | window (h x w, stride) | items | slots | steps | MMAs | staged MB | busiest pair / mean load\n";
+  double total = 0.0;
+  for (const PlanDir& dr : plan_dirs(d)) {
+    int max_acc = tc2_maxb(dr.N);
+    if (dr.force_acc > 0) max_acc = std::min(max_acc, dr.force_acc);
+    Tc2Plan plan;
+    const int rc = tc2_plan(dr.N, dr.K, dr.tab, dr.h, dr.w, max_acc, n_mpairs, n_pairs,
+                            tc2_ring_bytes(dr.N, dr.epi, dr.out_bytes), &plan);
+    if (rc) return -1;
+    char line[256];
+    const double mb = 2.0 * (double)plan.n_bytes / 1e6;
+    total += mb;
+    snprintf(line, sizeof line, "%s | %d | %d | %dx%d, %dx%d | %zu | %d | %lld | %lld | %.1f | %.3f\n", dr.name.c_str(), dr.N, dr.K,
+             plan.shape[0], plan.shape[1], plan.shape[2], plan.shape[3], plan.hdrs.size() * (size_t)n_mpairs, plan.n_slots,
+             plan.n_steps, plan.n_mma, mb, plan.load_max / std::max(plan.load_mean, 1.0));
+    out += line;
+  }
+  char line[64];
+  snprintf(line, sizeof line, "total staged MB per L-step | %.1f\n", total);
+  out += line;
+  const int n = (int)std::min(out.size(), (size_t)buf_len - 1);
+  memcpy(buf, out.data(), (size_t)n);
+  buf[n] = 0;
+  return n;
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ constexpr int TC2_TILE_BYTES = 128 * 128;    // one 128-row x 64-channel fp16 ti
 constexpr int TC2_BUF_COLS = 256;            // TMEM columns per accumulator buffer (2 buffers: MMA i+1 overlaps epilogue i)
 constexpr int TC2_EPI_WARPS = 8;             // two epilogue warps per TMEM lane quarter
 constexpr int TC2_THREADS = 64 + 32 * TC2_EPI_WARPS;
+constexpr int TC2_STORE_ROWS = 32;           // rows per output TMA store: each epilogue warp stores the 32 rows it holds
 
 struct __align__(16) TcItem2 {
   uint16_t q[16];
@@ -73,9 +74,15 @@ constexpr int TC2_STAGING_BYTES = 2 * TC2_REC_BATCH * (int)sizeof(TcRec);   // p
 __host__ __device__ constexpr int tc2_epi_tiles(int n_tile, int epi, int out_bytes) {
   return tc2_tma_epilogue(n_tile, epi, out_bytes) ? 2 : 0;
 }
+// The item's bias row staged in shared memory by the TMA-store epilogues: N_TILE floats; a per-pixel bias (the Linear:
+// N_TILE = 256, one accumulator per item) changes from item to item and is double-buffered by item parity.
+// (Sized per instantiation: the operand ring of the N = 64 / 128 layers must stay at 192 KB = 4 steps of 48 KB.)
+__host__ __device__ constexpr int tc2_bias_bytes(int n_tile, int epi, int out_bytes) {
+  return (tc2_tma_epilogue(n_tile, epi, out_bytes) && (epi == EPI_BIAS_RELU || epi == EPI_BIAS)) ? (n_tile == 256 ? 2048 : n_tile * 4) : 0;
+}
 __host__ __device__ constexpr int tc2_ring_bytes(int n_tile, int epi, int out_bytes) {
   const int epi_b = tc2_epi_tiles(n_tile, epi, out_bytes) * TC2_TILE_BYTES;
-  const int raw = ((TC2_SMEM_MAX - 1024 - 256 - TC2_STAGING_BYTES - epi_b) / 1024) * 1024;
+  const int raw = ((TC2_SMEM_MAX - 1024 - 256 - tc2_bias_bytes(n_tile, epi, out_bytes) - TC2_STAGING_BYTES - epi_b) / 1024) * 1024;
   return raw > 255 * 1024 ? 255 * 1024 : raw;
 }
 
@@ -88,7 +95,7 @@ struct Tc2Cfg {
   static constexpr int EPI_TILES = tc2_epi_tiles(N_TILE, EPI, OUT_BYTES);   // output staging tiles (0 or 2)
   static constexpr int EPI_BYTES = EPI_TILES * TC2_TILE_BYTES;
   static constexpr int RING_BYTES = tc2_ring_bytes(N_TILE, EPI, OUT_BYTES);          // operand ring (offsets are 8-bit KB)
-  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + TC2_STAGING_BYTES + 1024 + 256 + tc2_bias_bytes(N_TILE, EPI, OUT_BYTES);
 };
 
 namespace ptx {
@@ -236,12 +243,23 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   uint32_t rbeg = 0, rend = 0;
   uint4 mine = make_uint4(0, 0, 0, 0);
   int item_first = -1;
+  constexpr bool HAS_BIAS = TMA_EPI && (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS);
+  const int et = (warp - 2) * 32 + lane;              // 0..255 over the epilogue threads
+  uint32_t q_next = 0, nacc_next = 0;                 // epilogue: output pixel of accumulator `lane` (lanes 0..15), accumulator count
+  float bias_next = 0.f;                              // epilogue: element `et` of the next item's bias row
   const TcRec* __restrict__ stream = warp == 1 ? stream_m : (rank ? stream_p1 : stream_p0);
   if (warp <= 1) {
     rbeg = __ldg(stream_off + pair); rend = __ldg(stream_off + pair + 1);
     if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);   // lane = 16-byte half
   } else {
     item_first = tc2_item_at(eitems, 0, pair, n_pairs, n_slots);
+    if (item_first >= 0) {           // header of the first item (see the epilogue): tables and bias are constants too
+      const TcItem2* ip0 = items + (item_first >> 16);
+      if (lane < 16) q_next = (uint32_t)__ldg(&ip0->q[lane]);
+      nacc_next = __ldg(&ip0->n_acc);
+      if (HAS_BIAS && et < N_TILE)
+        bias_next = __ldg(bias + (size_t)__shfl_sync(0xffffffffu, q_next, 0) * bias_pstride + et);
+    }
   }
   // everything above overlapped the previous kernel's tail (PDL); from here on we read what it wrote
   pdl_launch_dependents();
@@ -355,22 +373,49 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // ===================== epilogue (warps 2..9, both CTAs) =====================
     // Two warps per TMEM lane quarter split the (accumulator, 32-column chunk) units of an item;
     // the TMEM load of a warp's next unit is in flight while it converts and stores the current one.
+    // Nothing on the per-unit path depends on a global load issued in the same unit (ncu source counters of the
+    // round-2 build: a third of the epilogue's time went to the chain item header -> output pixel -> bias / mask word):
+    // the window's output pixels live in lanes 0..15 (one shuffle per use), fetched one item ahead; the item's bias row
+    // is staged in shared memory before the accumulators are awaited; mask words are fetched two units ahead.
     const int lq = warp & 3;                          // TMEM lanes this warp may access
     const int half = (warp - 2) >> 2;                 // 0 | 1: which of the two warps of this quarter
     const int row = lq * 32 + lane;
+    const uint32_t bias_s = bar_base + 256;           // [2][256] floats
     uint32_t item_count = 0;
     for (int kk = 0, item_e = item_first, item_next; item_e >= 0; ++kk, ++item_count, item_e = item_next) {
       item_next = tc2_item_at(eitems, kk + 1, pair, n_pairs, n_slots);      // (window << 16 | row pair), one item ahead
-      const int win = item_e >> 16, mp = item_e & 0xFFFF;
-      const TcItem2* ip = items + win;
-      const int n_acc = (int)ip->n_acc;
+      const int mp = item_e & 0xFFFF;
+      const uint32_t q_mine = q_next;
+      const int n_acc = (int)nacc_next;
+      auto q_of = [&](int a) { return (int)__shfl_sync(0xffffffffu, q_mine, a); };
+      if (HAS_BIAS && (item_count == 0 || bias_pstride != 0)) {
+        // a per-pixel bias (Linear) comes with one accumulator per item (N_TILE = 256): the row of q[0] serves the item
+        if (et < N_TILE) ptx::st_shared_u32(bias_s + (item_count & 1u) * 1024u + (uint32_t)et * 4u, __float_as_uint(bias_next));
+        ptx::named_bar_sync(4, 32 * TC2_EPI_WARPS);   // also: every warp is done with the row of item_count - 2
+      }
+      if (item_next >= 0) {                            // next item's header, in flight during this item
+        const TcItem2* ipn = items + (item_next >> 16);
+        if (lane < 16) q_next = (uint32_t)__ldg(&ipn->q[lane]);
+        nacc_next = __ldg(&ipn->n_acc);
+        if (HAS_BIAS && bias_pstride != 0 && et < N_TILE)
+          bias_next = __ldg(bias + (size_t)__shfl_sync(0xffffffffu, q_next, 0) * bias_pstride + et);
+      }
       const size_t n = (size_t)(2 * mp + (int)rank) * kRowTile + row;
       const uint32_t buf = item_count & 1;
       const uint32_t tbuf = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * TC2_BUF_COLS;
       constexpr bool FINAL = (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3);
       float4 xq_next[FINAL ? (EPI == EPI_FINAL_SIGMOID1 ? 4 : 12) : 1];
       if (FINAL && half < n_acc)     // first block's target pixels: in flight while the MMAs finish
-        tc_final_targets<(EPI == EPI_FINAL_SIGMOID1 ? 1 : 3)>(reinterpret_cast<float4(&)[EPI == EPI_FINAL_SIGMOID1 ? 4 : 12]>(xq_next), fa, ip->q[half], (int)n);
+        tc_final_targets<(EPI == EPI_FINAL_SIGMOID1 ? 1 : 3)>(reinterpret_cast<float4(&)[EPI == EPI_FINAL_SIGMOID1 ? 4 : 12]>(xq_next), fa, q_of(half < n_acc ? half : 0), (int)n);
+      // EPI_MASK: mask words are fetched two units ahead; the first two are in flight while the MMAs finish
+      unsigned long long mbits = ~0ull, mbits_next = ~0ull, mbits_next2 = ~0ull;
+      if (TMA_EPI && EPI == EPI_MASK) {
+        constexpr int G0 = N_TILE / 64;
+        const int nu = n_acc * G0, u1 = half + 2;
+        const int q0 = q_of(half < nu ? half / G0 : 0), q1 = q_of(u1 < nu ? u1 / G0 : 0);
+        if (half < nu) mbits_next = __ldg(fa.mb_in + ((size_t)q0 * n_pad + n) * G0 + half % G0);
+        if (u1 < nu) mbits_next2 = __ldg(fa.mb_in + ((size_t)q1 * n_pad + n) * G0 + u1 % G0);
+      }
       ptx::mbar_wait(bar_acc_full + 8 * buf, (item_count >> 1) & 1);
       ptx::tc_fence_after();
       if (EPI == EPI_FINAL_SIGMOID1 || EPI == EPI_FINAL_TANH3) {
@@ -379,46 +424,48 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         for (int a = half; a < n_acc; a += 2) {
 #pragma unroll
           for (int j = 0; j < 4 * CO; ++j) xq[j] = xq_next[j];
-          if (a + 2 < n_acc) tc_final_targets<CO>(reinterpret_cast<float4(&)[4 * CO]>(xq_next), fa, ip->q[a + 2], (int)n);   // next block's targets in flight
+          const int qa = q_of(a), qa2 = q_of(a + 2 < n_acc ? a + 2 : a);
+          if (a + 2 < n_acc) tc_final_targets<CO>(reinterpret_cast<float4(&)[4 * CO]>(xq_next), fa, qa2, (int)n);   // next block's targets in flight
           const uint32_t taddr = tbuf + (uint32_t)(a * ACC_STRIDE);
           if (EPI == EPI_FINAL_SIGMOID1)
-            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out),
+            tc_final_epilogue<1, ACT_SIGMOID>(taddr, fa, bias, qa, (int)n, n_pad, reinterpret_cast<__half*>(out),
                                               reinterpret_cast<const float4(&)[4]>(xq));
           else
-            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, ip->q[a], (int)n, n_pad, reinterpret_cast<__half*>(out),
+            tc_final_epilogue<3, ACT_TANH>(taddr, fa, bias, qa, (int)n, n_pad, reinterpret_cast<__half*>(out),
                                            reinterpret_cast<const float4(&)[12]>(xq));
         }
       } else if (TMA_EPI) {
-        // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 ->
-        //      128B-swizzled smem tile -> one TMA store per 128x64 tile.
+        // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 -> this warp's 32-row
+        //      slice of a 128B-swizzled tile -> one TMA store of 32 rows x 64 channels per warp.  The warps of a half
+        //      share nothing: no block-level barrier on the unit path, each warp waits for its own previous store.
         constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
         const int n_units = n_acc * G;
-        const bool t0 = (warp == 2 + 4 * half) && lane == 0;  // issues this half's bulk copies
-        const int row0 = (2 * mp + (int)rank) * kRowTile;
-        const uint32_t swz = (uint32_t)(row & 7);
+        const int row0 = (2 * mp + (int)rank) * kRowTile + lq * 32;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        const uint32_t s_out = epi_base + (uint32_t)half * TC2_TILE_BYTES + (uint32_t)lq * 4096u;
+        const uint32_t bias_row = bias_s + ((bias_pstride != 0) ? (item_count & 1u) * 1024u : 0u);
         uint32_t r0[32], r1[32];
-        unsigned long long mbits = ~0ull, mbits_next = ~0ull;
         if (half < n_units) {
           const int a = half / G, g = half % G;
-          if (EPI == EPI_MASK) mbits_next = __ldg(fa.mb_in + ((size_t)ip->q[a] * n_pad + n) * G + g);
           ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64), r0);
           ptx::tmem_ld32(tbuf + (uint32_t)(a * ACC_STRIDE + g * 64 + 32), r1);
         }
         for (int u = half; u < n_units; u += 2) {
-          const int a = u / G, g = u % G, q = ip->q[a];
-          mbits = mbits_next;
+          const int a = u / G, g = u % G, q = q_of(a);
+          mbits = mbits_next; mbits_next = mbits_next2;
           ptx::tmem_ld_wait();
           uint32_t pk[32];
+          unsigned long long bits = 0ull;
           {
             float v[64];
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
-            if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS) {
-              const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)q * bias_pstride + g * 64);
+            if (HAS_BIAS) {
 #pragma unroll
               for (int j4 = 0; j4 < 16; ++j4) {
-                const float4 b = __ldg(bp + j4);
-                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+                const uint4 b = ptx::ld_shared_v4(bias_row + (uint32_t)(g * 256 + j4 * 16));
+                v[j4 * 4 + 0] += __uint_as_float(b.x); v[j4 * 4 + 1] += __uint_as_float(b.y);
+                v[j4 * 4 + 2] += __uint_as_float(b.z); v[j4 * 4 + 3] += __uint_as_float(b.w);
               }
               if (EPI == EPI_BIAS_RELU) {
 #pragma unroll
@@ -426,10 +473,8 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               }
             }
             if (EPI == EPI_BIAS_RELU && fa.mb_out != nullptr) {
-              unsigned long long bits = 0ull;
 #pragma unroll
               for (int j = 0; j < 64; ++j) bits |= (unsigned long long)(v[j] > 0.f) << j;
-              fa.mb_out[((size_t)q * n_pad + n) * G + g] = bits;
             }
             if (EPI == EPI_MASK) {
 #pragma unroll
@@ -441,21 +486,25 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
           if (u + 2 < n_units) {                           // next unit's accumulator columns: in flight during the store phase
             const int a2 = (u + 2) / G, g2 = (u + 2) % G;
-            if (EPI == EPI_MASK) mbits_next = __ldg(fa.mb_in + ((size_t)ip->q[a2] * n_pad + n) * G + g2);
             ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64), r0);
             ptx::tmem_ld32(tbuf + (uint32_t)(a2 * ACC_STRIDE + g2 * 64 + 32), r1);
           }
-          const uint32_t s_out = epi_base + (uint32_t)half * TC2_TILE_BYTES;
-          if (t0) ptx::bulk_wait_read0();                  // the store that last read s_out is done
-          ptx::named_bar_sync(1 + half, 128);              // s_out free
+          if (lane == 0) ptx::bulk_wait_read0();           // this warp's previous store has read its slice
+          __syncwarp();
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            ptx::st_shared_v4(s_out + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+            ptx::st_shared_v4(s_out + (uint32_t)lane * 128u + (((uint32_t)c ^ swz) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
           ptx::fence_proxy_async_smem();
-          ptx::named_bar_sync(1 + half, 128);              // tile complete
-          if (t0) {
+          __syncwarp();
+          if (lane == 0) {
             ptx::tma_store_3d(&tm_out, s_out, g * 64, row0, q);
             ptx::bulk_commit();
+          }
+          // global traffic of this unit after the proxy fence (which waits for the thread's outstanding accesses)
+          if (EPI == EPI_BIAS_RELU && fa.mb_out != nullptr) fa.mb_out[((size_t)q * n_pad + n) * G + g] = bits;
+          if (EPI == EPI_MASK && u + 4 < n_units) {
+            const int a4 = (u + 4) / G, g4 = (u + 4) % G;
+            mbits_next2 = __ldg(fa.mb_in + ((size_t)q_of(a4) * n_pad + n) * G + g4);
           }
         }
       } else {
@@ -467,11 +516,11 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         for (; u < n_units; u += 4) {
           ptx::tmem_ld_wait();
           if (u + 2 < n_units) ptx::tmem_ld32(tbuf + (uint32_t)(((u + 2) / CH) * ACC_STRIDE + ((u + 2) % CH) * 32), rB);
-          tc_store_chunk<N_TILE, EPI, TOUT>(rA, ip->q[u / CH], (u % CH) * 32, n, n_pad, out, bias, bias_pstride);
+          tc_store_chunk<N_TILE, EPI, TOUT>(rA, q_of(u / CH), (u % CH) * 32, n, n_pad, out, bias, bias_pstride);
           if (u + 2 < n_units) {
             ptx::tmem_ld_wait();
             if (u + 4 < n_units) ptx::tmem_ld32(tbuf + (uint32_t)(((u + 4) / CH) * ACC_STRIDE + ((u + 4) % CH) * 32), rA);
-            tc_store_chunk<N_TILE, EPI, TOUT>(rB, ip->q[(u + 2) / CH], ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride);
+            tc_store_chunk<N_TILE, EPI, TOUT>(rB, q_of((u + 2) / CH), ((u + 2) % CH) * 32, n, n_pad, out, bias, bias_pstride);
           }
         }
       }
@@ -534,7 +583,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
       }
     }
-    if (TMA_EPI && lane == 0 && (warp == 2 || warp == 6)) ptx::bulk_wait_all0();   // stores landed before exit
+    if (TMA_EPI && lane == 0) ptx::bulk_wait_read0();   // shared memory no longer read; the writes complete with the grid
   }
 
   ptx::tc_fence_before();
@@ -755,6 +804,7 @@ struct Tc2Plan {               // host result of the planner (what tc2_get_sched
   std::vector<uint32_t> stream_off;
   std::vector<int> eitems;
   long long n_mma = 0, n_single = 0, n_steps = 0, n_bytes = 0;
+  double load_max = 0.0, load_mean = 0.0;   // cost-model load of the busiest CTA pair / the mean over pairs (balance of the LPT assignment)
 };
 
 static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, int max_acc, int n_mpairs, int n_pairs,
@@ -795,6 +845,8 @@ static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, 
           const double makespan = *std::max_element(load.begin(), load.end());
           if (makespan < best_cost) {
             best_cost = makespan;
+            plan->load_max = makespan;
+            plan->load_mean = std::accumulate(load.begin(), load.end(), 0.0) / (double)n_pairs;
             best_shape[0] = wh; best_shape[1] = ww; best_shape[2] = sy; best_shape[3] = sx;
             best_items.swap(items); best_lists.swap(lists);
           }
@@ -1041,9 +1093,10 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   CUtensorMap tm_out = tm_a;                     // placeholder when unused
   if (tc2_tma_epilogue(w.N, epi, (int)sizeof(TOUT))) {
     if (pre_out != nullptr) tm_out = *pre_out;
-    else if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, 128))) return rc;
+    else if ((rc = tc_make_map(st, &tm_out, out, (uint64_t)w.N, (uint64_t)n_pad, (uint64_t)w.P_out, TC2_STORE_ROWS))) return rc;
   }
   if (n_pad % (2 * kRowTile) != 0) { set_error("pair kernel needs n_pad % 256 == 0"); return DGAN_ERR_INVALID_ARG; }
+  if (w.bias_pstride != 0 && w.N != 256) { set_error("a per-pixel bias needs one accumulator per item (N = 256)"); return DGAN_ERR_UNSUPPORTED; }
   const int n_mpairs = n_pad / (2 * kRowTile);
   const Tc2Schedule* schp = nullptr;
   const int pairs_avail = st.num_sms / 2;
