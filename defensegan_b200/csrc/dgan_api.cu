@@ -1088,6 +1088,17 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
 }
 
 
+#ifdef DGAN_PROBE
+// Developer build only: copy (and clear) the per-CTA cycle counters of the tensor-core kernels.  out: [48][160][4] u64.
+int dgan_debug_probe_read(unsigned long long* out) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out, dgan::g_tc2_probe, sizeof(dgan::g_tc2_probe)) != cudaSuccess) return -1;
+  static unsigned long long zeros[48 * 160 * 4];
+  if (cudaMemcpyToSymbol(dgan::g_tc2_probe, zeros, sizeof(zeros)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
+
 // Host-only developer aid (not in the public header): the plan of every layer-direction in numbers - window shape, items,
 // steps, MMAs, operand bytes staged from L2 into shared memory (both CTAs of every pair) - as text.  Returns the length.
 int dgan_debug_plan_stats(const dgan_desc* d, int n_rows, int n_pairs, char* buf, int buf_len) {

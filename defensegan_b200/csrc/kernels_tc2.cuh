@@ -26,6 +26,16 @@ constexpr int TC2_EPI_WARPS = 8;             // two epilogue warps per TMEM lane
 constexpr int TC2_THREADS = 64 + 32 * TC2_EPI_WARPS;
 constexpr int TC2_STORE_ROWS = 32;           // rows per output TMA store: each epilogue warp stores the 32 rows it holds
 
+// Where each CTA pair's work starts, passed in the kernel's parameter space (constant bank): the first records and the
+// first item's header are then ONE global round trip away from the kernel's entry, and that round trip overlaps the
+// barrier set-up and the TMEM allocation (the prologue of the last CTAs to start sits on the critical path between two
+// kernels of the chain).
+constexpr int TC2_MAX_PAIRS = 80;
+struct Tc2Heads {
+  uint32_t off[TC2_MAX_PAIRS + 1];    // record offsets of the pairs' step streams
+  int first[TC2_MAX_PAIRS];           // first item (window << 16 | row pair) of each pair, -1 = none
+};
+
 struct __align__(16) TcItem2 {
   uint16_t q[16];
   uint32_t n_acc, step_beg, n_steps, pad;
@@ -106,6 +116,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Execution barrier of the pair without the GPU-scope fence of a releasing arrive (end of the kernel: nothing another CTA
+// reads depends on it - shared-memory and TMEM lifetimes are ordered by the mbarriers and tcgen05 fences).
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 // TMA load executed by either CTA of the pair into its OWN shared memory; the transaction bytes
 // are credited to the barrier of the even CTA (peer bit cleared).
@@ -190,12 +205,21 @@ __device__ __forceinline__ int tc2_item_at(const int* __restrict__ order, int k,
   return k < n_slots ? __ldg(order + (size_t)k * n_pairs + pair) : -1;
 }
 
+#ifdef DGAN_PROBE
+// Developer build only (-DDGAN_PROBE): per kernel instantiation and CTA, summed over launches: cycles from the PDL wait to
+// the end of the CTA's work, launches, cycles from kernel entry to the PDL wait, cycles the MMA warp waited for operands.
+__device__ unsigned long long g_tc2_probe[48][160][4];
+__host__ __device__ constexpr int tc2_probe_key(int n_tile, int epi, int out_bytes) {
+  return (n_tile == 256 ? 0 : n_tile == 128 ? 1 : n_tile == 64 ? 2 : n_tile == 48 ? 3 : 4) * 8 + (out_bytes == 4 ? 6 : (epi < 4 ? epi : epi - 4));
+}
+#endif
+
 template <int N_TILE, int EPI, typename TOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_out,
                   const TcItem2* __restrict__ items, const TcRec* __restrict__ stream_p0, const TcRec* __restrict__ stream_p1,
-                  const TcRec* __restrict__ stream_m, const uint32_t* __restrict__ stream_off,
+                  const TcRec* __restrict__ stream_m, const __grid_constant__ Tc2Heads heads,
                   const int* __restrict__ eitems, int n_slots,
                   TOUT* __restrict__ out, int n_pad, const float* __restrict__ bias, int bias_pstride, const TcFinalArgs fa) {
   using Cfg = Tc2Cfg<N_TILE, EPI, (int)sizeof(TOUT)>;
@@ -216,6 +240,28 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
+  // The schedule tables are constants: each role's first entries are requested before anything else, so that their
+  // latency overlaps the set-up below (and, for CTAs that start early, the previous kernel's tail).
+  uint32_t rbeg = 0, rend = 0;
+  uint4 mine = make_uint4(0, 0, 0, 0);
+  int item_first = -1;
+  constexpr bool HAS_BIAS = TMA_EPI && (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS);
+  const int et = (warp - 2) * 32 + lane;              // 0..255 over the epilogue threads
+  uint32_t q_next = 0, nacc_next = 0;                 // epilogue: output pixel of accumulator `lane` (lanes 0..15), accumulator count
+  float bias_next = 0.f;                              // epilogue: element `et` of the next item's bias row
+  const TcRec* __restrict__ stream = warp == 1 ? stream_m : (rank ? stream_p1 : stream_p0);
+  if (warp <= 1) {
+    rbeg = heads.off[pair]; rend = heads.off[pair + 1];
+    if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);   // lane = 16-byte half
+  } else {
+    item_first = heads.first[pair];
+    if (item_first >= 0) {           // header of the first item (see the epilogue): tables and bias are constants too
+      const TcItem2* ip0 = items + (item_first >> 16);
+      if (lane < 16) q_next = (uint32_t)__ldg(&ip0->q[lane]);
+      nacc_next = __ldg(&ip0->n_acc);
+      if (HAS_BIAS && bias_pstride == 0 && et < N_TILE) bias_next = __ldg(bias + et);
+    }
+  }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
@@ -238,32 +284,18 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   ptx::cluster_sync_all();                     // barriers of BOTH CTAs initialised before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  // The schedule tables are constants: fetch each role's first entries before the PDL wait so their latency
-  // overlaps the previous kernel's tail as well.
-  uint32_t rbeg = 0, rend = 0;
-  uint4 mine = make_uint4(0, 0, 0, 0);
-  int item_first = -1;
-  constexpr bool HAS_BIAS = TMA_EPI && (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS);
-  const int et = (warp - 2) * 32 + lane;              // 0..255 over the epilogue threads
-  uint32_t q_next = 0, nacc_next = 0;                 // epilogue: output pixel of accumulator `lane` (lanes 0..15), accumulator count
-  float bias_next = 0.f;                              // epilogue: element `et` of the next item's bias row
-  const TcRec* __restrict__ stream = warp == 1 ? stream_m : (rank ? stream_p1 : stream_p0);
-  if (warp <= 1) {
-    rbeg = __ldg(stream_off + pair); rend = __ldg(stream_off + pair + 1);
-    if (2 * rbeg + lane < 2 * rend) mine = __ldg(reinterpret_cast<const uint4*>(stream + rbeg) + lane);   // lane = 16-byte half
-  } else {
-    item_first = tc2_item_at(eitems, 0, pair, n_pairs, n_slots);
-    if (item_first >= 0) {           // header of the first item (see the epilogue): tables and bias are constants too
-      const TcItem2* ip0 = items + (item_first >> 16);
-      if (lane < 16) q_next = (uint32_t)__ldg(&ip0->q[lane]);
-      nacc_next = __ldg(&ip0->n_acc);
-      if (HAS_BIAS && et < N_TILE)
-        bias_next = __ldg(bias + (size_t)__shfl_sync(0xffffffffu, q_next, 0) * bias_pstride + et);
-    }
-  }
+  if (HAS_BIAS && warp >= 2 && bias_pstride != 0 && item_first >= 0 && et < N_TILE)   // per-pixel bias: row of the first item's pixel
+    bias_next = __ldg(bias + (size_t)__shfl_sync(0xffffffffu, q_next, 0) * bias_pstride + et);
   // everything above overlapped the previous kernel's tail (PDL); from here on we read what it wrote
+#ifdef DGAN_PROBE
+  const long long probe_t_entry = clock64();
+#endif
   pdl_launch_dependents();
   pdl_wait();
+#ifdef DGAN_PROBE
+  const long long probe_t_go = clock64();
+  long long probe_wait_full = 0;
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -336,7 +368,13 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             buf = item_count & 1;
             ptx::mbar_wait(bar_acc_empty + 8 * buf, ((item_count >> 1) & 1) ^ 1);
           }
+#ifdef DGAN_PROBE
+          const long long probe_w0 = clock64();
+#endif
           ptx::mbar_wait(bar_full + 8 * slot, phase);
+#ifdef DGAN_PROBE
+          probe_wait_full += clock64() - probe_w0;
+#endif
           ptx::tc_fence_after();
           // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
           const uint32_t a_lo0 = desc_lo0 + ((r0.x & 0xFFu) << 6);
@@ -410,7 +448,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       // EPI_MASK: mask words are fetched two units ahead; the first two are in flight while the MMAs finish
       unsigned long long mbits = ~0ull, mbits_next = ~0ull, mbits_next2 = ~0ull;
       if (TMA_EPI && EPI == EPI_MASK) {
-        constexpr int G0 = N_TILE / 64;
+        constexpr int G0 = N_TILE >= 64 ? N_TILE / 64 : 1;
         const int nu = n_acc * G0, u1 = half + 2;
         const int q0 = q_of(half < nu ? half / G0 : 0), q1 = q_of(u1 < nu ? u1 / G0 : 0);
         if (half < nu) mbits_next = __ldg(fa.mb_in + ((size_t)q0 * n_pad + n) * G0 + half % G0);
@@ -438,7 +476,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         // ---- 64-column units through shared memory: TMEM -> regs -> (bias|ReLU|mask) -> fp16 -> this warp's 32-row
         //      slice of a 128B-swizzled tile -> one TMA store of 32 rows x 64 channels per warp.  The warps of a half
         //      share nothing: no block-level barrier on the unit path, each warp waits for its own previous store.
-        constexpr int G = N_TILE / 64;                    // 64-column groups per accumulator
+        constexpr int G = N_TILE >= 64 ? N_TILE / 64 : 1;   // 64-column groups per accumulator
         const int n_units = n_acc * G;
         const int row0 = (2 * mp + (int)rank) * kRowTile + lq * 32;
         const uint32_t swz = (uint32_t)(lane & 7);
@@ -586,8 +624,20 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (TMA_EPI && lane == 0) ptx::bulk_wait_read0();   // shared memory no longer read; the writes complete with the grid
   }
 
+#ifdef DGAN_PROBE
+  {
+    constexpr int key = tc2_probe_key(N_TILE, EPI, (int)sizeof(TOUT));
+    if (warp == 1 && lane == 0) atomicAdd(&g_tc2_probe[key][blockIdx.x][3], (unsigned long long)probe_wait_full);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(&g_tc2_probe[key][blockIdx.x][0], (unsigned long long)(clock64() - probe_t_go));
+      atomicAdd(&g_tc2_probe[key][blockIdx.x][1], 1ull);
+      atomicAdd(&g_tc2_probe[key][blockIdx.x][2], (unsigned long long)(probe_t_go - probe_t_entry));
+    }
+  }
+#endif
   ptx::tc_fence_before();
-  ptx::cluster_sync_all();     // the leader's MMAs read the peer's shared memory: nobody leaves early
+  ptx::cluster_sync_relaxed();   // the leader's MMAs read the peer's shared memory and TMEM is freed for the pair: nobody leaves early
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_2sm(tmem_base, 512);
@@ -601,7 +651,7 @@ struct Tc2Schedule {           // one window tiling of a layer-direction + its i
   TcItem2* items = nullptr;
   TcRec* stream_p[2] = {nullptr, nullptr};   // producer records per cluster rank; per CTA pair: its items' steps, concatenated
   TcRec* stream_m = nullptr;       // MMA records, same indexing
-  uint32_t* stream_off = nullptr;  // [n_pairs + 1] record offsets into the streams
+  Tc2Heads heads{};                // per pair: record offsets into the streams, first item (kernel parameter)
   int* eitems = nullptr;           // [n_slots][n_pairs] (window << 16 | row pair) for the epilogue warps, or -1
   int n_slots = 0, n_pairs = 0;
   int n_windows = 0;
@@ -842,6 +892,44 @@ static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, 
             load[best] += icost[(size_t)(idx / n_mpairs)];
             lists[best].push_back((int)idx);
           }
+          // Refinement: while the busiest pair can hand an item to - or swap one with - another pair so that both end
+          // up below its load, do the best such move (LPT alone leaves e.g. 35 on a mean of 30.4 for Generator.2 bwd's
+          // 160 items of cost 4..25).
+          auto cost_of = [&](int idx) { return icost[(size_t)(idx / n_mpairs)]; };
+          for (int iter = 0; iter < 4096; ++iter) {
+            const size_t P = (size_t)(std::max_element(load.begin(), load.end()) - load.begin());
+            double best_peak = load[P];
+            size_t bq = P; int bi = -1, bj = -1;
+            for (size_t Q = 0; Q < (size_t)n_pairs; ++Q) {
+              if (Q == P) continue;
+              for (size_t i = 0; i < lists[P].size(); ++i) {
+                const double ci = cost_of(lists[P][i]);
+                double peak = std::max(load[P] - ci, load[Q] + ci);           // move i: P -> Q
+                if (peak < best_peak - 1e-9) { best_peak = peak; bq = Q; bi = (int)i; bj = -1; }
+                for (size_t j = 0; j < lists[Q].size(); ++j) {                 // swap i <-> j
+                  const double cj = cost_of(lists[Q][j]);
+                  if (cj >= ci) continue;
+                  peak = std::max(load[P] - ci + cj, load[Q] + ci - cj);
+                  if (peak < best_peak - 1e-9) { best_peak = peak; bq = Q; bi = (int)i; bj = (int)j; }
+                }
+              }
+            }
+            if (bi < 0) break;
+            const int it_i = lists[P][(size_t)bi];
+            const double ci = cost_of(it_i);
+            if (bj < 0) {
+              lists[P].erase(lists[P].begin() + bi);
+              lists[bq].push_back(it_i);
+              load[P] -= ci; load[bq] += ci;
+            } else {
+              const int it_j = lists[bq][(size_t)bj];
+              const double cj = cost_of(it_j);
+              lists[P][(size_t)bi] = it_j; lists[bq][(size_t)bj] = it_i;
+              load[P] += cj - ci; load[bq] += ci - cj;
+            }
+          }
+          for (auto& l : lists)      // biggest first: a pair's last item is its smallest (shortest un-overlapped epilogue)
+            std::stable_sort(l.begin(), l.end(), [&](int a, int b) { return cost_of(a) > cost_of(b); });
           const double makespan = *std::max_element(load.begin(), load.end());
           if (makespan < best_cost) {
             best_cost = makespan;
@@ -1055,7 +1143,9 @@ static int tc2_get_schedule(TcState& st, const TcWeights& w1, const TcWeights2& 
   for (int r = 0; r < 2; ++r)
     if ((rc = tc_upload(allocs, plan.stream_p[r].data(), plan.stream_p[r].size() * sizeof(TcRec), (void**)&sc.stream_p[r], s))) return rc;
   if ((rc = tc_upload(allocs, plan.stream_m.data(), plan.stream_m.size() * sizeof(TcRec), (void**)&sc.stream_m, s))) return rc;
-  if ((rc = tc_upload(allocs, plan.stream_off.data(), plan.stream_off.size() * sizeof(uint32_t), (void**)&sc.stream_off, s))) return rc;
+  if (n_pairs > TC2_MAX_PAIRS) { set_error("more CTA pairs than the kernel's parameter block holds"); return DGAN_ERR_UNSUPPORTED; }
+  for (int pr = 0; pr <= n_pairs; ++pr) sc.heads.off[pr] = plan.stream_off[(size_t)pr];
+  for (int pr = 0; pr < n_pairs; ++pr) sc.heads.first[pr] = plan.n_slots > 0 ? plan.eitems[(size_t)pr] : -1;
   if ((rc = tc_upload(allocs, plan.eitems.data(), plan.eitems.size() * sizeof(int), (void**)&sc.eitems, s))) return rc;
   w2.by_mpairs.push_back({n_mpairs, sc});
   *out = &w2.by_mpairs.back().second;
@@ -1107,10 +1197,10 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
   cudaError_t le = cudaSuccess;
 #define TC2_GO(NT, EP)                                                                                                 \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, TOUT>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, (int)sizeof(TOUT)>::SMEM_BYTES, s, \
-                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, fa)
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.heads, w2s.eitems, w2s.n_slots, out, n_pad, bias, w.bias_pstride, fa)
 #define TC2_GO_H(NT, EP)                                                                                               \
   le = launch_pdl(tc_bsgemm2_kernel<NT, EP, __half>, dim3(grid), dim3(TC2_THREADS), Tc2Cfg<NT, EP, 2>::SMEM_BYTES, s,   \
-                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.stream_off, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, fa)
+                  tm_a, w2m.tm_b, tm_out, w2s.items, w2s.stream_p[0], w2s.stream_p[1], w2s.stream_m, w2s.heads, w2s.eitems, w2s.n_slots, reinterpret_cast<__half*>(out), n_pad, bias, 0, fa)
 #define TC2_BY_N(EP)                    \
   do {                                  \
     if (w.N == 64) TC2_GO(64, EP);      \
