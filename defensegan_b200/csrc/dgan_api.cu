@@ -221,6 +221,7 @@ struct Workspace {
   std::vector<float*> pre;           // use_bn: pre-normalisation outputs (null otherwise)
   std::vector<float*> bn_part;       // use_bn: [4][kBnSplits][G] partial sums (mean, var, S1, S2)
   std::vector<__half*> act_h, dact_h;  // fp16 path
+  std::vector<float*> pre_h;           // fp16 path, use_bn: pre-normalisation outputs, fp32 (null otherwise)
   __half* z_h = nullptr;
   std::vector<unsigned long long*> maskbits;   // fp16 path: 1-bit ReLU masks per hidden layer output
   // fp16 CTA-pair path: TMA descriptors of every launch site, encoded once per workspace
@@ -266,6 +267,14 @@ static Workspace carve(const dgan_ctx* c, int n_rows, void* base) {
       w.act_h.push_back((__half*)take(elems * 2));
       w.dact_h.push_back((__half*)take(elems * 2));
       w.maskbits.push_back((unsigned long long*)take(elems / 8));
+      if (l.bn_scale != nullptr) {
+        const size_t G = l.bn_per_pixel ? (size_t)l.P_out * l.C_out : (size_t)l.C_out;
+        w.pre_h.push_back((float*)take(elems * 4));
+        w.bn_part.push_back((float*)take((size_t)4 * kBnSplits * G * 4));
+      } else {
+        w.pre_h.push_back(nullptr);
+        w.bn_part.push_back(nullptr);
+      }
     } else {
       w.act.push_back((float*)take(elems * 4));
       w.dact.push_back((float*)take(elems * 4));
@@ -381,7 +390,7 @@ static int build_maps(dgan_ctx* c, Workspace& w) {
     const GemmLayer& L = c->layers[l];
     const void* fin = (l == 0) ? (const void*)w.z_h : (const void*)w.act_h[l - 1];
     if ((rc = mk(&w.map_in[2 * l], fin, L.C_in, L.P_in))) return rc;
-    if ((rc = mk(&w.map_out[2 * l], w.act_h[l], L.C_out, L.P_out, TC2_STORE_ROWS))) return rc;
+    if ((rc = mk(&w.map_out[2 * l], w.act_h[l], L.C_out, L.P_out, TC2_STORE_ROWS))) return rc;   // unused by BN layers (float epilogue)
     if ((rc = mk(&w.map_in[2 * l + 1], w.dact_h[l], L.C_out, L.P_out))) return rc;
     if (l >= 1 && (rc = mk(&w.map_out[2 * l + 1], w.dact_h[l - 1], L.C_in, L.P_in, TC2_STORE_ROWS))) return rc;
   }
@@ -390,6 +399,45 @@ static int build_maps(dgan_ctx* c, Workspace& w) {
   if ((rc = mk(&w.map_in[2 * nl + 1], w.dblk, 64, c->tc_fin.n_blocks))) return rc;
   if ((rc = mk(&w.map_out[2 * nl + 1], w.dact_h[nl - 1], last.C_out, last.P_out, TC2_STORE_ROWS))) return rc;
   w.have_maps = true;
+  return 0;
+}
+
+// ---- batch-statistics BatchNorm of layer l on either path's activations (tflib/ops/batchnorm.py:80-93) ----
+// forward: act = relu(BN(pre)); backward: d(act) -> d(pre) through the ReLU and the batch statistics, in place in dact
+template <typename TP, typename T>
+static int bn_forward_t(dgan_ctx* c, const Workspace& w, int l, const TP* pre, T* act, cudaStream_t s) {
+  const GemmLayer& L = c->layers[l];
+  const int G = L.bn_per_pixel ? L.P_out * L.C_out : L.C_out;
+  float* part = w.bn_part[l];
+  float *mean_p = part, *var_p = part + (size_t)kBnSplits * G;
+  dim3 rgrid(G / 32, kBnSplits);
+  bn_reduce_kernel<0, TP, T><<<rgrid, 256, 0, s>>>(pre, nullptr, nullptr, nullptr, nullptr, L.P_out, w.n_rows, w.n_pad, L.C_out,
+                                               L.bn_per_pixel, mean_p, nullptr);
+  DGAN_LAUNCH_CHECK(c);
+  bn_reduce_kernel<1, TP, T><<<rgrid, 256, 0, s>>>(pre, nullptr, nullptr, mean_p, nullptr, L.P_out, w.n_rows, w.n_pad, L.C_out,
+                                               L.bn_per_pixel, var_p, nullptr);
+  DGAN_LAUNCH_CHECK(c);
+  const size_t total = (size_t)L.P_out * w.n_pad * L.C_out;
+  bn_apply_fwd_kernel<TP, T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pre, mean_p, var_p, L.bn_scale, L.bn_offset, L.P_out,
+                                                                          w.n_rows, w.n_pad, L.C_out, L.bn_per_pixel, act);
+  DGAN_LAUNCH_CHECK(c);
+  return 0;
+}
+template <typename TP, typename T>
+static int bn_backward_t(dgan_ctx* c, const Workspace& w, int l, const TP* pre, const T* act, T* dact, cudaStream_t s) {
+  const GemmLayer& L = c->layers[l];
+  const int G = L.bn_per_pixel ? L.P_out * L.C_out : L.C_out;
+  float* part = w.bn_part[l];
+  float *mean_p = part, *var_p = part + (size_t)kBnSplits * G, *s1_p = part + (size_t)2 * kBnSplits * G,
+        *s2_p = part + (size_t)3 * kBnSplits * G;
+  dim3 rgrid(G / 32, kBnSplits);
+  bn_reduce_kernel<2, TP, T><<<rgrid, 256, 0, s>>>(pre, act, dact, mean_p, var_p, L.P_out, w.n_rows, w.n_pad, L.C_out,
+                                               L.bn_per_pixel, s1_p, s2_p);
+  DGAN_LAUNCH_CHECK(c);
+  const size_t total = (size_t)L.P_out * w.n_pad * L.C_out;
+  bn_apply_bwd_kernel<TP, T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pre, act, mean_p, var_p, s1_p, s2_p, L.bn_scale, L.P_out,
+                                                                          w.n_rows, w.n_pad, L.C_out, L.bn_per_pixel, dact);
+  DGAN_LAUNCH_CHECK(c);
   return 0;
 }
 
@@ -403,10 +451,17 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
     for (int l = 0; l < nl; ++l) {
       const GemmLayer& L = c->layers[l];
       ProfScope ps(c, 2 * l, s);
-      if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, s,
-                           (L.relu && want_grad) ? w.maskbits[l] : nullptr, nullptr,
-                           w.have_maps ? &w.map_in[2 * l] : nullptr, w.have_maps ? &w.map_out[2 * l] : nullptr)))
+      if (L.bn_scale != nullptr) {               // pre = GEMM + bias (fp32 out);  act = relu(BN_batchstat(pre)) (fp16)
+        TcFinalArgs fa{};
+        if ((rc = tc2_launch_impl<float>(c->tc, &c->launches, L.tc_f, L.tc2_f, in, w.pre_h[l], w.n_pad, EPI_BIAS, L.bias, s, &fa,
+                                         w.have_maps ? &w.map_in[2 * l] : nullptr, nullptr)))
+          return rc;
+        if ((rc = bn_forward_t<float, __half>(c, w, l, w.pre_h[l], w.act_h[l], s))) return rc;
+      } else if ((rc = tcx_launch(c, L.tc_f, L.tc2_f, in, w.act_h[l], w.n_pad, L.relu ? EPI_BIAS_RELU : EPI_BIAS, L.bias, s,
+                                  (L.relu && want_grad) ? w.maskbits[l] : nullptr, nullptr,
+                                  w.have_maps ? &w.map_in[2 * l] : nullptr, w.have_maps ? &w.map_out[2 * l] : nullptr))) {
         return rc;
+      }
       in = w.act_h[l];
     }
     ProfScope ps(c, 2 * nl, s);
@@ -426,20 +481,7 @@ static int run_forward(dgan_ctx* c, const Workspace& w, const float* x, int R, i
       if ((rc = launch_bsgemm_f32(c, EPI_BIAS, in, L.C_in, w.n_pad, L.wf, L.wf_tile_stride, L.wf_ld, L.fwd, w.pre[l], L.C_out,
                                   L.bias, L.bias_pstride, nullptr, s)))
         return rc;
-      const int G = L.bn_per_pixel ? L.P_out * L.C_out : L.C_out;
-      float* part = w.bn_part[l];
-      float *mean_p = part, *var_p = part + (size_t)kBnSplits * G;
-      dim3 rgrid(G / 32, kBnSplits);
-      bn_reduce_kernel<0><<<rgrid, 256, 0, s>>>(w.pre[l], nullptr, nullptr, nullptr, nullptr, L.P_out, w.n_rows, w.n_pad, L.C_out,
-                                                L.bn_per_pixel, mean_p, nullptr);
-      DGAN_LAUNCH_CHECK(c);
-      bn_reduce_kernel<1><<<rgrid, 256, 0, s>>>(w.pre[l], nullptr, nullptr, mean_p, nullptr, L.P_out, w.n_rows, w.n_pad, L.C_out,
-                                                L.bn_per_pixel, var_p, nullptr);
-      DGAN_LAUNCH_CHECK(c);
-      const size_t total = (size_t)L.P_out * w.n_pad * L.C_out;
-      bn_apply_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.pre[l], mean_p, var_p, L.bn_scale, L.bn_offset, L.P_out,
-                                                                           w.n_rows, w.n_pad, L.C_out, L.bn_per_pixel, w.act[l]);
-      DGAN_LAUNCH_CHECK(c);
+      if ((rc = bn_forward_t<float, float>(c, w, l, w.pre[l], w.act[l], s))) return rc;
     } else if ((rc = launch_bsgemm_f32(c, L.relu ? EPI_BIAS_RELU : EPI_BIAS, in, L.C_in, w.n_pad, L.wf, L.wf_tile_stride,
                                        L.wf_ld, L.fwd, w.act[l], L.C_out, L.bias, L.bias_pstride, nullptr, s))) {
       return rc;
@@ -460,21 +502,26 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
   const int nl = (int)c->layers.size();
   if (c->desc.precision == DGAN_PREC_FP16) {
     const GemmLayer& last = c->layers[nl - 1];
+    // with BatchNorm after layer j the GEMM writes d(act_j) unmasked and the BN backward turns it into d(pre_j) in place
+    auto bn_backward_h = [&](int j) -> int { return bn_backward_t<float, __half>(c, w, j, w.pre_h[j], w.act_h[j], w.dact_h[j], s); };
     {
       ProfScope ps(c, 2 * nl + 1, s);
-      if ((rc = tcx_launch(c, c->tc_fin.b, c->tc2_fin_b, w.dblk, w.dact_h[nl - 1], w.n_pad, last.relu ? EPI_MASK : EPI_NONE,
-                           nullptr, s, nullptr, last.relu ? w.maskbits[nl - 1] : nullptr,
+      const bool bn = last.bn_scale != nullptr, mask = last.relu && !bn;
+      if ((rc = tcx_launch(c, c->tc_fin.b, c->tc2_fin_b, w.dblk, w.dact_h[nl - 1], w.n_pad, mask ? EPI_MASK : EPI_NONE,
+                           nullptr, s, nullptr, mask ? w.maskbits[nl - 1] : nullptr,
                            w.have_maps ? &w.map_in[2 * nl + 1] : nullptr, w.have_maps ? &w.map_out[2 * nl + 1] : nullptr)))
         return rc;
+      if (bn && (rc = bn_backward_h(nl - 1))) return rc;
     }
     for (int l = nl - 1; l >= 1; --l) {
       const GemmLayer& L = c->layers[l];
-      const bool mask = c->layers[l - 1].relu;
+      const bool bn = c->layers[l - 1].bn_scale != nullptr, mask = c->layers[l - 1].relu && !bn;
       ProfScope ps(c, 2 * l + 1, s);
       if ((rc = tcx_launch(c, L.tc_b, L.tc2_b, w.dact_h[l], w.dact_h[l - 1], w.n_pad, mask ? EPI_MASK : EPI_NONE, nullptr,
                            s, nullptr, mask ? w.maskbits[l - 1] : nullptr,
                            w.have_maps ? &w.map_in[2 * l + 1] : nullptr, w.have_maps ? &w.map_out[2 * l + 1] : nullptr)))
         return rc;
+      if (bn && (rc = bn_backward_h(l - 1))) return rc;
     }
     const GemmLayer& L0 = c->layers[0];
     ProfScope ps(c, 1, s);
@@ -486,24 +533,7 @@ static int run_backward(dgan_ctx* c, const Workspace& w, cudaStream_t s, Momentu
     return tc2_launch_impl<float>(c->tc, &c->launches, L0.tc_b, L0.tc2_b, w.dact_h[0], w.g, w.n_pad, EPI_NONE, nullptr, s,
                                   &fa, w.have_maps ? &w.map_in[1] : nullptr, nullptr);
   }
-  // d(act) -> d(pre) through ReLU + batch-statistics BN of layer l (in place in w.dact[l])
-  auto bn_backward = [&](int l) -> int {
-    const GemmLayer& L = c->layers[l];
-    const int G = L.bn_per_pixel ? L.P_out * L.C_out : L.C_out;
-    float* part = w.bn_part[l];
-    float *mean_p = part, *var_p = part + (size_t)kBnSplits * G, *s1_p = part + (size_t)2 * kBnSplits * G,
-          *s2_p = part + (size_t)3 * kBnSplits * G;
-    dim3 rgrid(G / 32, kBnSplits);
-    bn_reduce_kernel<2><<<rgrid, 256, 0, s>>>(w.pre[l], w.act[l], w.dact[l], mean_p, var_p, L.P_out, w.n_rows, w.n_pad, L.C_out,
-                                              L.bn_per_pixel, s1_p, s2_p);
-    DGAN_LAUNCH_CHECK(c);
-    const size_t total = (size_t)L.P_out * w.n_pad * L.C_out;
-    bn_apply_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.pre[l], w.act[l], mean_p, var_p, s1_p, s2_p, L.bn_scale,
-                                                                         L.P_out, w.n_rows, w.n_pad, L.C_out, L.bn_per_pixel,
-                                                                         w.dact[l]);
-    DGAN_LAUNCH_CHECK(c);
-    return 0;
-  };
+  auto bn_backward = [&](int l) -> int { return bn_backward_t<float, float>(c, w, l, w.pre[l], w.act[l], w.dact[l], s); };
   const GemmLayer& last = c->layers[nl - 1];
   {
     ProfScope ps(c, 2 * nl + 1, s);
@@ -602,14 +632,16 @@ std::vector<PlanDir> plan_dirs(const dgan_desc* d) {
   struct DSpec { int c_in, c_out, h_in, h_used, in_raster; bool relu; };
   std::vector<DSpec> specs;
   if (celeba) specs = {{4 * nd, 2 * nd, 4, 8, 4, true}, {2 * nd, nd, 8, 16, 8, true}, {nd, nd, 16, 32, 16, false}};
+  else if (d->use_bn) specs = {{4 * nd, 2 * nd, 4, 8, 4, true}, {2 * nd, nd, 7, 14, 8, true}};   // BN2 sees the 8x8 raster (create_impl)
   else specs = {{4 * nd, 2 * nd, 4, 7, 4, true}, {2 * nd, nd, 7, 14, 7, true}};
   int li = 2;
   for (const DSpec& sp : specs) {
     const std::string nm = "Generator." + std::to_string(li == 4 ? 5 : li);
-    dirs.push_back({nm + ".fwd", sp.c_out, sp.c_in, deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.h_used, sp.h_used, 0,
-                    sp.relu ? EPI_BIAS_RELU : EPI_BIAS, 2});
-    dirs.push_back({nm + ".bwd", sp.c_in, sp.c_out, deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), sp.in_raster, sp.in_raster, 0,
-                    EPI_MASK, 2});
+    const bool bn = d->use_bn && li <= 3;          // a BN layer's GEMMs neither apply the ReLU nor its mask
+    dirs.push_back({nm + ".fwd", sp.c_out, sp.c_in, tc_with_zero_tile(deconv_fwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), kTaps),
+                    sp.h_used, sp.h_used, 0, (sp.relu && !bn) ? EPI_BIAS_RELU : EPI_BIAS, 2});
+    dirs.push_back({nm + ".bwd", sp.c_in, sp.c_out, tc_with_zero_tile(deconv_bwd_pairs(sp.h_in, sp.h_in, sp.h_used, sp.h_used, sp.in_raster), kTaps),
+                    sp.in_raster, sp.in_raster, 0, d->use_bn ? EPI_NONE : EPI_MASK, 2});
     ++li;
   }
   const int fh = celeba ? 32 : 14, c_img = celeba ? 3 : 1;
@@ -755,11 +787,11 @@ static int create_impl(dgan_ctx* c, const dgan_desc* d, const float* const* weig
       if ((rc = tc2_optin_all())) return fail(rc);
       for (size_t l = 0; l < c->layers.size(); ++l) {
         GemmLayer& L = c->layers[l];
-        if ((rc = tc2_build_direction(c->tc, L.tc_f, &L.tc2_f, L.fwd_host, L.h_used, L.w_used, 0, &c->allocs, s))) return fail(rc);
+        if ((rc = tc2_build_direction(c->tc, L.tc_f, &L.tc2_f, tc_with_zero_tile(L.fwd_host, L.tc_f.n_tiles - 1), L.h_used, L.w_used, 0, &c->allocs, s))) return fail(rc);
         if (l == 0) {
           const PairTable split = linear_split_pairs(L.P_out);
           if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, split, 1, TC_LINEAR_SPLIT, 1, &c->allocs, s))) return fail(rc);
-        } else if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, L.bwd_host, L.h_in, L.w_in, 0, &c->allocs, s))) {
+        } else if ((rc = tc2_build_direction(c->tc, L.tc_b, &L.tc2_b, tc_with_zero_tile(L.bwd_host, L.tc_b.n_tiles - 1), L.h_in, L.w_in, 0, &c->allocs, s))) {
           return fail(rc);
         }
       }
@@ -797,10 +829,6 @@ int dgan_create(dgan_handle* out, const dgan_desc* d, const float* const* weight
   if (d->abi_version != DGAN_ABI_VERSION) { set_error("ABI version mismatch"); return DGAN_ERR_INVALID_ARG; }
   if (d->arch != DGAN_ARCH_MNIST && d->arch != DGAN_ARCH_CELEBA) { set_error("unknown arch"); return DGAN_ERR_INVALID_ARG; }
   if (d->precision != DGAN_PREC_FP32 && d->precision != DGAN_PREC_FP16) { set_error("unknown precision"); return DGAN_ERR_INVALID_ARG; }
-  if (d->use_bn && d->precision != DGAN_PREC_FP32) {
-    set_error("use_bn=True (batch-statistics BatchNorm, tflib/ops/batchnorm.py:80-93) is built for precision fp32 only");
-    return DGAN_ERR_UNSUPPORTED;
-  }
   if (d->net_dim <= 0 || d->net_dim % 64 != 0) { set_error("net_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
   if (d->latent_dim <= 0 || d->latent_dim % 64 != 0) { set_error("latent_dim must be a positive multiple of 64"); return DGAN_ERR_UNSUPPORTED; }
   if (n_weights != dgan_num_weights(d)) { set_error("wrong number of weight tensors"); return DGAN_ERR_INVALID_ARG; }
@@ -844,7 +872,8 @@ static int plan_all(dgan_ctx* c, int n_rows) {
   const int nl = (int)c->layers.size();
   for (int l = 0; l < nl; ++l) {
     const GemmLayer& L = c->layers[(size_t)l];
-    if ((rc = one(L.tc_f, L.tc2_f, L.relu ? EPI_BIAS_RELU : EPI_BIAS, 2))) return rc;
+    const bool bn = L.bn_scale != nullptr;        // BN layers: float epilogue (fp32 pre-activations), see run_forward
+    if ((rc = one(L.tc_f, L.tc2_f, (L.relu && !bn) ? EPI_BIAS_RELU : EPI_BIAS, bn ? 4 : 2))) return rc;
     if (l == 0) { if ((rc = one(L.tc_b, L.tc2_b, EPI_NONE, 4))) return rc; }
     else if ((rc = one(L.tc_b, L.tc2_b, c->layers[(size_t)l - 1].relu ? EPI_MASK : EPI_NONE, 2))) return rc;
   }
@@ -1089,11 +1118,11 @@ int dgan_debug_check_plans(const dgan_desc* d, int n_rows, int n_pairs, int muta
 
 
 #ifdef DGAN_PROBE
-// Developer build only: copy (and clear) the per-CTA cycle counters of the tensor-core kernels.  out: [48][160][4] u64.
+// Developer build only: copy (and clear) the per-CTA cycle counters of the tensor-core kernels.  out: [48][160][8] u64.
 int dgan_debug_probe_read(unsigned long long* out) {
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
   if (cudaMemcpyFromSymbol(out, dgan::g_tc2_probe, sizeof(dgan::g_tc2_probe)) != cudaSuccess) return -1;
-  static unsigned long long zeros[48 * 160 * 4];
+  static unsigned long long zeros[48 * 160 * 8];
   if (cudaMemcpyToSymbol(dgan::g_tc2_probe, zeros, sizeof(zeros)) != cudaSuccess) return -1;
   return 0;
 }

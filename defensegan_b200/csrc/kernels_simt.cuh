@@ -389,11 +389,21 @@ namespace dgan {
 
 constexpr int kBnSplits = 16;
 
+// The BN kernels run on the fp32 path's activations (float) and on the tensor-core path's: pre-activations TP = float
+// (written by the GEMM's float epilogue: normalising a value that was first rounded to fp16 would amplify the rounding
+// by |pre| / sigma), activations and gradients T = fp16 storage with fp32 arithmetic.
+__device__ __forceinline__ float bn_ld(const float* p, size_t i) { return p[i]; }
+__device__ __forceinline__ float bn_ld(const __half* p, size_t i) { return __half2float(p[i]); }
+__device__ __forceinline__ void bn_st(float* p, size_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void bn_st(__half* p, size_t i, float v) {   // saturating, as the tensor-core epilogues
+  p[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+
 // MODE 0: sum x            MODE 1: sum (x - mean)^2
 // MODE 2: S1 = sum dy, S2 = sum dy * xhat with dy = dact * (act > 0), xhat = (pre - mean) * inv
-template <int MODE>
+template <int MODE, typename TP, typename T>
 __global__ void __launch_bounds__(256)
-bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ act, const float* __restrict__ dact,
+bn_reduce_kernel(const TP* __restrict__ x, const T* __restrict__ act, const T* __restrict__ dact,
                  const float* __restrict__ mean_part /*[splits][G]*/, const float* __restrict__ var_part, int P, int n_rows,
                  int n_pad, int C, int per_pixel, float* __restrict__ out0 /*[splits][G]*/, float* __restrict__ out1) {
   __shared__ float red0[8][33], red1[8][33];
@@ -420,12 +430,12 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ act, con
     const int p = per_pixel ? p_fixed : (int)(s / n_rows);
     const int n = per_pixel ? (int)s : (int)(s % n_rows);
     const size_t idx = ((size_t)p * n_pad + n) * C + c;
-    if (MODE == 0) a0 += x[idx];
-    if (MODE == 1) { const float d = x[idx] - mean; a0 = fmaf(d, d, a0); }
+    if (MODE == 0) a0 += bn_ld(x, idx);
+    if (MODE == 1) { const float d = bn_ld(x, idx) - mean; a0 = fmaf(d, d, a0); }
     if (MODE == 2) {
-      const float dy = act[idx] > 0.f ? dact[idx] : 0.f;
+      const float dy = bn_ld(act, idx) > 0.f ? bn_ld(dact, idx) : 0.f;
       a0 += dy;
-      a1 = fmaf(dy, (x[idx] - mean) * inv, a1);
+      a1 = fmaf(dy, (bn_ld(x, idx) - mean) * inv, a1);
     }
   }
   red0[ty][tx] = a0; red1[ty][tx] = a1;
@@ -440,38 +450,40 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ act, con
 
 // forward: act = relu((pre - mean) * inv * scale + offset), evaluated the way TF's batch_normalization does:
 // x * (inv*scale) + (offset - mean*inv*scale)
-__global__ void bn_apply_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ mean_part,
+template <typename TP, typename T>
+__global__ void bn_apply_fwd_kernel(const TP* __restrict__ pre, const float* __restrict__ mean_part,
                                     const float* __restrict__ var_part, const float* __restrict__ scale,
                                     const float* __restrict__ offset, int P, int n_rows, int n_pad, int C, int per_pixel,
-                                    float* __restrict__ act) {
+                                    T* __restrict__ act) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * n_pad * C;
   if (i >= total) return;
   const int c = (int)(i % C);
   const int n = (int)((i / C) % n_pad);
   const int p = (int)(i / ((size_t)C * n_pad));
-  if (n >= n_rows) { act[i] = 0.f; return; }
+  if (n >= n_rows) { bn_st(act, i, 0.f); return; }
   const int G = per_pixel ? P * C : C, g = per_pixel ? p * C + c : c;
   const float M = per_pixel ? (float)n_rows : (float)P * (float)n_rows;
   float sm = 0.f, sv = 0.f;
   for (int k = 0; k < kBnSplits; ++k) { sm += mean_part[(size_t)k * G + g]; sv += var_part[(size_t)k * G + g]; }
   const float mean = sm / M, inv = rsqrtf(sv / M + 1e-5f) * scale[g];
-  act[i] = fmaxf(fmaf(pre[i], inv, offset[g] - mean * inv), 0.f);
+  bn_st(act, i, fmaxf(fmaf(bn_ld(pre, i), inv, offset[g] - mean * inv), 0.f));
 }
 
 // backward through ReLU + BN:  dpre = scale*inv * (dy - S1/M - xhat * S2/M),  dy = dact * (act > 0)
-__global__ void bn_apply_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ act,
+template <typename TP, typename T>
+__global__ void bn_apply_bwd_kernel(const TP* __restrict__ pre, const T* __restrict__ act,
                                     const float* __restrict__ mean_part, const float* __restrict__ var_part,
                                     const float* __restrict__ s1_part, const float* __restrict__ s2_part,
                                     const float* __restrict__ scale, int P, int n_rows, int n_pad, int C, int per_pixel,
-                                    float* __restrict__ dact /*in: d(act), out: d(pre)*/) {
+                                    T* __restrict__ dact /*in: d(act), out: d(pre)*/) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * n_pad * C;
   if (i >= total) return;
   const int c = (int)(i % C);
   const int n = (int)((i / C) % n_pad);
   const int p = (int)(i / ((size_t)C * n_pad));
-  if (n >= n_rows) { dact[i] = 0.f; return; }
+  if (n >= n_rows) { bn_st(dact, i, 0.f); return; }
   const int G = per_pixel ? P * C : C, g = per_pixel ? p * C + c : c;
   const float M = per_pixel ? (float)n_rows : (float)P * (float)n_rows;
   float sm = 0.f, sv = 0.f, s1 = 0.f, s2 = 0.f;
@@ -480,9 +492,9 @@ __global__ void bn_apply_bwd_kernel(const float* __restrict__ pre, const float* 
     s1 += s1_part[(size_t)k * G + g]; s2 += s2_part[(size_t)k * G + g];
   }
   const float mean = sm / M, inv = rsqrtf(sv / M + 1e-5f);
-  const float xhat = (pre[i] - mean) * inv;
-  const float dy = act[i] > 0.f ? dact[i] : 0.f;
-  dact[i] = scale[g] * inv * (dy - s1 / M - xhat * (s2 / M));
+  const float xhat = (bn_ld(pre, i) - mean) * inv;
+  const float dy = bn_ld(act, i) > 0.f ? bn_ld(dact, i) : 0.f;
+  bn_st(dact, i, scale[g] * inv * (dy - s1 / M - xhat * (s2 / M)));
 }
 
 }  // namespace dgan

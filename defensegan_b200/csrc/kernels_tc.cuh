@@ -363,6 +363,19 @@ __global__ void tc_final_tiles_kernel(const float* __restrict__ F /*[25][C_out][
   }
 }
 
+// Pair table of the tensor-core path: an output pixel without contributions (use_bn on MNIST: Generator.3's backward
+// over the 8x8 raster of which 7x7 is used - the cropped outputs get no gradient) receives (pixel 0, zero tile).
+static PairTable tc_with_zero_tile(const PairTable& t, int zero_tile) {
+  PairTable r;
+  r.off.push_back(0);
+  for (size_t q = 0; q + 1 < t.off.size(); ++q) {
+    for (int e = t.off[q]; e < t.off[q + 1]; ++e) r.pairs.push_back(t.pairs[(size_t)e]);
+    if (t.off[q] == t.off[q + 1]) r.pairs.push_back(make_int2(0, zero_tile));
+    r.off.push_back((int)r.pairs.size());
+  }
+  return r;
+}
+
 // dz = sum over the Linear's 16 output pixels, as TC_LINEAR_SPLIT partial sums
 static PairTable linear_split_pairs(int n_pix) {
   PairTable split;
@@ -448,9 +461,14 @@ static int tc_build(TcState& st, std::vector<TcLayerSpec>& specs, int latent, st
     const bool linear = sp.linear_W != nullptr;
     const int n_tiles = linear ? sp.P_out : kTaps;
     const size_t elems = (size_t)n_tiles * sp.C_out * sp.C_in;
+    // one extra, all-zero tile per direction: tc_with_zero_tile() gives output pixels that receive nothing a single
+    // (pixel 0, zero tile) contribution, so their accumulators hold exact zeros and every item has a step
+    const size_t tile_elems = (size_t)sp.C_out * sp.C_in;
     __half *wf = nullptr, *wb = nullptr;
-    DGAN_CUDA_CHECK(cudaMalloc((void**)&wf, elems * 2)); allocs->push_back(wf);
-    DGAN_CUDA_CHECK(cudaMalloc((void**)&wb, elems * 2)); allocs->push_back(wb);
+    DGAN_CUDA_CHECK(cudaMalloc((void**)&wf, (elems + tile_elems) * 2)); allocs->push_back(wf);
+    DGAN_CUDA_CHECK(cudaMalloc((void**)&wb, (elems + tile_elems) * 2)); allocs->push_back(wb);
+    DGAN_CUDA_CHECK(cudaMemsetAsync(wf + elems, 0, tile_elems * 2, s));
+    DGAN_CUDA_CHECK(cudaMemsetAsync(wb + elems, 0, tile_elems * 2, s));
     const unsigned blocks = (unsigned)((elems + 255) / 256);
     if (linear) {
       // forward tile q: rows c (N = C_out), cols k (K = latent) = Wt[q*C + c][k]
@@ -466,8 +484,8 @@ static int tc_build(TcState& st, std::vector<TcLayerSpec>& specs, int latent, st
     sp.out_f->bias_pstride = sp.bias_pstride;
     // forward: N = C_out, K = C_in;  backward: N = C_in, K = C_out (the Linear's dz is summed over its 16 pixels as
     // TC_LINEAR_SPLIT partial outputs: more items, and the z update adds the partials in a fixed order)
-    if ((rc = tc_set_direction(sp.out_f, sp.C_out, sp.C_in, n_tiles, sp.P_in, sp.P_out))) return rc;
-    if ((rc = tc_set_direction(sp.out_b, sp.C_in, sp.C_out, n_tiles, sp.P_out, linear ? TC_LINEAR_SPLIT : sp.P_in))) return rc;
+    if ((rc = tc_set_direction(sp.out_f, sp.C_out, sp.C_in, n_tiles + 1, sp.P_in, sp.P_out))) return rc;
+    if ((rc = tc_set_direction(sp.out_b, sp.C_in, sp.C_out, n_tiles + 1, sp.P_out, linear ? TC_LINEAR_SPLIT : sp.P_in))) return rc;
   }
   (void)latent;
   return 0;

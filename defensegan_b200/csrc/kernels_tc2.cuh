@@ -208,7 +208,14 @@ __device__ __forceinline__ int tc2_item_at(const int* __restrict__ order, int k,
 #ifdef DGAN_PROBE
 // Developer build only (-DDGAN_PROBE): per kernel instantiation and CTA, summed over launches: cycles from the PDL wait to
 // the end of the CTA's work, launches, cycles from kernel entry to the PDL wait, cycles the MMA warp waited for operands.
-__device__ unsigned long long g_tc2_probe[48][160][4];
+// [4] cycles of the set-up (kernel entry to the PDL trigger), [5] / [6] %globaltimer (ns) at kernel entry / at the end of
+// the CTA's work in the LAST launch, [7] %globaltimer when the CTA's first operands had landed (leaders, last launch).
+__device__ unsigned long long g_tc2_probe[48][160][8];
+__device__ __forceinline__ unsigned long long probe_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __host__ __device__ constexpr int tc2_probe_key(int n_tile, int epi, int out_bytes) {
   return (n_tile == 256 ? 0 : n_tile == 128 ? 1 : n_tile == 64 ? 2 : n_tile == 48 ? 3 : 4) * 8 + (out_bytes == 4 ? 6 : (epi < 4 ? epi : epi - 4));
 }
@@ -226,6 +233,10 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   constexpr bool TMA_EPI = Cfg::TMA_EPI;
   constexpr int HALF_B = Cfg::HALF_B, ACC_STRIDE = Cfg::ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
+#ifdef DGAN_PROBE
+  const long long probe_t_start = clock64();
+  const unsigned long long probe_g_start = probe_gtime();
+#endif
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + Cfg::RING_BYTES;            // output staging tiles: EPI_TILES / 2 per epilogue half
   const uint32_t stg_base = epi_base + Cfg::EPI_BYTES;              // [producer ring][MMA ring] of TcRec
@@ -374,6 +385,7 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           ptx::mbar_wait(bar_full + 8 * slot, phase);
 #ifdef DGAN_PROBE
           probe_wait_full += clock64() - probe_w0;
+          if (it == 0 && lane == 0) g_tc2_probe[tc2_probe_key(N_TILE, EPI, (int)sizeof(TOUT))][blockIdx.x][7] = probe_gtime();
 #endif
           ptx::tc_fence_after();
           // descriptors differ only in the 14-bit start-address field: one 32-bit add each (smem < 256 KB, no carry)
@@ -633,6 +645,9 @@ tc_bsgemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       atomicAdd(&g_tc2_probe[key][blockIdx.x][0], (unsigned long long)(clock64() - probe_t_go));
       atomicAdd(&g_tc2_probe[key][blockIdx.x][1], 1ull);
       atomicAdd(&g_tc2_probe[key][blockIdx.x][2], (unsigned long long)(probe_t_go - probe_t_entry));
+      atomicAdd(&g_tc2_probe[key][blockIdx.x][4], (unsigned long long)(probe_t_entry - probe_t_start));
+      g_tc2_probe[key][blockIdx.x][5] = probe_g_start;
+      g_tc2_probe[key][blockIdx.x][6] = probe_gtime();
     }
   }
 #endif
@@ -1165,6 +1180,7 @@ static int tc2_optin_all() {
   TC2_OPTIN(64, EPI_MASK, __half); TC2_OPTIN(128, EPI_MASK, __half); TC2_OPTIN(256, EPI_MASK, __half);
   TC2_OPTIN(64, EPI_NONE, __half); TC2_OPTIN(128, EPI_NONE, __half); TC2_OPTIN(256, EPI_NONE, __half);
   TC2_OPTIN(64, EPI_NONE, float); TC2_OPTIN(128, EPI_NONE, float); TC2_OPTIN(256, EPI_NONE, float);
+  TC2_OPTIN(64, EPI_BIAS, float); TC2_OPTIN(128, EPI_BIAS, float); TC2_OPTIN(256, EPI_BIAS, float);   // use_bn: fp32 pre-activations
   TC2_OPTIN(16, EPI_FINAL_SIGMOID1, __half); TC2_OPTIN(48, EPI_FINAL_TANH3, __half);
 #undef TC2_OPTIN
   return 0;
@@ -1207,7 +1223,7 @@ static int tc2_launch_impl(TcState& st, int64_t* launches, const TcWeights& w, c
     else if (w.N == 128) TC2_GO(128, EP); \
     else TC2_GO(256, EP);               \
   } while (0)
-  if (sizeof(TOUT) == 4) { TC2_BY_N(EPI_NONE); }
+  if (sizeof(TOUT) == 4) { if (epi == EPI_BIAS) TC2_BY_N(EPI_BIAS); else TC2_BY_N(EPI_NONE); }
   else if (epi == EPI_FINAL_SIGMOID1) { TC2_GO_H(16, EPI_FINAL_SIGMOID1); }
   else if (epi == EPI_FINAL_TANH3) { TC2_GO_H(48, EPI_FINAL_TANH3); }
   else if (epi == EPI_BIAS_RELU) { TC2_BY_N(EPI_BIAS_RELU); }

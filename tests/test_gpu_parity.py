@@ -190,33 +190,38 @@ def test_error_paths_through_c_abi(gens):
     assert rc == -1
     assert lib.dgan_reconstruct(gen._handle, None, x.data_ptr(), None, rec.data_ptr(), None, None,
                                 ctypes.c_void_p(base), 1024, None) == -1
-    d = _native.dgan_desc(_native.ABI_VERSION, 0, 128, 64, 1, 1)     # use_bn with fp16 operands: explicit UNSUPPORTED, no fallback
-    h = ctypes.c_void_p(0)
-    arr = (ctypes.c_void_p * 14)(*([x.data_ptr()] * 14))
-    assert lib.dgan_create(ctypes.byref(h), ctypes.byref(d), arr, 14, None) == -3
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
 @pytest.mark.parametrize("case", ["mnist_bn", "celeba_bn"])
-def test_batchnorm_batch_statistics_path(golden_dir, case):
+def test_batchnorm_batch_statistics_path(golden_dir, case, precision):
     """use_bn=True (opt-in; tflib/ops/batchnorm.py:80-93 else-branch): batch statistics couple all rows
-    (SURVEY F2).  fp32 path vs the fp64 oracle: forward/loss/grad of one loop body and the short loop."""
+    (SURVEY F2).  Both paths vs the fp64 oracle: forward/loss/grad of one loop body and the short loop.  On the tensor-core
+    path the GEMMs write fp16 pre-activations, the statistics and the normalisation are fp32 arithmetic on them."""
     from defensegan_b200 import _native
     g = np.load(os.path.join(golden_dir, case + ".npz"))
     arch, B, R, L = str(g["arch"]), int(g["B"]), int(g["R"]), int(g["L"])
     w = O.init_generator_weights(arch, random_bias=True, use_bn=True)
     dev = torch.device("cuda", 0)
-    gen = _native.NativeGenerator(arch, [torch.as_tensor(v).to(dev) for v in w.values()], use_bn=True, precision="fp32",
+    gen = _native.NativeGenerator(arch, [torch.as_tensor(v).to(dev) for v in w.values()], use_bn=True, precision=precision,
                                   device=dev)
+    t = {"fp32": dict(y=5e-5, loss=1e-5, grad=1e-3, rec=1e-3, lmin=1e-4),
+         # fp16 operands: the batch statistics couple the rounding of every row into every row and L steps of lr 10 carry
+         # it along - the loss of the chosen restart stays within ~1e-4, single pixels of a CelebA image move by a few 1e-2
+         "fp16": dict(y=1e-2, loss=1e-3, grad=6e-2, rec=1e-1, lmin=1e-3)}[precision]
     x, z0 = torch.tensor(g["images"]).cuda(), torch.tensor(g["z0"]).cuda()
     y, loss, grad = gen.loss_grad(x, z0, R)
-    assert np.abs(y.cpu().numpy() - g["y0_64"]).max() <= 5e-5
-    assert np.abs(loss.cpu().numpy() - g["loss0_64"]).max() <= 1e-5
+    yerr, lerr = np.abs(y.cpu().numpy() - g["y0_64"]).max(), np.abs(loss.cpu().numpy() - g["loss0_64"]).max()
     gerr = np.abs(grad.cpu().numpy() - g["grad0_64"]).max() / np.abs(g["grad0_64"]).max()
-    assert gerr <= 1e-3, gerr
     rec, lmin, idx = gen.reconstruct(x, R, L, float(g["lr"]), z_init_val=z0, return_aux=True)
-    np.testing.assert_array_equal(idx.cpu().numpy(), g["idx64"])
-    assert np.abs(rec.cpu().numpy() - g["rec64"]).max() <= 1e-3
-    assert np.abs(lmin.cpu().numpy() - g["loss_min64"]).max() <= 1e-4
+    agree = idx.cpu().numpy() == g["idx64"]          # fp16 may pick another restart of (nearly) the same loss: compare
+    drec = np.abs(rec.cpu().numpy() - g["rec64"]).reshape(B, -1).max(axis=1)   # images where the restart is the oracle's
+    rerr, merr = float(drec[agree].max()) if agree.any() else 0.0, np.abs(lmin.cpu().numpy() - g["loss_min64"]).max()
+    print("%s %s BN: |dy| %.2e |dloss| %.2e grad rel %.2e |drec| %.2e (restart agreement %.2f) |dloss_min| %.2e"
+          % (case, precision, yerr, lerr, gerr, rerr, agree.mean(), merr))
+    assert yerr <= t["y"] and lerr <= t["loss"] and gerr <= t["grad"], (yerr, lerr, gerr)
+    assert agree.all() if precision == "fp32" else agree.mean() >= 0.5
+    assert rerr <= t["rec"] and merr <= t["lmin"], (rerr, merr)
     # rows are coupled: dropping one image changes the others' reconstructions (unlike the no-BN path)
     rec_sub = gen.reconstruct(x[:-1], R, L, float(g["lr"]), z_init_val=z0[:-R])
     assert not torch.equal(rec_sub, rec[:-1])

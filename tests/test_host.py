@@ -375,14 +375,14 @@ def test_load_generator_from_tf_checkpoint_dir(tmp_path):
 # ---------------------------------------------------------------------------------------------------
 # tensor-core schedule planner (host code of the CUDA library; needs no GPU)
 # ---------------------------------------------------------------------------------------------------
-def _check_plans(arch, n_rows, n_pairs=74, net_dim=64, mutate=0):
+def _check_plans(arch, n_rows, n_pairs=74, net_dim=64, mutate=0, use_bn=0):
     import ctypes
     from defensegan_b200 import _native
     lib = _native.load_library()
     lib.dgan_debug_check_plans.restype = ctypes.c_int
     lib.dgan_debug_check_plans.argtypes = [ctypes.POINTER(_native.dgan_desc), ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.dgan_last_error.restype = ctypes.c_char_p
-    desc = _native.dgan_desc(_native.ABI_VERSION, 0 if arch == "mnist" else 1, 128, net_dim, 0, 1)
+    desc = _native.dgan_desc(_native.ABI_VERSION, 0 if arch == "mnist" else 1, 128, net_dim, use_bn, 1)
     rc = lib.dgan_debug_check_plans(ctypes.byref(desc), n_rows, n_pairs, mutate)
     return rc, (lib.dgan_last_error() or b"").decode()
 
@@ -398,6 +398,16 @@ def test_schedule_plans_are_valid_for_many_batch_sizes(arch):
     for n_pairs in (1, 3, 37, 66):                               # fewer SMs available (smaller parts, MIG slices)
         rc, msg = _check_plans(arch, 2560 if arch == "mnist" else 640, n_pairs=n_pairs)
         assert rc == 0, "n_pairs=%d: %s" % (n_pairs, msg)
+
+
+@pytest.mark.parametrize("arch", ["mnist", "celeba"])
+def test_schedule_plans_with_batchnorm_geometry(arch):
+    """use_bn=True on the tensor-core path: MNIST's Generator.2 then lives on the 8x8 raster (BN2 sees the cropped outputs
+    too), so Generator.3's backward has output pixels that receive nothing - they must still be written (exact zeros
+    through the zero weight tile) and no window may come without a step (its epilogue would wait for ever)."""
+    for n_rows in (4, 256, 2560):
+        rc, msg = _check_plans(arch, n_rows, use_bn=1)
+        assert rc == 0, "n_rows=%d: %s" % (n_rows, msg)
 
 
 def test_schedule_validator_rejects_damaged_plans():

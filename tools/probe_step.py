@@ -24,17 +24,26 @@ lib = gan._native.lib if hasattr(gan, "_native") and gan._native is not None els
 gan.reconstruct(x, z_init_val=z0)
 torch.cuda.synchronize()
 lib = gan._native.lib
-buf = (ctypes.c_ulonglong * (48 * 160 * 4))()
+buf = (ctypes.c_ulonglong * (48 * 160 * 8))()
 lib.dgan_debug_probe_read.restype = ctypes.c_int
 lib.dgan_debug_probe_read.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
 assert lib.dgan_debug_probe_read(buf) == 0          # discard the first call (schedule upload, graph capture)
 gan.reconstruct(x, z_init_val=z0)
 torch.cuda.synchronize()
 assert lib.dgan_debug_probe_read(buf) == 0
-a = np.frombuffer(buf, dtype=np.uint64).reshape(48, 160, 4).astype(np.float64)
+a = np.frombuffer(buf, dtype=np.uint64).reshape(48, 160, 8).astype(np.float64)
+# algorithmic MACs per launch of the MNIST kernels (in-bounds pairs x C_in x C_out x rows), for the busy-time TFLOP/s column
+rows = B * 10
+kind_flops = {}
+if dataset != "celeba":
+    kind_flops = {(256, "bias+relu"): 524288.0 * rows, (128, "float-out"): 524288.0 * rows, (128, "bias+relu"): 7372800.0 * rows,
+                  (256, "mask"): 7372800.0 * rows, (64, "bias+relu"): 8388608.0 * rows, (128, "mask"): 8388608.0 * rows,
+                  (16, "final-sigmoid"): 287296.0 * rows, (64, "mask"): 287296.0 * rows}
 NT = [256, 128, 64, 48, 16]
 EP = ["bias+relu", "bias", "mask", "none", "final-sigmoid", "final-tanh", "float-out", "?"]
-print("kernel <N, epilogue> | launches | cycles from PDL wait to CTA end: mean / min / max over CTAs | (max-mean)/max | entry->wait mean | MMA operand wait mean (leaders)")
+raw = np.frombuffer(buf, dtype=np.uint64).reshape(48, 160, 8)
+print("kernel <N, epilogue> | launches | cycles from PDL wait to CTA end: mean / min / max over CTAs | (max-mean)/max | trigger->wait mean | MMA operand wait mean (leaders) | set-up cycles mean | last launch, ns from its first CTA entry: last entry / first operands (mean, leaders) / first CTA end / last CTA end")
+timeline = []
 for k in range(48):
     cnt = a[k, :, 1]
     act = cnt > 0
@@ -44,6 +53,26 @@ for k in range(48):
     pre = a[k, act, 2] / cnt[act]
     wf = a[k, act, 3] / cnt[act]
     lead = wf > 0
-    print("<%d, %s> | %d | %.0f / %.0f / %.0f | %.3f | %.0f | %.0f" % (NT[k // 8], EP[k % 8], int(cnt[act].max()), dur.mean(), dur.min(), dur.max(),
-                                                             (dur.max() - dur.mean()) / dur.max(), pre.mean(), wf[lead].mean() if lead.any() else 0))
-    np.save("gpurun_out/probe_%s_%d_%s.npy" % (dataset, NT[k // 8], EP[k % 8]), a[k])
+    setup = a[k, act, 4] / cnt[act]
+    g0 = raw[k, act, 5].astype(np.int64); g1 = raw[k, act, 6].astype(np.int64); gf = raw[k, act, 7].astype(np.int64)
+    t0 = g0.min()
+    print("<%d, %s> | %d | %.0f / %.0f / %.0f | %.3f | %.0f | %.0f | %.0f | %d / %.0f / %d / %d   [abs first entry %d, last end %d]" % (
+        NT[k // 8], EP[k % 8], int(cnt[act].max()), dur.mean(), dur.min(), dur.max(), (dur.max() - dur.mean()) / dur.max(), pre.mean(),
+        wf[lead].mean() if lead.any() else 0, setup.mean(), g0.max() - t0, (gf[gf > 0] - t0).mean() if (gf > 0).any() else -1, g1.min() - t0, g1.max() - t0, t0, g1.max()))
+    timeline.append((int(t0), "<%d, %s>" % (NT[k // 8], EP[k % 8]), int(g0.max()), float(gf[gf > 0].mean()) if (gf > 0).any() else float(g0.max()),
+                     int(g1.max()), 2.0 * kind_flops.get((NT[k // 8], EP[k % 8]), 0.0)))
+# the last launches of the kernels, in time order: how long each was busy and what the hand-over from its predecessor cost
+timeline.sort()
+print()
+print("last L-step, in time order | busy us (last CTA entry -> last CTA end) | hand-over us (predecessor's last CTA end -> first operands landed) | algorithmic TFLOP/s while busy")
+prev_end = None
+tot_busy = tot_gap = 0.0
+for t0, name, last_entry, first_full, last_end, flops in timeline:
+    busy = (last_end - last_entry) / 1e3
+    gap = (first_full - prev_end) / 1e3 if prev_end is not None and abs(first_full - prev_end) < 1e5 else float("nan")
+    print("%s | %.1f | %.1f | %s" % (name, busy, gap, ("%.0f" % (flops / busy / 1e6)) if flops else "-"))
+    tot_busy += busy
+    if gap == gap:
+        tot_gap += gap
+    prev_end = last_end
+print("sum | %.1f | %.1f |" % (tot_busy, tot_gap))
