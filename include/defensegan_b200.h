@@ -49,7 +49,7 @@ typedef struct dgan_desc {
   int32_t arch;        /* dgan_arch */
   int32_t latent_dim;  /* LATENT_DIM (experiments/cfgs/gans/default.yml:4) */
   int32_t net_dim;     /* NET_DIM    (default.yml:7) */
-  int32_t use_bn;      /* USE_BN     (default.yml:3); batch-statistics BN, tflib/ops/batchnorm.py:80-93 (both precisions; fp16 path: fp16 pre-activations, fp32 statistics) */
+  int32_t use_bn;      /* USE_BN     (default.yml:3); batch-statistics BN, tflib/ops/batchnorm.py:80-93 (both precisions; fp16 path: fp32 pre-activations and statistics, fp16 activations) */
   int32_t precision;   /* dgan_precision */
 } dgan_desc;
 
