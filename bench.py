@@ -389,6 +389,32 @@ def kernel_breakdown(wl, peaks, precision):
     return kernels, roofline
 
 
+def pipeline_timeline(wl, roofline):
+    """Where an L-step goes inside the real chain (graph replay, PDL): the probe build of the library (same sources,
+    -DDGAN_PROBE: per-CTA %globaltimer stamps) runs one short call of this workload in a process of its own and reports, per
+    kernel of the last L-step, how long it was busy and what the hand-over from its predecessor cost.  CUDA events around a
+    single launch (`kernels`, `roofline.achieved`) also time the launch, set-up and drain that PDL overlaps with the
+    neighbouring kernels; this pass does not.  Returns None when the probe library is not built."""
+    import subprocess
+    from defensegan_b200 import _native
+    if not os.path.exists(_native.PROBE_LIB_PATH) or wl.dataset == "celeba":
+        return None
+    env = dict(os.environ, DGAN_LIB=_native.PROBE_LIB_PATH)
+    try:
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_step.py"), wl.dataset, str(wl.B), "50", "--json"],
+                             env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=300)
+        tl = json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:      # a measurement aid must not take the bench line down
+        return {"error": repr(e)}
+    if roofline is not None:
+        for k in tl["kernels"]:
+            if k["kernel"] == roofline["kernel"] and k["tflops_while_busy"] and roofline.get("peak"):
+                roofline["in_pipeline"] = {"busy_us": k["busy_us"], "handover_us": k["handover_us"], "achieved": k["tflops_while_busy"],
+                                           "frac": k["tflops_while_busy"] / roofline["peak"],
+                                           "how": "probe build, %globaltimer: last CTA entry -> last CTA end of this kernel in the graph-replayed chain"}
+    return tl
+
+
 def main():
     with _OnlyJsonOnStdout() as out:
         _main(out)
@@ -457,8 +483,11 @@ def _main(out):
 
     peaks = load_peaks()
     kernels, roofline = (None, None)
+    timeline = None
     if rank == 0 and not args.no_profile:
         kernels, roofline = kernel_breakdown(wl, peaks, args.precision)
+        if world == 1 and args.precision == "fp16":
+            timeline = pipeline_timeline(wl, roofline)
 
     # ---- the other BASELINE configs, measured the same way at reduced step counts (rank 0 / N=1 only) ----
     extra, weak_base, small_batch = None, None, None
@@ -518,7 +547,7 @@ def _main(out):
             "algorithmic": {"gflop_per_image": gflop_per_image, "tflops_whole_step": step_tflops,
                             "frac_of_sustained_bf16_peak": step_tflops / (world * peaks["bf16_tflops_sustained"]),
                             "frac_of_burst_bf16_peak": step_tflops / (world * peaks["bf16_tflops"])},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "timeline": timeline,
             "kernel_timing": None if not kernels else {
                 "sum_of_kernel_us_per_call": round(sum(k["avg_us"] * k["launches"] for k in kernels), 1),
                 "live_us_per_call": round(1e3 * ms / args.steps, 1),

@@ -69,6 +69,23 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+PROBE_LIB_PATH = os.path.join(_PKG_DIR, "libdefensegan_b200_probe.so")
+
+
+def build_probe_library(force: bool = False) -> str:
+    """The same sources with -DDGAN_PROBE: per-CTA clock / %globaltimer counters in the tensor-core kernels and
+    dgan_debug_probe_read().  Measurement aid only (tools/probe_step.py, the `timeline` pass of bench.py run it in a
+    process of its own through DGAN_LIB); the product library carries none of it."""
+    srcs = [os.path.join(CSRC_DIR, f) for f in sorted(os.listdir(CSRC_DIR))]
+    if not force and os.path.exists(PROBE_LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(PROBE_LIB_PATH) for s in srcs):
+        return PROBE_LIB_PATH
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-DDGAN_PROBE", os.path.join(CSRC_DIR, "dgan_api.cu"), "-o", PROBE_LIB_PATH]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    return PROBE_LIB_PATH
+
+
 _lib = None
 
 
