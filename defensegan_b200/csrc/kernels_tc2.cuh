@@ -13,7 +13,9 @@
 // Roles per CTA: TMA producer warp / MMA issuer warp / 8 epilogue warps; only the even (leader) CTA
 // issues tcgen05.mma.cta_group::2, commits are multicast to both CTAs, TMA completions of both CTAs
 // land on the leader's "full" barrier (peer-bit mask), and the epilogue warps of both CTAs release
-// the accumulators on the leader's "acc_empty" barrier.
+// the accumulators on the leader's "acc_empty" barrier.  The epilogue warps are independent of each other: each
+// converts the 32 rows it can read from TMEM and stores them with its own TMA store; what a unit needs from global
+// memory (output pixel, bias row, mask word) is fetched ahead of time (profiles/r3_epilogue_stalls.md).
 #pragma once
 #include "kernels_tc.cuh"
 
