@@ -851,6 +851,12 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
   return tc_make_map(st, &w2->tm_b, w1.w, (uint64_t)K, (uint64_t)N, (uint64_t)w1.n_tiles, (uint32_t)(N / 2));
 }
 
+#ifndef DGAN_STEP_MAX_KB
+#define DGAN_STEP_MAX_KB 48
+#endif
+#ifndef DGAN_STEP_MAX_KB_N64
+#define DGAN_STEP_MAX_KB_N64 64
+#endif
 #ifndef DGAN_COST_EPI_KB
 #define DGAN_COST_EPI_KB 24.0
 #endif
@@ -880,7 +886,12 @@ static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, 
   const int max_a = TC2_MAX_A;
   // Step size: a step is consumed only once all of it has landed, so big steps cost pipeline depth (4 x 48 KB fit the
   // ring); measured on C2: 32 KB (= one A tile per step) 5359, 40 KB 5466, 48-56 KB 5660, 64 KB 5553, 96 KB 5385 images/s.
-  const int step_max = std::min((ring_bytes / 2) & ~1023, 48 * 1024);
+  // (second sweep, final round-2 epilogue: 40 KB 5679, 48 KB 6047 / 6004, 56 KB 6064, 64 KB 6041 - flat from 48 KB on, except that
+  //  the N = 64, K = 128 layer (Generator.3 forward: 4 KB weight half-tiles, 3 activation tiles + their taps per 64 KB step)
+  //  gains 2 - 3 us per launch with 64 KB steps while the N = 128 layers lose as much: configs[1] 5912 -> 5965 images/s on one
+  //  box; CelebA's layer of that shape is indifferent: 1556 vs 1546)
+  const int step_kb = (N == 64 && K == 128) ? DGAN_STEP_MAX_KB_N64 : DGAN_STEP_MAX_KB;
+  const int step_max = std::min((ring_bytes / 2) & ~1023, step_kb * 1024);
   double best_cost = 1e300;
   int best_shape[4] = {1, 1, 1, 1};
   std::vector<Tc2HostItem> best_items;
