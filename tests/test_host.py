@@ -410,6 +410,24 @@ def test_schedule_plans_with_batchnorm_geometry(arch):
         assert rc == 0, "n_rows=%d: %s" % (n_rows, msg)
 
 
+def test_plan_statistics_entry_point():
+    """tools/plan_stats.py's entry point: one line per layer-direction with the staged bytes and the balance of the
+    assignment; configs[1] stages < 1.9 GB per L-step and no big layer's busiest CTA pair exceeds the mean by 12 %."""
+    import ctypes
+    from defensegan_b200 import _native
+    lib = _native.load_library()
+    lib.dgan_debug_plan_stats.restype = ctypes.c_int
+    lib.dgan_debug_plan_stats.argtypes = [ctypes.POINTER(_native.dgan_desc), ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    desc = _native.dgan_desc(_native.ABI_VERSION, 0, 128, 64, 0, 1)
+    buf = ctypes.create_string_buffer(1 << 16)
+    assert lib.dgan_debug_plan_stats(ctypes.byref(desc), 2560, 74, buf, len(buf)) > 0
+    rows = [l.split(" | ") for l in buf.value.decode().strip().splitlines()[1:]]
+    by = {r[0]: r for r in rows}
+    assert float(by["total staged MB per L-step"][1]) < 1900.0
+    for name in ("Generator.2.fwd", "Generator.2.bwd", "Generator.3.fwd", "Generator.3.bwd"):
+        assert float(by[name][9]) < 1.12, (name, by[name])
+
+
 def test_schedule_validator_rejects_damaged_plans():
     """The validator is not vacuous: nine single faults injected into a valid plan (wrong first-MMA flag, accumulator,
     staged weight tile, input pixel, k-chunk, lost epilogue item, unsafe ring dependencies, region outside the ring,
