@@ -28,15 +28,16 @@ def model_loss(y, logits, mean=True):
 def fgm(model, x, y=None, eps=0.3, ord=np.inf, clip_min=None, clip_max=None, targeted=False):
     """x_adv = x + eps * normalised(grad_x loss(model(x), y))   (cleverhans/attacks_tf.py:23-99)."""
     x = x.detach().clone().requires_grad_(True)
-    logits = model(x)
-    if y is None:
-        # model predictions as ground truth to avoid label leaking (attacks_tf.py:52-56)
-        y = (logits == logits.max(dim=1, keepdim=True).values).to(logits.dtype).detach()
-    y = y / y.sum(dim=1, keepdim=True)
-    loss = model_loss(y, logits, mean=False)
-    if targeted:
-        loss = -loss
-    grad, = torch.autograd.grad(loss.sum(), x)
+    with torch.enable_grad():             # callers evaluate under no_grad (model_eval); the attack needs the graph
+        logits = model(x)
+        if y is None:
+            # model predictions as ground truth to avoid label leaking (attacks_tf.py:52-56)
+            y = (logits == logits.max(dim=1, keepdim=True).values).to(logits.dtype).detach()
+        y = y / y.sum(dim=1, keepdim=True)
+        loss = model_loss(y, logits, mean=False)
+        if targeted:
+            loss = -loss
+        grad, = torch.autograd.grad(loss.sum(), x)
     red = tuple(range(1, x.dim()))
     if ord == np.inf:
         normalized = torch.sign(grad)
