@@ -230,6 +230,21 @@ def test_cached_dataset_readers_and_result_files(tmp_path, monkeypatch):
     assert WB._results_dir_filename(gan, wf) == ("results/whitebox_adv_tr_mnist", "model=C_advTrEps=0.15attack=fgsm.txt")
 
 
+def test_command_line_flags_fold_into_cfg_and_flags():
+    """`--cfg` first, then every cfg key and every script flag as `--lower_case` options (reference utils/config.py,
+    blackbox.py:723-759, whitebox.py:344-392)."""
+    from defensegan_b200.utils.config import packaged_cfg_path
+    cfg, fl = BB._parse(["--cfg", packaged_cfg_path("mnist"), "--defense_type", "defense_gan", "--rec_rr", "5",
+                         "--bb_model", "A", "--override", "true"], "blackbox")
+    assert (cfg["REC_RR"], cfg["DATASET_NAME"], fl.defense_type, fl.bb_model, fl.override, fl.num_tests) == \
+        (5, "mnist", "defense_gan", "A", True, 2000)
+    gan = TemplateGAN()
+    E.set_test_time_rec_params(gan, fl, cfg)                      # --override applies the command-line values
+    assert gan.rec_rr == 5 and gan.rec_iters == cfg["REC_ITERS"]
+    cfg, fl = BB._parse(["--cfg", packaged_cfg_path("celeba"), "--alpha", "0.1", "--attack_type", "rand+fgsm"], "whitebox")
+    assert (fl.alpha, fl.attack_type, fl.num_tests, cfg["DATASET_NAME"]) == (0.1, "rand+fgsm", -1, "celeba")
+
+
 @pytest.mark.gpu
 def test_blackbox_and_whitebox_drive_the_cuda_projection():
     """The same drivers with the real projector: MNIST generator (random-init weights, fp16 tensor-core path), images on
