@@ -362,16 +362,40 @@ class DefenseGANBase(object):
         x = x.reshape([-1] + list(self.image_dim))
         return x
 
+    def _dataset_projector(self):
+        """(project, is_writer, agree) for reconstruct_dataset.  One process: `self.reconstruct`.  Under
+        torch.distributed with several ranks (the bulk offline job on the 8 GPUs of a box): every rank walks the same
+        batches, each batch is sharded over the ranks (`parallel.reconstruct_sharded`, one all-gather), rank 0 alone
+        writes the cache and its hit / miss decisions are broadcast so that no rank can skip a collective another
+        rank enters."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return self.reconstruct, True, (lambda flag: flag)
+        from ..parallel import reconstruct_sharded
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+        def project(x):
+            return reconstruct_sharded(self, x.to(dev))
+
+        def agree(flag):
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+            dist.broadcast(t, src=0)
+            return bool(t.item())
+
+        return project, dist.get_rank() == 0, agree
+
     def reconstruct_dataset(self, ckpt_path=None, max_num=-1, max_num_load=-1):
         """Projects the train/dev/test splits batch by batch (fresh z0 and zero momentum per batch, reference
         models/gan.py:541) behind the reference's two-level result cache (see `RecCache`).  Returns
         `{split: [all_recs, all_targets, orig_imgs]}` (numpy, images `[-1] + image_dim`), the reference's return value
-        (models/gan.py:451-587)."""
+        (models/gan.py:451-587).  Called on every rank of an initialised torch.distributed group it splits each batch
+        over the ranks (`_dataset_projector`); every rank returns the full result."""
         if not self.initialized:
             self.load_generator(ckpt_path=ckpt_path)
         limit = max(max_num, max_num_load)
         shape = [-1] + list(self.image_dim)
         results = {}
+        project, is_writer, agree = self._dataset_projector()
         for split in ('train', 'dev', 'test'):
             batches = getattr(self, split + '_gen_test', None)
             if batches is None:
@@ -379,23 +403,34 @@ class DefenseGANBase(object):
                                    "(dataset readers are outside this package)".format(split))
             cache = RecCache(self.rec_cache_dir(split, max_num), reuse=not self.test_again)
             whole_split = cache.load_split()
+            if not agree(whole_split is not None):          # rank 0's view of the cache decides for everybody
+                whole_split = None
+            elif whole_split is None:
+                raise RuntimeError("rank 0 read {} but this rank cannot (the cache must be on a file system all "
+                                   "ranks see)".format(cache.split_path))
             recs, targets, originals = [], [], []
             t_start = time.time()
+            first = 0                                   # position of the batch's first image in the split
             for b, (images, labels) in enumerate(batches()):
                 n = len(images)
-                if (limit > -1 and b * n > limit) or (self.debug and b > 2):
+                if (limit > -1 and first > limit) or (self.debug and b > 2):
                     break
                 x = self._transformed_batch(images)
                 if whole_split is None:
-                    r = cache.load_batch(b * n, labels)
-                    if r is None:
-                        r = self.reconstruct(x).detach().cpu().numpy()
-                        cache.store_batch(b * n, labels, r)
-                        if self.verbose:
-                            print('[rec] {} batch {:d}: projected in {:.2f} s'.format(split, b, time.time() - t_start))
+                    r = cache.load_batch(first, labels)
+                    if not agree(r is not None):
+                        r = project(x).detach().cpu().numpy()
+                        if is_writer:
+                            cache.store_batch(first, labels, r)
+                            if self.verbose:
+                                print('[rec] {} batch {:d}: projected in {:.2f} s'.format(split, b, time.time() - t_start))
+                    elif r is None:
+                        raise RuntimeError("rank 0 found batch {:d} of '{}' in {} but this rank cannot read it".format(
+                            b, split, cache.pickle_dir))
                     recs.append(r)
                 targets.append(np.asarray(labels))
                 originals.append(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x))
+                first += n
             empty = np.zeros([0] + list(self.image_dim), dtype=np.float32)
             if whole_split is not None:
                 all_recs = whole_split

@@ -245,6 +245,41 @@ def test_command_line_flags_fold_into_cfg_and_flags():
     assert (fl.alpha, fl.attack_type, fl.num_tests, cfg["DATASET_NAME"]) == (0.1, "rand+fgsm", -1, "celeba")
 
 
+def test_train_cli_fills_the_caches_the_attack_scripts_read(tmp_path, monkeypatch):
+    """`python -m defensegan_b200.train --save_ds --save_recs` (reference train.py:45-56) -> the files
+    `get_cached_gan_data` reads back (blackbox.py:272-367).  The projector is replaced (it needs a GPU)."""
+    from defensegan_b200 import train as T
+    from defensegan_b200.models.gan import DefenseGANBase
+    from defensegan_b200.utils.config import packaged_cfg_path
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(DefenseGANBase, "reconstruct", lambda self, x, **kw: x * 0.5)
+    monkeypatch.setattr(DefenseGANBase, "load_generator", lambda self, ckpt_path=None: True)
+    rs = np.random.RandomState(0)
+    arrays = {}
+    for sp, n in (("train", 9), ("dev", 4), ("test", 6)):
+        arrays[sp + "_x"] = rs.randint(0, 256, size=(n, 28, 28, 1)).astype("uint8")
+        arrays[sp + "_y"] = np.arange(n) % 3
+    np.savez("raw.npz", **arrays)
+    argv = ["--cfg", packaged_cfg_path("mnist"), "--dataset_npz", "raw.npz", "--save_ds", "--save_recs", "--rec_rr", "2",
+            "--rec_iters", "3", "--batch_size", "4", "--output_dir", str(tmp_path / "output")]
+    gan = T.main(*T._parse(argv))
+    assert (gan.rec_rr, gan.rec_iters, gan.batch_size) == (2, 3, 4)
+    rec_dir = gan.rec_cache_dir("train")
+    assert os.path.isfile(os.path.join(rec_dir, "feats.pkl")) and len(os.listdir(os.path.join(rec_dir, "pickles"))) == 9
+    orig = E.get_cached_gan_data(gan, True, orig_data_flag=True, flags=E.Flags("blackbox"))
+    np.testing.assert_allclose(orig.train_images, arrays["train_x"] / 255.0, rtol=1e-6)
+    np.testing.assert_allclose(orig.test_images, arrays["test_x"] / 255.0, rtol=1e-6)
+    assert orig.train_labels.shape == (9, 3) and orig.train_labels.argmax(1).tolist() == list(np.arange(9) % 3)
+    recs = E.get_cached_gan_data(gan, True, flags=E.Flags("blackbox", train_on_recs=True, defense_type="defense_gan"))
+    np.testing.assert_allclose(recs.train_images, arrays["train_x"] / 255.0 * 0.5, rtol=1e-6)
+    np.testing.assert_allclose(recs.test_images, arrays["test_x"] / 255.0 * 0.5, rtol=1e-6)
+    imgs, labels = E.get_pickle_split(os.path.dirname(rec_dir), "train", [28, 28, 1])
+    np.testing.assert_allclose(imgs, recs.train_images, rtol=1e-6)
+    assert labels.tolist() == list(np.arange(9) % 3)
+    with pytest.raises(SystemExit):
+        T.main(*T._parse(["--cfg", packaged_cfg_path("mnist"), "--is_train"]))
+
+
 @pytest.mark.gpu
 def test_blackbox_and_whitebox_drive_the_cuda_projection():
     """The same drivers with the real projector: MNIST generator (random-init weights, fp16 tensor-core path) in front

@@ -241,6 +241,8 @@ def test_reconstruct_dataset_cache_format(tmp_path, monkeypatch):
     np.testing.assert_allclose(recs, orig * 0.5, rtol=1e-6)
     with open(os.path.join(d, "pickles", "rec_0000003_l3.pkl"), "rb") as f:
         np.testing.assert_allclose(pickle.load(f), recs[3])
+    # a ragged last batch keeps its position in the split (5 images in batches of 2: the last one is image 4)
+    assert os.path.isfile(os.path.join(gan.rec_cache_dir("train"), "pickles", "rec_0000004_l4.pkl"))
     # second call: every batch comes from the per-image cache, no projection runs
     calls.clear()
     rets2 = gan.reconstruct_dataset()
@@ -256,6 +258,70 @@ def test_reconstruct_dataset_cache_format(tmp_path, monkeypatch):
     gan.reconstruct_dataset()
     assert calls == [2, 2, 1, 2, 1, 2, 2]
     assert gan.rec_cache_dir("dev", max_num=100).endswith(os.path.join("recs_rr2_lr0.50000_iters3_num100", "dev"))
+
+
+def _gloo_dataset_worker(rank, world, port, out_dir, ret):
+    """reconstruct_dataset on every rank of a gloo group: batches sharded over the ranks, rank 0 owns the cache."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from defensegan_b200.models.gan import MnistDefenseGAN, RecCache
+        gan = MnistDefenseGAN(test_mode=True, verbose=False, output_dir=out_dir)
+        gan.initialized = True
+        gan.rec_rr, gan.rec_lr, gan.rec_iters = 2, 0.5, 3
+        shards = []
+
+        def fake_reconstruct(x, z_init_val=None, out=None, z_row_offset=0, **kw):   # stand-in for the CUDA projector
+            shards.append((int(x.shape[0]), int(z_row_offset)))
+            out.copy_(x * 0.5)
+            return out
+
+        gan.reconstruct = fake_reconstruct
+        rs = np.random.RandomState(0)
+        data = {sp: (rs.randint(0, 256, size=(n, 28, 28, 1)).astype("uint8"), np.arange(n) % 10)
+                for sp, n in (("train", 7), ("dev", 3), ("test", 4))}
+
+        def gen(sp, bs=4):
+            def g():
+                x, y = data[sp]
+                for i in range(0, len(x), bs):
+                    yield x[i:i + bs], y[i:i + bs]
+            return g
+
+        stores = []
+        orig_store = RecCache.store_batch
+        RecCache.store_batch = lambda self, first, labels, recs: (stores.append(first), orig_store(self, first, labels, recs))
+        gan.set_dataset_generators(train=gen("train"), dev=gen("dev"), test=gen("test"))
+        rets = gan.reconstruct_dataset()
+        ok = all(np.allclose(rets[sp][0], data[sp][0] / 255.0 * 0.5) and rets[sp][0].shape[0] == len(data[sp][0])
+                 for sp in data)
+        # batches of 4, 3 | 3 | 4 images split over two ranks: rank 0 takes the larger half; z0 rows start at
+        # (first image of the shard) * rec_rr
+        want = {0: [(2, 0), (2, 0), (2, 0), (2, 0)], 1: [(2, 4), (1, 4), (1, 4), (2, 4)]}[rank]
+        ok = ok and shards == want and (len(stores) == 4) == (rank == 0)
+        dist.barrier()                                   # rank 0's files are on disk
+        shards.clear()
+        rets2 = gan.reconstruct_dataset()               # second pass: rank 0 reports hits, nobody projects
+        ok = ok and shards == [] and all(np.array_equal(rets2[sp][0], rets[sp][0]) for sp in data)
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reconstruct_dataset_shards_batches_over_ranks_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_dataset_worker, args=(r, 2, port, str(tmp_path), ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
 
 
 # ---------------------------------------------------------------------------------------------------
