@@ -217,8 +217,8 @@ def run_reference_arm(args, rank, world, out):
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(dataset, B, R, L, world), "dataset": dataset, "rec_rr": R, "rec_iters": L,
-                   "per_step_sample_images": sample},
+        "config": arm_config(dataset, B, R, L, world, args.precision),
+        "per_step_sample_images": sample,
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": port.cores_used, "cores_present": port.cores_present,
                          "kind": "port", "sample": port.describe(sample, R, L)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,6 +247,32 @@ def resolve_workload(args, world):
 def workload_name(dataset, B, R, L, world=1):
     return "%s %s generator projection, batch=%d/GPU x %d GPU, R=%d, L=%d" % (
         dataset, "64x64x3" if dataset == "celeba" else "28x28x1", B, world, R, L)
+
+
+def arm_config(dataset, B, R, L, world, precision):
+    """The `config` object of the JSON line.  Both arms (this repo's and `--impl reference`) print the SAME object for
+    the same command line - the contract runs the reference arm "on your arm's config" - so entries that only one arm
+    can realise say which arm they describe."""
+    b_global = B * world
+    if (R, L) != (10, 200):
+        base = "custom"
+    elif world == 1 and B == 256 and dataset == "mnist":
+        base = "configs[1]"
+    elif dataset == "mnist" and b_global == C5_GLOBAL_BATCH:
+        base = "configs[4]"
+    elif dataset == "mnist" and B == C5_PER_GPU:
+        base = "configs[4] per-GPU share x %d GPUs" % world
+    elif world == 1 and (dataset, B) in (("f-mnist", 256), ("celeba", 128)):
+        base = "configs[2]" if dataset == "f-mnist" else "configs[3]"
+    else:
+        base = "custom"
+    return {"workload": workload_name(dataset, B, R, L, world), "dataset": dataset, "global_batch": b_global,
+            "per_gpu_batch": B, "rec_rr": R, "rec_iters": L, "rec_lr": 10.0, "baseline_config": base,
+            "precision": "GPU arm: %s operands, f32 accumulate and state; CPU reference arm: f32" % precision,
+            "parallelism": "GPU arm: image-shard x%d + 1 all-gather (inside value and e2e); CPU reference arm: rank 0's "
+                           "host cores on a bounded sample of this workload (cpu_baseline.sample)" % world,
+            "l2": "GPU arm: 192 MiB memset between steps (inside the timed bracket); CPU reference arm: not applicable",
+            "e2e_bytes": "GPU arm, summed over ranks: each rank copies the full batch in and the full result out"}
 
 
 class _OnlyJsonOnStdout:
@@ -531,14 +557,7 @@ def _main(out):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(dataset, B, R, L, world), "dataset": dataset, "global_batch": wl.B_global,
-                       "per_gpu_batch": B, "rec_rr": R, "rec_iters": L, "rec_lr": 10.0, "precision": args.precision,
-                       "accumulate": "f32", "parallelism": "image-shard x%d + 1 all-gather (inside value and e2e)" % world,
-                       "baseline_config": "configs[1]" if (world == 1 and B == 256 and dataset == "mnist") else
-                                          ("configs[4]" if (dataset == "mnist" and wl.B_global == C5_GLOBAL_BATCH) else
-                                           ("configs[4] per-GPU share x %d GPUs" % world if dataset == "mnist" and B == C5_PER_GPU else "custom")),
-                       "l2": "192 MiB memset between steps (inside the timed bracket)",
-                       "e2e_bytes": "summed over ranks: each rank copies the full batch in and the full result out"},
+            "config": arm_config(dataset, B, R, L, world, args.precision),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io},
             "gpu_launches": int(launches_per_step) * args.steps * world,
             "gpu_launches_per_call": int(launches_per_step),
