@@ -29,7 +29,7 @@ from .utils import attacks
 from .utils.config import add_flags, load_config
 from .utils.experiment import (Flags, SplitData, add_script_flags, get_cached_gan_data, set_test_time_rec_params,
                                unique_result_path, write_results)
-from .utils.gan_defense import SharedReconstruction, model_eval_gan
+from .utils.gan_defense import PerBatchMemo, SharedReconstruction, model_eval_gan
 from .utils.network_builder import model_dict
 
 __all__ = ["prep_bbox", "train_sub", "jacobian_augmentation", "blackbox", "main"]
@@ -208,13 +208,7 @@ def blackbox(gan, rec_data_path=None, batch_size=128, learning_rate=0.001, nb_ep
     eval_params = {"batch_size": batch_size}
     if gan_defense:
         # one projection of the adversarial batch feeds both the classifier and the detection statistic (:565-578)
-        adv_of, rec = {}, SharedReconstruction(gan, reconstructor_id=4)
-
-        def adv_batch(x):
-            key = (id(x), getattr(x, "_version", None))
-            if adv_of.get("key") != key:
-                adv_of["key"], adv_of["val"] = key, craft(x)
-            return adv_of["val"]
+        adv_batch, rec = PerBatchMemo(craft), SharedReconstruction(gan, reconstructor_id=4)
 
         def predictions(x):
             with torch.no_grad():

@@ -35,6 +35,23 @@ class _ArgsWrapper(object):
         return None
 
 
+class PerBatchMemo(object):
+    """fn(x) evaluated once per batch OBJECT: a second call with the same tensor (same object, not modified in place
+    since) returns the remembered value.  The batch is kept referenced, so a later tensor cannot be mistaken for it by
+    re-using its id()."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self._x, self._version, self._val = None, None, None
+
+    def __call__(self, x):
+        version = getattr(x, "_version", None)
+        if self._x is not x or self._version != version:
+            self._val = self.fn(x)
+            self._x, self._version = x, version
+        return self._val
+
+
 class SharedReconstruction(object):
     """Memoises gan.reconstruct per input batch object so that several per-batch callables
     (predictions, diff_op) observe the *same* projection, like the shared `reconstructed`
@@ -42,14 +59,10 @@ class SharedReconstruction(object):
 
     def __init__(self, gan, **kwargs):
         self.gan, self.kwargs = gan, kwargs
-        self._key, self._val = None, None
+        self._memo = PerBatchMemo(lambda x: self.gan.reconstruct(x, **self.kwargs))
 
     def __call__(self, x):
-        key = (id(x), getattr(x, "_version", None))
-        if self._key != key:
-            self._val = self.gan.reconstruct(x, **self.kwargs)
-            self._key = key
-        return self._val
+        return self._memo(x)
 
 
 def _to_device_batch(arr, device):

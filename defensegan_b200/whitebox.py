@@ -35,7 +35,7 @@ from .models.gan import dataset_gan_dict
 from .utils import attacks
 from .utils.experiment import (Flags, SplitData, get_cached_gan_data, set_test_time_rec_params, unique_result_path,
                                write_results)
-from .utils.gan_defense import model_eval_gan
+from .utils.gan_defense import PerBatchMemo, model_eval_gan
 from .utils.network_builder import model_dict
 
 __all__ = ["whitebox", "main"]
@@ -130,13 +130,8 @@ def whitebox(gan, rec_data_path=None, batch_size=128, learning_rate=0.001, nb_ep
 
     if defense == "defense_gan":
         rec_layer = model._rec_layer
-        memo = {}
-
-        def adv_batch(x):                   # predictions and diff_op of one batch see the same adversarial examples
-            key = (id(x), getattr(x, "_version", None))
-            if memo.get("key") != key:
-                memo["key"], memo["val"] = key, _through_projection_attack(model, x, rec_layer.fprop, rec_grad, **fgsm_par)
-            return memo["val"]
+        # predictions and diff_op of one batch see the same adversarial examples
+        adv_batch = PerBatchMemo(lambda x: _through_projection_attack(model, x, rec_layer.fprop, rec_grad, **fgsm_par))
 
         def predictions(x):
             with torch.no_grad():
