@@ -863,6 +863,9 @@ static int tc2_build_direction(TcState& st, const TcWeights& w1, TcWeights2* w2,
 #ifndef DGAN_COST_FIXED_KB
 #define DGAN_COST_FIXED_KB 48.0
 #endif
+#ifndef TC2_REFINE_BUDGET
+#define TC2_REFINE_BUDGET (1LL << 26)    // candidate evaluations of the assignment refinement per window shape (tc2_plan)
+#endif
 
 // Pick (and build on first use) the window tiling for `n_mpairs` row pairs on `n_pairs` CTA pairs: every candidate
 // shape (wh x ww accumulators, strides 1 or 2) is scored by an LPT assignment of its items (window, row pair) to the
@@ -924,12 +927,18 @@ static int tc2_plan(int N, int K, const PairTable& tab, int h_grid, int w_grid, 
           // up below its load, do the best such move (LPT alone leaves e.g. 35 on a mean of 30.4 for Generator.2 bwd's
           // 160 items of cost 4..25).
           auto cost_of = [&](int idx) { return icost[(size_t)(idx / n_mpairs)]; };
-          for (int iter = 0; iter < 4096; ++iter) {
+          // One pass looks at |P| x (1 + |Q|) candidates for every other pair Q: quadratic in the items per pair.  With many
+          // items per pair (large batches: 160 row pairs x 1024 windows) LPT alone is already within one small item of
+          // the mean and the search would take minutes, so it runs on a budget of candidate evaluations that the
+          // benchmarked sizes (<= 20 row pairs) never reach.
+          long long work = 0;
+          for (int iter = 0; iter < 4096 && work < TC2_REFINE_BUDGET; ++iter) {
             const size_t P = (size_t)(std::max_element(load.begin(), load.end()) - load.begin());
             double best_peak = load[P];
             size_t bq = P; int bi = -1, bj = -1;
             for (size_t Q = 0; Q < (size_t)n_pairs; ++Q) {
               if (Q == P) continue;
+              work += (long long)lists[P].size() * (long long)(1 + lists[Q].size());
               for (size_t i = 0; i < lists[P].size(); ++i) {
                 const double ci = cost_of(lists[P][i]);
                 double peak = std::max(load[P] - ci, load[Q] + ci);           // move i: P -> Q

@@ -466,6 +466,20 @@ def test_schedule_plans_are_valid_for_many_batch_sizes(arch):
         assert rc == 0, "n_pairs=%d: %s" % (n_pairs, msg)
 
 
+def test_schedule_planning_stays_bounded_for_large_batches():
+    """configs[4] on ONE GPU (4096 images x 10 restarts = 160 row pairs) and a 1536-image CelebA batch: the assignment
+    refinement is quadratic in the items per CTA pair and runs on a budget of candidate evaluations (TC2_REFINE_BUDGET,
+    never reached by the benchmarked sizes), so planning - which dgan_workspace_bytes does on first sight of a batch
+    size - takes seconds, and the plans still pass the validator.  (Unbounded, the CelebA case took 40 s, larger ones
+    minutes.)"""
+    import time
+    for arch, n_rows in (("mnist", 40960), ("celeba", 15360)):
+        t0 = time.time()
+        rc, msg = _check_plans(arch, n_rows)
+        assert rc == 0, "%s n_rows=%d: %s" % (arch, n_rows, msg)
+        assert time.time() - t0 < 60.0, (arch, n_rows, time.time() - t0)
+
+
 @pytest.mark.parametrize("arch", ["mnist", "celeba"])
 def test_schedule_plans_with_batchnorm_geometry(arch):
     """use_bn=True on the tensor-core path: MNIST's Generator.2 then lives on the 8x8 raster (BN2 sees the cropped outputs
