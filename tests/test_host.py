@@ -32,6 +32,43 @@ def test_library_exports_every_header_symbol():
     assert lib.dgan_num_weights(ctypes.byref(d)) == 10
 
 
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_binding(tmp_path):
+    """The boundary is a C ABI: include/defensegan_b200.h must compile as C (gcc -std=c99 -pedantic, no C++ or CUDA types
+    in the signatures) and the structs the Python binding declares must have the compiler's size and field offsets."""
+    import ctypes
+    import shutil
+    import subprocess
+    from defensegan_b200 import _native
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    fields = {"dgan_desc": [f for f, _ in _native.dgan_desc._fields_], "dgan_rec_params": [f for f, _ in _native.dgan_rec_params._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "defensegan_b200.h"', 'int main(void) {']
+    for st, fs in fields.items():
+        lines.append('  printf("%s %%zu", sizeof(%s));' % (st, st))
+        for f in fs:
+            lines.append('  printf(" %%zu", offsetof(%s, %s));' % (st, f))
+        lines.append('  printf("\\n");')
+    lines += ['  printf("abi %d\\n", DGAN_ABI_VERSION);', '  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    res = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout.split("\n")
+    for line in out:
+        tok = line.split()
+        if not tok:
+            continue
+        if tok[0] == "abi":
+            assert int(tok[1]) == _native.ABI_VERSION
+            continue
+        cls = getattr(_native, tok[0])
+        assert int(tok[1]) == ctypes.sizeof(cls), tok[0]
+        assert [int(t) for t in tok[2:]] == [getattr(cls, f).offset for f in fields[tok[0]]], tok[0]
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
