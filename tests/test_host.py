@@ -49,11 +49,16 @@ def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_binding(tmp_path)
         for f in fs:
             lines.append('  printf(" %%zu", offsetof(%s, %s));' % (st, f))
         lines.append('  printf("\\n");')
-    lines += ['  printf("abi %d\\n", DGAN_ABI_VERSION);', '  return 0;', '}']
+    # a C caller linked against the library: version, weight count and an error reported through dgan_last_error()
+    lines += ['  dgan_desc d = {DGAN_ABI_VERSION, DGAN_ARCH_CELEBA, 128, 64, 0, 1};',
+              '  printf("abi %d %d %d\\n", DGAN_ABI_VERSION, dgan_abi_version(), dgan_num_weights(&d));',
+              '  printf("err %d %s\\n", dgan_create(NULL, &d, NULL, 0, NULL), dgan_last_error());', '  return 0;', '}']
     src = tmp_path / "abi.c"
     src.write_text("\n".join(lines))
     exe = tmp_path / "abi"
-    res = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+    libdir = os.path.dirname(_native.build_library())
+    res = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                          "-L", libdir, "-l:" + _native.LIB_NAME, "-Wl,-rpath," + libdir],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout.split("\n")
@@ -62,7 +67,10 @@ def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_binding(tmp_path)
         if not tok:
             continue
         if tok[0] == "abi":
-            assert int(tok[1]) == _native.ABI_VERSION
+            assert [int(t) for t in tok[1:]] == [_native.ABI_VERSION, _native.ABI_VERSION, 10]
+            continue
+        if tok[0] == "err":
+            assert int(tok[1]) < 0 and len(tok) > 2          # status code + message
             continue
         cls = getattr(_native, tok[0])
         assert int(tok[1]) == ctypes.sizeof(cls), tok[0]
