@@ -435,6 +435,37 @@ def test_tf_bundle_matches_independent_crc_and_proto_implementations():
                         "<u4": "DT_UINT32", "<u8": "DT_UINT64"}[dt.str]
 
 
+def test_tf_bundle_roundtrip_property(tmp_path):
+    """Random names (shared prefixes, so prefix compression and restart points are hit), dtypes, ranks 0-4 and block
+    sizes: write_bundle -> list_bundle / read_bundle returns the same arrays bit for bit, keys in sorted order."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from defensegan_b200 import tf_bundle as B
+    dtypes = ["<f4", "<f8", "<i4", "<i8", "|u1", "<f2", "|b1"]
+    names = st.text(alphabet="abG./_0123456789", min_size=1, max_size=24).map(lambda t: "Generator." + t)
+    tensor = st.tuples(st.sampled_from(dtypes), st.lists(st.integers(0, 5), min_size=0, max_size=4), st.integers(0, 2 ** 31 - 1))
+    counter = [0]
+
+    @settings(max_examples=30, deadline=None)
+    @given(st.dictionaries(names, tensor, min_size=1, max_size=12), st.sampled_from([64, 300, 4096, 262144]))
+    def run(spec, block_size):
+        counter[0] += 1
+        prefix = str(tmp_path / ("case%d" % counter[0]) / "GAN.model-7")
+        tensors = {}
+        for name, (dt, shape, seed) in spec.items():
+            rs = np.random.RandomState(seed)
+            tensors[name] = (rs.randint(0, 255, size=shape) if dt != "|b1" else rs.randint(0, 2, size=shape)).astype(np.dtype(dt))
+        B.write_bundle(prefix, tensors, block_size=block_size)
+        listed = B.list_bundle(prefix)
+        assert list(listed) == sorted(tensors)
+        got = B.read_bundle(prefix)
+        for name, want in tensors.items():
+            assert got[name].dtype == want.dtype and got[name].shape == want.shape and np.array_equal(got[name], want)
+            assert listed[name] == (want.dtype, want.shape)
+
+    run()
+
+
 def test_tf_bundle_detects_corruption(tmp_path):
     from defensegan_b200 import tf_bundle as B
     prefix = str(tmp_path / "GAN.model-1")
