@@ -542,6 +542,23 @@ def test_schedule_plans_are_valid_for_many_batch_sizes(arch):
         assert rc == 0, "n_pairs=%d: %s" % (n_pairs, msg)
 
 
+def test_schedule_plans_are_valid_for_random_sizes_and_sm_counts():
+    """Any (latent rows, CTA pairs, net_dim) a caller or a smaller part could present: ragged batches of model_eval_gan,
+    MIG slices, half-width generators."""
+    pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.sampled_from(["mnist", "celeba"]), st.integers(1, 3000), st.integers(1, 74), st.sampled_from([64, 64, 64, 32]),
+           st.sampled_from([0, 0, 1]))
+    def run(arch, n_rows, n_pairs, net_dim, use_bn):
+        rc, msg = _check_plans(arch, n_rows, n_pairs=n_pairs, net_dim=net_dim, use_bn=use_bn)
+        # a geometry the tensor-core path does not serve must be refused by name, never planned wrongly
+        assert rc == 0 or "unsupported" in msg.lower(), (arch, n_rows, n_pairs, net_dim, use_bn, msg)
+
+    run()
+
+
 def test_schedule_planning_stays_bounded_for_large_batches():
     """configs[4] on ONE GPU (4096 images x 10 restarts = 160 row pairs) and a 1536-image CelebA batch: the assignment
     refinement is quadratic in the items per CTA pair and runs on a budget of candidate evaluations (TC2_REFINE_BUDGET,
